@@ -1,0 +1,312 @@
+// capi.cu -- host side of the C ABI declared in include/amrvw_b200.h: context, workspace,
+// launches, H2D/D2H staging.  No CPU compute path exists here: every entry point launches the
+// sm_100a kernels of kernels.cuh / pipeline.cuh or fails.
+#include "../../include/amrvw_b200.h"
+#include "kernels.cuh"
+#include "pipeline.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace amrvw;
+
+struct DevBuf {
+    void* ptr = nullptr;
+    size_t cap = 0;
+};
+
+struct amrvw_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    amrvw_options opt;
+    std::string err;
+    // grow-only device buffers
+    DevBuf chains[5], diags[3], coeffs, coeffs2, offsets, roots, nroots, nunconv, stats, shifts, state;
+    int sm_count = 148;
+};
+
+static int fail(amrvw_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+#define CUDA_TRY(ctx, call)                                                                     \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess)                                                                 \
+            return fail(ctx, AMRVW_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+static int reserve(amrvw_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap && b.ptr) return 0;
+    if (b.ptr) CUDA_TRY(ctx, cudaFree(b.ptr));
+    b.ptr = nullptr; b.cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    CUDA_TRY(ctx, cudaMalloc(&b.ptr, want));
+    b.cap = want;
+    return 0;
+}
+
+extern "C" {
+
+int amrvw_version(void) { return 100; }
+
+void amrvw_default_options(amrvw_options* opt) {
+    if (!opt) return;
+    opt->schedule = AMRVW_SCHEDULE_AUTO;
+    opt->lanes_per_poly = 0;
+    opt->shift_reuse = 0;
+    opt->small_window = 0;
+    opt->seed = 0;
+}
+
+int amrvw_create(amrvw_ctx** out, int device, uint64_t seed) {
+    if (!out) return AMRVW_ERR_ARGUMENT;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return AMRVW_ERR_NO_DEVICE;  // no CPU fallback
+    amrvw_ctx* ctx = new amrvw_ctx();
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) { delete ctx; return AMRVW_ERR_CUDA; } }
+    if (device >= ndev) { delete ctx; return AMRVW_ERR_ARGUMENT; }
+    ctx->device = device;
+    amrvw_default_options(&ctx->opt);
+    ctx->opt.seed = seed;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        delete ctx;
+        return AMRVW_ERR_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    *out = ctx;
+    return AMRVW_OK;
+}
+
+int amrvw_destroy(amrvw_ctx* ctx) {
+    if (!ctx) return AMRVW_OK;
+    cudaSetDevice(ctx->device);
+    DevBuf* all[] = {&ctx->chains[0], &ctx->chains[1], &ctx->chains[2], &ctx->chains[3], &ctx->chains[4], &ctx->diags[0], &ctx->diags[1], &ctx->diags[2],
+                     &ctx->coeffs, &ctx->coeffs2, &ctx->offsets, &ctx->roots, &ctx->nroots, &ctx->nunconv, &ctx->stats, &ctx->shifts, &ctx->state};
+    for (DevBuf* b : all) if (b->ptr) cudaFree(b->ptr);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return AMRVW_OK;
+}
+
+const char* amrvw_last_error(const amrvw_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int amrvw_set_options(amrvw_ctx* ctx, const amrvw_options* opt) {
+    if (!ctx || !opt) return AMRVW_ERR_ARGUMENT;
+    if (opt->schedule < 0 || opt->schedule > 2) return fail(ctx, AMRVW_ERR_ARGUMENT, "schedule must be 0, 1 or 2");
+    const int L = opt->lanes_per_poly;
+    if (!(L == 0 || L == 4 || L == 8 || L == 16 || L == 32)) return fail(ctx, AMRVW_ERR_ARGUMENT, "lanes_per_poly must be 0, 4, 8, 16 or 32");
+    if (!(opt->shift_reuse == 0 || opt->shift_reuse == 1 || opt->shift_reuse == 2 || opt->shift_reuse == 4))
+        return fail(ctx, AMRVW_ERR_ARGUMENT, "shift_reuse must be 0, 1, 2 or 4");
+    if (opt->small_window < 0) return fail(ctx, AMRVW_ERR_ARGUMENT, "small_window must be >= 0");
+    ctx->opt = *opt;
+    return AMRVW_OK;
+}
+
+int amrvw_set_stream(amrvw_ctx* ctx, void* s) {
+    if (!ctx) return AMRVW_ERR_ARGUMENT;
+    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return AMRVW_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+enum Variant { V_RDS = 0, V_CSS = 1, V_PENCIL_R = 2, V_PENCIL_C = 3 };
+
+struct StatsAccum { long long turnovers, sweeps, exceptional, unconverged, fat_steps; };
+
+__global__ void reduce_stats_kernel(const PolyStats* st, long long n, StatsAccum* out) {
+    long long t = 0, s = 0, e = 0, u = 0, f = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        t += st[i].turnovers; s += st[i].sweeps; e += st[i].exceptional; u += st[i].unconverged; f += st[i].fat_steps;
+    }
+    atomicAdd((unsigned long long*)&out->turnovers, (unsigned long long)t);
+    atomicAdd((unsigned long long*)&out->sweeps, (unsigned long long)s);
+    atomicAdd((unsigned long long*)&out->exceptional, (unsigned long long)e);
+    atomicAdd((unsigned long long*)&out->unconverged, (unsigned long long)u);
+    atomicAdd((unsigned long long*)&out->fat_steps, (unsigned long long)f);
+}
+
+template <class S>
+static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, const int64_t* d_offsets, int64_t nbatch, int64_t total, int64_t max_len,
+                   double* d_roots, int32_t* d_nroots, int32_t* d_nunconv, amrvw_stats* stats) {
+    if (!ctx) return AMRVW_ERR_ARGUMENT;
+    if (nbatch < 0 || total < 0) return fail(ctx, AMRVW_ERR_ARGUMENT, "negative batch or total");
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    if (nbatch == 0) return AMRVW_OK;
+    if (!d_a || !d_offsets || !d_roots || !d_nroots || !d_nunconv) return fail(ctx, AMRVW_ERR_ARGUMENT, "null buffer");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const bool pencil = (var == V_PENCIL_R || var == V_PENCIL_C);
+    if (pencil && !d_w) return fail(ctx, AMRVW_ERR_ARGUMENT, "null ws buffer");
+    const int extra = pencil ? 2 : 1;
+    const size_t slots = (size_t)total + (size_t)extra * (size_t)nbatch + 4;
+    const int nchains = pencil ? 5 : 3;
+    for (int c = 0; c < nchains; ++c) { int rc = reserve(ctx, ctx->chains[c], slots * sizeof(Rot<S>)); if (rc) return rc; }
+    if (!is_real<S>::value) {
+        const int nd = pencil ? 3 : 2;
+        for (int c = 0; c < nd; ++c) { int rc = reserve(ctx, ctx->diags[c], slots * sizeof(S)); if (rc) return rc; }
+    }
+    { int rc = reserve(ctx, ctx->stats, (size_t)nbatch * sizeof(PolyStats) + sizeof(StatsAccum)); if (rc) return rc; }
+
+    Problem<S> pr;
+    pr.coeffs = d_a; pr.ws = d_w; pr.offsets = (const long long*)d_offsets; pr.nbatch = nbatch;
+    pr.roots = (cplx*)d_roots; pr.nroots = d_nroots; pr.nunconv = d_nunconv;
+    pr.stats = (PolyStats*)ctx->stats.ptr;
+    pr.Q = (Rot<S>*)ctx->chains[0].ptr; pr.B = (Rot<S>*)ctx->chains[1].ptr; pr.Ct = (Rot<S>*)ctx->chains[2].ptr;
+    pr.WB = (Rot<S>*)ctx->chains[3].ptr; pr.WCt = (Rot<S>*)ctx->chains[4].ptr;
+    pr.DQ = (S*)ctx->diags[0].ptr; pr.DR = (S*)ctx->diags[1].ptr; pr.WD = (S*)ctx->diags[2].ptr;
+    pr.extra = extra;
+    pr.seed = ctx->opt.seed;
+
+    cudaStream_t st = ctx->stream;
+    int launches = 0;
+    if (stats) CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, st));
+
+    bool done = false;
+    if constexpr (is_real<S>::value) {
+        if (var == V_RDS && ctx->opt.schedule != AMRVW_SCHEDULE_REFERENCE) {
+            int rc = launch_pipelined_rds(pr, ctx->opt, (int)max_len, ctx->sm_count, st, &launches);
+            if (rc != 0) return fail(ctx, AMRVW_ERR_CUDA, std::string("pipelined launch: ") + cudaGetErrorString((cudaError_t)rc));
+            done = true;
+        }
+    }
+    if (!done) {
+        const int threads = 64;   // one polynomial per thread; small blocks spread the batch over all SMs
+        const int blocks = (int)((nbatch + threads - 1) / threads);
+        if (pencil) roots_pencil_reference_kernel<S><<<blocks, threads, 0, st>>>(pr);
+        else roots_reference_kernel<S><<<blocks, threads, 0, st>>>(pr);
+        launches += 1;
+        CUDA_TRY(ctx, cudaGetLastError());
+    }
+    if (stats) {
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, st));
+        StatsAccum* acc = (StatsAccum*)((char*)ctx->stats.ptr + (size_t)nbatch * sizeof(PolyStats));
+        CUDA_TRY(ctx, cudaMemsetAsync(acc, 0, sizeof(StatsAccum), st));
+        reduce_stats_kernel<<<64, 256, 0, st>>>(pr.stats, nbatch, acc);
+        CUDA_TRY(ctx, cudaGetLastError());
+        StatsAccum h;
+        CUDA_TRY(ctx, cudaMemcpyAsync(&h, acc, sizeof(h), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        float ms = 0.f;
+        CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        stats->turnovers = h.turnovers; stats->sweeps = h.sweeps; stats->exceptional = h.exceptional;
+        stats->unconverged = h.unconverged; stats->fat_steps = h.fat_steps;
+        stats->launches = launches; stats->device_ms = ms;
+    }
+    return AMRVW_OK;
+}
+
+template <class S>
+static int run_host(amrvw_ctx* ctx, Variant var, const S* a, const S* w, const int64_t* offsets, int64_t nbatch,
+                    double* roots, int32_t* nroots, int32_t* nunconv, amrvw_stats* stats) {
+    if (!ctx) return AMRVW_ERR_ARGUMENT;
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    if (nbatch < 0) return fail(ctx, AMRVW_ERR_ARGUMENT, "negative batch");
+    if (nbatch == 0) return AMRVW_OK;
+    if (!offsets || !roots || !nroots || !nunconv) return fail(ctx, AMRVW_ERR_ARGUMENT, "null buffer");
+    const bool pencil = (var == V_PENCIL_R || var == V_PENCIL_C);
+    int64_t max_len = 0;
+    for (int64_t p = 0; p < nbatch; ++p) {
+        const int64_t len = offsets[p + 1] - offsets[p];
+        if (len < 0) return fail(ctx, AMRVW_ERR_ARGUMENT, "offsets must be non-decreasing");
+        if (len > max_len) max_len = len;
+    }
+    if (offsets[0] != 0) return fail(ctx, AMRVW_ERR_ARGUMENT, "offsets[0] must be 0");
+    const int64_t total = offsets[nbatch];
+    if (total > 0 && (!a || (pencil && !w))) return fail(ctx, AMRVW_ERR_ARGUMENT, "null coefficient buffer");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t root_slots = (size_t)total + 1;  // non-pencil uses total - nbatch of them
+    int rc;
+    if ((rc = reserve(ctx, ctx->coeffs, (size_t)total * sizeof(S) + 16))) return rc;
+    if (pencil && (rc = reserve(ctx, ctx->coeffs2, (size_t)total * sizeof(S) + 16))) return rc;
+    if ((rc = reserve(ctx, ctx->offsets, (size_t)(nbatch + 1) * sizeof(int64_t)))) return rc;
+    if ((rc = reserve(ctx, ctx->roots, root_slots * sizeof(cplx)))) return rc;
+    if ((rc = reserve(ctx, ctx->nroots, (size_t)nbatch * sizeof(int32_t)))) return rc;
+    if ((rc = reserve(ctx, ctx->nunconv, (size_t)nbatch * sizeof(int32_t)))) return rc;
+    cudaStream_t st = ctx->stream;
+    if (total > 0) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->coeffs.ptr, a, (size_t)total * sizeof(S), cudaMemcpyHostToDevice, st));
+    if (pencil && total > 0) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->coeffs2.ptr, w, (size_t)total * sizeof(S), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->offsets.ptr, offsets, (size_t)(nbatch + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    rc = run_dev<S>(ctx, var, (const S*)ctx->coeffs.ptr, pencil ? (const S*)ctx->coeffs2.ptr : nullptr, (const int64_t*)ctx->offsets.ptr, nbatch, total, max_len,
+                    (double*)ctx->roots.ptr, (int32_t*)ctx->nroots.ptr, (int32_t*)ctx->nunconv.ptr, stats);
+    if (rc) return rc;
+    const size_t out_slots = pencil ? (size_t)total : (size_t)(total - nbatch > 0 ? total - nbatch : 0);
+    if (out_slots > 0) CUDA_TRY(ctx, cudaMemcpyAsync(roots, ctx->roots.ptr, out_slots * sizeof(cplx), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(nroots, ctx->nroots.ptr, (size_t)nbatch * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(nunconv, ctx->nunconv.ptr, (size_t)nbatch * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return AMRVW_OK;
+}
+
+extern "C" {
+
+int amrvw_roots_rds_f64(amrvw_ctx* ctx, const double* coeffs, const int64_t* offsets, int64_t nbatch, double* roots, int32_t* nroots, int32_t* nunconv, amrvw_stats* stats) {
+    return run_host<double>(ctx, V_RDS, coeffs, nullptr, offsets, nbatch, roots, nroots, nunconv, stats);
+}
+int amrvw_roots_css_c64(amrvw_ctx* ctx, const double* coeffs, const int64_t* offsets, int64_t nbatch, double* roots, int32_t* nroots, int32_t* nunconv, amrvw_stats* stats) {
+    return run_host<cplx>(ctx, V_CSS, (const cplx*)coeffs, nullptr, offsets, nbatch, roots, nroots, nunconv, stats);
+}
+int amrvw_roots_pencil_f64(amrvw_ctx* ctx, const double* vs, const double* ws, const int64_t* offsets, int64_t nbatch, double* roots, int32_t* nroots, int32_t* nunconv, amrvw_stats* stats) {
+    return run_host<double>(ctx, V_PENCIL_R, vs, ws, offsets, nbatch, roots, nroots, nunconv, stats);
+}
+int amrvw_roots_pencil_c64(amrvw_ctx* ctx, const double* vs, const double* ws, const int64_t* offsets, int64_t nbatch, double* roots, int32_t* nroots, int32_t* nunconv, amrvw_stats* stats) {
+    return run_host<cplx>(ctx, V_PENCIL_C, (const cplx*)vs, (const cplx*)ws, offsets, nbatch, roots, nroots, nunconv, stats);
+}
+
+int amrvw_roots_rds_f64_dev(amrvw_ctx* ctx, const double* a, const int64_t* off, int64_t nb, int64_t total, int64_t max_len, double* r, int32_t* nr, int32_t* nu, amrvw_stats* stats) {
+    return run_dev<double>(ctx, V_RDS, a, nullptr, off, nb, total, max_len, r, nr, nu, stats);
+}
+int amrvw_roots_css_c64_dev(amrvw_ctx* ctx, const double* a, const int64_t* off, int64_t nb, int64_t total, int64_t max_len, double* r, int32_t* nr, int32_t* nu, amrvw_stats* stats) {
+    return run_dev<cplx>(ctx, V_CSS, (const cplx*)a, nullptr, off, nb, total, max_len, r, nr, nu, stats);
+}
+int amrvw_roots_pencil_f64_dev(amrvw_ctx* ctx, const double* v, const double* w, const int64_t* off, int64_t nb, int64_t total, int64_t max_len, double* r, int32_t* nr, int32_t* nu, amrvw_stats* stats) {
+    return run_dev<double>(ctx, V_PENCIL_R, v, w, off, nb, total, max_len, r, nr, nu, stats);
+}
+int amrvw_roots_pencil_c64_dev(amrvw_ctx* ctx, const double* v, const double* w, const int64_t* off, int64_t nb, int64_t total, int64_t max_len, double* r, int32_t* nr, int32_t* nu, amrvw_stats* stats) {
+    return run_dev<cplx>(ctx, V_PENCIL_C, (const cplx*)v, (const cplx*)w, off, nb, total, max_len, r, nr, nu, stats);
+}
+
+int amrvw_count_real_roots_dev(amrvw_ctx* ctx, const double* d_roots, const int64_t* d_offsets, int64_t nbatch, int32_t shift, const int32_t* d_nroots, int32_t* d_counts3) {
+    if (!ctx) return AMRVW_ERR_ARGUMENT;
+    if (nbatch <= 0) return AMRVW_OK;
+    if (!d_roots || !d_offsets || !d_nroots || !d_counts3) return fail(ctx, AMRVW_ERR_ARGUMENT, "null buffer");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int threads = 128;
+    count_real_roots_kernel<<<(int)((nbatch + threads - 1) / threads), threads, 0, ctx->stream>>>((const cplx*)d_roots, (const long long*)d_offsets, nbatch, shift, d_nroots, d_counts3);
+    CUDA_TRY(ctx, cudaGetLastError());
+    return AMRVW_OK;
+}
+
+int amrvw_measure_fp64_peak(amrvw_ctx* ctx, double* tflops) {
+    if (!ctx || !tflops) return AMRVW_ERR_ARGUMENT;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int blocks = ctx->sm_count * 8, threads = 256, iters = 4096;
+    int rc = reserve(ctx, ctx->state, (size_t)blocks * threads * sizeof(double));
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, st));
+        fp64_peak_kernel<<<blocks, threads, 0, st>>>((double*)ctx->state.ptr, iters, 1.0 + rep);
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        float ms = 0.f;
+        CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    const double flops = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    return AMRVW_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,202 @@
+// kernels.cuh -- __global__ entry points of the one-bulge-at-a-time path (reference schedule):
+// one polynomial per thread, everything on device: zero trimming, closed forms for degree <= 2,
+// factorization set-up, the Francis iteration, sort, zero roots.
+#pragma once
+#include "solver.cuh"
+
+namespace amrvw {
+
+template <class S> struct Problem {
+    const S* coeffs;          // non-pencil: a0..an per polynomial; pencil: vs
+    const S* ws;              // pencil only
+    const long long* offsets; // nbatch+1, CSR
+    long long nbatch;
+    cplx* roots;              // complex slots; polynomial p at offsets[p] - p (non-pencil) / offsets[p] (pencil)
+    int* nroots;
+    int* nunconv;
+    PolyStats* stats;         // nullable
+    // workspace: chains are arrays of `slots` rotators; polynomial p starts at slot offsets[p] + extra*p
+    Rot<S>* Q; Rot<S>* B; Rot<S>* Ct; Rot<S>* WB; Rot<S>* WCt;
+    S* DQ; S* DR; S* WD;
+    int extra;                // 1 (non-pencil: len+1 slots) or 2 (pencil: N+2 slots)
+    unsigned long long seed;
+};
+
+template <class S, bool P> AMRVW_DI Fact<S, P> make_fact(const Problem<S>& pr, long long p, int N) {
+    const long long base = pr.offsets[p] + (long long)pr.extra * p;
+    Fact<S, P> F;
+    F.Q = pr.Q + base; F.B = pr.B + base; F.Ct = pr.Ct + base;
+    F.WB = P ? pr.WB + base : nullptr; F.WCt = P ? pr.WCt + base : nullptr;
+    if constexpr (is_real<S>::value) { F.DQ = nullptr; F.DR = nullptr; F.WD = nullptr; }
+    else { F.DQ = pr.DQ + base; F.DR = pr.DR + base; F.WD = P ? pr.WD + base : nullptr; }
+    F.N = N;
+    F.turnovers = 0;
+    return F;
+}
+
+// Trim exact zeros at both ends (utils.jl:14-22): first/last non-zero positions, -1 if none.
+template <class S> AMRVW_DI void trim_zeros(const S* a, int len, int& first, int& last) {
+    first = -1; last = -1;
+    for (int i = 0; i < len; ++i)
+        if (!iszero_(a[i])) { if (first < 0) first = i; last = i; }
+}
+
+template <class S> AMRVW_DI void finish_poly(const Problem<S>& pr, long long p, cplx* out, int cnt, int K, int unconv, const PolyStats& st) {
+    for (int i = 0; i < K; ++i) out[cnt + i] = cplx(0.0, 0.0);   // companion.jl:266-268
+    pr.nroots[p] = cnt + K;
+    pr.nunconv[p] = unconv;
+    if (pr.stats) pr.stats[p] = st;
+}
+
+// Factor (companion.jl:150-159) the trimmed polynomial ps[0..n] into the workspace.
+template <class S> AMRVW_DI void factor_companion(Fact<S, false>& F, const S* ps) {
+    const int n = F.N;
+    const S pNi = inv_(ps[n]);
+    q_factorization(F);
+    r_factorization(F.B, F.Ct, F.DR, n, [&](int i) { return decompose_entry(ps, n, i, pNi); });
+}
+
+// ---------------------------------------------------------------- roots(ps), one bulge at a time
+template <class S>
+__global__ void __launch_bounds__(64) roots_reference_kernel(Problem<S> pr) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= pr.nbatch) return;
+    const long long off = pr.offsets[p];
+    const int len = (int)(pr.offsets[p + 1] - off);
+    cplx* out = pr.roots + (off - p);
+    PolyStats st = {0, 0, 0, 0, 0};
+    int first, last;
+    trim_zeros(pr.coeffs + off, len, first, last);
+    if (first < 0) { finish_poly(pr, p, out, 0, 0, 0, st); return; }
+    const S* ps = pr.coeffs + off + first;
+    const int ncoef = last - first + 1, K = first;
+    if (ncoef <= 3) {
+        const int cnt = solve_simple(ps, ncoef, out);
+        finish_poly(pr, p, out, cnt, K, 0, st);
+        return;
+    }
+    const int N = ncoef - 1;
+    Fact<S, false> F = make_fact<S, false>(pr, p, N);
+    factor_companion(F, ps);
+    for (int i = 0; i < N; ++i) out[i] = cplx(0.0, 0.0);   // EIGS = zeros (AMRVW_algorithm.jl:23)
+    Counter ctr = {0, 1, N - 1, 15, N - 2};                 // AMRVW_algorithm.jl:18
+    int ord = 0;
+    const int unconv = drive_window(F, 1, N - 1, ctr, out - 1, 20ll * (N - 1), pr.seed, (unsigned long long)p, ord, st, ReferenceStep());
+    sort_roots(out, N);
+    st.turnovers = F.turnovers;
+    st.unconverged = unconv;
+    finish_poly(pr, p, out, N, K, unconv, st);
+}
+
+// ---------------------------------------------------------------- roots(vs, ws), one bulge at a time
+template <class S>
+__global__ void __launch_bounds__(64) roots_pencil_reference_kernel(Problem<S> pr) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= pr.nbatch) return;
+    const long long off = pr.offsets[p];
+    const int N0 = (int)(pr.offsets[p + 1] - off);
+    cplx* out = pr.roots + off;
+    PolyStats st = {0, 0, 0, 0, 0};
+    if (N0 <= 0) { finish_poly(pr, p, out, 0, 0, 0, st); return; }
+    const S* vs = pr.coeffs + off;
+    const S* ws = pr.ws + off;
+    // deflate_leading_zeros(vs, ws) (utils.jl:29-58) without touching the inputs: the reference's two
+    // in-place edits become overrides of one entry each.  Indices below are 1-based like the reference.
+    int N = N0, wsN_idx = 0, vsK_idx = 0;
+    S wsN_val = S(0.0), vsK_val = S(0.0);
+    if (iszero_(ws[N0 - 1])) {
+        N -= 1;
+        while (N >= 1) {
+            const S ai = vs[N] + ws[N - 1];
+            if (!iszero_(ai)) { wsN_idx = N; wsN_val = ai; break; }
+            N -= 1;
+        }
+    }
+    int K = 1;
+    if (iszero_(vs[0])) {
+        K = 2;
+        while (K <= N) {
+            const S wprev = (K - 1 == wsN_idx) ? wsN_val : ws[K - 2];
+            const S ai = vs[K - 1] + wprev;
+            if (!iszero_(ai)) { vsK_idx = K; vsK_val = ai; break; }
+            K += 1;
+        }
+    }
+    auto V = [&](int i) { return i == vsK_idx ? vsK_val : vs[i - 1]; };  // 1-based
+    auto W = [&](int i) { return i == wsN_idx ? wsN_val : ws[i - 1]; };
+    const int n = N - K + 1;   // length of vs[K:N]
+    const int Kz = K - 1;
+    if (n <= 0) { finish_poly(pr, p, out, 0, 0, 0, st); return; }
+    if (n <= 2) {  // companion.jl:288-293: rs = vcat(ps,0) + vcat(0,qs); roots(rs)
+        S rs[3] = {S(0.0), S(0.0), S(0.0)};
+        for (int i = 0; i < n; ++i) { rs[i] = rs[i] + V(K + i); rs[i + 1] = rs[i + 1] + W(K + i); }
+        int f2, l2;
+        trim_zeros(rs, n + 1, f2, l2);
+        int cnt = 0;
+        if (f2 >= 0) {
+            cnt = solve_simple(rs + f2, l2 - f2 + 1, out);
+            for (int i = 0; i < f2; ++i) out[cnt + i] = cplx(0.0, 0.0);
+            cnt += f2;
+        }
+        finish_poly(pr, p, out, cnt, Kz, 0, st);
+        return;
+    }
+    // amrvw(vs, ws) (companion.jl:163-204): ps = basic_decompose([vs; 1]); ws sign-adjusted; qs = [ws; -1]
+    Fact<S, true> F = make_fact<S, true>(pr, p, n);
+    q_factorization(F);
+    {
+        const double par = (n % 2 == 0) ? 1.0 : -1.0;
+        auto xs_v = [&](int i) -> S {   // basic_decompose of [vs[K:N]; 1], monic so pNi = 1
+            if (i == n + 1) return S(-1.0);
+            if (i == n) return par * V(K) * S(1.0);
+            const double sg = ((i + 1) % 2 == 0) ? 1.0 : -1.0;
+            return (par * sg) * V(K + i) * S(1.0);
+        };
+        auto xs_w = [&](int i) -> S {   // adjust_pencil: entries n-1, n-3, ... change sign (companion.jl:168-170)
+            if (i == n + 1) return S(-1.0);
+            const S w = W(K + i - 1);
+            return ((n - 1 - i) % 2 == 0 && i <= n - 1) ? -w : w;
+        };
+        r_factorization(F.B, F.Ct, F.DR, n, xs_v);
+        r_factorization(F.WB, F.WCt, F.WD, n, xs_w);
+    }
+    for (int i = 0; i < n; ++i) out[i] = cplx(0.0, 0.0);
+    Counter ctr = {0, 1, n - 1, 15, n - 2};
+    int ord = 0;
+    const int unconv = drive_window(F, 1, n - 1, ctr, out - 1, 20ll * (n - 1), pr.seed, (unsigned long long)p, ord, st, ReferenceStep());
+    sort_roots(out, n);
+    st.turnovers = F.turnovers;
+    st.unconverged = unconv;
+    finish_poly(pr, p, out, n, Kz, unconv, st);
+}
+
+// ---------------------------------------------------------------- real_polynomial_roots counts
+__global__ void count_real_roots_kernel(const cplx* roots, const long long* offsets, long long nbatch, int shift, const int* nroots, int* counts3) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nbatch) return;
+    const cplx* r = roots + (offsets[p] - (long long)shift * p);
+    int nre = 0, npos = 0, nneg = 0;
+    for (int i = 0; i < nroots[p]; ++i) {
+        const double im = r[i].im;
+        if (im == 0.0) nre++; else if (im > 0.0) npos++; else nneg++;
+    }
+    counts3[3 * p] = nre; counts3[3 * p + 1] = npos; counts3[3 * p + 2] = nneg;
+}
+
+// ---------------------------------------------------------------- FP64 peak probe
+// 8 independent DFMA chains per thread, no memory traffic: measures the FP64 vector-pipe roofline.
+__global__ void fp64_peak_kernel(double* out, int iters, double seed) {
+    double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+    const double m = 1.0000001, b = 1e-9;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fma(a0, m, b); a1 = fma(a1, m, b); a2 = fma(a2, m, b); a3 = fma(a3, m, b);
+            a4 = fma(a4, m, b); a5 = fma(a5, m, b); a6 = fma(a6, m, b); a7 = fma(a7, m, b);
+        }
+    }
+    out[(long long)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+}  // namespace amrvw

@@ -1,0 +1,213 @@
+"""Host-side mirror of the reference's user API for the batched-roots path.
+
+Same names and argument meaning as the reference (all under /root/reference/src):
+    roots(ps)                      companion.jl:252-272   Float64 -> RDS, ComplexF64 -> CSS
+    roots(vs, ws)                  companion.jl:282-303   companion pencil
+    basic_pencil(ps)               companion.jl:44-54
+    real_polynomial_roots(ps)      complex_conjugate_root_theorem.jl:32-54
+plus the one thing the reference lacks: `roots` of a *sequence of coefficient vectors* roots them
+all in one call on the GPU (the reference's batch is the comprehension of README.md:121).
+
+Everything numeric happens in the CUDA library behind include/amrvw_b200.h; this file only packs
+ragged inputs into CSR buffers and unpacks the result.  No CPU fallback.
+"""
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import AmrvwError, Options, Stats
+
+
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data if a is not None else 0)
+
+
+class Context:
+    """One per host thread and device (amrvw_ctx)."""
+
+    def __init__(self, device=-1, seed=0, strict=False, **options):
+        self._lib = _lib.load(strict=strict)
+        self._h = ctypes.c_void_p()
+        rc = self._lib.amrvw_create(ctypes.byref(self._h), int(device), ctypes.c_uint64(seed))
+        if rc != 0:
+            self._h = ctypes.c_void_p()
+            raise AmrvwError(f"amrvw_create failed ({rc}): no usable CUDA device; this package has no CPU path")
+        self.last_stats = None
+        if options:
+            self.set_options(seed=seed, **options)
+
+    # -- plumbing
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.amrvw_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc != 0:
+            raise AmrvwError(f"amrvw error {rc}: {self._lib.amrvw_last_error(self._h).decode()}")
+
+    def set_options(self, schedule=0, lanes_per_poly=0, shift_reuse=0, small_window=0, seed=0):
+        o = Options(int(schedule), int(lanes_per_poly), int(shift_reuse), int(small_window), int(seed))
+        self._check(self._lib.amrvw_set_options(self._h, ctypes.byref(o)))
+
+    def set_stream(self, cuda_stream_handle):
+        self._check(self._lib.amrvw_set_stream(self._h, ctypes.c_void_p(int(cuda_stream_handle or 0))))
+
+    def fp64_peak_tflops(self):
+        v = ctypes.c_double()
+        self._check(self._lib.amrvw_measure_fp64_peak(self._h, ctypes.byref(v)))
+        return v.value
+
+    # -- host buffers (CSR) in, host buffers out
+    def roots_csr(self, coeffs, offsets, ws=None, want_stats=True):
+        """coeffs: flat float64 or complex128 array; offsets: int64[B+1]; ws: pencil second vector.
+        Returns (roots complex128 flat, root_offsets int64[B+1], nroots int32[B], n_unconverged int32[B])."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        B = len(offsets) - 1
+        cx = np.iscomplexobj(coeffs) or (ws is not None and np.iscomplexobj(ws))
+        dt = np.complex128 if cx else np.float64
+        coeffs = np.ascontiguousarray(coeffs, dtype=dt)
+        pencil = ws is not None
+        if pencil:
+            ws = np.ascontiguousarray(ws, dtype=dt)
+            if ws.shape != coeffs.shape:
+                raise ValueError("vs and ws must have the same layout")
+        total = int(offsets[-1]) if B >= 0 and len(offsets) else 0
+        if pencil:
+            root_off = offsets.copy()
+        else:
+            root_off = offsets - np.arange(B + 1, dtype=np.int64)
+        out = np.zeros(max(int(root_off[-1]) if B > 0 else 0, 0) + (B if not pencil else 0) + 1, dtype=np.complex128)
+        nroots = np.zeros(max(B, 1), dtype=np.int32)
+        nunc = np.zeros(max(B, 1), dtype=np.int32)
+        st = Stats()
+        stp = ctypes.byref(st) if want_stats else None
+        L = self._lib
+        if pencil:
+            fn = L.amrvw_roots_pencil_c64 if cx else L.amrvw_roots_pencil_f64
+            rc = fn(self._h, _ptr(coeffs), _ptr(ws), _ptr(offsets), B, _ptr(out), _ptr(nroots), _ptr(nunc), stp)
+        else:
+            fn = L.amrvw_roots_css_c64 if cx else L.amrvw_roots_rds_f64
+            rc = fn(self._h, _ptr(coeffs), _ptr(offsets), B, _ptr(out), _ptr(nroots), _ptr(nunc), stp)
+        self._check(rc)
+        self.last_stats = st.as_dict() if want_stats else None
+        return out, root_off, nroots[:B], nunc[:B]
+
+    # -- device pointers (ints) in/out: used by bench.py with torch-owned HBM buffers
+    def roots_dev(self, kind, d_coeffs, d_offsets, B, total, max_len, d_roots, d_nroots, d_nunconv, d_ws=None, want_stats=False):
+        st = Stats()
+        stp = ctypes.byref(st) if want_stats else None
+        L = self._lib
+        P = ctypes.c_void_p
+        if kind in ("pencil_f64", "pencil_c64"):
+            fn = L.amrvw_roots_pencil_f64_dev if kind == "pencil_f64" else L.amrvw_roots_pencil_c64_dev
+            rc = fn(self._h, P(d_coeffs), P(d_ws), P(d_offsets), B, total, max_len, P(d_roots), P(d_nroots), P(d_nunconv), stp)
+        else:
+            fn = {"rds_f64": L.amrvw_roots_rds_f64_dev, "css_c64": L.amrvw_roots_css_c64_dev}[kind]
+            rc = fn(self._h, P(d_coeffs), P(d_offsets), B, total, max_len, P(d_roots), P(d_nroots), P(d_nunconv), stp)
+        self._check(rc)
+        self.last_stats = st.as_dict() if want_stats else None
+        return self.last_stats
+
+    def count_real_roots_dev(self, d_roots, d_offsets, B, shift, d_nroots, d_counts3):
+        P = ctypes.c_void_p
+        self._check(self._lib.amrvw_count_real_roots_dev(self._h, P(d_roots), P(d_offsets), B, int(shift), P(d_nroots), P(d_counts3)))
+
+
+_default_ctx = None
+
+
+def default_context():
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context()
+    return _default_ctx
+
+
+def _is_batch(ps):
+    if isinstance(ps, np.ndarray):
+        return ps.ndim == 2 or ps.dtype == object
+    if isinstance(ps, (list, tuple)):
+        return len(ps) > 0 and isinstance(ps[0], (list, tuple, np.ndarray))
+    return False
+
+
+def _pack(seq):
+    arrs = [np.asarray(a) for a in seq]
+    cx = any(np.iscomplexobj(a) for a in arrs)
+    dt = np.complex128 if cx else np.float64
+    lens = np.array([a.shape[0] if a.ndim else 0 for a in arrs], dtype=np.int64)
+    offsets = np.zeros(len(arrs) + 1, dtype=np.int64)
+    np.cumsum(lens, out=offsets[1:])
+    flat = np.concatenate([a.astype(dt, copy=False).reshape(-1) for a in arrs]) if len(arrs) and offsets[-1] > 0 else np.zeros(0, dtype=dt)
+    return flat, offsets
+
+
+def roots(ps, ws=None, ctx=None):
+    """AMRVW.roots: `roots(ps)` or `roots(vs, ws)`; either a single coefficient vector
+    (a0..an, lowest degree first) or a sequence of them (rooted in one GPU call).
+
+    Float64 coefficients use the real double shift algorithm, ComplexF64 the complex single shift
+    one (companion.jl:252-272); two arguments select the companion pencil (companion.jl:282-303).
+    Returns complex128 roots sorted by (real, imag) with the zero roots of trimmed low-order zeros
+    appended, exactly like the reference; a batch returns a list of such arrays.
+    """
+    ctx = ctx or default_context()
+    batch = _is_batch(ps)
+    seq = list(ps) if batch else [ps]
+    flat, offsets = _pack(seq)
+    wflat = None
+    if ws is not None:
+        wseq = list(ws) if batch else [ws]
+        wflat, woff = _pack(wseq)
+        if not np.array_equal(woff, offsets):
+            raise ValueError("roots(vs, ws): vs and ws must have equal lengths")
+        if np.iscomplexobj(wflat) != np.iscomplexobj(flat):
+            flat = flat.astype(np.complex128)
+            wflat = wflat.astype(np.complex128)
+    out, roff, nroots, _ = ctx.roots_csr(flat, offsets, wflat)
+    res = [out[roff[p]: roff[p] + nroots[p]].copy() for p in range(len(seq))]
+    return res if batch else res[0]
+
+
+def basic_pencil(ps):
+    """companion.jl:44-54: vs = [a0..a_{n-1}], ws = [0,..,0,a_n]."""
+    ps = np.asarray(ps)
+    qs = np.zeros(len(ps) - 1, dtype=ps.dtype)
+    qs[-1] = ps[-1]
+    return ps[:-1].copy(), qs
+
+
+@dataclass
+class ComplexConjugateRootTheoremRoots:
+    """complex_conjugate_root_theorem.jl:7-10: real roots, and the upper-half-plane member of each
+    conjugate pair."""
+    real_roots: np.ndarray
+    complex_roots: np.ndarray
+
+    def __eq__(self, other):
+        return np.array_equal(self.real_roots, other.real_roots) and np.array_equal(self.complex_roots, other.complex_roots)
+
+
+class ComplexConjugateException(Exception):
+    """complex_conjugate_root_theorem.jl:22-26."""
+
+    def __init__(self, count_real, count_cc_negimag, count_cc_posimag):
+        super().__init__(count_real, count_cc_negimag, count_cc_posimag)
+        self.count_real, self.count_cc_negimag, self.count_cc_posimag = count_real, count_cc_negimag, count_cc_posimag
+
+
+def real_polynomial_roots(coefs, ctx=None):
+    """complex_conjugate_root_theorem.jl:32-54: classify by exact imag == 0 / imag > 0."""
+    coefs = np.asarray(coefs, dtype=np.float64)
+    rts = roots(coefs, ctx=ctx)
+    real_roots = rts.real[rts.imag == 0]
+    complex_roots = rts[rts.imag > 0]
+    cn = int(np.sum(rts.imag < 0))
+    if cn != len(complex_roots):
+        raise ComplexConjugateException(len(real_roots), cn, len(complex_roots))
+    return ComplexConjugateRootTheoremRoots(real_roots, complex_roots)

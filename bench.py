@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the batched core-chasing root finder (BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W            # ours; N > 1 under torchrun
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference algorithm on host cores
+
+A "step" is one pass of the hot path over one batch: rooting `batch` polynomials of degree `degree`
+(default: BASELINE config 2, the README statistics workload -- 3000 N(0,1) polynomials of degree
+3000, Float64 real double shift) per GPU.  Polynomials are independent, so the batch is sharded by
+polynomial with no collective ("scaling": "weak": every rank roots a full batch of its own).
+
+Printed JSON (one line, rank 0): metric polynomials/s (`value`: inputs resident in HBM, CUDA-event
+timed; `e2e`: through the C ABI with pinned HOST buffers, H2D + kernels + D2H inside the timed
+region), plus `roofline` (FP64 vector pipe -- measured live with a DFMA probe because
+MEASURED_PEAKS.json has no FP64 entry -- and the HBM figure next to it), `cpu_baseline` (the oracle =
+the reference's algorithm and schedule, OpenMP over polynomials on this box's host cores, bounded
+sample), clocks sampled during the timed region, and the kernel launch count.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (kind, batch, degree, input law, seed)   -- BASELINE.json configs[0..4]
+    "c1": ("rds_f64", 1000, 100, 0, 1),
+    "c2": ("rds_f64", 3000, 3000, 0, 2),
+    "c3": ("css_c64", 2000, 1000, 1, 3),
+    "c4": ("pencil_f64", 1000, 500, 0, 4),
+    "c5": ("rds_f64", 64, 10000, 2, 5),     # 512 over 8 GPUs = 64 per GPU
+}
+FLOP_PER_TURNOVER = {"rds_f64": 37.0, "css_c64": 94.0, "pencil_f64": 37.0}
+BYTES_PER_TURNOVER = {"rds_f64": 96.0 / 7, "css_c64": 208.0 / 3, "pencil_f64": 160.0 / 11}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (development only)")
+    ap.add_argument("--degree", type=int, default=0, help="override the degree (development only)")
+    ap.add_argument("--schedule", type=int, default=0, help="0 auto, 1 reference one-bulge, 2 pipelined")
+    ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--reuse", type=int, default=0)
+    ap.add_argument("--small", type=int, default=0)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="polynomials in the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def make_inputs(kind, batch, degree, law, seed, first_id):
+    from amrvw_jl_b200 import synth
+    ids = np.arange(first_id, first_id + batch)
+    if kind == "css_c64":
+        raw = synth.fill_coeffs(seed, ids, law, 2 * (degree + 1))
+        flat = np.ascontiguousarray(raw).reshape(-1)          # interleaved (re, im)
+        ncoef = degree + 1
+    else:
+        flat = np.ascontiguousarray(synth.fill_coeffs(seed, ids, law, degree + 1)).reshape(-1)
+        ncoef = degree + 1
+    if kind == "pencil_f64":                                   # basic_pencil split (companion.jl:44-54)
+        a = flat.reshape(batch, degree + 1)
+        vs = np.ascontiguousarray(a[:, :-1]).reshape(-1)
+        ws = np.zeros((batch, degree)); ws[:, -1] = a[:, -1]
+        offsets = np.arange(batch + 1, dtype=np.int64) * degree
+        return vs, ws.reshape(-1), offsets, degree
+    offsets = np.arange(batch + 1, dtype=np.int64) * ncoef
+    return flat, None, offsets, ncoef
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for nm, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                "power_w_max": max(float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()), "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def cpu_baseline(kind, degree, law, seed, sample, threads=0):
+    """The reference's algorithm and schedule (the oracle port) on this box's host cores."""
+    from oracle import oracle as orc            # allowed here: cpu_baseline / --impl reference legs only
+    cores = orc.num_threads() if threads <= 0 else threads
+    if sample <= 0:
+        per_core_s = {"rds_f64": 1.5e-7, "css_c64": 2.3e-7, "pencil_f64": 2.4e-7}[kind] * degree * degree * (4.5 if kind != "pencil_f64" else 8)
+        sample = max(cores, min(64 * cores, int(cores * max(1.0, 12.0 / max(per_core_s, 1e-9)))))
+    flat, ws, offsets, _ = make_inputs(kind, sample, degree, law, seed, 0)
+    if kind == "css_c64":
+        flat = flat.view(np.complex128)
+    t0 = time.perf_counter()
+    out, roff, nr, st = orc.roots_csr(flat, offsets, ws=ws, seed=0, threads=cores)
+    dt = time.perf_counter() - t0
+    return {"value": sample / dt, "unit": "polynomials/s", "cores": cores, "kind": "port",
+            "sample": f"{sample} polynomials of degree {degree} (same generator and seed as the GPU batch), {dt:.2f} s wall, OpenMP dynamic over polynomials",
+            "turnovers_per_s": st["turnovers"] / dt, "turnovers_per_poly": st["turnovers"] / sample, "seconds": dt}
+
+
+def main():
+    args = parse()
+    kind, batch, degree, law, seed = CONFIGS[args.config]
+    if args.batch:
+        batch = args.batch
+    if args.degree:
+        degree = args.degree
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = f"{args.config}: {kind} batch={batch}/GPU degree={degree} law={['N(0,1)', 'U[0,1)', 'U[0,1)-1/2'][law]} seed={seed}"
+    config = {"workload": workload, "kind": kind, "batch_per_gpu": batch, "degree": degree, "parallelism": f"shard-by-polynomial x{world}",
+              "l2": "per-step working set (rotator chains, rewritten by the set-up every step) exceeds the 126 MB L2 for c2/c5; no flush between steps"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        runs = []
+        sample = args.cpu_sample
+        for i in range(args.warmup + args.steps):
+            cb = cpu_baseline(kind, degree, law, seed, sample)
+            if sample <= 0:
+                sample = int(cb["sample"].split()[0])
+            if i >= args.warmup:
+                runs.append(cb)
+            if i == 0 and cb["seconds"] * (args.warmup + args.steps) > 240:   # keep the whole run within minutes
+                sample = max(cb["cores"], int(sample * 240 / (cb["seconds"] * (args.warmup + args.steps))))
+        secs = sum(r["seconds"] for r in runs)
+        n = sum(int(r["sample"].split()[0]) for r in runs)
+        val = n / secs
+        line = {"impl": "reference", "metric": "polynomials/sec", "value": val, "unit": "polynomials/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * secs / len(runs), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": "polynomials/s", "cores": runs[-1]["cores"], "kind": "port", "sample": runs[-1]["sample"],
+                                 "turnovers_per_s": sum(r["turnovers_per_s"] * r["seconds"] for r in runs) / secs},
+                "e2e": {"value": val, "unit": "polynomials/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "note": "Julia is not available in this image: the reference arm is the C++ oracle (same algorithm, same one-bulge schedule); each step is a bounded sample of the workload"}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm (GPU)
+    import torch
+    import torch.distributed as dist
+    import amrvw_jl_b200 as A
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: this framework has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    flat, ws, offsets, ncoef = make_inputs(kind, batch, degree, law, seed, rank * batch)
+    total = int(offsets[-1])
+    ctx = A.Context(device=local_rank, seed=seed, schedule=args.schedule, lanes_per_poly=args.lanes, shift_reuse=args.reuse, small_window=args.small)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    d_c = torch.from_numpy(flat).to(dev)
+    d_w = torch.from_numpy(ws).to(dev) if ws is not None else None
+    d_o = torch.from_numpy(offsets).to(dev)
+    nroot_slots = total if kind.startswith("pencil") else total - batch
+    d_r = torch.zeros(2 * (total + 1), dtype=torch.float64, device=dev)
+    d_n = torch.zeros(batch, dtype=torch.int32, device=dev)
+    d_u = torch.zeros(batch, dtype=torch.int32, device=dev)
+
+    def step(stats=False):
+        return ctx.roots_dev(kind, d_c.data_ptr(), d_o.data_ptr(), batch, total, ncoef, d_r.data_ptr(), d_n.data_ptr(), d_u.data_ptr(),
+                             d_ws=d_w.data_ptr() if d_w is not None else None, want_stats=stats)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    fp64_peak = ctx.fp64_peak_tflops()
+    st = None
+    for _ in range(max(args.warmup, 1)):
+        st = step(stats=True)           # warm-up also yields the per-step counters (launches, turnovers)
+    torch.cuda.synchronize()
+    n_unconv = int(d_u.sum().item())
+    nroots_ok = int(d_n.sum().item())
+
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with ClockSampler(local_rank) as clk:
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step()
+        ev1.record(stream)
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = world * batch * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the C ABI with pinned host buffers
+    e2e = None
+    if not args.no_e2e:
+        h_c = torch.from_numpy(flat).pin_memory()
+        h_w = torch.from_numpy(ws).pin_memory() if ws is not None else None
+        h_o = torch.from_numpy(offsets).pin_memory()
+        h_r = torch.zeros(2 * (total + 1), dtype=torch.float64).pin_memory()
+        h_n = torch.zeros(batch, dtype=torch.int32).pin_memory()
+        h_u = torch.zeros(batch, dtype=torch.int32).pin_memory()
+        lib = A.load()
+        import ctypes
+        P = ctypes.c_void_p
+
+        def e2e_step():
+            if kind == "pencil_f64":
+                rc = lib.amrvw_roots_pencil_f64(ctx._h, P(h_c.data_ptr()), P(h_w.data_ptr()), P(h_o.data_ptr()), batch, P(h_r.data_ptr()), P(h_n.data_ptr()), P(h_u.data_ptr()), None)
+            elif kind == "css_c64":
+                rc = lib.amrvw_roots_css_c64(ctx._h, P(h_c.data_ptr()), P(h_o.data_ptr()), batch, P(h_r.data_ptr()), P(h_n.data_ptr()), P(h_u.data_ptr()), None)
+            else:
+                rc = lib.amrvw_roots_rds_f64(ctx._h, P(h_c.data_ptr()), P(h_o.data_ptr()), batch, P(h_r.data_ptr()), P(h_n.data_ptr()), P(h_u.data_ptr()), None)
+            assert rc == 0, lib.amrvw_last_error(ctx._h)
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()                  # synchronous: returns after the D2H copy of the roots
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        h2d = flat.nbytes + (ws.nbytes if ws is not None else 0) + offsets.nbytes
+        d2h = 16 * nroot_slots + 8 * batch
+        e2e = {"value": world * batch * args.steps / dt, "unit": "polynomials/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "roots_checksum": float(h_r[: 2 * nroot_slots].abs().sum().item())}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- CPU baseline (rank 0, N = 1 only) and roofline
+    cb = None
+    if world == 1 and not args.no_cpu_baseline:
+        cb = cpu_baseline(kind, degree, law, seed, args.cpu_sample)
+    ms_step = ms / args.steps
+    executed = st["turnovers"]
+    useful_per_poly = cb["turnovers_per_poly"] if cb else None
+    useful = useful_per_poly * batch if useful_per_poly else executed
+    kernel_ms = st["device_ms"]
+    flops = useful * FLOP_PER_TURNOVER[kind]
+    tf = flops / (ms_step * 1e-3) / 1e12
+    hbm_peak, hbm_src = 6650.0, "fallback"
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        hbm_peak, hbm_src = float(mp["hbm_gbs"]), "measured"
+    except Exception:
+        pass
+    gbs = useful * BYTES_PER_TURNOVER[kind] / (ms_step * 1e-3) / 1e9
+    roofline = {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak, "traffic": None,
+                "peak_source": "DFMA probe measured live in this run (MEASURED_PEAKS.json has no FP64 entry); nominal 37.2",
+                "kernel": "the one kernel of the step (device_ms of one warm-up step: %.2f ms)" % kernel_ms,
+                "useful_turnovers_per_step": useful, "executed_turnovers_per_step": executed,
+                "useful_definition": "the reference schedule's turnover count on the same inputs (CPU sample mean x batch) x 37 flop",
+                "hbm": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": hbm_src + " copy bandwidth",
+                        "note": "algorithmic bytes = 96 B per 7 turnovers; the path is not HBM-bound"}}
+    line = {"metric": "polynomials/sec", "value": value, "unit": "polynomials/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config, "turnovers_per_sec": world * useful / (ms_step * 1e-3), "roofline": roofline, "cpu_baseline": cb, "e2e": e2e,
+            "gpu_launches": int(st["launches"] * args.steps), "clocks": clk.summary(),
+            "stats_per_step": {k: st[k] for k in ("turnovers", "sweeps", "exceptional", "unconverged", "fat_steps", "launches")},
+            "unconverged": n_unconv, "roots_found": nroots_ok}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

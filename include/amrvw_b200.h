@@ -1,0 +1,128 @@
+/* amrvw_b200.h -- C ABI of the B200-native batched core-chasing root finder.
+ *
+ * Drop-in boundary for ONE path of jverzani/AMRVW.jl: `AMRVW.roots` applied to many independent
+ * polynomials.  The reference has no FFI layer; its boundary is the Julia method table
+ *     roots(ps::Vector{S})                       src/companion.jl:252-272
+ *     roots(vs::Vector{S}, ws::Vector{S})        src/companion.jl:282-303
+ * and "a batch" is a user comprehension over it (README.md:121).  A maintainer adds one batched
+ * method roots(::AbstractVector{<:AbstractVector{T}}) that `ccall`s the entry points below
+ * (INTEGRATION.md shows the Julia stub; amrvw.jl_b200/roots.py is the same binding via ctypes).
+ *
+ * Conventions
+ *   - Polynomials are ragged, CSR style: polynomial p owns coeffs[offsets[p] .. offsets[p+1]),
+ *     lowest degree first (a0 .. an), exactly the vector AMRVW.roots takes.  Complex data is
+ *     interleaved (re, im), bit-compatible with Julia's Vector{ComplexF64}.
+ *   - Roots are interleaved (re, im) doubles.  Non-pencil calls write polynomial p's roots at
+ *     complex slot offsets[p] - p (a polynomial with len coefficients has at most len-1 roots);
+ *     pencil calls (vs, ws of equal length N_p) write at complex slot offsets[p].
+ *     nroots[p] says how many were written: like the reference, leading/trailing zero coefficients
+ *     are trimmed (utils.jl:14-58), degree <= 2 goes through the closed forms (utils.jl:63-140),
+ *     roots come back sorted by (real, imag) (AMRVW_algorithm.jl:134) followed by the K zero roots
+ *     of the trimmed low end (companion.jl:266-268).
+ *   - Non-convergence is not an error (AMRVW_algorithm.jl:23-30 leaves the missing roots at 0):
+ *     n_unconverged[p] counts the slots left at zero.
+ *   - Every function returns 0 on success, a negative amrvw_status otherwise; the message is
+ *     available from amrvw_last_error.  No exceptions cross the boundary.  A context is bound to
+ *     one CUDA device and is not thread-safe (one per host thread), like the reference's
+ *     single-threaded state.
+ *   - There is no CPU fallback: without a CUDA device amrvw_create fails.
+ */
+#ifndef AMRVW_B200_H
+#define AMRVW_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct amrvw_ctx amrvw_ctx;
+
+enum amrvw_status {
+    AMRVW_OK = 0,
+    AMRVW_ERR_ARGUMENT = -1,
+    AMRVW_ERR_CUDA = -2,
+    AMRVW_ERR_NO_DEVICE = -3
+};
+
+enum amrvw_schedule {
+    AMRVW_SCHEDULE_AUTO = 0,       /* pipelined multishift for Float64 RDS, one-bulge otherwise */
+    AMRVW_SCHEDULE_REFERENCE = 1,  /* one bulge at a time, shifts from the trailing 2x2 block: the
+                                      reference's own order of operations (bulge-step.jl:11-19)    */
+    AMRVW_SCHEDULE_PIPELINED = 2   /* several bulges in flight per polynomial, three indices apart */
+};
+
+/* Mirrors the reference's compile-time constants: IT_COUNT = 15
+ * (create-bulge.jl:9), it_max = 20 n (AMRVW_algorithm.jl:25), tol = eps (AMRVW_algorithm.jl:184). */
+typedef struct amrvw_options {
+    int32_t schedule;        /* amrvw_schedule */
+    int32_t lanes_per_poly;  /* pipelined: bulges in flight per polynomial (4, 8, 16 or 32); 0 = auto */
+    int32_t shift_reuse;     /* pipelined: bulges driven by each shift pair (1, 2 or 4); 0 = auto     */
+    int32_t small_window;    /* pipelined: windows up to this size use the one-bulge step; 0 = auto   */
+    uint64_t seed;           /* exceptional (random) shifts: counter-based, reproducible              */
+} amrvw_options;
+
+typedef struct amrvw_stats {
+    int64_t turnovers;     /* executed calls of the turnover primitive (transformations.jl:208) */
+    int64_t sweeps;        /* bulges chased */
+    int64_t exceptional;   /* random shifts taken (create-bulge.jl:25-37, 85-93) */
+    int64_t unconverged;   /* root slots left at zero */
+    int64_t fat_steps;     /* pipelined multi-bulge steps */
+    int64_t launches;      /* kernels launched by this call */
+    double device_ms;      /* CUDA-event time of the kernels of this call */
+} amrvw_stats;
+
+/* device < 0: current device. */
+int amrvw_create(amrvw_ctx** ctx, int device, uint64_t seed);
+int amrvw_destroy(amrvw_ctx* ctx);
+const char* amrvw_last_error(const amrvw_ctx* ctx);
+void amrvw_default_options(amrvw_options* opt);
+int amrvw_set_options(amrvw_ctx* ctx, const amrvw_options* opt);
+/* Run on an existing CUDA stream (cudaStream_t passed as void*); NULL = the context's own. */
+int amrvw_set_stream(amrvw_ctx* ctx, void* cuda_stream);
+
+/* ---- host buffers in, host buffers out (H2D + kernels + D2H inside the call) ------------------ */
+
+/* roots(ps) for Vector{Float64}: real double shift (src/RDS.jl).  companion.jl:252. */
+int amrvw_roots_rds_f64(amrvw_ctx* ctx, const double* coeffs, const int64_t* offsets, int64_t nbatch,
+                        double* roots_reim, int32_t* nroots, int32_t* n_unconverged, amrvw_stats* stats);
+/* roots(ps) for Vector{ComplexF64}: complex single shift (src/CSS.jl).  companion.jl:252. */
+int amrvw_roots_css_c64(amrvw_ctx* ctx, const double* coeffs_reim, const int64_t* offsets, int64_t nbatch,
+                        double* roots_reim, int32_t* nroots, int32_t* n_unconverged, amrvw_stats* stats);
+/* roots(vs, ws): companion pencil (src/pencil.jl), Float64 / ComplexF64.  companion.jl:282.
+ * Inputs are const: the reference's in-place edits of vs/ws (utils.jl:38,50, companion.jl:168-170)
+ * are not reproduced. */
+int amrvw_roots_pencil_f64(amrvw_ctx* ctx, const double* vs, const double* ws, const int64_t* offsets, int64_t nbatch,
+                           double* roots_reim, int32_t* nroots, int32_t* n_unconverged, amrvw_stats* stats);
+int amrvw_roots_pencil_c64(amrvw_ctx* ctx, const double* vs_reim, const double* ws_reim, const int64_t* offsets, int64_t nbatch,
+                           double* roots_reim, int32_t* nroots, int32_t* n_unconverged, amrvw_stats* stats);
+
+/* ---- device-resident variants: every pointer except stats is a DEVICE pointer on the context's
+ * device; total = offsets[nbatch] and max_len = longest polynomial are passed by value so the
+ * call needs no device->host read.  Asynchronous on the context's stream unless stats != NULL
+ * (stats needs the event time and the device-side counters, so it synchronises). */
+int amrvw_roots_rds_f64_dev(amrvw_ctx* ctx, const double* d_coeffs, const int64_t* d_offsets, int64_t nbatch, int64_t total, int64_t max_len,
+                            double* d_roots_reim, int32_t* d_nroots, int32_t* d_n_unconverged, amrvw_stats* stats);
+int amrvw_roots_css_c64_dev(amrvw_ctx* ctx, const double* d_coeffs_reim, const int64_t* d_offsets, int64_t nbatch, int64_t total, int64_t max_len,
+                            double* d_roots_reim, int32_t* d_nroots, int32_t* d_n_unconverged, amrvw_stats* stats);
+int amrvw_roots_pencil_f64_dev(amrvw_ctx* ctx, const double* d_vs, const double* d_ws, const int64_t* d_offsets, int64_t nbatch, int64_t total, int64_t max_len,
+                               double* d_roots_reim, int32_t* d_nroots, int32_t* d_n_unconverged, amrvw_stats* stats);
+int amrvw_roots_pencil_c64_dev(amrvw_ctx* ctx, const double* d_vs_reim, const double* d_ws_reim, const int64_t* d_offsets, int64_t nbatch, int64_t total, int64_t max_len,
+                               double* d_roots_reim, int32_t* d_nroots, int32_t* d_n_unconverged, amrvw_stats* stats);
+
+/* real_polynomial_roots (src/complex_conjugate_root_theorem.jl:32-54) reduced on device: for each
+ * polynomial the number of roots with imag == 0 exactly, imag > 0 and imag < 0 (counts[3*p..]).
+ * Device pointers; the README statistics workload (README.md:121) needs only this. */
+int amrvw_count_real_roots_dev(amrvw_ctx* ctx, const double* d_roots_reim, const int64_t* d_offsets, int64_t nbatch,
+                               int32_t slot_shift_per_poly, const int32_t* d_nroots, int32_t* d_counts3);
+
+/* FP64 DFMA micro-benchmark: dependent-chain-free FMA throughput of the device, in TFLOP/s
+ * (the FP64 roofline denominator; MEASURED_PEAKS.json only has HBM and bf16). */
+int amrvw_measure_fp64_peak(amrvw_ctx* ctx, double* tflops);
+
+int amrvw_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMRVW_B200_H */

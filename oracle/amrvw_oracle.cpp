@@ -1,0 +1,1308 @@
+// =====================================================================================
+// oracle/amrvw_oracle.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// A CPU restatement of the AMRVW.jl hot path (roots of a polynomial by core chasing on the
+// rotator-factored companion matrix / companion pencil).  Only tests/, __graft_entry__.smoke()
+// and bench.py's cpu_baseline / --impl reference legs may load this library; the CUDA product
+// under amrvw.jl_b200/ never links, imports or calls it.
+//
+// Every function cites the reference file:line (relative to /root/reference) it follows.  The
+// reference is pure Julia and Julia is not available in this image, so the oracle cannot be
+// checked against the reference *running*; it is pinned instead on every known-answer vector the
+// reference's own tests hold for this path (tests/test_oracle_golden.py).
+//
+// Arithmetic that lives OUTSIDE /root/reference (Julia stdlib, version only lower-bounded at
+// julia 1.6 by Project.toml:11-14): LinearAlgebra.givensAlgorithm (a port of LAPACK dlartg /
+// zlartg), Base complex division (Baudin & Smith robust division), Base.sqrt(::Complex),
+// abs(::Complex) = hypot, LinearAlgebra.sorteig!, Base.rand.  Those are restated here from their
+// published algorithms; the reference tests pin that boundary by property only (second component
+// annihilated, test/test-amrvw-basics.jl:26-32,56-62), so value parity AT THAT BOUNDARY IS
+// UNPINNED ("parity unpinned" for the last bits of givens/cdiv/csqrt; everything inside
+// /root/reference is restated operation by operation in Julia's left-to-right evaluation order,
+// without FMA contraction -- build with -ffp-contract=off).
+//
+// Besides the reference schedule (one bulge at a time) the file also holds the "multishift"
+// schedule used by the pipelined GPU kernel (section MS below): the same rotator operations, a
+// different order of shifts.  It exists so the GPU schedule can be checked step for step.
+// =====================================================================================
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <type_traits>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace orc {
+
+// ------------------------------------------------------------------ scalars
+// Julia's Complex{Float64} arithmetic, written out (base/complex.jl): no FMA, no NaN recovery.
+struct cplx {
+    double re, im;
+    cplx() : re(0), im(0) {}
+    cplx(double r) : re(r), im(0) {}
+    cplx(double r, double i) : re(r), im(i) {}
+};
+static inline cplx operator+(cplx a, cplx b) { return {a.re + b.re, a.im + b.im}; }
+static inline cplx operator-(cplx a, cplx b) { return {a.re - b.re, a.im - b.im}; }
+static inline cplx operator-(cplx a) { return {-a.re, -a.im}; }
+static inline cplx operator*(cplx a, cplx b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+static inline cplx operator*(cplx a, double s) { return {a.re * s, a.im * s}; }
+static inline cplx operator*(double s, cplx a) { return {s * a.re, s * a.im}; }
+static inline cplx operator/(cplx a, double s) { return {a.re / s, a.im / s}; }
+static inline cplx operator-(cplx a, double s) { return {a.re - s, a.im}; }
+static inline cplx operator+(cplx a, double s) { return {a.re + s, a.im}; }
+static inline cplx conj_(cplx a) { return {a.re, -a.im}; }
+static inline double conj_(double a) { return a; }
+static inline double real_(cplx a) { return a.re; }
+static inline double real_(double a) { return a; }
+static inline bool iszero_(cplx a) { return a.re == 0 && a.im == 0; }
+static inline bool iszero_(double a) { return a == 0; }
+static inline double abs_(cplx a) { return std::hypot(a.re, a.im); }  // Base.abs(::Complex) = hypot
+static inline double abs_(double a) { return std::fabs(a); }
+static inline double abs2_(cplx a) { return a.re * a.re + a.im * a.im; }
+static inline double sign_(double x) { return x > 0 ? 1.0 : (x < 0 ? -1.0 : x); }  // Base.sign
+
+// Base./(::ComplexF64, ::ComplexF64): Baudin & Smith robust complex division (normal range only;
+// the over/underflow rescaling branch is not reachable for the O(1) entries on this path).
+static inline double robust_cdiv2(double a, double b, double c, double d, double r, double t) {
+    if (r != 0) {
+        double br = b * r;
+        return br != 0 ? (a + br) * t : a * t + (b * t) * r;
+    }
+    return (a + d * (b / c)) * t;
+}
+static inline void robust_cdiv1(double a, double b, double c, double d, double& p, double& q) {
+    double r = d / c;
+    double t = 1.0 / (c + d * r);
+    p = robust_cdiv2(a, b, c, d, r, t);
+    q = robust_cdiv2(b, -a, c, d, r, t);
+}
+static inline cplx operator/(cplx z, cplx w) {
+    double p, q;
+    if (std::fabs(w.im) <= std::fabs(w.re)) {
+        robust_cdiv1(z.re, z.im, w.re, w.im, p, q);
+    } else {
+        robust_cdiv1(z.im, z.re, w.im, w.re, p, q);
+        q = -q;
+    }
+    return {p, q};
+}
+static inline double operator_div(double a, double b) { return a / b; }
+
+// Base.sqrt(::Complex): principal branch, sqrt((|z|+|x|)/2) formulation.
+static inline cplx csqrt_(cplx z) {
+    double x = z.re, y = z.im;
+    if (x == 0 && y == 0) return {0.0, y};
+    double rho = std::sqrt((std::hypot(x, y) + std::fabs(x)) / 2);
+    double xi = rho, eta = y;
+    if (rho != 0) {
+        eta = (eta / rho) / 2;
+        if (x < 0) {
+            xi = std::fabs(eta);
+            eta = std::copysign(rho, y);
+        }
+    }
+    return {xi, eta};
+}
+
+template <class S> struct is_real : std::is_same<S, double> {};
+
+// ------------------------------------------------------------------ counters / RNG
+struct Stats {
+    int64_t turnovers = 0;     // calls of turnover (transformations.jl:208) -- the unit of work
+    int64_t sweeps = 0;        // bulge steps (bulge-step.jl:11)
+    int64_t exceptional = 0;   // random shifts taken (create-bulge.jl:25-37, 85-93)
+    int64_t trips = 0;         // driver loop trips (AMRVW_algorithm.jl:30)
+    int64_t unconverged = 0;   // eigenvalue slots never written (left 0, AMRVW_algorithm.jl:23)
+    int64_t fat_steps = 0;     // multishift schedule only: pipelined multi-bulge steps
+    int64_t serial_turnovers = 0;  // multishift: turnovers on the serial path (shift sub-solves + small windows)
+    int64_t pipe_steps = 0;    // multishift: sum over fat steps of (window + 3(L-1)) lock-step chase steps
+};
+
+// Counter-based generator shared by oracle, CUDA kernels and bench inputs:
+// splitmix64 of (seed, polynomial id, ordinal) -> 53-bit uniform in [0,1).
+static inline uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+static inline double uniform01(uint64_t seed, uint64_t poly, uint64_t k) {
+    uint64_t h = splitmix64(seed ^ splitmix64(poly * 0x9E3779B97F4A7C15ull + k));
+    return (double)(h >> 11) * (1.0 / 9007199254740992.0);
+}
+struct Rng {  // stands in for Base.rand in the exceptional shift (create-bulge.jl:28,88)
+    uint64_t seed = 0, poly = 0, ordinal = 0;
+    double next() { return uniform01(seed ^ 0xA5A5A5A5DEADBEEFull, poly, ordinal++); }
+};
+
+// ------------------------------------------------------------------ givens (Julia stdlib, NOT in /root/reference)
+static const double SAFMN2 = 0x1p-485;  // floatmin2(Float64) = 2^trunc(log2(floatmin/eps)/2)
+static const double SAFMX2 = 0x1p+485;
+static const double SAFMIN = 2.2250738585072014e-308;
+
+// LinearAlgebra.givensAlgorithm(f::Float64, g::Float64) -- port of LAPACK dlartg.
+static inline void givens_algorithm(double f, double g, double& cs, double& sn, double& r) {
+    if (g == 0) { cs = 1; sn = 0; r = f; return; }
+    if (f == 0) { cs = 0; sn = 1; r = g; return; }
+    double f1 = f, g1 = g;
+    double scale = std::max(std::fabs(f1), std::fabs(g1));
+    if (scale >= SAFMX2) {
+        int count = 0;
+        do { ++count; f1 *= SAFMN2; g1 *= SAFMN2; scale = std::max(std::fabs(f1), std::fabs(g1)); } while (scale >= SAFMX2 && count < 20);
+        r = std::sqrt(f1 * f1 + g1 * g1); cs = f1 / r; sn = g1 / r;
+        for (int i = 0; i < count; ++i) r *= SAFMX2;
+    } else if (scale <= SAFMN2) {
+        int count = 0;
+        do { ++count; f1 *= SAFMX2; g1 *= SAFMX2; scale = std::max(std::fabs(f1), std::fabs(g1)); } while (scale <= SAFMN2);
+        r = std::sqrt(f1 * f1 + g1 * g1); cs = f1 / r; sn = g1 / r;
+        for (int i = 0; i < count; ++i) r *= SAFMN2;
+    } else {
+        r = std::sqrt(f1 * f1 + g1 * g1); cs = f1 / r; sn = g1 / r;
+    }
+    if (std::fabs(f) > std::fabs(g) && cs < 0) { cs = -cs; sn = -sn; r = -r; }
+}
+
+// LinearAlgebra.givensAlgorithm(f::ComplexF64, g::ComplexF64) -- port of LAPACK zlartg.
+static inline double abs1(cplx z) { return std::max(std::fabs(z.re), std::fabs(z.im)); }
+static inline void givens_algorithm(cplx f, cplx g, double& cs, cplx& sn, cplx& r) {
+    double scale = std::max(abs1(f), abs1(g));
+    cplx fs = f, gs = g;
+    int count = 0;
+    if (scale >= SAFMX2) {
+        do { ++count; fs = fs * SAFMN2; gs = gs * SAFMN2; scale *= SAFMN2; } while (scale >= SAFMX2 && count < 20);
+    } else if (scale <= SAFMN2) {
+        if (iszero_(g)) { cs = 1; sn = cplx(0, 0); r = f; return; }
+        do { --count; fs = fs * SAFMX2; gs = gs * SAFMX2; scale *= SAFMX2; } while (scale <= SAFMN2);
+    }
+    double f2 = abs2_(fs), g2 = abs2_(gs);
+    if (f2 <= std::max(g2, 1.0) * SAFMIN) {  // rare: F very small
+        if (iszero_(f)) {
+            cs = 0;
+            r = cplx(std::hypot(g.re, g.im), 0);
+            double d = std::hypot(gs.re, gs.im);
+            sn = cplx(gs.re / d, -gs.im / d);
+            return;
+        }
+        double f2s = std::hypot(fs.re, fs.im);
+        double g2s = std::sqrt(g2);
+        cs = f2s / g2s;
+        cplx ff;
+        if (abs1(f) > 1) {
+            double d = std::hypot(f.re, f.im);
+            ff = cplx(f.re / d, f.im / d);
+        } else {
+            double dr = SAFMX2 * f.re, di = SAFMX2 * f.im;
+            double d = std::hypot(dr, di);
+            ff = cplx(dr / d, di / d);
+        }
+        sn = ff * cplx(gs.re / g2s, -gs.im / g2s);
+        r = cs * f + sn * g;
+    } else {  // common case
+        double f2s = std::sqrt(1.0 + g2 / f2);
+        r = cplx(f2s * fs.re, f2s * fs.im);
+        cs = 1.0 / f2s;
+        double d = f2 + g2;
+        sn = cplx(r.re / d, r.im / d);
+        sn = sn * conj_(gs);
+        if (count > 0) for (int i = 0; i < count; ++i) r = r * SAFMX2;
+        if (count < 0) for (int i = 0; i < -count; ++i) r = r * SAFMN2;
+    }
+}
+
+// transformations.jl:17-21 -- real givensrot: [c s; -s c]*[a,b] = [r,0], r >= 0.
+static inline void givensrot(double a, double b, double& c, double& s, double& r) {
+    double gc, gs, gr;
+    givens_algorithm(a, b, gc, gs, gr);
+    double sg = gr >= 0 ? 1.0 : -1.0;
+    c = sg * gc; s = sg * gs; r = sg * gr;
+}
+// transformations.jl:28-31 -- complex givensrot: G,r = givens(b,a); return G.s, real(G.c), r.
+static inline void givensrot(cplx a, cplx b, cplx& c, double& s, cplx& r) {
+    double cs; cplx sn;
+    givens_algorithm(b, a, cs, sn, r);
+    c = sn; s = cs;
+}
+// transformations.jl:33 -- real second argument is promoted.
+static inline void givensrot(cplx a, double b, cplx& c, double& s, cplx& r) { givensrot(a, cplx(b, 0.0), c, s, r); }
+
+// transformations.jl:57-64
+static inline void approx_givensrot(double a, double b, double& c, double& s) {
+    double delta = std::fabs(a * a) + b * b - 1.0;
+    double r = 1.0 - delta / 2.0;
+    c = a * r; s = b * r;
+}
+static inline void approx_givensrot(cplx a, double b, cplx& c, double& s) {
+    cplx aa = a * conj_(a);
+    double delta = std::hypot(aa.re, aa.im) + b * b - 1.0;  // abs(a*conj(a))
+    double r = 1.0 - delta / 2.0;
+    cplx cc = a * r;
+    c = conj_(cc); s = b * r;
+}
+// transformations.jl:67-73
+static inline void polish_givens(double& c, double& s) {
+    double delta = c * c + s * s - 1.0;
+    double r = 1.0 - delta / 2.0;
+    c = r * c; s = r * s;
+}
+static inline void polish_givens(cplx& c, double& s) {
+    double delta = real_(conj_(c) * c) + s * s - 1.0;
+    double r = 1.0 - delta / 2.0;
+    c = r * c; s = r * s;
+}
+
+// ------------------------------------------------------------------ rotators
+// rotators.jl:80-84 -- [c s; -s conj(c)], s always real.  The index lives in the array position.
+template <class S> struct Rot {
+    S c; double s;
+};
+template <class S> static inline Rot<S> adjoint(Rot<S> u) { return {conj_(u.c), -u.s}; }  // rotators.jl:86-89
+
+// transformations.jl:80-93 (real) -- fuse: product of two same-index rotators.
+static inline Rot<double> fuse(Rot<double> a, Rot<double> b) {
+    double u = a.c * b.c - a.s * b.s;
+    double v = a.c * b.s + a.s * b.c;
+    polish_givens(u, v);
+    return {u, v};
+}
+// transformations.jl:101-118 (complex) -- returns the rotator and the phase alpha' = conj(alpha)
+// of the diagonal rotator D(conj alpha) with a*b = (ab) * D.
+static inline Rot<cplx> fuse(Rot<cplx> a, Rot<cplx> b, cplx& dphase) {
+    cplx u = a.c * b.c - a.s * b.s;
+    cplx v = a.c * b.s + a.s * conj_(b.c);
+    double s = abs_(v);
+    cplx alpha = iszero_(v) ? cplx(1.0, 0.0) : v / s;
+    cplx c = u * alpha;
+    polish_givens(c, s);
+    dphase = conj_(alpha);
+    return {c, s};
+}
+
+// transformations.jl:158-202 -- _turnover.
+template <class S>
+static inline void turnover_core(S c1, double s1, S c2, double s2, S c3, double s3,
+                                 S& c4, double& s4, S& c5, double& s5, S& c6, double& s6) {
+    S u21 = (-c2) * s3 * conj_(c1) - c3 * s1;
+    double u31 = s2 * s3;
+    if (iszero_(u21) && u31 == 0) {
+        if (iszero_(s2 * conj_(c3))) {
+            c4 = S(1.0); s4 = 0; c5 = c1 * c3 - c2 * s1 * s3; s5 = 0; c6 = c2; s6 = 0;
+            return;
+        }
+    }
+    S r4;
+    givensrot(u21, u31, c4, s4, r4);
+    c4 = conj_(c4); s4 = -s4;
+    S u11 = c1 * c3 - c2 * s1 * s3;
+    approx_givensrot(u11, real_(r4), c5, s5);
+    c5 = conj_(c5); s5 = -s5;
+    if (s5 != 0) {
+        S a = conj_(c1) * s2 * s4 + conj_(c2) * c4;
+        double b = s1 * s2 / s5;
+        approx_givensrot(a, b, c6, s6);
+    } else {
+        S a = c2 * conj_(c1);
+        double b = -s2;
+        S r6;
+        givensrot(a, b, c6, s6, r6);
+    }
+}
+
+// transformations.jl:208-229 -- turnover(Q1@i, Q2@j, Q3@i) -> R1@j, R2@i, R3@j.
+template <class S>
+static inline void turnover(Rot<S> q1, Rot<S> q2, Rot<S> q3, Rot<S>& r1, Rot<S>& r2, Rot<S>& r3, Stats& st) {
+    ++st.turnovers;
+    turnover_core<S>(q1.c, q1.s, q2.c, q2.s, q3.c, q3.s, r1.c, r1.s, r2.c, r2.s, r3.c, r3.s);
+}
+
+// ------------------------------------------------------------------ factorization state
+// One rank-one R factor (rfactorization.jl:70-74): Ct ascending, B descending, D diagonal.
+// All arrays are indexed by ROTATOR INDEX 1..N (slot 0 unused); the reference stores Ct reversed
+// (chains.jl:41-44), which is storage only.
+template <class S> struct RankOne {
+    int N = 0;
+    std::vector<Rot<S>> Ct, B;
+    std::vector<S> D;  // complex only, 1..N+1 (diagonal.jl:12-18: empty == identity for real)
+    void init(int n) {
+        N = n; Ct.assign(n + 2, Rot<S>{S(1.0), 0.0}); B.assign(n + 2, Rot<S>{S(1.0), 0.0});
+        if (!is_real<S>::value) D.assign(n + 3, S(1.0));
+    }
+    S d(int k) const { if constexpr (is_real<S>::value) return 1.0; else return D[k]; }
+};
+
+template <class S> struct State {  // QRFactorization (qrfactorization.jl:15-18)
+    int N = 0;                     // degree; Q has N-1 rotators, R factors have N
+    std::vector<Rot<S>> Q;         // descending chain, 1..N-1
+    std::vector<S> DQ;             // complex only 1..N (qfactorization.jl:44)
+    RankOne<S> V;                  // R = V (rank one) or V * W^{-1} (pencil.jl:13-16)
+    RankOne<S> W;
+    bool pencil = false;
+    S dq(int k) const { if constexpr (is_real<S>::value) return 1.0; else return DQ[k]; }
+    int nq() const { return N - 1; }
+};
+
+struct Counter {  // AMRVW_algorithm.jl:142-148
+    int zero_index, start_index, stop_index, it_count, tr;
+};
+
+// ------------------------------------------------------------------ matrix entries
+// rfactorization.jl:83-97
+template <class S> static inline S w_entry(const RankOne<S>& RF, int j, int k) {
+    S ck = RF.B[k].c; double sk = RF.B[k].s;
+    if (j == k) return S(-sk);
+    S cj = RF.B[j].c;
+    double s = 1.0;
+    for (int i = j + 1; i <= k - 1; ++i) s *= RF.B[i].s;
+    return conj_(cj) * s * ck;
+}
+// rfactorization.jl:139-170
+template <class S> static inline S r_entry(const RankOne<S>& RF, int j, int k) {
+    int N = RF.N;
+    if (k < j || j == 0 || k > N + 1) return S(0.0);
+    S cj = RF.Ct[j].c; double s = RF.Ct[j].s;
+    double par = -1;
+    S dk = RF.d(k);
+    S w = w_entry(RF, j, k) * dk;
+    S tot = w / s;
+    for (int i = j + 1; i <= k; ++i) {
+        w = w_entry(RF, i, k);
+        S ci = RF.Ct[i].c; double si = RF.Ct[i].s;
+        s = s * si;
+        tot = tot + par * cj * conj_(ci) / s * w * dk;
+        par *= -1;
+    }
+    return tot;
+}
+// pencil.jl:29-45 -- entries of V * W^{-1}
+template <class S> static inline S r_entry(const State<S>& st, int l, int k) {
+    if (!st.pencil) return r_entry(st.V, l, k);
+    const RankOne<S>& V = st.V; const RankOne<S>& W = st.W;
+    int delta = k - l;
+    if (l <= 0) return S(0.0);
+    if (delta == 0) return r_entry(V, k, k) / r_entry(W, k, k);
+    if (delta == 1) {
+        int j = l;
+        return -r_entry(V, j, j) * r_entry(W, j, k) / (r_entry(W, j, j) * r_entry(W, k, k)) + r_entry(V, j, k) / r_entry(W, k, k);
+    }
+    int i = l, j = l + 1;
+    return r_entry(V, i, i) * (r_entry(W, i, j) * r_entry(W, j, k) - r_entry(W, i, k) * r_entry(W, j, j)) /
+               (r_entry(W, i, i) * r_entry(W, j, j) * r_entry(W, k, k)) -
+           (r_entry(V, i, j) * r_entry(W, j, k)) / (r_entry(W, j, j) * r_entry(W, k, k)) + r_entry(V, i, k) / r_entry(W, k, k);
+}
+// chains.jl:109-158 -- entry (i,j) of a descending chain of nq rotators.
+template <class S> static inline S qchain_entry(const State<S>& st, int i, int j) {
+    int N = st.nq();
+    const std::vector<Rot<S>>& x = st.Q;
+    if (i > j + 1 || i <= 0 || j <= 0) return S(0.0);
+    if (j == N + 1) {
+        j -= 1;
+        S cj = x[j].c; double sj = x[j].s;
+        if (i == N + 1) return conj_(cj);
+        i -= 1;
+        double s = sj;
+        for (int l = i + 1; l <= j - 1; ++l) s *= x[l].s;
+        S ci = i > 0 ? x[i].c : S(1.0);
+        return s * conj_(ci);
+    }
+    S cj = x[j].c; double sj = x[j].s;
+    if (i == j + 1) return S(-sj);
+    if (j == i) {
+        S ci = i >= 2 ? x[i - 1].c : S(1.0);
+        return conj_(ci) * cj;
+    }
+    double s = 1.0;
+    for (int l = i; l <= j - 1; ++l) s *= x[l].s;
+    S cl = i >= 2 ? x[i - 1].c : S(1.0);
+    return cj * s * conj_(cl);
+}
+// qfactorization.jl:67-70
+template <class S> static inline S q_entry(const State<S>& st, int j, int k) {
+    if (j <= 0 || k <= 0) return S(0.0);
+    return qchain_entry(st, j, k) * st.dq(k);
+}
+// diagonal-block.jl:12-36 -- A = (Q*R)[j:j+1, j:j+1]
+template <class S> static inline void diagonal_block(const State<S>& st, int j, S A[4]) {
+    int i = j - 1, k = j + 1;
+    S qji = q_entry(st, j, i), qjj = q_entry(st, j, j), qjk = q_entry(st, j, k), qkj = q_entry(st, k, j), qkk = q_entry(st, k, k);
+    S rjj = r_entry(st, j, j), rjk = r_entry(st, j, k), rkk = r_entry(st, k, k);
+    S rij, rik;
+    if (i >= 1) { rij = r_entry(st, i, j); rik = r_entry(st, i, k); }
+    else { rij = S(0.0) * rkk; rik = S(0.0) * rkk; }
+    A[0] = qji * rij + qjj * rjj;              // A11
+    A[1] = qji * rik + qjj * rjk + qjk * rkk;  // A12
+    A[2] = qkj * rjj;                          // A21
+    A[3] = qkj * rjk + qkk * rkk;              // A22
+}
+
+// utils.jl:130-140 -- qdrtc(b,c): roots of x^2 - 2bx + c.
+static inline void qdrtc(double b, double c, double& e1r, double& e1i, double& e2r, double& e2i) {
+    double d = b * b - c;
+    if (d <= 0) {
+        e1r = b; e1i = std::sqrt(-d); e2r = b; e2i = -e1i;
+    } else {
+        double r = std::sqrt(d) * (sign_(b) + (b == 0 ? 1.0 : 0.0)) + b;
+        e1r = r; e1i = 0.0; e2r = c / r; e2i = 0.0;
+    }
+}
+// diagonal-block.jl:117-124
+static inline void eigen_values(const double A[4], cplx& e1, cplx& e2) {
+    double b = (A[0] + A[3]) / 2;
+    double c = A[0] * A[3] - A[1] * A[2];
+    qdrtc(b, c, e1.re, e1.im, e2.re, e2.im);
+}
+// diagonal-block.jl:127-142
+static inline void eigen_values(const cplx A[4], cplx& e1, cplx& e2) {
+    cplx tr = A[0] + A[3];
+    cplx detm = A[0] * A[3] - A[2] * A[1];
+    cplx disc = csqrt_(tr * tr - 4.0 * detm);
+    cplx u = abs_(tr + disc) > abs_(tr - disc) ? tr + disc : tr - disc;
+    if (iszero_(u)) { e1 = cplx(0, 0); e2 = cplx(0, 0); return; }
+    e1 = u / 2.0;
+    e2 = detm / e1;
+}
+
+// ------------------------------------------------------------------ passthroughs (chains.jl:360-400)
+// passthrough!(A::DescendingChain, U): U@i right->left, leaves at i+1 (chains.jl:360-368)
+template <class S> static inline void pass_desc(std::vector<Rot<S>>& X, Rot<S>& U, int& i, Stats& st) {
+    Rot<S> r1, r2, r3;
+    turnover(X[i], X[i + 1], U, r1, r2, r3, st);
+    U = r1; X[i] = r2; X[i + 1] = r3; i += 1;
+}
+// passthrough!(A::AscendingChain, U): U@i right->left, leaves at i-1 (chains.jl:370-378)
+template <class S> static inline void pass_asc(std::vector<Rot<S>>& X, Rot<S>& U, int& i, Stats& st) {
+    Rot<S> r1, r2, r3;
+    turnover(X[i], X[i - 1], U, r1, r2, r3, st);
+    U = r1; X[i] = r2; X[i - 1] = r3; i -= 1;
+}
+// passthrough!(U, A::DescendingChain): U@i left->right, leaves at i-1 (chains.jl:381-389)
+template <class S> static inline void pass_desc_lr(Rot<S>& U, std::vector<Rot<S>>& X, int& i, Stats& st) {
+    Rot<S> r1, r2, r3;
+    turnover(U, X[i - 1], X[i], r1, r2, r3, st);
+    X[i - 1] = r1; X[i] = r2; U = r3; i -= 1;
+}
+// passthrough!(U, A::AscendingChain): U@i left->right, leaves at i+1 (chains.jl:391-400)
+template <class S> static inline void pass_asc_lr(Rot<S>& U, std::vector<Rot<S>>& X, int& i, Stats& st) {
+    Rot<S> r1, r2, r3;
+    turnover(U, X[i + 1], X[i], r1, r2, r3, st);
+    X[i + 1] = r1; X[i] = r2; U = r3; i += 1;
+}
+// diagonal.jl:84-96 (complex) / :113-118 (real, empty diagonal: no-op)
+template <class S> static inline void pass_diag(std::vector<S>& D, Rot<S>& U, int i) {
+    if constexpr (!is_real<S>::value) {
+        S alpha = D[i], beta = D[i + 1];
+        S beta1 = alpha * conj_(beta);
+        D[i] = beta; D[i + 1] = alpha;
+        U.c = beta1 * U.c;
+    }
+}
+// rfactorization.jl:198-206 -- passthrough!(RF, U): D, then B, then Ct; index returns to i.
+template <class S> static inline void pass_rankone(RankOne<S>& RF, Rot<S>& U, int& i, Stats& st) {
+    pass_diag(RF.D, U, i);
+    pass_desc(RF.B, U, i, st);
+    pass_asc(RF.Ct, U, i, st);
+}
+// rfactorization.jl:208-216 -- passthrough!(U, RF): Ct, then B, then D.
+template <class S> static inline void pass_rankone_lr(Rot<S>& U, RankOne<S>& RF, int& i, Stats& st) {
+    pass_asc_lr(U, RF.Ct, i, st);
+    pass_desc_lr(U, RF.B, i, st);
+    pass_diag(RF.D, U, i);  // diagonal.jl:100-101: passthrough!(U, D) returns passthrough!(D, U)
+}
+// passthrough!(RF, U) for rank one (rfactorization.jl:198) or pencil (pencil.jl:63-71)
+template <class S> static inline void pass_R(State<S>& s, Rot<S>& U, int& i, Stats& st) {
+    if (s.pencil) {
+        Rot<S> Ut = adjoint(U);
+        pass_rankone_lr(Ut, s.W, i, st);
+        U = adjoint(Ut);
+    }
+    pass_rankone(s.V, U, i, st);
+}
+// qfactorization.jl:86-91 -- passthrough!(QF, U): D then Q.
+template <class S> static inline void pass_Q(State<S>& s, Rot<S>& U, int& i, Stats& st) {
+    pass_diag(s.DQ, U, i);
+    pass_desc(s.Q, U, i, st);
+}
+
+// diagonal.jl:199-225 -- passthrough_phase!(Di(alpha)@i, Q::DescendingChain, D)
+static inline void passthrough_phase(State<cplx>& s, cplx alpha, int i) {
+    int M = s.nq();
+    s.DQ[i] = s.DQ[i] * alpha;
+    while (i < M) {
+        int j = i + 1;
+        if (s.Q[j].s == 0) break;
+        s.Q[j].c = conj_(alpha) * s.Q[j].c;
+        i = i + 1;
+    }
+    s.DQ[i + 1] = s.DQ[i + 1] * conj_(alpha);
+}
+
+// RDS.jl:146-154 get_parity, RDS.jl:169-174 dflip
+static inline double get_parity(const State<double>& s, int k) { return k > s.nq() ? 1.0 : sign_(s.Q[k].c); }
+static inline Rot<double> dflip(Rot<double> a, double d) { return {a.c, sign_(d) * a.s}; }
+
+// ------------------------------------------------------------------ companion set-up (companion.jl)
+// companion.jl:6-24
+template <class S> static std::vector<S> basic_decompose(const S* ps, int len) {
+    int n = len - 1;
+    S p0 = ps[0];
+    S pNi = S(1.0) / ps[n];
+    std::vector<S> qs(n + 2);  // 1-based: qs[1..n+1]
+    double par = (n % 2 == 0) ? 1.0 : -1.0;
+    for (int i = 1; i <= n - 1; ++i) {
+        double sg = ((i + 1) % 2 == 0) ? 1.0 : -1.0;  // (-1)^(i+1)
+        qs[i] = (par * sg) * ps[i] * pNi;              // par * (-1)^(i+1) * ps[i+1] * pNi  (1-based ps)
+    }
+    qs[n] = par * p0 * pNi;
+    qs[n + 1] = S(-1.0);
+    return qs;
+}
+// companion.jl:79-93 (real)
+static void r_factorization(const std::vector<double>& xs, RankOne<double>& RF) {
+    int N = (int)xs.size() - 2;  // xs is 1-based with N+1 entries
+    RF.init(N);
+    double c, s, tmp;
+    givensrot(xs[N], -1.0, c, s, tmp);
+    RF.Ct[N] = {c, -s};   // C'
+    RF.B[N] = {s, -c};    // not the adjoint: Ct_N * B_N = [0 -1; 1 0]
+    for (int i = N - 1; i >= 1; --i) {
+        givensrot(xs[i], tmp, c, s, tmp);
+        RF.Ct[i] = {c, -s};
+        RF.B[i] = {c, s};
+    }
+}
+// companion.jl:97-120 (complex)
+static void r_factorization(const std::vector<cplx>& xs, RankOne<cplx>& RF) {
+    int N = (int)xs.size() - 2;
+    RF.init(N);
+    cplx c, tmp; double s;
+    givensrot(xs[N], cplx(-1.0, 0.0), c, s, tmp);
+    double nrm = abs_(c);
+    cplx alpha = c / nrm;
+    RF.Ct[N] = {conj_(c), -s};
+    RF.B[N] = {s * alpha, -nrm};
+    RF.D[N] = conj_(alpha);
+    RF.D[N + 1] = alpha;
+    for (int i = N - 1; i >= 1; --i) {
+        cplx t2;
+        givensrot(xs[i], tmp, c, s, t2);
+        tmp = t2;
+        RF.Ct[i] = {conj_(c), -s};
+        RF.B[i] = {c, s};
+    }
+}
+// companion.jl:123-137 + qfactorization.jl:41-48
+template <class S> static void q_factorization(State<S>& st, int N) {
+    st.N = N;
+    st.Q.assign(N + 1, Rot<S>{S(0.0), 1.0});
+    if (!is_real<S>::value) st.DQ.assign(N + 2, S(1.0));
+}
+// companion.jl:150-159 -- amrvw(ps)
+template <class S> static void amrvw(const S* ps, int len, State<S>& st) {
+    std::vector<S> xs = basic_decompose(ps, len);
+    q_factorization(st, len - 1);
+    r_factorization(xs, st.V);
+    st.pencil = false;
+}
+// companion.jl:163-204 -- amrvw(vs, ws); does not mutate the caller's arrays (the reference does).
+template <class S> static void amrvw_pencil(const S* vs, const S* ws_in, int N, State<S>& st) {
+    std::vector<S> v1(vs, vs + N);
+    v1.push_back(S(1.0));
+    std::vector<S> ps = basic_decompose(v1.data(), N + 1);
+    std::vector<S> ws(ws_in, ws_in + N);
+    for (int i = N - 1; i >= 1; i -= 2) ws[i - 1] = -ws[i - 1];  // for i in length(ws)-1:-2:1 (1-based)
+    std::vector<S> qs(N + 2);
+    for (int i = 1; i <= N; ++i) qs[i] = ws[i - 1];
+    qs[N + 1] = S(-1.0);
+    q_factorization(st, N);
+    r_factorization(ps, st.V);
+    r_factorization(qs, st.W);
+    st.pencil = true;
+}
+
+// ------------------------------------------------------------------ bulge step, RDS (create-bulge.jl:20-77, RDS.jl)
+struct BulgeR { Rot<double> U, V, W; int iu; };  // storage.VU[2], VU[1], limb[1]; idx(U)=iu, idx(V)=iu+1
+
+static const int IT_COUNT = 15;  // create-bulge.jl:9
+
+// create-bulge.jl:20-77.  If shifts != nullptr they replace the eigenvalues of block(stop)
+// (multishift schedule); otherwise this is the reference.
+static void create_bulge(State<double>& s, Counter& ctr, BulgeR& bg, Rng& rng, Stats& st, const cplx* shifts = nullptr) {
+    int i = ctr.start_index;
+    if (ctr.it_count == 0 && !shifts) {
+        ctr.it_count = IT_COUNT;
+        ++st.exceptional;
+        double t = rng.next() * M_PI;
+        double re1 = std::sin(t), ie1 = std::cos(t);
+        bg.U = {re1, ie1};
+        bg.V = {re1, -ie1};
+    } else {
+        cplx e1, e2;
+        double A[4];
+        if (shifts) { e1 = shifts[0]; e2 = shifts[1]; }
+        else { diagonal_block(s, ctr.stop_index, A); eigen_values(A, e1, e2); }
+        double l1r = e1.re, l1i = e1.im, l2r = e2.re, l2i = e2.im;
+        diagonal_block(s, i, A);
+        double bk11 = A[0], bk12 = A[1], bk21 = A[2], bk22 = A[3];
+        diagonal_block(s, i + 1, A);
+        double bk32 = A[2];
+        double c1 = -l1i * l2i + l1r * l2r - l1r * bk11 - l2r * bk11 + bk11 * bk11 + bk12 * bk21;
+        double c2 = -l1r * bk21 - l2r * bk21 + bk11 * bk21 + bk21 * bk22;
+        double c3 = bk21 * bk32;
+        double c, sn, nrm, tmp;
+        givensrot(c2, c3, c, sn, nrm);
+        bg.V = {c, -sn};
+        givensrot(c1, nrm, c, sn, tmp);
+        bg.U = {c, -sn};
+    }
+    bg.iu = i;
+}
+// RDS.jl:14-36
+static void absorb_Ut(State<double>& s, BulgeR& bg, Stats& st) {
+    int i = bg.iu;
+    Rot<double> Ut = adjoint(bg.U), Vt = adjoint(bg.V);
+    Rot<double> W = s.Q[i];
+    double p = i == 1 ? 1.0 : get_parity(s, i - 1);
+    W = dflip(W, p);
+    Rot<double> r1, r2, r3;
+    turnover(Ut, Vt, W, r1, r2, r3, st);
+    W = r1; Ut = r2; Vt = r3;
+    s.Q[i + 1] = fuse(Vt, s.Q[i + 1]);  // fuse!(Vt, QF)  qfactorization.jl:124-129
+    Ut = dflip(Ut, p);
+    s.Q[i] = Ut;
+    bg.W = W;
+}
+// RDS.jl:42-70 passthrough_triu with RDS.jl:73-88 simple_passthrough!
+static void passthrough_triu(State<double>& s, Counter& ctr, BulgeR& bg, Stats& st) {
+    int j = bg.iu + 1;
+    bool flag = false;
+    if (j <= ctr.tr && !s.pencil) {  // pencil.jl:85-87: simple_passthrough! returns false
+        Rot<double> V = bg.V, U = bg.U;
+        int jv = j, iu = bg.iu;
+        pass_desc(s.V.B, V, jv, st);
+        pass_desc(s.V.B, U, iu, st);
+        for (int k = -1; k <= 1; ++k) s.V.Ct[j + k] = {s.V.B[j + k].c, -s.V.B[j + k].s};
+        flag = true;
+    }
+    if (j > ctr.tr || !flag) {
+        int jv = j, iu = bg.iu;
+        pass_R(s, bg.V, jv, st);
+        pass_R(s, bg.U, iu, st);
+    }
+    ctr.tr -= 2;
+}
+// RDS.jl:97-131; returns true when the bulge has been absorbed.
+static bool passthrough_Q(State<double>& s, Counter& ctr, BulgeR& bg, Stats& st) {
+    int i = bg.iu, j = i + 1;
+    if (j < ctr.stop_index) {
+        int jv = j, iu = i;
+        pass_Q(s, bg.V, jv, st);
+        pass_Q(s, bg.U, iu, st);
+        Rot<double> r1, r2, r3;
+        turnover(bg.W, bg.V, bg.U, r1, r2, r3, st);
+        bg.V = r1; bg.U = r2; bg.W = r3;
+        bg.iu = i + 1;
+        return false;
+    }
+    double p = get_parity(s, j + 1);
+    bg.V = dflip(bg.V, p);
+    s.Q[j] = fuse(s.Q[j], bg.V);  // fuse!(QF, V)  qfactorization.jl:117-122
+    int iu = i;
+    pass_desc(s.Q, bg.U, iu, st);  // passthrough!(QF.Q, U)
+    Rot<double> U = fuse(bg.W, bg.U);
+    pass_R(s, U, iu, st);
+    p = get_parity(s, iu + 1);
+    U = dflip(U, p);
+    s.Q[iu] = fuse(s.Q[iu], U);
+    return true;
+}
+// bulge-step.jl:11-19, 36-49
+static void bulge_step(State<double>& s, Counter& ctr, Rng& rng, Stats& st, const cplx* shifts = nullptr) {
+    BulgeR bg;
+    ++st.sweeps;
+    create_bulge(s, ctr, bg, rng, st, shifts);
+    absorb_Ut(s, bg, st);
+    bool flag = false;
+    while (!flag) {
+        passthrough_triu(s, ctr, bg, st);
+        flag = passthrough_Q(s, ctr, bg, st);
+    }
+}
+// RDS.jl:134-141
+static void deflate(State<double>& s, int k) { s.Q[k] = {sign_(s.Q[k].c), 0.0}; }
+
+// ------------------------------------------------------------------ bulge step, CSS (create-bulge.jl:80-118, CSS.jl)
+static void bulge_step(State<cplx>& s, Counter& ctr, Rng& rng, Stats& st, const cplx* shifts = nullptr) {
+    ++st.sweeps;
+    cplx A[4];
+    cplx shift;
+    if (ctr.it_count == 0 && !shifts) {  // create-bulge.jl:85-93 (ray = true)
+        ctr.it_count = IT_COUNT;
+        ++st.exceptional;
+        double t = rng.next() * M_PI;
+        shift = cplx(std::cos(t), std::sin(t));
+    } else if (shifts) {
+        shift = shifts[0];
+    } else {  // Wilkinson shift, create-bulge.jl:95-103
+        diagonal_block(s, ctr.stop_index, A);
+        cplx e1, e2;
+        eigen_values(A, e1, e2);
+        shift = abs_(A[3] - e1) < abs_(A[3] - e2) ? e1 : e2;
+    }
+    int i = ctr.start_index;
+    diagonal_block(s, i, A);
+    cplx c, nrm; double sn;
+    givensrot(A[0] - shift, A[2], c, sn, nrm);
+    Rot<cplx> R = {c, sn};
+    Rot<cplx> U = adjoint(R);  // storage.VU[1] = R'
+    // absorb_Ut, CSS.jl:8-14: fuse!(Ut, QF) (qfactorization.jl:143-149)
+    {
+        cplx dph;
+        s.Q[i] = fuse(adjoint(U), s.Q[i], dph);
+        passthrough_phase(s, dph, i);
+    }
+    // absorb_U, bulge-step.jl:36-49
+    bool done = false;
+    while (!done) {
+        // passthrough_triu, CSS.jl:17-41 with simple_passthrough! CSS.jl:45-61
+        bool flag = false;
+        if (i < ctr.tr && !s.pencil) {
+            Rot<cplx> Uc = U; int iu = i;
+            pass_desc(s.V.B, Uc, iu, st);
+            for (int k = 0; k <= 1; ++k) s.V.Ct[i + k] = {conj_(s.V.B[i + k].c), -s.V.B[i + k].s};
+            flag = true;
+        }
+        if (i > ctr.tr || !flag) { int iu = i; pass_R(s, U, iu, st); }
+        ctr.tr -= 1;
+        // passthrough_Q, CSS.jl:64-88
+        if (i < ctr.stop_index) {
+            pass_Q(s, U, i, st);
+        } else {
+            pass_diag(s.DQ, U, i);
+            cplx dph;  // fuse!(QF, U) qfactorization.jl:131-141
+            s.Q[i] = fuse(s.Q[i], U, dph);
+            s.DQ[i] = s.DQ[i] * dph;
+            s.DQ[i + 1] = s.DQ[i + 1] * conj_(dph);
+            done = true;
+        }
+    }
+}
+// CSS.jl:98-122
+static void deflate(State<cplx>& s, int k) {
+    cplx alpha = s.Q[k].c;
+    s.Q[k] = {cplx(1.0, 0.0), 0.0};
+    passthrough_phase(s, alpha, k);
+}
+
+// ------------------------------------------------------------------ driver (AMRVW_algorithm.jl)
+static const double EPS = 2.220446049250313e-16;
+
+// AMRVW_algorithm.jl:181-202
+template <class S> static void check_deflation(State<S>& s, Counter& ctr) {
+    for (int k = ctr.stop_index; k >= ctr.start_index; --k) {
+        if (std::fabs(s.Q[k].s) <= EPS) {
+            deflate(s, k);
+            ctr.zero_index = k;
+            ctr.start_index = k + 1;
+            ctr.it_count = 15;
+            return;
+        }
+    }
+}
+
+static inline cplx to_c(double x) { return cplx(x, 0.0); }
+static inline cplx to_c(cplx x) { return x; }
+static inline void eig2(const double A[4], cplx& e1, cplx& e2) { eigen_values(A, e1, e2); }
+static inline void eig2(const cplx A[4], cplx& e1, cplx& e2) { eigen_values(A, e1, e2); }
+
+// Julia's LinearAlgebra.sorteig!: sort by (real, imag)   (AMRVW_algorithm.jl:134)
+static inline bool isless_(double a, double b) {  // Base.isless: total order, -0.0 < 0.0, NaN last
+    if (std::isnan(a)) return false;
+    if (std::isnan(b)) return true;
+    return a < b || (a == b && std::signbit(a) && !std::signbit(b));
+}
+static inline bool isequal_(double a, double b) { return (a == b && std::signbit(a) == std::signbit(b)) || (std::isnan(a) && std::isnan(b)); }
+static inline bool eig_less(const cplx& a, const cplx& b) { return isless_(a.re, b.re) || (isequal_(a.re, b.re) && isless_(a.im, b.im)); }
+
+// AMRVW_algorithm.jl:10-138 restricted to eigenvalue slots lo..hi+1, assuming Q[lo-1] is
+// diagonal (or lo == 1).  lo = 1, hi = N-1 is the reference driver.  EIGS is 1-based.
+// Returns true if finished (every slot written).
+template <class S>
+static bool driver_window(State<S>& s, int lo, int /*hi*/, Counter& ctr, std::vector<cplx>& EIGS, Rng& rng, Stats& st, int64_t it_max) {
+    int64_t kk = 0;
+    S A[4];
+    check_deflation(s, ctr);
+    while (kk <= it_max) {
+        if (ctr.stop_index < lo) return true;
+        check_deflation(s, ctr);
+        ++kk; ++st.trips;
+        int k = ctr.stop_index;
+        int delta = ctr.stop_index - ctr.zero_index;
+        if (delta == 1) {
+            diagonal_block(s, k, A);
+            cplx e1, e2;
+            eig2(A, e1, e2);
+            EIGS[k] = e1; EIGS[k + 1] = e2;
+            if (ctr.stop_index == lo + 1) {
+                diagonal_block(s, lo, A);
+                EIGS[lo] = to_c(A[0]);
+                ctr.stop_index = lo - 1;
+                return true;
+            }
+            ctr.stop_index = ctr.zero_index - 1;
+            ctr.zero_index = lo - 1;
+            ctr.start_index = lo;
+            check_deflation(s, ctr);
+            if (ctr.stop_index < lo) return true;
+        } else if (delta <= 0) {
+            diagonal_block(s, k, A);
+            if (ctr.stop_index == lo) {
+                EIGS[lo] = to_c(A[0]); EIGS[lo + 1] = to_c(A[3]);
+                ctr.stop_index = lo - 1;
+                return true;
+            }
+            EIGS[k + 1] = to_c(A[3]);
+            ctr.stop_index = ctr.zero_index - 1;
+            if (ctr.stop_index < lo) return true;
+            ctr.zero_index = lo - 1;
+            ctr.start_index = lo;
+            check_deflation(s, ctr);
+        } else {
+            bulge_step(s, ctr, rng, st);
+            ctr.it_count -= 1;
+        }
+    }
+    return ctr.stop_index < lo;
+}
+
+template <class S>
+static void amrvw_algorithm(State<S>& s, std::vector<cplx>& EIGS, Rng& rng, Stats& st) {
+    int n = s.nq();
+    Counter ctr = {0, 1, n, IT_COUNT, n - 1};  // AMRVW_algorithm.jl:18
+    EIGS.assign(n + 2, cplx(0, 0));
+    int64_t it_max = 20 * (int64_t)n;          // :25
+    bool ok = driver_window(s, 1, n, ctr, EIGS, rng, st, it_max);
+    if (!ok) st.unconverged += std::max(0, ctr.stop_index + 1);
+    std::sort(EIGS.begin() + 1, EIGS.begin() + n + 2, eig_less);
+}
+
+// ------------------------------------------------------------------ MS: multishift schedule (GPU pipelined kernel's order of work)
+// NOT in the reference.  Same rotator operations; for windows larger than `small` each "fat step"
+// takes L shift pairs -- the eigenvalues of the trailing 2L x 2L block of the active window,
+// obtained by running the reference driver on a scratch copy whose top rotator is made diagonal --
+// and chases L bulges with them one after another (on the GPU: pipelined, three indices apart,
+// which commutes exactly with this sequential order).  Smaller windows use the reference step.
+struct MsParams { int L = 8; int small = 24; int reuse = 1; /* each shift pair drives `reuse` bulges */ };
+
+static void ms_shifts(const State<double>& s, const Counter& ctr, int m, std::vector<cplx>& sh, Rng& rng, Stats& st_sub) {
+    // scratch copy; window [k+1, stop] with Q[k] made diagonal
+    State<double> t = s;
+    int stop = ctr.stop_index, k = stop - m;
+    t.Q[k] = {sign_(t.Q[k].c) == 0 ? 1.0 : sign_(t.Q[k].c), 0.0};
+    Counter c2 = {k, k + 1, stop, IT_COUNT, 0 /* tr: simple passthrough never applies */};
+    std::vector<cplx> E(s.N + 2, cplx(0, 0));
+    driver_window(t, k + 1, stop, c2, E, rng, st_sub, 20 * (int64_t)m);
+    sh.assign(E.begin() + k + 1, E.begin() + stop + 2);  // m eigenvalues, slots k+1..stop+1
+}
+
+static void ms_pair_shifts(std::vector<cplx>& sh, std::vector<cplx>& pairs) {
+    // Real double shift needs conjugate-closed pairs: complex pairs stay together (they leave the
+    // 2x2 solver adjacent and exactly conjugate), real ones are paired in order; an odd real
+    // left over is used twice.
+    pairs.clear();
+    std::vector<cplx> reals;
+    for (size_t i = 0; i < sh.size(); ++i) {
+        if (sh[i].im != 0 && i + 1 < sh.size() && sh[i + 1].im == -sh[i].im && sh[i + 1].re == sh[i].re) {
+            pairs.push_back(sh[i]); pairs.push_back(sh[i + 1]); ++i;
+        } else if (sh[i].im != 0) {  // unpaired complex (should not happen): use it with its conjugate
+            pairs.push_back(sh[i]); pairs.push_back(conj_(sh[i]));
+        } else reals.push_back(sh[i]);
+    }
+    for (size_t i = 0; i + 1 < reals.size(); i += 2) { pairs.push_back(reals[i]); pairs.push_back(reals[i + 1]); }
+    if (reals.size() % 2) { pairs.push_back(reals.back()); pairs.push_back(reals.back()); }
+}
+
+static void amrvw_algorithm_ms(State<double>& s, std::vector<cplx>& EIGS, Rng& rng, Stats& st, MsParams P) {
+    int n = s.nq();
+    Counter ctr = {0, 1, n, IT_COUNT, -1 /* the GPU kernels never take the simple passthrough */};
+    EIGS.assign(n + 2, cplx(0, 0));
+    int64_t it_max = 20 * (int64_t)n, kk = 0;
+    double A[4];
+    const int lo = 1;
+    check_deflation(s, ctr);
+    while (kk <= it_max) {
+        if (ctr.stop_index < lo) break;
+        check_deflation(s, ctr);
+        ++kk; ++st.trips;
+        int k = ctr.stop_index;
+        int delta = ctr.stop_index - ctr.zero_index;
+        if (delta == 1) {
+            diagonal_block(s, k, A);
+            cplx e1, e2; eig2(A, e1, e2);
+            EIGS[k] = e1; EIGS[k + 1] = e2;
+            if (ctr.stop_index == lo + 1) { diagonal_block(s, lo, A); EIGS[lo] = to_c(A[0]); ctr.stop_index = 0; break; }
+            ctr.stop_index = ctr.zero_index - 1; ctr.zero_index = 0; ctr.start_index = 1;
+            check_deflation(s, ctr);
+            if (ctr.stop_index < lo) break;
+        } else if (delta <= 0) {
+            diagonal_block(s, k, A);
+            if (ctr.stop_index == lo) { EIGS[lo] = to_c(A[0]); EIGS[lo + 1] = to_c(A[3]); ctr.stop_index = 0; break; }
+            EIGS[k + 1] = to_c(A[3]);
+            ctr.stop_index = ctr.zero_index - 1;
+            if (ctr.stop_index < lo) break;
+            ctr.zero_index = 0; ctr.start_index = 1;
+            check_deflation(s, ctr);
+        } else if (delta <= P.small || ctr.it_count == 0) {
+            int64_t t0 = st.turnovers;
+            bulge_step(s, ctr, rng, st);
+            st.serial_turnovers += st.turnovers - t0;
+            ctr.it_count -= 1;
+        } else {
+            int m = std::min(2 * P.L / P.reuse, delta - 1);
+            m -= m % 2;
+            std::vector<cplx> sh, pairs;
+            Stats sub;
+            ms_shifts(s, ctr, m, sh, rng, sub);
+            st.turnovers += sub.turnovers;  // executed work; kept separately from the reference count by the caller
+            st.serial_turnovers += sub.turnovers;
+            st.pipe_steps += (ctr.stop_index - ctr.start_index + 1) + 3 * (P.L - 1);
+            ms_pair_shifts(sh, pairs);
+            ++st.fat_steps;
+            for (int rep = 0; rep < P.reuse; ++rep)
+                for (size_t b = 0; b + 1 < pairs.size(); b += 2) bulge_step(s, ctr, rng, st, &pairs[b]);
+            ctr.it_count -= 1;
+        }
+    }
+    if (ctr.stop_index >= lo) st.unconverged += ctr.stop_index + 1;
+    std::sort(EIGS.begin() + 1, EIGS.begin() + n + 2, eig_less);
+}
+
+// ------------------------------------------------------------------ roots (companion.jl:252-303, utils.jl)
+// utils.jl:100-128 -- qdrtc(a,b,c) with discr
+static inline double discr(double a, double b, double c) {
+    double pie = 3.0;
+    double d = b * b - a * c;
+    double e = b * b + a * c;
+    if (pie * std::fabs(d) > e) return d;
+    double p = b * b;
+    double dp = std::fma(b, b, -p);
+    double q = a * c;
+    double dq = std::fma(a, c, -q);
+    return (p - q) + (dp - dq);
+}
+static inline void qdrtc3(double a, double b, double c, double out[4]) {
+    double d = discr(a, b, c);
+    if (d <= 0) {
+        double r = b / a, s = std::sqrt(-d) / a;
+        out[0] = r; out[1] = s; out[2] = r; out[3] = -s;
+    } else {
+        double r = std::sqrt(d) * (sign_(b) + (b == 0 ? 1.0 : 0.0)) + b;
+        out[0] = r / a; out[1] = 0.0; out[2] = c / r; out[3] = 0.0;
+    }
+}
+// utils.jl:63-79 solve_simple_cases (N = number of coefficients <= 3)
+static int solve_simple_cases(const double* ps, int N, cplx* out) {
+    if (N <= 1) return 0;
+    if (N == 2) { out[0] = cplx(-ps[0] / ps[1], 0.0); return 1; }
+    double o[4];
+    qdrtc3(ps[2], -ps[1] / 2, ps[0], o);  // quadratic_equation(a,b,c) = qdrtc(a, -b/2, c), utils.jl:83-85
+    out[0] = cplx(o[0], o[1]); out[1] = cplx(o[2], o[3]);
+    return 2;
+}
+static int solve_simple_cases(const cplx* ps, int N, cplx* out) {
+    if (N <= 1) return 0;
+    if (N == 2) { out[0] = -ps[0] / ps[1]; return 1; }
+    cplx c = ps[0], b = ps[1], a = ps[2];  // utils.jl:88-94
+    cplx d = csqrt_(b * b - 4.0 * a * c);
+    out[0] = (-b + d) / (2.0 * a);
+    out[1] = (-b - d) / (2.0 * a);
+    return 2;
+}
+
+enum Schedule { SCHED_REFERENCE = 0, SCHED_MULTISHIFT = 1 };
+
+// roots(ps) companion.jl:252-272.  `out` receives len-1 roots... precisely: (trimmed degree) roots
+// sorted by (re,im) followed by K zeros; slots beyond (for trailing zero coefficients, which lower
+// the degree) are left untouched and *nroots tells how many were produced.
+template <class S>
+static void roots_one(const S* ps_in, int len, cplx* out, int* nroots, uint64_t seed, uint64_t poly, Stats& st, int sched, MsParams P) {
+    // utils.jl:14-22 deflate_leading_zeros
+    int first = -1, last = -1;
+    for (int i = 0; i < len; ++i) if (!iszero_(ps_in[i])) { if (first < 0) first = i; last = i; }
+    if (first < 0) { *nroots = 0; return; }
+    const S* ps = ps_in + first;
+    int n = last - first + 1;  // number of coefficients kept
+    int K = first;             // zero roots
+    int cnt = 0;
+    if (n <= 3) {
+        cnt = solve_simple_cases(ps, n, out);
+    } else {
+        State<S> s;
+        amrvw(ps, n, s);
+        std::vector<cplx> E;
+        Rng rng; rng.seed = seed; rng.poly = poly;
+        if constexpr (is_real<S>::value) {
+            if (sched == SCHED_MULTISHIFT) amrvw_algorithm_ms(s, E, rng, st, P);
+            else amrvw_algorithm(s, E, rng, st);
+        } else amrvw_algorithm(s, E, rng, st);
+        cnt = n - 1;
+        for (int i = 0; i < cnt; ++i) out[i] = E[i + 1];
+    }
+    for (int i = 0; i < K; ++i) out[cnt + i] = cplx(0, 0);
+    *nroots = cnt + K;
+}
+
+// utils.jl:29-58 deflate_leading_zeros(vs, ws) on copies + roots(vs, ws) companion.jl:282-303
+template <class S>
+static void roots_pencil_one(const S* vs_in, const S* ws_in, int N0, cplx* out, int* nroots, uint64_t seed, uint64_t poly, Stats& st) {
+    if (N0 <= 0) { *nroots = 0; return; }
+    std::vector<S> vs(vs_in, vs_in + N0), ws(ws_in, ws_in + N0);  // 0-based copies; reference is 1-based
+    int N = N0;
+    if (iszero_(ws[N0 - 1])) {
+        N -= 1;
+        while (N >= 1) {
+            S ai = vs[N] + ws[N - 1];  // vs[N+1] + ws[N]
+            if (!iszero_(ai)) { ws[N - 1] = ai; break; }
+            N -= 1;
+        }
+    }
+    int K = 1;
+    if (iszero_(vs[0])) {
+        K = 2;
+        while (K <= N) {
+            S ai = vs[K - 1] + ws[K - 2];
+            if (!iszero_(ai)) { vs[K - 1] = ai; break; }
+            K += 1;
+        }
+    }
+    int len = N - K + 1;  // vs[K:N]
+    int Kz = K - 1;
+    int cnt = 0;
+    if (len <= 0) { *nroots = 0; return; }  // all-zero input (the reference would throw on empty slices)
+    const S* ps = vs.data() + (K - 1);
+    const S* qs = ws.data() + (K - 1);
+    if (len <= 2) {
+        // rs = vcat(ps, 0) + vcat(0, qs); roots(rs)   companion.jl:288-293
+        std::vector<S> rs(len + 1, S(0.0));
+        for (int i = 0; i < len; ++i) { rs[i] = rs[i] + ps[i]; rs[i + 1] = rs[i + 1] + qs[i]; }
+        int c2 = 0;
+        roots_one<S>(rs.data(), len + 1, out, &c2, seed, poly, st, SCHED_REFERENCE, MsParams());
+        cnt = c2;
+    } else {
+        State<S> s;
+        amrvw_pencil(ps, qs, len, s);
+        std::vector<cplx> E;
+        Rng rng; rng.seed = seed; rng.poly = poly;
+        amrvw_algorithm(s, E, rng, st);
+        cnt = len;
+        for (int i = 0; i < cnt; ++i) out[i] = E[i + 1];
+    }
+    for (int i = 0; i < Kz; ++i) out[cnt + i] = cplx(0, 0);
+    *nroots = cnt + Kz;
+}
+
+// ------------------------------------------------------------------ flat-array state (tests)
+template <class S> static void state_to_flat(const State<S>& s, double* buf);
+static inline void put(double*& p, double x) { *p++ = x; }
+static inline void put(double*& p, cplx x) { *p++ = x.re; *p++ = x.im; }
+static inline void get(const double*& p, double& x) { x = *p++; }
+static inline void get(const double*& p, cplx& x) { x.re = *p++; x.im = *p++; }
+
+// layout (in doubles; S-values take 1 (real) or 2 (complex) doubles):
+//   Q: (c,s) x (N-1) | V.B: (c,s) x N | V.Ct: (c,s) x N | [W.B | W.Ct if pencil] | [DQ x N | V.D x (N+1) | W.D x (N+1) if complex]
+template <class S> static int64_t flat_size(int N, bool pencil) {
+    int w = is_real<S>::value ? 1 : 2;
+    int64_t rot = w + 1;
+    int64_t sz = rot * (N - 1) + rot * N * 2 * (pencil ? 2 : 1);
+    if (!is_real<S>::value) sz += 2 * (N + (N + 1) * (pencil ? 2 : 1));
+    return sz;
+}
+template <class S> static void state_to_flat(const State<S>& s, double* buf) {
+    double* p = buf; int N = s.N;
+    for (int i = 1; i <= N - 1; ++i) { put(p, s.Q[i].c); put(p, s.Q[i].s); }
+    auto chain = [&](const std::vector<Rot<S>>& X) { for (int i = 1; i <= N; ++i) { put(p, X[i].c); put(p, X[i].s); } };
+    chain(s.V.B); chain(s.V.Ct);
+    if (s.pencil) { chain(s.W.B); chain(s.W.Ct); }
+    if constexpr (!is_real<S>::value) {
+        for (int i = 1; i <= N; ++i) put(p, s.DQ[i]);
+        for (int i = 1; i <= N + 1; ++i) put(p, s.V.D[i]);
+        if (s.pencil) for (int i = 1; i <= N + 1; ++i) put(p, s.W.D[i]);
+    }
+}
+template <class S> static void flat_to_state(const double* buf, int N, bool pencil, State<S>& s) {
+    const double* p = buf;
+    q_factorization(s, N);
+    s.pencil = pencil; s.V.init(N); if (pencil) s.W.init(N);
+    for (int i = 1; i <= N - 1; ++i) { get(p, s.Q[i].c); get(p, s.Q[i].s); }
+    auto chain = [&](std::vector<Rot<S>>& X) { for (int i = 1; i <= N; ++i) { get(p, X[i].c); get(p, X[i].s); } };
+    chain(s.V.B); chain(s.V.Ct);
+    if (pencil) { chain(s.W.B); chain(s.W.Ct); }
+    if constexpr (!is_real<S>::value) {
+        for (int i = 1; i <= N; ++i) get(p, s.DQ[i]);
+        for (int i = 1; i <= N + 1; ++i) get(p, s.V.D[i]);
+        if (pencil) for (int i = 1; i <= N + 1; ++i) get(p, s.W.D[i]);
+    }
+}
+
+}  // namespace orc
+
+// =====================================================================================
+// C ABI of the oracle (ctypes; tests and bench's CPU legs only)
+// =====================================================================================
+using namespace orc;
+
+extern "C" {
+
+struct orc_stats { int64_t turnovers, sweeps, exceptional, trips, unconverged, fat_steps, serial_turnovers, pipe_steps; };
+static void add_stats(orc_stats* o, const Stats& s) {
+    if (!o) return;
+    o->turnovers += s.turnovers; o->sweeps += s.sweeps; o->exceptional += s.exceptional;
+    o->trips += s.trips; o->unconverged += s.unconverged; o->fat_steps += s.fat_steps;
+    o->serial_turnovers += s.serial_turnovers; o->pipe_steps += s.pipe_steps;
+}
+
+int orc_num_threads() {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+// Batched roots, CSR layout: polynomial p has coefficients coeffs[offsets[p] .. offsets[p+1])
+// (a0..an; interleaved re,im when is_complex), roots go to roots_reim[2*(offsets[p]-p) ...] --
+// at most len-1 of them; nroots[p] says how many.  per_poly_stats (B entries) optional.
+// threads <= 0: all OpenMP threads.  sched: 0 reference schedule, 1 multishift (real only).
+int orc_roots_batch(const double* coeffs, const int64_t* offsets, int64_t B, int is_complex, double* roots_reim,
+                    int32_t* nroots, orc_stats* total, orc_stats* per_poly, uint64_t seed, int threads, int sched, int ms_L, int ms_small) {
+    MsParams P; if (ms_L > 0) P.L = ms_L; if (ms_small > 0) P.small = ms_small % 1000; if (ms_small >= 1000) P.reuse = ms_small / 1000;
+#ifdef _OPENMP
+    int nt = threads > 0 ? threads : omp_get_max_threads();
+#else
+    int nt = 1;
+#endif
+    (void)nt;
+    if (total) std::memset(total, 0, sizeof(*total));
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nt)
+    for (int64_t p = 0; p < B; ++p) {
+        Stats st;
+        int len = (int)(offsets[p + 1] - offsets[p]);
+        cplx* out = reinterpret_cast<cplx*>(roots_reim) + (offsets[p] - p);
+        int nr = 0;
+        if (is_complex) roots_one<cplx>(reinterpret_cast<const cplx*>(coeffs) + offsets[p], len, out, &nr, seed, (uint64_t)p, st, SCHED_REFERENCE, P);
+        else roots_one<double>(coeffs + offsets[p], len, out, &nr, seed, (uint64_t)p, st, sched, P);
+        nroots[p] = nr;
+        if (per_poly) { std::memset(&per_poly[p], 0, sizeof(orc_stats)); add_stats(&per_poly[p], st); }
+        if (total) {
+#pragma omp critical
+            add_stats(total, st);
+        }
+    }
+    return 0;
+}
+
+// Batched pencil roots: vs, ws share offsets (N_p entries each); roots at roots_reim[2*offsets[p]...].
+int orc_roots_pencil_batch(const double* vs, const double* ws, const int64_t* offsets, int64_t B, int is_complex, double* roots_reim,
+                           int32_t* nroots, orc_stats* total, uint64_t seed, int threads) {
+#ifdef _OPENMP
+    int nt = threads > 0 ? threads : omp_get_max_threads();
+#else
+    int nt = 1;
+#endif
+    (void)nt;
+    if (total) std::memset(total, 0, sizeof(*total));
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nt)
+    for (int64_t p = 0; p < B; ++p) {
+        Stats st;
+        int len = (int)(offsets[p + 1] - offsets[p]);
+        cplx* out = reinterpret_cast<cplx*>(roots_reim) + offsets[p];
+        int nr = 0;
+        if (is_complex) roots_pencil_one<cplx>(reinterpret_cast<const cplx*>(vs) + offsets[p], reinterpret_cast<const cplx*>(ws) + offsets[p], len, out, &nr, seed, (uint64_t)p, st);
+        else roots_pencil_one<double>(vs + offsets[p], ws + offsets[p], len, out, &nr, seed, (uint64_t)p, st);
+        nroots[p] = nr;
+        if (total) {
+#pragma omp critical
+            add_stats(total, st);
+        }
+    }
+    return 0;
+}
+
+// ---- primitives, for the unit tests that mirror test/test-amrvw-basics.jl
+void orc_givensrot_real(double a, double b, double* out3) { givensrot(a, b, out3[0], out3[1], out3[2]); }
+void orc_givensrot_cplx(const double* a, const double* b, double* out5) {  // -> c.re c.im s r.re r.im
+    cplx c, r; double s;
+    givensrot(cplx(a[0], a[1]), cplx(b[0], b[1]), c, s, r);
+    out5[0] = c.re; out5[1] = c.im; out5[2] = s; out5[3] = r.re; out5[4] = r.im;
+}
+void orc_turnover_real(const double* in6, double* out6) {
+    turnover_core<double>(in6[0], in6[1], in6[2], in6[3], in6[4], in6[5], out6[0], out6[1], out6[2], out6[3], out6[4], out6[5]);
+}
+void orc_turnover_cplx(const double* in9, double* out9) {  // (c.re c.im s) x 3
+    cplx c4, c5, c6; double s4, s5, s6;
+    turnover_core<cplx>(cplx(in9[0], in9[1]), in9[2], cplx(in9[3], in9[4]), in9[5], cplx(in9[6], in9[7]), in9[8], c4, s4, c5, s5, c6, s6);
+    out9[0] = c4.re; out9[1] = c4.im; out9[2] = s4; out9[3] = c5.re; out9[4] = c5.im; out9[5] = s5; out9[6] = c6.re; out9[7] = c6.im; out9[8] = s6;
+}
+void orc_fuse_real(const double* in4, double* out2) {
+    Rot<double> r = fuse(Rot<double>{in4[0], in4[1]}, Rot<double>{in4[2], in4[3]});
+    out2[0] = r.c; out2[1] = r.s;
+}
+void orc_fuse_cplx(const double* in6, double* out5) {  // -> c.re c.im s dphase.re dphase.im
+    cplx d;
+    Rot<cplx> r = fuse(Rot<cplx>{cplx(in6[0], in6[1]), in6[2]}, Rot<cplx>{cplx(in6[3], in6[4]), in6[5]}, d);
+    out5[0] = r.c.re; out5[1] = r.c.im; out5[2] = r.s; out5[3] = d.re; out5[4] = d.im;
+}
+
+int64_t orc_state_size(int N, int is_complex, int pencil) { return is_complex ? flat_size<cplx>(N, pencil) : flat_size<double>(N, pencil); }
+
+// amrvw(ps) / amrvw(vs, ws): factorization -> flat state.  len = number of coefficients (no
+// trimming is done here: the caller passes a polynomial with non-zero end coefficients).
+int orc_factor(const double* ps, int len, int is_complex, double* state) {
+    if (is_complex) { State<cplx> s; amrvw(reinterpret_cast<const cplx*>(ps), len, s); state_to_flat(s, state); }
+    else { State<double> s; amrvw(ps, len, s); state_to_flat(s, state); }
+    return 0;
+}
+int orc_factor_pencil(const double* vs, const double* ws, int N, int is_complex, double* state) {
+    if (is_complex) { State<cplx> s; amrvw_pencil(reinterpret_cast<const cplx*>(vs), reinterpret_cast<const cplx*>(ws), N, s); state_to_flat(s, state); }
+    else { State<double> s; amrvw_pencil(vs, ws, N, s); state_to_flat(s, state); }
+    return 0;
+}
+// diagonal_block!(A, QF, RF, j, j) on a flat state -> A11 A12 A21 A22 (re,im pairs if complex)
+int orc_diagonal_block(const double* state, int N, int is_complex, int pencil, int j, double* A) {
+    if (is_complex) { State<cplx> s; flat_to_state(state, N, pencil, s); cplx a[4]; diagonal_block(s, j, a); for (int i = 0; i < 4; ++i) { A[2 * i] = a[i].re; A[2 * i + 1] = a[i].im; } }
+    else { State<double> s; flat_to_state(state, N, pencil, s); diagonal_block(s, j, A); }
+    return 0;
+}
+// One bulge_step on the flat state with counter (zero,start,stop,it_count,tr) -- in/out.
+int orc_bulge_step(double* state, int N, int is_complex, int pencil, int32_t* ctr5, uint64_t seed) {
+    Counter c = {ctr5[0], ctr5[1], ctr5[2], ctr5[3], ctr5[4]};
+    Stats st; Rng rng; rng.seed = seed;
+    if (is_complex) { State<cplx> s; flat_to_state(state, N, pencil, s); bulge_step(s, c, rng, st); state_to_flat(s, state); }
+    else { State<double> s; flat_to_state(state, N, pencil, s); bulge_step(s, c, rng, st); state_to_flat(s, state); }
+    ctr5[0] = c.zero_index; ctr5[1] = c.start_index; ctr5[2] = c.stop_index; ctr5[3] = c.it_count; ctr5[4] = c.tr;
+    return (int)st.turnovers;
+}
+// AMRVW_algorithm!(state) on a flat state -> n+1 = N eigenvalues (re,im), sorted.
+int orc_eigvals(double* state, int N, int is_complex, int pencil, double* eig_reim, uint64_t seed) {
+    Stats st; Rng rng; rng.seed = seed; std::vector<cplx> E;
+    if (is_complex) { State<cplx> s; flat_to_state(state, N, pencil, s); amrvw_algorithm(s, E, rng, st); state_to_flat(s, state); }
+    else { State<double> s; flat_to_state(state, N, pencil, s); amrvw_algorithm(s, E, rng, st); state_to_flat(s, state); }
+    for (int i = 0; i < N; ++i) { eig_reim[2 * i] = E[i + 1].re; eig_reim[2 * i + 1] = E[i + 1].im; }
+    return (int)st.unconverged;
+}
+
+// Synthetic inputs shared by every leg: kind 0 = N(0,1) (Box-Muller), 1 = U[0,1),
+// 2 = U[0,1) - 1/2.  Writes `count` doubles for polynomial `poly`.
+void orc_fill_coeffs(uint64_t seed, uint64_t poly, int kind, int64_t count, double* out) {
+    for (int64_t k = 0; k < count; ++k) {
+        if (kind == 0) {
+            double u1 = uniform01(seed, poly, 2 * k), u2 = uniform01(seed, poly, 2 * k + 1);
+            if (u1 < 1e-300) u1 = 1e-300;
+            out[k] = std::sqrt(-2.0 * std::log(u1)) * std::cos(2.0 * M_PI * u2);
+        } else if (kind == 1) out[k] = uniform01(seed, poly, k);
+        else out[k] = uniform01(seed, poly, k) - 0.5;
+    }
+}
+
+}  // extern "C"

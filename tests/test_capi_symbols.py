@@ -1,0 +1,85 @@
+"""CPU tests of the boundary: the C-ABI library builds for sm_100a, loads, and exports every symbol
+include/amrvw_b200.h declares; the host mirror fails loudly without a device (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "amrvw_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(amrvw_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_declares_the_path():
+    syms = header_symbols()
+    for need in ("amrvw_create", "amrvw_destroy", "amrvw_roots_rds_f64", "amrvw_roots_css_c64", "amrvw_roots_pencil_f64",
+                 "amrvw_roots_rds_f64_dev", "amrvw_last_error"):
+        assert need in syms
+
+
+@pytest.mark.parametrize("strict", [False, True])
+def test_library_exports_every_declared_symbol(A, strict):
+    lib = ctypes.CDLL(A.lib_path(strict=strict))
+    for s in header_symbols():
+        assert hasattr(lib, s), f"{s} declared in include/amrvw_b200.h but not exported"
+    assert set(header_symbols()) == set(A.EXPORTS)
+    assert lib.amrvw_version() >= 100
+
+
+def test_library_is_sm100a_and_in_tree(A):
+    path = A.lib_path()
+    assert os.path.dirname(path) == os.path.join(ROOT, "amrvw.jl_b200")
+    import shutil, subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-lelf", path], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_default_options_and_argument_errors_need_no_gpu(A):
+    lib = A.load()
+    o = A.Options(9, 9, 9, 9, 9)
+    lib.amrvw_default_options(ctypes.byref(o))
+    assert (o.schedule, o.lanes_per_poly, o.shift_reuse, o.small_window) == (0, 0, 0, 0)
+    assert lib.amrvw_set_options(None, ctypes.byref(o)) == -1
+    assert lib.amrvw_destroy(None) == 0
+    assert lib.amrvw_last_error(None) == b"null context"
+
+
+def test_no_cpu_fallback(A):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(A.AmrvwError):
+        A.Context()
+    with pytest.raises(A.AmrvwError):
+        A.roots([1.0, 2.0, 3.0, 4.0, 5.0])
+
+
+def test_product_never_imports_oracle():
+    """The product path must not route through oracle/ (parity would be void)."""
+    pk = os.path.join(ROOT, "amrvw.jl_b200")
+    for dirpath, _, files in os.walk(pk):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("the oracle", "").replace("oracle (which", "") or f == "build.py", (dirpath, f)
+
+
+def test_host_packing_logic(A):
+    from importlib import import_module
+    R = import_module("amrvw_jl_b200.roots")
+    flat, off = R._pack([[1.0, 2.0], [3.0], [4.0, 5.0, 6.0]])
+    assert off.tolist() == [0, 2, 3, 6] and flat.tolist() == [1, 2, 3, 4, 5, 6] and flat.dtype == np.float64
+    flat, off = R._pack([[1.0, 2.0], [3.0 + 1j]])
+    assert flat.dtype == np.complex128
+    assert R._is_batch([[1.0, 2.0], [3.0]]) and not R._is_batch([1.0, 2.0]) and R._is_batch(np.zeros((3, 4)))
+    vs, ws = A.basic_pencil([1.0, 2.0, 3.0])
+    assert vs.tolist() == [1.0, 2.0] and ws.tolist() == [0.0, 3.0]

@@ -1,0 +1,309 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Everything goes through the C ABI
+(ctypes over amrvw.jl_b200/libamrvw_b200.so); the oracle is only the checker.
+
+Parity rule (north star / SURVEY.md 8c): roots matched by minimum-distance assignment,
+|dz| <= tau * kappa(z) * max(1,|z|) with tau = C n u ||a||/|a_n| (C = 64), and the number of
+exactly-real roots (imag == 0) must agree exactly.  For the one-bulge (reference-schedule) kernels
+built without FMA contraction the real double shift path is additionally bit-identical to the
+oracle, which itself reproduces the reference's printed digits."""
+import numpy as np
+import pytest
+
+from conftest import match_roots, pencil_split, root_condition_tolerance, wilkinson_coeffs
+
+pytestmark = pytest.mark.gpu
+
+p4 = np.array([24.0, -50.0, 35.0, -10.0, 1.0])
+p5 = np.array([-120.0, 274.0, -225.0, 85.0, -15.0, 1.0])
+p6 = np.array([720.0, -1764.0, 1624.0, -735.0, 175.0, -21.0, 1.0])
+pc = np.array([40.0 + 10.0j, -76.0 + 60.0j, 10.0 - 95.0j, 25.0 + 40.0j, -10.0 - 5.0j, 1.0 + 0.0j])
+pc_rts = np.array([1j, 1 + 1j, 2 + 1j, 3 + 1j, 4 + 1j])
+pc2 = np.array([1j, -1, 0, 0, -1j, 1])
+SQEPS = np.sqrt(np.finfo(float).eps)
+
+
+def _g(rows):
+    return np.array([complex(float(a), float(b)) for a, b in rows])
+
+
+@pytest.fixture(scope="module")
+def ctx(A):
+    c = A.Context(seed=0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def ctx_ref(A):
+    c = A.Context(seed=0, schedule=A.SCHEDULE_REFERENCE)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def ctx_strict(A):
+    c = A.Context(seed=0, strict=True, schedule=A.SCHEDULE_REFERENCE)
+    yield c
+    c.close()
+
+
+def batch(oracle, seed, B, n, kind=0, cx=False):
+    w = 2 if cx else 1
+    rows = [oracle.fill_coeffs(seed, p, kind, w * (n + 1)) for p in range(B)]
+    if cx:
+        rows = [r[0::2] + 1j * r[1::2] for r in rows]
+    return rows
+
+
+def check_parity(coeff_rows, got, want, C=64.0, real_counts=True):
+    worst = 0.0
+    for a, g, w in zip(coeff_rows, got, want):
+        assert len(g) == len(w)
+        d, idx = match_roots(g, w)
+        tol = root_condition_tolerance(a, w[idx], C=C)
+        ratio = np.max(d / np.maximum(tol, 1e-300))
+        worst = max(worst, ratio)
+        assert ratio <= 1.0, f"root parity violated: max |dz|/tol = {ratio:.3g}"
+        if real_counts:
+            assert np.sum(g.imag == 0) == np.sum(w.imag == 0)
+    return worst
+
+
+# ------------------------------------------------------------------ golden vectors through the C ABI
+def test_gpu_golden_p4(A, ctx_strict, golden):
+    r = A.roots(p4, ctx=ctx_strict)
+    want = _g(golden["p4"]["roots"])
+    assert np.array_equal(r.real, want.real) and np.all(r.imag == 0)     # the reference's printed digits, bit for bit
+
+
+def test_gpu_golden_pencil_p4(A, ctx_strict, golden):
+    vs, ws = A.basic_pencil(p4)
+    r = A.roots(vs, ws, ctx=ctx_strict)
+    want = _g(golden["p4_pencil"]["roots"])
+    assert np.array_equal(r.real, want.real) and np.all(r.imag == 0)
+
+
+def test_gpu_golden_pc(A, ctx_strict, golden):
+    r = A.roots(pc2, ctx=ctx_strict)
+    want = _g(golden["pc"]["roots"])
+    d, _ = match_roots(r, want)
+    assert d.max() <= 4e-16
+
+
+@pytest.mark.parametrize("which", ["default", "reference"])
+def test_gpu_known_answers(A, ctx, ctx_ref, which):
+    c = ctx if which == "default" else ctx_ref
+    for p in (p4, p5, p6):
+        r = A.roots(p, ctx=c)
+        assert np.allclose(r.real, np.arange(1, len(p)), rtol=SQEPS) and np.all(r.imag == 0)
+        rr = A.real_polynomial_roots(p, ctx=c)
+        assert np.allclose(rr.real_roots, np.arange(1, len(p))) and len(rr.complex_roots) == 0
+        vs, ws = A.basic_pencil(p)
+        r = A.roots(vs, ws, ctx=c)
+        assert np.allclose(r.real, np.arange(1, len(p)), rtol=SQEPS)
+    r = A.roots(pc, ctx=c)
+    assert np.all(np.abs(r - pc_rts) <= SQEPS)
+    vs, ws = A.basic_pencil(pc)
+    assert np.allclose(np.round(A.roots(vs, ws, ctx=c), 12), pc_rts)
+    for i in range(1, 5):
+        vs, ws = pencil_split(p4, i)
+        assert np.linalg.norm(A.roots(vs, ws, ctx=c) - np.array([1, 2, 3, 4])) <= SQEPS
+
+
+def test_gpu_simple_cases_and_trimming(A, ctx):    # test/test-roots.jl:18-108
+    cases = [(np.array([]), np.array([])), (np.array([1.0]), np.array([])), (np.array([1.0, 1.0]), np.array([-1.0])),
+             (np.array([1.0, 2.0, 1.0]), np.array([-1.0, -1.0]))]
+    for cx in (False, True):
+        inputs, wants = [], []
+        for ps, rts in cases:
+            ps = ps.astype(complex) if cx else ps
+            z2 = np.zeros(2, dtype=ps.dtype)
+            pad = np.concatenate([rts, [0, 0]]) if len(ps) else rts
+            inputs += [ps, np.concatenate([z2, ps]), np.concatenate([ps, z2]), np.concatenate([z2, ps, z2])]
+            wants += [rts, pad, rts, pad]
+        got = A.roots(inputs, ctx=ctx)             # ragged batch, including empty and all-zero inputs
+        for g, w in zip(got, wants):
+            assert len(g) == len(w) and np.all(g == w)
+        for ps, rts in cases[2:]:
+            ps = ps.astype(complex) if cx else ps
+            z2 = np.zeros(2, dtype=ps.dtype)
+            for inp, want in [(ps, rts), (np.concatenate([z2, ps]), np.concatenate([rts, [0, 0]])), (np.concatenate([ps, z2]), rts),
+                              (np.concatenate([z2, ps, z2]), np.concatenate([rts, [0, 0]]))]:
+                vs, ws = A.basic_pencil(inp)
+                g = A.roots(vs, ws, ctx=ctx)
+                assert len(g) == len(want) and np.all(g == want)
+    # zero roots are appended after the sorted non-zero ones (companion.jl:266-268)
+    r = A.roots(np.concatenate([[0.0, 0.0], p4]), ctx=ctx)
+    assert np.allclose(r[:4].real, [1, 2, 3, 4]) and np.all(r[4:] == 0)
+
+
+# ------------------------------------------------------------------ bit parity of the reference-schedule kernels
+def test_gpu_rds_bitwise_vs_oracle(A, ctx_strict, oracle):
+    """One bulge at a time, no FMA contraction: the GPU's real double shift path performs the same
+    IEEE operations in the same order as the oracle -> identical bits (inputs that take an
+    exceptional shift are excluded: sincos differs between libm and CUDA in the last bit)."""
+    rows = batch(oracle, 11, 48, 60) + batch(oracle, 12, 8, 301) + [p4, p5, p6]
+    flat = np.concatenate(rows); off = np.zeros(len(rows) + 1, dtype=np.int64); np.cumsum([len(r) for r in rows], out=off[1:])
+    out, roff, nr, _, pp = oracle.roots_csr(flat, off, per_poly=True)
+    got = A.roots(rows, ctx=ctx_strict)
+    n_checked = 0
+    for p, g in enumerate(got):
+        if pp[p]["exceptional"]:
+            continue
+        w = out[roff[p]:roff[p] + nr[p]]
+        assert np.array_equal(g.view(np.float64), w.view(np.float64)), f"polynomial {p} differs"
+        n_checked += 1
+    assert n_checked >= 50
+    assert ctx_strict.last_stats["turnovers"] > 0
+
+
+def test_gpu_pencil_bitwise_vs_oracle(A, ctx_strict, oracle):
+    rows = batch(oracle, 13, 24, 40)
+    vs, ws = zip(*[pencil_split(r, len(r) // 2) for r in rows])
+    got = A.roots(list(vs), list(ws), ctx=ctx_strict)
+    for v, w, g in zip(vs, ws, got):
+        want, st = oracle.roots(v, ws=w)
+        if st["exceptional"]:
+            continue
+        assert np.array_equal(g.view(np.float64), want.view(np.float64))
+
+
+# ------------------------------------------------------------------ tolerance parity, all variants, both schedules
+@pytest.mark.parametrize("n,B", [(100, 64), (333, 16), (1000, 4)])
+@pytest.mark.parametrize("which", ["default", "reference"])
+def test_gpu_rds_parity(A, ctx, ctx_ref, oracle, n, B, which):
+    c = ctx if which == "default" else ctx_ref
+    rows = batch(oracle, 1, B, n)                       # C1-style: N(0,1) coefficients
+    want = [oracle.roots(r)[0] for r in rows]
+    got = A.roots(rows, ctx=c)
+    check_parity(rows, got, want)
+    assert c.last_stats["unconverged"] == 0
+
+
+@pytest.mark.parametrize("n,B,kind", [(100, 32, 1), (500, 8, 1), (200, 8, 0)])
+def test_gpu_css_parity(A, ctx, oracle, n, B, kind):   # C3-style: U[0,1) + i U[0,1), and complex normal
+    rows = batch(oracle, 3, B, n, kind=kind, cx=True)
+    want = [oracle.roots(r)[0] for r in rows]
+    got = A.roots(rows, ctx=ctx)
+    check_parity(rows, got, want, real_counts=False)
+
+
+@pytest.mark.parametrize("n,B", [(100, 32), (500, 8)])
+def test_gpu_pencil_parity(A, ctx, oracle, n, B):      # C4-style: basic_pencil and a mid split
+    rows = batch(oracle, 4, B, n)
+    for split in ("basic", "half"):
+        pairs = [A.basic_pencil(r) if split == "basic" else pencil_split(r, n // 2) for r in rows]
+        vs, ws = zip(*pairs)
+        want = [oracle.roots(v, ws=w)[0] for v, w in pairs]
+        got = A.roots(list(vs), list(ws), ctx=ctx)
+        check_parity(rows, got, want, C=256.0)
+
+
+def test_gpu_c5_style_uniform_shifted(A, ctx, oracle):  # C5 input law U[0,1) - 1/2 at reduced degree
+    rows = batch(oracle, 5, 8, 600, kind=2)
+    want = [oracle.roots(r)[0] for r in rows]
+    got = A.roots(rows, ctx=ctx)
+    check_parity(rows, got, want)
+
+
+def test_gpu_ragged_batch(A, ctx, oracle):
+    degs = [3, 4, 5, 7, 16, 33, 64, 100, 129, 257, 2, 1, 0]
+    rows = [oracle.fill_coeffs(21, i, 0, d + 1) for i, d in enumerate(degs)]
+    got = A.roots(rows, ctx=ctx)
+    for r, g in zip(rows, got):
+        w, _ = oracle.roots(r)
+        assert len(g) == len(w)
+        if len(r) > 3:
+            check_parity([r], [g], [w])
+        else:
+            assert np.array_equal(g, w)
+
+
+def test_gpu_exceptional_shift_inputs(A, ctx, ctx_ref, oracle):   # x^n - 1, x^64 + 1, Wilkinson-20, (x-1)^8
+    p1 = np.zeros(21); p1[0] = -1; p1[-1] = 1
+    p2 = np.zeros(65); p2[0] = 1; p2[-1] = 1
+    for c in (ctx, ctx_ref):
+        r = A.roots(p1, ctx=c)
+        d, _ = match_roots(r, np.exp(2j * np.pi * np.arange(20) / 20))
+        assert d.max() < 1e-12
+        r = A.roots(p2, ctx=c)
+        d, _ = match_roots(r, np.exp(1j * np.pi * (2 * np.arange(64) + 1) / 64))
+        assert d.max() < 1e-12
+    r = A.roots(wilkinson_coeffs(20), ctx=ctx_ref)
+    assert ctx_ref.last_stats["exceptional"] >= 1
+    assert len(r) == 20 and np.all(np.isfinite(r.view(np.float64)))
+    r8 = A.roots(np.poly(np.ones(8))[::-1].copy(), ctx=ctx)
+    assert np.max(np.abs(r8 - 1)) < 0.1
+
+
+def test_gpu_wilkinson_golden(A, ctx_ref, golden):
+    r = A.roots(wilkinson_coeffs(20), ctx=ctx_ref)
+    want = _g(golden["wilkinson20"]["roots"])
+    d, _ = match_roots(r, want)
+    assert d.max() < 1e-7 and np.sum(r.imag == 0) == 12
+
+
+# ------------------------------------------------------------------ full-size, size-independent properties
+def horner_backward_error(a, z):
+    """max over roots of |p(z)| / sum |a_k||z|^k, evaluated stably for |z| > 1 via the reversed polynomial."""
+    a = np.asarray(a, dtype=np.complex128)
+    z = np.asarray(z, dtype=np.complex128)
+    out = np.empty(len(z))
+    inside = np.abs(z) <= 1
+    for mask, coef, pts in ((inside, a, z[inside]), (~inside, a[::-1], 1.0 / z[~inside])):
+        if pts.size == 0:
+            continue
+        num = np.polyval(coef[::-1], pts)
+        den = np.polyval(np.abs(coef[::-1]), np.abs(pts))
+        out[mask] = np.abs(num) / den
+    return out
+
+
+def test_gpu_full_size_c2_properties(A, ctx, oracle):
+    """BASELINE config 2 at full degree (n = 3000), a slice of the batch: every polynomial converges,
+    residuals are at backward-error level, conjugate pairing is exact, real-root statistics follow
+    README.md:121-127; and one polynomial is checked root-by-root against the oracle."""
+    n, B = 3000, 96
+    rows = batch(oracle, 2, B, n)
+    got = A.roots(rows, ctx=ctx)
+    assert ctx.last_stats["unconverged"] == 0
+    counts = []
+    for r, g in zip(rows, got):
+        assert len(g) == n
+        be = horner_backward_error(r, g)
+        assert be.max() < 1e-10
+        counts.append(np.sum(g.imag == 0))
+        pos = np.sort_complex(g[g.imag > 0]); neg = np.sort_complex(np.conj(g[g.imag < 0]))
+        assert np.array_equal(pos, neg)            # exact conjugate pairs (qdrtc, utils.jl:130-140)
+        keys = g.real + 0  # sorted by (re, im)
+        assert np.all(np.diff(keys) >= 0)
+    expect = 2 / np.pi * np.log(n) + 0.625738072 + 2 / (np.pi * n)
+    counts = np.array(counts)
+    assert abs(counts.mean() - expect) < 4 * counts.std() / np.sqrt(B) + 0.2
+    want, _ = oracle.roots(rows[0])
+    check_parity(rows[:1], got[:1], [want])
+
+
+def test_gpu_count_real_roots_dev(A, ctx, oracle):
+    import torch
+    rows = batch(oracle, 8, 40, 120)
+    flat = np.concatenate(rows); off = np.arange(41, dtype=np.int64) * 121
+    dev = torch.device("cuda:0")
+    d_c = torch.from_numpy(flat).to(dev); d_o = torch.from_numpy(off).to(dev)
+    d_r = torch.zeros(2 * int(off[-1]), dtype=torch.float64, device=dev)
+    d_n = torch.zeros(40, dtype=torch.int32, device=dev); d_u = torch.zeros(40, dtype=torch.int32, device=dev)
+    d_cnt = torch.zeros(120, dtype=torch.int32, device=dev)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    ctx.roots_dev("rds_f64", d_c.data_ptr(), d_o.data_ptr(), 40, int(off[-1]), 121, d_r.data_ptr(), d_n.data_ptr(), d_u.data_ptr())
+    ctx.count_real_roots_dev(d_r.data_ptr(), d_o.data_ptr(), 40, 1, d_n.data_ptr(), d_cnt.data_ptr())
+    torch.cuda.synchronize()
+    ctx.set_stream(0)
+    cnt = d_cnt.cpu().numpy().reshape(40, 3)
+    for p, r in enumerate(rows):
+        w, _ = oracle.roots(r)
+        assert cnt[p, 0] == np.sum(w.imag == 0) and cnt[p, 1] == cnt[p, 2] and cnt[p].sum() == 120
+
+
+def test_gpu_fp64_peak_probe(ctx):
+    tf = ctx.fp64_peak_tflops()
+    assert 5.0 < tf < 80.0
