@@ -36,6 +36,7 @@ _SIGS = {
     "amrvw_default_options": (None, [ctypes.POINTER(Options)]),
     "amrvw_set_options": (ctypes.c_int, [_P, ctypes.POINTER(Options)]),
     "amrvw_set_stream": (ctypes.c_int, [_P, _P]),
+    "amrvw_use_own_stream": (ctypes.c_int, [_P]),
     "amrvw_roots_rds_f64": (ctypes.c_int, [_P, _P, _P, _I64, _P, _P, _P, ctypes.POINTER(Stats)]),
     "amrvw_roots_css_c64": (ctypes.c_int, [_P, _P, _P, _I64, _P, _P, _P, ctypes.POINTER(Stats)]),
     "amrvw_roots_pencil_f64": (ctypes.c_int, [_P, _P, _P, _P, _I64, _P, _P, _P, ctypes.POINTER(Stats)]),

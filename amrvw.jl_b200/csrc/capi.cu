@@ -114,7 +114,12 @@ int amrvw_set_options(amrvw_ctx* ctx, const amrvw_options* opt) {
 
 int amrvw_set_stream(amrvw_ctx* ctx, void* s) {
     if (!ctx) return AMRVW_ERR_ARGUMENT;
-    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    ctx->stream = (cudaStream_t)s;   // NULL = legacy default stream
+    return AMRVW_OK;
+}
+int amrvw_use_own_stream(amrvw_ctx* ctx) {
+    if (!ctx) return AMRVW_ERR_ARGUMENT;
+    ctx->stream = ctx->own_stream;
     return AMRVW_OK;
 }
 

@@ -1,15 +1,425 @@
-// pipeline.cuh -- pipelined (multishift) real-double-shift kernel.  PLACEHOLDER while the
-// one-bulge path is brought up on hardware: forwards to the reference-schedule kernel.
+// pipeline.cuh -- pipelined (multishift) real-double-shift kernel: the north-star path.
+//
+// The reference chases ONE bulge at a time down the three rotator chains (bulge-step.jl:36-49); a
+// bulge at position i only touches indices i..i+2 of Q, B and Ct, so a second bulge
+// can follow three indices behind without ever seeing a half-updated rotator.  This kernel keeps
+// L bulges in flight per polynomial, one per lane of a group of L lanes (G = 32/L polynomials per
+// warp), as a register-resident systolic array:
+//
+//        HBM/L2 --(lane 0 loads index start+t)--> [lane 0: window of 3 indices + bulge 0]
+//               --shfl_up--> [lane 1: window + bulge 1] --shfl_up--> ... --> [lane L-1] --store--> HBM
+//
+//   * every lane holds a sliding window of three consecutive rotators of each chain (18 doubles) and
+//     its bulge U, V, W (6 doubles) in registers; per step it does the 7 turnovers of one chase
+//     step, retires the finished rotator triple to the next lane with warp shuffles and receives the
+//     next one.  Each rotator is read from memory once and written once per L bulges: 96 B of
+//     traffic per step per group instead of per bulge, no shared-memory staging of the chains, no
+//     bank conflicts.
+//   * the L bulges of one "fat step" use 2L/reuse shifts = the eigenvalues of the trailing block of
+//     the active window.  They come from running the one-bulge algorithm on a copy of the last
+//     2L/reuse rotators whose top rotator is made diagonal (so the copy is exactly the trailing
+//     principal block), staged in shared memory by the group's lane 0 ("phase A").
+//   * windows of at most `small` rotators are decoupled from the rest of the matrix; lane 0 finishes
+//     them completely in shared memory with the reference's one-bulge schedule.
+//   * phases alternate warp-synchronously: phase A (lane 0 of every group: deflation scan, 2x2/1x1
+//     extraction, small windows, shift sub-solve), phase B (all 32 lanes chase).
+//
+// The operations are the reference's (same turnover/fuse/create_bulge code as solver.cuh); only
+// their order differs, so roots agree with the reference to backward-error level, not bit for bit.
+// oracle/amrvw_oracle.cpp holds the same schedule executed sequentially (amrvw_algorithm_ms): bulges
+// three apart commute exactly, so that is what this kernel is tested against.
 #pragma once
 #include "kernels.cuh"
 #include "../../include/amrvw_b200.h"
 
 namespace amrvw {
-static int launch_pipelined_rds(const Problem<double>& pr, const amrvw_options&, int, int, cudaStream_t st, int* launches) {
-    const int threads = 64;
-    const int blocks = (int)((pr.nbatch + threads - 1) / threads);
-    roots_reference_kernel<double><<<blocks, threads, 0, st>>>(pr);
-    *launches += 1;
+
+struct PipeParams {
+    int reuse;   // bulges per shift pair
+    int small;   // windows <= small are finished serially in shared memory
+    int ms;      // scratch slots per group and chain (>= max(2L/reuse, small) + 3)
+};
+
+AMRVW_DI Rot<double> shfl_up_rot(const Rot<double> r, int width) {
+    Rot<double> o;
+    o.c = __shfl_up_sync(0xffffffffu, r.c, 1, width);
+    o.s = __shfl_up_sync(0xffffffffu, r.s, 1, width);
+    return o;
+}
+AMRVW_DI Rot<double> ldg_rot(const Rot<double>* p) {
+    const double2 v = *reinterpret_cast<const double2*>(p);
+    return make_rot<double>(v.x, v.y);
+}
+AMRVW_DI void stg_rot(Rot<double>* p, const Rot<double> r) { *reinterpret_cast<double2*>(p) = make_double2(r.c, r.s); }
+
+#define AMRVW_TURN(a, b, c, o1, o2, o3)      \
+    do {                                      \
+        Rot<double> t1_, t2_, t3_;            \
+        turnover(a, b, c, t1_, t2_, t3_);     \
+        o1 = t1_; o2 = t2_; o3 = t3_;         \
+    } while (0)
+
+// Shared-memory scratch of one group: a window of up to ms rotators of each chain + eigenvalue slots.
+struct GroupScratch {
+    Rot<double>* q; Rot<double>* b; Rot<double>* c; cplx* e;
+};
+
+// Copy chain indices k..hi+1 of the polynomial into scratch and return a view whose indices are the
+// global ones (scratch slot 0 <-> index k).
+AMRVW_DI Fact<double, false> stage_window(const Fact<double, false>& F, const GroupScratch& sc, int k, int hi) {
+    const int cnt = hi + 1 - k + 1;
+    for (int t = 0; t < cnt; ++t) {
+        sc.q[t] = ldg_rot(F.Q + k + t);
+        sc.b[t] = ldg_rot(F.B + k + t);
+        sc.c[t] = ldg_rot(F.Ct + k + t);
+    }
+    Fact<double, false> W = F;
+    W.Q = sc.q - k; W.B = sc.b - k; W.Ct = sc.c - k;
+    W.turnovers = 0;
+    return W;
+}
+
+struct LeaderState {
+    Counter ctr;
+    long long kk, it_max;
+    int ord;
+    int unconv;
+    bool started;
+};
+
+// Phase A: the driver (AMRVW_algorithm.jl:10-138) up to the next fat step.  Returns 0 when the
+// polynomial is finished, 1 for a fat step with shifts in shl[0..nb), 2 for a fat step of nb
+// exceptional (random) bulges.
+AMRVW_DI int phase_a(Fact<double, false>& F, LeaderState& ls, cplx* E, const GroupScratch& sc, Shifts* shl, const int L, const PipeParams pp,
+                     int& nb, const uint64_t seed, const uint64_t poly, PolyStats& st) {
+    Counter& ctr = ls.ctr;
+    double A[4];
+    if (!ls.started) { check_deflation(F, ctr); ls.started = true; }
+    while (ls.kk <= ls.it_max) {
+        if (ctr.stop_index < 1) return 0;
+        check_deflation(F, ctr);
+        ++ls.kk;
+        const int k = ctr.stop_index;
+        const int delta = ctr.stop_index - ctr.zero_index;
+        if (delta == 1) {
+            diagonal_block(F, k, A);
+            cplx e1, e2;
+            eig2x2(A, e1, e2);
+            E[k] = e1; E[k + 1] = e2;
+            if (ctr.stop_index == 2) { diagonal_block(F, 1, A); E[1] = to_c(A[0]); ctr.stop_index = 0; return 0; }
+            ctr.stop_index = ctr.zero_index - 1; ctr.zero_index = 0; ctr.start_index = 1;
+            check_deflation(F, ctr);
+            if (ctr.stop_index < 1) return 0;
+        } else if (delta <= 0) {
+            diagonal_block(F, k, A);
+            if (ctr.stop_index == 1) { E[1] = to_c(A[0]); E[2] = to_c(A[3]); ctr.stop_index = 0; return 0; }
+            E[k + 1] = to_c(A[3]);
+            ctr.stop_index = ctr.zero_index - 1;
+            if (ctr.stop_index < 1) return 0;
+            ctr.zero_index = 0; ctr.start_index = 1;
+            check_deflation(F, ctr);
+        } else if (delta <= pp.small) {
+            // decoupled small window [lo2, hi2]: finish it in shared memory, one bulge at a time
+            const int lo2 = ctr.start_index, hi2 = ctr.stop_index;
+            Fact<double, false> W = stage_window(F, sc, lo2 - 1, hi2);
+            Counter c2 = {lo2 - 1, lo2, hi2, ctr.it_count, -1};
+            const int left = drive_window(W, lo2, hi2, c2, E, 20ll * (hi2 - lo2 + 1), seed, poly, ls.ord, st, ReferenceStep());
+            F.turnovers += W.turnovers;
+            ls.unconv += left;
+            if (lo2 == 2) { diagonal_block(F, 1, A); E[1] = to_c(A[0]); }
+            ctr.stop_index = lo2 - 2; ctr.zero_index = 0; ctr.start_index = 1; ctr.it_count = 15;
+            if (ctr.stop_index >= 1) check_deflation(F, ctr);
+        } else if (ctr.it_count == 0) {
+            st.fat_steps++;
+            nb = L;
+            return 2;
+        } else {
+            // shifts: eigenvalues of the trailing (m+1) x (m+1) block = the window [k0+1, stop] of a copy
+            // whose rotator k0 is made diagonal
+            int m = min(2 * L / pp.reuse - 1, delta - 1);
+            if (m % 2 == 0) m -= 1;
+            const int stop = ctr.stop_index, k0 = stop - m;
+            Fact<double, false> W = stage_window(F, sc, k0, stop);
+            {
+                const double sg = sign_(W.Q[k0].c);
+                W.Q[k0] = make_rot<double>(sg == 0.0 ? 1.0 : sg, 0.0);
+            }
+            cplx* Es = sc.e - (k0 + 1);
+            for (int t = 0; t <= m; ++t) sc.e[t] = cplx(0.0, 0.0);
+            Counter c2 = {k0, k0 + 1, stop, 15, -1};
+            PolyStats sub = {0, 0, 0, 0, 0};
+            drive_window(W, k0 + 1, stop, c2, Es, 20ll * m, seed, poly, ls.ord, sub, ReferenceStep());
+            F.turnovers += W.turnovers;
+            // pair the m+1 shifts: conjugate pairs first (slot order), then the reals two by two
+            int np = 0;
+            for (int t = 0; t <= m; ++t) {
+                const cplx z = sc.e[t];
+                if (z.im != 0.0) {
+                    if (t + 1 <= m && sc.e[t + 1].im == -z.im && sc.e[t + 1].re == z.re) { shl[np].e1 = z; shl[np].e2 = sc.e[t + 1]; ++np; ++t; }
+                    else { shl[np].e1 = z; shl[np].e2 = conj_(z); ++np; }
+                }
+            }
+            bool have = false;
+            cplx pend;
+            for (int t = 0; t <= m; ++t) {
+                const cplx z = sc.e[t];
+                if (z.im == 0.0) {
+                    if (have) { shl[np].e1 = pend; shl[np].e2 = z; ++np; have = false; }
+                    else { pend = z; have = true; }
+                }
+            }
+            if (have) { shl[np].e1 = pend; shl[np].e2 = pend; ++np; }
+            if (np * pp.reuse > L) np = L / pp.reuse;
+            for (int rep = 1; rep < pp.reuse; ++rep)
+                for (int b = 0; b < np; ++b) shl[rep * np + b] = shl[b];
+            nb = np * pp.reuse;
+            st.fat_steps++;
+            ctr.it_count -= 1;
+            return 1;
+        }
+    }
+    return 0;
+}
+
+template <int L, int WPB>
+__global__ void __launch_bounds__(32 * WPB) roots_pipelined_kernel(Problem<double> pr, PipeParams pp) {
+    constexpr int G = 32 / L;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int wib = threadIdx.x >> 5, lane32 = threadIdx.x & 31;
+    const int grp = lane32 / L, lane = lane32 % L;
+    const long long p = ((long long)blockIdx.x * WPB + wib) * G + grp;
+    const bool valid = p < pr.nbatch;
+    const bool leader = valid && lane == 0;
+
+    // shared memory carve-up: per warp [32 Shifts][G groups x (3 chains x ms rotators + ms eigenvalues)]
+    const size_t per_group = (size_t)pp.ms * (3 * sizeof(Rot<double>) + sizeof(cplx));
+    const size_t per_warp = 32 * sizeof(Shifts) + G * per_group;
+    unsigned char* wbase = smem_raw + (size_t)wib * per_warp;
+    Shifts* shl = reinterpret_cast<Shifts*>(wbase) + grp * L;
+    GroupScratch sc;
+    {
+        unsigned char* g = wbase + 32 * sizeof(Shifts) + (size_t)grp * per_group;
+        sc.q = reinterpret_cast<Rot<double>*>(g);
+        sc.b = sc.q + pp.ms;
+        sc.c = sc.b + pp.ms;
+        sc.e = reinterpret_cast<cplx*>(sc.c + pp.ms);
+    }
+
+    // ---------------- set-up (lane 0 of each group): trim, closed forms, factorization
+    Fact<double, false> F;
+    F.N = 0; F.turnovers = 0;
+    F.Q = F.B = F.Ct = F.WB = F.WCt = nullptr; F.DQ = F.DR = F.WD = nullptr;
+    PolyStats st = {0, 0, 0, 0, 0};
+    LeaderState ls;
+    ls.kk = 0; ls.it_max = 0; ls.ord = 0; ls.unconv = 0; ls.started = false;
+    ls.ctr = {0, 1, 0, 15, -1};
+    cplx* out = nullptr;
+    int N = 0, K = 0;
+    int mode = 0;   // 0: nothing to do / finished, 1: fat step, 2: exceptional fat step
+    bool iterating = false;
+    if (valid) {
+        const long long off = pr.offsets[p];
+        out = pr.roots + (off - p);
+        if (leader) {
+            const int len = (int)(pr.offsets[p + 1] - off);
+            int first, last;
+            trim_zeros(pr.coeffs + off, len, first, last);
+            if (first < 0) {
+                finish_poly(pr, p, out, 0, 0, 0, st);
+            } else {
+                const double* ps = pr.coeffs + off + first;
+                const int ncoef = last - first + 1;
+                K = first;
+                if (ncoef <= 3) {
+                    const int cnt = solve_simple(ps, ncoef, out);
+                    finish_poly(pr, p, out, cnt, K, 0, st);
+                } else {
+                    N = ncoef - 1;
+                    F = make_fact<double, false>(pr, p, N);
+                    factor_companion(F, ps);
+                    for (int i = 0; i < N; ++i) out[i] = cplx(0.0, 0.0);
+                    ls.ctr = {0, 1, N - 1, 15, -1};
+                    ls.it_max = 20ll * (N - 1);
+                    iterating = true;
+                }
+            }
+        }
+    }
+    // every lane of the group needs the chain pointers
+    N = __shfl_sync(0xffffffffu, N, grp * L);
+    if (valid && N > 0 && !leader) F = make_fact<double, false>(pr, p, N);
+    __syncwarp();
+
+    long long my_turnovers = 0;
+    int nb = 0;
+    for (;;) {
+        // ---------------- phase A
+        mode = 0;
+        if (leader && iterating) {
+            mode = phase_a(F, ls, out - 1, sc, shl, L, pp, nb, pr.seed, (uint64_t)p, st);
+            if (mode == 0) iterating = false;
+        }
+        __syncwarp();
+        if (!__any_sync(0xffffffffu, mode != 0)) break;
+        // group-uniform parameters of the fat step
+        mode = __shfl_sync(0xffffffffu, mode, grp * L);
+        nb = __shfl_sync(0xffffffffu, nb, grp * L);
+        const int start = __shfl_sync(0xffffffffu, ls.ctr.start_index, grp * L);
+        const int stop = __shfl_sync(0xffffffffu, ls.ctr.stop_index, grp * L);
+        const int ord0 = __shfl_sync(0xffffffffu, ls.ord, grp * L);
+        const bool act = mode != 0;
+        const int T = act ? (stop - start + 3 * L + 1) : 0;
+        const int Tmax = __reduce_max_sync(0xffffffffu, T);
+
+        // ---------------- phase B: systolic chase of nb bulges through [start, stop]
+        Rot<double> q0, q1, q2, b0, b1, b2, c0, c1, c2, U, V, W;
+        q0 = q1 = q2 = b0 = b1 = b2 = c0 = c1 = c2 = U = V = W = make_rot<double>(1.0, 0.0);
+        Rot<double> nq = q0, nbr = q0, nc = q0;   // lane 0's prefetched next index
+        Shifts mysh;
+        mysh.e1 = cplx(0.0, 0.0); mysh.e2 = cplx(0.0, 0.0);
+        const bool has_bulge = act && lane < nb;
+        if (has_bulge && mode == 1) mysh = shl[lane];
+        double ptop = 1.0, pbot = 1.0;
+        Rot<double> qm = q0, bm = q0, cm = q0;   // static rotators at index start-1
+        if (act) {
+            qm = ldg_rot(F.Q + start - 1);                 // Q[0] is the (1,0) sentinel
+            if (start > 1) { bm = ldg_rot(F.B + start - 1); cm = ldg_rot(F.Ct + start - 1); }
+            ptop = sign_(qm.c);
+            pbot = sign_(F.Q[stop + 1].c);                 // Q[N] is the (1,0) sentinel
+            if (lane == 0) { nq = ldg_rot(F.Q + start); nbr = ldg_rot(F.B + start); nc = ldg_rot(F.Ct + start); }
+        }
+        for (int t = 0; t < Tmax; ++t) {
+            const int tp = t - 3 * lane;
+            // ingest: what the previous lane finished last step (lane 0: from memory)
+            Rot<double> iq = shfl_up_rot(q0, L), ib = shfl_up_rot(b0, L), ic = shfl_up_rot(c0, L);
+            if (lane == 0) {
+                iq = nq; ib = nbr; ic = nc;
+                const int nidx = start + t + 1;
+                if (act && nidx <= stop + 1) { nq = ldg_rot(F.Q + nidx); nbr = ldg_rot(F.B + nidx); nc = ldg_rot(F.Ct + nidx); }
+            }
+            q0 = q1; q1 = q2; q2 = iq;
+            b0 = b1; b1 = b2; b2 = ib;
+            c0 = c1; c1 = c2; c2 = ic;
+            const int i = start + tp - 2;   // position of this lane's bulge; window = indices i..i+2
+            if (has_bulge && tp >= 2 && i <= stop - 1) {
+                if (tp == 2) {
+                    // create_bulge (create-bulge.jl:20-77) on the window [start-1 .. start+2], then absorb_Ut
+                    if (mode == 2) {
+                        const double ang = uniform01(pr.seed ^ 0xA5A5A5A5DEADBEEFull, (uint64_t)p, (uint64_t)(ord0 + lane)) * 3.141592653589793;
+                        double sn, cs;
+                        sincos(ang, &sn, &cs);
+                        U = make_rot<double>(sn, cs);
+                        V = make_rot<double>(sn, -cs);
+                    } else {
+                        Rot<double> lq[4] = {qm, q0, q1, q2}, lb[4] = {bm, b0, b1, b2}, lc[4] = {cm, c0, c1, c2};
+                        Fact<double, false> Fl = F;
+                        Fl.Q = lq - (start - 1); Fl.B = lb - (start - 1); Fl.Ct = lc - (start - 1);
+                        Counter cl = {start - 1, start, stop, 15, -1};
+                        int dummy = 0;
+                        PolyStats ds = {0, 0, 0, 0, 0};
+                        create_bulge_rds(Fl, cl, U, V, &mysh, pr.seed, (uint64_t)p, dummy, ds);
+                    }
+                    // absorb_Ut (RDS.jl:14-36)
+                    Rot<double> w = q0;
+                    w.s = sign_(ptop) * w.s;
+                    Rot<double> r1, r2, r3;
+                    turnover(adjoint(U), adjoint(V), w, r1, r2, r3);
+                    W = r1;
+                    q1 = fuse(r3, q1);
+                    r2.s = sign_(ptop) * r2.s;
+                    q0 = r2;
+                    my_turnovers += 1;
+                }
+                // passthrough_triu (RDS.jl:42-70): V then U through B and Ct
+                AMRVW_TURN(b1, b2, V, V, b1, b2);
+                AMRVW_TURN(c2, c1, V, V, c2, c1);
+                AMRVW_TURN(b0, b1, U, U, b0, b1);
+                AMRVW_TURN(c1, c0, U, U, c1, c0);
+                if (i <= stop - 2) {
+                    // passthrough_Q (RDS.jl:97-108): V, U through Q, then the limb turnover
+                    AMRVW_TURN(q1, q2, V, V, q1, q2);
+                    AMRVW_TURN(q0, q1, U, U, q0, q1);
+                    AMRVW_TURN(W, V, U, V, U, W);
+                    my_turnovers += 7;
+                } else {
+                    // last position (j == stop): fuse the bulge into Q (RDS.jl:110-128)
+                    V.s = sign_(pbot) * V.s;
+                    q1 = fuse(q1, V);
+                    AMRVW_TURN(q0, q1, U, U, q0, q1);
+                    U = fuse(W, U);
+                    AMRVW_TURN(b1, b2, U, U, b1, b2);
+                    AMRVW_TURN(c2, c1, U, U, c2, c1);
+                    U.s = sign_(pbot) * U.s;
+                    q1 = fuse(q1, U);
+                    my_turnovers += 7;
+                }
+            }
+            // retire: the last lane writes index i back
+            if (lane == L - 1 && act && i >= start && i <= stop + 1) {
+                stg_rot(F.Q + i, q0); stg_rot(F.B + i, b0); stg_rot(F.Ct + i, c0);
+            }
+        }
+        if (leader && act) {
+            st.sweeps += nb;
+            if (mode == 2) { st.exceptional += nb; ls.ord += nb; ls.ctr.it_count = 14; }
+        }
+        __syncwarp();
+    }
+
+    // ---------------- epilogue: turnover count, sort, zero roots
+    for (int d = L / 2; d >= 1; d >>= 1) my_turnovers += __shfl_down_sync(0xffffffffu, my_turnovers, d, L);
+    if (leader && N > 0) {
+        sort_roots(out, N);
+        st.turnovers = F.turnovers + my_turnovers;
+        st.unconverged = ls.unconv + (ls.ctr.stop_index >= 1 ? ls.ctr.stop_index + 1 : 0);
+        finish_poly(pr, p, out, N, K, st.unconverged, st);
+    }
+}
+
+template <int L>
+static int launch_pipelined_L(const Problem<double>& pr, PipeParams pp, cudaStream_t st) {
+    constexpr int WPB = 2;
+    constexpr int G = 32 / L;
+    const size_t per_warp = 32 * sizeof(Shifts) + (size_t)G * pp.ms * (3 * sizeof(Rot<double>) + sizeof(cplx));
+    const size_t smem = WPB * per_warp;
+    const long long groups_per_block = (long long)WPB * G;
+    const int blocks = (int)((pr.nbatch + groups_per_block - 1) / groups_per_block);
+    auto kern = roots_pipelined_kernel<L, WPB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<blocks, 32 * WPB, smem, st>>>(pr, pp);
     return (int)cudaGetLastError();
 }
+
+// Chooses L (bulges in flight per polynomial) from the degree and the batch: enough lanes to fill the
+// GPU, not more than the windows can feed (a fat step needs a window > small >= 2L/reuse).
+static int launch_pipelined_rds(const Problem<double>& pr, const amrvw_options& opt, int max_len, int sm_count, cudaStream_t st, int* launches) {
+    const int degree = max_len - 1;
+    int L = opt.lanes_per_poly;
+    if (L == 0) {
+        if (degree < 48) L = 4;
+        else if (degree < 200) L = 8;
+        else if (degree < 1200 && pr.nbatch * 16 > (long long)sm_count * 512) L = 8;
+        else L = 16;
+        if (degree >= 1200 && pr.nbatch * 32 <= (long long)sm_count * 256) L = 32;
+    }
+    PipeParams pp;
+    pp.reuse = opt.shift_reuse ? opt.shift_reuse : 2;
+    if (pp.reuse > L / 2) pp.reuse = L / 2 > 0 ? L / 2 : 1;
+    const int mshift = 2 * L / pp.reuse;
+    pp.small = opt.small_window ? opt.small_window : (mshift + 8 > 24 ? mshift + 8 : 24);
+    if (pp.small < mshift) pp.small = mshift;      // a fat step needs delta - 1 >= m
+    if (pp.small > 96) pp.small = 96;
+    pp.ms = (mshift > pp.small ? mshift : pp.small) + 4;
+    int rc;
+    switch (L) {
+        case 4: rc = launch_pipelined_L<4>(pr, pp, st); break;
+        case 8: rc = launch_pipelined_L<8>(pr, pp, st); break;
+        case 16: rc = launch_pipelined_L<16>(pr, pp, st); break;
+        default: rc = launch_pipelined_L<32>(pr, pp, st); break;
+    }
+    *launches += 1;
+    return rc;
+}
+
 }  // namespace amrvw

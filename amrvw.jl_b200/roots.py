@@ -55,7 +55,11 @@ class Context:
         self._check(self._lib.amrvw_set_options(self._h, ctypes.byref(o)))
 
     def set_stream(self, cuda_stream_handle):
-        self._check(self._lib.amrvw_set_stream(self._h, ctypes.c_void_p(int(cuda_stream_handle or 0))))
+        """Run on the caller's stream; 0 is the legacy default stream.  None: back to the private stream."""
+        if cuda_stream_handle is None:
+            self._check(self._lib.amrvw_use_own_stream(self._h))
+        else:
+            self._check(self._lib.amrvw_set_stream(self._h, ctypes.c_void_p(int(cuda_stream_handle))))
 
     def fp64_peak_tflops(self):
         v = ctypes.c_double()

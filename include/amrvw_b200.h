@@ -78,8 +78,11 @@ int amrvw_destroy(amrvw_ctx* ctx);
 const char* amrvw_last_error(const amrvw_ctx* ctx);
 void amrvw_default_options(amrvw_options* opt);
 int amrvw_set_options(amrvw_ctx* ctx, const amrvw_options* opt);
-/* Run on an existing CUDA stream (cudaStream_t passed as void*); NULL = the context's own. */
+/* Run on the caller's CUDA stream (cudaStream_t passed as void*).  NULL is a valid handle: the
+ * legacy default stream (what torch.cuda.current_stream().cuda_stream is by default).
+ * amrvw_use_own_stream goes back to the context's private non-blocking stream (the default). */
 int amrvw_set_stream(amrvw_ctx* ctx, void* cuda_stream);
+int amrvw_use_own_stream(amrvw_ctx* ctx);
 
 /* ---- host buffers in, host buffers out (H2D + kernels + D2H inside the call) ------------------ */
 

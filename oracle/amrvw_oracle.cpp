@@ -953,18 +953,32 @@ static void amrvw_algorithm_ms(State<double>& s, std::vector<cplx>& EIGS, Rng& r
             if (ctr.stop_index < lo) break;
             ctr.zero_index = 0; ctr.start_index = 1;
             check_deflation(s, ctr);
-        } else if (delta <= P.small || ctr.it_count == 0) {
-            int64_t t0 = st.turnovers;
-            bulge_step(s, ctr, rng, st);
+        } else if (delta <= P.small) {
+            // small bottom window: it is decoupled (Q[start-1] is diagonal), so finish it completely with
+            // the reference schedule (on the GPU: one lane, window staged in shared memory)
+            const int lo2 = ctr.start_index, hi2 = ctr.stop_index;
+            const int64_t t0 = st.turnovers;
+            Counter c2 = {lo2 - 1, lo2, hi2, ctr.it_count, -1};
+            bool ok = driver_window(s, lo2, hi2, c2, EIGS, rng, st, 20 * (int64_t)(hi2 - lo2 + 1));
             st.serial_turnovers += st.turnovers - t0;
-            ctr.it_count -= 1;
+            if (!ok) st.unconverged += c2.stop_index - lo2 + 2;
+            if (lo2 == 2) { diagonal_block(s, 1, A); EIGS[1] = to_c(A[0]); }   // slot 1 is a 1x1 block above Q[1]
+            ctr.stop_index = lo2 - 2; ctr.zero_index = 0; ctr.start_index = 1; ctr.it_count = IT_COUNT;
+            if (ctr.stop_index >= lo) check_deflation(s, ctr);
+        } else if (ctr.it_count == 0) {
+            // stagnation on a large window: a fat step of L exceptional (random) bulges
+            ++st.fat_steps;
+            st.pipe_steps += (ctr.stop_index - ctr.start_index + 1) + 3 * (P.L - 1);
+            for (int b = 0; b < P.L; ++b) { ctr.it_count = 0; bulge_step(s, ctr, rng, st); }
+            ctr.it_count = IT_COUNT - 1;
         } else {
-            int m = std::min(2 * P.L / P.reuse, delta - 1);
-            m -= m % 2;
+            // sub-window of m rotators -> m+1 eigenvalues -> (m+1)/2 shift pairs <= L/reuse: m must be odd
+            int m = std::min(2 * P.L / P.reuse - 1, delta - 1);
+            if (m % 2 == 0) m -= 1;
             std::vector<cplx> sh, pairs;
             Stats sub;
             ms_shifts(s, ctr, m, sh, rng, sub);
-            st.turnovers += sub.turnovers;  // executed work; kept separately from the reference count by the caller
+            st.turnovers += sub.turnovers;  // executed work
             st.serial_turnovers += sub.turnovers;
             st.pipe_steps += (ctr.stop_index - ctr.start_index + 1) + 3 * (P.L - 1);
             ms_pair_shifts(sh, pairs);
