@@ -54,6 +54,8 @@ _libs = {}
 
 
 def lib_path(strict=False):
+    if not strict and os.environ.get("AMRVW_B200_LIB"):      # development: try an alternative build of the same ABI
+        return os.environ["AMRVW_B200_LIB"]
     return os.path.join(HERE, "libamrvw_b200_strict.so" if strict else "libamrvw_b200.so")
 
 

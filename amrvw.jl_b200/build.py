@@ -33,7 +33,7 @@ def _stale(out):
 def build(strict=True, force=False, verbose=False):
     outs = [(os.path.join(HERE, "libamrvw_b200.so"), [])]
     if strict:
-        outs.append((os.path.join(HERE, "libamrvw_b200_strict.so"), ["-fmad=false"]))
+        outs.append((os.path.join(HERE, "libamrvw_b200_strict.so"), ["-fmad=false", "-DAMRVW_STRICT"]))
     for out, extra in outs:
         if not force and not _stale(out):
             continue

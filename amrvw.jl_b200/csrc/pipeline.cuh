@@ -55,7 +55,7 @@ AMRVW_DI void stg_rot(Rot<double>* p, const Rot<double> r) { *reinterpret_cast<d
 #define AMRVW_TURN(a, b, c, o1, o2, o3)      \
     do {                                      \
         Rot<double> t1_, t2_, t3_;            \
-        turnover(a, b, c, t1_, t2_, t3_);     \
+        turnover_fast(a, b, c, t1_, t2_, t3_); \
         o1 = t1_; o2 = t2_; o3 = t3_;         \
     } while (0)
 
@@ -181,8 +181,11 @@ AMRVW_DI int phase_a(Fact<double, false>& F, LeaderState& ls, cplx* E, const Gro
     return 0;
 }
 
+#ifndef AMRVW_PIPE_MINBLOCKS
+#define AMRVW_PIPE_MINBLOCKS 6
+#endif
 template <int L, int WPB>
-__global__ void __launch_bounds__(32 * WPB) roots_pipelined_kernel(Problem<double> pr, PipeParams pp) {
+__global__ void __launch_bounds__(32 * WPB, AMRVW_PIPE_MINBLOCKS) roots_pipelined_kernel(Problem<double> pr, PipeParams pp) {
     constexpr int G = 32 / L;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int wib = threadIdx.x >> 5, lane32 = threadIdx.x & 31;
@@ -323,7 +326,7 @@ __global__ void __launch_bounds__(32 * WPB) roots_pipelined_kernel(Problem<doubl
                     Rot<double> w = q0;
                     w.s = sign_(ptop) * w.s;
                     Rot<double> r1, r2, r3;
-                    turnover(adjoint(U), adjoint(V), w, r1, r2, r3);
+                    turnover_fast(adjoint(U), adjoint(V), w, r1, r2, r3);
                     W = r1;
                     q1 = fuse(r3, q1);
                     r2.s = sign_(ptop) * r2.s;

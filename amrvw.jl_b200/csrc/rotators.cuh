@@ -18,6 +18,7 @@
 namespace amrvw {
 
 #define AMRVW_DI __device__ __forceinline__
+#define AMRVW_NI __device__ __noinline__
 
 // ---------------------------------------------------------------- complex scalar (ComplexF64)
 struct cplx {
@@ -232,8 +233,22 @@ AMRVW_DI Rot<cplx> fuse(Rot<cplx> a, Rot<cplx> b, cplx& dphase) {
 
 // ---------------------------------------------------------------- turnover (transformations.jl:158-229)
 // Q1@i Q2@(i+-1) Q3@i  ->  R1@(i+-1) R2@i R3@(i+-1), same product.  37 flop real / 94 complex.
+//
+// Three forms of the same operation:
+//   turnover_ieee  the reference's formulas operation by operation (IEEE sqrt and divisions, all
+//                  special cases): ~170 dependent FP64-pipe instructions once div/sqrt are expanded.
+//   turnover_fast  real case, the common path without any division: 1/r by rsqrt, and the
+//                  reference's b = s1 s2 / s5 rewritten with s5 = -r (1 - d/2), 1/(1 - d/2) = 1 + d/2
+//                  + O(d^2), d = O(u).  ~45 instructions; anything unusual (zero or denormal norm)
+//                  goes to the out-of-line IEEE copy.  Results differ from turnover_ieee in the last
+//                  bit or two, and are renormalised by the same first-order correction.
+//   turnover       what the serial code calls: ONE out-of-line copy per scalar type (the whole
+//                  iteration inlined 30 times over was 560 KB of SASS and ran out of the I-cache).
+// -DAMRVW_STRICT (the no-FMA build used by the bit-parity tests) maps everything to turnover_ieee.
+template <class S> struct Rot3 { Rot<S> r1, r2, r3; };
+
 template <class S>
-AMRVW_DI void turnover(const Rot<S> q1, const Rot<S> q2, const Rot<S> q3, Rot<S>& r1, Rot<S>& r2, Rot<S>& r3) {
+AMRVW_DI void turnover_ieee(const Rot<S> q1, const Rot<S> q2, const Rot<S> q3, Rot<S>& r1, Rot<S>& r2, Rot<S>& r3) {
     const S c1 = q1.c, c2 = q2.c, c3 = q3.c;
     const double s1 = q1.s, s2 = q2.s, s3 = q3.s;
     const S u21 = (-c2) * s3 * conj_(c1) - c3 * s1;
@@ -265,6 +280,62 @@ AMRVW_DI void turnover(const Rot<S> q1, const Rot<S> q2, const Rot<S> q3, Rot<S>
     r1 = make_rot<S>(c4, s4);
     r2 = make_rot<S>(c5, s5);
     r3 = make_rot<S>(c6, s6);
+}
+
+template <class S> AMRVW_NI Rot3<S> turnover_ieee_call(const Rot<S> q1, const Rot<S> q2, const Rot<S> q3) {
+    Rot3<S> o;
+    turnover_ieee(q1, q2, q3, o.r1, o.r2, o.r3);
+    return o;
+}
+
+// division-free common path (real); returns false when the caller must take the general path
+AMRVW_DI bool turnover_fast_try(const Rot<double> q1, const Rot<double> q2, const Rot<double> q3, Rot<double>& r1, Rot<double>& r2, Rot<double>& r3) {
+    const double c1 = q1.c, s1 = q1.s, c2 = q2.c, s2 = q2.s, c3 = q3.c, s3 = q3.s;
+    const double u21 = -c2 * s3 * c1 - c3 * s1;
+    const double u31 = s2 * s3;
+    const double u11 = c1 * c3 - c2 * s1 * s3;
+    const double x = u21 * u21 + u31 * u31;
+    const double rinv = rsqrt(x);
+    const double c4 = u21 * rinv, s4 = -(u31 * rinv);
+    const double r4 = x * rinv;
+    const double h5 = 0.5 * (u11 * u11 + (x - 1.0));
+    const double rho5 = 1.0 - h5;
+    const double a = c1 * s2 * s4 + c2 * c4;
+    const double b = -(s1 * s2) * rinv * (1.0 + h5);
+    const double rho6 = 1.0 - 0.5 * (a * a + b * b - 1.0);
+    r1 = make_rot<double>(c4, s4);
+    r2 = make_rot<double>(u11 * rho5, -(r4 * rho5));
+    r3 = make_rot<double>(a * rho6, b * rho6);
+    return x >= 1e-280;   // also false for NaN
+}
+AMRVW_DI void turnover_fast(const Rot<double> q1, const Rot<double> q2, const Rot<double> q3, Rot<double>& r1, Rot<double>& r2, Rot<double>& r3) {
+#ifdef AMRVW_STRICT
+    const Rot3<double> o = turnover_ieee_call<double>(q1, q2, q3);
+    r1 = o.r1; r2 = o.r2; r3 = o.r3;
+#else
+    if (!turnover_fast_try(q1, q2, q3, r1, r2, r3)) {
+        const Rot3<double> o = turnover_ieee_call<double>(q1, q2, q3);
+        r1 = o.r1; r2 = o.r2; r3 = o.r3;
+    }
+#endif
+}
+AMRVW_NI Rot3<double> turnover_fast_call(const Rot<double> q1, const Rot<double> q2, const Rot<double> q3) {
+    Rot3<double> o;
+    turnover_fast(q1, q2, q3, o.r1, o.r2, o.r3);
+    return o;
+}
+// the serial code's turnover: one out-of-line copy
+AMRVW_DI void turnover(const Rot<double> q1, const Rot<double> q2, const Rot<double> q3, Rot<double>& r1, Rot<double>& r2, Rot<double>& r3) {
+#ifdef AMRVW_STRICT
+    const Rot3<double> o = turnover_ieee_call<double>(q1, q2, q3);
+#else
+    const Rot3<double> o = turnover_fast_call(q1, q2, q3);
+#endif
+    r1 = o.r1; r2 = o.r2; r3 = o.r3;
+}
+AMRVW_DI void turnover(const Rot<cplx> q1, const Rot<cplx> q2, const Rot<cplx> q3, Rot<cplx>& r1, Rot<cplx>& r2, Rot<cplx>& r3) {
+    const Rot3<cplx> o = turnover_ieee_call<cplx>(q1, q2, q3);
+    r1 = o.r1; r2 = o.r2; r3 = o.r3;
 }
 
 // ---------------------------------------------------------------- 2x2 eigenvalues

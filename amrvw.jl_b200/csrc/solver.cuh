@@ -103,7 +103,7 @@ template <class S, bool P> AMRVW_DI S r_entry(const Fact<S, P>& F, int l, int k)
     }
 }
 // A = (Q R)[j:j+1, j:j+1]   (diagonal-block.jl:12-36)
-template <class S, bool P> AMRVW_DI void diagonal_block(const Fact<S, P>& F, int j, S A[4]) {
+template <class S, bool P> AMRVW_NI void diagonal_block(const Fact<S, P>& F, int j, S A[4]) {
     S qji, qjj, qjk, qkj, qkk;
     q_block(F, j, qji, qjj, qjk, qkj, qkk);
     const int i = j - 1, k = j + 1;
@@ -163,7 +163,7 @@ template <class S, bool P> AMRVW_DI void pass_Q(Fact<S, P>& F, Rot<S>& U, int& i
     pass_desc(F, F.Q, U, i);
 }
 // phase push-down (diagonal.jl:199-225): Diag(alpha)@i moves down Q into D_Q
-template <bool P> AMRVW_DI void push_phase(Fact<cplx, P>& F, cplx alpha, int i) {
+template <bool P> AMRVW_NI void push_phase(Fact<cplx, P>& F, cplx alpha, int i) {
     const int M = F.N - 1;
     F.DQ[i] = F.DQ[i] * alpha;
     const cplx ca = conj_(alpha);
@@ -183,7 +183,7 @@ struct Shifts { cplx e1, e2; };
 // create_bulge (create-bulge.jl:20-77).  given != nullptr: use these shifts instead of the
 // eigenvalues of block(stop) (multishift schedule).
 template <bool P>
-AMRVW_DI void create_bulge_rds(Fact<double, P>& F, Counter& ctr, Rot<double>& U, Rot<double>& V, const Shifts* given,
+AMRVW_NI void create_bulge_rds(Fact<double, P>& F, Counter& ctr, Rot<double>& U, Rot<double>& V, const Shifts* given,
                                uint64_t seed, uint64_t poly, int& rng_ordinal, PolyStats& st) {
     const int i = ctr.start_index;
     if (ctr.it_count == 0 && !given) {
@@ -215,7 +215,7 @@ AMRVW_DI void create_bulge_rds(Fact<double, P>& F, Counter& ctr, Rot<double>& U,
 }
 
 template <bool P>
-AMRVW_DI void bulge_step(Fact<double, P>& F, Counter& ctr, const Shifts* given, uint64_t seed, uint64_t poly, int& rng_ordinal, PolyStats& st) {
+AMRVW_NI void bulge_step(Fact<double, P>& F, Counter& ctr, const Shifts* given, uint64_t seed, uint64_t poly, int& rng_ordinal, PolyStats& st) {
     st.sweeps++;
     Rot<double> U, V, W;
     create_bulge_rds(F, ctr, U, V, given, seed, poly, rng_ordinal, st);
@@ -275,7 +275,7 @@ template <bool P> AMRVW_DI void deflate(Fact<double, P>& F, int k) { F.Q[k] = ma
 
 // ---------------------------------------------------------------- bulge step, complex single shift
 template <bool P>
-AMRVW_DI void bulge_step(Fact<cplx, P>& F, Counter& ctr, const Shifts* given, uint64_t seed, uint64_t poly, int& rng_ordinal, PolyStats& st) {
+AMRVW_NI void bulge_step(Fact<cplx, P>& F, Counter& ctr, const Shifts* given, uint64_t seed, uint64_t poly, int& rng_ordinal, PolyStats& st) {
     st.sweeps++;
     cplx A[4];
     cplx shift;
@@ -339,7 +339,7 @@ template <bool P> AMRVW_DI void deflate(Fact<cplx, P>& F, int k) {  // CSS.jl:98
 // ---------------------------------------------------------------- driver
 #define AMRVW_EPS 2.220446049250313e-16
 
-template <class S, bool P> AMRVW_DI void check_deflation(Fact<S, P>& F, Counter& ctr) {  // AMRVW_algorithm.jl:181-202
+template <class S, bool P> AMRVW_NI void check_deflation(Fact<S, P>& F, Counter& ctr) {  // AMRVW_algorithm.jl:181-202
     for (int k = ctr.stop_index; k >= ctr.start_index; --k) {
         if (fabs(F.Q[k].s) <= AMRVW_EPS) {
             deflate(F, k);
@@ -424,7 +424,7 @@ AMRVW_DI bool isequal_(double a, double b) { return (a == b && signbit(a) == sig
 AMRVW_DI bool eig_less(cplx a, cplx b) { return isless_(a.re, b.re) || (isequal_(a.re, b.re) && isless_(a.im, b.im)); }
 
 // in-place heap sort of E[0..n): O(n log n) compares, no extra memory, 0.1% of the flops
-AMRVW_DI void sort_roots(cplx* E, int n) {
+AMRVW_NI void sort_roots(cplx* E, int n) {
     auto sift = [&](int start, int end) {
         int root = start;
         const cplx v = E[root];
