@@ -162,6 +162,7 @@ static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, cons
         for (int c = 0; c < nd; ++c) { int rc = reserve(ctx, ctx->diags[c], slots * sizeof(S)); if (rc) return rc; }
     }
     { int rc = reserve(ctx, ctx->stats, (size_t)nbatch * sizeof(PolyStats) + sizeof(StatsAccum)); if (rc) return rc; }
+    if (var == V_RDS) { int rc = reserve(ctx, ctx->shifts, slots * sizeof(int)); if (rc) return rc; }
 
     Problem<S> pr;
     pr.coeffs = d_a; pr.ws = d_w; pr.offsets = (const long long*)d_offsets; pr.nbatch = nbatch;
@@ -170,6 +171,7 @@ static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, cons
     pr.Q = (Rot<S>*)ctx->chains[0].ptr; pr.B = (Rot<S>*)ctx->chains[1].ptr; pr.Ct = (Rot<S>*)ctx->chains[2].ptr;
     pr.WB = (Rot<S>*)ctx->chains[3].ptr; pr.WCt = (Rot<S>*)ctx->chains[4].ptr;
     pr.DQ = (S*)ctx->diags[0].ptr; pr.DR = (S*)ctx->diags[1].ptr; pr.WD = (S*)ctx->diags[2].ptr;
+    pr.dstack = (int*)ctx->shifts.ptr;
     pr.extra = extra;
     pr.seed = ctx->opt.seed;
 

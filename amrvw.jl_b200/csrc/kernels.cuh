@@ -18,6 +18,7 @@ template <class S> struct Problem {
     // workspace: chains are arrays of `slots` rotators; polynomial p starts at slot offsets[p] + extra*p
     Rot<S>* Q; Rot<S>* B; Rot<S>* Ct; Rot<S>* WB; Rot<S>* WCt;
     S* DQ; S* DR; S* WD;
+    int* dstack;              // pipelined kernel: per-polynomial stack of deflated Q indices (same slot layout)
     int extra;                // 1 (non-pencil: len+1 slots) or 2 (pencil: N+2 slots)
     unsigned long long seed;
 };

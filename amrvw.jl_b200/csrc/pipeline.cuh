@@ -79,25 +79,78 @@ AMRVW_DI Fact<double, false> stage_window(const Fact<double, false>& F, const Gr
     return W;
 }
 
+// The 24 doubles a lane owns during a chase step: its window of Q, B, Ct and its bulge.
+struct StepState {
+    Rot<double> q0, q1, q2, b0, b1, b2, c0, c1, c2, U, V, W;
+};
+
+// General-path versions of the chase step (all special cases of the turnover), out of line: taken
+// when the division-free step flags a degenerate turnover, and for the last position of a bulge.
+AMRVW_NI void chase_step_general(StepState& z) {
+    turnover(z.b1, z.b2, z.V, z.V, z.b1, z.b2);
+    turnover(z.c2, z.c1, z.V, z.V, z.c2, z.c1);
+    turnover(z.b0, z.b1, z.U, z.U, z.b0, z.b1);
+    turnover(z.c1, z.c0, z.U, z.U, z.c1, z.c0);
+    turnover(z.q1, z.q2, z.V, z.V, z.q1, z.q2);
+    turnover(z.q0, z.q1, z.U, z.U, z.q0, z.q1);
+    turnover(z.W, z.V, z.U, z.V, z.U, z.W);
+}
+// last position (j == stop): passthrough_triu, then fuse the bulge into Q (RDS.jl:110-128)
+AMRVW_NI void chase_step_final(StepState& z, double pbot) {
+    turnover(z.b1, z.b2, z.V, z.V, z.b1, z.b2);
+    turnover(z.c2, z.c1, z.V, z.V, z.c2, z.c1);
+    turnover(z.b0, z.b1, z.U, z.U, z.b0, z.b1);
+    turnover(z.c1, z.c0, z.U, z.U, z.c1, z.c0);
+    z.V.s = sign_(pbot) * z.V.s;
+    z.q1 = fuse(z.q1, z.V);
+    turnover(z.q0, z.q1, z.U, z.U, z.q0, z.q1);
+    z.U = fuse(z.W, z.U);
+    turnover(z.b1, z.b2, z.U, z.U, z.b1, z.b2);
+    turnover(z.c2, z.c1, z.U, z.U, z.c2, z.c1);
+    z.U.s = sign_(pbot) * z.U.s;
+    z.q1 = fuse(z.q1, z.U);
+}
+
 struct LeaderState {
     Counter ctr;
     long long kk, it_max;
     int ord;
     int unconv;
-    bool started;
+    int sp;        // size of the deflation stack
 };
+
+// check_deflation (AMRVW_algorithm.jl:181-202) without the O(window) scan.  The reference scans
+// k = stop..start for the first |s_k| <= eps.  Here every deflatable rotator is recorded when the
+// chase writes it back (ascending index order, so the top of the stack is the highest one), and
+// rotators above the active window never change, so "highest deflatable index <= stop" is the top of
+// the stack: O(1) instead of n^2/4 dependent loads per polynomial (20% of the kernel in the ncu
+// source view before this).
+AMRVW_DI void check_deflation_stack(Fact<double, false>& F, LeaderState& ls, const int* dstack) {
+    if (ls.sp > 0) {
+        const int k = dstack[ls.sp - 1];
+        if (k >= ls.ctr.start_index && k <= ls.ctr.stop_index) {
+            deflate(F, k);
+            ls.ctr.zero_index = k;
+            ls.ctr.start_index = k + 1;
+            ls.ctr.it_count = 15;
+        }
+    }
+}
+// the window below rotator zero_index is finished: drop that boundary, expose the one above it
+AMRVW_DI void pop_window(LeaderState& ls) {
+    if (ls.ctr.zero_index > 0 && ls.sp > 0) ls.sp -= 1;
+}
 
 // Phase A: the driver (AMRVW_algorithm.jl:10-138) up to the next fat step.  Returns 0 when the
 // polynomial is finished, 1 for a fat step with shifts in shl[0..nb), 2 for a fat step of nb
 // exceptional (random) bulges.
 AMRVW_DI int phase_a(Fact<double, false>& F, LeaderState& ls, cplx* E, const GroupScratch& sc, Shifts* shl, const int L, const PipeParams pp,
-                     int& nb, const uint64_t seed, const uint64_t poly, PolyStats& st) {
+                     int& nb, const uint64_t seed, const uint64_t poly, PolyStats& st, const int* dstack) {
     Counter& ctr = ls.ctr;
     double A[4];
-    if (!ls.started) { check_deflation(F, ctr); ls.started = true; }
     while (ls.kk <= ls.it_max) {
         if (ctr.stop_index < 1) return 0;
-        check_deflation(F, ctr);
+        check_deflation_stack(F, ls, dstack);
         ++ls.kk;
         const int k = ctr.stop_index;
         const int delta = ctr.stop_index - ctr.zero_index;
@@ -107,28 +160,31 @@ AMRVW_DI int phase_a(Fact<double, false>& F, LeaderState& ls, cplx* E, const Gro
             eig2x2(A, e1, e2);
             E[k] = e1; E[k + 1] = e2;
             if (ctr.stop_index == 2) { diagonal_block(F, 1, A); E[1] = to_c(A[0]); ctr.stop_index = 0; return 0; }
+            pop_window(ls);
             ctr.stop_index = ctr.zero_index - 1; ctr.zero_index = 0; ctr.start_index = 1;
-            check_deflation(F, ctr);
+            check_deflation_stack(F, ls, dstack);
             if (ctr.stop_index < 1) return 0;
         } else if (delta <= 0) {
             diagonal_block(F, k, A);
             if (ctr.stop_index == 1) { E[1] = to_c(A[0]); E[2] = to_c(A[3]); ctr.stop_index = 0; return 0; }
             E[k + 1] = to_c(A[3]);
+            pop_window(ls);
             ctr.stop_index = ctr.zero_index - 1;
             if (ctr.stop_index < 1) return 0;
             ctr.zero_index = 0; ctr.start_index = 1;
-            check_deflation(F, ctr);
+            check_deflation_stack(F, ls, dstack);
         } else if (delta <= pp.small) {
             // decoupled small window [lo2, hi2]: finish it in shared memory, one bulge at a time
             const int lo2 = ctr.start_index, hi2 = ctr.stop_index;
             Fact<double, false> W = stage_window(F, sc, lo2 - 1, hi2);
             Counter c2 = {lo2 - 1, lo2, hi2, ctr.it_count, -1};
-            const int left = drive_window(W, lo2, hi2, c2, E, 20ll * (hi2 - lo2 + 1), seed, poly, ls.ord, st, ReferenceStep());
+            const int left = drive_window(W, lo2, hi2, c2, E, ls.it_max, seed, poly, ls.ord, st, ReferenceStep());   // the reference's cap is global (20 n)
             F.turnovers += W.turnovers;
             ls.unconv += left;
             if (lo2 == 2) { diagonal_block(F, 1, A); E[1] = to_c(A[0]); }
+            pop_window(ls);
             ctr.stop_index = lo2 - 2; ctr.zero_index = 0; ctr.start_index = 1; ctr.it_count = 15;
-            if (ctr.stop_index >= 1) check_deflation(F, ctr);
+            if (ctr.stop_index >= 1) check_deflation_stack(F, ls, dstack);
         } else if (ctr.it_count == 0) {
             st.fat_steps++;
             nb = L;
@@ -198,6 +254,9 @@ __global__ void __launch_bounds__(32 * WPB, AMRVW_PIPE_MINBLOCKS) roots_pipeline
     const size_t per_group = (size_t)pp.ms * (3 * sizeof(Rot<double>) + sizeof(cplx));
     const size_t per_warp = 32 * sizeof(Shifts) + G * per_group;
     unsigned char* wbase = smem_raw + (size_t)wib * per_warp;
+    [[maybe_unused]] constexpr int NT = 32 * WPB;
+    double2* snap = reinterpret_cast<double2*>(smem_raw + (size_t)WPB * per_warp);   // [12][NT] step snapshots
+    (void)snap;
     Shifts* shl = reinterpret_cast<Shifts*>(wbase) + grp * L;
     GroupScratch sc;
     {
@@ -214,15 +273,17 @@ __global__ void __launch_bounds__(32 * WPB, AMRVW_PIPE_MINBLOCKS) roots_pipeline
     F.Q = F.B = F.Ct = F.WB = F.WCt = nullptr; F.DQ = F.DR = F.WD = nullptr;
     PolyStats st = {0, 0, 0, 0, 0};
     LeaderState ls;
-    ls.kk = 0; ls.it_max = 0; ls.ord = 0; ls.unconv = 0; ls.started = false;
+    ls.kk = 0; ls.it_max = 0; ls.ord = 0; ls.unconv = 0; ls.sp = 0;
     ls.ctr = {0, 1, 0, 15, -1};
     cplx* out = nullptr;
+    int* dstack = nullptr;
     int N = 0, K = 0;
     int mode = 0;   // 0: nothing to do / finished, 1: fat step, 2: exceptional fat step
     bool iterating = false;
     if (valid) {
         const long long off = pr.offsets[p];
         out = pr.roots + (off - p);
+        dstack = pr.dstack + (off + (long long)pr.extra * p);
         if (leader) {
             const int len = (int)(pr.offsets[p + 1] - off);
             int first, last;
@@ -259,7 +320,7 @@ __global__ void __launch_bounds__(32 * WPB, AMRVW_PIPE_MINBLOCKS) roots_pipeline
         // ---------------- phase A
         mode = 0;
         if (leader && iterating) {
-            mode = phase_a(F, ls, out - 1, sc, shl, L, pp, nb, pr.seed, (uint64_t)p, st);
+            mode = phase_a(F, ls, out - 1, sc, shl, L, pp, nb, pr.seed, (uint64_t)p, st, dstack);
             if (mode == 0) iterating = false;
         }
         __syncwarp();
@@ -270,6 +331,7 @@ __global__ void __launch_bounds__(32 * WPB, AMRVW_PIPE_MINBLOCKS) roots_pipeline
         const int start = __shfl_sync(0xffffffffu, ls.ctr.start_index, grp * L);
         const int stop = __shfl_sync(0xffffffffu, ls.ctr.stop_index, grp * L);
         const int ord0 = __shfl_sync(0xffffffffu, ls.ord, grp * L);
+        int sp = __shfl_sync(0xffffffffu, ls.sp, grp * L);
         const bool act = mode != 0;
         const int T = act ? (stop - start + 3 * L + 1) : 0;
         const int Tmax = __reduce_max_sync(0xffffffffu, T);
@@ -333,36 +395,58 @@ __global__ void __launch_bounds__(32 * WPB, AMRVW_PIPE_MINBLOCKS) roots_pipeline
                     q0 = r2;
                     my_turnovers += 1;
                 }
-                // passthrough_triu (RDS.jl:42-70): V then U through B and Ct
-                AMRVW_TURN(b1, b2, V, V, b1, b2);
-                AMRVW_TURN(c2, c1, V, V, c2, c1);
-                AMRVW_TURN(b0, b1, U, U, b0, b1);
-                AMRVW_TURN(c1, c0, U, U, c1, c0);
                 if (i <= stop - 2) {
-                    // passthrough_Q (RDS.jl:97-108): V, U through Q, then the limb turnover
-                    AMRVW_TURN(q1, q2, V, V, q1, q2);
-                    AMRVW_TURN(q0, q1, U, U, q0, q1);
-                    AMRVW_TURN(W, V, U, V, U, W);
+                    // regular position: the 7 turnovers of one chase step (RDS.jl:42-70, 97-108) as ONE
+                    // straight-line block, so the independent ones (T2|T3, T4|T5) overlap.  The inputs are
+                    // parked in shared memory first; a degenerate turnover (flagged, essentially never)
+                    // redoes the step on the general path from that snapshot.
+#ifndef AMRVW_STRICT
+                    double2* sn = snap + threadIdx.x;
+                    sn[0 * NT] = make_double2(q0.c, q0.s); sn[1 * NT] = make_double2(q1.c, q1.s); sn[2 * NT] = make_double2(q2.c, q2.s);
+                    sn[3 * NT] = make_double2(b0.c, b0.s); sn[4 * NT] = make_double2(b1.c, b1.s); sn[5 * NT] = make_double2(b2.c, b2.s);
+                    sn[6 * NT] = make_double2(c0.c, c0.s); sn[7 * NT] = make_double2(c1.c, c1.s); sn[8 * NT] = make_double2(c2.c, c2.s);
+                    sn[9 * NT] = make_double2(U.c, U.s); sn[10 * NT] = make_double2(V.c, V.s); sn[11 * NT] = make_double2(W.c, W.s);
+                    bool ok = true;
+                    Rot<double> t1, t2, t3;
+                    ok &= turnover_fast_try(b1, b2, V, t1, t2, t3); V = t1; b1 = t2; b2 = t3;
+                    ok &= turnover_fast_try(c2, c1, V, t1, t2, t3); V = t1; c2 = t2; c1 = t3;
+                    ok &= turnover_fast_try(b0, b1, U, t1, t2, t3); U = t1; b0 = t2; b1 = t3;
+                    ok &= turnover_fast_try(c1, c0, U, t1, t2, t3); U = t1; c1 = t2; c0 = t3;
+                    ok &= turnover_fast_try(q1, q2, V, t1, t2, t3); V = t1; q1 = t2; q2 = t3;
+                    ok &= turnover_fast_try(q0, q1, U, t1, t2, t3); U = t1; q0 = t2; q1 = t3;
+                    ok &= turnover_fast_try(W, V, U, t1, t2, t3); V = t1; U = t2; W = t3;
+                    if (!ok) {
+                        StepState z;
+                        double2 v;
+                        v = sn[0 * NT]; z.q0 = make_rot<double>(v.x, v.y); v = sn[1 * NT]; z.q1 = make_rot<double>(v.x, v.y); v = sn[2 * NT]; z.q2 = make_rot<double>(v.x, v.y);
+                        v = sn[3 * NT]; z.b0 = make_rot<double>(v.x, v.y); v = sn[4 * NT]; z.b1 = make_rot<double>(v.x, v.y); v = sn[5 * NT]; z.b2 = make_rot<double>(v.x, v.y);
+                        v = sn[6 * NT]; z.c0 = make_rot<double>(v.x, v.y); v = sn[7 * NT]; z.c1 = make_rot<double>(v.x, v.y); v = sn[8 * NT]; z.c2 = make_rot<double>(v.x, v.y);
+                        v = sn[9 * NT]; z.U = make_rot<double>(v.x, v.y); v = sn[10 * NT]; z.V = make_rot<double>(v.x, v.y); v = sn[11 * NT]; z.W = make_rot<double>(v.x, v.y);
+                        chase_step_general(z);
+                        q0 = z.q0; q1 = z.q1; q2 = z.q2; b0 = z.b0; b1 = z.b1; b2 = z.b2; c0 = z.c0; c1 = z.c1; c2 = z.c2; U = z.U; V = z.V; W = z.W;
+                    }
+#else
+                    StepState z = {q0, q1, q2, b0, b1, b2, c0, c1, c2, U, V, W};
+                    chase_step_general(z);
+                    q0 = z.q0; q1 = z.q1; q2 = z.q2; b0 = z.b0; b1 = z.b1; b2 = z.b2; c0 = z.c0; c1 = z.c1; c2 = z.c2; U = z.U; V = z.V; W = z.W;
+#endif
                     my_turnovers += 7;
                 } else {
-                    // last position (j == stop): fuse the bulge into Q (RDS.jl:110-128)
-                    V.s = sign_(pbot) * V.s;
-                    q1 = fuse(q1, V);
-                    AMRVW_TURN(q0, q1, U, U, q0, q1);
-                    U = fuse(W, U);
-                    AMRVW_TURN(b1, b2, U, U, b1, b2);
-                    AMRVW_TURN(c2, c1, U, U, c2, c1);
-                    U.s = sign_(pbot) * U.s;
-                    q1 = fuse(q1, U);
+                    StepState z = {q0, q1, q2, b0, b1, b2, c0, c1, c2, U, V, W};
+                    chase_step_final(z, pbot);
+                    q0 = z.q0; q1 = z.q1; q2 = z.q2; b0 = z.b0; b1 = z.b1; b2 = z.b2; c0 = z.c0; c1 = z.c1; c2 = z.c2; U = z.U; V = z.V; W = z.W;
                     my_turnovers += 7;
                 }
             }
             // retire: the last lane writes index i back
             if (lane == L - 1 && act && i >= start && i <= stop + 1) {
                 stg_rot(F.Q + i, q0); stg_rot(F.B + i, b0); stg_rot(F.Ct + i, c0);
+                if (i <= stop && fabs(q0.s) <= AMRVW_EPS) dstack[sp++] = i;   // deflatable: record for phase A
             }
         }
+        sp = __shfl_sync(0xffffffffu, sp, grp * L + L - 1);
         if (leader && act) {
+            ls.sp = sp;
             st.sweeps += nb;
             if (mode == 2) { st.exceptional += nb; ls.ord += nb; ls.ctr.it_count = 14; }
         }
@@ -384,7 +468,7 @@ static int launch_pipelined_L(const Problem<double>& pr, PipeParams pp, cudaStre
     constexpr int WPB = 2;
     constexpr int G = 32 / L;
     const size_t per_warp = 32 * sizeof(Shifts) + (size_t)G * pp.ms * (3 * sizeof(Rot<double>) + sizeof(cplx));
-    const size_t smem = WPB * per_warp;
+    const size_t smem = WPB * per_warp + (size_t)12 * 32 * WPB * sizeof(double2);
     const long long groups_per_block = (long long)WPB * G;
     const int blocks = (int)((pr.nbatch + groups_per_block - 1) / groups_per_block);
     auto kern = roots_pipelined_kernel<L, WPB>;

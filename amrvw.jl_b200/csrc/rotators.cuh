@@ -288,6 +288,24 @@ template <class S> AMRVW_NI Rot3<S> turnover_ieee_call(const Rot<S> q1, const Ro
     return o;
 }
 
+// 1/sqrt(x) for x in the normal range: MUFU.RSQ64H seed + two Newton steps (no special-case branches;
+// callers guard the range)
+AMRVW_DI double rsqrt_nr(double x) {
+#ifdef AMRVW_STRICT
+    return 1.0 / sqrt(x);
+#else
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double t = x * y;
+    double e = fma(-t, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    t = x * y;
+    e = fma(-t, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    return y;
+#endif
+}
+
 // division-free common path (real); returns false when the caller must take the general path
 AMRVW_DI bool turnover_fast_try(const Rot<double> q1, const Rot<double> q2, const Rot<double> q3, Rot<double>& r1, Rot<double>& r2, Rot<double>& r3) {
     const double c1 = q1.c, s1 = q1.s, c2 = q2.c, s2 = q2.s, c3 = q3.c, s3 = q3.s;
@@ -295,7 +313,7 @@ AMRVW_DI bool turnover_fast_try(const Rot<double> q1, const Rot<double> q2, cons
     const double u31 = s2 * s3;
     const double u11 = c1 * c3 - c2 * s1 * s3;
     const double x = u21 * u21 + u31 * u31;
-    const double rinv = rsqrt(x);
+    const double rinv = rsqrt_nr(x);
     const double c4 = u21 * rinv, s4 = -(u31 * rinv);
     const double r4 = x * rinv;
     const double h5 = 0.5 * (u11 * u11 + (x - 1.0));

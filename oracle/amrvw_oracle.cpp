@@ -959,7 +959,7 @@ static void amrvw_algorithm_ms(State<double>& s, std::vector<cplx>& EIGS, Rng& r
             const int lo2 = ctr.start_index, hi2 = ctr.stop_index;
             const int64_t t0 = st.turnovers;
             Counter c2 = {lo2 - 1, lo2, hi2, ctr.it_count, -1};
-            bool ok = driver_window(s, lo2, hi2, c2, EIGS, rng, st, 20 * (int64_t)(hi2 - lo2 + 1));
+            bool ok = driver_window(s, lo2, hi2, c2, EIGS, rng, st, it_max);   // the reference's cap is global (20 n)
             st.serial_turnovers += st.turnovers - t0;
             if (!ok) st.unconverged += c2.stop_index - lo2 + 2;
             if (lo2 == 2) { diagonal_block(s, 1, A); EIGS[1] = to_c(A[0]); }   // slot 1 is a 1x1 block above Q[1]
