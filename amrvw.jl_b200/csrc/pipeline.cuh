@@ -52,6 +52,16 @@ AMRVW_DI Rot<double> ldg_rot(const Rot<double>* p) {
 }
 AMRVW_DI void stg_rot(Rot<double>* p, const Rot<double> r) { *reinterpret_cast<double2*>(p) = make_double2(r.c, r.s); }
 
+// 16-byte asynchronous global->shared copy (LDGSTS): lane 0's look-ahead of the next chain index goes
+// through shared memory so that it holds no registers across the chase step (with the value kept in
+// registers ptxas spilled it, and the spill store waited for the load: 14% of all stall samples).
+AMRVW_DI void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+AMRVW_DI void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+AMRVW_DI void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 #define AMRVW_TURN(a, b, c, o1, o2, o3)      \
     do {                                      \
         Rot<double> t1_, t2_, t3_;            \
@@ -111,6 +121,105 @@ AMRVW_NI void chase_step_final(StepState& z, double pbot) {
     z.q1 = fuse(z.q1, z.U);
 }
 
+// One chase step at a regular position (RDS.jl:42-70, 97-108) on registers: the 7 turnovers as ONE
+// straight-line block so the independent ones (T2|T3, T4|T5) overlap.  The inputs are parked in the
+// thread's shared-memory snapshot slots first; a degenerate turnover (flagged, essentially never)
+// redoes the step on the general path from that snapshot.  Used by the systolic lanes and by the
+// serial window solver.
+#define AMRVW_CHASE_REGULAR(sn, NT)                                                                                              \
+    do {                                                                                                                          \
+        (sn)[0 * (NT)] = make_double2(q0.c, q0.s); (sn)[1 * (NT)] = make_double2(q1.c, q1.s); (sn)[2 * (NT)] = make_double2(q2.c, q2.s); \
+        (sn)[3 * (NT)] = make_double2(b0.c, b0.s); (sn)[4 * (NT)] = make_double2(b1.c, b1.s); (sn)[5 * (NT)] = make_double2(b2.c, b2.s); \
+        (sn)[6 * (NT)] = make_double2(c0.c, c0.s); (sn)[7 * (NT)] = make_double2(c1.c, c1.s); (sn)[8 * (NT)] = make_double2(c2.c, c2.s); \
+        (sn)[9 * (NT)] = make_double2(U.c, U.s); (sn)[10 * (NT)] = make_double2(V.c, V.s); (sn)[11 * (NT)] = make_double2(W.c, W.s);    \
+        bool ok_ = true;                                                                                                          \
+        Rot<double> t1_, t2_, t3_;                                                                                                \
+        ok_ &= turnover_fast_try(b1, b2, V, t1_, t2_, t3_); V = t1_; b1 = t2_; b2 = t3_;                                          \
+        ok_ &= turnover_fast_try(c2, c1, V, t1_, t2_, t3_); V = t1_; c2 = t2_; c1 = t3_;                                          \
+        ok_ &= turnover_fast_try(b0, b1, U, t1_, t2_, t3_); U = t1_; b0 = t2_; b1 = t3_;                                          \
+        ok_ &= turnover_fast_try(c1, c0, U, t1_, t2_, t3_); U = t1_; c1 = t2_; c0 = t3_;                                          \
+        ok_ &= turnover_fast_try(q1, q2, V, t1_, t2_, t3_); V = t1_; q1 = t2_; q2 = t3_;                                          \
+        ok_ &= turnover_fast_try(q0, q1, U, t1_, t2_, t3_); U = t1_; q0 = t2_; q1 = t3_;                                          \
+        ok_ &= turnover_fast_try(W, V, U, t1_, t2_, t3_); V = t1_; U = t2_; W = t3_;                                              \
+        if (!ok_) {                                                                                                               \
+            StepState z_;                                                                                                         \
+            double2 v_;                                                                                                           \
+            v_ = (sn)[0 * (NT)]; z_.q0 = make_rot<double>(v_.x, v_.y); v_ = (sn)[1 * (NT)]; z_.q1 = make_rot<double>(v_.x, v_.y); \
+            v_ = (sn)[2 * (NT)]; z_.q2 = make_rot<double>(v_.x, v_.y); v_ = (sn)[3 * (NT)]; z_.b0 = make_rot<double>(v_.x, v_.y); \
+            v_ = (sn)[4 * (NT)]; z_.b1 = make_rot<double>(v_.x, v_.y); v_ = (sn)[5 * (NT)]; z_.b2 = make_rot<double>(v_.x, v_.y); \
+            v_ = (sn)[6 * (NT)]; z_.c0 = make_rot<double>(v_.x, v_.y); v_ = (sn)[7 * (NT)]; z_.c1 = make_rot<double>(v_.x, v_.y); \
+            v_ = (sn)[8 * (NT)]; z_.c2 = make_rot<double>(v_.x, v_.y); v_ = (sn)[9 * (NT)]; z_.U = make_rot<double>(v_.x, v_.y);  \
+            v_ = (sn)[10 * (NT)]; z_.V = make_rot<double>(v_.x, v_.y); v_ = (sn)[11 * (NT)]; z_.W = make_rot<double>(v_.x, v_.y); \
+            chase_step_general(z_);                                                                                               \
+            q0 = z_.q0; q1 = z_.q1; q2 = z_.q2; b0 = z_.b0; b1 = z_.b1; b2 = z_.b2; c0 = z_.c0; c1 = z_.c1; c2 = z_.c2;           \
+            U = z_.U; V = z_.V; W = z_.W;                                                                                         \
+        }                                                                                                                         \
+    } while (0)
+
+#define AMRVW_CHASE_GENERAL()                                                     \
+    do {                                                                          \
+        StepState z_ = {q0, q1, q2, b0, b1, b2, c0, c1, c2, U, V, W};             \
+        chase_step_general(z_);                                                   \
+        q0 = z_.q0; q1 = z_.q1; q2 = z_.q2; b0 = z_.b0; b1 = z_.b1; b2 = z_.b2;   \
+        c0 = z_.c0; c1 = z_.c1; c2 = z_.c2; U = z_.U; V = z_.V; W = z_.W;         \
+    } while (0)
+
+// One whole bulge (bulge-step.jl:11-19 for Float64, rank-one R, no B-only shortcut) chased serially
+// through the window [start, stop] with the same register window as the systolic lanes: per position
+// three rotators in, three out, instead of six memory round trips per turnover.  Same operations in
+// the same order as solver.cuh's bulge_step.
+AMRVW_NI void bulge_step_window(Fact<double, false>& F, Counter& ctr, const Shifts* given, uint64_t seed, uint64_t poly, int& ord, PolyStats& st,
+                                double2* sn, int NT) {
+    st.sweeps++;
+    Rot<double> U, V, W;
+    create_bulge_rds(F, ctr, U, V, given, seed, poly, ord, st);
+    int i = ctr.start_index;
+    const int stop = ctr.stop_index;
+    const double ptop = sign_(F.Q[i - 1].c);       // Q[0] = (1,0) sentinel
+    const double pbot = sign_(F.Q[stop + 1].c);    // Q[N] = (1,0) sentinel
+    Rot<double> q0 = F.Q[i], q1 = F.Q[i + 1], b0 = F.B[i], b1 = F.B[i + 1], c0 = F.Ct[i], c1 = F.Ct[i + 1];
+    Rot<double> q2 = q1, b2 = b1, c2 = c1;
+    {   // absorb_Ut (RDS.jl:14-36)
+        Rot<double> w = q0;
+        w.s = sign_(ptop) * w.s;
+        Rot<double> r1, r2, r3;
+        turnover(adjoint(U), adjoint(V), w, r1, r2, r3);
+        W = r1;
+        q1 = fuse(r3, q1);
+        r2.s = sign_(ptop) * r2.s;
+        q0 = r2;
+        F.turnovers++;
+    }
+    for (; i <= stop - 2; ++i) {
+        q2 = F.Q[i + 2]; b2 = F.B[i + 2]; c2 = F.Ct[i + 2];
+#ifndef AMRVW_STRICT
+        AMRVW_CHASE_REGULAR(sn, NT);
+#else
+        AMRVW_CHASE_GENERAL();
+#endif
+        F.Q[i] = q0; F.B[i] = b0; F.Ct[i] = c0;
+        q0 = q1; q1 = q2; b0 = b1; b1 = b2; c0 = c1; c1 = c2;
+        F.turnovers += 7;
+    }
+    {   // last position: i == stop - 1
+        b2 = F.B[stop + 1]; c2 = F.Ct[stop + 1];
+        StepState z = {q0, q1, q2, b0, b1, b2, c0, c1, c2, U, V, W};
+        chase_step_final(z, pbot);
+        F.Q[i] = z.q0; F.Q[i + 1] = z.q1;
+        F.B[i] = z.b0; F.B[i + 1] = z.b1; F.B[i + 2] = z.b2;
+        F.Ct[i] = z.c0; F.Ct[i + 1] = z.c1; F.Ct[i + 2] = z.c2;
+        F.turnovers += 7;
+    }
+}
+
+// drive_window's step for the pipelined kernel's serial phases
+struct WindowStep {
+    double2* sn; int NT;
+    AMRVW_DI void operator()(Fact<double, false>& F, Counter& ctr, uint64_t seed, uint64_t poly, int& ord, PolyStats& st) const {
+        bulge_step_window(F, ctr, (const Shifts*)nullptr, seed, poly, ord, st, sn, NT);
+    }
+};
+
 struct LeaderState {
     Counter ctr;
     long long kk, it_max;
@@ -145,7 +254,8 @@ AMRVW_DI void pop_window(LeaderState& ls) {
 // polynomial is finished, 1 for a fat step with shifts in shl[0..nb), 2 for a fat step of nb
 // exceptional (random) bulges.
 AMRVW_DI int phase_a(Fact<double, false>& F, LeaderState& ls, cplx* E, const GroupScratch& sc, Shifts* shl, const int L, const PipeParams pp,
-                     int& nb, const uint64_t seed, const uint64_t poly, PolyStats& st, const int* dstack) {
+                     int& nb, const uint64_t seed, const uint64_t poly, PolyStats& st, const int* dstack, double2* sn, const int NT) {
+    const WindowStep wstep = {sn, NT};
     Counter& ctr = ls.ctr;
     double A[4];
     while (ls.kk <= ls.it_max) {
@@ -178,7 +288,7 @@ AMRVW_DI int phase_a(Fact<double, false>& F, LeaderState& ls, cplx* E, const Gro
             const int lo2 = ctr.start_index, hi2 = ctr.stop_index;
             Fact<double, false> W = stage_window(F, sc, lo2 - 1, hi2);
             Counter c2 = {lo2 - 1, lo2, hi2, ctr.it_count, -1};
-            const int left = drive_window(W, lo2, hi2, c2, E, ls.it_max, seed, poly, ls.ord, st, ReferenceStep());   // the reference's cap is global (20 n)
+            const int left = drive_window(W, lo2, hi2, c2, E, ls.it_max, seed, poly, ls.ord, st, wstep);   // the reference's cap is global (20 n)
             F.turnovers += W.turnovers;
             ls.unconv += left;
             if (lo2 == 2) { diagonal_block(F, 1, A); E[1] = to_c(A[0]); }
@@ -204,7 +314,7 @@ AMRVW_DI int phase_a(Fact<double, false>& F, LeaderState& ls, cplx* E, const Gro
             for (int t = 0; t <= m; ++t) sc.e[t] = cplx(0.0, 0.0);
             Counter c2 = {k0, k0 + 1, stop, 15, -1};
             PolyStats sub = {0, 0, 0, 0, 0};
-            drive_window(W, k0 + 1, stop, c2, Es, 20ll * m, seed, poly, ls.ord, sub, ReferenceStep());
+            drive_window(W, k0 + 1, stop, c2, Es, 20ll * m, seed, poly, ls.ord, sub, wstep);
             F.turnovers += W.turnovers;
             // pair the m+1 shifts: conjugate pairs first (slot order), then the reals two by two
             int np = 0;
@@ -257,6 +367,7 @@ __global__ void __launch_bounds__(32 * WPB, AMRVW_PIPE_MINBLOCKS) roots_pipeline
     [[maybe_unused]] constexpr int NT = 32 * WPB;
     double2* snap = reinterpret_cast<double2*>(smem_raw + (size_t)WPB * per_warp);   // [12][NT] step snapshots
     (void)snap;
+    double2* stage = snap + 12 * NT + (wib * G + grp) * 6;                            // [2][3] look-ahead ring of lane 0
     Shifts* shl = reinterpret_cast<Shifts*>(wbase) + grp * L;
     GroupScratch sc;
     {
@@ -320,7 +431,7 @@ __global__ void __launch_bounds__(32 * WPB, AMRVW_PIPE_MINBLOCKS) roots_pipeline
         // ---------------- phase A
         mode = 0;
         if (leader && iterating) {
-            mode = phase_a(F, ls, out - 1, sc, shl, L, pp, nb, pr.seed, (uint64_t)p, st, dstack);
+            mode = phase_a(F, ls, out - 1, sc, shl, L, pp, nb, pr.seed, (uint64_t)p, st, dstack, snap + threadIdx.x, NT);
             if (mode == 0) iterating = false;
         }
         __syncwarp();
@@ -339,7 +450,6 @@ __global__ void __launch_bounds__(32 * WPB, AMRVW_PIPE_MINBLOCKS) roots_pipeline
         // ---------------- phase B: systolic chase of nb bulges through [start, stop]
         Rot<double> q0, q1, q2, b0, b1, b2, c0, c1, c2, U, V, W;
         q0 = q1 = q2 = b0 = b1 = b2 = c0 = c1 = c2 = U = V = W = make_rot<double>(1.0, 0.0);
-        Rot<double> nq = q0, nbr = q0, nc = q0;   // lane 0's prefetched next index
         Shifts mysh;
         mysh.e1 = cplx(0.0, 0.0); mysh.e2 = cplx(0.0, 0.0);
         const bool has_bulge = act && lane < nb;
@@ -351,16 +461,23 @@ __global__ void __launch_bounds__(32 * WPB, AMRVW_PIPE_MINBLOCKS) roots_pipeline
             if (start > 1) { bm = ldg_rot(F.B + start - 1); cm = ldg_rot(F.Ct + start - 1); }
             ptop = sign_(qm.c);
             pbot = sign_(F.Q[stop + 1].c);                 // Q[N] is the (1,0) sentinel
-            if (lane == 0) { nq = ldg_rot(F.Q + start); nbr = ldg_rot(F.B + start); nc = ldg_rot(F.Ct + start); }
+            if (lane == 0) { cp_async16(stage + 0, F.Q + start); cp_async16(stage + 1, F.B + start); cp_async16(stage + 2, F.Ct + start); cp_async_commit(); }
         }
         for (int t = 0; t < Tmax; ++t) {
             const int tp = t - 3 * lane;
             // ingest: what the previous lane finished last step (lane 0: from memory)
             Rot<double> iq = shfl_up_rot(q0, L), ib = shfl_up_rot(b0, L), ic = shfl_up_rot(c0, L);
             if (lane == 0) {
-                iq = nq; ib = nbr; ic = nc;
+                cp_async_wait_all();
+                const double2* sg = stage + (t & 1) * 3;
+                const double2 vq = sg[0], vb = sg[1], vc = sg[2];
+                iq = make_rot<double>(vq.x, vq.y); ib = make_rot<double>(vb.x, vb.y); ic = make_rot<double>(vc.x, vc.y);
                 const int nidx = start + t + 1;
-                if (act && nidx <= stop + 1) { nq = ldg_rot(F.Q + nidx); nbr = ldg_rot(F.B + nidx); nc = ldg_rot(F.Ct + nidx); }
+                if (act && nidx <= stop + 1) {
+                    double2* sn2 = stage + ((t + 1) & 1) * 3;
+                    cp_async16(sn2 + 0, F.Q + nidx); cp_async16(sn2 + 1, F.B + nidx); cp_async16(sn2 + 2, F.Ct + nidx);
+                    cp_async_commit();
+                }
             }
             q0 = q1; q1 = q2; q2 = iq;
             b0 = b1; b1 = b2; b2 = ib;
@@ -382,7 +499,10 @@ __global__ void __launch_bounds__(32 * WPB, AMRVW_PIPE_MINBLOCKS) roots_pipeline
                         Counter cl = {start - 1, start, stop, 15, -1};
                         int dummy = 0;
                         PolyStats ds = {0, 0, 0, 0, 0};
-                        create_bulge_rds(Fl, cl, U, V, &mysh, pr.seed, (uint64_t)p, dummy, ds);
+                        Rot<double> Uc, Vc;   // temporaries: U and V must never have their address taken (they live in registers)
+                        const Shifts shc = mysh;
+                        create_bulge_rds(Fl, cl, Uc, Vc, &shc, pr.seed, (uint64_t)p, dummy, ds);
+                        U = Uc; V = Vc;
                     }
                     // absorb_Ut (RDS.jl:14-36)
                     Rot<double> w = q0;
@@ -401,34 +521,9 @@ __global__ void __launch_bounds__(32 * WPB, AMRVW_PIPE_MINBLOCKS) roots_pipeline
                     // parked in shared memory first; a degenerate turnover (flagged, essentially never)
                     // redoes the step on the general path from that snapshot.
 #ifndef AMRVW_STRICT
-                    double2* sn = snap + threadIdx.x;
-                    sn[0 * NT] = make_double2(q0.c, q0.s); sn[1 * NT] = make_double2(q1.c, q1.s); sn[2 * NT] = make_double2(q2.c, q2.s);
-                    sn[3 * NT] = make_double2(b0.c, b0.s); sn[4 * NT] = make_double2(b1.c, b1.s); sn[5 * NT] = make_double2(b2.c, b2.s);
-                    sn[6 * NT] = make_double2(c0.c, c0.s); sn[7 * NT] = make_double2(c1.c, c1.s); sn[8 * NT] = make_double2(c2.c, c2.s);
-                    sn[9 * NT] = make_double2(U.c, U.s); sn[10 * NT] = make_double2(V.c, V.s); sn[11 * NT] = make_double2(W.c, W.s);
-                    bool ok = true;
-                    Rot<double> t1, t2, t3;
-                    ok &= turnover_fast_try(b1, b2, V, t1, t2, t3); V = t1; b1 = t2; b2 = t3;
-                    ok &= turnover_fast_try(c2, c1, V, t1, t2, t3); V = t1; c2 = t2; c1 = t3;
-                    ok &= turnover_fast_try(b0, b1, U, t1, t2, t3); U = t1; b0 = t2; b1 = t3;
-                    ok &= turnover_fast_try(c1, c0, U, t1, t2, t3); U = t1; c1 = t2; c0 = t3;
-                    ok &= turnover_fast_try(q1, q2, V, t1, t2, t3); V = t1; q1 = t2; q2 = t3;
-                    ok &= turnover_fast_try(q0, q1, U, t1, t2, t3); U = t1; q0 = t2; q1 = t3;
-                    ok &= turnover_fast_try(W, V, U, t1, t2, t3); V = t1; U = t2; W = t3;
-                    if (!ok) {
-                        StepState z;
-                        double2 v;
-                        v = sn[0 * NT]; z.q0 = make_rot<double>(v.x, v.y); v = sn[1 * NT]; z.q1 = make_rot<double>(v.x, v.y); v = sn[2 * NT]; z.q2 = make_rot<double>(v.x, v.y);
-                        v = sn[3 * NT]; z.b0 = make_rot<double>(v.x, v.y); v = sn[4 * NT]; z.b1 = make_rot<double>(v.x, v.y); v = sn[5 * NT]; z.b2 = make_rot<double>(v.x, v.y);
-                        v = sn[6 * NT]; z.c0 = make_rot<double>(v.x, v.y); v = sn[7 * NT]; z.c1 = make_rot<double>(v.x, v.y); v = sn[8 * NT]; z.c2 = make_rot<double>(v.x, v.y);
-                        v = sn[9 * NT]; z.U = make_rot<double>(v.x, v.y); v = sn[10 * NT]; z.V = make_rot<double>(v.x, v.y); v = sn[11 * NT]; z.W = make_rot<double>(v.x, v.y);
-                        chase_step_general(z);
-                        q0 = z.q0; q1 = z.q1; q2 = z.q2; b0 = z.b0; b1 = z.b1; b2 = z.b2; c0 = z.c0; c1 = z.c1; c2 = z.c2; U = z.U; V = z.V; W = z.W;
-                    }
+                    AMRVW_CHASE_REGULAR(snap + threadIdx.x, NT);
 #else
-                    StepState z = {q0, q1, q2, b0, b1, b2, c0, c1, c2, U, V, W};
-                    chase_step_general(z);
-                    q0 = z.q0; q1 = z.q1; q2 = z.q2; b0 = z.b0; b1 = z.b1; b2 = z.b2; c0 = z.c0; c1 = z.c1; c2 = z.c2; U = z.U; V = z.V; W = z.W;
+                    AMRVW_CHASE_GENERAL();
 #endif
                     my_turnovers += 7;
                 } else {
@@ -468,7 +563,7 @@ static int launch_pipelined_L(const Problem<double>& pr, PipeParams pp, cudaStre
     constexpr int WPB = 2;
     constexpr int G = 32 / L;
     const size_t per_warp = 32 * sizeof(Shifts) + (size_t)G * pp.ms * (3 * sizeof(Rot<double>) + sizeof(cplx));
-    const size_t smem = WPB * per_warp + (size_t)12 * 32 * WPB * sizeof(double2);
+    const size_t smem = WPB * per_warp + (size_t)12 * 32 * WPB * sizeof(double2) + (size_t)WPB * G * 6 * sizeof(double2);
     const long long groups_per_block = (long long)WPB * G;
     const int blocks = (int)((pr.nbatch + groups_per_block - 1) / groups_per_block);
     auto kern = roots_pipelined_kernel<L, WPB>;
