@@ -124,9 +124,9 @@ def cpu_baseline(kind, degree, law, seed, sample, threads=0):
     """The reference's algorithm and schedule (the oracle port) on this box's host cores."""
     from oracle import oracle as orc            # allowed here: cpu_baseline / --impl reference legs only
     cores = orc.num_threads() if threads <= 0 else threads
-    if sample <= 0:
-        per_core_s = {"rds_f64": 1.5e-7, "css_c64": 2.3e-7, "pencil_f64": 2.4e-7}[kind] * degree * degree * (4.5 if kind != "pencil_f64" else 8)
-        sample = max(cores, min(64 * cores, int(cores * max(1.0, 12.0 / max(per_core_s, 1e-9)))))
+    if sample <= 0:   # ~12 s of wall time: one polynomial costs about k * degree^2 seconds on one core
+        per_poly_s = {"rds_f64": 1.6e-7, "css_c64": 4.7e-7, "pencil_f64": 3.5e-7}[kind] * degree * degree
+        sample = max(cores, min(4096, int(cores * max(1.0, 12.0 / max(per_poly_s, 1e-9)))))
     flat, ws, offsets, _ = make_inputs(kind, sample, degree, law, seed, 0)
     if kind == "css_c64":
         flat = flat.view(np.complex128)
@@ -297,7 +297,11 @@ def main():
     except Exception:
         pass
     gbs = useful * BYTES_PER_TURNOVER[kind] / (ms_step * 1e-3) / 1e9
-    roofline = {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak, "traffic": None,
+    # dram__bytes_read.sum + dram__bytes_write.sum of the kernel from the committed ncu --set full capture
+    # (profiles/r01_c2_pipelined_ncu_full_keymetrics.csv); only valid for the default c2 launch
+    traffic = 138.6e9 if (args.config == "c2" and not args.batch and not args.degree and not args.lanes) else None
+    roofline = {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak, "traffic": traffic,
+                "traffic_note": "bytes per launch (ncu dram read+write); the reference-schedule algorithmic bytes (96 B per chase step per bulge) are 12x larger: the systolic chase reuses each rotator for L bulges",
                 "peak_source": "DFMA probe measured live in this run (MEASURED_PEAKS.json has no FP64 entry); nominal 37.2",
                 "kernel": "the one kernel of the step (device_ms of one warm-up step: %.2f ms)" % kernel_ms,
                 "useful_turnovers_per_step": useful, "executed_turnovers_per_step": executed,
