@@ -47,6 +47,7 @@ _SIGS = {
     "amrvw_roots_pencil_c64_dev": (ctypes.c_int, [_P, _P, _P, _P, _I64, _I64, _I64, _P, _P, _P, ctypes.POINTER(Stats)]),
     "amrvw_count_real_roots_dev": (ctypes.c_int, [_P, _P, _P, _I64, ctypes.c_int32, _P, _P]),
     "amrvw_measure_fp64_peak": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double)]),
+    "amrvw_selftest": (ctypes.c_int, [_P, _I64, ctypes.POINTER(ctypes.c_double)]),
 }
 EXPORTS = tuple(_SIGS)
 

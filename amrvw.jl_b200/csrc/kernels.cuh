@@ -184,6 +184,53 @@ __global__ void count_real_roots_kernel(const cplx* roots, const long long* offs
     counts3[3 * p] = nre; counts3[3 * p + 1] = npos; counts3[3 * p + 2] = nneg;
 }
 
+// ---------------------------------------------------------------- device self-test of the fast primitives
+// out[0]: max relative error of rsqrt_nr against 1/sqrt over a log-uniform sweep of [1e-280, 4]
+// out[1]: max |Q1 Q2 Q3 - R1 R2 R3| over random real turnovers on the division-free path
+// out[2]: max | |c|^2 + s^2 - 1 | of the rotators it returns
+// out[3]: number of turnovers that took the general (IEEE) path
+// (mirrors test/test-amrvw-basics.jl:35-42: the turnover must preserve the product)
+AMRVW_DI void rot3(double M[9], const Rot<double> r, int i) {   // M <- M * G(r)@i, 3x3, i in {0,1}
+    for (int k = 0; k < 3; ++k) {
+        const double a = M[3 * k + i], b = M[3 * k + i + 1];
+        M[3 * k + i] = r.c * a - r.s * b;
+        M[3 * k + i + 1] = r.s * a + r.c * b;
+    }
+}
+__global__ void selftest_kernel(double* out, int n, unsigned long long seed) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    double e_rsqrt = 0.0, e_prod = 0.0, e_unit = 0.0, n_gen = 0.0;
+    for (int k = tid; k < n; k += gridDim.x * blockDim.x) {
+        const double u = uniform01(seed, 1, (uint64_t)k);
+        const double x = exp(u * (log(4.0) - log(1e-280)) + log(1e-280));
+        const double y = rsqrt_nr(x), yref = 1.0 / sqrt(x);
+        e_rsqrt = fmax(e_rsqrt, fabs(y - yref) / yref);
+        Rot<double> q[3];
+        for (int j = 0; j < 3; ++j) {
+            double sn, cs;
+            sincos(6.283185307179586 * uniform01(seed, 2 + j, (uint64_t)k), &sn, &cs);
+            // every 7th triple: a nearly deflated rotator, sines down to 1e-18
+            if (k % 7 == j) { sn *= exp(-40.0 * uniform01(seed, 9, (uint64_t)k)); cs = copysign(sqrt(fmax(0.0, 1.0 - sn * sn)), cs); }
+            q[j] = make_rot<double>(cs, sn);
+        }
+        Rot<double> r1, r2, r3;
+        if (!turnover_fast_try(q[0], q[1], q[2], r1, r2, r3)) {
+            n_gen += 1.0;
+            turnover_ieee(q[0], q[1], q[2], r1, r2, r3);
+        }
+        double A[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, Bm[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        rot3(A, q[0], 0); rot3(A, q[1], 1); rot3(A, q[2], 0);
+        rot3(Bm, r1, 1); rot3(Bm, r2, 0); rot3(Bm, r3, 1);
+        for (int j = 0; j < 9; ++j) e_prod = fmax(e_prod, fabs(A[j] - Bm[j]));
+        e_unit = fmax(e_unit, fmax(fabs(r1.c * r1.c + r1.s * r1.s - 1.0), fmax(fabs(r2.c * r2.c + r2.s * r2.s - 1.0), fabs(r3.c * r3.c + r3.s * r3.s - 1.0))));
+    }
+    // doubles are non-negative: compare as integers for an atomic max
+    atomicMax((unsigned long long*)&out[0], (unsigned long long)__double_as_longlong(e_rsqrt));
+    atomicMax((unsigned long long*)&out[1], (unsigned long long)__double_as_longlong(e_prod));
+    atomicMax((unsigned long long*)&out[2], (unsigned long long)__double_as_longlong(e_unit));
+    atomicAdd(&out[3], n_gen);
+}
+
 // ---------------------------------------------------------------- FP64 peak probe
 // 8 independent DFMA chains per thread, no memory traffic: measures the FP64 vector-pipe roofline.
 __global__ void fp64_peak_kernel(double* out, int iters, double seed) {

@@ -212,6 +212,38 @@ AMRVW_NI void bulge_step_window(Fact<double, false>& F, Counter& ctr, const Shif
     }
 }
 
+// create_bulge (create-bulge.jl:20-77) on the lane's window [start-1 .. start+2] + absorb_Ut
+// (RDS.jl:14-36), out of line: once per bulge per fat step, keeps the chase loop small.
+AMRVW_NI void create_and_absorb(StepState& z, const Rot<double> qm, const Rot<double> bm, const Rot<double> cm, const Fact<double, false>& F,
+                                int start, int stop, int mode, const Shifts sh, uint64_t seed, uint64_t poly, int ordinal) {
+    Rot<double> U, V;
+    if (mode == 2) {
+        const double ang = uniform01(seed ^ 0xA5A5A5A5DEADBEEFull, poly, (uint64_t)ordinal) * 3.141592653589793;
+        double sn, cs;
+        sincos(ang, &sn, &cs);
+        U = make_rot<double>(sn, cs);
+        V = make_rot<double>(sn, -cs);
+    } else {
+        Rot<double> lq[4] = {qm, z.q0, z.q1, z.q2}, lb[4] = {bm, z.b0, z.b1, z.b2}, lc[4] = {cm, z.c0, z.c1, z.c2};
+        Fact<double, false> Fl = F;
+        Fl.Q = lq - (start - 1); Fl.B = lb - (start - 1); Fl.Ct = lc - (start - 1);
+        Counter cl = {start - 1, start, stop, 15, -1};
+        int dummy = 0;
+        PolyStats ds = {0, 0, 0, 0, 0};
+        create_bulge_rds(Fl, cl, U, V, &sh, seed, poly, dummy, ds);
+    }
+    const double ptop = sign_(qm.c);
+    Rot<double> w = z.q0;
+    w.s = sign_(ptop) * w.s;
+    Rot<double> r1, r2, r3;
+    turnover(adjoint(U), adjoint(V), w, r1, r2, r3);
+    z.W = r1;
+    z.q1 = fuse(r3, z.q1);
+    r2.s = sign_(ptop) * r2.s;
+    z.q0 = r2;
+    z.U = U; z.V = V;
+}
+
 // drive_window's step for the pipelined kernel's serial phases
 struct WindowStep {
     double2* sn; int NT;
@@ -454,12 +486,11 @@ __global__ void __launch_bounds__(32 * WPB, AMRVW_PIPE_MINBLOCKS) roots_pipeline
         mysh.e1 = cplx(0.0, 0.0); mysh.e2 = cplx(0.0, 0.0);
         const bool has_bulge = act && lane < nb;
         if (has_bulge && mode == 1) mysh = shl[lane];
-        double ptop = 1.0, pbot = 1.0;
+        double pbot = 1.0;
         Rot<double> qm = q0, bm = q0, cm = q0;   // static rotators at index start-1
         if (act) {
             qm = ldg_rot(F.Q + start - 1);                 // Q[0] is the (1,0) sentinel
             if (start > 1) { bm = ldg_rot(F.B + start - 1); cm = ldg_rot(F.Ct + start - 1); }
-            ptop = sign_(qm.c);
             pbot = sign_(F.Q[stop + 1].c);                 // Q[N] is the (1,0) sentinel
             if (lane == 0) { cp_async16(stage + 0, F.Q + start); cp_async16(stage + 1, F.B + start); cp_async16(stage + 2, F.Ct + start); cp_async_commit(); }
         }
@@ -485,34 +516,9 @@ __global__ void __launch_bounds__(32 * WPB, AMRVW_PIPE_MINBLOCKS) roots_pipeline
             const int i = start + tp - 2;   // position of this lane's bulge; window = indices i..i+2
             if (has_bulge && tp >= 2 && i <= stop - 1) {
                 if (tp == 2) {
-                    // create_bulge (create-bulge.jl:20-77) on the window [start-1 .. start+2], then absorb_Ut
-                    if (mode == 2) {
-                        const double ang = uniform01(pr.seed ^ 0xA5A5A5A5DEADBEEFull, (uint64_t)p, (uint64_t)(ord0 + lane)) * 3.141592653589793;
-                        double sn, cs;
-                        sincos(ang, &sn, &cs);
-                        U = make_rot<double>(sn, cs);
-                        V = make_rot<double>(sn, -cs);
-                    } else {
-                        Rot<double> lq[4] = {qm, q0, q1, q2}, lb[4] = {bm, b0, b1, b2}, lc[4] = {cm, c0, c1, c2};
-                        Fact<double, false> Fl = F;
-                        Fl.Q = lq - (start - 1); Fl.B = lb - (start - 1); Fl.Ct = lc - (start - 1);
-                        Counter cl = {start - 1, start, stop, 15, -1};
-                        int dummy = 0;
-                        PolyStats ds = {0, 0, 0, 0, 0};
-                        Rot<double> Uc, Vc;   // temporaries: U and V must never have their address taken (they live in registers)
-                        const Shifts shc = mysh;
-                        create_bulge_rds(Fl, cl, Uc, Vc, &shc, pr.seed, (uint64_t)p, dummy, ds);
-                        U = Uc; V = Vc;
-                    }
-                    // absorb_Ut (RDS.jl:14-36)
-                    Rot<double> w = q0;
-                    w.s = sign_(ptop) * w.s;
-                    Rot<double> r1, r2, r3;
-                    turnover_fast(adjoint(U), adjoint(V), w, r1, r2, r3);
-                    W = r1;
-                    q1 = fuse(r3, q1);
-                    r2.s = sign_(ptop) * r2.s;
-                    q0 = r2;
+                    StepState z = {q0, q1, q2, b0, b1, b2, c0, c1, c2, U, V, W};
+                    create_and_absorb(z, qm, bm, cm, F, start, stop, mode, mysh, pr.seed, (uint64_t)p, ord0 + lane);
+                    q0 = z.q0; q1 = z.q1; U = z.U; V = z.V; W = z.W;
                     my_turnovers += 1;
                 }
                 if (i <= stop - 2) {
@@ -560,7 +566,10 @@ __global__ void __launch_bounds__(32 * WPB, AMRVW_PIPE_MINBLOCKS) roots_pipeline
 
 template <int L>
 static int launch_pipelined_L(const Problem<double>& pr, PipeParams pp, cudaStream_t st) {
-    constexpr int WPB = 2;
+#ifndef AMRVW_PIPE_WPB
+#define AMRVW_PIPE_WPB 2
+#endif
+    constexpr int WPB = AMRVW_PIPE_WPB;
     constexpr int G = 32 / L;
     const size_t per_warp = 32 * sizeof(Shifts) + (size_t)G * pp.ms * (3 * sizeof(Rot<double>) + sizeof(cplx));
     const size_t smem = WPB * per_warp + (size_t)12 * 32 * WPB * sizeof(double2) + (size_t)WPB * G * 6 * sizeof(double2);

@@ -296,6 +296,14 @@ AMRVW_DI double rsqrt_nr(double x) {
 #else
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#ifndef AMRVW_NEWTON2
+    // one third-order step: y <- y (1 + e/2 + 3 e^2/8), e = 1 - x y^2
+    const double t = x * y;
+    const double e = fma(-t, y, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    const double q = y * e;
+    return fma(q, p, y);
+#else
     double t = x * y;
     double e = fma(-t, y, 1.0);
     y = fma(0.5 * y, e, y);
@@ -303,6 +311,7 @@ AMRVW_DI double rsqrt_nr(double x) {
     e = fma(-t, y, 1.0);
     y = fma(0.5 * y, e, y);
     return y;
+#endif
 #endif
 }
 

@@ -66,6 +66,11 @@ class Context:
         self._check(self._lib.amrvw_measure_fp64_peak(self._h, ctypes.byref(v)))
         return v.value
 
+    def selftest(self, n=200000):
+        out = (ctypes.c_double * 4)()
+        self._check(self._lib.amrvw_selftest(self._h, int(n), out))
+        return {"rsqrt_rel_err": out[0], "turnover_product_err": out[1], "unit_norm_err": out[2], "general_path": out[3]}
+
     # -- host buffers (CSR) in, host buffers out
     def roots_csr(self, coeffs, offsets, ws=None, want_stats=True):
         """coeffs: flat float64 or complex128 array; offsets: int64[B+1]; ws: pencil second vector.

@@ -123,6 +123,11 @@ int amrvw_count_real_roots_dev(amrvw_ctx* ctx, const double* d_roots_reim, const
  * (the FP64 roofline denominator; MEASURED_PEAKS.json only has HBM and bf16). */
 int amrvw_measure_fp64_peak(amrvw_ctx* ctx, double* tflops);
 
+/* Device self-test of the division-free primitives (mirrors test/test-amrvw-basics.jl:35-42, the
+ * turnover must preserve the product): out4 = {max rel. error of the Newton rsqrt, max |Q1Q2Q3 -
+ * R1R2R3| over n random turnovers, max deviation from unit norm, turnovers sent to the IEEE path}. */
+int amrvw_selftest(amrvw_ctx* ctx, int64_t n, double* out4);
+
 int amrvw_version(void);
 
 #ifdef __cplusplus

@@ -340,3 +340,13 @@ def test_gpu_count_real_roots_dev(A, ctx, oracle):
 def test_gpu_fp64_peak_probe(ctx):
     tf = ctx.fp64_peak_tflops()
     assert 5.0 < tf < 80.0
+
+
+def test_gpu_fast_primitives_selftest(ctx):
+    """Division-free turnover and Newton rsqrt on device (test/test-amrvw-basics.jl:35-42: the turnover
+    preserves the product; here to 8 eps like the oracle's version of the test)."""
+    r = ctx.selftest(400000)
+    eps = np.finfo(float).eps
+    assert r["rsqrt_rel_err"] <= 2 * eps, r
+    assert r["turnover_product_err"] <= 8 * eps, r
+    assert r["unit_norm_err"] <= 8 * eps, r
