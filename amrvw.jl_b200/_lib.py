@@ -12,7 +12,7 @@ class AmrvwError(RuntimeError):
 
 class Options(ctypes.Structure):
     _fields_ = [("schedule", ctypes.c_int32), ("lanes_per_poly", ctypes.c_int32), ("shift_reuse", ctypes.c_int32),
-                ("small_window", ctypes.c_int32), ("seed", ctypes.c_uint64)]
+                ("small_window", ctypes.c_int32), ("shift_solver", ctypes.c_int32), ("reserved", ctypes.c_int32), ("seed", ctypes.c_uint64)]
 
 
 class Stats(ctypes.Structure):
@@ -25,6 +25,7 @@ class Stats(ctypes.Structure):
 
 
 SCHEDULE_AUTO, SCHEDULE_REFERENCE, SCHEDULE_PIPELINED = 0, 1, 2
+SHIFTS_AUTO, SHIFTS_CHASE, SHIFTS_DENSE = 0, 1, 2
 
 _P = ctypes.c_void_p
 _I64 = ctypes.c_int64
@@ -48,6 +49,7 @@ _SIGS = {
     "amrvw_count_real_roots_dev": (ctypes.c_int, [_P, _P, _P, _I64, ctypes.c_int32, _P, _P]),
     "amrvw_measure_fp64_peak": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double)]),
     "amrvw_selftest": (ctypes.c_int, [_P, _I64, ctypes.POINTER(ctypes.c_double)]),
+    "amrvw_last_profile": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_int64)]),
 }
 EXPORTS = tuple(_SIGS)
 

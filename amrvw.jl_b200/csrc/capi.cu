@@ -25,7 +25,7 @@ struct amrvw_ctx {
     amrvw_options opt;
     std::string err;
     // grow-only device buffers
-    DevBuf chains[5], diags[3], coeffs, coeffs2, offsets, roots, nroots, nunconv, stats, shifts, state;
+    DevBuf chains[5], diags[3], coeffs, coeffs2, offsets, roots, nroots, nunconv, stats, shifts, state, prof;
     int sm_count = 148;
 };
 
@@ -60,6 +60,8 @@ void amrvw_default_options(amrvw_options* opt) {
     opt->lanes_per_poly = 0;
     opt->shift_reuse = 0;
     opt->small_window = 0;
+    opt->shift_solver = AMRVW_SHIFTS_AUTO;
+    opt->reserved = 0;
     opt->seed = 0;
 }
 
@@ -89,7 +91,7 @@ int amrvw_destroy(amrvw_ctx* ctx) {
     if (!ctx) return AMRVW_OK;
     cudaSetDevice(ctx->device);
     DevBuf* all[] = {&ctx->chains[0], &ctx->chains[1], &ctx->chains[2], &ctx->chains[3], &ctx->chains[4], &ctx->diags[0], &ctx->diags[1], &ctx->diags[2],
-                     &ctx->coeffs, &ctx->coeffs2, &ctx->offsets, &ctx->roots, &ctx->nroots, &ctx->nunconv, &ctx->stats, &ctx->shifts, &ctx->state};
+                     &ctx->coeffs, &ctx->coeffs2, &ctx->offsets, &ctx->roots, &ctx->nroots, &ctx->nunconv, &ctx->stats, &ctx->shifts, &ctx->state, &ctx->prof};
     for (DevBuf* b : all) if (b->ptr) cudaFree(b->ptr);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -108,6 +110,7 @@ int amrvw_set_options(amrvw_ctx* ctx, const amrvw_options* opt) {
     if (!(opt->shift_reuse == 0 || opt->shift_reuse == 1 || opt->shift_reuse == 2 || opt->shift_reuse == 4))
         return fail(ctx, AMRVW_ERR_ARGUMENT, "shift_reuse must be 0, 1, 2 or 4");
     if (opt->small_window < 0) return fail(ctx, AMRVW_ERR_ARGUMENT, "small_window must be >= 0");
+    if (opt->shift_solver < 0 || opt->shift_solver > 2) return fail(ctx, AMRVW_ERR_ARGUMENT, "shift_solver must be 0, 1 or 2");
     ctx->opt = *opt;
     return AMRVW_OK;
 }
@@ -172,6 +175,12 @@ static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, cons
     pr.WB = (Rot<S>*)ctx->chains[3].ptr; pr.WCt = (Rot<S>*)ctx->chains[4].ptr;
     pr.DQ = (S*)ctx->diags[0].ptr; pr.DR = (S*)ctx->diags[1].ptr; pr.WD = (S*)ctx->diags[2].ptr;
     pr.dstack = (int*)ctx->shifts.ptr;
+    pr.prof = nullptr;
+    if (var == V_RDS && stats) {   // warp-cycle counters ride along with the statistics
+        int rc = reserve(ctx, ctx->prof, 16 * sizeof(unsigned long long)); if (rc) return rc;
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->prof.ptr, 0, 16 * sizeof(unsigned long long), ctx->stream));
+        pr.prof = (unsigned long long*)ctx->prof.ptr;
+    }
     pr.extra = extra;
     pr.seed = ctx->opt.seed;
 
@@ -291,6 +300,16 @@ int amrvw_count_real_roots_dev(amrvw_ctx* ctx, const double* d_roots, const int6
     const int threads = 128;
     count_real_roots_kernel<<<(int)((nbatch + threads - 1) / threads), threads, 0, ctx->stream>>>((const cplx*)d_roots, (const long long*)d_offsets, nbatch, shift, d_nroots, d_counts3);
     CUDA_TRY(ctx, cudaGetLastError());
+    return AMRVW_OK;
+}
+
+int amrvw_last_profile(amrvw_ctx* ctx, int64_t* out16) {
+    if (!ctx || !out16) return AMRVW_ERR_ARGUMENT;
+    std::memset(out16, 0, 16 * sizeof(int64_t));
+    if (!ctx->prof.ptr) return AMRVW_OK;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaMemcpyAsync(out16, ctx->prof.ptr, 16 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return AMRVW_OK;
 }
 

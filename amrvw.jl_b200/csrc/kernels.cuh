@@ -20,6 +20,7 @@ template <class S> struct Problem {
     S* DQ; S* DR; S* WD;
     int* dstack;              // pipelined kernel: per-polynomial stack of deflated Q indices (same slot layout)
     int extra;                // 1 (non-pencil: len+1 slots) or 2 (pencil: N+2 slots)
+    unsigned long long* prof; // pipelined kernel: 16 warp-cycle counters (nullable), see amrvw_last_profile
     unsigned long long seed;
 };
 

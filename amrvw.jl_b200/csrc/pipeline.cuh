@@ -30,6 +30,7 @@
 // three apart commute exactly, so that is what this kernel is tested against.
 #pragma once
 #include "kernels.cuh"
+#include "shifts.cuh"
 #include "../../include/amrvw_b200.h"
 
 namespace amrvw {
@@ -38,6 +39,8 @@ struct PipeParams {
     int reuse;   // bulges per shift pair
     int small;   // windows <= small are finished serially in shared memory
     int ms;      // scratch slots per group and chain (>= max(2L/reuse, small) + 3)
+    int dense;   // shifts from the dense trailing block (shifts.cuh) instead of the core-chasing sub-solve
+    int mh;      // dense: order of the largest trailing block (2L/reuse)
 };
 
 AMRVW_DI Rot<double> shfl_up_rot(const Rot<double> r, int width) {
@@ -61,6 +64,11 @@ AMRVW_DI void cp_async16(void* smem_dst, const void* gsrc) {
 }
 AMRVW_DI void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 AMRVW_DI void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// look-ahead ring of a group's feeding lane: AMRVW_RING slots of three rotators; the triple of step
+// t sits in slot t % AMRVW_RING and is requested AMRVW_RING - 1 steps ahead (one step of look-ahead
+// left lane 0 waiting on far-L2 / HBM latency: a step is ~1100 cycles).
+#define AMRVW_RING 4
+AMRVW_DI void cp_async_wait_ring() { asm volatile("cp.async.wait_group %0;" ::"n"(AMRVW_RING - 2) : "memory"); }
 
 #define AMRVW_TURN(a, b, c, o1, o2, o3)      \
     do {                                      \
@@ -72,6 +80,7 @@ AMRVW_DI void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "m
 // Shared-memory scratch of one group: a window of up to ms rotators of each chain + eigenvalue slots.
 struct GroupScratch {
     Rot<double>* q; Rot<double>* b; Rot<double>* c; cplx* e;
+    double* H; double* isg;   // dense shifts: mh x mh block, mh + 1 reciprocals
 };
 
 // Copy chain indices k..hi+1 of the polynomial into scratch and return a view whose indices are the
@@ -258,6 +267,8 @@ struct LeaderState {
     int ord;
     int unconv;
     int sp;        // size of the deflation stack
+    long long pc_sub, pc_small;   // profile: cycles in shift sub-solves / small-window solves
+    int pn_small;
 };
 
 // check_deflation (AMRVW_algorithm.jl:181-202) without the O(window) scan.  The reference scans
@@ -317,6 +328,7 @@ AMRVW_DI int phase_a(Fact<double, false>& F, LeaderState& ls, cplx* E, const Gro
             check_deflation_stack(F, ls, dstack);
         } else if (delta <= pp.small) {
             // decoupled small window [lo2, hi2]: finish it in shared memory, one bulge at a time
+            const long long pc0 = clock64();
             const int lo2 = ctr.start_index, hi2 = ctr.stop_index;
             Fact<double, false> W = stage_window(F, sc, lo2 - 1, hi2);
             Counter c2 = {lo2 - 1, lo2, hi2, ctr.it_count, -1};
@@ -327,6 +339,7 @@ AMRVW_DI int phase_a(Fact<double, false>& F, LeaderState& ls, cplx* E, const Gro
             pop_window(ls);
             ctr.stop_index = lo2 - 2; ctr.zero_index = 0; ctr.start_index = 1; ctr.it_count = 15;
             if (ctr.stop_index >= 1) check_deflation_stack(F, ls, dstack);
+            ls.pc_small += clock64() - pc0; ls.pn_small += 1;
         } else if (ctr.it_count == 0) {
             st.fat_steps++;
             nb = L;
@@ -334,6 +347,7 @@ AMRVW_DI int phase_a(Fact<double, false>& F, LeaderState& ls, cplx* E, const Gro
         } else {
             // shifts: eigenvalues of the trailing (m+1) x (m+1) block = the window [k0+1, stop] of a copy
             // whose rotator k0 is made diagonal
+            const long long pc0 = clock64();
             int m = min(2 * L / pp.reuse - 1, delta - 1);
             if (m % 2 == 0) m -= 1;
             const int stop = ctr.stop_index, k0 = stop - m;
@@ -342,12 +356,14 @@ AMRVW_DI int phase_a(Fact<double, false>& F, LeaderState& ls, cplx* E, const Gro
                 const double sg = sign_(W.Q[k0].c);
                 W.Q[k0] = make_rot<double>(sg == 0.0 ? 1.0 : sg, 0.0);
             }
-            cplx* Es = sc.e - (k0 + 1);
-            for (int t = 0; t <= m; ++t) sc.e[t] = cplx(0.0, 0.0);
-            Counter c2 = {k0, k0 + 1, stop, 15, -1};
-            PolyStats sub = {0, 0, 0, 0, 0};
-            drive_window(W, k0 + 1, stop, c2, Es, 20ll * m, seed, poly, ls.ord, sub, wstep);
-            F.turnovers += W.turnovers;
+            if (!(pp.dense && dense_shifts(W.Q, W.B, W.Ct, k0, stop, sc.H, sc.isg, sc.e))) {
+                cplx* Es = sc.e - (k0 + 1);
+                for (int t = 0; t <= m; ++t) sc.e[t] = cplx(0.0, 0.0);
+                Counter c2 = {k0, k0 + 1, stop, 15, -1};
+                PolyStats sub = {0, 0, 0, 0, 0};
+                drive_window(W, k0 + 1, stop, c2, Es, 20ll * m, seed, poly, ls.ord, sub, wstep);
+                F.turnovers += W.turnovers;
+            }
             // pair the m+1 shifts: conjugate pairs first (slot order), then the reals two by two
             int np = 0;
             for (int t = 0; t <= m; ++t) {
@@ -373,10 +389,91 @@ AMRVW_DI int phase_a(Fact<double, false>& F, LeaderState& ls, cplx* E, const Gro
             nb = np * pp.reuse;
             st.fat_steps++;
             ctr.it_count -= 1;
+            ls.pc_sub += clock64() - pc0;
             return 1;
         }
     }
     return 0;
+}
+
+
+// ---------------------------------------------------------------- the lean systolic loop
+// Steps [t0, t1) of phase B during which EVERY lane of the warp is at a regular chase position (or
+// belongs to a group with nothing to do): no bulge is being created or fused, so the step is
+// ingest -> 7 turnovers -> retire with no per-lane case analysis.  Out of line on purpose: inside
+// the kernel body the same loop carried ~300 register moves and spill instructions per step for the
+// cold state around it (649 instructions per step against ~330 here; tools/ubench.cu measures the
+// loop in isolation).  Shared memory is addressed through 32-bit shared-window addresses so that
+// the snapshot and the look-ahead ring compile to STS/LDS/LDGSTS without generic-address glue.
+AMRVW_DI void sts_rot(unsigned sa, const Rot<double> r) { asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(sa), "d"(r.c), "d"(r.s) : "memory"); }
+AMRVW_DI Rot<double> lds_rot(unsigned sa) {
+    Rot<double> r;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.c), "=d"(r.s) : "r"(sa) : "memory");
+    return r;
+}
+AMRVW_DI void cp_async16_sa(unsigned sa, const void* gsrc) { asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory"); }
+
+// role: bit 0: the lane's group is chasing, bit 1: lane 0 of its group (feeds), bit 2: lane L-1 (retires)
+template <int L, int NT>
+AMRVW_NI int lean_chase(StepState& z, Rot<double>* gq, Rot<double>* gb, Rot<double>* gc, const unsigned stage_sa, const unsigned snap_sa, int* dstack, int sp,
+                        const int start, const int t0, const int t1, const int role) {
+    Rot<double> q0 = z.q0, q1 = z.q1, q2 = z.q2, b0 = z.b0, b1 = z.b1, b2 = z.b2, c0 = z.c0, c1 = z.c1, c2 = z.c2, U = z.U, V = z.V, W = z.W;
+    const bool chasing = role & 1, feeds = (role & 3) == 3, retires = (role & 5) == 5;
+    constexpr unsigned SS = NT * 16;     // snapshot slot stride in bytes
+    // feeding lane: next index to prefetch; retiring lane: index leaving the pipeline
+    gq += start; gb += start; gc += start;
+    const int kofs = feeds ? AMRVW_RING - 1 : -(3 * (L - 1) + 2);
+    gq += t0 + kofs; gb += t0 + kofs; gc += t0 + kofs;
+    int kidx = start + t0 + kofs;
+#pragma unroll 1
+    for (int t = t0; t < t1; ++t) {
+        Rot<double> iq = shfl_up_rot(q0, L), ib = shfl_up_rot(b0, L), ic = shfl_up_rot(c0, L);
+        if (feeds) {
+            cp_async_wait_ring();
+            const unsigned sg = stage_sa + (t & (AMRVW_RING - 1)) * 48, sn2 = stage_sa + ((t + AMRVW_RING - 1) & (AMRVW_RING - 1)) * 48;
+            iq = lds_rot(sg); ib = lds_rot(sg + 16); ic = lds_rot(sg + 32);
+            cp_async16_sa(sn2, gq); cp_async16_sa(sn2 + 16, gb); cp_async16_sa(sn2 + 32, gc);
+            cp_async_commit();
+        }
+        q0 = q1; q1 = q2; q2 = iq;
+        b0 = b1; b1 = b2; b2 = ib;
+        c0 = c1; c1 = c2; c2 = ic;
+#ifndef AMRVW_STRICT
+        sts_rot(snap_sa + 0 * SS, q0); sts_rot(snap_sa + 1 * SS, q1); sts_rot(snap_sa + 2 * SS, q2);
+        sts_rot(snap_sa + 3 * SS, b0); sts_rot(snap_sa + 4 * SS, b1); sts_rot(snap_sa + 5 * SS, b2);
+        sts_rot(snap_sa + 6 * SS, c0); sts_rot(snap_sa + 7 * SS, c1); sts_rot(snap_sa + 8 * SS, c2);
+        sts_rot(snap_sa + 9 * SS, U); sts_rot(snap_sa + 10 * SS, V); sts_rot(snap_sa + 11 * SS, W);
+        bool ok = true;
+        {
+            Rot<double> t1_, t2_, t3_;
+            ok &= turnover_fast_try(b1, b2, V, t1_, t2_, t3_); V = t1_; b1 = t2_; b2 = t3_;
+            ok &= turnover_fast_try(c2, c1, V, t1_, t2_, t3_); V = t1_; c2 = t2_; c1 = t3_;
+            ok &= turnover_fast_try(b0, b1, U, t1_, t2_, t3_); U = t1_; b0 = t2_; b1 = t3_;
+            ok &= turnover_fast_try(c1, c0, U, t1_, t2_, t3_); U = t1_; c1 = t2_; c0 = t3_;
+            ok &= turnover_fast_try(q1, q2, V, t1_, t2_, t3_); V = t1_; q1 = t2_; q2 = t3_;
+            ok &= turnover_fast_try(q0, q1, U, t1_, t2_, t3_); U = t1_; q0 = t2_; q1 = t3_;
+            ok &= turnover_fast_try(W, V, U, t1_, t2_, t3_); V = t1_; U = t2_; W = t3_;
+        }
+        if (!ok && chasing) {   // a degenerate turnover (essentially never): redo the step on the general path
+            StepState y;
+            y.q0 = lds_rot(snap_sa + 0 * SS); y.q1 = lds_rot(snap_sa + 1 * SS); y.q2 = lds_rot(snap_sa + 2 * SS);
+            y.b0 = lds_rot(snap_sa + 3 * SS); y.b1 = lds_rot(snap_sa + 4 * SS); y.b2 = lds_rot(snap_sa + 5 * SS);
+            y.c0 = lds_rot(snap_sa + 6 * SS); y.c1 = lds_rot(snap_sa + 7 * SS); y.c2 = lds_rot(snap_sa + 8 * SS);
+            y.U = lds_rot(snap_sa + 9 * SS); y.V = lds_rot(snap_sa + 10 * SS); y.W = lds_rot(snap_sa + 11 * SS);
+            chase_step_general(y);
+            q0 = y.q0; q1 = y.q1; q2 = y.q2; b0 = y.b0; b1 = y.b1; b2 = y.b2; c0 = y.c0; c1 = y.c1; c2 = y.c2; U = y.U; V = y.V; W = y.W;
+        }
+#else
+        if (chasing) AMRVW_CHASE_GENERAL();
+#endif
+        if (retires) {
+            stg_rot(gq, q0); stg_rot(gb, b0); stg_rot(gc, c0);
+            if (fabs(q0.s) <= AMRVW_EPS) dstack[sp++] = kidx;
+        }
+        gq += 1; gb += 1; gc += 1; kidx += 1;
+    }
+    z.q0 = q0; z.q1 = q1; z.q2 = q2; z.b0 = b0; z.b1 = b1; z.b2 = b2; z.c0 = c0; z.c1 = c1; z.c2 = c2; z.U = U; z.V = V; z.W = W;
+    return sp;
 }
 
 #ifndef AMRVW_PIPE_MINBLOCKS
@@ -393,13 +490,13 @@ __global__ void __launch_bounds__(32 * WPB, AMRVW_PIPE_MINBLOCKS) roots_pipeline
     const bool leader = valid && lane == 0;
 
     // shared memory carve-up: per warp [32 Shifts][G groups x (3 chains x ms rotators + ms eigenvalues)]
-    const size_t per_group = (size_t)pp.ms * (3 * sizeof(Rot<double>) + sizeof(cplx));
+    const size_t per_group = (size_t)pp.ms * (3 * sizeof(Rot<double>) + sizeof(cplx)) + (pp.dense ? ((size_t)pp.mh * pp.mh + pp.mh + 2) * sizeof(double) : 0);
     const size_t per_warp = 32 * sizeof(Shifts) + G * per_group;
     unsigned char* wbase = smem_raw + (size_t)wib * per_warp;
     [[maybe_unused]] constexpr int NT = 32 * WPB;
     double2* snap = reinterpret_cast<double2*>(smem_raw + (size_t)WPB * per_warp);   // [12][NT] step snapshots
     (void)snap;
-    double2* stage = snap + 12 * NT + (wib * G + grp) * 6;                            // [2][3] look-ahead ring of lane 0
+    double2* stage = snap + 12 * NT + (wib * G + grp) * (3 * AMRVW_RING);               // [AMRVW_RING][3] look-ahead ring of lane 0
     Shifts* shl = reinterpret_cast<Shifts*>(wbase) + grp * L;
     GroupScratch sc;
     {
@@ -408,15 +505,19 @@ __global__ void __launch_bounds__(32 * WPB, AMRVW_PIPE_MINBLOCKS) roots_pipeline
         sc.b = sc.q + pp.ms;
         sc.c = sc.b + pp.ms;
         sc.e = reinterpret_cast<cplx*>(sc.c + pp.ms);
+        sc.H = reinterpret_cast<double*>(sc.e + pp.ms);
+        sc.isg = sc.H + (size_t)pp.mh * pp.mh;
     }
 
     // ---------------- set-up (lane 0 of each group): trim, closed forms, factorization
+    const long long pc_begin = clock64();
+    long long pc_a = 0, pc_lean = 0, pc_b = 0, pn_lean = 0, pn_gen = 0, pn_calls = 0;
     Fact<double, false> F;
     F.N = 0; F.turnovers = 0;
     F.Q = F.B = F.Ct = F.WB = F.WCt = nullptr; F.DQ = F.DR = F.WD = nullptr;
     PolyStats st = {0, 0, 0, 0, 0};
     LeaderState ls;
-    ls.kk = 0; ls.it_max = 0; ls.ord = 0; ls.unconv = 0; ls.sp = 0;
+    ls.kk = 0; ls.it_max = 0; ls.ord = 0; ls.unconv = 0; ls.sp = 0; ls.pc_sub = 0; ls.pc_small = 0; ls.pn_small = 0;
     ls.ctr = {0, 1, 0, 15, -1};
     cplx* out = nullptr;
     int* dstack = nullptr;
@@ -459,8 +560,10 @@ __global__ void __launch_bounds__(32 * WPB, AMRVW_PIPE_MINBLOCKS) roots_pipeline
 
     long long my_turnovers = 0;
     int nb = 0;
+    const long long pc_setup = clock64();
     for (;;) {
         // ---------------- phase A
+        const long long pc_t0 = clock64();
         mode = 0;
         if (leader && iterating) {
             mode = phase_a(F, ls, out - 1, sc, shl, L, pp, nb, pr.seed, (uint64_t)p, st, dstack, snap + threadIdx.x, NT);
@@ -478,6 +581,8 @@ __global__ void __launch_bounds__(32 * WPB, AMRVW_PIPE_MINBLOCKS) roots_pipeline
         const bool act = mode != 0;
         const int T = act ? (stop - start + 3 * L + 1) : 0;
         const int Tmax = __reduce_max_sync(0xffffffffu, T);
+        const long long pc_t1 = clock64();
+        pc_a += pc_t1 - pc_t0;
 
         // ---------------- phase B: systolic chase of nb bulges through [start, stop]
         Rot<double> q0, q1, q2, b0, b1, b2, c0, c1, c2, U, V, W;
@@ -492,23 +597,46 @@ __global__ void __launch_bounds__(32 * WPB, AMRVW_PIPE_MINBLOCKS) roots_pipeline
             qm = ldg_rot(F.Q + start - 1);                 // Q[0] is the (1,0) sentinel
             if (start > 1) { bm = ldg_rot(F.B + start - 1); cm = ldg_rot(F.Ct + start - 1); }
             pbot = sign_(F.Q[stop + 1].c);                 // Q[N] is the (1,0) sentinel
-            if (lane == 0) { cp_async16(stage + 0, F.Q + start); cp_async16(stage + 1, F.B + start); cp_async16(stage + 2, F.Ct + start); cp_async_commit(); }
+            if (lane == 0) {
+                for (int a = 0; a < AMRVW_RING - 1; ++a) {
+                    const int nidx = min(start + a, stop + 1);
+                    cp_async16(stage + 3 * a + 0, F.Q + nidx); cp_async16(stage + 3 * a + 1, F.B + nidx); cp_async16(stage + 3 * a + 2, F.Ct + nidx);
+                    cp_async_commit();
+                }
+            }
         }
         for (int t = 0; t < Tmax; ++t) {
+            {   // every lane of the warp at a regular position (or idle for good): hand over to the lean loop
+                const bool g_dead = !act || t >= T;
+                const bool g_main = act && nb == L && t >= 3 * L && t <= stop - start;
+                if (__all_sync(0xffffffffu, g_dead || g_main) && __any_sync(0xffffffffu, g_main)) {
+                    const int te = __reduce_min_sync(0xffffffffu, g_main ? stop - start + 1 : 0x7fffffff);
+                    const long long pc_l0 = clock64();
+                    StepState z = {q0, q1, q2, b0, b1, b2, c0, c1, c2, U, V, W};
+                    const int role = (g_main ? 1 : 0) | (lane == 0 ? 2 : 0) | (lane == L - 1 ? 4 : 0);
+                    sp = lean_chase<L, NT>(z, F.Q, F.B, F.Ct, (unsigned)__cvta_generic_to_shared(stage), (unsigned)__cvta_generic_to_shared(snap + threadIdx.x), dstack, sp,
+                                           start, t, te, role);
+                    q0 = z.q0; q1 = z.q1; q2 = z.q2; b0 = z.b0; b1 = z.b1; b2 = z.b2; c0 = z.c0; c1 = z.c1; c2 = z.c2; U = z.U; V = z.V; W = z.W;
+                    if (g_main) my_turnovers += 7ll * (te - t);
+                    pc_lean += clock64() - pc_l0; pn_lean += te - t; pn_calls += 1; pn_gen -= 1;
+                    t = te - 1;
+                    continue;
+                }
+            }
             const int tp = t - 3 * lane;
             // ingest: what the previous lane finished last step (lane 0: from memory)
             Rot<double> iq = shfl_up_rot(q0, L), ib = shfl_up_rot(b0, L), ic = shfl_up_rot(c0, L);
             if (lane == 0) {
-                cp_async_wait_all();
-                const double2* sg = stage + (t & 1) * 3;
+                cp_async_wait_ring();
+                const double2* sg = stage + (t & (AMRVW_RING - 1)) * 3;
                 const double2 vq = sg[0], vb = sg[1], vc = sg[2];
                 iq = make_rot<double>(vq.x, vq.y); ib = make_rot<double>(vb.x, vb.y); ic = make_rot<double>(vc.x, vc.y);
-                const int nidx = start + t + 1;
-                if (act && nidx <= stop + 1) {
-                    double2* sn2 = stage + ((t + 1) & 1) * 3;
+                if (act) {
+                    const int nidx = min(start + t + AMRVW_RING - 1, stop + 1);
+                    double2* sn2 = stage + ((t + AMRVW_RING - 1) & (AMRVW_RING - 1)) * 3;
                     cp_async16(sn2 + 0, F.Q + nidx); cp_async16(sn2 + 1, F.B + nidx); cp_async16(sn2 + 2, F.Ct + nidx);
-                    cp_async_commit();
                 }
+                cp_async_commit();
             }
             q0 = q1; q1 = q2; q2 = iq;
             b0 = b1; b1 = b2; b2 = ib;
@@ -545,6 +673,8 @@ __global__ void __launch_bounds__(32 * WPB, AMRVW_PIPE_MINBLOCKS) roots_pipeline
                 if (i <= stop && fabs(q0.s) <= AMRVW_EPS) dstack[sp++] = i;   // deflatable: record for phase A
             }
         }
+        if (lane == 0) cp_async_wait_all();   // drain look-ahead requests past the end of the window
+        pc_b += clock64() - pc_t1; pn_gen += Tmax;
         sp = __shfl_sync(0xffffffffu, sp, grp * L + L - 1);
         if (leader && act) {
             ls.sp = sp;
@@ -555,12 +685,35 @@ __global__ void __launch_bounds__(32 * WPB, AMRVW_PIPE_MINBLOCKS) roots_pipeline
     }
 
     // ---------------- epilogue: turnover count, sort, zero roots
+    const long long pc_loop_end = clock64();
     for (int d = L / 2; d >= 1; d >>= 1) my_turnovers += __shfl_down_sync(0xffffffffu, my_turnovers, d, L);
     if (leader && N > 0) {
         sort_roots(out, N);
         st.turnovers = F.turnovers + my_turnovers;
         st.unconverged = ls.unconv + (ls.ctr.stop_index >= 1 ? ls.ctr.stop_index + 1 : 0);
         finish_poly(pr, p, out, N, K, st.unconverged, st);
+    }
+    if (pr.prof) {   // warp-cycle accounting for amrvw_last_profile
+        __syncwarp();
+        if (leader) {
+            atomicAdd(pr.prof + 11, (unsigned long long)ls.pc_sub);
+            atomicAdd(pr.prof + 12, (unsigned long long)ls.pc_small);
+            atomicAdd(pr.prof + 13, (unsigned long long)ls.pn_small);
+        }
+        if (lane32 == 0) {
+            const long long pc_end = clock64();
+            atomicAdd(pr.prof + 0, (unsigned long long)(pc_end - pc_begin));
+            atomicAdd(pr.prof + 1, (unsigned long long)pc_a);
+            atomicAdd(pr.prof + 2, (unsigned long long)pc_lean);
+            atomicAdd(pr.prof + 3, (unsigned long long)(pc_b - pc_lean));
+            atomicAdd(pr.prof + 4, (unsigned long long)pn_lean);
+            atomicAdd(pr.prof + 5, (unsigned long long)(pn_gen - pn_lean));
+            atomicAdd(pr.prof + 6, (unsigned long long)pn_calls);
+            atomicAdd(pr.prof + 7, 1ull);
+            atomicAdd(pr.prof + 8, (unsigned long long)(pc_setup - pc_begin));
+            atomicAdd(pr.prof + 9, (unsigned long long)(pc_end - pc_loop_end));
+            atomicMax(pr.prof + 10, (unsigned long long)(pc_end - pc_begin));
+        }
     }
 }
 
@@ -571,8 +724,9 @@ static int launch_pipelined_L(const Problem<double>& pr, PipeParams pp, cudaStre
 #endif
     constexpr int WPB = AMRVW_PIPE_WPB;
     constexpr int G = 32 / L;
-    const size_t per_warp = 32 * sizeof(Shifts) + (size_t)G * pp.ms * (3 * sizeof(Rot<double>) + sizeof(cplx));
-    const size_t smem = WPB * per_warp + (size_t)12 * 32 * WPB * sizeof(double2) + (size_t)WPB * G * 6 * sizeof(double2);
+    const size_t per_group = (size_t)pp.ms * (3 * sizeof(Rot<double>) + sizeof(cplx)) + (pp.dense ? ((size_t)pp.mh * pp.mh + pp.mh + 2) * sizeof(double) : 0);
+    const size_t per_warp = 32 * sizeof(Shifts) + (size_t)G * per_group;
+    const size_t smem = WPB * per_warp + (size_t)12 * 32 * WPB * sizeof(double2) + (size_t)WPB * G * 3 * AMRVW_RING * sizeof(double2);
     const long long groups_per_block = (long long)WPB * G;
     const int blocks = (int)((pr.nbatch + groups_per_block - 1) / groups_per_block);
     auto kern = roots_pipelined_kernel<L, WPB>;
@@ -602,6 +756,8 @@ static int launch_pipelined_rds(const Problem<double>& pr, const amrvw_options& 
     if (pp.small < mshift) pp.small = mshift;      // a fat step needs delta - 1 >= m
     if (pp.small > 96) pp.small = 96;
     pp.ms = (mshift > pp.small ? mshift : pp.small) + 4;
+    pp.dense = opt.shift_solver != AMRVW_SHIFTS_CHASE;
+    pp.mh = mshift;
     int rc;
     switch (L) {
         case 4: rc = launch_pipelined_L<4>(pr, pp, st); break;

@@ -315,21 +315,30 @@ AMRVW_DI double rsqrt_nr(double x) {
 #endif
 }
 
-// division-free common path (real); returns false when the caller must take the general path
+// division-free common path (real); returns false when the caller must take the general path.
+// 31 FP64-pipe instructions + one MUFU: every product is contracted by hand (the reference's
+// formulas, transformations.jl:162-191, with 1/r by rsqrt).  b = s1 s2 / s5 with s5 = -r (1 - h),
+// h = O(u) the first-order norm correction of the second rotator: the factor 1/(1 - h) is dropped,
+// a relative perturbation of b of a few ulp that the first-order renormalisation of (a, b) absorbs
+// (amrvw_selftest measures the product error of exactly this code against the IEEE path).
 AMRVW_DI bool turnover_fast_try(const Rot<double> q1, const Rot<double> q2, const Rot<double> q3, Rot<double>& r1, Rot<double>& r2, Rot<double>& r3) {
     const double c1 = q1.c, s1 = q1.s, c2 = q2.c, s2 = q2.s, c3 = q3.c, s3 = q3.s;
-    const double u21 = -c2 * s3 * c1 - c3 * s1;
+    const double t = c2 * s3;
+    const double m1 = c3 * s1;
+    const double u21 = fma(-t, c1, -m1);
     const double u31 = s2 * s3;
-    const double u11 = c1 * c3 - c2 * s1 * s3;
-    const double x = u21 * u21 + u31 * u31;
-    const double rinv = rsqrt_nr(x);
-    const double c4 = u21 * rinv, s4 = -(u31 * rinv);
-    const double r4 = x * rinv;
-    const double h5 = 0.5 * (u11 * u11 + (x - 1.0));
-    const double rho5 = 1.0 - h5;
-    const double a = c1 * s2 * s4 + c2 * c4;
-    const double b = -(s1 * s2) * rinv * (1.0 + h5);
-    const double rho6 = 1.0 - 0.5 * (a * a + b * b - 1.0);
+    const double m2 = c1 * c3;
+    const double u11 = fma(-t, s1, m2);
+    const double x = fma(u21, u21, u31 * u31);
+    const double y = rsqrt_nr(x);
+    const double c4 = u21 * y, s4 = -(u31 * y);
+    const double r4 = x * y;
+    const double d5 = fma(u11, u11, x - 1.0);
+    const double rho5 = fma(-0.5, d5, 1.0);
+    const double a = fma(c2, c4, (c1 * s2) * s4);
+    const double b = -((s1 * s2) * y);
+    const double d6 = fma(b, b, fma(a, a, -1.0));
+    const double rho6 = fma(-0.5, d6, 1.0);
     r1 = make_rot<double>(c4, s4);
     r2 = make_rot<double>(u11 * rho5, -(r4 * rho5));
     r3 = make_rot<double>(a * rho6, b * rho6);

@@ -50,8 +50,8 @@ class Context:
         if rc != 0:
             raise AmrvwError(f"amrvw error {rc}: {self._lib.amrvw_last_error(self._h).decode()}")
 
-    def set_options(self, schedule=0, lanes_per_poly=0, shift_reuse=0, small_window=0, seed=0):
-        o = Options(int(schedule), int(lanes_per_poly), int(shift_reuse), int(small_window), int(seed))
+    def set_options(self, schedule=0, lanes_per_poly=0, shift_reuse=0, small_window=0, shift_solver=0, seed=0):
+        o = Options(int(schedule), int(lanes_per_poly), int(shift_reuse), int(small_window), int(shift_solver), 0, int(seed))
         self._check(self._lib.amrvw_set_options(self._h, ctypes.byref(o)))
 
     def set_stream(self, cuda_stream_handle):
@@ -70,6 +70,14 @@ class Context:
         out = (ctypes.c_double * 4)()
         self._check(self._lib.amrvw_selftest(self._h, int(n), out))
         return {"rsqrt_rel_err": out[0], "turnover_product_err": out[1], "unit_norm_err": out[2], "general_path": out[3]}
+
+    def last_profile(self):
+        """Warp-cycle accounting of the last pipelined RDS call made with stats (amrvw_last_profile)."""
+        out = (ctypes.c_int64 * 16)()
+        self._check(self._lib.amrvw_last_profile(self._h, out))
+        keys = ("cycles_total", "cycles_phase_a", "cycles_lean", "cycles_general", "steps_lean", "steps_general", "lean_calls", "warps",
+                "cycles_setup", "cycles_epilogue", "cycles_max_warp", "leader_cycles_subsolve", "leader_cycles_small", "small_windows")
+        return {k: int(out[i]) for i, k in enumerate(keys)}
 
     # -- host buffers (CSR) in, host buffers out
     def roots_csr(self, coeffs, offsets, ws=None, want_stats=True):

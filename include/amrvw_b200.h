@@ -52,6 +52,14 @@ enum amrvw_schedule {
     AMRVW_SCHEDULE_PIPELINED = 2   /* several bulges in flight per polynomial, three indices apart */
 };
 
+/* Where the 2L/reuse shifts of a pipelined fat step come from (no reference counterpart: the
+ * reference takes two shifts from the trailing 2x2 block, create-bulge.jl:40-52). */
+enum amrvw_shift_solver {
+    AMRVW_SHIFTS_AUTO = 0,
+    AMRVW_SHIFTS_CHASE = 1,   /* core-chasing iteration on a copy of the trailing block              */
+    AMRVW_SHIFTS_DENSE = 2    /* trailing block written out densely + double-shift Hessenberg QR     */
+};
+
 /* Mirrors the reference's compile-time constants: IT_COUNT = 15
  * (create-bulge.jl:9), it_max = 20 n (AMRVW_algorithm.jl:25), tol = eps (AMRVW_algorithm.jl:184). */
 typedef struct amrvw_options {
@@ -59,6 +67,8 @@ typedef struct amrvw_options {
     int32_t lanes_per_poly;  /* pipelined: bulges in flight per polynomial (4, 8, 16 or 32); 0 = auto */
     int32_t shift_reuse;     /* pipelined: bulges driven by each shift pair (1, 2 or 4); 0 = auto     */
     int32_t small_window;    /* pipelined: windows up to this size use the one-bulge step; 0 = auto   */
+    int32_t shift_solver;    /* pipelined: amrvw_shift_solver; 0 = auto (dense)                        */
+    int32_t reserved;        /* must be 0 */
     uint64_t seed;           /* exceptional (random) shifts: counter-based, reproducible              */
 } amrvw_options;
 
@@ -127,6 +137,12 @@ int amrvw_measure_fp64_peak(amrvw_ctx* ctx, double* tflops);
  * turnover must preserve the product): out4 = {max rel. error of the Newton rsqrt, max |Q1Q2Q3 -
  * R1R2R3| over n random turnovers, max deviation from unit norm, turnovers sent to the IEEE path}. */
 int amrvw_selftest(amrvw_ctx* ctx, int64_t n, double* out4);
+
+/* Warp-cycle accounting of the last pipelined RDS call that asked for stats (development aid, no
+ * reference counterpart).  out16 = {sum over warps of: lifetime cycles, phase A (driver, shift
+ * sub-solves), lean systolic loop, general systolic loop; lean steps, general steps, lean calls,
+ * warps, set-up cycles, epilogue cycles; max lifetime over warps; 0...}. */
+int amrvw_last_profile(amrvw_ctx* ctx, int64_t* out16);
 
 int amrvw_version(void);
 

@@ -893,7 +893,163 @@ static void amrvw_algorithm(State<S>& s, std::vector<cplx>& EIGS, Rng& rng, Stat
 // obtained by running the reference driver on a scratch copy whose top rotator is made diagonal --
 // and chases L bulges with them one after another (on the GPU: pipelined, three indices apart,
 // which commutes exactly with this sequential order).  Smaller windows use the reference step.
-struct MsParams { int L = 8; int small = 24; int reuse = 1; /* each shift pair drives `reuse` bulges */ };
+struct MsParams { int L = 8; int small = 24; int reuse = 1; /* each shift pair drives `reuse` bulges */ int dense = 0; /* shifts by dense_shifts */ };
+
+// Shifts of a fat step from the DENSE trailing block (GPU kernel: csrc/shifts.cuh, same operations in
+// the same order).  The (m+1) x (m+1) trailing principal block of Q*R with Q[k0] made diagonal is
+// written out entry by entry -- column k top-down recurrences over the closed forms of
+// rfactorization.jl:83-97,139-170 and chains.jl:109-158 -- and its eigenvalues are found by the
+// classical double-shift Hessenberg QR (EISPACK hqr).  Shifts only steer convergence, so this
+// replaces the O(m^2)-turnover sub-solve of ms_shifts by O(m^3) plain flops with no dependent
+// rotator chains.  Returns false (caller falls back to ms_shifts) if hqr does not converge or
+// anything is not finite.
+static void dense_trailing_block(const State<double>& s, int k0, int stop, std::vector<double>& H, int M) {
+    const int j0 = k0 + 1;
+    H.assign((size_t)M * M, 0.0);
+    std::vector<double> cq(M + 1), sq(M + 1), isg(M);   // cq[t - k0], t = k0..stop+1; isg[j - j0] = 1/Ct[j].s
+    {
+        const double sg = sign_(s.Q[k0].c);
+        cq[0] = sg == 0 ? 1.0 : sg; sq[0] = 0.0;
+        for (int t = k0 + 1; t <= stop + 1; ++t) {
+            if (t <= s.nq()) { cq[t - k0] = s.Q[t].c; sq[t - k0] = s.Q[t].s; }
+            else { cq[t - k0] = 1.0; sq[t - k0] = 0.0; }
+        }
+        for (int j = j0; j <= stop + 1; ++j) isg[j - j0] = 1.0 / s.V.Ct[j].s;
+    }
+    for (int k = j0; k <= stop + 1; ++k) {
+        double P = 1.0, T = 0.0, Vacc = 0.0;
+        const double ck = s.V.B[k].c, sk = s.V.B[k].s;
+        for (int j = k; j >= j0; --j) {
+            const double w = (j == k) ? -sk : (s.V.B[j].c * P) * ck;
+            const double ctc = s.V.Ct[j].c;
+            const double R = (w + ctc * T) * isg[j - j0];
+            if (j + 1 <= stop + 1) H[(size_t)(j + 1 - j0) * M + (k - j0)] = cq[j - k0] * Vacc - sq[j - k0] * R;
+            Vacc = cq[j - k0] * R + sq[j - k0] * Vacc;
+            T = (-(ctc * w) - T) * isg[j - j0];
+            if (j < k) P = P * s.V.B[j].s;
+        }
+        H[(size_t)0 * M + (k - j0)] = cq[0] * Vacc;
+    }
+}
+
+// Double-shift Hessenberg QR after EISPACK hqr (eigenvalues only), 0-based, row major; every bulge
+// starts at the top of the active block and quotients by a common divisor are one reciprocal and
+// multiplications -- operation for operation what csrc/shifts.cuh does.
+static bool hqr_eigenvalues(std::vector<double>& Hm, int M, std::vector<cplx>& E) {
+    auto h = [&](int i, int j) -> double& { return Hm[(size_t)i * M + j]; };
+    auto rcp_ = [](double x) { return 1.0 / x; };
+    E.assign(M, cplx(0, 0));
+    double norm = 0.0;
+    for (int i = 0; i < M; ++i)
+        for (int j = (i > 0 ? i - 1 : 0); j < M; ++j) norm += std::fabs(h(i, j));
+    int en = M - 1, itn = 30 * M;
+    double t = 0.0;
+    while (en >= 0) {
+        int its = 0;
+        const int na = en - 1, enm2 = na - 1;
+        for (;;) {
+            int l;
+            for (l = en; l >= 1; --l) {
+                double s = std::fabs(h(l - 1, l - 1)) + std::fabs(h(l, l));
+                if (s == 0.0) s = norm;
+                const double tst2 = s + std::fabs(h(l, l - 1));
+                if (tst2 == s) break;
+            }
+            double x = h(en, en);
+            if (l == en) { E[en] = cplx(x + t, 0.0); en = na; break; }
+            double y = h(na, na);
+            double w = h(en, na) * h(na, en);
+            if (l == na) {
+                const double p = (y - x) * 0.5;
+                const double q = p * p + w;
+                double zz = std::sqrt(std::fabs(q));
+                x = x + t;
+                if (q >= 0.0) {
+                    zz = p + (p >= 0.0 ? zz : -zz);
+                    E[na] = cplx(x + zz, 0.0);
+                    E[en] = E[na];
+                    if (zz != 0.0) E[en] = cplx(x - w * rcp_(zz), 0.0);
+                } else {
+                    E[na] = cplx(x + p, zz);
+                    E[en] = cplx(x + p, -zz);
+                }
+                en = enm2;
+                break;
+            }
+            if (itn == 0) return false;
+            if (its == 10 || its == 20) {
+                t += x;
+                for (int i = 0; i <= en; ++i) h(i, i) -= x;
+                const double s = std::fabs(h(en, na)) + std::fabs(h(na, enm2));
+                x = 0.75 * s; y = x; w = -0.4375 * s * s;
+            }
+            ++its; --itn;
+            double p, q, r;
+            {
+                const double zz = h(l, l);
+                const double r0 = x - zz, s0 = y - zz;
+                p = (r0 * s0 - w) * rcp_(h(l + 1, l)) + h(l, l + 1);
+                q = h(l + 1, l + 1) - zz - r0 - s0;
+                r = h(l + 2, l + 1);
+                const double is = rcp_(std::fabs(p) + std::fabs(q) + std::fabs(r));
+                p = p * is; q = q * is; r = r * is;
+            }
+            for (int i = l + 2; i <= en; ++i) { h(i, i - 2) = 0.0; if (i != l + 2) h(i, i - 3) = 0.0; }
+            for (int k = l; k <= na; ++k) {
+                const bool notlas = (k != na);
+                double xs = 0.0;
+                if (k != l) {
+                    p = h(k, k - 1); q = h(k + 1, k - 1); r = notlas ? h(k + 2, k - 1) : 0.0;
+                    xs = std::fabs(p) + std::fabs(q) + std::fabs(r);
+                    if (xs == 0.0) continue;
+                    const double ix = rcp_(xs);
+                    p = p * ix; q = q * ix; r = r * ix;
+                }
+                double s = std::sqrt(p * p + q * q + r * r);
+                if (p < 0.0) s = -s;
+                if (k != l) h(k, k - 1) = -s * xs;
+                p = p + s;
+                const double is = rcp_(s), ip = rcp_(p);
+                const double hx = p * is, hy = q * is, hz = r * is;
+                q = q * ip; r = r * ip;
+                const int ihi = std::min(en, k + 3);
+                if (notlas) {
+                    for (int j = k; j <= en; ++j) {
+                        const double a0 = h(k, j), a1 = h(k + 1, j), a2 = h(k + 2, j);
+                        const double pp = a0 + q * a1 + r * a2;
+                        h(k, j) = a0 - pp * hx; h(k + 1, j) = a1 - pp * hy; h(k + 2, j) = a2 - pp * hz;
+                    }
+                    for (int i = l; i <= ihi; ++i) {
+                        const double a0 = h(i, k), a1 = h(i, k + 1), a2 = h(i, k + 2);
+                        const double pp = hx * a0 + hy * a1 + hz * a2;
+                        h(i, k) = a0 - pp; h(i, k + 1) = a1 - pp * q; h(i, k + 2) = a2 - pp * r;
+                    }
+                } else {
+                    for (int j = k; j <= en; ++j) {
+                        const double a0 = h(k, j), a1 = h(k + 1, j);
+                        const double pp = a0 + q * a1;
+                        h(k, j) = a0 - pp * hx; h(k + 1, j) = a1 - pp * hy;
+                    }
+                    for (int i = l; i <= ihi; ++i) {
+                        const double a0 = h(i, k), a1 = h(i, k + 1);
+                        const double pp = hx * a0 + hy * a1;
+                        h(i, k) = a0 - pp; h(i, k + 1) = a1 - pp * q;
+                    }
+                }
+            }
+        }
+    }
+    for (int i = 0; i < M; ++i)
+        if (!(std::isfinite(E[i].re) && std::isfinite(E[i].im))) return false;
+    return true;
+}
+
+static bool ms_shifts_dense(const State<double>& s, const Counter& ctr, int m, std::vector<cplx>& sh) {
+    const int stop = ctr.stop_index, k0 = stop - m, M = m + 1;
+    std::vector<double> H;
+    dense_trailing_block(s, k0, stop, H, M);
+    return hqr_eigenvalues(H, M, sh);
+}
 
 static void ms_shifts(const State<double>& s, const Counter& ctr, int m, std::vector<cplx>& sh, Rng& rng, Stats& st_sub) {
     // scratch copy; window [k+1, stop] with Q[k] made diagonal
@@ -977,9 +1133,11 @@ static void amrvw_algorithm_ms(State<double>& s, std::vector<cplx>& EIGS, Rng& r
             if (m % 2 == 0) m -= 1;
             std::vector<cplx> sh, pairs;
             Stats sub;
-            ms_shifts(s, ctr, m, sh, rng, sub);
-            st.turnovers += sub.turnovers;  // executed work
-            st.serial_turnovers += sub.turnovers;
+            if (!(P.dense && ms_shifts_dense(s, ctr, m, sh))) {
+                ms_shifts(s, ctr, m, sh, rng, sub);
+                st.turnovers += sub.turnovers;  // executed work
+                st.serial_turnovers += sub.turnovers;
+            }
             st.pipe_steps += (ctr.stop_index - ctr.start_index + 1) + 3 * (P.L - 1);
             ms_pair_shifts(sh, pairs);
             ++st.fat_steps;
@@ -1190,7 +1348,7 @@ int orc_num_threads() {
 // threads <= 0: all OpenMP threads.  sched: 0 reference schedule, 1 multishift (real only).
 int orc_roots_batch(const double* coeffs, const int64_t* offsets, int64_t B, int is_complex, double* roots_reim,
                     int32_t* nroots, orc_stats* total, orc_stats* per_poly, uint64_t seed, int threads, int sched, int ms_L, int ms_small) {
-    MsParams P; if (ms_L > 0) P.L = ms_L; if (ms_small > 0) P.small = ms_small % 1000; if (ms_small >= 1000) P.reuse = ms_small / 1000;
+    MsParams P; if (ms_L > 0) P.L = ms_L; if (ms_small > 0) P.small = ms_small % 1000; if (ms_small >= 1000) P.reuse = (ms_small / 1000) % 100; P.dense = (ms_small / 100000) % 10;
 #ifdef _OPENMP
     int nt = threads > 0 ? threads : omp_get_max_threads();
 #else

@@ -45,7 +45,7 @@ def num_threads():
     return lib().orc_num_threads()
 
 
-def roots_csr(coeffs, offsets, ws=None, seed=0, threads=0, sched=0, L=8, small=24, reuse=1, per_poly=False):
+def roots_csr(coeffs, offsets, ws=None, seed=0, threads=0, sched=0, L=8, small=24, reuse=1, dense=0, per_poly=False):
     """Batched oracle roots.  Returns (flat complex128 roots, root offsets, nroots, total stats[, per-poly stats])."""
     offsets = np.ascontiguousarray(offsets, dtype=np.int64)
     B = len(offsets) - 1
@@ -59,7 +59,7 @@ def roots_csr(coeffs, offsets, ws=None, seed=0, threads=0, sched=0, L=8, small=2
         roff = offsets - np.arange(B + 1, dtype=np.int64)
         out = np.zeros(int(offsets[-1]) + 1, dtype=np.complex128)
         lib().orc_roots_batch(_p(coeffs), _p(offsets), ctypes.c_int64(B), int(cx), _p(out), _p(nroots), ctypes.byref(st),
-                              pp, ctypes.c_uint64(seed), int(threads), int(sched), int(L), int(small + 1000 * reuse))
+                              pp, ctypes.c_uint64(seed), int(threads), int(sched), int(L), int(small + 1000 * reuse + 100000 * dense))
     else:
         ws = np.ascontiguousarray(ws, dtype=dt)
         roff = offsets.copy()

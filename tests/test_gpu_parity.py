@@ -168,18 +168,19 @@ def test_gpu_pencil_bitwise_vs_oracle(A, ctx_strict, oracle):
         assert np.array_equal(g.view(np.float64), want.view(np.float64))
 
 
-@pytest.mark.parametrize("L,reuse,small", [(4, 1, 16), (8, 2, 16), (16, 2, 24), (16, 1, 40), (32, 2, 40), (32, 4, 24)])
-def test_gpu_pipelined_bitwise_vs_sequential_multishift(A, oracle, L, reuse, small):
+@pytest.mark.parametrize("L,reuse,small,dense", [(4, 1, 16, 1), (8, 2, 16, 1), (16, 2, 24, 1), (16, 2, 24, 0), (16, 1, 40, 1), (32, 2, 40, 1), (32, 4, 24, 0), (32, 4, 24, 1)])
+def test_gpu_pipelined_bitwise_vs_sequential_multishift(A, oracle, L, reuse, small, dense):
     """The pipelined kernel (L bulges in flight, three indices apart, data handed lane to lane by
     shuffles) against the same multishift schedule executed one bulge after the other on the CPU
     (oracle amrvw_algorithm_ms): bulges three apart commute exactly, so without FMA contraction the
-    two must agree bit for bit -- this pins the systolic data flow, the shift sub-solves and the
-    small-window path."""
-    c = A.Context(seed=0, strict=True, schedule=A.SCHEDULE_PIPELINED, lanes_per_poly=L, shift_reuse=reuse, small_window=small)
+    two must agree bit for bit -- this pins the systolic data flow, the shift computation (dense
+    trailing block + Hessenberg QR, or the core-chasing sub-solve) and the small-window path."""
+    c = A.Context(seed=0, strict=True, schedule=A.SCHEDULE_PIPELINED, lanes_per_poly=L, shift_reuse=reuse, small_window=small,
+                  shift_solver=A.SHIFTS_DENSE if dense else A.SHIFTS_CHASE)
     try:
         rows = batch(oracle, 31, 10, 150) + batch(oracle, 32, 5, 421) + batch(oracle, 33, 6, 64) + batch(oracle, 34, 3, 30) + [p4, p5, p6]
         flat = np.concatenate(rows); off = np.zeros(len(rows) + 1, dtype=np.int64); np.cumsum([len(r) for r in rows], out=off[1:])
-        out, roff, nr, tot, pp = oracle.roots_csr(flat, off, sched=1, L=L, small=small, reuse=reuse, per_poly=True)
+        out, roff, nr, tot, pp = oracle.roots_csr(flat, off, sched=1, L=L, small=small, reuse=reuse, dense=dense, per_poly=True)
         got = A.roots(rows, ctx=c)
         n_checked = 0
         for p, g in enumerate(got):
