@@ -4,6 +4,7 @@
 #include "../../include/amrvw_b200.h"
 #include "kernels.cuh"
 #include "pipeline.cuh"
+#include "rounds.cuh"
 
 #include <cstdio>
 #include <cstring>
@@ -25,7 +26,10 @@ struct amrvw_ctx {
     amrvw_options opt;
     std::string err;
     // grow-only device buffers
-    DevBuf chains[5], diags[3], coeffs, coeffs2, offsets, roots, nroots, nunconv, stats, shifts, state, prof;
+    DevBuf chains[5], diags[3], coeffs, coeffs2, offsets, roots, nroots, nunconv, stats, shifts, state, prof, rec, fatshifts, swlist, counters, round_active;
+    unsigned* h_counters = nullptr;     // pinned
+    cudaEvent_t evpool[32] = {};
+    RoundsTimes times = {};
     int sm_count = 148;
 };
 
@@ -91,8 +95,11 @@ int amrvw_destroy(amrvw_ctx* ctx) {
     if (!ctx) return AMRVW_OK;
     cudaSetDevice(ctx->device);
     DevBuf* all[] = {&ctx->chains[0], &ctx->chains[1], &ctx->chains[2], &ctx->chains[3], &ctx->chains[4], &ctx->diags[0], &ctx->diags[1], &ctx->diags[2],
-                     &ctx->coeffs, &ctx->coeffs2, &ctx->offsets, &ctx->roots, &ctx->nroots, &ctx->nunconv, &ctx->stats, &ctx->shifts, &ctx->state, &ctx->prof};
+                     &ctx->coeffs, &ctx->coeffs2, &ctx->offsets, &ctx->roots, &ctx->nroots, &ctx->nunconv, &ctx->stats, &ctx->shifts, &ctx->state, &ctx->prof,
+                     &ctx->rec, &ctx->fatshifts, &ctx->swlist, &ctx->counters, &ctx->round_active};
     for (DevBuf* b : all) if (b->ptr) cudaFree(b->ptr);
+    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+    for (cudaEvent_t e : ctx->evpool) if (e) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -175,7 +182,7 @@ static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, cons
     pr.WB = (Rot<S>*)ctx->chains[3].ptr; pr.WCt = (Rot<S>*)ctx->chains[4].ptr;
     pr.DQ = (S*)ctx->diags[0].ptr; pr.DR = (S*)ctx->diags[1].ptr; pr.WD = (S*)ctx->diags[2].ptr;
     pr.dstack = (int*)ctx->shifts.ptr;
-    pr.prof = nullptr;
+    pr.prof = nullptr; pr.rec = nullptr; pr.shifts = nullptr; pr.swlist = nullptr; pr.counters = nullptr;
     if (var == V_RDS && stats) {   // warp-cycle counters ride along with the statistics
         int rc = reserve(ctx, ctx->prof, 16 * sizeof(unsigned long long)); if (rc) return rc;
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->prof.ptr, 0, 16 * sizeof(unsigned long long), ctx->stream));
@@ -191,8 +198,20 @@ static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, cons
     bool done = false;
     if constexpr (is_real<S>::value) {
         if (var == V_RDS && ctx->opt.schedule != AMRVW_SCHEDULE_REFERENCE) {
-            int rc = launch_pipelined_rds(pr, ctx->opt, (int)max_len, ctx->sm_count, st, &launches);
-            if (rc != 0) return fail(ctx, AMRVW_ERR_CUDA, std::string("pipelined launch: ") + cudaGetErrorString((cudaError_t)rc));
+            // rounds schedule: per-polynomial records, shifts, small-window queue, counters
+            const int max_rounds = 20 * (int)max_len + 8;
+            int rc;
+            if ((rc = reserve(ctx, ctx->rec, (size_t)nbatch * sizeof(PolyRec)))) return rc;
+            if ((rc = reserve(ctx, ctx->fatshifts, (size_t)nbatch * 32 * sizeof(Shifts)))) return rc;
+            if ((rc = reserve(ctx, ctx->swlist, ((size_t)total / 3 + (size_t)nbatch + 16) * sizeof(SmallWin)))) return rc;
+            if ((rc = reserve(ctx, ctx->counters, CNT_WORDS * sizeof(unsigned)))) return rc;
+            if ((rc = reserve(ctx, ctx->round_active, (size_t)max_rounds * sizeof(unsigned)))) return rc;
+            if (!ctx->h_counters) CUDA_TRY(ctx, cudaMallocHost((void**)&ctx->h_counters, 16 * sizeof(unsigned)));
+            if (stats && !ctx->evpool[0]) for (cudaEvent_t& e : ctx->evpool) CUDA_TRY(ctx, cudaEventCreate(&e));
+            pr.rec = (PolyRec*)ctx->rec.ptr; pr.shifts = (Shifts*)ctx->fatshifts.ptr; pr.swlist = ctx->swlist.ptr; pr.counters = (unsigned*)ctx->counters.ptr;
+            cudaError_t e = launch_rounds_rds(pr, ctx->opt, (int)max_len, ctx->sm_count, st, &launches, ctx->h_counters, (unsigned*)ctx->round_active.ptr, max_rounds,
+                                              ctx->evpool, stats ? &ctx->times : nullptr);
+            if (e != cudaSuccess) return fail(ctx, AMRVW_ERR_CUDA, std::string("rounds schedule: ") + cudaGetErrorString(e));
             done = true;
         }
     }
@@ -310,6 +329,10 @@ int amrvw_last_profile(amrvw_ctx* ctx, int64_t* out16) {
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     CUDA_TRY(ctx, cudaMemcpyAsync(out16, ctx->prof.ptr, 16 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    // kernel times of the rounds schedule, microseconds
+    out16[8] = (int64_t)(ctx->times.setup_ms * 1e3); out16[9] = (int64_t)(ctx->times.a_ms * 1e3); out16[10] = (int64_t)(ctx->times.b_ms * 1e3);
+    out16[11] = (int64_t)(ctx->times.small_ms * 1e3); out16[12] = (int64_t)(ctx->times.finish_ms * 1e3);
+    out16[13] = ctx->times.rounds; out16[14] = ctx->times.small_windows;
     return AMRVW_OK;
 }
 

@@ -6,6 +6,8 @@
 
 namespace amrvw {
 
+struct PolyRec;   // rounds.cuh
+
 template <class S> struct Problem {
     const S* coeffs;          // non-pencil: a0..an per polynomial; pencil: vs
     const S* ws;              // pencil only
@@ -20,7 +22,10 @@ template <class S> struct Problem {
     S* DQ; S* DR; S* WD;
     int* dstack;              // pipelined kernel: per-polynomial stack of deflated Q indices (same slot layout)
     int extra;                // 1 (non-pencil: len+1 slots) or 2 (pencil: N+2 slots)
-    unsigned long long* prof; // pipelined kernel: 16 warp-cycle counters (nullable), see amrvw_last_profile
+    unsigned long long* prof; // pipelined kernels: 16 warp-cycle counters (nullable), see amrvw_last_profile
+    // rounds schedule (rounds.cuh): per-polynomial records, shifts of the pending fat steps, queue of
+    // deferred small windows, round counters
+    PolyRec* rec; Shifts* shifts; void* swlist; unsigned* counters;
     unsigned long long seed;
 };
 

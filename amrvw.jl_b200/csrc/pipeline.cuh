@@ -115,7 +115,7 @@ AMRVW_NI void chase_step_general(StepState& z) {
     turnover(z.W, z.V, z.U, z.V, z.U, z.W);
 }
 // last position (j == stop): passthrough_triu, then fuse the bulge into Q (RDS.jl:110-128)
-AMRVW_NI void chase_step_final(StepState& z, double pbot) {
+AMRVW_DI void chase_step_final(StepState& z, double pbot) {
     turnover(z.b1, z.b2, z.V, z.V, z.b1, z.b2);
     turnover(z.c2, z.c1, z.V, z.V, z.c2, z.c1);
     turnover(z.b0, z.b1, z.U, z.U, z.b0, z.b1);
@@ -223,7 +223,7 @@ AMRVW_NI void bulge_step_window(Fact<double, false>& F, Counter& ctr, const Shif
 
 // create_bulge (create-bulge.jl:20-77) on the lane's window [start-1 .. start+2] + absorb_Ut
 // (RDS.jl:14-36), out of line: once per bulge per fat step, keeps the chase loop small.
-AMRVW_NI void create_and_absorb(StepState& z, const Rot<double> qm, const Rot<double> bm, const Rot<double> cm, const Fact<double, false>& F,
+AMRVW_DI void create_and_absorb(StepState& z, const Rot<double> qm, const Rot<double> bm, const Rot<double> cm, const Fact<double, false>& F,
                                 int start, int stop, int mode, const Shifts sh, uint64_t seed, uint64_t poly, int ordinal) {
     Rot<double> U, V;
     if (mode == 2) {
@@ -251,6 +251,23 @@ AMRVW_NI void create_and_absorb(StepState& z, const Rot<double> qm, const Rot<do
     r2.s = sign_(ptop) * r2.s;
     z.q0 = r2;
     z.U = U; z.V = V;
+}
+
+// create_bulge + absorb_Ut for the lane whose bulge enters the window this step; everything it needs
+// beyond the lane's window is read here (the rotators at start-1 never change during a fat step)
+AMRVW_NI void create_and_absorb_at(StepState& z, const Fact<double, false>& F, const int start, const int stop, const int mode, const Shifts* shl, const int lane,
+                                   const uint64_t seed, const uint64_t poly, const int ordinal) {
+    const Rot<double> one = make_rot<double>(1.0, 0.0);
+    const Rot<double> qm = ldg_rot(F.Q + start - 1);                 // Q[0] is the (1,0) sentinel
+    Rot<double> bm = one, cm = one;
+    if (start > 1) { bm = ldg_rot(F.B + start - 1); cm = ldg_rot(F.Ct + start - 1); }
+    Shifts sh;
+    sh.e1 = cplx(0.0, 0.0); sh.e2 = cplx(0.0, 0.0);
+    if (mode == 1) sh = shl[lane];
+    create_and_absorb(z, qm, bm, cm, F, start, stop, mode, sh, seed, poly, ordinal);
+}
+AMRVW_NI void chase_step_final_at(StepState& z, const Fact<double, false>& F, const int stop) {
+    chase_step_final(z, sign_(F.Q[stop + 1].c));                      // Q[N] is the (1,0) sentinel
 }
 
 // drive_window's step for the pipelined kernel's serial phases
@@ -296,8 +313,20 @@ AMRVW_DI void pop_window(LeaderState& ls) {
 // Phase A: the driver (AMRVW_algorithm.jl:10-138) up to the next fat step.  Returns 0 when the
 // polynomial is finished, 1 for a fat step with shifts in shl[0..nb), 2 for a fat step of nb
 // exceptional (random) bulges.
+// Decoupled small windows are not solved on the spot: they are queued for the small-window kernel
+// (rounds.cuh), one thread each.
+struct SmallWinRec { int poly, lo, hi, it_count; };
+struct SmallSink {
+    void* list; unsigned* count; int poly;
+    AMRVW_DI void push(int lo, int hi, int it_count) const {
+        const unsigned k = atomicAdd(count, 1u);
+        SmallWinRec r = {poly, lo, hi, it_count};
+        reinterpret_cast<SmallWinRec*>(list)[k] = r;
+    }
+};
+
 AMRVW_DI int phase_a(Fact<double, false>& F, LeaderState& ls, cplx* E, const GroupScratch& sc, Shifts* shl, const int L, const PipeParams pp,
-                     int& nb, const uint64_t seed, const uint64_t poly, PolyStats& st, const int* dstack, double2* sn, const int NT) {
+                     int& nb, const uint64_t seed, const uint64_t poly, PolyStats& st, const int* dstack, double2* sn, const int NT, const SmallSink& sink) {
     const WindowStep wstep = {sn, NT};
     Counter& ctr = ls.ctr;
     double A[4];
@@ -327,19 +356,15 @@ AMRVW_DI int phase_a(Fact<double, false>& F, LeaderState& ls, cplx* E, const Gro
             ctr.zero_index = 0; ctr.start_index = 1;
             check_deflation_stack(F, ls, dstack);
         } else if (delta <= pp.small) {
-            // decoupled small window [lo2, hi2]: finish it in shared memory, one bulge at a time
-            const long long pc0 = clock64();
+            // decoupled small window [lo2, hi2]: nothing above it ever touches its rotators again, so it
+            // is queued and finished later with the reference's one-bulge schedule (rounds_small_kernel)
             const int lo2 = ctr.start_index, hi2 = ctr.stop_index;
-            Fact<double, false> W = stage_window(F, sc, lo2 - 1, hi2);
-            Counter c2 = {lo2 - 1, lo2, hi2, ctr.it_count, -1};
-            const int left = drive_window(W, lo2, hi2, c2, E, ls.it_max, seed, poly, ls.ord, st, wstep);   // the reference's cap is global (20 n)
-            F.turnovers += W.turnovers;
-            ls.unconv += left;
+            sink.push(lo2, hi2, ctr.it_count);
             if (lo2 == 2) { diagonal_block(F, 1, A); E[1] = to_c(A[0]); }
             pop_window(ls);
             ctr.stop_index = lo2 - 2; ctr.zero_index = 0; ctr.start_index = 1; ctr.it_count = 15;
             if (ctr.stop_index >= 1) check_deflation_stack(F, ls, dstack);
-            ls.pc_small += clock64() - pc0; ls.pn_small += 1;
+            ls.pn_small += 1;
         } else if (ctr.it_count == 0) {
             st.fat_steps++;
             nb = L;
@@ -415,7 +440,7 @@ AMRVW_DI void cp_async16_sa(unsigned sa, const void* gsrc) { asm volatile("cp.as
 
 // role: bit 0: the lane's group is chasing, bit 1: lane 0 of its group (feeds), bit 2: lane L-1 (retires)
 template <int L, int NT>
-AMRVW_NI int lean_chase(StepState& z, Rot<double>* gq, Rot<double>* gb, Rot<double>* gc, const unsigned stage_sa, const unsigned snap_sa, int* dstack, int sp,
+AMRVW_DI int lean_chase(StepState& z, Rot<double>* gq, Rot<double>* gb, Rot<double>* gc, const unsigned stage_sa, const unsigned snap_sa, int* dstack, int sp,
                         const int start, const int t0, const int t1, const int role) {
     Rot<double> q0 = z.q0, q1 = z.q1, q2 = z.q2, b0 = z.b0, b1 = z.b1, b2 = z.b2, c0 = z.c0, c1 = z.c1, c2 = z.c2, U = z.U, V = z.V, W = z.W;
     const bool chasing = role & 1, feeds = (role & 3) == 3, retires = (role & 5) == 5;
@@ -474,299 +499,6 @@ AMRVW_NI int lean_chase(StepState& z, Rot<double>* gq, Rot<double>* gb, Rot<doub
     }
     z.q0 = q0; z.q1 = q1; z.q2 = q2; z.b0 = b0; z.b1 = b1; z.b2 = b2; z.c0 = c0; z.c1 = c1; z.c2 = c2; z.U = U; z.V = V; z.W = W;
     return sp;
-}
-
-#ifndef AMRVW_PIPE_MINBLOCKS
-#define AMRVW_PIPE_MINBLOCKS 6
-#endif
-template <int L, int WPB>
-__global__ void __launch_bounds__(32 * WPB, AMRVW_PIPE_MINBLOCKS) roots_pipelined_kernel(Problem<double> pr, PipeParams pp) {
-    constexpr int G = 32 / L;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int wib = threadIdx.x >> 5, lane32 = threadIdx.x & 31;
-    const int grp = lane32 / L, lane = lane32 % L;
-    const long long p = ((long long)blockIdx.x * WPB + wib) * G + grp;
-    const bool valid = p < pr.nbatch;
-    const bool leader = valid && lane == 0;
-
-    // shared memory carve-up: per warp [32 Shifts][G groups x (3 chains x ms rotators + ms eigenvalues)]
-    const size_t per_group = (size_t)pp.ms * (3 * sizeof(Rot<double>) + sizeof(cplx)) + (pp.dense ? ((size_t)pp.mh * pp.mh + pp.mh + 2) * sizeof(double) : 0);
-    const size_t per_warp = 32 * sizeof(Shifts) + G * per_group;
-    unsigned char* wbase = smem_raw + (size_t)wib * per_warp;
-    [[maybe_unused]] constexpr int NT = 32 * WPB;
-    double2* snap = reinterpret_cast<double2*>(smem_raw + (size_t)WPB * per_warp);   // [12][NT] step snapshots
-    (void)snap;
-    double2* stage = snap + 12 * NT + (wib * G + grp) * (3 * AMRVW_RING);               // [AMRVW_RING][3] look-ahead ring of lane 0
-    Shifts* shl = reinterpret_cast<Shifts*>(wbase) + grp * L;
-    GroupScratch sc;
-    {
-        unsigned char* g = wbase + 32 * sizeof(Shifts) + (size_t)grp * per_group;
-        sc.q = reinterpret_cast<Rot<double>*>(g);
-        sc.b = sc.q + pp.ms;
-        sc.c = sc.b + pp.ms;
-        sc.e = reinterpret_cast<cplx*>(sc.c + pp.ms);
-        sc.H = reinterpret_cast<double*>(sc.e + pp.ms);
-        sc.isg = sc.H + (size_t)pp.mh * pp.mh;
-    }
-
-    // ---------------- set-up (lane 0 of each group): trim, closed forms, factorization
-    const long long pc_begin = clock64();
-    long long pc_a = 0, pc_lean = 0, pc_b = 0, pn_lean = 0, pn_gen = 0, pn_calls = 0;
-    Fact<double, false> F;
-    F.N = 0; F.turnovers = 0;
-    F.Q = F.B = F.Ct = F.WB = F.WCt = nullptr; F.DQ = F.DR = F.WD = nullptr;
-    PolyStats st = {0, 0, 0, 0, 0};
-    LeaderState ls;
-    ls.kk = 0; ls.it_max = 0; ls.ord = 0; ls.unconv = 0; ls.sp = 0; ls.pc_sub = 0; ls.pc_small = 0; ls.pn_small = 0;
-    ls.ctr = {0, 1, 0, 15, -1};
-    cplx* out = nullptr;
-    int* dstack = nullptr;
-    int N = 0, K = 0;
-    int mode = 0;   // 0: nothing to do / finished, 1: fat step, 2: exceptional fat step
-    bool iterating = false;
-    if (valid) {
-        const long long off = pr.offsets[p];
-        out = pr.roots + (off - p);
-        dstack = pr.dstack + (off + (long long)pr.extra * p);
-        if (leader) {
-            const int len = (int)(pr.offsets[p + 1] - off);
-            int first, last;
-            trim_zeros(pr.coeffs + off, len, first, last);
-            if (first < 0) {
-                finish_poly(pr, p, out, 0, 0, 0, st);
-            } else {
-                const double* ps = pr.coeffs + off + first;
-                const int ncoef = last - first + 1;
-                K = first;
-                if (ncoef <= 3) {
-                    const int cnt = solve_simple(ps, ncoef, out);
-                    finish_poly(pr, p, out, cnt, K, 0, st);
-                } else {
-                    N = ncoef - 1;
-                    F = make_fact<double, false>(pr, p, N);
-                    factor_companion(F, ps);
-                    for (int i = 0; i < N; ++i) out[i] = cplx(0.0, 0.0);
-                    ls.ctr = {0, 1, N - 1, 15, -1};
-                    ls.it_max = 20ll * (N - 1);
-                    iterating = true;
-                }
-            }
-        }
-    }
-    // every lane of the group needs the chain pointers
-    N = __shfl_sync(0xffffffffu, N, grp * L);
-    if (valid && N > 0 && !leader) F = make_fact<double, false>(pr, p, N);
-    __syncwarp();
-
-    long long my_turnovers = 0;
-    int nb = 0;
-    const long long pc_setup = clock64();
-    for (;;) {
-        // ---------------- phase A
-        const long long pc_t0 = clock64();
-        mode = 0;
-        if (leader && iterating) {
-            mode = phase_a(F, ls, out - 1, sc, shl, L, pp, nb, pr.seed, (uint64_t)p, st, dstack, snap + threadIdx.x, NT);
-            if (mode == 0) iterating = false;
-        }
-        __syncwarp();
-        if (!__any_sync(0xffffffffu, mode != 0)) break;
-        // group-uniform parameters of the fat step
-        mode = __shfl_sync(0xffffffffu, mode, grp * L);
-        nb = __shfl_sync(0xffffffffu, nb, grp * L);
-        const int start = __shfl_sync(0xffffffffu, ls.ctr.start_index, grp * L);
-        const int stop = __shfl_sync(0xffffffffu, ls.ctr.stop_index, grp * L);
-        const int ord0 = __shfl_sync(0xffffffffu, ls.ord, grp * L);
-        int sp = __shfl_sync(0xffffffffu, ls.sp, grp * L);
-        const bool act = mode != 0;
-        const int T = act ? (stop - start + 3 * L + 1) : 0;
-        const int Tmax = __reduce_max_sync(0xffffffffu, T);
-        const long long pc_t1 = clock64();
-        pc_a += pc_t1 - pc_t0;
-
-        // ---------------- phase B: systolic chase of nb bulges through [start, stop]
-        Rot<double> q0, q1, q2, b0, b1, b2, c0, c1, c2, U, V, W;
-        q0 = q1 = q2 = b0 = b1 = b2 = c0 = c1 = c2 = U = V = W = make_rot<double>(1.0, 0.0);
-        Shifts mysh;
-        mysh.e1 = cplx(0.0, 0.0); mysh.e2 = cplx(0.0, 0.0);
-        const bool has_bulge = act && lane < nb;
-        if (has_bulge && mode == 1) mysh = shl[lane];
-        double pbot = 1.0;
-        Rot<double> qm = q0, bm = q0, cm = q0;   // static rotators at index start-1
-        if (act) {
-            qm = ldg_rot(F.Q + start - 1);                 // Q[0] is the (1,0) sentinel
-            if (start > 1) { bm = ldg_rot(F.B + start - 1); cm = ldg_rot(F.Ct + start - 1); }
-            pbot = sign_(F.Q[stop + 1].c);                 // Q[N] is the (1,0) sentinel
-            if (lane == 0) {
-                for (int a = 0; a < AMRVW_RING - 1; ++a) {
-                    const int nidx = min(start + a, stop + 1);
-                    cp_async16(stage + 3 * a + 0, F.Q + nidx); cp_async16(stage + 3 * a + 1, F.B + nidx); cp_async16(stage + 3 * a + 2, F.Ct + nidx);
-                    cp_async_commit();
-                }
-            }
-        }
-        for (int t = 0; t < Tmax; ++t) {
-            {   // every lane of the warp at a regular position (or idle for good): hand over to the lean loop
-                const bool g_dead = !act || t >= T;
-                const bool g_main = act && nb == L && t >= 3 * L && t <= stop - start;
-                if (__all_sync(0xffffffffu, g_dead || g_main) && __any_sync(0xffffffffu, g_main)) {
-                    const int te = __reduce_min_sync(0xffffffffu, g_main ? stop - start + 1 : 0x7fffffff);
-                    const long long pc_l0 = clock64();
-                    StepState z = {q0, q1, q2, b0, b1, b2, c0, c1, c2, U, V, W};
-                    const int role = (g_main ? 1 : 0) | (lane == 0 ? 2 : 0) | (lane == L - 1 ? 4 : 0);
-                    sp = lean_chase<L, NT>(z, F.Q, F.B, F.Ct, (unsigned)__cvta_generic_to_shared(stage), (unsigned)__cvta_generic_to_shared(snap + threadIdx.x), dstack, sp,
-                                           start, t, te, role);
-                    q0 = z.q0; q1 = z.q1; q2 = z.q2; b0 = z.b0; b1 = z.b1; b2 = z.b2; c0 = z.c0; c1 = z.c1; c2 = z.c2; U = z.U; V = z.V; W = z.W;
-                    if (g_main) my_turnovers += 7ll * (te - t);
-                    pc_lean += clock64() - pc_l0; pn_lean += te - t; pn_calls += 1; pn_gen -= 1;
-                    t = te - 1;
-                    continue;
-                }
-            }
-            const int tp = t - 3 * lane;
-            // ingest: what the previous lane finished last step (lane 0: from memory)
-            Rot<double> iq = shfl_up_rot(q0, L), ib = shfl_up_rot(b0, L), ic = shfl_up_rot(c0, L);
-            if (lane == 0) {
-                cp_async_wait_ring();
-                const double2* sg = stage + (t & (AMRVW_RING - 1)) * 3;
-                const double2 vq = sg[0], vb = sg[1], vc = sg[2];
-                iq = make_rot<double>(vq.x, vq.y); ib = make_rot<double>(vb.x, vb.y); ic = make_rot<double>(vc.x, vc.y);
-                if (act) {
-                    const int nidx = min(start + t + AMRVW_RING - 1, stop + 1);
-                    double2* sn2 = stage + ((t + AMRVW_RING - 1) & (AMRVW_RING - 1)) * 3;
-                    cp_async16(sn2 + 0, F.Q + nidx); cp_async16(sn2 + 1, F.B + nidx); cp_async16(sn2 + 2, F.Ct + nidx);
-                }
-                cp_async_commit();
-            }
-            q0 = q1; q1 = q2; q2 = iq;
-            b0 = b1; b1 = b2; b2 = ib;
-            c0 = c1; c1 = c2; c2 = ic;
-            const int i = start + tp - 2;   // position of this lane's bulge; window = indices i..i+2
-            if (has_bulge && tp >= 2 && i <= stop - 1) {
-                if (tp == 2) {
-                    StepState z = {q0, q1, q2, b0, b1, b2, c0, c1, c2, U, V, W};
-                    create_and_absorb(z, qm, bm, cm, F, start, stop, mode, mysh, pr.seed, (uint64_t)p, ord0 + lane);
-                    q0 = z.q0; q1 = z.q1; U = z.U; V = z.V; W = z.W;
-                    my_turnovers += 1;
-                }
-                if (i <= stop - 2) {
-                    // regular position: the 7 turnovers of one chase step (RDS.jl:42-70, 97-108) as ONE
-                    // straight-line block, so the independent ones (T2|T3, T4|T5) overlap.  The inputs are
-                    // parked in shared memory first; a degenerate turnover (flagged, essentially never)
-                    // redoes the step on the general path from that snapshot.
-#ifndef AMRVW_STRICT
-                    AMRVW_CHASE_REGULAR(snap + threadIdx.x, NT);
-#else
-                    AMRVW_CHASE_GENERAL();
-#endif
-                    my_turnovers += 7;
-                } else {
-                    StepState z = {q0, q1, q2, b0, b1, b2, c0, c1, c2, U, V, W};
-                    chase_step_final(z, pbot);
-                    q0 = z.q0; q1 = z.q1; q2 = z.q2; b0 = z.b0; b1 = z.b1; b2 = z.b2; c0 = z.c0; c1 = z.c1; c2 = z.c2; U = z.U; V = z.V; W = z.W;
-                    my_turnovers += 7;
-                }
-            }
-            // retire: the last lane writes index i back
-            if (lane == L - 1 && act && i >= start && i <= stop + 1) {
-                stg_rot(F.Q + i, q0); stg_rot(F.B + i, b0); stg_rot(F.Ct + i, c0);
-                if (i <= stop && fabs(q0.s) <= AMRVW_EPS) dstack[sp++] = i;   // deflatable: record for phase A
-            }
-        }
-        if (lane == 0) cp_async_wait_all();   // drain look-ahead requests past the end of the window
-        pc_b += clock64() - pc_t1; pn_gen += Tmax;
-        sp = __shfl_sync(0xffffffffu, sp, grp * L + L - 1);
-        if (leader && act) {
-            ls.sp = sp;
-            st.sweeps += nb;
-            if (mode == 2) { st.exceptional += nb; ls.ord += nb; ls.ctr.it_count = 14; }
-        }
-        __syncwarp();
-    }
-
-    // ---------------- epilogue: turnover count, sort, zero roots
-    const long long pc_loop_end = clock64();
-    for (int d = L / 2; d >= 1; d >>= 1) my_turnovers += __shfl_down_sync(0xffffffffu, my_turnovers, d, L);
-    if (leader && N > 0) {
-        sort_roots(out, N);
-        st.turnovers = F.turnovers + my_turnovers;
-        st.unconverged = ls.unconv + (ls.ctr.stop_index >= 1 ? ls.ctr.stop_index + 1 : 0);
-        finish_poly(pr, p, out, N, K, st.unconverged, st);
-    }
-    if (pr.prof) {   // warp-cycle accounting for amrvw_last_profile
-        __syncwarp();
-        if (leader) {
-            atomicAdd(pr.prof + 11, (unsigned long long)ls.pc_sub);
-            atomicAdd(pr.prof + 12, (unsigned long long)ls.pc_small);
-            atomicAdd(pr.prof + 13, (unsigned long long)ls.pn_small);
-        }
-        if (lane32 == 0) {
-            const long long pc_end = clock64();
-            atomicAdd(pr.prof + 0, (unsigned long long)(pc_end - pc_begin));
-            atomicAdd(pr.prof + 1, (unsigned long long)pc_a);
-            atomicAdd(pr.prof + 2, (unsigned long long)pc_lean);
-            atomicAdd(pr.prof + 3, (unsigned long long)(pc_b - pc_lean));
-            atomicAdd(pr.prof + 4, (unsigned long long)pn_lean);
-            atomicAdd(pr.prof + 5, (unsigned long long)(pn_gen - pn_lean));
-            atomicAdd(pr.prof + 6, (unsigned long long)pn_calls);
-            atomicAdd(pr.prof + 7, 1ull);
-            atomicAdd(pr.prof + 8, (unsigned long long)(pc_setup - pc_begin));
-            atomicAdd(pr.prof + 9, (unsigned long long)(pc_end - pc_loop_end));
-            atomicMax(pr.prof + 10, (unsigned long long)(pc_end - pc_begin));
-        }
-    }
-}
-
-template <int L>
-static int launch_pipelined_L(const Problem<double>& pr, PipeParams pp, cudaStream_t st) {
-#ifndef AMRVW_PIPE_WPB
-#define AMRVW_PIPE_WPB 2
-#endif
-    constexpr int WPB = AMRVW_PIPE_WPB;
-    constexpr int G = 32 / L;
-    const size_t per_group = (size_t)pp.ms * (3 * sizeof(Rot<double>) + sizeof(cplx)) + (pp.dense ? ((size_t)pp.mh * pp.mh + pp.mh + 2) * sizeof(double) : 0);
-    const size_t per_warp = 32 * sizeof(Shifts) + (size_t)G * per_group;
-    const size_t smem = WPB * per_warp + (size_t)12 * 32 * WPB * sizeof(double2) + (size_t)WPB * G * 3 * AMRVW_RING * sizeof(double2);
-    const long long groups_per_block = (long long)WPB * G;
-    const int blocks = (int)((pr.nbatch + groups_per_block - 1) / groups_per_block);
-    auto kern = roots_pipelined_kernel<L, WPB>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    kern<<<blocks, 32 * WPB, smem, st>>>(pr, pp);
-    return (int)cudaGetLastError();
-}
-
-// Chooses L (bulges in flight per polynomial) from the degree and the batch: enough lanes to fill the
-// GPU, not more than the windows can feed (a fat step needs a window > small >= 2L/reuse).
-static int launch_pipelined_rds(const Problem<double>& pr, const amrvw_options& opt, int max_len, int sm_count, cudaStream_t st, int* launches) {
-    const int degree = max_len - 1;
-    int L = opt.lanes_per_poly;
-    if (L == 0) {
-        if (degree < 48) L = 4;
-        else if (degree < 200) L = 8;
-        else if (degree < 1200 && pr.nbatch * 16 > (long long)sm_count * 512) L = 8;
-        else L = 16;
-        if (degree >= 1200 && pr.nbatch * 32 <= (long long)sm_count * 256) L = 32;
-    }
-    PipeParams pp;
-    pp.reuse = opt.shift_reuse ? opt.shift_reuse : 2;
-    if (pp.reuse > L / 2) pp.reuse = L / 2 > 0 ? L / 2 : 1;
-    const int mshift = 2 * L / pp.reuse;
-    pp.small = opt.small_window ? opt.small_window : (mshift + 8 > 24 ? mshift + 8 : 24);
-    if (pp.small < mshift) pp.small = mshift;      // a fat step needs delta - 1 >= m
-    if (pp.small > 96) pp.small = 96;
-    pp.ms = (mshift > pp.small ? mshift : pp.small) + 4;
-    pp.dense = opt.shift_solver != AMRVW_SHIFTS_CHASE;
-    pp.mh = mshift;
-    int rc;
-    switch (L) {
-        case 4: rc = launch_pipelined_L<4>(pr, pp, st); break;
-        case 8: rc = launch_pipelined_L<8>(pr, pp, st); break;
-        case 16: rc = launch_pipelined_L<16>(pr, pp, st); break;
-        default: rc = launch_pipelined_L<32>(pr, pp, st); break;
-    }
-    *launches += 1;
-    return rc;
 }
 
 }  // namespace amrvw

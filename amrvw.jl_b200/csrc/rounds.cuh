@@ -1,0 +1,414 @@
+// rounds.cuh -- the pipelined multishift RDS path as ROUNDS of two kernels (the north-star path).
+//
+//   set-up kernel      one thread per polynomial: trim, closed forms, companion factorization
+//   repeat until no polynomial is iterating:
+//     phase A kernel   one thread per polynomial: the driver of AMRVW_algorithm.jl:10-138 up to the
+//                      next fat step -- deflation bookkeeping, 1x1 / 2x2 extraction, shifts from the
+//                      dense trailing block (shifts.cuh); small decoupled windows are only QUEUED
+//     phase B kernel   one group of L lanes per polynomial: the systolic chase of L bulges
+//                      (pipeline.cuh: lean loop + fill/drain loop)
+//   small-window kernel  one thread per queued window: the reference's one-bulge iteration.  A window
+//                      below a deflated rotator is decoupled from everything above it (no turnover
+//                      of the upper window touches its rotators), so solving all of
+//                      them at the end, in parallel, gives bit-identical eigenvalues
+//   finish kernel      one thread per polynomial: sort, zero roots, statistics
+//
+// Why kernels and not one fused kernel (the round-1 design, 0.93 s on config 2):
+//   * the serial phases ran on ONE lane of a 32-lane warp while the other 31 waited, 28% of every
+//     warp's life (profiles/r01_warp_cycles.txt), and shared the FP64 pipe with the chase warps;
+//     one thread per polynomial runs 32 of them per warp-instruction, off the chase's critical path;
+//   * ptxas stacks the registers of a callee on top of what its caller keeps live, so inside the
+//     fused kernel the systolic loop was scheduled into 93 registers (1119 cycles per step alone on
+//     an SMSP) where it wants ~115 of its own (853 cycles: tools/ubench_lean.cu); here it is the
+//     body of its own kernel;
+//   * the rounds cost one grid-wide join per fat step: sum over rounds of the largest window is
+//     1.04x the slowest polynomial's own step count (oracle trace, n = 1000), i.e. what the fused
+//     kernel already paid to its slowest warp.
+#pragma once
+#include "pipeline.cuh"
+
+namespace amrvw {
+
+// per-polynomial record of the rounds schedule (global memory)
+struct PolyRec {
+    LeaderState ls;
+    PolyStats st;
+    long long serial_turnovers;   // turnovers of the serial phases
+    long long chase_turnovers;    // turnovers of phase B
+    int N, K;                     // trimmed degree, number of trimmed zero roots
+    int mode, nb;                 // pending fat step: 0 none, 1 shifted, 2 exceptional; bulges
+    int iterating;
+    int pad;
+};
+typedef SmallWinRec SmallWin;
+
+// counters[0]: polynomials that got a fat step from the last phase A launch
+// counters[1]: small windows queued
+// counters[2..]: reserved
+enum { CNT_ACTIVE = 0, CNT_SMALL = 1, CNT_WORDS = 8 };
+
+// ---------------------------------------------------------------- set-up
+__global__ void __launch_bounds__(64) rounds_setup_kernel(Problem<double> pr) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= pr.nbatch) return;
+    PolyRec rec;
+    rec.ls.kk = 0; rec.ls.it_max = 0; rec.ls.ord = 0; rec.ls.unconv = 0; rec.ls.sp = 0; rec.ls.pc_sub = 0; rec.ls.pc_small = 0; rec.ls.pn_small = 0;
+    rec.ls.ctr = {0, 1, 0, 15, -1};
+    rec.st = {0, 0, 0, 0, 0};
+    rec.serial_turnovers = 0; rec.chase_turnovers = 0;
+    rec.N = 0; rec.K = 0; rec.mode = 0; rec.nb = 0; rec.iterating = 0; rec.pad = 0;
+    const long long off = pr.offsets[p];
+    const int len = (int)(pr.offsets[p + 1] - off);
+    cplx* out = pr.roots + (off - p);
+    int first, last;
+    trim_zeros(pr.coeffs + off, len, first, last);
+    if (first < 0) {
+        finish_poly(pr, p, out, 0, 0, 0, rec.st);
+    } else {
+        const double* ps = pr.coeffs + off + first;
+        const int ncoef = last - first + 1;
+        rec.K = first;
+        if (ncoef <= 3) {
+            const int cnt = solve_simple(ps, ncoef, out);
+            finish_poly(pr, p, out, cnt, rec.K, 0, rec.st);
+        } else {
+            const int N = ncoef - 1;
+            Fact<double, false> F = make_fact<double, false>(pr, p, N);
+            factor_companion(F, ps);
+            for (int i = 0; i < N; ++i) out[i] = cplx(0.0, 0.0);
+            rec.N = N;
+            rec.ls.ctr = {0, 1, N - 1, 15, -1};
+            rec.ls.it_max = 20ll * (N - 1);
+            rec.iterating = 1;
+        }
+    }
+    pr.rec[p] = rec;
+}
+
+// ---------------------------------------------------------------- phase A
+// MH: largest order of the dense trailing block this instantiation can hold (per-thread local memory)
+template <int MH>
+__global__ void __launch_bounds__(32) rounds_phase_a_kernel(Problem<double> pr, PipeParams pp, int L, unsigned* round_active) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= pr.nbatch) return;
+    if (!pr.rec[p].iterating) return;
+    PolyRec rec = pr.rec[p];
+    Fact<double, false> F = make_fact<double, false>(pr, p, rec.N);
+    // per-thread scratch: staged trailing block, its eigenvalues, the dense block, one step snapshot
+    Rot<double> sq[MH + 3], sb[MH + 3], scc[MH + 3];
+    cplx se[MH + 3];
+    double sH[MH * MH], sisg[MH + 2];
+    double2 sn[12];
+    GroupScratch sc;
+    sc.q = sq; sc.b = sb; sc.c = scc; sc.e = se; sc.H = sH; sc.isg = sisg;
+    cplx* out = pr.roots + (pr.offsets[p] - p);
+    const int* dstack = pr.dstack + (pr.offsets[p] + (long long)pr.extra * p);
+    int nb = 0;
+    SmallSink sink;
+    sink.list = pr.swlist; sink.count = pr.counters + CNT_SMALL; sink.poly = (int)p;
+    const int mode = phase_a(F, rec.ls, out - 1, sc, pr.shifts + p * L, L, pp, nb, pr.seed, (uint64_t)p, rec.st, dstack, sn, 1, sink);
+    rec.serial_turnovers += F.turnovers;
+    rec.mode = mode; rec.nb = nb;
+    if (mode == 0) rec.iterating = 0;
+    else atomicAdd(round_active, 1u);
+    pr.rec[p] = rec;
+}
+
+// ---------------------------------------------------------------- phase B
+#ifndef AMRVW_PIPE_MINBLOCKS
+#define AMRVW_PIPE_MINBLOCKS 6
+#endif
+template <int L, int WPB>
+__global__ void __launch_bounds__(32 * WPB, AMRVW_PIPE_MINBLOCKS) rounds_phase_b_kernel(Problem<double> pr) {
+    constexpr int G = 32 / L;
+    constexpr int NT = 32 * WPB;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int wib = threadIdx.x >> 5, lane32 = threadIdx.x & 31;
+    const int grp = lane32 / L, lane = lane32 % L;
+    const long long p = ((long long)blockIdx.x * WPB + wib) * G + grp;
+    const bool valid = p < pr.nbatch;
+    double2* const snap_t = reinterpret_cast<double2*>(smem_raw) + threadIdx.x;                            // [12][NT] step snapshots
+    double2* const stage = reinterpret_cast<double2*>(smem_raw) + 12 * NT + (wib * G + grp) * (3 * AMRVW_RING);   // look-ahead ring of lane 0
+
+    // the group's fat step (every lane reads the same record: broadcast loads)
+    int mode = 0, nb = 0, start = 1, stop = 0, ord0 = 0, sp = 0, N = 0;
+    if (valid) {
+        const PolyRec* r = pr.rec + p;
+        if (r->iterating) { mode = r->mode; nb = r->nb; start = r->ls.ctr.start_index; stop = r->ls.ctr.stop_index; ord0 = r->ls.ord; sp = r->ls.sp; N = r->N; }
+    }
+    const bool act = mode != 0;
+    if (!__any_sync(0xffffffffu, act)) return;
+    const int T = act ? (stop - start + 3 * L + 1) : 0;
+    const int Tmax = __reduce_max_sync(0xffffffffu, T);
+    const long long pc_t1 = clock64();
+    long long pc_lean = 0;
+    int pn_lean = 0, pn_calls = 0, nturn = 0;
+
+    Fact<double, false> F;
+    F.Q = F.B = F.Ct = F.WB = F.WCt = nullptr; F.DQ = F.DR = F.WD = nullptr; F.N = N; F.turnovers = 0;
+    int* dstack = nullptr;
+    if (act) {
+        F = make_fact<double, false>(pr, p, N);
+        dstack = pr.dstack + (pr.offsets[p] + (long long)pr.extra * p);
+    }
+    Rot<double>* const FQ = F.Q;
+    Rot<double>* const FB = F.B;
+    Rot<double>* const FC = F.Ct;
+    const unsigned stage_sa = (unsigned)__cvta_generic_to_shared(stage), snap_sa = (unsigned)__cvta_generic_to_shared(snap_t);
+
+    Rot<double> q0, q1, q2, b0, b1, b2, c0, c1, c2, U, V, W;
+    q0 = q1 = q2 = b0 = b1 = b2 = c0 = c1 = c2 = U = V = W = make_rot<double>(1.0, 0.0);
+    const bool has_bulge = act && lane < nb;
+    if (act && lane == 0) {
+        for (int a = 0; a < AMRVW_RING - 1; ++a) {
+            const int nidx = min(start + a, stop + 1);
+            cp_async16_sa(stage_sa + 48 * a, FQ + nidx); cp_async16_sa(stage_sa + 48 * a + 16, FB + nidx); cp_async16_sa(stage_sa + 48 * a + 32, FC + nidx);
+            cp_async_commit();
+        }
+    }
+    for (int t = 0; t < Tmax; ++t) {
+        {   // every lane of the warp at a regular position (or idle for good): the lean loop
+            const bool g_dead = !act || t >= T;
+            const bool g_main = act && nb == L && t >= 3 * L && t <= stop - start;
+            if (__all_sync(0xffffffffu, g_dead || g_main) && __any_sync(0xffffffffu, g_main)) {
+                const int te = __reduce_min_sync(0xffffffffu, g_main ? stop - start + 1 : 0x7fffffff);
+                const long long pc_l0 = clock64();
+                StepState z = {q0, q1, q2, b0, b1, b2, c0, c1, c2, U, V, W};
+                const int role = (g_main ? 1 : 0) | (lane == 0 ? 2 : 0) | (lane == L - 1 ? 4 : 0);
+                sp = lean_chase<L, NT>(z, FQ, FB, FC, stage_sa, snap_sa, dstack, sp, start, t, te, role);
+                q0 = z.q0; q1 = z.q1; q2 = z.q2; b0 = z.b0; b1 = z.b1; b2 = z.b2; c0 = z.c0; c1 = z.c1; c2 = z.c2; U = z.U; V = z.V; W = z.W;
+                if (g_main) nturn += 7 * (te - t);
+                pc_lean += clock64() - pc_l0; pn_lean += te - t; pn_calls += 1;
+                t = te - 1;
+                continue;
+            }
+        }
+        const int tp = t - 3 * lane;
+        // ingest: what the previous lane finished last step (lane 0: from memory)
+        Rot<double> iq = shfl_up_rot(q0, L), ib = shfl_up_rot(b0, L), ic = shfl_up_rot(c0, L);
+        if (lane == 0) {
+            cp_async_wait_ring();
+            const unsigned sg = stage_sa + (t & (AMRVW_RING - 1)) * 48;
+            iq = lds_rot(sg); ib = lds_rot(sg + 16); ic = lds_rot(sg + 32);
+            if (act) {
+                const int nidx = min(start + t + AMRVW_RING - 1, stop + 1);
+                const unsigned sn2 = stage_sa + ((t + AMRVW_RING - 1) & (AMRVW_RING - 1)) * 48;
+                cp_async16_sa(sn2, FQ + nidx); cp_async16_sa(sn2 + 16, FB + nidx); cp_async16_sa(sn2 + 32, FC + nidx);
+            }
+            cp_async_commit();
+        }
+        q0 = q1; q1 = q2; q2 = iq;
+        b0 = b1; b1 = b2; b2 = ib;
+        c0 = c1; c1 = c2; c2 = ic;
+        const int i = start + tp - 2;   // position of this lane's bulge; window = indices i..i+2
+        if (has_bulge && tp >= 2 && i <= stop - 1) {
+            if (tp == 2) {
+                StepState z = {q0, q1, q2, b0, b1, b2, c0, c1, c2, U, V, W};
+                create_and_absorb_at(z, F, start, stop, mode, pr.shifts + p * L, lane, pr.seed, (uint64_t)p, ord0 + lane);
+                q0 = z.q0; q1 = z.q1; U = z.U; V = z.V; W = z.W;
+                nturn += 1;
+            }
+            if (i <= stop - 2) {
+                // regular position: the 7 turnovers of one chase step (RDS.jl:42-70, 97-108) as ONE
+                // straight-line block; a degenerate turnover (flagged, essentially never) redoes the
+                // step on the general path from the shared-memory snapshot
+#ifndef AMRVW_STRICT
+                AMRVW_CHASE_REGULAR(snap_t, NT);
+#else
+                AMRVW_CHASE_GENERAL();
+#endif
+            } else {
+                StepState z = {q0, q1, q2, b0, b1, b2, c0, c1, c2, U, V, W};
+                chase_step_final_at(z, F, stop);
+                q0 = z.q0; q1 = z.q1; q2 = z.q2; b0 = z.b0; b1 = z.b1; b2 = z.b2; c0 = z.c0; c1 = z.c1; c2 = z.c2; U = z.U; V = z.V; W = z.W;
+            }
+            nturn += 7;
+        }
+        // retire: the last lane writes index i back
+        if (lane == L - 1 && act && i >= start && i <= stop + 1) {
+            stg_rot(FQ + i, q0); stg_rot(FB + i, b0); stg_rot(FC + i, c0);
+            if (i <= stop && fabs(q0.s) <= AMRVW_EPS) dstack[sp++] = i;   // deflatable: record for phase A
+        }
+    }
+    if (lane == 0) cp_async_wait_all();   // drain look-ahead requests past the end of the window
+    sp = __shfl_sync(0xffffffffu, sp, grp * L + L - 1);
+    for (int d = L / 2; d >= 1; d >>= 1) nturn += __shfl_down_sync(0xffffffffu, nturn, d, L);
+    if (act && lane == 0) {
+        PolyRec* r = pr.rec + p;
+        r->ls.sp = sp;
+        r->st.sweeps += nb;
+        r->chase_turnovers += nturn;
+        if (mode == 2) { r->st.exceptional += nb; r->ls.ord += nb; r->ls.ctr.it_count = 14; }
+    }
+    if (pr.prof && lane32 == 0) {
+        const long long pc_b = clock64() - pc_t1;
+        atomicAdd(pr.prof + 0, (unsigned long long)pc_b);
+        atomicAdd(pr.prof + 2, (unsigned long long)pc_lean);
+        atomicAdd(pr.prof + 3, (unsigned long long)(pc_b - pc_lean));
+        atomicAdd(pr.prof + 4, (unsigned long long)pn_lean);
+        atomicAdd(pr.prof + 5, (unsigned long long)(Tmax - pn_lean));
+        atomicAdd(pr.prof + 6, (unsigned long long)pn_calls);
+        atomicAdd(pr.prof + 7, 1ull);
+    }
+}
+
+// ---------------------------------------------------------------- small windows
+// SM: largest window (rotators) this instantiation stages in per-thread local memory
+template <int SM>
+__global__ void __launch_bounds__(64) rounds_small_kernel(Problem<double> pr, unsigned nwin) {
+    const unsigned w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nwin) return;
+    const SmallWin sw = reinterpret_cast<const SmallWin*>(pr.swlist)[w];
+    const long long p = sw.poly;
+    const PolyRec* r = pr.rec + p;
+    Fact<double, false> F = make_fact<double, false>(pr, p, r->N);
+    cplx* E = pr.roots + (pr.offsets[p] - p) - 1;
+    Rot<double> sq[SM + 3], sb[SM + 3], scc[SM + 3];
+    double2 sn[12];
+    GroupScratch sc;
+    sc.q = sq; sc.b = sb; sc.c = scc; sc.e = nullptr; sc.H = nullptr; sc.isg = nullptr;
+    Fact<double, false> W = stage_window(F, sc, sw.lo - 1, sw.hi);
+    Counter c2 = {sw.lo - 1, sw.lo, sw.hi, sw.it_count, -1};
+    PolyStats st = {0, 0, 0, 0, 0};
+    int ord = 1000000 + sw.lo;   // exceptional shifts of a deferred window: ordinal keyed by the window, not by time
+    const WindowStep wstep = {sn, 1};
+    const int left = drive_window(W, sw.lo, sw.hi, c2, E, 20ll * (r->N - 1), pr.seed, (uint64_t)p, ord, st, wstep);
+    PolyRec* rw = pr.rec + p;
+    atomicAdd((unsigned long long*)&rw->serial_turnovers, (unsigned long long)W.turnovers);
+    atomicAdd(&rw->st.sweeps, st.sweeps);
+    if (st.exceptional) atomicAdd(&rw->st.exceptional, st.exceptional);
+    if (left) atomicAdd(&rw->ls.unconv, left);
+}
+
+// ---------------------------------------------------------------- finish
+__global__ void __launch_bounds__(32) rounds_finish_kernel(Problem<double> pr) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= pr.nbatch) return;
+    PolyRec rec = pr.rec[p];
+    if (rec.N <= 0) return;   // closed forms were finished by the set-up kernel
+    cplx* out = pr.roots + (pr.offsets[p] - p);
+    sort_roots(out, rec.N);
+    rec.st.turnovers = rec.serial_turnovers + rec.chase_turnovers;
+    rec.st.unconverged = rec.ls.unconv + (rec.ls.ctr.stop_index >= 1 ? rec.ls.ctr.stop_index + 1 : 0);
+    finish_poly(pr, p, out, rec.N, rec.K, rec.st.unconverged, rec.st);
+}
+
+
+// ---------------------------------------------------------------- host side
+struct RoundsTimes { float setup_ms, a_ms, b_ms, small_ms, finish_ms; int rounds; unsigned small_windows; };
+
+template <int L>
+static cudaError_t launch_phase_b(const Problem<double>& pr, cudaStream_t st) {
+#ifndef AMRVW_PIPE_WPB
+#define AMRVW_PIPE_WPB 2
+#endif
+    constexpr int WPB = AMRVW_PIPE_WPB;
+    constexpr int G = 32 / L;
+    const size_t smem = (size_t)12 * 32 * WPB * sizeof(double2) + (size_t)WPB * G * 3 * AMRVW_RING * sizeof(double2);
+    const long long groups_per_block = (long long)WPB * G;
+    const int blocks = (int)((pr.nbatch + groups_per_block - 1) / groups_per_block);
+    rounds_phase_b_kernel<L, WPB><<<blocks, 32 * WPB, smem, st>>>(pr);
+    return cudaGetLastError();
+}
+
+// Chooses L (bulges in flight per polynomial) from the degree and the batch: enough lanes to fill the
+// GPU, not more than the windows can feed (a fat step needs a window > small >= 2L/reuse).
+static void choose_pipe_params(const amrvw_options& opt, long long nbatch, int max_len, int sm_count, int& L, PipeParams& pp) {
+    const int degree = max_len - 1;
+    L = opt.lanes_per_poly;
+    if (L == 0) {
+        if (degree < 48) L = 4;
+        else if (degree < 200) L = 8;
+        else if (degree < 1200 && nbatch * 16 > (long long)sm_count * 512) L = 8;
+        else L = 16;
+        if (degree >= 1200 && nbatch * 32 <= (long long)sm_count * 256) L = 32;
+    }
+    pp.reuse = opt.shift_reuse ? opt.shift_reuse : 2;
+    if (pp.reuse > L / 2) pp.reuse = L / 2 > 0 ? L / 2 : 1;
+    const int mshift = 2 * L / pp.reuse;
+    pp.small = opt.small_window ? opt.small_window : (mshift + 8 > 24 ? mshift + 8 : 24);
+    if (pp.small < mshift) pp.small = mshift;      // a fat step needs delta - 1 >= m
+    if (pp.small > 96) pp.small = 96;
+    pp.ms = (mshift > pp.small ? mshift : pp.small) + 4;
+    pp.dense = opt.shift_solver != AMRVW_SHIFTS_CHASE;
+    pp.mh = mshift;
+}
+
+// Runs the whole schedule on `st`.  h_counters: pinned host words for the round counters.  Blocks the
+// host once per chunk of rounds (the termination test needs the device's count of pending fat steps).
+static cudaError_t launch_rounds_rds(Problem<double> pr, const amrvw_options& opt, int max_len, int sm_count, cudaStream_t st, int* launches,
+                                     unsigned* h_counters, unsigned* d_round_active, int max_rounds, cudaEvent_t* ev, RoundsTimes* times) {
+    int L; PipeParams pp;
+    choose_pipe_params(opt, pr.nbatch, max_len, sm_count, L, pp);
+    cudaError_t e;
+    const int nb32 = (int)((pr.nbatch + 31) / 32), nb64 = (int)((pr.nbatch + 63) / 64);
+    if ((e = cudaMemsetAsync(pr.counters, 0, CNT_WORDS * sizeof(unsigned), st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(d_round_active, 0, (size_t)max_rounds * sizeof(unsigned), st)) != cudaSuccess) return e;
+    if (times) { *times = RoundsTimes{0, 0, 0, 0, 0, 0, 0}; cudaEventRecord(ev[0], st); }
+    rounds_setup_kernel<<<nb64, 64, 0, st>>>(pr);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    *launches += 1;
+    if (times) cudaEventRecord(ev[1], st);
+    // kernel attributes of phase B (dynamic shared memory is small; nothing to opt into)
+    const int chunk = 8;
+    int round = 0;
+    bool done = false;
+    float a_ms = 0.f, b_ms = 0.f;
+    while (!done && round < max_rounds) {
+        const int r0 = round;
+        for (int k = 0; k < chunk && round < max_rounds; ++k, ++round) {
+            if (times) cudaEventRecord(ev[2 + 3 * k], st);
+            if (pp.mh <= 16) rounds_phase_a_kernel<16><<<nb32, 32, 0, st>>>(pr, pp, L, d_round_active + round);
+            else if (pp.mh <= 32) rounds_phase_a_kernel<32><<<nb32, 32, 0, st>>>(pr, pp, L, d_round_active + round);
+            else rounds_phase_a_kernel<64><<<nb32, 32, 0, st>>>(pr, pp, L, d_round_active + round);
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            if (times) cudaEventRecord(ev[3 + 3 * k], st);
+            switch (L) {
+                case 4: e = launch_phase_b<4>(pr, st); break;
+                case 8: e = launch_phase_b<8>(pr, st); break;
+                case 16: e = launch_phase_b<16>(pr, st); break;
+                default: e = launch_phase_b<32>(pr, st); break;
+            }
+            if (e != cudaSuccess) return e;
+            if (times) cudaEventRecord(ev[4 + 3 * k], st);
+            *launches += 2;
+        }
+        if ((e = cudaMemcpyAsync(h_counters, d_round_active + (round - 1), sizeof(unsigned), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+        if (times) {
+            for (int k = 0; k < round - r0; ++k) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, ev[2 + 3 * k], ev[3 + 3 * k]); a_ms += ms;
+                cudaEventElapsedTime(&ms, ev[3 + 3 * k], ev[4 + 3 * k]); b_ms += ms;
+            }
+        }
+        if (h_counters[0] == 0) done = true;
+    }
+    // deferred small windows
+    if ((e = cudaMemcpyAsync(h_counters, pr.counters + CNT_SMALL, sizeof(unsigned), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+    const unsigned nwin = h_counters[0];
+    if (times) cudaEventRecord(ev[2], st);
+    if (nwin > 0) {
+        const int blocks = (int)((nwin + 63) / 64);
+        if (pp.small <= 32) rounds_small_kernel<32><<<blocks, 64, 0, st>>>(pr, nwin);
+        else rounds_small_kernel<96><<<blocks, 64, 0, st>>>(pr, nwin);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        *launches += 1;
+    }
+    if (times) cudaEventRecord(ev[3], st);
+    rounds_finish_kernel<<<nb32, 32, 0, st>>>(pr);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    *launches += 1;
+    if (times) {
+        cudaEventRecord(ev[4], st);
+        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+        cudaEventElapsedTime(&times->setup_ms, ev[0], ev[1]);
+        cudaEventElapsedTime(&times->small_ms, ev[2], ev[3]);
+        cudaEventElapsedTime(&times->finish_ms, ev[3], ev[4]);
+        times->a_ms = a_ms; times->b_ms = b_ms; times->rounds = round; times->small_windows = nwin;
+    }
+    return cudaSuccess;
+}
+
+}  // namespace amrvw

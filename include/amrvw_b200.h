@@ -138,10 +138,11 @@ int amrvw_measure_fp64_peak(amrvw_ctx* ctx, double* tflops);
  * R1R2R3| over n random turnovers, max deviation from unit norm, turnovers sent to the IEEE path}. */
 int amrvw_selftest(amrvw_ctx* ctx, int64_t n, double* out4);
 
-/* Warp-cycle accounting of the last pipelined RDS call that asked for stats (development aid, no
- * reference counterpart).  out16 = {sum over warps of: lifetime cycles, phase A (driver, shift
- * sub-solves), lean systolic loop, general systolic loop; lean steps, general steps, lean calls,
- * warps, set-up cycles, epilogue cycles; max lifetime over warps; 0...}. */
+/* Accounting of the last pipelined RDS call that asked for stats (development aid, no reference
+ * counterpart).  out16 = {[0] sum over phase-B warps of their cycles, [2] of which in the lean
+ * systolic loop, [3] in the fill/drain loop; [4] lean steps, [5] fill/drain steps, [6] lean calls,
+ * [7] phase-B warp launches; kernel times in microseconds: [8] set-up, [9] phase A (all rounds),
+ * [10] phase B (all rounds), [11] small windows, [12] finish; [13] rounds, [14] small windows}. */
 int amrvw_last_profile(amrvw_ctx* ctx, int64_t* out16);
 
 int amrvw_version(void);

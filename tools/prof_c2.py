@@ -19,13 +19,9 @@ for rep in range(2):
     out = ctx.roots_csr(coeffs, offsets, want_stats=True)
 st = ctx.last_stats
 pf = ctx.last_profile()
-w = max(pf["warps"], 1)
-tot = pf["cycles_total"]
-print(json.dumps({"B": B, "n": n, "opts": kw, "device_ms": st["device_ms"], "turnovers": st["turnovers"], "fat_steps": st["fat_steps"], "sweeps": st["sweeps"]}))
-print("  warps %d  mean lifetime %.1f Mcyc  max %.1f Mcyc" % (w, tot / w / 1e6, pf["cycles_max_warp"] / 1e6))
-for k in ("cycles_setup", "cycles_phase_a", "cycles_lean", "cycles_general", "cycles_epilogue"):
-    print("  %-16s %5.1f%%" % (k, 100.0 * pf[k] / tot))
-print("  lean steps %d (%.0f cyc/step)  general steps %d (%.0f cyc/step)  lean calls %d" % (
-    pf["steps_lean"], pf["cycles_lean"] / max(pf["steps_lean"], 1), pf["steps_general"], pf["cycles_general"] / max(pf["steps_general"], 1), pf["lean_calls"]))
-print("  per polynomial: shift sub-solves %.1f Mcyc, small windows %.1f Mcyc (%d windows); warp lifetime %.1f Mcyc" % (
-    pf["leader_cycles_subsolve"] / B / 1e6, pf["leader_cycles_small"] / B / 1e6, pf["small_windows"] // B, tot / w / 1e6))
+print(json.dumps({"B": B, "n": n, "opts": kw, "device_ms": st["device_ms"], "turnovers": st["turnovers"], "fat_steps": st["fat_steps"], "sweeps": st["sweeps"], "launches": st["launches"]}))
+print("  kernel ms: set-up %.2f  phase A %.2f  phase B %.2f  small windows %.2f  finish %.2f   rounds %d  small windows %d" % (
+    pf["us_setup"] / 1e3, pf["us_phase_a"] / 1e3, pf["us_phase_b"] / 1e3, pf["us_small"] / 1e3, pf["us_finish"] / 1e3, pf["rounds"], pf["small_windows"]))
+print("  phase B: lean steps %d (%.0f cyc/step)  general steps %d (%.0f cyc/step)  lean calls %d; lean share of warp cycles %.1f%%" % (
+    pf["steps_lean"], pf["cycles_lean"] / max(pf["steps_lean"], 1), pf["steps_general"], pf["cycles_general"] / max(pf["steps_general"], 1), pf["lean_calls"],
+    100.0 * pf["cycles_lean"] / max(pf["cycles_phase_b"], 1)))
