@@ -311,8 +311,48 @@ AMRVW_DI void pop_window(LeaderState& ls) {
 }
 
 // Phase A: the driver (AMRVW_algorithm.jl:10-138) up to the next fat step.  Returns 0 when the
-// polynomial is finished, 1 for a fat step with shifts in shl[0..nb), 2 for a fat step of nb
-// exceptional (random) bulges.
+// polynomial is finished, 3 for a fat step whose shifts are still to be computed (nb = m, the order of
+// the trailing block minus one), 2 for a fat step of nb exceptional (random) bulges.
+// pair the m+1 shifts e[0..m] for the real double shift: conjugate pairs first (slot order), then the
+// reals two by two; each pair drives `reuse` bulges.  Returns the number of bulges.
+AMRVW_DI int pair_shifts(const cplx* e, const int m, Shifts* shl, const int L, const int reuse) {
+    int np = 0;
+    for (int t = 0; t <= m; ++t) {
+        const cplx z = e[t];
+        if (z.im != 0.0) {
+            if (t + 1 <= m && e[t + 1].im == -z.im && e[t + 1].re == z.re) { shl[np].e1 = z; shl[np].e2 = e[t + 1]; ++np; ++t; }
+            else { shl[np].e1 = z; shl[np].e2 = conj_(z); ++np; }
+        }
+    }
+    bool have = false;
+    cplx pend;
+    for (int t = 0; t <= m; ++t) {
+        const cplx z = e[t];
+        if (z.im == 0.0) {
+            if (have) { shl[np].e1 = pend; shl[np].e2 = z; ++np; have = false; }
+            else { pend = z; have = true; }
+        }
+    }
+    if (have) { shl[np].e1 = pend; shl[np].e2 = pend; ++np; }
+    if (np * reuse > L) np = L / reuse;
+    for (int rep = 1; rep < reuse; ++rep)
+        for (int b = 0; b < np; ++b) shl[rep * np + b] = shl[b];
+    return np * reuse;
+}
+
+// shifts by the core-chasing iteration on the staged copy W of the trailing block (window
+// [k0+1, stop], Q[k0] already diagonal): the fall-back of the dense solver, and AMRVW_SHIFTS_CHASE
+AMRVW_NI long long chase_shifts(Fact<double, false>& W, const int k0, const int stop, cplx* e, const uint64_t seed, const uint64_t poly, int& ord, double2* sn, const int NT) {
+    const WindowStep wstep = {sn, NT};
+    const int m = stop - k0;
+    cplx* Es = e - (k0 + 1);
+    for (int t = 0; t <= m; ++t) e[t] = cplx(0.0, 0.0);
+    Counter c2 = {k0, k0 + 1, stop, 15, -1};
+    PolyStats sub = {0, 0, 0, 0, 0};
+    drive_window(W, k0 + 1, stop, c2, Es, 20ll * m, seed, poly, ord, sub, wstep);
+    return W.turnovers;
+}
+
 // Decoupled small windows are not solved on the spot: they are queued for the small-window kernel
 // (rounds.cuh), one thread each.
 struct SmallWinRec { int poly, lo, hi, it_count; };
@@ -327,7 +367,7 @@ struct SmallSink {
 
 AMRVW_DI int phase_a(Fact<double, false>& F, LeaderState& ls, cplx* E, const GroupScratch& sc, Shifts* shl, const int L, const PipeParams pp,
                      int& nb, const uint64_t seed, const uint64_t poly, PolyStats& st, const int* dstack, double2* sn, const int NT, const SmallSink& sink) {
-    const WindowStep wstep = {sn, NT};
+    (void)sc; (void)shl; (void)seed; (void)poly; (void)sn; (void)NT;
     Counter& ctr = ls.ctr;
     double A[4];
     while (ls.kk <= ls.it_max) {
@@ -370,52 +410,14 @@ AMRVW_DI int phase_a(Fact<double, false>& F, LeaderState& ls, cplx* E, const Gro
             nb = L;
             return 2;
         } else {
-            // shifts: eigenvalues of the trailing (m+1) x (m+1) block = the window [k0+1, stop] of a copy
-            // whose rotator k0 is made diagonal
-            const long long pc0 = clock64();
+            // fat step with 2L/reuse shifts = eigenvalues of the trailing (m+1) x (m+1) block: computed by
+            // the shift kernel (rounds.cuh), one warp per polynomial
             int m = min(2 * L / pp.reuse - 1, delta - 1);
             if (m % 2 == 0) m -= 1;
-            const int stop = ctr.stop_index, k0 = stop - m;
-            Fact<double, false> W = stage_window(F, sc, k0, stop);
-            {
-                const double sg = sign_(W.Q[k0].c);
-                W.Q[k0] = make_rot<double>(sg == 0.0 ? 1.0 : sg, 0.0);
-            }
-            if (!(pp.dense && dense_shifts(W.Q, W.B, W.Ct, k0, stop, sc.H, sc.isg, sc.e))) {
-                cplx* Es = sc.e - (k0 + 1);
-                for (int t = 0; t <= m; ++t) sc.e[t] = cplx(0.0, 0.0);
-                Counter c2 = {k0, k0 + 1, stop, 15, -1};
-                PolyStats sub = {0, 0, 0, 0, 0};
-                drive_window(W, k0 + 1, stop, c2, Es, 20ll * m, seed, poly, ls.ord, sub, wstep);
-                F.turnovers += W.turnovers;
-            }
-            // pair the m+1 shifts: conjugate pairs first (slot order), then the reals two by two
-            int np = 0;
-            for (int t = 0; t <= m; ++t) {
-                const cplx z = sc.e[t];
-                if (z.im != 0.0) {
-                    if (t + 1 <= m && sc.e[t + 1].im == -z.im && sc.e[t + 1].re == z.re) { shl[np].e1 = z; shl[np].e2 = sc.e[t + 1]; ++np; ++t; }
-                    else { shl[np].e1 = z; shl[np].e2 = conj_(z); ++np; }
-                }
-            }
-            bool have = false;
-            cplx pend;
-            for (int t = 0; t <= m; ++t) {
-                const cplx z = sc.e[t];
-                if (z.im == 0.0) {
-                    if (have) { shl[np].e1 = pend; shl[np].e2 = z; ++np; have = false; }
-                    else { pend = z; have = true; }
-                }
-            }
-            if (have) { shl[np].e1 = pend; shl[np].e2 = pend; ++np; }
-            if (np * pp.reuse > L) np = L / pp.reuse;
-            for (int rep = 1; rep < pp.reuse; ++rep)
-                for (int b = 0; b < np; ++b) shl[rep * np + b] = shl[b];
-            nb = np * pp.reuse;
+            nb = m;            // handed to the shift kernel through the record
             st.fat_steps++;
             ctr.it_count -= 1;
-            ls.pc_sub += clock64() - pc0;
-            return 1;
+            return 3;
         }
     }
     return 0;

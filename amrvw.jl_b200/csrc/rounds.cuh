@@ -85,33 +85,87 @@ __global__ void __launch_bounds__(64) rounds_setup_kernel(Problem<double> pr) {
     pr.rec[p] = rec;
 }
 
-// ---------------------------------------------------------------- phase A
-// MH: largest order of the dense trailing block this instantiation can hold (per-thread local memory)
-template <int MH>
+// ---------------------------------------------------------------- phase A, part 1: the driver
+// One thread per polynomial: deflation bookkeeping, 1x1 / 2x2 extraction, queueing of small windows,
+// up to the next fat step.  mode 3 = the fat step still needs its shifts (part 2).
 __global__ void __launch_bounds__(32) rounds_phase_a_kernel(Problem<double> pr, PipeParams pp, int L, unsigned* round_active) {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= pr.nbatch) return;
     if (!pr.rec[p].iterating) return;
     PolyRec rec = pr.rec[p];
     Fact<double, false> F = make_fact<double, false>(pr, p, rec.N);
-    // per-thread scratch: staged trailing block, its eigenvalues, the dense block, one step snapshot
-    Rot<double> sq[MH + 3], sb[MH + 3], scc[MH + 3];
-    cplx se[MH + 3];
-    double sH[MH * MH], sisg[MH + 2];
-    double2 sn[12];
     GroupScratch sc;
-    sc.q = sq; sc.b = sb; sc.c = scc; sc.e = se; sc.H = sH; sc.isg = sisg;
+    sc.q = sc.b = sc.c = nullptr; sc.e = nullptr; sc.H = nullptr; sc.isg = nullptr;
     cplx* out = pr.roots + (pr.offsets[p] - p);
     const int* dstack = pr.dstack + (pr.offsets[p] + (long long)pr.extra * p);
     int nb = 0;
     SmallSink sink;
     sink.list = pr.swlist; sink.count = pr.counters + CNT_SMALL; sink.poly = (int)p;
-    const int mode = phase_a(F, rec.ls, out - 1, sc, pr.shifts + p * L, L, pp, nb, pr.seed, (uint64_t)p, rec.st, dstack, sn, 1, sink);
+    const int mode = phase_a(F, rec.ls, out - 1, sc, nullptr, L, pp, nb, pr.seed, (uint64_t)p, rec.st, dstack, nullptr, 1, sink);
     rec.serial_turnovers += F.turnovers;
     rec.mode = mode; rec.nb = nb;
     if (mode == 0) rec.iterating = 0;
     else atomicAdd(round_active, 1u);
     pr.rec[p] = rec;
+}
+
+// ---------------------------------------------------------------- phase A, part 2: the shifts
+// One warp per polynomial with a pending fat step (mode 3): stage the trailing block's rotators,
+// write the block out densely, Hessenberg QR with the lanes sharing rows and columns (shifts.cuh),
+// pair the shifts.  MH: largest order of the trailing block this instantiation holds in shared
+// memory; WPC warps per CTA.
+template <int MH, int WPC>
+__global__ void __launch_bounds__(32 * WPC) rounds_shift_kernel(Problem<double> pr, PipeParams pp, int L) {
+    constexpr int LDH = MH + 1;
+    struct __align__(16) WarpScratch {
+        Rot<double> q[MH + 3], b[MH + 3], c[MH + 3];
+        cplx e[MH + 3];
+        double H[MH * LDH];
+        double isg[MH + 2];
+        double2 sn[12];
+    };
+    __shared__ WarpScratch scratch[WPC];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long p = (long long)blockIdx.x * WPC + wib;
+    if (p >= pr.nbatch) return;
+    PolyRec* rec = pr.rec + p;
+    if (!rec->iterating || rec->mode != 3) return;
+    WarpScratch& ws = scratch[wib];
+    const int m = rec->nb, stop = rec->ls.ctr.stop_index, k0 = stop - m, M = m + 1;
+    Fact<double, false> F = make_fact<double, false>(pr, p, rec->N);
+    // staged copy with global indices: slot t <-> index k0 + t
+    for (int t = lane; t <= m + 1; t += 32) {
+        ws.q[t] = ldg_rot(F.Q + k0 + t); ws.b[t] = ldg_rot(F.B + k0 + t); ws.c[t] = ldg_rot(F.Ct + k0 + t);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        const double sg = sign_(ws.q[0].c);
+        ws.q[0] = make_rot<double>(sg == 0.0 ? 1.0 : sg, 0.0);
+    }
+    __syncwarp();
+    const Rot<double>* q = ws.q - k0;
+    const Rot<double>* b = ws.b - k0;
+    const Rot<double>* c = ws.c - k0;
+    bool ok = false;
+    if (pp.dense) {
+        dense_trailing_block_warp(q, b, c, k0, stop, ws.H, LDH, ws.isg, M, lane);
+        ok = hqr_eigenvalues_warp(ws.H, LDH, M, ws.e, lane);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        long long turnovers = 0;
+        int ord = rec->ls.ord;
+        if (!ok) {   // core-chasing iteration on the staged copy (also AMRVW_SHIFTS_CHASE)
+            Fact<double, false> W = F;
+            W.Q = ws.q - k0; W.B = ws.b - k0; W.Ct = ws.c - k0; W.turnovers = 0;
+            turnovers = chase_shifts(W, k0, stop, ws.e, pr.seed, (uint64_t)p, ord, ws.sn, 1);
+        }
+        const int nb = pair_shifts(ws.e, m, pr.shifts + p * L, L, pp.reuse);
+        rec->ls.ord = ord;
+        rec->serial_turnovers += turnovers;
+        rec->nb = nb;
+        rec->mode = 1;
+    }
 }
 
 // ---------------------------------------------------------------- phase B
@@ -358,9 +412,11 @@ static cudaError_t launch_rounds_rds(Problem<double> pr, const amrvw_options& op
         const int r0 = round;
         for (int k = 0; k < chunk && round < max_rounds; ++k, ++round) {
             if (times) cudaEventRecord(ev[2 + 3 * k], st);
-            if (pp.mh <= 16) rounds_phase_a_kernel<16><<<nb32, 32, 0, st>>>(pr, pp, L, d_round_active + round);
-            else if (pp.mh <= 32) rounds_phase_a_kernel<32><<<nb32, 32, 0, st>>>(pr, pp, L, d_round_active + round);
-            else rounds_phase_a_kernel<64><<<nb32, 32, 0, st>>>(pr, pp, L, d_round_active + round);
+            rounds_phase_a_kernel<<<nb32, 32, 0, st>>>(pr, pp, L, d_round_active + round);
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            if (pp.mh <= 16) rounds_shift_kernel<16, 4><<<(int)((pr.nbatch + 3) / 4), 128, 0, st>>>(pr, pp, L);
+            else if (pp.mh <= 32) rounds_shift_kernel<32, 2><<<(int)((pr.nbatch + 1) / 2), 64, 0, st>>>(pr, pp, L);
+            else rounds_shift_kernel<64, 1><<<(int)pr.nbatch, 32, 0, st>>>(pr, pp, L);
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
             if (times) cudaEventRecord(ev[3 + 3 * k], st);
             switch (L) {
@@ -371,7 +427,7 @@ static cudaError_t launch_rounds_rds(Problem<double> pr, const amrvw_options& op
             }
             if (e != cudaSuccess) return e;
             if (times) cudaEventRecord(ev[4 + 3 * k], st);
-            *launches += 2;
+            *launches += 3;
         }
         if ((e = cudaMemcpyAsync(h_counters, d_round_active + (round - 1), sizeof(unsigned), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
         if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;

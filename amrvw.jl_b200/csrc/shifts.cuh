@@ -185,6 +185,166 @@ AMRVW_DI bool hqr_eigenvalues(double* H, int M, cplx* E) {
     return true;
 }
 
+// ---------------------------------------------------------------- one warp per block (rounds schedule)
+// The same two routines with the lanes of a warp sharing the work: every lane executes the scalar
+// control flow on the same shared-memory values (no divergence, no communication), the entries are
+// written / the rows and columns are updated one per lane.  Each entry sees exactly the arithmetic of
+// the sequential routine above, so the strict build stays bit-identical to the oracle.
+// H has leading dimension LD >= M (LD = M + 1 keeps column accesses off a single bank).
+AMRVW_DI void dense_trailing_block_warp(const Rot<double>* q, const Rot<double>* b, const Rot<double>* c, int k0, int stop, double* H, int LD, double* isg, int M, int lane) {
+    const int j0 = k0 + 1;
+    for (int i = lane; i < M * LD; i += 32) H[i] = 0.0;
+    for (int j = j0 + lane; j <= stop + 1; j += 32) isg[j - j0] = rcp_(c[j].s);
+    __syncwarp();
+    for (int k = j0 + lane; k <= stop + 1; k += 32) {
+        double P = 1.0, T = 0.0, Vacc = 0.0;
+        const double ck = b[k].c, sk = b[k].s;
+        for (int j = k; j >= j0; --j) {
+            const double w = (j == k) ? -sk : (b[j].c * P) * ck;
+            const double ctc = c[j].c;
+            const double ig = isg[j - j0];
+            const double R = (w + ctc * T) * ig;
+            const Rot<double> qj = q[j];
+            if (j + 1 <= stop + 1) H[(j + 1 - j0) * LD + (k - j0)] = qj.c * Vacc - qj.s * R;
+            Vacc = qj.c * R + qj.s * Vacc;
+            T = (-(ctc * w) - T) * ig;
+            if (j < k) P = P * b[j].s;
+        }
+        H[k - j0] = q[k0].c * Vacc;
+    }
+    __syncwarp();
+}
+
+AMRVW_DI bool hqr_eigenvalues_warp(double* H, const int LD, const int M, cplx* E, const int lane) {
+#define AMRVW_H(i, j) H[(i) * LD + (j)]
+    double norm = 0.0;
+    if (lane == 0) {   // sequential sum: the value must not depend on the number of lanes
+        for (int i = 0; i < M; ++i)
+            for (int j = (i > 0 ? i - 1 : 0); j < M; ++j) norm += fabs(AMRVW_H(i, j));
+    }
+    norm = __shfl_sync(0xffffffffu, norm, 0);
+    int en = M - 1, itn = 30 * M;
+    double t = 0.0;
+    while (en >= 0) {
+        int its = 0;
+        const int na = en - 1, enm2 = na - 1;
+        for (;;) {
+            __syncwarp();
+            // highest l in 1..en with a negligible subdiagonal entry, 0 if none
+            int l = 0;
+            for (int base = (en / 32) * 32; base >= 0 && l == 0; base -= 32) {
+                const int lc = base + lane;
+                bool small = false;
+                if (lc >= 1 && lc <= en) {
+                    double s = fabs(AMRVW_H(lc - 1, lc - 1)) + fabs(AMRVW_H(lc, lc));
+                    if (s == 0.0) s = norm;
+                    const double tst2 = s + fabs(AMRVW_H(lc, lc - 1));
+                    small = (tst2 == s);
+                }
+                const unsigned mask = __ballot_sync(0xffffffffu, small);
+                if (mask) l = base + 31 - __clz(mask);
+            }
+            double x = AMRVW_H(en, en);
+            if (l == en) { if (lane == 0) E[en] = cplx(x + t, 0.0); en = na; break; }
+            double y = AMRVW_H(na, na);
+            double w = AMRVW_H(en, na) * AMRVW_H(na, en);
+            if (l == na) {
+                const double p = (y - x) * 0.5;
+                const double q = p * p + w;
+                double zz = sqrt_(fabs(q));
+                x = x + t;
+                if (lane == 0) {
+                    if (q >= 0.0) {
+                        zz = p + (p >= 0.0 ? zz : -zz);
+                        E[na] = cplx(x + zz, 0.0);
+                        E[en] = E[na];
+                        if (zz != 0.0) E[en] = cplx(x - w * rcp_(zz), 0.0);
+                    } else {
+                        E[na] = cplx(x + p, zz);
+                        E[en] = cplx(x + p, -zz);
+                    }
+                }
+                en = enm2;
+                break;
+            }
+            if (itn == 0) return false;
+            if (its == 10 || its == 20) {
+                t += x;
+                __syncwarp();
+                for (int i = lane; i <= en; i += 32) AMRVW_H(i, i) -= x;
+                __syncwarp();
+                const double s = fabs(AMRVW_H(en, na)) + fabs(AMRVW_H(na, enm2));
+                x = 0.75 * s; y = x; w = -0.4375 * s * s;
+            }
+            ++its; --itn;
+            double p, q, r;
+            {
+                const double zz = AMRVW_H(l, l);
+                const double r0 = x - zz, s0 = y - zz;
+                p = (r0 * s0 - w) * rcp_(AMRVW_H(l + 1, l)) + AMRVW_H(l, l + 1);
+                q = AMRVW_H(l + 1, l + 1) - zz - r0 - s0;
+                r = AMRVW_H(l + 2, l + 1);
+                const double is = rcp_(fabs(p) + fabs(q) + fabs(r));
+                p = p * is; q = q * is; r = r * is;
+            }
+            __syncwarp();
+            for (int i = l + 2 + lane; i <= en; i += 32) { AMRVW_H(i, i - 2) = 0.0; if (i != l + 2) AMRVW_H(i, i - 3) = 0.0; }
+            for (int k = l; k <= na; ++k) {
+                __syncwarp();
+                const bool notlas = (k != na);
+                double xs = 0.0;
+                if (k != l) {
+                    p = AMRVW_H(k, k - 1); q = AMRVW_H(k + 1, k - 1); r = notlas ? AMRVW_H(k + 2, k - 1) : 0.0;
+                    xs = fabs(p) + fabs(q) + fabs(r);
+                    if (xs == 0.0) continue;
+                    const double ix = rcp_(xs);
+                    p = p * ix; q = q * ix; r = r * ix;
+                }
+                double s = sqrt_(p * p + q * q + r * r);
+                if (p < 0.0) s = -s;
+                __syncwarp();   // every lane has read column k-1 before it is overwritten
+                if (k != l && lane == 0) AMRVW_H(k, k - 1) = -s * xs;
+                p = p + s;
+                const double is = rcp_(s), ip = rcp_(p);
+                const double hx = p * is, hy = q * is, hz = r * is;
+                q = q * ip; r = r * ip;
+                const int ihi = min(en, k + 3);
+                if (notlas) {
+                    for (int j = k + lane; j <= en; j += 32) {
+                        const double a0 = AMRVW_H(k, j), a1 = AMRVW_H(k + 1, j), a2 = AMRVW_H(k + 2, j);
+                        const double pp = a0 + q * a1 + r * a2;
+                        AMRVW_H(k, j) = a0 - pp * hx; AMRVW_H(k + 1, j) = a1 - pp * hy; AMRVW_H(k + 2, j) = a2 - pp * hz;
+                    }
+                    __syncwarp();
+                    for (int i = l + lane; i <= ihi; i += 32) {
+                        const double a0 = AMRVW_H(i, k), a1 = AMRVW_H(i, k + 1), a2 = AMRVW_H(i, k + 2);
+                        const double pp = hx * a0 + hy * a1 + hz * a2;
+                        AMRVW_H(i, k) = a0 - pp; AMRVW_H(i, k + 1) = a1 - pp * q; AMRVW_H(i, k + 2) = a2 - pp * r;
+                    }
+                } else {
+                    for (int j = k + lane; j <= en; j += 32) {
+                        const double a0 = AMRVW_H(k, j), a1 = AMRVW_H(k + 1, j);
+                        const double pp = a0 + q * a1;
+                        AMRVW_H(k, j) = a0 - pp * hx; AMRVW_H(k + 1, j) = a1 - pp * hy;
+                    }
+                    __syncwarp();
+                    for (int i = l + lane; i <= ihi; i += 32) {
+                        const double a0 = AMRVW_H(i, k), a1 = AMRVW_H(i, k + 1);
+                        const double pp = hx * a0 + hy * a1;
+                        AMRVW_H(i, k) = a0 - pp; AMRVW_H(i, k + 1) = a1 - pp * q;
+                    }
+                }
+            }
+        }
+    }
+#undef AMRVW_H
+    __syncwarp();
+    bool ok = true;
+    for (int i = lane; i < M; i += 32)
+        if (!(isfinite(E[i].re) && isfinite(E[i].im))) ok = false;
+    return __all_sync(0xffffffffu, ok);
+}
+
 // one out-of-line copy: formation + hqr
 AMRVW_NI bool dense_shifts(const Rot<double>* q, const Rot<double>* b, const Rot<double>* c, int k0, int stop, double* H, double* isg, cplx* E) {
     const int M = stop - k0 + 1;
