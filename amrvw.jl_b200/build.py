@@ -10,7 +10,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "capi.cu")
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("capi.cu", "kernels.cuh", "solver.cuh", "rotators.cuh", "pipeline.cuh", "shifts.cuh")] + [
+DEPS = [os.path.join(HERE, "csrc", f) for f in sorted(os.listdir(os.path.join(HERE, "csrc"))) if f.endswith((".cu", ".cuh"))] + [
     os.path.join(HERE, "..", "include", "amrvw_b200.h")
 ]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

@@ -26,6 +26,8 @@
 //     kernel already paid to its slowest warp.
 #pragma once
 #include "pipeline.cuh"
+#include <cstdio>
+#include <cstdlib>
 
 namespace amrvw {
 
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(32 * WPC) rounds_shift_kernel(Problem<double> 
 
 // ---------------------------------------------------------------- phase B
 #ifndef AMRVW_PIPE_MINBLOCKS
-#define AMRVW_PIPE_MINBLOCKS 6
+#define AMRVW_PIPE_MINBLOCKS 12
 #endif
 template <int L, int WPB>
 __global__ void __launch_bounds__(32 * WPB, AMRVW_PIPE_MINBLOCKS) rounds_phase_b_kernel(Problem<double> pr) {
@@ -335,18 +337,53 @@ __global__ void __launch_bounds__(64) rounds_small_kernel(Problem<double> pr, un
 }
 
 // ---------------------------------------------------------------- finish
-__global__ void __launch_bounds__(32) rounds_finish_kernel(Problem<double> pr) {
-    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= pr.nbatch) return;
-    PolyRec rec = pr.rec[p];
-    if (rec.N <= 0) return;   // closed forms were finished by the set-up kernel
+// One CTA per polynomial: sort (LinearAlgebra.sorteig!, AMRVW_algorithm.jl:134: by (real, imag) in
+// isless order), zero roots, statistics.  The sort is a bitonic network in its all-ascending form
+// (first step of every merge pairs i with i ^ (2^(k+1) - 1), the others i with i ^ 2^j; every
+// comparator puts the smaller element at the lower index), so slots >= n act as +infinity without
+// being stored; it runs in shared memory when the polynomial fits, otherwise in place in global
+// memory.  eig_less is a total order, so the result is the one the serial heap sort gives.
+#define AMRVW_SORT_SMEM 4096
+__global__ void __launch_bounds__(256) rounds_finish_kernel(Problem<double> pr, int smem_elems) {
+    extern __shared__ __align__(16) unsigned char sort_smem[];
+    cplx* tile = reinterpret_cast<cplx*>(sort_smem);
+    const long long p = blockIdx.x;
+    const PolyRec* recp = pr.rec + p;
+    const int n = recp->N;
+    if (n <= 0) return;   // closed forms were finished by the set-up kernel
     cplx* out = pr.roots + (pr.offsets[p] - p);
-    sort_roots(out, rec.N);
-    rec.st.turnovers = rec.serial_turnovers + rec.chase_turnovers;
-    rec.st.unconverged = rec.ls.unconv + (rec.ls.ctr.stop_index >= 1 ? rec.ls.ctr.stop_index + 1 : 0);
-    finish_poly(pr, p, out, rec.N, rec.K, rec.st.unconverged, rec.st);
+    cplx* a = out;
+    const bool in_smem = n <= smem_elems;
+    if (in_smem) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) tile[i] = out[i];
+        a = tile;
+    }
+    __syncthreads();
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    for (int k = 2; k <= np2; k <<= 1) {
+        for (int j = k >> 1; j >= 1; j >>= 1) {
+            const bool first = (j == (k >> 1));
+            for (int t = threadIdx.x; t < (np2 >> 1); t += blockDim.x) {
+                // t-th comparator of this step: lower index i has bit j clear
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = first ? (i ^ (k - 1)) : (i | j);
+                if (l < n && i < n) {
+                    const cplx x = a[i], y = a[l];
+                    if (eig_less(y, x)) { a[i] = y; a[l] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (in_smem) for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = tile[i];
+    if (threadIdx.x == 0) {
+        PolyRec rec = *recp;
+        rec.st.turnovers = rec.serial_turnovers + rec.chase_turnovers;
+        rec.st.unconverged = rec.ls.unconv + (rec.ls.ctr.stop_index >= 1 ? rec.ls.ctr.stop_index + 1 : 0);
+        finish_poly(pr, p, out, rec.N, rec.K, rec.st.unconverged, rec.st);
+    }
 }
-
 
 // ---------------------------------------------------------------- host side
 struct RoundsTimes { float setup_ms, a_ms, b_ms, small_ms, finish_ms; int rounds; unsigned small_windows; };
@@ -354,7 +391,7 @@ struct RoundsTimes { float setup_ms, a_ms, b_ms, small_ms, finish_ms; int rounds
 template <int L>
 static cudaError_t launch_phase_b(const Problem<double>& pr, cudaStream_t st) {
 #ifndef AMRVW_PIPE_WPB
-#define AMRVW_PIPE_WPB 2
+#define AMRVW_PIPE_WPB 1
 #endif
     constexpr int WPB = AMRVW_PIPE_WPB;
     constexpr int G = 32 / L;
@@ -432,10 +469,14 @@ static cudaError_t launch_rounds_rds(Problem<double> pr, const amrvw_options& op
         if ((e = cudaMemcpyAsync(h_counters, d_round_active + (round - 1), sizeof(unsigned), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
         if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
         if (times) {
+            static const bool trace = std::getenv("AMRVW_TRACE_ROUNDS") != nullptr;   // development: per-round kernel times on stderr
+            unsigned act[16] = {0};
+            if (trace) cudaMemcpy(act, d_round_active + r0, (size_t)(round - r0) * sizeof(unsigned), cudaMemcpyDeviceToHost);
             for (int k = 0; k < round - r0; ++k) {
-                float ms = 0.f;
+                float ms = 0.f, ms2 = 0.f;
                 cudaEventElapsedTime(&ms, ev[2 + 3 * k], ev[3 + 3 * k]); a_ms += ms;
-                cudaEventElapsedTime(&ms, ev[3 + 3 * k], ev[4 + 3 * k]); b_ms += ms;
+                cudaEventElapsedTime(&ms2, ev[3 + 3 * k], ev[4 + 3 * k]); b_ms += ms2;
+                if (trace) std::fprintf(stderr, "round %d active %u a_ms %.4f b_ms %.4f\n", r0 + k, act[k], ms, ms2);
             }
         }
         if (h_counters[0] == 0) done = true;
@@ -453,7 +494,12 @@ static cudaError_t launch_rounds_rds(Problem<double> pr, const amrvw_options& op
         *launches += 1;
     }
     if (times) cudaEventRecord(ev[3], st);
-    rounds_finish_kernel<<<nb32, 32, 0, st>>>(pr);
+    {
+        const int smem_elems = max_len - 1 <= AMRVW_SORT_SMEM ? (max_len > 1 ? max_len - 1 : 1) : AMRVW_SORT_SMEM;
+        const size_t smem = (size_t)smem_elems * sizeof(cplx);
+        if ((e = cudaFuncSetAttribute(rounds_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        rounds_finish_kernel<<<(int)pr.nbatch, 256, smem, st>>>(pr, smem_elems);
+    }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     *launches += 1;
     if (times) {
