@@ -26,7 +26,7 @@ struct amrvw_ctx {
     amrvw_options opt;
     std::string err;
     // grow-only device buffers
-    DevBuf chains[5], diags[3], coeffs, coeffs2, offsets, roots, nroots, nunconv, stats, shifts, state, prof, rec, fatshifts, swlist, counters, round_active;
+    DevBuf chains[5], diags[3], coeffs, coeffs2, offsets, roots, nroots, nunconv, stats, shifts, state, prof, rec, fatshifts, swlist, counters, round_active, queue, qslots, park, parked;
     unsigned* h_counters = nullptr;     // pinned
     cudaEvent_t evpool[32] = {};
     RoundsTimes times = {};
@@ -96,7 +96,7 @@ int amrvw_destroy(amrvw_ctx* ctx) {
     cudaSetDevice(ctx->device);
     DevBuf* all[] = {&ctx->chains[0], &ctx->chains[1], &ctx->chains[2], &ctx->chains[3], &ctx->chains[4], &ctx->diags[0], &ctx->diags[1], &ctx->diags[2],
                      &ctx->coeffs, &ctx->coeffs2, &ctx->offsets, &ctx->roots, &ctx->nroots, &ctx->nunconv, &ctx->stats, &ctx->shifts, &ctx->state, &ctx->prof,
-                     &ctx->rec, &ctx->fatshifts, &ctx->swlist, &ctx->counters, &ctx->round_active};
+                     &ctx->rec, &ctx->fatshifts, &ctx->swlist, &ctx->counters, &ctx->round_active, &ctx->queue, &ctx->qslots, &ctx->park, &ctx->parked};
     for (DevBuf* b : all) if (b->ptr) cudaFree(b->ptr);
     if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     for (cudaEvent_t e : ctx->evpool) if (e) cudaEventDestroy(e);
@@ -206,11 +206,22 @@ static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, cons
             if ((rc = reserve(ctx, ctx->swlist, ((size_t)total / 3 + (size_t)nbatch + 16) * sizeof(SmallWin)))) return rc;
             if ((rc = reserve(ctx, ctx->counters, CNT_WORDS * sizeof(unsigned)))) return rc;
             if ((rc = reserve(ctx, ctx->round_active, (size_t)max_rounds * sizeof(unsigned)))) return rc;
+            // unit queue of phase B: two round-parity queues, slots a power of two above units + resident warps
+            const size_t max_units = (size_t)(nbatch + 0) ;   // L >= 4 gives fewer; one per polynomial is an upper bound (L = 32)
+            size_t qcap = 1024;
+            while (qcap < 2 * max_units + 4096) qcap <<= 1;
+            if ((rc = reserve(ctx, ctx->queue, 2 * sizeof(RoundQueue)))) return rc;
+            if ((rc = reserve(ctx, ctx->qslots, 2 * qcap * sizeof(int)))) return rc;
+            if ((rc = reserve(ctx, ctx->park, max_units * sizeof(UnitPark)))) return rc;
+            if ((rc = reserve(ctx, ctx->parked, max_units * 32 * sizeof(StepState)))) return rc;
+            QueueBufs qb;
+            qb.q = (RoundQueue*)ctx->queue.ptr; qb.slots = (int*)ctx->qslots.ptr; qb.mask = (unsigned)(qcap - 1);
+            qb.park = (UnitPark*)ctx->park.ptr; qb.parked = (StepState*)ctx->parked.ptr;
             if (!ctx->h_counters) CUDA_TRY(ctx, cudaMallocHost((void**)&ctx->h_counters, 16 * sizeof(unsigned)));
             if (stats && !ctx->evpool[0]) for (cudaEvent_t& e : ctx->evpool) CUDA_TRY(ctx, cudaEventCreate(&e));
             pr.rec = (PolyRec*)ctx->rec.ptr; pr.shifts = (Shifts*)ctx->fatshifts.ptr; pr.swlist = ctx->swlist.ptr; pr.counters = (unsigned*)ctx->counters.ptr;
             cudaError_t e = launch_rounds_rds(pr, ctx->opt, (int)max_len, ctx->sm_count, st, &launches, ctx->h_counters, (unsigned*)ctx->round_active.ptr, max_rounds,
-                                              ctx->evpool, stats ? &ctx->times : nullptr);
+                                              ctx->evpool, stats ? &ctx->times : nullptr, qb);
             if (e != cudaSuccess) return fail(ctx, AMRVW_ERR_CUDA, std::string("rounds schedule: ") + cudaGetErrorString(e));
             done = true;
         }

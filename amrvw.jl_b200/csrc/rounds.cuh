@@ -171,140 +171,243 @@ __global__ void __launch_bounds__(32 * WPC) rounds_shift_kernel(Problem<double> 
 }
 
 // ---------------------------------------------------------------- phase B
+// Work unit = one warp's worth of polynomials (G = 32/L groups) for SEG lock-steps of their fat step.
+// Units circulate through a device-side queue: a warp pops a unit, chases SEG steps, parks the lanes'
+// 24 doubles in global memory and pushes the unit back, until the fat step is through.  Why: 1500
+// units on 592 SMSPs leave some SMSPs with 3 resident warps and some with 2; an SMSP delivers the
+// same ~1.67 steps per kilocycle either way (the FP64 pipe is ~72% busy with two warps already), so
+// its warps advance at 1/1772 or 1/1213 steps per cycle and a launch that binds a fat step to a
+// warp lasts as long as the slow ones while the fast SMSPs idle (27% of phase B: profiles/).  With
+// the queue every unit sees the average speed and every SMSP stays busy to the end of the round.
+struct RoundQueue {
+    unsigned head, tail, remaining, pad;
+};
+struct UnitPark {           // mutable per-unit state between segments; accessed with ld.cg / st.cg only
+    int t;                  // next lock-step
+    int sp[8];              // deflation-stack sizes of the unit's polynomials
+    int nturn[8];           // turnovers so far in this fat step
+    int pad[3];
+};
+
+AMRVW_DI void st_cg_rot(Rot<double>* p, const Rot<double> r) { __stcg(reinterpret_cast<double2*>(p), make_double2(r.c, r.s)); }
+AMRVW_DI Rot<double> ld_cg_rot(const Rot<double>* p) { const double2 v = __ldcg(reinterpret_cast<const double2*>(p)); return make_rot<double>(v.x, v.y); }
+
+// queue the units that have a fat step pending; one thread per unit
+template <int L>
+__global__ void rounds_enqueue_kernel(Problem<double> pr, RoundQueue* q, int* slots, unsigned mask, UnitPark* park, RoundQueue* q_next) {
+    constexpr int G = 32 / L;
+    const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u == 0 && q_next) { q_next->head = 0; q_next->tail = 0; q_next->remaining = 0; }
+    const long long nunits = (pr.nbatch + G - 1) / G;
+    if (u >= nunits) return;
+    bool any = false;
+    UnitPark up;
+    up.t = 0;
+    for (int g = 0; g < 8; ++g) { up.sp[g] = 0; up.nturn[g] = 0; }
+    up.pad[0] = up.pad[1] = up.pad[2] = 0;
+    for (int g = 0; g < G; ++g) {
+        const long long p = u * G + g;
+        if (p < pr.nbatch) {
+            const PolyRec* r = pr.rec + p;
+            if (r->iterating && r->mode != 0) { any = true; up.sp[g] = r->ls.sp; }
+        }
+    }
+    if (!any) return;
+    park[u] = up;
+    __threadfence();
+    atomicAdd(&q->remaining, 1u);
+    const unsigned k = atomicAdd(&q->tail, 1u);
+    atomicExch(slots + (k & mask), (int)u);
+}
+
 #ifndef AMRVW_PIPE_MINBLOCKS
 #define AMRVW_PIPE_MINBLOCKS 12
 #endif
-template <int L, int WPB>
-__global__ void __launch_bounds__(32 * WPB, AMRVW_PIPE_MINBLOCKS) rounds_phase_b_kernel(Problem<double> pr) {
+template <int L>
+__global__ void __launch_bounds__(32, AMRVW_PIPE_MINBLOCKS) rounds_phase_b_kernel(Problem<double> pr, RoundQueue* q, int* slots, unsigned mask, UnitPark* park, StepState* parked,
+                                                                                 int seg_steps) {
     constexpr int G = 32 / L;
-    constexpr int NT = 32 * WPB;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int wib = threadIdx.x >> 5, lane32 = threadIdx.x & 31;
+    constexpr int NT = 32;
+    __shared__ __align__(16) double2 smem_snap[12 * NT + G * 3 * AMRVW_RING];
+    const int lane32 = threadIdx.x & 31;
     const int grp = lane32 / L, lane = lane32 % L;
-    const long long p = ((long long)blockIdx.x * WPB + wib) * G + grp;
-    const bool valid = p < pr.nbatch;
-    double2* const snap_t = reinterpret_cast<double2*>(smem_raw) + threadIdx.x;                            // [12][NT] step snapshots
-    double2* const stage = reinterpret_cast<double2*>(smem_raw) + 12 * NT + (wib * G + grp) * (3 * AMRVW_RING);   // look-ahead ring of lane 0
+    double2* const snap_t = smem_snap + threadIdx.x;                                   // [12][NT] step snapshots
+    const unsigned stage_sa = (unsigned)__cvta_generic_to_shared(smem_snap + 12 * NT + grp * (3 * AMRVW_RING));   // look-ahead ring of lane 0
+    const unsigned snap_sa = (unsigned)__cvta_generic_to_shared(snap_t);
+    long long pc_all = 0, pc_lean = 0;
+    int pn_lean = 0, pn_all = 0, pn_calls = 0, pn_units = 0;
 
-    // the group's fat step (every lane reads the same record: broadcast loads)
-    int mode = 0, nb = 0, start = 1, stop = 0, ord0 = 0, sp = 0, N = 0;
-    if (valid) {
-        const PolyRec* r = pr.rec + p;
-        if (r->iterating) { mode = r->mode; nb = r->nb; start = r->ls.ctr.start_index; stop = r->ls.ctr.stop_index; ord0 = r->ls.ord; sp = r->ls.sp; N = r->N; }
-    }
-    const bool act = mode != 0;
-    if (!__any_sync(0xffffffffu, act)) return;
-    const int T = act ? (stop - start + 3 * L + 1) : 0;
-    const int Tmax = __reduce_max_sync(0xffffffffu, T);
-    const long long pc_t1 = clock64();
-    long long pc_lean = 0;
-    int pn_lean = 0, pn_calls = 0, nturn = 0;
-
-    Fact<double, false> F;
-    F.Q = F.B = F.Ct = F.WB = F.WCt = nullptr; F.DQ = F.DR = F.WD = nullptr; F.N = N; F.turnovers = 0;
-    int* dstack = nullptr;
-    if (act) {
-        F = make_fact<double, false>(pr, p, N);
-        dstack = pr.dstack + (pr.offsets[p] + (long long)pr.extra * p);
-    }
-    Rot<double>* const FQ = F.Q;
-    Rot<double>* const FB = F.B;
-    Rot<double>* const FC = F.Ct;
-    const unsigned stage_sa = (unsigned)__cvta_generic_to_shared(stage), snap_sa = (unsigned)__cvta_generic_to_shared(snap_t);
-
-    Rot<double> q0, q1, q2, b0, b1, b2, c0, c1, c2, U, V, W;
-    q0 = q1 = q2 = b0 = b1 = b2 = c0 = c1 = c2 = U = V = W = make_rot<double>(1.0, 0.0);
-    const bool has_bulge = act && lane < nb;
-    if (act && lane == 0) {
-        for (int a = 0; a < AMRVW_RING - 1; ++a) {
-            const int nidx = min(start + a, stop + 1);
-            cp_async16_sa(stage_sa + 48 * a, FQ + nidx); cp_async16_sa(stage_sa + 48 * a + 16, FB + nidx); cp_async16_sa(stage_sa + 48 * a + 32, FC + nidx);
-            cp_async_commit();
-        }
-    }
-    for (int t = 0; t < Tmax; ++t) {
-        {   // every lane of the warp at a regular position (or idle for good): the lean loop
-            const bool g_dead = !act || t >= T;
-            const bool g_main = act && nb == L && t >= 3 * L && t <= stop - start;
-            if (__all_sync(0xffffffffu, g_dead || g_main) && __any_sync(0xffffffffu, g_main)) {
-                const int te = __reduce_min_sync(0xffffffffu, g_main ? stop - start + 1 : 0x7fffffff);
-                const long long pc_l0 = clock64();
-                StepState z = {q0, q1, q2, b0, b1, b2, c0, c1, c2, U, V, W};
-                const int role = (g_main ? 1 : 0) | (lane == 0 ? 2 : 0) | (lane == L - 1 ? 4 : 0);
-                sp = lean_chase<L, NT>(z, FQ, FB, FC, stage_sa, snap_sa, dstack, sp, start, t, te, role);
-                q0 = z.q0; q1 = z.q1; q2 = z.q2; b0 = z.b0; b1 = z.b1; b2 = z.b2; c0 = z.c0; c1 = z.c1; c2 = z.c2; U = z.U; V = z.V; W = z.W;
-                if (g_main) nturn += 7 * (te - t);
-                pc_lean += clock64() - pc_l0; pn_lean += te - t; pn_calls += 1;
-                t = te - 1;
-                continue;
+    for (;;) {
+        // ---------------- pop a unit
+        int u = -1;
+        if (lane32 == 0) {
+            const unsigned k = atomicAdd(&q->head, 1u);
+            int* slot = slots + (k & mask);
+            for (unsigned spins = 0;; ++spins) {
+                u = atomicExch(slot, -1);
+                if (u >= 0) break;
+                if (*reinterpret_cast<volatile unsigned*>(&q->remaining) == 0u) { u = -2; break; }
+                if (spins > (1u << 24)) { u = -3; break; }   // ~10 s without work: give up rather than hang the device
+                __nanosleep(500);
             }
         }
-        const int tp = t - 3 * lane;
-        // ingest: what the previous lane finished last step (lane 0: from memory)
-        Rot<double> iq = shfl_up_rot(q0, L), ib = shfl_up_rot(b0, L), ic = shfl_up_rot(c0, L);
-        if (lane == 0) {
-            cp_async_wait_ring();
-            const unsigned sg = stage_sa + (t & (AMRVW_RING - 1)) * 48;
-            iq = lds_rot(sg); ib = lds_rot(sg + 16); ic = lds_rot(sg + 32);
-            if (act) {
-                const int nidx = min(start + t + AMRVW_RING - 1, stop + 1);
-                const unsigned sn2 = stage_sa + ((t + AMRVW_RING - 1) & (AMRVW_RING - 1)) * 48;
-                cp_async16_sa(sn2, FQ + nidx); cp_async16_sa(sn2 + 16, FB + nidx); cp_async16_sa(sn2 + 32, FC + nidx);
-            }
-            cp_async_commit();
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u < 0) break;
+        __threadfence();
+        const long long pc_u0 = clock64();
+
+        // ---------------- the unit's fat steps (every lane of a group reads the same record)
+        const long long p = (long long)u * G + grp;
+        int mode = 0, nb = 0, start = 1, stop = 0, ord0 = 0, N = 0;
+        if (p < pr.nbatch) {
+            const PolyRec* r = pr.rec + p;
+            if (r->iterating) { mode = r->mode; nb = r->nb; start = r->ls.ctr.start_index; stop = r->ls.ctr.stop_index; ord0 = r->ls.ord; N = r->N; }
         }
-        q0 = q1; q1 = q2; q2 = iq;
-        b0 = b1; b1 = b2; b2 = ib;
-        c0 = c1; c1 = c2; c2 = ic;
-        const int i = start + tp - 2;   // position of this lane's bulge; window = indices i..i+2
-        if (has_bulge && tp >= 2 && i <= stop - 1) {
-            if (tp == 2) {
-                StepState z = {q0, q1, q2, b0, b1, b2, c0, c1, c2, U, V, W};
-                create_and_absorb_at(z, F, start, stop, mode, pr.shifts + p * L, lane, pr.seed, (uint64_t)p, ord0 + lane);
-                q0 = z.q0; q1 = z.q1; U = z.U; V = z.V; W = z.W;
-                nturn += 1;
+        const bool act = mode != 0;
+        const int T = act ? (stop - start + 3 * L + 1) : 0;
+        const int Tmax = __reduce_max_sync(0xffffffffu, T);
+        UnitPark* const up = park + u;
+        const int t0 = __ldcg(&up->t);
+        const int t1 = min(Tmax, t0 + seg_steps);
+        int sp = __ldcg(&up->sp[grp]);
+        int nturn = 0;
+
+        Fact<double, false> F;
+        F.Q = F.B = F.Ct = F.WB = F.WCt = nullptr; F.DQ = F.DR = F.WD = nullptr; F.N = N; F.turnovers = 0;
+        int* dstack = nullptr;
+        if (act) {
+            F = make_fact<double, false>(pr, p, N);
+            dstack = pr.dstack + (pr.offsets[p] + (long long)pr.extra * p);
+        }
+        Rot<double>* const FQ = F.Q;
+        Rot<double>* const FB = F.B;
+        Rot<double>* const FC = F.Ct;
+
+        Rot<double> q0, q1, q2, b0, b1, b2, c0, c1, c2, U, V, W;
+        if (t0 == 0) {
+            q0 = q1 = q2 = b0 = b1 = b2 = c0 = c1 = c2 = U = V = W = make_rot<double>(1.0, 0.0);
+        } else {
+            const StepState* z = parked + ((long long)u * 32 + lane32);
+            q0 = ld_cg_rot(&z->q0); q1 = ld_cg_rot(&z->q1); q2 = ld_cg_rot(&z->q2);
+            b0 = ld_cg_rot(&z->b0); b1 = ld_cg_rot(&z->b1); b2 = ld_cg_rot(&z->b2);
+            c0 = ld_cg_rot(&z->c0); c1 = ld_cg_rot(&z->c1); c2 = ld_cg_rot(&z->c2);
+            U = ld_cg_rot(&z->U); V = ld_cg_rot(&z->V); W = ld_cg_rot(&z->W);
+        }
+        const bool has_bulge = act && lane < nb;
+        if (act && lane == 0) {
+            for (int a = 0; a < AMRVW_RING - 1; ++a) {
+                const int nidx = min(start + t0 + a, stop + 1);
+                const unsigned sg = stage_sa + ((t0 + a) & (AMRVW_RING - 1)) * 48;
+                cp_async16_sa(sg, FQ + nidx); cp_async16_sa(sg + 16, FB + nidx); cp_async16_sa(sg + 32, FC + nidx);
+                cp_async_commit();
             }
-            if (i <= stop - 2) {
-                // regular position: the 7 turnovers of one chase step (RDS.jl:42-70, 97-108) as ONE
-                // straight-line block; a degenerate turnover (flagged, essentially never) redoes the
-                // step on the general path from the shared-memory snapshot
+        }
+        for (int t = t0; t < t1; ++t) {
+            {   // every lane of the warp at a regular position (or idle for good): the lean loop
+                const bool g_dead = !act || t >= T;
+                const bool g_main = act && nb == L && t >= 3 * L && t <= stop - start;
+                if (__all_sync(0xffffffffu, g_dead || g_main) && __any_sync(0xffffffffu, g_main)) {
+                    const int te = min(t1, __reduce_min_sync(0xffffffffu, g_main ? stop - start + 1 : 0x7fffffff));
+                    const long long pc_l0 = clock64();
+                    StepState z = {q0, q1, q2, b0, b1, b2, c0, c1, c2, U, V, W};
+                    const int role = (g_main ? 1 : 0) | (lane == 0 ? 2 : 0) | (lane == L - 1 ? 4 : 0);
+                    sp = lean_chase<L, NT>(z, FQ, FB, FC, stage_sa, snap_sa, dstack, sp, start, t, te, role);
+                    q0 = z.q0; q1 = z.q1; q2 = z.q2; b0 = z.b0; b1 = z.b1; b2 = z.b2; c0 = z.c0; c1 = z.c1; c2 = z.c2; U = z.U; V = z.V; W = z.W;
+                    if (g_main) nturn += 7 * (te - t);
+                    pc_lean += clock64() - pc_l0; pn_lean += te - t; pn_calls += 1;
+                    t = te - 1;
+                    continue;
+                }
+            }
+            const int tp = t - 3 * lane;
+            // ingest: what the previous lane finished last step (lane 0: from memory)
+            Rot<double> iq = shfl_up_rot(q0, L), ib = shfl_up_rot(b0, L), ic = shfl_up_rot(c0, L);
+            if (lane == 0) {
+                cp_async_wait_ring();
+                const unsigned sg = stage_sa + (t & (AMRVW_RING - 1)) * 48;
+                iq = lds_rot(sg); ib = lds_rot(sg + 16); ic = lds_rot(sg + 32);
+                if (act) {
+                    const int nidx = min(start + t + AMRVW_RING - 1, stop + 1);
+                    const unsigned sn2 = stage_sa + ((t + AMRVW_RING - 1) & (AMRVW_RING - 1)) * 48;
+                    cp_async16_sa(sn2, FQ + nidx); cp_async16_sa(sn2 + 16, FB + nidx); cp_async16_sa(sn2 + 32, FC + nidx);
+                }
+                cp_async_commit();
+            }
+            q0 = q1; q1 = q2; q2 = iq;
+            b0 = b1; b1 = b2; b2 = ib;
+            c0 = c1; c1 = c2; c2 = ic;
+            const int i = start + tp - 2;   // position of this lane's bulge; window = indices i..i+2
+            if (has_bulge && tp >= 2 && i <= stop - 1) {
+                if (tp == 2) {
+                    StepState z = {q0, q1, q2, b0, b1, b2, c0, c1, c2, U, V, W};
+                    create_and_absorb_at(z, F, start, stop, mode, pr.shifts + p * L, lane, pr.seed, (uint64_t)p, ord0 + lane);
+                    q0 = z.q0; q1 = z.q1; U = z.U; V = z.V; W = z.W;
+                    nturn += 1;
+                }
+                if (i <= stop - 2) {
+                    // regular position: the 7 turnovers of one chase step (RDS.jl:42-70, 97-108) as ONE
+                    // straight-line block; a degenerate turnover (flagged, essentially never) redoes the
+                    // step on the general path from the shared-memory snapshot
 #ifndef AMRVW_STRICT
-                AMRVW_CHASE_REGULAR(snap_t, NT);
+                    AMRVW_CHASE_REGULAR(snap_t, NT);
 #else
-                AMRVW_CHASE_GENERAL();
+                    AMRVW_CHASE_GENERAL();
 #endif
-            } else {
-                StepState z = {q0, q1, q2, b0, b1, b2, c0, c1, c2, U, V, W};
-                chase_step_final_at(z, F, stop);
-                q0 = z.q0; q1 = z.q1; q2 = z.q2; b0 = z.b0; b1 = z.b1; b2 = z.b2; c0 = z.c0; c1 = z.c1; c2 = z.c2; U = z.U; V = z.V; W = z.W;
+                } else {
+                    StepState z = {q0, q1, q2, b0, b1, b2, c0, c1, c2, U, V, W};
+                    chase_step_final_at(z, F, stop);
+                    q0 = z.q0; q1 = z.q1; q2 = z.q2; b0 = z.b0; b1 = z.b1; b2 = z.b2; c0 = z.c0; c1 = z.c1; c2 = z.c2; U = z.U; V = z.V; W = z.W;
+                }
+                nturn += 7;
             }
-            nturn += 7;
+            // retire: the last lane writes index i back
+            if (lane == L - 1 && act && i >= start && i <= stop + 1) {
+                stg_rot(FQ + i, q0); stg_rot(FB + i, b0); stg_rot(FC + i, c0);
+                if (i <= stop && fabs(q0.s) <= AMRVW_EPS) dstack[sp++] = i;   // deflatable: record for phase A
+            }
         }
-        // retire: the last lane writes index i back
-        if (lane == L - 1 && act && i >= start && i <= stop + 1) {
-            stg_rot(FQ + i, q0); stg_rot(FB + i, b0); stg_rot(FC + i, c0);
-            if (i <= stop && fabs(q0.s) <= AMRVW_EPS) dstack[sp++] = i;   // deflatable: record for phase A
+        if (lane == 0) cp_async_wait_all();   // drain look-ahead requests past the end of the segment
+        sp = __shfl_sync(0xffffffffu, sp, grp * L + L - 1);
+        for (int d = L / 2; d >= 1; d >>= 1) nturn += __shfl_down_sync(0xffffffffu, nturn, d, L);
+        pn_all += t1 - t0; pn_units += 1;
+        if (t1 < Tmax) {
+            // ---------------- park the unit and hand it back
+            StepState* z = parked + ((long long)u * 32 + lane32);
+            st_cg_rot(&z->q0, q0); st_cg_rot(&z->q1, q1); st_cg_rot(&z->q2, q2);
+            st_cg_rot(&z->b0, b0); st_cg_rot(&z->b1, b1); st_cg_rot(&z->b2, b2);
+            st_cg_rot(&z->c0, c0); st_cg_rot(&z->c1, c1); st_cg_rot(&z->c2, c2);
+            st_cg_rot(&z->U, U); st_cg_rot(&z->V, V); st_cg_rot(&z->W, W);
+            if (lane == 0) { __stcg(&up->sp[grp], sp); __stcg(&up->nturn[grp], __ldcg(&up->nturn[grp]) + nturn); }
+            if (lane32 == 0) __stcg(&up->t, t1);
+            __threadfence();
+            __syncwarp();
+            if (lane32 == 0) {
+                const unsigned k = atomicAdd(&q->tail, 1u);
+                atomicExch(slots + (k & mask), u);
+            }
+        } else {
+            // ---------------- fat step through: back to the record for phase A
+            if (act && lane == 0) {
+                PolyRec* r = pr.rec + p;
+                r->ls.sp = sp;
+                r->st.sweeps += nb;
+                r->chase_turnovers += nturn + __ldcg(&up->nturn[grp]);
+                if (mode == 2) { r->st.exceptional += nb; r->ls.ord += nb; r->ls.ctr.it_count = 14; }
+            }
+            __threadfence();
+            __syncwarp();
+            if (lane32 == 0) atomicSub(&q->remaining, 1u);
         }
-    }
-    if (lane == 0) cp_async_wait_all();   // drain look-ahead requests past the end of the window
-    sp = __shfl_sync(0xffffffffu, sp, grp * L + L - 1);
-    for (int d = L / 2; d >= 1; d >>= 1) nturn += __shfl_down_sync(0xffffffffu, nturn, d, L);
-    if (act && lane == 0) {
-        PolyRec* r = pr.rec + p;
-        r->ls.sp = sp;
-        r->st.sweeps += nb;
-        r->chase_turnovers += nturn;
-        if (mode == 2) { r->st.exceptional += nb; r->ls.ord += nb; r->ls.ctr.it_count = 14; }
+        pc_all += clock64() - pc_u0;
     }
     if (pr.prof && lane32 == 0) {
-        const long long pc_b = clock64() - pc_t1;
-        atomicAdd(pr.prof + 0, (unsigned long long)pc_b);
+        atomicAdd(pr.prof + 0, (unsigned long long)pc_all);
         atomicAdd(pr.prof + 2, (unsigned long long)pc_lean);
-        atomicAdd(pr.prof + 3, (unsigned long long)(pc_b - pc_lean));
+        atomicAdd(pr.prof + 3, (unsigned long long)(pc_all - pc_lean));
         atomicAdd(pr.prof + 4, (unsigned long long)pn_lean);
-        atomicAdd(pr.prof + 5, (unsigned long long)(Tmax - pn_lean));
+        atomicAdd(pr.prof + 5, (unsigned long long)(pn_all - pn_lean));
         atomicAdd(pr.prof + 6, (unsigned long long)pn_calls);
-        atomicAdd(pr.prof + 7, 1ull);
+        atomicAdd(pr.prof + 7, (unsigned long long)pn_units);
     }
 }
 
@@ -388,17 +491,21 @@ __global__ void __launch_bounds__(256) rounds_finish_kernel(Problem<double> pr, 
 // ---------------------------------------------------------------- host side
 struct RoundsTimes { float setup_ms, a_ms, b_ms, small_ms, finish_ms; int rounds; unsigned small_windows; };
 
+struct QueueBufs { RoundQueue* q; int* slots; unsigned mask; UnitPark* park; StepState* parked; };
+
 template <int L>
-static cudaError_t launch_phase_b(const Problem<double>& pr, cudaStream_t st) {
-#ifndef AMRVW_PIPE_WPB
-#define AMRVW_PIPE_WPB 1
-#endif
-    constexpr int WPB = AMRVW_PIPE_WPB;
+static cudaError_t launch_phase_b(const Problem<double>& pr, const QueueBufs& qb, int round, int seg_steps, int sm_count, cudaStream_t st) {
     constexpr int G = 32 / L;
-    const size_t smem = (size_t)12 * 32 * WPB * sizeof(double2) + (size_t)WPB * G * 3 * AMRVW_RING * sizeof(double2);
-    const long long groups_per_block = (long long)WPB * G;
-    const int blocks = (int)((pr.nbatch + groups_per_block - 1) / groups_per_block);
-    rounds_phase_b_kernel<L, WPB><<<blocks, 32 * WPB, smem, st>>>(pr);
+    const long long nunits = (pr.nbatch + G - 1) / G;
+    RoundQueue* q = qb.q + (round & 1);
+    RoundQueue* q_next = qb.q + ((round + 1) & 1);
+    int* slots = qb.slots + (size_t)(round & 1) * (qb.mask + 1);
+    rounds_enqueue_kernel<L><<<(int)((nunits + 127) / 128), 128, 0, st>>>(pr, q, slots, qb.mask, qb.park, q_next);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const long long resident = (long long)sm_count * AMRVW_PIPE_MINBLOCKS;
+    const int blocks = (int)(nunits < resident ? nunits : resident);
+    rounds_phase_b_kernel<L><<<blocks, 32, 0, st>>>(pr, q, slots, qb.mask, qb.park, qb.parked, seg_steps);
     return cudaGetLastError();
 }
 
@@ -428,13 +535,17 @@ static void choose_pipe_params(const amrvw_options& opt, long long nbatch, int m
 // Runs the whole schedule on `st`.  h_counters: pinned host words for the round counters.  Blocks the
 // host once per chunk of rounds (the termination test needs the device's count of pending fat steps).
 static cudaError_t launch_rounds_rds(Problem<double> pr, const amrvw_options& opt, int max_len, int sm_count, cudaStream_t st, int* launches,
-                                     unsigned* h_counters, unsigned* d_round_active, int max_rounds, cudaEvent_t* ev, RoundsTimes* times) {
+                                     unsigned* h_counters, unsigned* d_round_active, int max_rounds, cudaEvent_t* ev, RoundsTimes* times, const QueueBufs& qb) {
     int L; PipeParams pp;
     choose_pipe_params(opt, pr.nbatch, max_len, sm_count, L, pp);
     cudaError_t e;
     const int nb32 = (int)((pr.nbatch + 31) / 32), nb64 = (int)((pr.nbatch + 63) / 64);
     if ((e = cudaMemsetAsync(pr.counters, 0, CNT_WORDS * sizeof(unsigned), st)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(d_round_active, 0, (size_t)max_rounds * sizeof(unsigned), st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(qb.q, 0, 2 * sizeof(RoundQueue), st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(qb.slots, 0xFF, 2 * (size_t)(qb.mask + 1) * sizeof(int), st)) != cudaSuccess) return e;
+    static const int seg_env = std::getenv("AMRVW_SEG_STEPS") ? std::atoi(std::getenv("AMRVW_SEG_STEPS")) : 0;   // development knob
+    const int seg_steps = seg_env > 0 ? seg_env : 64;
     if (times) { *times = RoundsTimes{0, 0, 0, 0, 0, 0, 0}; cudaEventRecord(ev[0], st); }
     rounds_setup_kernel<<<nb64, 64, 0, st>>>(pr);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
@@ -457,14 +568,14 @@ static cudaError_t launch_rounds_rds(Problem<double> pr, const amrvw_options& op
             if ((e = cudaGetLastError()) != cudaSuccess) return e;
             if (times) cudaEventRecord(ev[3 + 3 * k], st);
             switch (L) {
-                case 4: e = launch_phase_b<4>(pr, st); break;
-                case 8: e = launch_phase_b<8>(pr, st); break;
-                case 16: e = launch_phase_b<16>(pr, st); break;
-                default: e = launch_phase_b<32>(pr, st); break;
+                case 4: e = launch_phase_b<4>(pr, qb, round, seg_steps, sm_count, st); break;
+                case 8: e = launch_phase_b<8>(pr, qb, round, seg_steps, sm_count, st); break;
+                case 16: e = launch_phase_b<16>(pr, qb, round, seg_steps, sm_count, st); break;
+                default: e = launch_phase_b<32>(pr, qb, round, seg_steps, sm_count, st); break;
             }
             if (e != cudaSuccess) return e;
             if (times) cudaEventRecord(ev[4 + 3 * k], st);
-            *launches += 3;
+            *launches += 4;
         }
         if ((e = cudaMemcpyAsync(h_counters, d_round_active + (round - 1), sizeof(unsigned), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
         if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
