@@ -26,8 +26,7 @@ struct amrvw_ctx {
     amrvw_options opt;
     std::string err;
     // grow-only device buffers
-    DevBuf chains[5], diags[3], coeffs, coeffs2, offsets, roots, nroots, nunconv, stats, shifts, state, prof, rec, fatshifts, swlist, counters, round_active, queue, qslots, park, parked;
-    unsigned* h_counters = nullptr;     // pinned
+    DevBuf chains[5], diags[3], coeffs, coeffs2, offsets, roots, nroots, nunconv, stats, shifts, state, prof, rec, fatshifts, swlist, counters, queue, qslots, park, parked;
     cudaEvent_t evpool[32] = {};
     RoundsTimes times = {};
     int sm_count = 148;
@@ -96,9 +95,8 @@ int amrvw_destroy(amrvw_ctx* ctx) {
     cudaSetDevice(ctx->device);
     DevBuf* all[] = {&ctx->chains[0], &ctx->chains[1], &ctx->chains[2], &ctx->chains[3], &ctx->chains[4], &ctx->diags[0], &ctx->diags[1], &ctx->diags[2],
                      &ctx->coeffs, &ctx->coeffs2, &ctx->offsets, &ctx->roots, &ctx->nroots, &ctx->nunconv, &ctx->stats, &ctx->shifts, &ctx->state, &ctx->prof,
-                     &ctx->rec, &ctx->fatshifts, &ctx->swlist, &ctx->counters, &ctx->round_active, &ctx->queue, &ctx->qslots, &ctx->park, &ctx->parked};
+                     &ctx->rec, &ctx->fatshifts, &ctx->swlist, &ctx->counters, &ctx->queue, &ctx->qslots, &ctx->park, &ctx->parked};
     for (DevBuf* b : all) if (b->ptr) cudaFree(b->ptr);
-    if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
     for (cudaEvent_t e : ctx->evpool) if (e) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -198,31 +196,26 @@ static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, cons
     bool done = false;
     if constexpr (is_real<S>::value) {
         if (var == V_RDS && ctx->opt.schedule != AMRVW_SCHEDULE_REFERENCE) {
-            // rounds schedule: per-polynomial records, shifts, small-window queue, counters
-            const int max_rounds = 20 * (int)max_len + 8;
+            // unit schedule: per-polynomial records, shifts, small-window queue, unit queue and parking
             int rc;
             if ((rc = reserve(ctx, ctx->rec, (size_t)nbatch * sizeof(PolyRec)))) return rc;
             if ((rc = reserve(ctx, ctx->fatshifts, (size_t)nbatch * 32 * sizeof(Shifts)))) return rc;
             if ((rc = reserve(ctx, ctx->swlist, ((size_t)total / 3 + (size_t)nbatch + 16) * sizeof(SmallWin)))) return rc;
             if ((rc = reserve(ctx, ctx->counters, CNT_WORDS * sizeof(unsigned)))) return rc;
-            if ((rc = reserve(ctx, ctx->round_active, (size_t)max_rounds * sizeof(unsigned)))) return rc;
-            // unit queue of phase B: two round-parity queues, slots a power of two above units + resident warps
-            const size_t max_units = (size_t)(nbatch + 0) ;   // L >= 4 gives fewer; one per polynomial is an upper bound (L = 32)
+            const size_t max_units = (size_t)nbatch;   // one per polynomial is the upper bound (L = 32)
             size_t qcap = 1024;
             while (qcap < 2 * max_units + 4096) qcap <<= 1;
-            if ((rc = reserve(ctx, ctx->queue, 2 * sizeof(RoundQueue)))) return rc;
-            if ((rc = reserve(ctx, ctx->qslots, 2 * qcap * sizeof(int)))) return rc;
+            if ((rc = reserve(ctx, ctx->queue, sizeof(RoundQueue)))) return rc;
+            if ((rc = reserve(ctx, ctx->qslots, qcap * sizeof(int)))) return rc;
             if ((rc = reserve(ctx, ctx->park, max_units * sizeof(UnitPark)))) return rc;
             if ((rc = reserve(ctx, ctx->parked, max_units * 32 * sizeof(StepState)))) return rc;
             QueueBufs qb;
             qb.q = (RoundQueue*)ctx->queue.ptr; qb.slots = (int*)ctx->qslots.ptr; qb.mask = (unsigned)(qcap - 1);
             qb.park = (UnitPark*)ctx->park.ptr; qb.parked = (StepState*)ctx->parked.ptr;
-            if (!ctx->h_counters) CUDA_TRY(ctx, cudaMallocHost((void**)&ctx->h_counters, 16 * sizeof(unsigned)));
             if (stats && !ctx->evpool[0]) for (cudaEvent_t& e : ctx->evpool) CUDA_TRY(ctx, cudaEventCreate(&e));
             pr.rec = (PolyRec*)ctx->rec.ptr; pr.shifts = (Shifts*)ctx->fatshifts.ptr; pr.swlist = ctx->swlist.ptr; pr.counters = (unsigned*)ctx->counters.ptr;
-            cudaError_t e = launch_rounds_rds(pr, ctx->opt, (int)max_len, ctx->sm_count, st, &launches, ctx->h_counters, (unsigned*)ctx->round_active.ptr, max_rounds,
-                                              ctx->evpool, stats ? &ctx->times : nullptr, qb);
-            if (e != cudaSuccess) return fail(ctx, AMRVW_ERR_CUDA, std::string("rounds schedule: ") + cudaGetErrorString(e));
+            cudaError_t e = launch_rounds_rds(pr, ctx->opt, (int)max_len, (long long)total, ctx->sm_count, st, &launches, ctx->evpool, stats ? &ctx->times : nullptr, qb);
+            if (e != cudaSuccess) return fail(ctx, AMRVW_ERR_CUDA, std::string("unit schedule: ") + cudaGetErrorString(e));
             done = true;
         }
     }
@@ -340,10 +333,14 @@ int amrvw_last_profile(amrvw_ctx* ctx, int64_t* out16) {
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     CUDA_TRY(ctx, cudaMemcpyAsync(out16, ctx->prof.ptr, 16 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    // kernel times of the rounds schedule, microseconds
-    out16[8] = (int64_t)(ctx->times.setup_ms * 1e3); out16[9] = (int64_t)(ctx->times.a_ms * 1e3); out16[10] = (int64_t)(ctx->times.b_ms * 1e3);
+    // kernel times of the unit schedule, microseconds
+    out16[8] = (int64_t)(ctx->times.setup_ms * 1e3); out16[9] = (int64_t)(ctx->times.main_ms * 1e3);
     out16[11] = (int64_t)(ctx->times.small_ms * 1e3); out16[12] = (int64_t)(ctx->times.finish_ms * 1e3);
-    out16[13] = ctx->times.rounds; out16[14] = ctx->times.small_windows;
+    {
+        unsigned cnt[CNT_WORDS];
+        CUDA_TRY(ctx, cudaMemcpy(cnt, ctx->counters.ptr, sizeof(cnt), cudaMemcpyDeviceToHost));
+        out16[14] = cnt[CNT_SMALL];
+    }
     return AMRVW_OK;
 }
 

@@ -54,13 +54,21 @@ AMRVW_DI Rot<double> ldg_rot(const Rot<double>* p) {
     return make_rot<double>(v.x, v.y);
 }
 AMRVW_DI void stg_rot(Rot<double>* p, const Rot<double> r) { *reinterpret_cast<double2*>(p) = make_double2(r.c, r.s); }
+// L2-coherent loads.  In the persistent kernel (rounds.cuh) a polynomial's chains, deflation stack and
+// record are written by whichever warp held its unit last, possibly on another SM; L1 is not
+// coherent across SMs, so everything that was written during the kernel is read with ld.global.cg
+// (and cp.async.cg).  Stores are write-through and need nothing.
+AMRVW_DI Rot<double> ldcg_rot(const Rot<double>* p) {
+    const double2 v = __ldcg(reinterpret_cast<const double2*>(p));
+    return make_rot<double>(v.x, v.y);
+}
 
 // 16-byte asynchronous global->shared copy (LDGSTS): lane 0's look-ahead of the next chain index goes
 // through shared memory so that it holds no registers across the chase step (with the value kept in
 // registers ptxas spilled it, and the spill store waited for the load: 14% of all stall samples).
 AMRVW_DI void cp_async16(void* smem_dst, const void* gsrc) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
 }
 AMRVW_DI void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 AMRVW_DI void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -258,16 +266,19 @@ AMRVW_DI void create_and_absorb(StepState& z, const Rot<double> qm, const Rot<do
 AMRVW_NI void create_and_absorb_at(StepState& z, const Fact<double, false>& F, const int start, const int stop, const int mode, const Shifts* shl, const int lane,
                                    const uint64_t seed, const uint64_t poly, const int ordinal) {
     const Rot<double> one = make_rot<double>(1.0, 0.0);
-    const Rot<double> qm = ldg_rot(F.Q + start - 1);                 // Q[0] is the (1,0) sentinel
+    const Rot<double> qm = ldcg_rot(F.Q + start - 1);                // Q[0] is the (1,0) sentinel
     Rot<double> bm = one, cm = one;
-    if (start > 1) { bm = ldg_rot(F.B + start - 1); cm = ldg_rot(F.Ct + start - 1); }
+    if (start > 1) { bm = ldcg_rot(F.B + start - 1); cm = ldcg_rot(F.Ct + start - 1); }
     Shifts sh;
     sh.e1 = cplx(0.0, 0.0); sh.e2 = cplx(0.0, 0.0);
-    if (mode == 1) sh = shl[lane];
+    if (mode == 1) {
+        const double2 v1 = __ldcg(reinterpret_cast<const double2*>(shl + lane)), v2 = __ldcg(reinterpret_cast<const double2*>(shl + lane) + 1);
+        sh.e1 = cplx(v1.x, v1.y); sh.e2 = cplx(v2.x, v2.y);
+    }
     create_and_absorb(z, qm, bm, cm, F, start, stop, mode, sh, seed, poly, ordinal);
 }
 AMRVW_NI void chase_step_final_at(StepState& z, const Fact<double, false>& F, const int stop) {
-    chase_step_final(z, sign_(F.Q[stop + 1].c));                      // Q[N] is the (1,0) sentinel
+    chase_step_final(z, sign_(ldcg_rot(F.Q + stop + 1).c));            // Q[N] is the (1,0) sentinel
 }
 
 // drive_window's step for the pipelined kernel's serial phases
@@ -294,11 +305,23 @@ struct LeaderState {
 // rotators above the active window never change, so "highest deflatable index <= stop" is the top of
 // the stack: O(1) instead of n^2/4 dependent loads per polynomial (20% of the kernel in the ncu
 // source view before this).
+// diagonal_block (diagonal-block.jl:12-36) at j through a coherent copy of indices j-1..j+1
+AMRVW_DI void diagonal_block_cg(const Fact<double, false>& F, const int j, double A[4]) {
+    Rot<double> lq[3], lb[3], lc[3];
+    for (int t = 0; t < 3; ++t) {
+        lq[t] = ldcg_rot(F.Q + j - 1 + t);                         // Q[0], Q[N] are the (1,0) sentinels
+        lb[t] = (j - 1 + t >= 1) ? ldcg_rot(F.B + j - 1 + t) : make_rot<double>(1.0, 0.0);
+        lc[t] = (j - 1 + t >= 1) ? ldcg_rot(F.Ct + j - 1 + t) : make_rot<double>(1.0, 0.0);
+    }
+    Fact<double, false> Fl = F;
+    Fl.Q = lq - (j - 1); Fl.B = lb - (j - 1); Fl.Ct = lc - (j - 1);
+    diagonal_block(Fl, j, A);
+}
 AMRVW_DI void check_deflation_stack(Fact<double, false>& F, LeaderState& ls, const int* dstack) {
     if (ls.sp > 0) {
-        const int k = dstack[ls.sp - 1];
+        const int k = __ldcg(dstack + ls.sp - 1);
         if (k >= ls.ctr.start_index && k <= ls.ctr.stop_index) {
-            deflate(F, k);
+            F.Q[k] = make_rot<double>(sign_(ldcg_rot(F.Q + k).c), 0.0);   // deflate (RDS.jl:134-141)
             ls.ctr.zero_index = k;
             ls.ctr.start_index = k + 1;
             ls.ctr.it_count = 15;
@@ -377,17 +400,17 @@ AMRVW_DI int phase_a(Fact<double, false>& F, LeaderState& ls, cplx* E, const Gro
         const int k = ctr.stop_index;
         const int delta = ctr.stop_index - ctr.zero_index;
         if (delta == 1) {
-            diagonal_block(F, k, A);
+            diagonal_block_cg(F, k, A);
             cplx e1, e2;
             eig2x2(A, e1, e2);
             E[k] = e1; E[k + 1] = e2;
-            if (ctr.stop_index == 2) { diagonal_block(F, 1, A); E[1] = to_c(A[0]); ctr.stop_index = 0; return 0; }
+            if (ctr.stop_index == 2) { diagonal_block_cg(F, 1, A); E[1] = to_c(A[0]); ctr.stop_index = 0; return 0; }
             pop_window(ls);
             ctr.stop_index = ctr.zero_index - 1; ctr.zero_index = 0; ctr.start_index = 1;
             check_deflation_stack(F, ls, dstack);
             if (ctr.stop_index < 1) return 0;
         } else if (delta <= 0) {
-            diagonal_block(F, k, A);
+            diagonal_block_cg(F, k, A);
             if (ctr.stop_index == 1) { E[1] = to_c(A[0]); E[2] = to_c(A[3]); ctr.stop_index = 0; return 0; }
             E[k + 1] = to_c(A[3]);
             pop_window(ls);
@@ -400,7 +423,7 @@ AMRVW_DI int phase_a(Fact<double, false>& F, LeaderState& ls, cplx* E, const Gro
             // is queued and finished later with the reference's one-bulge schedule (rounds_small_kernel)
             const int lo2 = ctr.start_index, hi2 = ctr.stop_index;
             sink.push(lo2, hi2, ctr.it_count);
-            if (lo2 == 2) { diagonal_block(F, 1, A); E[1] = to_c(A[0]); }
+            if (lo2 == 2) { diagonal_block_cg(F, 1, A); E[1] = to_c(A[0]); }
             pop_window(ls);
             ctr.stop_index = lo2 - 2; ctr.zero_index = 0; ctr.start_index = 1; ctr.it_count = 15;
             if (ctr.stop_index >= 1) check_deflation_stack(F, ls, dstack);
@@ -438,7 +461,7 @@ AMRVW_DI Rot<double> lds_rot(unsigned sa) {
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.c), "=d"(r.s) : "r"(sa) : "memory");
     return r;
 }
-AMRVW_DI void cp_async16_sa(unsigned sa, const void* gsrc) { asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory"); }
+AMRVW_DI void cp_async16_sa(unsigned sa, const void* gsrc) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory"); }
 
 // role: bit 0: the lane's group is chasing, bit 1: lane 0 of its group (feeds), bit 2: lane L-1 (retires)
 template <int L, int NT>

@@ -87,14 +87,86 @@ __global__ void __launch_bounds__(64) rounds_setup_kernel(Problem<double> pr) {
     pr.rec[p] = rec;
 }
 
-// ---------------------------------------------------------------- phase A, part 1: the driver
-// One thread per polynomial: deflation bookkeeping, 1x1 / 2x2 extraction, queueing of small windows,
-// up to the next fat step.  mode 3 = the fat step still needs its shifts (part 2).
-__global__ void __launch_bounds__(32) rounds_phase_a_kernel(Problem<double> pr, PipeParams pp, int L, unsigned* round_active) {
-    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= pr.nbatch) return;
-    if (!pr.rec[p].iterating) return;
-    PolyRec rec = pr.rec[p];
+// ---------------------------------------------------------------- records, coherently
+// PolyRec is read and written by whichever warp holds the unit: whole-record ld.cg / st.cg copies.
+static_assert(sizeof(PolyRec) % 8 == 0, "PolyRec is copied in 8-byte words");
+AMRVW_DI PolyRec load_rec(const PolyRec* g) {
+    PolyRec r;
+    const long long* src = reinterpret_cast<const long long*>(g);
+    long long* dst = reinterpret_cast<long long*>(&r);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(PolyRec) / 8); ++i) dst[i] = __ldcg(src + i);
+    return r;
+}
+AMRVW_DI void store_rec(PolyRec* g, const PolyRec& r) {
+    long long* dst = reinterpret_cast<long long*>(g);
+    const long long* src = reinterpret_cast<const long long*>(&r);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(PolyRec) / 8); ++i) __stcg(dst + i, src[i]);
+}
+
+// ---------------------------------------------------------------- the unit queue
+// Work unit = one warp's worth of polynomials (G = 32/L groups).  A unit is either waiting for its
+// phase A (park.t < 0) or in the middle of a fat step (park.t = next lock-step).  Units circulate
+// through a device-side FIFO: a warp pops a unit, runs phase A if it is due, chases SEG lock-steps,
+// parks the lanes' 24 doubles in global memory and pushes the unit back, until its polynomials are
+// done.  Why a queue: 1500 units on 592 SMSPs leave some SMSPs with 3 resident warps and some with
+// 2; an SMSP delivers the same ~1.67 steps per kilocycle either way (the FP64 pipe is ~72% busy with
+// two warps), so warps advance at 1/1772 or 1/1213 steps per cycle.  Binding a fat step (or a whole
+// polynomial) to a warp makes everything wait for the slow SMSPs -- 27% of the chase time in the
+// round-per-kernel version of this file, 20% in the fused round-1 kernel (profiles/).  Through the
+// queue every unit sees the average speed and no SMSP runs dry before the last units finish.
+struct RoundQueue {
+    unsigned head, tail, remaining, pad;
+};
+struct UnitPark {           // mutable per-unit state between visits; accessed with ld.cg / st.cg only
+    int t;                  // next lock-step of the pending fat step; < 0: phase A is due
+    int sp[8];              // deflation-stack sizes of the unit's polynomials
+    int nturn[8];           // turnovers so far in this fat step
+    int pad[3];
+};
+
+AMRVW_DI void st_cg_rot(Rot<double>* p, const Rot<double> r) { __stcg(reinterpret_cast<double2*>(p), make_double2(r.c, r.s)); }
+
+// queue every unit that has a polynomial to iterate; one thread per unit
+template <int L>
+__global__ void unit_enqueue_kernel(Problem<double> pr, RoundQueue* q, int* slots, unsigned mask, UnitPark* park) {
+    constexpr int G = 32 / L;
+    const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nunits = (pr.nbatch + G - 1) / G;
+    if (u >= nunits) return;
+    bool any = false;
+    for (int g = 0; g < G; ++g) {
+        const long long p = u * G + g;
+        if (p < pr.nbatch && pr.rec[p].iterating) any = true;
+    }
+    if (!any) return;
+    UnitPark up;
+    up.t = -1;
+    for (int g = 0; g < 8; ++g) { up.sp[g] = 0; up.nturn[g] = 0; }
+    up.pad[0] = up.pad[1] = up.pad[2] = 0;
+    park[u] = up;
+    __threadfence();
+    atomicAdd(&q->remaining, 1u);
+    const unsigned k = atomicAdd(&q->tail, 1u);
+    atomicExch(slots + (k & mask), (int)u);
+}
+
+// shared-memory scratch of one warp for the shift computation
+template <int MH> struct __align__(16) ShiftScratch {
+    Rot<double> q[MH + 3], b[MH + 3], c[MH + 3];
+    cplx e[MH + 3];
+    double H[MH * (MH + 1)];
+    double isg[MH + 2];
+    double2 sn[12];
+};
+
+// ---------------------------------------------------------------- phase A of a unit
+// Part 1, the driver (AMRVW_algorithm.jl:10-138): lane 0 of each group, up to the next fat step --
+// deflation bookkeeping, 1x1 / 2x2 extraction, queueing of small windows.
+AMRVW_NI int unit_driver(const Problem<double>& pr, const PipeParams pp, const int L, const long long p) {
+    PolyRec rec = load_rec(pr.rec + p);
+    if (!rec.iterating) return 0;
     Fact<double, false> F = make_fact<double, false>(pr, p, rec.N);
     GroupScratch sc;
     sc.q = sc.b = sc.c = nullptr; sc.e = nullptr; sc.H = nullptr; sc.isg = nullptr;
@@ -107,37 +179,22 @@ __global__ void __launch_bounds__(32) rounds_phase_a_kernel(Problem<double> pr, 
     rec.serial_turnovers += F.turnovers;
     rec.mode = mode; rec.nb = nb;
     if (mode == 0) rec.iterating = 0;
-    else atomicAdd(round_active, 1u);
-    pr.rec[p] = rec;
+    store_rec(pr.rec + p, rec);
+    return mode;
 }
-
-// ---------------------------------------------------------------- phase A, part 2: the shifts
-// One warp per polynomial with a pending fat step (mode 3): stage the trailing block's rotators,
-// write the block out densely, Hessenberg QR with the lanes sharing rows and columns (shifts.cuh),
-// pair the shifts.  MH: largest order of the trailing block this instantiation holds in shared
-// memory; WPC warps per CTA.
-template <int MH, int WPC>
-__global__ void __launch_bounds__(32 * WPC) rounds_shift_kernel(Problem<double> pr, PipeParams pp, int L) {
+// Part 2, the shifts of a pending fat step (mode 3), the whole warp on one polynomial: stage the
+// trailing block's rotators, write the block out densely, Hessenberg QR with the lanes sharing rows
+// and columns (shifts.cuh), pair the shifts.
+template <int MH>
+AMRVW_NI void unit_shifts(const Problem<double>& pr, const PipeParams pp, const int L, const long long p, ShiftScratch<MH>& ws, const int lane) {
     constexpr int LDH = MH + 1;
-    struct __align__(16) WarpScratch {
-        Rot<double> q[MH + 3], b[MH + 3], c[MH + 3];
-        cplx e[MH + 3];
-        double H[MH * LDH];
-        double isg[MH + 2];
-        double2 sn[12];
-    };
-    __shared__ WarpScratch scratch[WPC];
-    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long p = (long long)blockIdx.x * WPC + wib;
-    if (p >= pr.nbatch) return;
-    PolyRec* rec = pr.rec + p;
-    if (!rec->iterating || rec->mode != 3) return;
-    WarpScratch& ws = scratch[wib];
-    const int m = rec->nb, stop = rec->ls.ctr.stop_index, k0 = stop - m, M = m + 1;
-    Fact<double, false> F = make_fact<double, false>(pr, p, rec->N);
+    PolyRec rec = load_rec(pr.rec + p);
+    const int m = rec.nb, stop = rec.ls.ctr.stop_index, k0 = stop - m, M = m + 1;
+    Fact<double, false> F = make_fact<double, false>(pr, p, rec.N);
+    __syncwarp();
     // staged copy with global indices: slot t <-> index k0 + t
     for (int t = lane; t <= m + 1; t += 32) {
-        ws.q[t] = ldg_rot(F.Q + k0 + t); ws.b[t] = ldg_rot(F.B + k0 + t); ws.c[t] = ldg_rot(F.Ct + k0 + t);
+        ws.q[t] = ldcg_rot(F.Q + k0 + t); ws.b[t] = ldcg_rot(F.B + k0 + t); ws.c[t] = ldcg_rot(F.Ct + k0 + t);
     }
     __syncwarp();
     if (lane == 0) {
@@ -145,96 +202,42 @@ __global__ void __launch_bounds__(32 * WPC) rounds_shift_kernel(Problem<double> 
         ws.q[0] = make_rot<double>(sg == 0.0 ? 1.0 : sg, 0.0);
     }
     __syncwarp();
-    const Rot<double>* q = ws.q - k0;
-    const Rot<double>* b = ws.b - k0;
-    const Rot<double>* c = ws.c - k0;
     bool ok = false;
     if (pp.dense) {
-        dense_trailing_block_warp(q, b, c, k0, stop, ws.H, LDH, ws.isg, M, lane);
+        dense_trailing_block_warp(ws.q - k0, ws.b - k0, ws.c - k0, k0, stop, ws.H, LDH, ws.isg, M, lane);
         ok = hqr_eigenvalues_warp(ws.H, LDH, M, ws.e, lane);
     }
     __syncwarp();
     if (lane == 0) {
-        long long turnovers = 0;
-        int ord = rec->ls.ord;
         if (!ok) {   // core-chasing iteration on the staged copy (also AMRVW_SHIFTS_CHASE)
             Fact<double, false> W = F;
             W.Q = ws.q - k0; W.B = ws.b - k0; W.Ct = ws.c - k0; W.turnovers = 0;
-            turnovers = chase_shifts(W, k0, stop, ws.e, pr.seed, (uint64_t)p, ord, ws.sn, 1);
+            rec.serial_turnovers += chase_shifts(W, k0, stop, ws.e, pr.seed, (uint64_t)p, rec.ls.ord, ws.sn, 1);
         }
-        const int nb = pair_shifts(ws.e, m, pr.shifts + p * L, L, pp.reuse);
-        rec->ls.ord = ord;
-        rec->serial_turnovers += turnovers;
-        rec->nb = nb;
-        rec->mode = 1;
+        rec.nb = pair_shifts(ws.e, m, pr.shifts + p * L, L, pp.reuse);
+        rec.mode = 1;
+        store_rec(pr.rec + p, rec);
     }
+    __syncwarp();
 }
 
-// ---------------------------------------------------------------- phase B
-// Work unit = one warp's worth of polynomials (G = 32/L groups) for SEG lock-steps of their fat step.
-// Units circulate through a device-side queue: a warp pops a unit, chases SEG steps, parks the lanes'
-// 24 doubles in global memory and pushes the unit back, until the fat step is through.  Why: 1500
-// units on 592 SMSPs leave some SMSPs with 3 resident warps and some with 2; an SMSP delivers the
-// same ~1.67 steps per kilocycle either way (the FP64 pipe is ~72% busy with two warps already), so
-// its warps advance at 1/1772 or 1/1213 steps per cycle and a launch that binds a fat step to a
-// warp lasts as long as the slow ones while the fast SMSPs idle (27% of phase B: profiles/).  With
-// the queue every unit sees the average speed and every SMSP stays busy to the end of the round.
-struct RoundQueue {
-    unsigned head, tail, remaining, pad;
-};
-struct UnitPark {           // mutable per-unit state between segments; accessed with ld.cg / st.cg only
-    int t;                  // next lock-step
-    int sp[8];              // deflation-stack sizes of the unit's polynomials
-    int nturn[8];           // turnovers so far in this fat step
-    int pad[3];
-};
-
-AMRVW_DI void st_cg_rot(Rot<double>* p, const Rot<double> r) { __stcg(reinterpret_cast<double2*>(p), make_double2(r.c, r.s)); }
-AMRVW_DI Rot<double> ld_cg_rot(const Rot<double>* p) { const double2 v = __ldcg(reinterpret_cast<const double2*>(p)); return make_rot<double>(v.x, v.y); }
-
-// queue the units that have a fat step pending; one thread per unit
-template <int L>
-__global__ void rounds_enqueue_kernel(Problem<double> pr, RoundQueue* q, int* slots, unsigned mask, UnitPark* park, RoundQueue* q_next) {
-    constexpr int G = 32 / L;
-    const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (u == 0 && q_next) { q_next->head = 0; q_next->tail = 0; q_next->remaining = 0; }
-    const long long nunits = (pr.nbatch + G - 1) / G;
-    if (u >= nunits) return;
-    bool any = false;
-    UnitPark up;
-    up.t = 0;
-    for (int g = 0; g < 8; ++g) { up.sp[g] = 0; up.nturn[g] = 0; }
-    up.pad[0] = up.pad[1] = up.pad[2] = 0;
-    for (int g = 0; g < G; ++g) {
-        const long long p = u * G + g;
-        if (p < pr.nbatch) {
-            const PolyRec* r = pr.rec + p;
-            if (r->iterating && r->mode != 0) { any = true; up.sp[g] = r->ls.sp; }
-        }
-    }
-    if (!any) return;
-    park[u] = up;
-    __threadfence();
-    atomicAdd(&q->remaining, 1u);
-    const unsigned k = atomicAdd(&q->tail, 1u);
-    atomicExch(slots + (k & mask), (int)u);
-}
-
+// ---------------------------------------------------------------- the persistent kernel
 #ifndef AMRVW_PIPE_MINBLOCKS
 #define AMRVW_PIPE_MINBLOCKS 12
 #endif
-template <int L>
-__global__ void __launch_bounds__(32, AMRVW_PIPE_MINBLOCKS) rounds_phase_b_kernel(Problem<double> pr, RoundQueue* q, int* slots, unsigned mask, UnitPark* park, StepState* parked,
-                                                                                 int seg_steps) {
+template <int L, int MH>
+__global__ void __launch_bounds__(32, AMRVW_PIPE_MINBLOCKS) unit_kernel(Problem<double> pr, PipeParams pp, RoundQueue* q, int* slots, unsigned mask, UnitPark* park, StepState* parked,
+                                                                        int seg_steps) {
     constexpr int G = 32 / L;
     constexpr int NT = 32;
     __shared__ __align__(16) double2 smem_snap[12 * NT + G * 3 * AMRVW_RING];
+    __shared__ ShiftScratch<MH> shift_scratch;
     const int lane32 = threadIdx.x & 31;
     const int grp = lane32 / L, lane = lane32 % L;
     double2* const snap_t = smem_snap + threadIdx.x;                                   // [12][NT] step snapshots
     const unsigned stage_sa = (unsigned)__cvta_generic_to_shared(smem_snap + 12 * NT + grp * (3 * AMRVW_RING));   // look-ahead ring of lane 0
     const unsigned snap_sa = (unsigned)__cvta_generic_to_shared(snap_t);
-    long long pc_all = 0, pc_lean = 0;
+    long long pc_all = 0, pc_lean = 0, pc_a = 0;
     int pn_lean = 0, pn_all = 0, pn_calls = 0, pn_units = 0;
 
     for (;;) {
@@ -255,19 +258,45 @@ __global__ void __launch_bounds__(32, AMRVW_PIPE_MINBLOCKS) rounds_phase_b_kerne
         if (u < 0) break;
         __threadfence();
         const long long pc_u0 = clock64();
+        UnitPark* const up = park + u;
+        const long long p = (long long)u * G + grp;
+        int t0 = __ldcg(&up->t);
+
+        // ---------------- phase A when due
+        if (t0 < 0) {
+            int m0 = 0;
+            if (lane == 0 && p < pr.nbatch) m0 = unit_driver(pr, pp, L, p);
+            __syncwarp();
+            for (int g = 0; g < G; ++g) {
+                const int mg = __shfl_sync(0xffffffffu, m0, g * L);
+                if (mg == 3) unit_shifts<MH>(pr, pp, L, (long long)u * G + g, shift_scratch, lane32);
+            }
+            pc_a += clock64() - pc_u0;
+            if (!__any_sync(0xffffffffu, m0 != 0)) {   // every polynomial of the unit is finished
+                if (lane32 == 0) atomicSub(&q->remaining, 1u);
+                continue;
+            }
+            if (lane == 0) {
+                int sp0 = 0;
+                if (m0 != 0) sp0 = __ldcg(&pr.rec[p].ls.sp);
+                __stcg(&up->sp[grp], sp0); __stcg(&up->nturn[grp], 0);
+            }
+            __syncwarp();
+            t0 = 0;
+        }
 
         // ---------------- the unit's fat steps (every lane of a group reads the same record)
-        const long long p = (long long)u * G + grp;
         int mode = 0, nb = 0, start = 1, stop = 0, ord0 = 0, N = 0;
         if (p < pr.nbatch) {
             const PolyRec* r = pr.rec + p;
-            if (r->iterating) { mode = r->mode; nb = r->nb; start = r->ls.ctr.start_index; stop = r->ls.ctr.stop_index; ord0 = r->ls.ord; N = r->N; }
+            if (__ldcg(&r->iterating)) {
+                mode = __ldcg(&r->mode); nb = __ldcg(&r->nb); start = __ldcg(&r->ls.ctr.start_index); stop = __ldcg(&r->ls.ctr.stop_index);
+                ord0 = __ldcg(&r->ls.ord); N = __ldcg(&r->N);
+            }
         }
         const bool act = mode != 0;
         const int T = act ? (stop - start + 3 * L + 1) : 0;
         const int Tmax = __reduce_max_sync(0xffffffffu, T);
-        UnitPark* const up = park + u;
-        const int t0 = __ldcg(&up->t);
         const int t1 = min(Tmax, t0 + seg_steps);
         int sp = __ldcg(&up->sp[grp]);
         int nturn = 0;
@@ -288,10 +317,10 @@ __global__ void __launch_bounds__(32, AMRVW_PIPE_MINBLOCKS) rounds_phase_b_kerne
             q0 = q1 = q2 = b0 = b1 = b2 = c0 = c1 = c2 = U = V = W = make_rot<double>(1.0, 0.0);
         } else {
             const StepState* z = parked + ((long long)u * 32 + lane32);
-            q0 = ld_cg_rot(&z->q0); q1 = ld_cg_rot(&z->q1); q2 = ld_cg_rot(&z->q2);
-            b0 = ld_cg_rot(&z->b0); b1 = ld_cg_rot(&z->b1); b2 = ld_cg_rot(&z->b2);
-            c0 = ld_cg_rot(&z->c0); c1 = ld_cg_rot(&z->c1); c2 = ld_cg_rot(&z->c2);
-            U = ld_cg_rot(&z->U); V = ld_cg_rot(&z->V); W = ld_cg_rot(&z->W);
+            q0 = ldcg_rot(&z->q0); q1 = ldcg_rot(&z->q1); q2 = ldcg_rot(&z->q2);
+            b0 = ldcg_rot(&z->b0); b1 = ldcg_rot(&z->b1); b2 = ldcg_rot(&z->b2);
+            c0 = ldcg_rot(&z->c0); c1 = ldcg_rot(&z->c1); c2 = ldcg_rot(&z->c2);
+            U = ldcg_rot(&z->U); V = ldcg_rot(&z->V); W = ldcg_rot(&z->W);
         }
         const bool has_bulge = act && lane < nb;
         if (act && lane == 0) {
@@ -371,7 +400,7 @@ __global__ void __launch_bounds__(32, AMRVW_PIPE_MINBLOCKS) rounds_phase_b_kerne
         for (int d = L / 2; d >= 1; d >>= 1) nturn += __shfl_down_sync(0xffffffffu, nturn, d, L);
         pn_all += t1 - t0; pn_units += 1;
         if (t1 < Tmax) {
-            // ---------------- park the unit and hand it back
+            // ---------------- park the lanes' state
             StepState* z = parked + ((long long)u * 32 + lane32);
             st_cg_rot(&z->q0, q0); st_cg_rot(&z->q1, q1); st_cg_rot(&z->q2, q2);
             st_cg_rot(&z->b0, b0); st_cg_rot(&z->b1, b1); st_cg_rot(&z->b2, b2);
@@ -379,31 +408,33 @@ __global__ void __launch_bounds__(32, AMRVW_PIPE_MINBLOCKS) rounds_phase_b_kerne
             st_cg_rot(&z->U, U); st_cg_rot(&z->V, V); st_cg_rot(&z->W, W);
             if (lane == 0) { __stcg(&up->sp[grp], sp); __stcg(&up->nturn[grp], __ldcg(&up->nturn[grp]) + nturn); }
             if (lane32 == 0) __stcg(&up->t, t1);
-            __threadfence();
-            __syncwarp();
-            if (lane32 == 0) {
-                const unsigned k = atomicAdd(&q->tail, 1u);
-                atomicExch(slots + (k & mask), u);
-            }
         } else {
-            // ---------------- fat step through: back to the record for phase A
+            // ---------------- fat step through: back to the record, phase A is due
             if (act && lane == 0) {
                 PolyRec* r = pr.rec + p;
-                r->ls.sp = sp;
-                r->st.sweeps += nb;
-                r->chase_turnovers += nturn + __ldcg(&up->nturn[grp]);
-                if (mode == 2) { r->st.exceptional += nb; r->ls.ord += nb; r->ls.ctr.it_count = 14; }
+                PolyRec rec = load_rec(r);
+                rec.ls.sp = sp;
+                rec.st.sweeps += nb;
+                rec.chase_turnovers += nturn + __ldcg(&up->nturn[grp]);
+                if (mode == 2) { rec.st.exceptional += nb; rec.ls.ord += nb; rec.ls.ctr.it_count = 14; }
+                store_rec(r, rec);
             }
-            __threadfence();
-            __syncwarp();
-            if (lane32 == 0) atomicSub(&q->remaining, 1u);
+            if (lane32 == 0) __stcg(&up->t, -1);
+        }
+        // ---------------- hand the unit back
+        __threadfence();
+        __syncwarp();
+        if (lane32 == 0) {
+            const unsigned k = atomicAdd(&q->tail, 1u);
+            atomicExch(slots + (k & mask), u);
         }
         pc_all += clock64() - pc_u0;
     }
     if (pr.prof && lane32 == 0) {
         atomicAdd(pr.prof + 0, (unsigned long long)pc_all);
+        atomicAdd(pr.prof + 1, (unsigned long long)pc_a);
         atomicAdd(pr.prof + 2, (unsigned long long)pc_lean);
-        atomicAdd(pr.prof + 3, (unsigned long long)(pc_all - pc_lean));
+        atomicAdd(pr.prof + 3, (unsigned long long)(pc_all - pc_lean - pc_a));
         atomicAdd(pr.prof + 4, (unsigned long long)pn_lean);
         atomicAdd(pr.prof + 5, (unsigned long long)(pn_all - pn_lean));
         atomicAdd(pr.prof + 6, (unsigned long long)pn_calls);
@@ -414,9 +445,9 @@ __global__ void __launch_bounds__(32, AMRVW_PIPE_MINBLOCKS) rounds_phase_b_kerne
 // ---------------------------------------------------------------- small windows
 // SM: largest window (rotators) this instantiation stages in per-thread local memory
 template <int SM>
-__global__ void __launch_bounds__(64) rounds_small_kernel(Problem<double> pr, unsigned nwin) {
+__global__ void __launch_bounds__(64) rounds_small_kernel(Problem<double> pr) {
     const unsigned w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= nwin) return;
+    if (w >= pr.counters[CNT_SMALL]) return;
     const SmallWin sw = reinterpret_cast<const SmallWin*>(pr.swlist)[w];
     const long long p = sw.poly;
     const PolyRec* r = pr.rec + p;
@@ -489,25 +520,8 @@ __global__ void __launch_bounds__(256) rounds_finish_kernel(Problem<double> pr, 
 }
 
 // ---------------------------------------------------------------- host side
-struct RoundsTimes { float setup_ms, a_ms, b_ms, small_ms, finish_ms; int rounds; unsigned small_windows; };
-
+struct RoundsTimes { float setup_ms, main_ms, small_ms, finish_ms; };
 struct QueueBufs { RoundQueue* q; int* slots; unsigned mask; UnitPark* park; StepState* parked; };
-
-template <int L>
-static cudaError_t launch_phase_b(const Problem<double>& pr, const QueueBufs& qb, int round, int seg_steps, int sm_count, cudaStream_t st) {
-    constexpr int G = 32 / L;
-    const long long nunits = (pr.nbatch + G - 1) / G;
-    RoundQueue* q = qb.q + (round & 1);
-    RoundQueue* q_next = qb.q + ((round + 1) & 1);
-    int* slots = qb.slots + (size_t)(round & 1) * (qb.mask + 1);
-    rounds_enqueue_kernel<L><<<(int)((nunits + 127) / 128), 128, 0, st>>>(pr, q, slots, qb.mask, qb.park, q_next);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    const long long resident = (long long)sm_count * AMRVW_PIPE_MINBLOCKS;
-    const int blocks = (int)(nunits < resident ? nunits : resident);
-    rounds_phase_b_kernel<L><<<blocks, 32, 0, st>>>(pr, q, slots, qb.mask, qb.park, qb.parked, seg_steps);
-    return cudaGetLastError();
-}
 
 // Chooses L (bulges in flight per polynomial) from the degree and the batch: enough lanes to fill the
 // GPU, not more than the windows can feed (a fat step needs a window > small >= 2L/reuse).
@@ -532,77 +546,59 @@ static void choose_pipe_params(const amrvw_options& opt, long long nbatch, int m
     pp.mh = mshift;
 }
 
-// Runs the whole schedule on `st`.  h_counters: pinned host words for the round counters.  Blocks the
-// host once per chunk of rounds (the termination test needs the device's count of pending fat steps).
-static cudaError_t launch_rounds_rds(Problem<double> pr, const amrvw_options& opt, int max_len, int sm_count, cudaStream_t st, int* launches,
-                                     unsigned* h_counters, unsigned* d_round_active, int max_rounds, cudaEvent_t* ev, RoundsTimes* times, const QueueBufs& qb) {
+template <int L, int MH>
+static cudaError_t launch_units(const Problem<double>& pr, const PipeParams& pp, const QueueBufs& qb, int seg_steps, int sm_count, cudaStream_t st) {
+    constexpr int G = 32 / L;
+    const long long nunits = (pr.nbatch + G - 1) / G;
+    unit_enqueue_kernel<L><<<(int)((nunits + 127) / 128), 128, 0, st>>>(pr, qb.q, qb.slots, qb.mask, qb.park);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, unit_kernel<L, MH>, 32, 0)) != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    const long long resident = (long long)sm_count * per_sm;     // every warp of the grid must be resident: they wait on each other
+    const int blocks = (int)(nunits < resident ? nunits : resident);
+    unit_kernel<L, MH><<<blocks, 32, 0, st>>>(pr, pp, qb.q, qb.slots, qb.mask, qb.park, qb.parked, seg_steps);
+    return cudaGetLastError();
+}
+template <int L>
+static cudaError_t launch_units_mh(const Problem<double>& pr, const PipeParams& pp, const QueueBufs& qb, int seg_steps, int sm_count, cudaStream_t st) {
+    if (pp.mh <= 16) return launch_units<L, 16>(pr, pp, qb, seg_steps, sm_count, st);
+    if (pp.mh <= 32) return launch_units<L, 32>(pr, pp, qb, seg_steps, sm_count, st);
+    return launch_units<L, 64>(pr, pp, qb, seg_steps, sm_count, st);
+}
+
+// Queues the whole schedule on `st`: set-up, the persistent unit kernel, small windows, finish.
+// Nothing here waits for the device unless `times` is asked for.
+static cudaError_t launch_rounds_rds(Problem<double> pr, const amrvw_options& opt, int max_len, long long total, int sm_count, cudaStream_t st, int* launches, cudaEvent_t* ev,
+                                     RoundsTimes* times, const QueueBufs& qb) {
     int L; PipeParams pp;
     choose_pipe_params(opt, pr.nbatch, max_len, sm_count, L, pp);
     cudaError_t e;
-    const int nb32 = (int)((pr.nbatch + 31) / 32), nb64 = (int)((pr.nbatch + 63) / 64);
+    const int nb64 = (int)((pr.nbatch + 63) / 64);
     if ((e = cudaMemsetAsync(pr.counters, 0, CNT_WORDS * sizeof(unsigned), st)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(d_round_active, 0, (size_t)max_rounds * sizeof(unsigned), st)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(qb.q, 0, 2 * sizeof(RoundQueue), st)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(qb.slots, 0xFF, 2 * (size_t)(qb.mask + 1) * sizeof(int), st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(qb.q, 0, sizeof(RoundQueue), st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(qb.slots, 0xFF, (size_t)(qb.mask + 1) * sizeof(int), st)) != cudaSuccess) return e;
     static const int seg_env = std::getenv("AMRVW_SEG_STEPS") ? std::atoi(std::getenv("AMRVW_SEG_STEPS")) : 0;   // development knob
-    const int seg_steps = seg_env > 0 ? seg_env : 64;
-    if (times) { *times = RoundsTimes{0, 0, 0, 0, 0, 0, 0}; cudaEventRecord(ev[0], st); }
+    const int seg_steps = seg_env > 0 ? seg_env : 128;
+    if (times) cudaEventRecord(ev[0], st);
     rounds_setup_kernel<<<nb64, 64, 0, st>>>(pr);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    *launches += 1;
     if (times) cudaEventRecord(ev[1], st);
-    // kernel attributes of phase B (dynamic shared memory is small; nothing to opt into)
-    const int chunk = 8;
-    int round = 0;
-    bool done = false;
-    float a_ms = 0.f, b_ms = 0.f;
-    while (!done && round < max_rounds) {
-        const int r0 = round;
-        for (int k = 0; k < chunk && round < max_rounds; ++k, ++round) {
-            if (times) cudaEventRecord(ev[2 + 3 * k], st);
-            rounds_phase_a_kernel<<<nb32, 32, 0, st>>>(pr, pp, L, d_round_active + round);
-            if ((e = cudaGetLastError()) != cudaSuccess) return e;
-            if (pp.mh <= 16) rounds_shift_kernel<16, 4><<<(int)((pr.nbatch + 3) / 4), 128, 0, st>>>(pr, pp, L);
-            else if (pp.mh <= 32) rounds_shift_kernel<32, 2><<<(int)((pr.nbatch + 1) / 2), 64, 0, st>>>(pr, pp, L);
-            else rounds_shift_kernel<64, 1><<<(int)pr.nbatch, 32, 0, st>>>(pr, pp, L);
-            if ((e = cudaGetLastError()) != cudaSuccess) return e;
-            if (times) cudaEventRecord(ev[3 + 3 * k], st);
-            switch (L) {
-                case 4: e = launch_phase_b<4>(pr, qb, round, seg_steps, sm_count, st); break;
-                case 8: e = launch_phase_b<8>(pr, qb, round, seg_steps, sm_count, st); break;
-                case 16: e = launch_phase_b<16>(pr, qb, round, seg_steps, sm_count, st); break;
-                default: e = launch_phase_b<32>(pr, qb, round, seg_steps, sm_count, st); break;
-            }
-            if (e != cudaSuccess) return e;
-            if (times) cudaEventRecord(ev[4 + 3 * k], st);
-            *launches += 4;
-        }
-        if ((e = cudaMemcpyAsync(h_counters, d_round_active + (round - 1), sizeof(unsigned), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
-        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
-        if (times) {
-            static const bool trace = std::getenv("AMRVW_TRACE_ROUNDS") != nullptr;   // development: per-round kernel times on stderr
-            unsigned act[16] = {0};
-            if (trace) cudaMemcpy(act, d_round_active + r0, (size_t)(round - r0) * sizeof(unsigned), cudaMemcpyDeviceToHost);
-            for (int k = 0; k < round - r0; ++k) {
-                float ms = 0.f, ms2 = 0.f;
-                cudaEventElapsedTime(&ms, ev[2 + 3 * k], ev[3 + 3 * k]); a_ms += ms;
-                cudaEventElapsedTime(&ms2, ev[3 + 3 * k], ev[4 + 3 * k]); b_ms += ms2;
-                if (trace) std::fprintf(stderr, "round %d active %u a_ms %.4f b_ms %.4f\n", r0 + k, act[k], ms, ms2);
-            }
-        }
-        if (h_counters[0] == 0) done = true;
+    switch (L) {
+        case 4: e = launch_units_mh<4>(pr, pp, qb, seg_steps, sm_count, st); break;
+        case 8: e = launch_units_mh<8>(pr, pp, qb, seg_steps, sm_count, st); break;
+        case 16: e = launch_units_mh<16>(pr, pp, qb, seg_steps, sm_count, st); break;
+        default: e = launch_units_mh<32>(pr, pp, qb, seg_steps, sm_count, st); break;
     }
-    // deferred small windows
-    if ((e = cudaMemcpyAsync(h_counters, pr.counters + CNT_SMALL, sizeof(unsigned), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
-    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
-    const unsigned nwin = h_counters[0];
+    if (e != cudaSuccess) return e;
     if (times) cudaEventRecord(ev[2], st);
-    if (nwin > 0) {
-        const int blocks = (int)((nwin + 63) / 64);
-        if (pp.small <= 32) rounds_small_kernel<32><<<blocks, 64, 0, st>>>(pr, nwin);
-        else rounds_small_kernel<96><<<blocks, 64, 0, st>>>(pr, nwin);
+    {   // deferred small windows: the grid covers the queue's capacity, the kernel reads the count
+        const long long cap = total / 3 + pr.nbatch + 16;
+        const int blocks = (int)((cap + 63) / 64);
+        if (pp.small <= 32) rounds_small_kernel<32><<<blocks, 64, 0, st>>>(pr);
+        else rounds_small_kernel<96><<<blocks, 64, 0, st>>>(pr);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        *launches += 1;
     }
     if (times) cudaEventRecord(ev[3], st);
     {
@@ -610,16 +606,16 @@ static cudaError_t launch_rounds_rds(Problem<double> pr, const amrvw_options& op
         const size_t smem = (size_t)smem_elems * sizeof(cplx);
         if ((e = cudaFuncSetAttribute(rounds_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
         rounds_finish_kernel<<<(int)pr.nbatch, 256, smem, st>>>(pr, smem_elems);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    *launches += 1;
+    *launches += 5;
     if (times) {
         cudaEventRecord(ev[4], st);
         if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
         cudaEventElapsedTime(&times->setup_ms, ev[0], ev[1]);
+        cudaEventElapsedTime(&times->main_ms, ev[1], ev[2]);
         cudaEventElapsedTime(&times->small_ms, ev[2], ev[3]);
         cudaEventElapsedTime(&times->finish_ms, ev[3], ev[4]);
-        times->a_ms = a_ms; times->b_ms = b_ms; times->rounds = round; times->small_windows = nwin;
     }
     return cudaSuccess;
 }

@@ -75,8 +75,8 @@ class Context:
         """Warp-cycle accounting of the last pipelined RDS call made with stats (amrvw_last_profile)."""
         out = (ctypes.c_int64 * 16)()
         self._check(self._lib.amrvw_last_profile(self._h, out))
-        keys = ("cycles_phase_b", "_1", "cycles_lean", "cycles_general", "steps_lean", "steps_general", "lean_calls", "warp_launches",
-                "us_setup", "us_phase_a", "us_phase_b", "us_small", "us_finish", "rounds", "small_windows")
+        keys = ("cycles_units", "cycles_phase_a", "cycles_lean", "cycles_general", "steps_lean", "steps_general", "lean_calls", "unit_visits",
+                "us_setup", "us_main", "_10", "us_small", "us_finish", "_13", "small_windows")
         return {k: int(out[i]) for i, k in enumerate(keys)}
 
     # -- host buffers (CSR) in, host buffers out
