@@ -334,7 +334,7 @@ int amrvw_last_profile(amrvw_ctx* ctx, int64_t* out16) {
     CUDA_TRY(ctx, cudaMemcpyAsync(out16, ctx->prof.ptr, 16 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     // kernel times of the unit schedule, microseconds
-    out16[8] = (int64_t)(ctx->times.setup_ms * 1e3); out16[9] = (int64_t)(ctx->times.main_ms * 1e3);
+    out16[8] = (int64_t)(ctx->times.setup_ms * 1e3); out16[9] = (int64_t)(ctx->times.main_ms * 1e3);   // [10] driver cycles, [13] pop cycles stay as counted
     out16[11] = (int64_t)(ctx->times.small_ms * 1e3); out16[12] = (int64_t)(ctx->times.finish_ms * 1e3);
     {
         unsigned cnt[CNT_WORDS];

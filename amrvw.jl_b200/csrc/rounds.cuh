@@ -182,32 +182,32 @@ AMRVW_NI int unit_driver(const Problem<double>& pr, const PipeParams pp, const i
     store_rec(pr.rec + p, rec);
     return mode;
 }
-// Part 2, the shifts of a pending fat step (mode 3), the whole warp on one polynomial: stage the
+// Part 2, the shifts of a pending fat step (mode 3), each lane group on its own polynomial: stage the
 // trailing block's rotators, write the block out densely, Hessenberg QR with the lanes sharing rows
 // and columns (shifts.cuh), pair the shifts.
 template <int MH>
-AMRVW_NI void unit_shifts(const Problem<double>& pr, const PipeParams pp, const int L, const long long p, ShiftScratch<MH>& ws, const int lane) {
+AMRVW_NI void unit_shifts(const Problem<double>& pr, const PipeParams pp, const int L, const long long p, ShiftScratch<MH>& ws, const int lane, const unsigned gmask) {
     constexpr int LDH = MH + 1;
     PolyRec rec = load_rec(pr.rec + p);
     const int m = rec.nb, stop = rec.ls.ctr.stop_index, k0 = stop - m, M = m + 1;
     Fact<double, false> F = make_fact<double, false>(pr, p, rec.N);
-    __syncwarp();
+    __syncwarp(gmask);
     // staged copy with global indices: slot t <-> index k0 + t
-    for (int t = lane; t <= m + 1; t += 32) {
+    for (int t = lane; t <= m + 1; t += L) {
         ws.q[t] = ldcg_rot(F.Q + k0 + t); ws.b[t] = ldcg_rot(F.B + k0 + t); ws.c[t] = ldcg_rot(F.Ct + k0 + t);
     }
-    __syncwarp();
+    __syncwarp(gmask);
     if (lane == 0) {
         const double sg = sign_(ws.q[0].c);
         ws.q[0] = make_rot<double>(sg == 0.0 ? 1.0 : sg, 0.0);
     }
-    __syncwarp();
+    __syncwarp(gmask);
     bool ok = false;
     if (pp.dense) {
-        dense_trailing_block_warp(ws.q - k0, ws.b - k0, ws.c - k0, k0, stop, ws.H, LDH, ws.isg, M, lane);
-        ok = hqr_eigenvalues_warp(ws.H, LDH, M, ws.e, lane);
+        dense_trailing_block_warp(ws.q - k0, ws.b - k0, ws.c - k0, k0, stop, ws.H, LDH, ws.isg, M, lane, gmask, L);
+        ok = hqr_eigenvalues_warp(ws.H, LDH, M, ws.e, lane, gmask, L);
     }
-    __syncwarp();
+    __syncwarp(gmask);
     if (lane == 0) {
         if (!ok) {   // core-chasing iteration on the staged copy (also AMRVW_SHIFTS_CHASE)
             Fact<double, false> W = F;
@@ -218,7 +218,7 @@ AMRVW_NI void unit_shifts(const Problem<double>& pr, const PipeParams pp, const 
         rec.mode = 1;
         store_rec(pr.rec + p, rec);
     }
-    __syncwarp();
+    __syncwarp(gmask);
 }
 
 // ---------------------------------------------------------------- the persistent kernel
@@ -231,17 +231,18 @@ __global__ void __launch_bounds__(32, AMRVW_PIPE_MINBLOCKS) unit_kernel(Problem<
     constexpr int G = 32 / L;
     constexpr int NT = 32;
     __shared__ __align__(16) double2 smem_snap[12 * NT + G * 3 * AMRVW_RING];
-    __shared__ ShiftScratch<MH> shift_scratch;
+    __shared__ ShiftScratch<MH> shift_scratch[G];
     const int lane32 = threadIdx.x & 31;
     const int grp = lane32 / L, lane = lane32 % L;
     double2* const snap_t = smem_snap + threadIdx.x;                                   // [12][NT] step snapshots
     const unsigned stage_sa = (unsigned)__cvta_generic_to_shared(smem_snap + 12 * NT + grp * (3 * AMRVW_RING));   // look-ahead ring of lane 0
     const unsigned snap_sa = (unsigned)__cvta_generic_to_shared(snap_t);
-    long long pc_all = 0, pc_lean = 0, pc_a = 0;
+    long long pc_all = 0, pc_lean = 0, pc_a = 0, pc_drv = 0, pc_pop = 0;
     int pn_lean = 0, pn_all = 0, pn_calls = 0, pn_units = 0;
 
     for (;;) {
         // ---------------- pop a unit
+        const long long pc_p0 = clock64();
         int u = -1;
         if (lane32 == 0) {
             const unsigned k = atomicAdd(&q->head, 1u);
@@ -258,6 +259,7 @@ __global__ void __launch_bounds__(32, AMRVW_PIPE_MINBLOCKS) unit_kernel(Problem<
         if (u < 0) break;
         __threadfence();
         const long long pc_u0 = clock64();
+        pc_pop += pc_u0 - pc_p0;
         UnitPark* const up = park + u;
         const long long p = (long long)u * G + grp;
         int t0 = __ldcg(&up->t);
@@ -267,9 +269,12 @@ __global__ void __launch_bounds__(32, AMRVW_PIPE_MINBLOCKS) unit_kernel(Problem<
             int m0 = 0;
             if (lane == 0 && p < pr.nbatch) m0 = unit_driver(pr, pp, L, p);
             __syncwarp();
-            for (int g = 0; g < G; ++g) {
-                const int mg = __shfl_sync(0xffffffffu, m0, g * L);
-                if (mg == 3) unit_shifts<MH>(pr, pp, L, (long long)u * G + g, shift_scratch, lane32);
+            pc_drv += clock64() - pc_u0;
+            {   // the groups compute their shifts side by side
+                const int mg = __shfl_sync(0xffffffffu, m0, grp * L);
+                const unsigned gmask = (L == 32 ? 0xffffffffu : ((1u << L) - 1u)) << (grp * L);
+                if (mg == 3) unit_shifts<MH>(pr, pp, L, p, shift_scratch[grp], lane, gmask);
+                __syncwarp();
             }
             pc_a += clock64() - pc_u0;
             if (!__any_sync(0xffffffffu, m0 != 0)) {   // every polynomial of the unit is finished
@@ -439,6 +444,8 @@ __global__ void __launch_bounds__(32, AMRVW_PIPE_MINBLOCKS) unit_kernel(Problem<
         atomicAdd(pr.prof + 5, (unsigned long long)(pn_all - pn_lean));
         atomicAdd(pr.prof + 6, (unsigned long long)pn_calls);
         atomicAdd(pr.prof + 7, (unsigned long long)pn_units);
+        atomicAdd(pr.prof + 10, (unsigned long long)pc_drv);
+        atomicAdd(pr.prof + 13, (unsigned long long)pc_pop);
     }
 }
 
@@ -563,9 +570,13 @@ static cudaError_t launch_units(const Problem<double>& pr, const PipeParams& pp,
 }
 template <int L>
 static cudaError_t launch_units_mh(const Problem<double>& pr, const PipeParams& pp, const QueueBufs& qb, int seg_steps, int sm_count, cudaStream_t st) {
+    // the trailing block has order 2L/reuse <= 2L: only those scratch sizes exist
     if (pp.mh <= 16) return launch_units<L, 16>(pr, pp, qb, seg_steps, sm_count, st);
-    if (pp.mh <= 32) return launch_units<L, 32>(pr, pp, qb, seg_steps, sm_count, st);
-    return launch_units<L, 64>(pr, pp, qb, seg_steps, sm_count, st);
+    if constexpr (L >= 16) {
+        if (pp.mh <= 32) return launch_units<L, 32>(pr, pp, qb, seg_steps, sm_count, st);
+    }
+    if constexpr (L >= 32) return launch_units<L, 64>(pr, pp, qb, seg_steps, sm_count, st);
+    return cudaErrorInvalidValue;
 }
 
 // Queues the whole schedule on `st`: set-up, the persistent unit kernel, small windows, finish.
@@ -580,7 +591,7 @@ static cudaError_t launch_rounds_rds(Problem<double> pr, const amrvw_options& op
     if ((e = cudaMemsetAsync(qb.q, 0, sizeof(RoundQueue), st)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(qb.slots, 0xFF, (size_t)(qb.mask + 1) * sizeof(int), st)) != cudaSuccess) return e;
     static const int seg_env = std::getenv("AMRVW_SEG_STEPS") ? std::atoi(std::getenv("AMRVW_SEG_STEPS")) : 0;   // development knob
-    const int seg_steps = seg_env > 0 ? seg_env : 128;
+    const int seg_steps = seg_env > 0 ? seg_env : 512;
     if (times) cudaEventRecord(ev[0], st);
     rounds_setup_kernel<<<nb64, 64, 0, st>>>(pr);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;

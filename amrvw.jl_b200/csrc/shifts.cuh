@@ -185,18 +185,20 @@ AMRVW_DI bool hqr_eigenvalues(double* H, int M, cplx* E) {
     return true;
 }
 
-// ---------------------------------------------------------------- one warp per block (rounds schedule)
-// The same two routines with the lanes of a warp sharing the work: every lane executes the scalar
+// ---------------------------------------------------------------- one lane group per block (unit schedule)
+// The same two routines with a group of GL lanes of a warp (GL = 4..32, mask gmask, lane = index in
+// the group) sharing the work; the groups of a warp run their blocks side by side.  Within a group: every lane executes the scalar
 // control flow on the same shared-memory values (no divergence, no communication), the entries are
 // written / the rows and columns are updated one per lane.  Each entry sees exactly the arithmetic of
 // the sequential routine above, so the strict build stays bit-identical to the oracle.
 // H has leading dimension LD >= M (LD = M + 1 keeps column accesses off a single bank).
-AMRVW_DI void dense_trailing_block_warp(const Rot<double>* q, const Rot<double>* b, const Rot<double>* c, int k0, int stop, double* H, int LD, double* isg, int M, int lane) {
+AMRVW_DI void dense_trailing_block_warp(const Rot<double>* q, const Rot<double>* b, const Rot<double>* c, int k0, int stop, double* H, int LD, double* isg, int M, int lane,
+                                        const unsigned gmask, const int GL) {
     const int j0 = k0 + 1;
-    for (int i = lane; i < M * LD; i += 32) H[i] = 0.0;
-    for (int j = j0 + lane; j <= stop + 1; j += 32) isg[j - j0] = rcp_(c[j].s);
-    __syncwarp();
-    for (int k = j0 + lane; k <= stop + 1; k += 32) {
+    for (int i = lane; i < M * LD; i += GL) H[i] = 0.0;
+    for (int j = j0 + lane; j <= stop + 1; j += GL) isg[j - j0] = rcp_(c[j].s);
+    __syncwarp(gmask);
+    for (int k = j0 + lane; k <= stop + 1; k += GL) {
         double P = 1.0, T = 0.0, Vacc = 0.0;
         const double ck = b[k].c, sk = b[k].s;
         for (int j = k; j >= j0; --j) {
@@ -212,27 +214,28 @@ AMRVW_DI void dense_trailing_block_warp(const Rot<double>* q, const Rot<double>*
         }
         H[k - j0] = q[k0].c * Vacc;
     }
-    __syncwarp();
+    __syncwarp(gmask);
 }
 
-AMRVW_DI bool hqr_eigenvalues_warp(double* H, const int LD, const int M, cplx* E, const int lane) {
+AMRVW_DI bool hqr_eigenvalues_warp(double* H, const int LD, const int M, cplx* E, const int lane, const unsigned gmask, const int GL) {
+    const int gbase = __ffs(gmask) - 1;   // first lane of the group
 #define AMRVW_H(i, j) H[(i) * LD + (j)]
     double norm = 0.0;
     if (lane == 0) {   // sequential sum: the value must not depend on the number of lanes
         for (int i = 0; i < M; ++i)
             for (int j = (i > 0 ? i - 1 : 0); j < M; ++j) norm += fabs(AMRVW_H(i, j));
     }
-    norm = __shfl_sync(0xffffffffu, norm, 0);
+    norm = __shfl_sync(gmask, norm, gbase);
     int en = M - 1, itn = 30 * M;
     double t = 0.0;
     while (en >= 0) {
         int its = 0;
         const int na = en - 1, enm2 = na - 1;
         for (;;) {
-            __syncwarp();
+            __syncwarp(gmask);
             // highest l in 1..en with a negligible subdiagonal entry, 0 if none
             int l = 0;
-            for (int base = (en / 32) * 32; base >= 0 && l == 0; base -= 32) {
+            for (int base = (en / GL) * GL; base >= 0 && l == 0; base -= GL) {
                 const int lc = base + lane;
                 bool small = false;
                 if (lc >= 1 && lc <= en) {
@@ -241,8 +244,8 @@ AMRVW_DI bool hqr_eigenvalues_warp(double* H, const int LD, const int M, cplx* E
                     const double tst2 = s + fabs(AMRVW_H(lc, lc - 1));
                     small = (tst2 == s);
                 }
-                const unsigned mask = __ballot_sync(0xffffffffu, small);
-                if (mask) l = base + 31 - __clz(mask);
+                const unsigned mask = __ballot_sync(gmask, small) & gmask;
+                if (mask) l = base + (31 - __clz(mask)) - gbase;
             }
             double x = AMRVW_H(en, en);
             if (l == en) { if (lane == 0) E[en] = cplx(x + t, 0.0); en = na; break; }
@@ -270,9 +273,9 @@ AMRVW_DI bool hqr_eigenvalues_warp(double* H, const int LD, const int M, cplx* E
             if (itn == 0) return false;
             if (its == 10 || its == 20) {
                 t += x;
-                __syncwarp();
-                for (int i = lane; i <= en; i += 32) AMRVW_H(i, i) -= x;
-                __syncwarp();
+                __syncwarp(gmask);
+                for (int i = lane; i <= en; i += GL) AMRVW_H(i, i) -= x;
+                __syncwarp(gmask);
                 const double s = fabs(AMRVW_H(en, na)) + fabs(AMRVW_H(na, enm2));
                 x = 0.75 * s; y = x; w = -0.4375 * s * s;
             }
@@ -287,10 +290,10 @@ AMRVW_DI bool hqr_eigenvalues_warp(double* H, const int LD, const int M, cplx* E
                 const double is = rcp_(fabs(p) + fabs(q) + fabs(r));
                 p = p * is; q = q * is; r = r * is;
             }
-            __syncwarp();
-            for (int i = l + 2 + lane; i <= en; i += 32) { AMRVW_H(i, i - 2) = 0.0; if (i != l + 2) AMRVW_H(i, i - 3) = 0.0; }
+            __syncwarp(gmask);
+            for (int i = l + 2 + lane; i <= en; i += GL) { AMRVW_H(i, i - 2) = 0.0; if (i != l + 2) AMRVW_H(i, i - 3) = 0.0; }
             for (int k = l; k <= na; ++k) {
-                __syncwarp();
+                __syncwarp(gmask);
                 const bool notlas = (k != na);
                 double xs = 0.0;
                 if (k != l) {
@@ -302,7 +305,7 @@ AMRVW_DI bool hqr_eigenvalues_warp(double* H, const int LD, const int M, cplx* E
                 }
                 double s = sqrt_(p * p + q * q + r * r);
                 if (p < 0.0) s = -s;
-                __syncwarp();   // every lane has read column k-1 before it is overwritten
+                __syncwarp(gmask);   // every lane has read column k-1 before it is overwritten
                 if (k != l && lane == 0) AMRVW_H(k, k - 1) = -s * xs;
                 p = p + s;
                 const double is = rcp_(s), ip = rcp_(p);
@@ -310,25 +313,25 @@ AMRVW_DI bool hqr_eigenvalues_warp(double* H, const int LD, const int M, cplx* E
                 q = q * ip; r = r * ip;
                 const int ihi = min(en, k + 3);
                 if (notlas) {
-                    for (int j = k + lane; j <= en; j += 32) {
+                    for (int j = k + lane; j <= en; j += GL) {
                         const double a0 = AMRVW_H(k, j), a1 = AMRVW_H(k + 1, j), a2 = AMRVW_H(k + 2, j);
                         const double pp = a0 + q * a1 + r * a2;
                         AMRVW_H(k, j) = a0 - pp * hx; AMRVW_H(k + 1, j) = a1 - pp * hy; AMRVW_H(k + 2, j) = a2 - pp * hz;
                     }
-                    __syncwarp();
-                    for (int i = l + lane; i <= ihi; i += 32) {
+                    __syncwarp(gmask);
+                    for (int i = l + lane; i <= ihi; i += GL) {
                         const double a0 = AMRVW_H(i, k), a1 = AMRVW_H(i, k + 1), a2 = AMRVW_H(i, k + 2);
                         const double pp = hx * a0 + hy * a1 + hz * a2;
                         AMRVW_H(i, k) = a0 - pp; AMRVW_H(i, k + 1) = a1 - pp * q; AMRVW_H(i, k + 2) = a2 - pp * r;
                     }
                 } else {
-                    for (int j = k + lane; j <= en; j += 32) {
+                    for (int j = k + lane; j <= en; j += GL) {
                         const double a0 = AMRVW_H(k, j), a1 = AMRVW_H(k + 1, j);
                         const double pp = a0 + q * a1;
                         AMRVW_H(k, j) = a0 - pp * hx; AMRVW_H(k + 1, j) = a1 - pp * hy;
                     }
-                    __syncwarp();
-                    for (int i = l + lane; i <= ihi; i += 32) {
+                    __syncwarp(gmask);
+                    for (int i = l + lane; i <= ihi; i += GL) {
                         const double a0 = AMRVW_H(i, k), a1 = AMRVW_H(i, k + 1);
                         const double pp = hx * a0 + hy * a1;
                         AMRVW_H(i, k) = a0 - pp; AMRVW_H(i, k + 1) = a1 - pp * q;
@@ -338,11 +341,11 @@ AMRVW_DI bool hqr_eigenvalues_warp(double* H, const int LD, const int M, cplx* E
         }
     }
 #undef AMRVW_H
-    __syncwarp();
+    __syncwarp(gmask);
     bool ok = true;
-    for (int i = lane; i < M; i += 32)
+    for (int i = lane; i < M; i += GL)
         if (!(isfinite(E[i].re) && isfinite(E[i].im))) ok = false;
-    return __all_sync(0xffffffffu, ok);
+    return __all_sync(gmask, ok);
 }
 
 // one out-of-line copy: formation + hqr

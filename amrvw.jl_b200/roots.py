@@ -76,7 +76,7 @@ class Context:
         out = (ctypes.c_int64 * 16)()
         self._check(self._lib.amrvw_last_profile(self._h, out))
         keys = ("cycles_units", "cycles_phase_a", "cycles_lean", "cycles_general", "steps_lean", "steps_general", "lean_calls", "unit_visits",
-                "us_setup", "us_main", "_10", "us_small", "us_finish", "_13", "small_windows")
+                "us_setup", "us_main", "cycles_driver", "us_small", "us_finish", "cycles_pop", "small_windows")
         return {k: int(out[i]) for i, k in enumerate(keys)}
 
     # -- host buffers (CSR) in, host buffers out

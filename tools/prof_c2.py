@@ -26,3 +26,5 @@ tot = max(pf["cycles_units"], 1)
 print("  unit kernel: busy warp-cycles %.3e (phase A %.1f%%, lean %.1f%%, general %.1f%%); lean steps %d (%.0f cyc/step)  general steps %d (%.0f cyc/step)  visits %d" % (
     tot, 100.0 * pf["cycles_phase_a"] / tot, 100.0 * pf["cycles_lean"] / tot, 100.0 * pf["cycles_general"] / tot,
     pf["steps_lean"], pf["cycles_lean"] / max(pf["steps_lean"], 1), pf["steps_general"], pf["cycles_general"] / max(pf["steps_general"], 1), pf["unit_visits"]))
+print("  phase A split: driver %.1f%% of busy cycles, shifts %.1f%%; waiting in pop: %.3e warp-cycles (%.1f%% of busy)" % (
+    100.0 * pf["cycles_driver"] / tot, 100.0 * (pf["cycles_phase_a"] - pf["cycles_driver"]) / tot, pf["cycles_pop"], 100.0 * pf["cycles_pop"] / tot))
