@@ -336,11 +336,6 @@ int amrvw_last_profile(amrvw_ctx* ctx, int64_t* out16) {
     // kernel times of the unit schedule, microseconds
     out16[8] = (int64_t)(ctx->times.setup_ms * 1e3); out16[9] = (int64_t)(ctx->times.main_ms * 1e3);   // [10] driver cycles, [13] pop cycles stay as counted
     out16[11] = (int64_t)(ctx->times.small_ms * 1e3); out16[12] = (int64_t)(ctx->times.finish_ms * 1e3);
-    {
-        unsigned cnt[CNT_WORDS];
-        CUDA_TRY(ctx, cudaMemcpy(cnt, ctx->counters.ptr, sizeof(cnt), cudaMemcpyDeviceToHost));
-        out16[14] = cnt[CNT_SMALL];
-    }
     return AMRVW_OK;
 }
 

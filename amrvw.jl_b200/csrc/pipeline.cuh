@@ -124,16 +124,16 @@ AMRVW_NI void chase_step_general(StepState& z) {
 }
 // last position (j == stop): passthrough_triu, then fuse the bulge into Q (RDS.jl:110-128)
 AMRVW_DI void chase_step_final(StepState& z, double pbot) {
-    turnover(z.b1, z.b2, z.V, z.V, z.b1, z.b2);
-    turnover(z.c2, z.c1, z.V, z.V, z.c2, z.c1);
-    turnover(z.b0, z.b1, z.U, z.U, z.b0, z.b1);
-    turnover(z.c1, z.c0, z.U, z.U, z.c1, z.c0);
+    turnover_fast(z.b1, z.b2, z.V, z.V, z.b1, z.b2);
+    turnover_fast(z.c2, z.c1, z.V, z.V, z.c2, z.c1);
+    turnover_fast(z.b0, z.b1, z.U, z.U, z.b0, z.b1);
+    turnover_fast(z.c1, z.c0, z.U, z.U, z.c1, z.c0);
     z.V.s = sign_(pbot) * z.V.s;
     z.q1 = fuse(z.q1, z.V);
-    turnover(z.q0, z.q1, z.U, z.U, z.q0, z.q1);
+    turnover_fast(z.q0, z.q1, z.U, z.U, z.q0, z.q1);
     z.U = fuse(z.W, z.U);
-    turnover(z.b1, z.b2, z.U, z.U, z.b1, z.b2);
-    turnover(z.c2, z.c1, z.U, z.U, z.c2, z.c1);
+    turnover_fast(z.b1, z.b2, z.U, z.U, z.b1, z.b2);
+    turnover_fast(z.c2, z.c1, z.U, z.U, z.c2, z.c1);
     z.U.s = sign_(pbot) * z.U.s;
     z.q1 = fuse(z.q1, z.U);
 }
@@ -231,6 +231,61 @@ AMRVW_NI void bulge_step_window(Fact<double, false>& F, Counter& ctr, const Shif
 
 // create_bulge (create-bulge.jl:20-77) on the lane's window [start-1 .. start+2] + absorb_Ut
 // (RDS.jl:14-36), out of line: once per bulge per fat step, keeps the chase loop small.
+// Bulge creation with reciprocals instead of divisions.  The bulge rotators only choose WHICH unitary
+// similarity is applied (it is applied exactly, by turnovers), so their last bits steer convergence,
+// not accuracy; the IEEE divisions of the entry formulas made one creation ~7.7 k cycles during which
+// the other 15 lanes of the group wait (12% of the kernel: profiles/).  Same formulas as
+// r1_entry / diagonal_block / create_bulge_rds (solver.cuh); the strict build calls those.
+AMRVW_DI double r1_entry_fast(const Rot<double>* B, const Rot<double>* Ct, const int j, const int k) {
+    const double cj = Ct[j].c;
+    double s = Ct[j].s;
+    double par = -1.0;
+    double tot = w_entry(B, j, k) * rcp_(s);
+    for (int i = j + 1; i <= k; ++i) {
+        const double w = w_entry(B, i, k);
+        s = s * Ct[i].s;
+        tot = tot + par * cj * Ct[i].c * rcp_(s) * w;
+        par = -par;
+    }
+    return tot;
+}
+AMRVW_DI void givensrot_fast(const double a, const double b, double& c, double& s, double& r) {
+    const double x = a * a + b * b;
+    if (x >= 1e-280 && x <= 1e280) {
+        const double ri = rsqrt_nr(x);
+        c = a * ri; s = b * ri; r = x * ri;
+    } else {
+        givensrot(a, b, c, s, r);
+    }
+}
+// lq/lb/lc hold indices start-1 .. start+2 (slot 0 = start-1); shifts e1, e2
+AMRVW_DI void create_bulge_fast(const Rot<double>* lq, const Rot<double>* lb, const Rot<double>* lc, const int start, const Shifts sh, Rot<double>& U, Rot<double>& V) {
+    const Rot<double>* Q = lq - (start - 1);
+    const Rot<double>* B = lb - (start - 1);
+    const Rot<double>* Ct = lc - (start - 1);
+    const int j = start, i = j - 1, k = j + 1;
+    // diagonal block at j (diagonal-block.jl:12-36) and block(j+1).A21
+    const Rot<double> qm = Q[j - 1], q0 = Q[j], qp = Q[j + 1];
+    const double qji = -qm.s, qjj = qm.c * q0.c, qjk = qp.c * q0.s * qm.c, qkj = -q0.s, qkk = q0.c * qp.c;
+    const double rjj = r1_entry_fast(B, Ct, j, j), rjk = r1_entry_fast(B, Ct, j, k), rkk = r1_entry_fast(B, Ct, k, k);
+    double rij = 0.0, rik = 0.0;
+    if (i >= 1) { rij = r1_entry_fast(B, Ct, i, j); rik = r1_entry_fast(B, Ct, i, k); }
+    const double bk11 = qji * rij + qjj * rjj;
+    const double bk12 = qji * rik + qjj * rjk + qjk * rkk;
+    const double bk21 = qkj * rjj;
+    const double bk22 = qkj * rjk + qkk * rkk;
+    const double bk32 = (-Q[j + 1].s) * rkk;
+    const cplx e1 = sh.e1, e2 = sh.e2;
+    const double c1 = -e1.im * e2.im + e1.re * e2.re - e1.re * bk11 - e2.re * bk11 + bk11 * bk11 + bk12 * bk21;
+    const double c2 = -e1.re * bk21 - e2.re * bk21 + bk11 * bk21 + bk21 * bk22;
+    const double c3 = bk21 * bk32;
+    double c, s, nrm, tmp;
+    givensrot_fast(c2, c3, c, s, nrm);
+    V = make_rot<double>(c, -s);
+    givensrot_fast(c1, nrm, c, s, tmp);
+    U = make_rot<double>(c, -s);
+}
+
 AMRVW_DI void create_and_absorb(StepState& z, const Rot<double> qm, const Rot<double> bm, const Rot<double> cm, const Fact<double, false>& F,
                                 int start, int stop, int mode, const Shifts sh, uint64_t seed, uint64_t poly, int ordinal) {
     Rot<double> U, V;
@@ -242,18 +297,23 @@ AMRVW_DI void create_and_absorb(StepState& z, const Rot<double> qm, const Rot<do
         V = make_rot<double>(sn, -cs);
     } else {
         Rot<double> lq[4] = {qm, z.q0, z.q1, z.q2}, lb[4] = {bm, z.b0, z.b1, z.b2}, lc[4] = {cm, z.c0, z.c1, z.c2};
+#ifndef AMRVW_STRICT
+        (void)F; (void)stop;
+        create_bulge_fast(lq, lb, lc, start, sh, U, V);
+#else
         Fact<double, false> Fl = F;
         Fl.Q = lq - (start - 1); Fl.B = lb - (start - 1); Fl.Ct = lc - (start - 1);
         Counter cl = {start - 1, start, stop, 15, -1};
         int dummy = 0;
         PolyStats ds = {0, 0, 0, 0, 0};
         create_bulge_rds(Fl, cl, U, V, &sh, seed, poly, dummy, ds);
+#endif
     }
     const double ptop = sign_(qm.c);
     Rot<double> w = z.q0;
     w.s = sign_(ptop) * w.s;
     Rot<double> r1, r2, r3;
-    turnover(adjoint(U), adjoint(V), w, r1, r2, r3);
+    turnover_fast(adjoint(U), adjoint(V), w, r1, r2, r3);
     z.W = r1;
     z.q1 = fuse(r3, z.q1);
     r2.s = sign_(ptop) * r2.s;

@@ -315,6 +315,29 @@ AMRVW_DI double rsqrt_nr(double x) {
 #endif
 }
 
+// reciprocal and square root where the last bit does not matter (shifts, bulge creation): IEEE in
+// the strict build (bit parity with the oracle), MUFU seed + Newton otherwise -- an FP64 division
+// expands to ~35 dependent instructions, ~300 cycles next to warps that keep the FP64 pipe busy
+AMRVW_DI double rcp_(double x) {
+#ifdef AMRVW_STRICT
+    return 1.0 / x;
+#else
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+#endif
+}
+AMRVW_DI double sqrt_(double x) {
+#ifdef AMRVW_STRICT
+    return sqrt(x);
+#else
+    return x > 0.0 ? x * rsqrt_nr(x) : 0.0;
+#endif
+}
+
 // division-free common path (real); returns false when the caller must take the general path.
 // 31 FP64-pipe instructions + one MUFU: every product is contracted by hand (the reference's
 // formulas, transformations.jl:162-191, with 1/r by rsqrt).  b = s1 s2 / s5 with s5 = -r (1 - h),

@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(32, AMRVW_PIPE_MINBLOCKS) unit_kernel(Problem<
     double2* const snap_t = smem_snap + threadIdx.x;                                   // [12][NT] step snapshots
     const unsigned stage_sa = (unsigned)__cvta_generic_to_shared(smem_snap + 12 * NT + grp * (3 * AMRVW_RING));   // look-ahead ring of lane 0
     const unsigned snap_sa = (unsigned)__cvta_generic_to_shared(snap_t);
-    long long pc_all = 0, pc_lean = 0, pc_a = 0, pc_drv = 0, pc_pop = 0;
+    long long pc_all = 0, pc_lean = 0, pc_a = 0, pc_drv = 0, pc_pop = 0, pc_special = 0, pc_loop = 0;
     int pn_lean = 0, pn_all = 0, pn_calls = 0, pn_units = 0;
 
     for (;;) {
@@ -336,6 +336,7 @@ __global__ void __launch_bounds__(32, AMRVW_PIPE_MINBLOCKS) unit_kernel(Problem<
                 cp_async_commit();
             }
         }
+        const long long pc_lp0 = clock64();
         for (int t = t0; t < t1; ++t) {
             {   // every lane of the warp at a regular position (or idle for good): the lean loop
                 const bool g_dead = !act || t >= T;
@@ -373,10 +374,12 @@ __global__ void __launch_bounds__(32, AMRVW_PIPE_MINBLOCKS) unit_kernel(Problem<
             const int i = start + tp - 2;   // position of this lane's bulge; window = indices i..i+2
             if (has_bulge && tp >= 2 && i <= stop - 1) {
                 if (tp == 2) {
+                    const long long pc_s0 = clock64();
                     StepState z = {q0, q1, q2, b0, b1, b2, c0, c1, c2, U, V, W};
                     create_and_absorb_at(z, F, start, stop, mode, pr.shifts + p * L, lane, pr.seed, (uint64_t)p, ord0 + lane);
                     q0 = z.q0; q1 = z.q1; U = z.U; V = z.V; W = z.W;
                     nturn += 1;
+                    pc_special += clock64() - pc_s0;
                 }
                 if (i <= stop - 2) {
                     // regular position: the 7 turnovers of one chase step (RDS.jl:42-70, 97-108) as ONE
@@ -388,9 +391,11 @@ __global__ void __launch_bounds__(32, AMRVW_PIPE_MINBLOCKS) unit_kernel(Problem<
                     AMRVW_CHASE_GENERAL();
 #endif
                 } else {
+                    const long long pc_s0 = clock64();
                     StepState z = {q0, q1, q2, b0, b1, b2, c0, c1, c2, U, V, W};
                     chase_step_final_at(z, F, stop);
                     q0 = z.q0; q1 = z.q1; q2 = z.q2; b0 = z.b0; b1 = z.b1; b2 = z.b2; c0 = z.c0; c1 = z.c1; c2 = z.c2; U = z.U; V = z.V; W = z.W;
+                    pc_special += clock64() - pc_s0;
                 }
                 nturn += 7;
             }
@@ -400,6 +405,7 @@ __global__ void __launch_bounds__(32, AMRVW_PIPE_MINBLOCKS) unit_kernel(Problem<
                 if (i <= stop && fabs(q0.s) <= AMRVW_EPS) dstack[sp++] = i;   // deflatable: record for phase A
             }
         }
+        pc_loop += clock64() - pc_lp0;
         if (lane == 0) cp_async_wait_all();   // drain look-ahead requests past the end of the segment
         sp = __shfl_sync(0xffffffffu, sp, grp * L + L - 1);
         for (int d = L / 2; d >= 1; d >>= 1) nturn += __shfl_down_sync(0xffffffffu, nturn, d, L);
@@ -446,6 +452,12 @@ __global__ void __launch_bounds__(32, AMRVW_PIPE_MINBLOCKS) unit_kernel(Problem<
         atomicAdd(pr.prof + 7, (unsigned long long)pn_units);
         atomicAdd(pr.prof + 10, (unsigned long long)pc_drv);
         atomicAdd(pr.prof + 13, (unsigned long long)pc_pop);
+        atomicAdd(pr.prof + 14, (unsigned long long)pc_loop);
+    }
+    if (pr.prof) {   // per-lane time in bulge creation / last-position steps (the lanes take them one at a time)
+        unsigned long long v = (unsigned long long)pc_special;
+        for (int d = 16; d >= 1; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+        if (lane32 == 0) atomicAdd(pr.prof + 15, v);
     }
 }
 

@@ -21,28 +21,6 @@
 
 namespace amrvw {
 
-// reciprocal and square root of the shift solver: IEEE in the strict build (bit parity with the
-// oracle), MUFU seed + Newton otherwise (an FP64 division expands to ~30 dependent instructions)
-AMRVW_DI double rcp_(double x) {
-#ifdef AMRVW_STRICT
-    return 1.0 / x;
-#else
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
-    return fma(y, e, y);
-#endif
-}
-AMRVW_DI double sqrt_(double x) {
-#ifdef AMRVW_STRICT
-    return sqrt(x);
-#else
-    return x > 0.0 ? x * rsqrt_nr(x) : 0.0;
-#endif
-}
-
 // H: M x M row-major scratch; isg: M + 1 doubles scratch; q/b/c: staged rotators with GLOBAL indices
 // (q[k0 .. stop+1], b/c[k0+1 .. stop+1] valid), q[k0] already made diagonal.
 AMRVW_DI void dense_trailing_block(const Rot<double>* q, const Rot<double>* b, const Rot<double>* c, int k0, int stop, double* H, double* isg, int M) {

@@ -76,7 +76,7 @@ class Context:
         out = (ctypes.c_int64 * 16)()
         self._check(self._lib.amrvw_last_profile(self._h, out))
         keys = ("cycles_units", "cycles_phase_a", "cycles_lean", "cycles_general", "steps_lean", "steps_general", "lean_calls", "unit_visits",
-                "us_setup", "us_main", "cycles_driver", "us_small", "us_finish", "cycles_pop", "small_windows")
+                "us_setup", "us_main", "cycles_driver", "us_small", "us_finish", "cycles_pop", "cycles_loop", "lane_cycles_special")
         return {k: int(out[i]) for i, k in enumerate(keys)}
 
     # -- host buffers (CSR) in, host buffers out
