@@ -365,7 +365,9 @@ AMRVW_DI bool turnover_fast_try(const Rot<double> q1, const Rot<double> q2, cons
     r1 = make_rot<double>(c4, s4);
     r2 = make_rot<double>(u11 * rho5, -(r4 * rho5));
     r3 = make_rot<double>(a * rho6, b * rho6);
-    return x >= 1e-280;   // also false for NaN
+    // x in [2^-930, inf): tested on the high word in the integer pipe (a DSETP would take an FP64 issue
+    // slot in a loop that is bound by that pipe); false for 0, denormals, inf and NaN
+    return (unsigned)(__double2hiint(x) - 0x05d00000) < (0x7ff00000u - 0x05d00000u);
 }
 AMRVW_DI void turnover_fast(const Rot<double> q1, const Rot<double> q2, const Rot<double> q3, Rot<double>& r1, Rot<double>& r2, Rot<double>& r3) {
 #ifdef AMRVW_STRICT

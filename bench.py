@@ -39,6 +39,7 @@ CONFIGS = {
 }
 FLOP_PER_TURNOVER = {"rds_f64": 37.0, "css_c64": 94.0, "pencil_f64": 37.0}
 BYTES_PER_TURNOVER = {"rds_f64": 96.0 / 7, "css_c64": 208.0 / 3, "pencil_f64": 160.0 / 11}
+NCU_TRAFFIC_C2 = 143.5e9   # dram read 62.9 GB + write 80.6 GB: profiles/r01_c2_unit_kernel_ncu_full_keymetrics.csv (ncu --set full, default c2 launch)
 
 
 def parse():
@@ -219,6 +220,7 @@ def main():
     for _ in range(max(args.warmup, 1)):
         st = step(stats=True)           # warm-up also yields the per-step counters (launches, turnovers)
     torch.cuda.synchronize()
+    prof = ctx.last_profile() if kind == "rds_f64" and args.schedule != 1 else None   # per-kernel CUDA-event times of the last warm-up step
     n_unconv = int(d_u.sum().item())
     nroots_ok = int(d_n.sum().item())
 
@@ -287,27 +289,37 @@ def main():
     executed = st["turnovers"]
     useful_per_poly = cb["turnovers_per_poly"] if cb else None
     useful = useful_per_poly * batch if useful_per_poly else executed
-    kernel_ms = st["device_ms"]
+    # dominant kernel: the persistent unit kernel (phase A + systolic chase) for the pipelined RDS path, the
+    # one iteration kernel otherwise; its duration is the CUDA-event time of that launch in the last warm-up step
+    if prof and prof["us_main"] > 0:
+        kernel_ms, kernel_name = prof["us_main"] / 1e3, "unit_kernel<L,MH> (phase A + systolic chase behind the unit queue)"
+    else:
+        kernel_ms, kernel_name = st["device_ms"], "roots_reference_kernel / roots_pencil_reference_kernel (one polynomial per thread)"
     flops = useful * FLOP_PER_TURNOVER[kind]
-    tf = flops / (ms_step * 1e-3) / 1e12
+    tf = flops / (kernel_ms * 1e-3) / 1e12
     hbm_peak, hbm_src = 6650.0, "fallback"
     try:
         mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         hbm_peak, hbm_src = float(mp["hbm_gbs"]), "measured"
     except Exception:
         pass
-    gbs = useful * BYTES_PER_TURNOVER[kind] / (ms_step * 1e-3) / 1e9
-    # dram__bytes_read.sum + dram__bytes_write.sum of the kernel from the committed ncu --set full capture
-    # (profiles/r01_c2_pipelined_ncu_full_keymetrics.csv); only valid for the default c2 launch
-    traffic = 138.6e9 if (args.config == "c2" and not args.batch and not args.degree and not args.lanes) else None
+    gbs = useful * BYTES_PER_TURNOVER[kind] / (kernel_ms * 1e-3) / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed ncu --set full capture
+    # (profiles/r01_c2_unit_kernel_ncu_full_keymetrics.csv); only valid for the default c2 launch
+    traffic = NCU_TRAFFIC_C2 if (args.config == "c2" and not args.batch and not args.degree and not args.lanes) else None
     roofline = {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak, "traffic": traffic,
-                "traffic_note": "bytes per launch (ncu dram read+write); the reference-schedule algorithmic bytes (96 B per chase step per bulge) are 12x larger: the systolic chase reuses each rotator for L bulges",
+                "traffic_note": "bytes per launch (ncu dram read+write); the reference-schedule algorithmic bytes (96 B per chase step per bulge) are ~12x larger: the systolic chase streams each rotator once per 16 bulges",
                 "peak_source": "DFMA probe measured live in this run (MEASURED_PEAKS.json has no FP64 entry); nominal 37.2",
-                "kernel": "the one kernel of the step (device_ms of one warm-up step: %.2f ms)" % kernel_ms,
+                "kernel": kernel_name, "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / st["device_ms"] if st["device_ms"] else None,
                 "useful_turnovers_per_step": useful, "executed_turnovers_per_step": executed,
-                "useful_definition": "the reference schedule's turnover count on the same inputs (CPU sample mean x batch) x 37 flop",
+                "useful_definition": "the reference schedule's turnover count on the same inputs (CPU sample mean x batch) x 37 flop (94 complex)",
                 "hbm": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": hbm_src + " copy bandwidth",
                         "note": "algorithmic bytes = 96 B per 7 turnovers; the path is not HBM-bound"}}
+    if prof:
+        busy = max(prof["cycles_units"], 1)
+        roofline["warp_cycle_shares"] = {"phase_a": prof["cycles_phase_a"] / busy, "lean_chase": prof["cycles_lean"] / busy, "fill_drain_chase": prof["cycles_general"] / busy,
+                                         "queue_wait_vs_busy": prof["cycles_pop"] / busy, "lean_cycles_per_step": prof["cycles_lean"] / max(prof["steps_lean"], 1)}
+        roofline["kernel_times_ms"] = {"setup": prof["us_setup"] / 1e3, "unit_kernel": prof["us_main"] / 1e3, "small_windows": prof["us_small"] / 1e3, "finish": prof["us_finish"] / 1e3}
     line = {"metric": "polynomials/sec", "value": value, "unit": "polynomials/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config, "turnovers_per_sec": world * useful / (ms_step * 1e-3), "roofline": roofline, "cpu_baseline": cb, "e2e": e2e,
