@@ -1464,6 +1464,25 @@ int orc_eigvals(double* state, int N, int is_complex, int pencil, double* eig_re
     return (int)st.unconverged;
 }
 
+// Multishift schedule pieces on a flat real state, window [ctr.start, ctr.stop]: the (m+1) x (m+1)
+// dense trailing block (row major, Q[stop-m] made diagonal) and its eigenvalues by the Hessenberg QR
+// (dense_reim) and by the core-chasing sub-solve (chase_reim) -- what a fat step's shifts come from.
+int orc_ms_shift_check(const double* state, int N, const int32_t* ctr5, int m, double* H, double* dense_reim, double* chase_reim) {
+    State<double> s; flat_to_state(state, N, 0, s);
+    Counter c = {ctr5[0], ctr5[1], ctr5[2], ctr5[3], ctr5[4]};
+    const int stop = c.stop_index, k0 = stop - m, M = m + 1;
+    std::vector<double> Hm;
+    dense_trailing_block(s, k0, stop, Hm, M);
+    for (int i = 0; i < M * M; ++i) H[i] = Hm[i];
+    std::vector<cplx> E;
+    const bool ok = hqr_eigenvalues(Hm, M, E);
+    for (int i = 0; i < M; ++i) { dense_reim[2 * i] = E[i].re; dense_reim[2 * i + 1] = E[i].im; }
+    std::vector<cplx> sh; Rng rng; Stats sub;
+    ms_shifts(s, c, m, sh, rng, sub);
+    for (int i = 0; i < M; ++i) { chase_reim[2 * i] = sh[i].re; chase_reim[2 * i + 1] = sh[i].im; }
+    return ok ? 0 : 1;
+}
+
 // Synthetic inputs shared by every leg: kind 0 = N(0,1) (Box-Muller), 1 = U[0,1),
 // 2 = U[0,1) - 1/2.  Writes `count` doubles for polynomial `poly`.
 void orc_fill_coeffs(uint64_t seed, uint64_t poly, int kind, int64_t count, double* out) {

@@ -212,6 +212,14 @@ class FlatState:
         lib().orc_bulge_step(_p(self.buf), self.N, int(self.cx), int(self.pencil), _p(c), ctypes.c_uint64(seed))
         return [int(x) for x in c]
 
+    def ms_shift_check(self, ctr, m):
+        """Dense trailing block of the window ctr (order m+1), its eigenvalues by the Hessenberg QR and by the core-chasing sub-solve."""
+        c = np.array(ctr, dtype=np.int32)
+        M = m + 1
+        H = np.zeros(M * M); d = np.zeros(2 * M); e = np.zeros(2 * M)
+        rc = lib().orc_ms_shift_check(_p(self.buf), self.N, _p(c), int(m), _p(H), _p(d), _p(e))
+        return H.reshape(M, M), d[0::2] + 1j * d[1::2], e[0::2] + 1j * e[1::2], rc
+
     def eigvals(self, seed=0):
         out = np.zeros(2 * self.N)
         unconv = lib().orc_eigvals(_p(self.buf), self.N, int(self.cx), int(self.pencil), _p(out), ctypes.c_uint64(seed))

@@ -376,6 +376,57 @@ def test_multishift_schedule_same_roots(oracle):
             assert np.sum(r1.imag == 0) == np.sum(r0.imag == 0)
 
 
+def test_dense_trailing_block_and_hessenberg_qr(oracle):
+    """The shifts of a fat step (oracle ms_shifts_dense = GPU shifts.cuh): the trailing block written out
+    entry by entry must equal the dense matrix of the factorization, and the Hessenberg QR must find
+    its eigenvalues (numpy) -- which are also what the core-chasing sub-solve returns."""
+    rng = np.random.default_rng(7)
+    for n, m in ((40, 7), (64, 15), (90, 31)):
+        p = rng.standard_normal(n + 1)
+        st = oracle.FlatState(ps=p)
+        ctr = [0, 1, n - 1, 15, -1]
+        for _ in range(6):                    # a few ordinary sweeps so that the block is not the initial companion
+            ctr = st.bulge_step(ctr)
+            ctr[3] = 15
+        H, dense, chase, rc = st.ms_shift_check(ctr, m)
+        assert rc == 0
+        stop, k0 = ctr[2], ctr[2] - m
+        A = st.dense()                          # slot k <-> row k-1
+        blk = A[k0:stop + 1, k0:stop + 1].copy()
+        # Q[k0] is made diagonal for the shifts: that only rescales the first row by 1/|c_k0| and drops what
+        # couples the block to the rows above it, so compare everything except the first row
+        assert np.allclose(H[1:, :], blk[1:, :], rtol=1e-9, atol=1e-11)
+        assert np.allclose(np.tril(H, -2), 0.0)
+        ev = np.linalg.eigvals(H)
+        d, _ = match_roots(dense, ev)
+        assert d.max() < 1e-9 * max(1.0, np.abs(ev).max())
+        d, _ = match_roots(dense, chase)
+        assert d.max() < 1e-8 * max(1.0, np.abs(ev).max())
+        # conjugate pairs come out adjacent and exactly conjugate (the pairing of the real double shift relies on it)
+        k = 0
+        while k < len(dense):
+            if dense[k].imag != 0:
+                assert dense[k + 1] == np.conj(dense[k]); k += 2
+            else:
+                k += 1
+
+
+def test_multishift_dense_shifts_same_roots(oracle):
+    rng = np.random.default_rng(43)
+    for n in (120, 400):
+        p = rng.standard_normal(n + 1)
+        r0, s0 = oracle.roots(p)
+        for L, reuse in ((8, 2), (16, 2), (16, 1), (32, 4)):
+            small = max(24, 2 * L // reuse + 8)
+            r1, s1 = oracle.roots(p, sched=1, L=L, small=small, reuse=reuse, dense=1)
+            r2, s2 = oracle.roots(p, sched=1, L=L, small=small, reuse=reuse, dense=0)
+            d, _ = match_roots(r1, r0)
+            assert s1["unconverged"] == 0 and d.max() < 1e-10
+            assert np.sum(r1.imag == 0) == np.sum(r0.imag == 0)
+            assert abs(s1["fat_steps"] - s2["fat_steps"]) <= max(3, s2["fat_steps"] // 10)     # same convergence as the sub-solve's shifts
+            assert s1["serial_turnovers"] < s2["serial_turnovers"]
+
+
 def test_readme_statistic_miniature(oracle):
     """README.md:121-127 in miniature: mean number of exactly-real roots of randn polynomials
     against the Kac-type formula (count(imag == 0) semantics of real_polynomial_roots)."""
