@@ -5,6 +5,7 @@
 #include "kernels.cuh"
 #include "pipeline.cuh"
 #include "rounds.cuh"
+#include "css_units.cuh"
 
 #include <cstdio>
 #include <cstring>
@@ -170,7 +171,7 @@ static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, cons
         for (int c = 0; c < nd; ++c) { int rc = reserve(ctx, ctx->diags[c], slots * sizeof(S)); if (rc) return rc; }
     }
     { int rc = reserve(ctx, ctx->stats, (size_t)nbatch * sizeof(PolyStats) + sizeof(StatsAccum)); if (rc) return rc; }
-    if (var == V_RDS) { int rc = reserve(ctx, ctx->shifts, slots * sizeof(int)); if (rc) return rc; }
+    if (var == V_RDS || var == V_CSS) { int rc = reserve(ctx, ctx->shifts, slots * sizeof(int)); if (rc) return rc; }
 
     Problem<S> pr;
     pr.coeffs = d_a; pr.ws = d_w; pr.offsets = (const long long*)d_offsets; pr.nbatch = nbatch;
@@ -181,7 +182,7 @@ static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, cons
     pr.DQ = (S*)ctx->diags[0].ptr; pr.DR = (S*)ctx->diags[1].ptr; pr.WD = (S*)ctx->diags[2].ptr;
     pr.dstack = (int*)ctx->shifts.ptr;
     pr.prof = nullptr; pr.rec = nullptr; pr.shifts = nullptr; pr.swlist = nullptr; pr.counters = nullptr;
-    if (var == V_RDS && stats) {   // warp-cycle counters ride along with the statistics
+    if (var == V_RDS && stats) {   // warp-cycle counters ride along with the statistics (real path)
         int rc = reserve(ctx, ctx->prof, 16 * sizeof(unsigned long long)); if (rc) return rc;
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->prof.ptr, 0, 16 * sizeof(unsigned long long), ctx->stream));
         pr.prof = (unsigned long long*)ctx->prof.ptr;
@@ -216,6 +217,27 @@ static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, cons
             pr.rec = (PolyRec*)ctx->rec.ptr; pr.shifts = (Shifts*)ctx->fatshifts.ptr; pr.swlist = ctx->swlist.ptr; pr.counters = (unsigned*)ctx->counters.ptr;
             cudaError_t e = launch_rounds_rds(pr, ctx->opt, (int)max_len, (long long)total, ctx->sm_count, st, &launches, ctx->evpool, stats ? &ctx->times : nullptr, qb);
             if (e != cudaSuccess) return fail(ctx, AMRVW_ERR_CUDA, std::string("unit schedule: ") + cudaGetErrorString(e));
+            done = true;
+        }
+    }
+    if constexpr (!is_real<S>::value) {
+        if (var == V_CSS && ctx->opt.schedule != AMRVW_SCHEDULE_REFERENCE) {
+            int rc;
+            if ((rc = reserve(ctx, ctx->rec, (size_t)nbatch * sizeof(PolyRec)))) return rc;
+            if ((rc = reserve(ctx, ctx->fatshifts, (size_t)nbatch * 32 * sizeof(Shifts)))) return rc;
+            if ((rc = reserve(ctx, ctx->swlist, ((size_t)total / 3 + (size_t)nbatch + 16) * sizeof(SmallWin)))) return rc;
+            if ((rc = reserve(ctx, ctx->counters, CNT_WORDS * sizeof(unsigned)))) return rc;
+            const size_t max_units = (size_t)nbatch;
+            size_t qcap = 1024;
+            while (qcap < 2 * max_units + 4096) qcap <<= 1;
+            if ((rc = reserve(ctx, ctx->queue, sizeof(RoundQueue)))) return rc;
+            if ((rc = reserve(ctx, ctx->qslots, qcap * sizeof(int)))) return rc;
+            if ((rc = reserve(ctx, ctx->park, max_units * sizeof(UnitPark)))) return rc;
+            if ((rc = reserve(ctx, ctx->parked, max_units * 32 * sizeof(CssLane)))) return rc;
+            pr.rec = (PolyRec*)ctx->rec.ptr; pr.shifts = (Shifts*)ctx->fatshifts.ptr; pr.swlist = ctx->swlist.ptr; pr.counters = (unsigned*)ctx->counters.ptr;
+            cudaError_t e = launch_css_pipelined(pr, ctx->opt, (int)max_len, (long long)total, ctx->sm_count, st, &launches, (RoundQueue*)ctx->queue.ptr, (int*)ctx->qslots.ptr,
+                                                 (unsigned)(qcap - 1), (UnitPark*)ctx->park.ptr, (CssLane*)ctx->parked.ptr);
+            if (e != cudaSuccess) return fail(ctx, AMRVW_ERR_CUDA, std::string("complex unit schedule: ") + cudaGetErrorString(e));
             done = true;
         }
     }

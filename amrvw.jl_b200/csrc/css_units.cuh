@@ -1,0 +1,628 @@
+// css_units.cuh -- complex single shift (CSS.jl) on the unit queue: pipelined multishift chase.
+//
+// Same architecture as the RDS path (rounds.cuh): work units (one warp = 32/L polynomials) circulate
+// through a device-side FIFO; a visit runs phase A when the unit's fat step is through (driver on
+// lane 0 of each group, then the L shifts of the next fat step) and then up to SEG lock-steps of the
+// systolic chase of L bulges, one per lane.
+//
+// What is different for the complex single shift (reference: CSS.jl, bulge-step.jl:22-33):
+//   * a bulge is ONE rotator U at position i and touches indices i, i+1 of Q, B, Ct and of the two
+//     phase diagonals D_Q, D_R, so bulges TWO indices apart commute; a lane holds a 2-index window
+//     (13 doubles per index) and per step does the two diagonal swaps (diagonal.jl:84-96) and the three
+//     turnovers of passthrough_triu / passthrough_Q (CSS.jl:17-41, 64-88);
+//   * absorb_Ut (CSS.jl:8-14) fuses the new rotator into Q[start] and pushes the resulting phase down
+//     the WHOLE Q chain (diagonal.jl:199-225: every Q[k].c, k > start, is multiplied by conj(alpha) until
+//     an exact zero sine, where the phase lands in D_Q) -- an O(window) sweep per bulge that would
+//     serialise the pipeline.  Here the phase travels with its bulge: lane m multiplies every Q rotator
+//     it ingests by its own conj(alpha_m), exactly when the sequential order would have (after bulge
+//     m-1 is through with that index, before bulge m's turnover on it), and deposits it in D_Q at the
+//     first zero sine / the end of the window.  The push-down costs one complex multiplication per
+//     lock-step instead of a pass over memory;
+//   * shifts: the L eigenvalues of the trailing block come from the core-chasing iteration on a
+//     shared-memory copy (lane 0 of the group); the turnover is the IEEE one.  Both are the obvious
+//     next steps (dense complex Hessenberg QR shared by the lanes, division-free complex turnover).
+//
+// Roots agree with the reference schedule to backward-error level (tests: minimum-distance matching
+// against the oracle); there is no bit-level twin of this schedule in the oracle yet.
+#pragma once
+#include "rounds.cuh"
+
+namespace amrvw {
+
+// one index of the five arrays
+struct CssIdx {
+    Rot<cplx> q, b, c;
+    cplx dq, dr;
+};
+struct CssLane {            // what a lane owns between lock-steps
+    CssIdx w0, w1;          // indices i, i+1 (i = position of the lane's bulge)
+    Rot<cplx> U;            // the bulge
+    cplx ca;                // conj(alpha) of the bulge's creation, still travelling down Q
+    int alive;              // 1 while ca has not been deposited in D_Q
+    int pad[3];
+};
+static_assert(sizeof(CssLane) % 16 == 0, "CssLane is parked in 16-byte words");
+
+AMRVW_DI Rot<cplx> ldcg_crot(const Rot<cplx>* p) {
+    const double2 a = __ldcg(reinterpret_cast<const double2*>(p)), b = __ldcg(reinterpret_cast<const double2*>(p) + 1);
+    Rot<cplx> r;
+    r.c = cplx(a.x, a.y); r.s = b.x; r.pad = 0.0;
+    return r;
+}
+AMRVW_DI cplx ldcg_cplx(const cplx* p) {
+    const double2 a = __ldcg(reinterpret_cast<const double2*>(p));
+    return cplx(a.x, a.y);
+}
+AMRVW_DI CssIdx css_load_index(const Fact<cplx, false>& F, const int k) {
+    CssIdx x;
+    x.q = ldcg_crot(F.Q + k); x.b = ldcg_crot(F.B + k); x.c = ldcg_crot(F.Ct + k);
+    x.dq = ldcg_cplx(F.DQ + k); x.dr = ldcg_cplx(F.DR + k);
+    return x;
+}
+AMRVW_DI void css_store_index(const Fact<cplx, false>& F, const int k, const CssIdx& x) {
+    F.Q[k] = x.q; F.B[k] = x.b; F.Ct[k] = x.c; F.DQ[k] = x.dq; F.DR[k] = x.dr;
+}
+AMRVW_DI CssIdx css_shfl_up(const CssIdx& x, const int width) {
+    CssIdx o;
+    const double* src = reinterpret_cast<const double*>(&x);
+    double* dst = reinterpret_cast<double*>(&o);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(CssIdx) / 8); ++i) dst[i] = __shfl_up_sync(0xffffffffu, src[i], 1, width);
+    return o;
+}
+AMRVW_DI CssIdx css_identity_index() {
+    CssIdx x;
+    x.q = make_rot<cplx>(cplx(1.0, 0.0), 0.0); x.b = x.q; x.c = x.q; x.q.pad = x.b.pad = x.c.pad = 0.0;
+    x.dq = cplx(1.0, 0.0); x.dr = cplx(1.0, 0.0);
+    return x;
+}
+
+// diagonal swap (diagonal.jl:84-96): the bulge passes the two phases at i, i+1
+AMRVW_DI void css_pass_diag(cplx& d0, cplx& d1, Rot<cplx>& U) {
+    const cplx alpha = d0, beta = d1;
+    d0 = beta; d1 = alpha;
+    U.c = (alpha * conj_(beta)) * U.c;
+}
+// passthrough_triu (CSS.jl:17-41): U at i right -> left through R = Ct (B D_R)
+AMRVW_DI void css_pass_R(CssIdx& w0, CssIdx& w1, Rot<cplx>& U) {
+    css_pass_diag(w0.dr, w1.dr, U);
+    Rot<cplx> r1, r2, r3;
+    turnover(w0.b, w1.b, U, r1, r2, r3);      // pass_desc on B: U moves to i+1
+    U = r1; w0.b = r2; w1.b = r3;
+    turnover(w1.c, w0.c, U, r1, r2, r3);      // pass_asc on Ct: U back at i
+    U = r1; w1.c = r2; w0.c = r3;
+}
+// regular position (CSS.jl:64-75): through R, then through D_Q and Q; the bulge leaves at i+1
+AMRVW_NI void css_step_regular(CssLane& z) {
+    css_pass_R(z.w0, z.w1, z.U);
+    css_pass_diag(z.w0.dq, z.w1.dq, z.U);
+    Rot<cplx> r1, r2, r3;
+    turnover(z.w0.q, z.w1.q, z.U, r1, r2, r3);
+    z.U = r1; z.w0.q = r2; z.w1.q = r3;
+}
+// last position i == stop (CSS.jl:76-88): through R, through D_Q, fuse into Q[stop]
+AMRVW_NI void css_step_final(CssLane& z) {
+    css_pass_R(z.w0, z.w1, z.U);
+    css_pass_diag(z.w0.dq, z.w1.dq, z.U);
+    cplx dph;
+    z.w0.q = fuse(z.w0.q, z.U, dph);
+    z.w0.dq = z.w0.dq * dph;
+    z.w1.dq = z.w1.dq * conj_(dph);
+}
+// create_bulge (create-bulge.jl:80-118) + absorb_Ut (CSS.jl:8-14) for the lane whose window just became
+// (start, start+1); wm = index start-1 (static during the fat step, read from memory)
+AMRVW_NI void css_create(CssLane& z, const Fact<cplx, false>& F, const int start, const int stop, const cplx shift) {
+    CssIdx wm = css_identity_index();
+    if (start >= 1) {
+        wm.q = ldcg_crot(F.Q + start - 1); wm.dq = ldcg_cplx(F.DQ + start - 1);       // Q[0], D_Q[0] are sentinels
+        if (start > 1) { wm.b = ldcg_crot(F.B + start - 1); wm.c = ldcg_crot(F.Ct + start - 1); wm.dr = ldcg_cplx(F.DR + start - 1); }
+    }
+    Rot<cplx> lq[3] = {wm.q, z.w0.q, z.w1.q}, lb[3] = {wm.b, z.w0.b, z.w1.b}, lc[3] = {wm.c, z.w0.c, z.w1.c};
+    cplx ldq[3] = {wm.dq, z.w0.dq, z.w1.dq}, ldr[3] = {wm.dr, z.w0.dr, z.w1.dr};
+    Fact<cplx, false> Fl = F;
+    Fl.Q = lq - (start - 1); Fl.B = lb - (start - 1); Fl.Ct = lc - (start - 1); Fl.DQ = ldq - (start - 1); Fl.DR = ldr - (start - 1);
+    cplx A[4];
+    diagonal_block(Fl, start, A);
+    cplx c, nrm; double sn;
+    givensrot(A[0] - shift, A[2], c, sn, nrm);
+    const Rot<cplx> R = make_rot<cplx>(c, sn);
+    z.U = adjoint(R);
+    cplx dph;
+    z.w0.q = fuse(R, z.w0.q, dph);
+    // push_phase (diagonal.jl:199-225), first two actions; the rest travels with the bulge
+    z.w0.dq = z.w0.dq * dph;
+    z.ca = conj_(dph);
+    z.alive = 1;
+    if (start + 1 > stop || z.w1.q.s == 0.0) { z.w1.dq = z.w1.dq * z.ca; z.alive = 0; }
+    else z.w1.q.c = z.ca * z.w1.q.c;
+}
+
+// ---------------------------------------------------------------- phase A of a complex unit
+AMRVW_DI void css_diagonal_block_cg(const Fact<cplx, false>& F, const int j, cplx A[4]) {
+    Rot<cplx> lq[3], lb[3], lc[3];
+    cplx ldq[3], ldr[3];
+    for (int t = 0; t < 3; ++t) {
+        const int k = j - 1 + t;
+        lq[t] = ldcg_crot(F.Q + k); ldq[t] = ldcg_cplx(F.DQ + k);
+        if (k >= 1) { lb[t] = ldcg_crot(F.B + k); lc[t] = ldcg_crot(F.Ct + k); ldr[t] = ldcg_cplx(F.DR + k); }
+        else { lb[t] = make_rot<cplx>(cplx(1.0, 0.0), 0.0); lc[t] = lb[t]; ldr[t] = cplx(1.0, 0.0); }
+    }
+    Fact<cplx, false> Fl = F;
+    Fl.Q = lq - (j - 1); Fl.B = lb - (j - 1); Fl.Ct = lc - (j - 1); Fl.DQ = ldq - (j - 1); Fl.DR = ldr - (j - 1);
+    diagonal_block(Fl, j, A);
+}
+// deflate (CSS.jl:98-122) with coherent reads: Q[k] becomes the identity, its phase goes down Q
+AMRVW_DI void css_deflate_cg(Fact<cplx, false>& F, const int k) {
+    const cplx alpha = ldcg_crot(F.Q + k).c;
+    F.Q[k] = make_rot<cplx>(cplx(1.0, 0.0), 0.0);
+    const int M = F.N - 1;
+    F.DQ[k] = ldcg_cplx(F.DQ + k) * alpha;
+    const cplx ca = conj_(alpha);
+    int i = k;
+    while (i < M) {
+        Rot<cplx> q = ldcg_crot(F.Q + i + 1);
+        if (q.s == 0.0) break;
+        q.c = ca * q.c;
+        F.Q[i + 1] = q;
+        ++i;
+    }
+    F.DQ[i + 1] = ldcg_cplx(F.DQ + i + 1) * ca;
+}
+AMRVW_DI void css_check_deflation_stack(Fact<cplx, false>& F, LeaderState& ls, const int* dstack) {
+    if (ls.sp > 0) {
+        const int k = __ldcg(dstack + ls.sp - 1);
+        if (k >= ls.ctr.start_index && k <= ls.ctr.stop_index) {
+            css_deflate_cg(F, k);
+            ls.ctr.zero_index = k;
+            ls.ctr.start_index = k + 1;
+            ls.ctr.it_count = 15;
+        }
+    }
+}
+// the driver (AMRVW_algorithm.jl:10-138) up to the next fat step: 0 finished, 2 exceptional fat step,
+// 3 fat step that needs nb + 1 shifts (nb = rotators of the trailing block)
+AMRVW_NI int css_unit_driver(const Problem<cplx>& pr, const PipeParams pp, const int L, const long long p) {
+    PolyRec rec = load_rec(pr.rec + p);
+    if (!rec.iterating) return 0;
+    Fact<cplx, false> F = make_fact<cplx, false>(pr, p, rec.N);
+    cplx* E = pr.roots + (pr.offsets[p] - p) - 1;
+    const int* dstack = pr.dstack + (pr.offsets[p] + (long long)pr.extra * p);
+    SmallSink sink;
+    sink.list = pr.swlist; sink.count = pr.counters + CNT_SMALL; sink.poly = (int)p;
+    LeaderState& ls = rec.ls;
+    Counter& ctr = ls.ctr;
+    cplx A[4];
+    int mode = 0, nb = 0;
+    while (ls.kk <= ls.it_max) {
+        if (ctr.stop_index < 1) break;
+        css_check_deflation_stack(F, ls, dstack);
+        ++ls.kk;
+        const int k = ctr.stop_index;
+        const int delta = ctr.stop_index - ctr.zero_index;
+        if (delta == 1) {
+            css_diagonal_block_cg(F, k, A);
+            cplx e1, e2;
+            eig2x2(A, e1, e2);
+            E[k] = e1; E[k + 1] = e2;
+            if (ctr.stop_index == 2) { css_diagonal_block_cg(F, 1, A); E[1] = A[0]; ctr.stop_index = 0; break; }
+            pop_window(ls);
+            ctr.stop_index = ctr.zero_index - 1; ctr.zero_index = 0; ctr.start_index = 1;
+            css_check_deflation_stack(F, ls, dstack);
+            if (ctr.stop_index < 1) break;
+        } else if (delta <= 0) {
+            css_diagonal_block_cg(F, k, A);
+            if (ctr.stop_index == 1) { E[1] = A[0]; E[2] = A[3]; ctr.stop_index = 0; break; }
+            E[k + 1] = A[3];
+            pop_window(ls);
+            ctr.stop_index = ctr.zero_index - 1;
+            if (ctr.stop_index < 1) break;
+            ctr.zero_index = 0; ctr.start_index = 1;
+            css_check_deflation_stack(F, ls, dstack);
+        } else if (delta <= pp.small) {
+            const int lo2 = ctr.start_index, hi2 = ctr.stop_index;
+            sink.push(lo2, hi2, ctr.it_count);
+            if (lo2 == 2) { css_diagonal_block_cg(F, 1, A); E[1] = A[0]; }
+            pop_window(ls);
+            ctr.stop_index = lo2 - 2; ctr.zero_index = 0; ctr.start_index = 1; ctr.it_count = 15;
+            if (ctr.stop_index >= 1) css_check_deflation_stack(F, ls, dstack);
+            ls.pn_small += 1;
+        } else if (ctr.it_count == 0) {
+            rec.st.fat_steps++;
+            nb = L; mode = 2;
+            break;
+        } else {
+            nb = min(L - 1, delta - 1);       // rotators of the trailing block: nb + 1 shifts
+            rec.st.fat_steps++;
+            ctr.it_count -= 1;
+            mode = 3;
+            break;
+        }
+    }
+    rec.mode = mode; rec.nb = nb;
+    if (mode == 0) rec.iterating = 0;
+    store_rec(pr.rec + p, rec);
+    return mode;
+}
+
+// shared-memory scratch of one lane group for the shift sub-solve
+template <int MH> struct __align__(16) CssShiftScratch {
+    Rot<cplx> q[MH + 3], b[MH + 3], c[MH + 3];
+    cplx dq[MH + 3], dr[MH + 3], e[MH + 3];
+};
+// the nb + 1 shifts of a pending fat step: eigenvalues of the trailing block, by the one-bulge iteration
+// on a shared-memory copy whose top rotator is made diagonal (lane 0 of the group; the others stage)
+template <int MH>
+AMRVW_NI void css_unit_shifts(const Problem<cplx>& pr, const int L, const long long p, CssShiftScratch<MH>& ws, const int lane, const unsigned gmask) {
+    PolyRec rec = load_rec(pr.rec + p);
+    const int m = rec.nb, stop = rec.ls.ctr.stop_index, k0 = stop - m;
+    Fact<cplx, false> F = make_fact<cplx, false>(pr, p, rec.N);
+    __syncwarp(gmask);
+    for (int t = lane; t <= m + 1; t += L) {
+        const int k = k0 + t;
+        ws.q[t] = ldcg_crot(F.Q + k); ws.dq[t] = ldcg_cplx(F.DQ + k);
+        if (k >= 1) { ws.b[t] = ldcg_crot(F.B + k); ws.c[t] = ldcg_crot(F.Ct + k); ws.dr[t] = ldcg_cplx(F.DR + k); }
+        else { ws.b[t] = make_rot<cplx>(cplx(1.0, 0.0), 0.0); ws.c[t] = ws.b[t]; ws.dr[t] = cplx(1.0, 0.0); }
+    }
+    __syncwarp(gmask);
+    if (lane == 0) {
+        Fact<cplx, false> W = F;
+        W.Q = ws.q - k0; W.B = ws.b - k0; W.Ct = ws.c - k0; W.DQ = ws.dq - k0; W.DR = ws.dr - k0; W.turnovers = 0;
+        W.N = stop + 1;                       // the copy ends at the window: phase push-downs stop at Q[stop]
+        {   // make Q[k0] diagonal: keep its phase (as deflate does), drop its sine
+            const cplx c0 = W.Q[k0].c;
+            const double a = abs_(c0);
+            W.Q[k0] = make_rot<cplx>(a == 0.0 ? cplx(1.0, 0.0) : c0 / a, 0.0);
+            deflate(W, k0);
+        }
+        cplx* Es = ws.e - (k0 + 1);
+        for (int t = 0; t <= m; ++t) ws.e[t] = cplx(0.0, 0.0);
+        Counter c2 = {k0, k0 + 1, stop, 15, -1};
+        PolyStats sub = {0, 0, 0, 0, 0};
+        drive_window(W, k0 + 1, stop, c2, Es, 20ll * (m + 1), pr.seed, (uint64_t)p, rec.ls.ord, sub, ReferenceStep());
+        rec.serial_turnovers += W.turnovers;
+        Shifts* shl = pr.shifts + p * L;
+        for (int t = 0; t <= m; ++t) { shl[t].e1 = ws.e[t]; shl[t].e2 = cplx(0.0, 0.0); }
+        rec.nb = m + 1;
+        rec.mode = 1;
+        store_rec(pr.rec + p, rec);
+    }
+    __syncwarp(gmask);
+}
+
+// ---------------------------------------------------------------- the persistent kernel
+template <int L, int MH>
+__global__ void __launch_bounds__(32, 8) css_unit_kernel(Problem<cplx> pr, PipeParams pp, RoundQueue* q, int* slots, unsigned mask, UnitPark* park, CssLane* parked, int seg_steps) {
+    constexpr int G = 32 / L;
+    __shared__ CssShiftScratch<MH> shift_scratch[G];
+    const int lane32 = threadIdx.x & 31;
+    const int grp = lane32 / L, lane = lane32 % L;
+
+    for (;;) {
+        // ---------------- pop a unit
+        int u = -1;
+        if (lane32 == 0) {
+            const unsigned k = atomicAdd(&q->head, 1u);
+            int* slot = slots + (k & mask);
+            for (unsigned spins = 0;; ++spins) {
+                u = atomicExch(slot, -1);
+                if (u >= 0) break;
+                if (*reinterpret_cast<volatile unsigned*>(&q->remaining) == 0u) { u = -2; break; }
+                if (spins > (1u << 24)) { u = -3; break; }
+                __nanosleep(500);
+            }
+        }
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u < 0) break;
+        __threadfence();
+        UnitPark* const up = park + u;
+        const long long p = (long long)u * G + grp;
+        int t0 = __ldcg(&up->t);
+
+        // ---------------- phase A when due
+        if (t0 < 0) {
+            int m0 = 0;
+            if (lane == 0 && p < pr.nbatch) m0 = css_unit_driver(pr, pp, L, p);
+            __syncwarp();
+            {
+                const int mg = __shfl_sync(0xffffffffu, m0, grp * L);
+                const unsigned gmask = (L == 32 ? 0xffffffffu : ((1u << L) - 1u)) << (grp * L);
+                if (mg == 3) css_unit_shifts<MH>(pr, L, p, shift_scratch[grp], lane, gmask);
+                __syncwarp();
+            }
+            if (!__any_sync(0xffffffffu, m0 != 0)) {
+                if (lane32 == 0) atomicSub(&q->remaining, 1u);
+                continue;
+            }
+            if (lane == 0) {
+                int sp0 = 0;
+                if (m0 != 0) sp0 = __ldcg(&pr.rec[p].ls.sp);
+                __stcg(&up->sp[grp], sp0); __stcg(&up->nturn[grp], 0);
+            }
+            __syncwarp();
+            t0 = 0;
+        }
+
+        // ---------------- the unit's fat steps
+        int mode = 0, nb = 0, start = 1, stop = 0, ord0 = 0, N = 0;
+        if (p < pr.nbatch) {
+            const PolyRec* r = pr.rec + p;
+            if (__ldcg(&r->iterating)) {
+                mode = __ldcg(&r->mode); nb = __ldcg(&r->nb); start = __ldcg(&r->ls.ctr.start_index); stop = __ldcg(&r->ls.ctr.stop_index);
+                ord0 = __ldcg(&r->ls.ord); N = __ldcg(&r->N);
+            }
+        }
+        const bool act = mode != 0;
+        const int T = act ? (stop - start + 2 * L + 1) : 0;
+        const int Tmax = __reduce_max_sync(0xffffffffu, T);
+        const int t1 = min(Tmax, t0 + seg_steps);
+        int sp = __ldcg(&up->sp[grp]);
+        int nturn = 0;
+        Fact<cplx, false> F;
+        F.Q = F.B = F.Ct = F.WB = F.WCt = nullptr; F.DQ = F.DR = F.WD = nullptr; F.N = N; F.turnovers = 0;
+        int* dstack = nullptr;
+        if (act) {
+            F = make_fact<cplx, false>(pr, p, N);
+            dstack = pr.dstack + (pr.offsets[p] + (long long)pr.extra * p);
+        }
+        CssLane z;
+        if (t0 == 0) {
+            z.w0 = css_identity_index(); z.w1 = z.w0;
+            z.U = make_rot<cplx>(cplx(1.0, 0.0), 0.0); z.U.pad = 0.0;
+            z.ca = cplx(1.0, 0.0); z.alive = 0; z.pad[0] = z.pad[1] = z.pad[2] = 0;
+        } else {
+            const double2* src = reinterpret_cast<const double2*>(parked + ((long long)u * 32 + lane32));
+            double2* dst = reinterpret_cast<double2*>(&z);
+#pragma unroll
+            for (int i = 0; i < (int)(sizeof(CssLane) / 16); ++i) dst[i] = __ldcg(src + i);
+        }
+        const bool has_bulge = act && lane < nb;
+        cplx shift = cplx(0.0, 0.0);
+        if (has_bulge) {
+            if (mode == 2) {   // exceptional: a point on the unit circle (create-bulge.jl:85-93)
+                const double ang = uniform01(pr.seed ^ 0xA5A5A5A5DEADBEEFull, (uint64_t)p, (uint64_t)(ord0 + lane)) * 3.141592653589793;
+                double sn, cs;
+                sincos(ang, &sn, &cs);
+                shift = cplx(cs, sn);
+            } else {
+                shift = ldcg_cplx(&pr.shifts[p * L + lane].e1);
+            }
+        }
+        // lane 0 reads one index ahead
+        CssIdx nxt = css_identity_index();
+        if (act && lane == 0) nxt = css_load_index(F, min(start + t0, stop + 1));
+        for (int t = t0; t < t1; ++t) {
+            const int tp = t - 2 * lane;
+            // ingest: the index the previous lane finished last step (lane 0: from memory)
+            CssIdx in = css_shfl_up(z.w0, L);
+            if (lane == 0) {
+                in = nxt;
+                if (act) nxt = css_load_index(F, min(start + t + 1, stop + 1));
+            }
+            z.w0 = z.w1; z.w1 = in;
+            const int knew = start + tp;          // index just ingested; the bulge sits at knew - 1
+            if (has_bulge && z.alive && tp >= 2) {
+                // the creation phase of this lane's bulge reaches index knew (diagonal.jl:199-225)
+                if (knew > stop || z.w1.q.s == 0.0) { z.w1.dq = z.w1.dq * z.ca; z.alive = 0; }
+                else z.w1.q.c = z.ca * z.w1.q.c;
+            }
+            const int i = knew - 1;
+            if (has_bulge && tp >= 1 && i <= stop) {
+                if (tp == 1) css_create(z, F, start, stop, shift);
+                if (i < stop) css_step_regular(z);
+                else css_step_final(z);
+                nturn += (i < stop) ? 3 : 2;
+            }
+            // retire: the last lane writes index i back
+            if (lane == L - 1 && act && i >= start && i <= stop + 1) {
+                css_store_index(F, i, z.w0);
+                if (i <= stop && fabs(z.w0.q.s) <= AMRVW_EPS) dstack[sp++] = i;
+            }
+        }
+        sp = __shfl_sync(0xffffffffu, sp, grp * L + L - 1);
+        for (int d = L / 2; d >= 1; d >>= 1) nturn += __shfl_down_sync(0xffffffffu, nturn, d, L);
+        if (t1 < Tmax) {
+            double2* dst = reinterpret_cast<double2*>(parked + ((long long)u * 32 + lane32));
+            const double2* src = reinterpret_cast<const double2*>(&z);
+#pragma unroll
+            for (int i = 0; i < (int)(sizeof(CssLane) / 16); ++i) __stcg(dst + i, src[i]);
+            if (lane == 0) { __stcg(&up->sp[grp], sp); __stcg(&up->nturn[grp], __ldcg(&up->nturn[grp]) + nturn); }
+            if (lane32 == 0) __stcg(&up->t, t1);
+        } else {
+            if (act && lane == 0) {
+                PolyRec* r = pr.rec + p;
+                PolyRec rec = load_rec(r);
+                rec.ls.sp = sp;
+                rec.st.sweeps += nb;
+                rec.chase_turnovers += nturn + __ldcg(&up->nturn[grp]);
+                if (mode == 2) { rec.st.exceptional += nb; rec.ls.ord += nb; rec.ls.ctr.it_count = 14; }
+                store_rec(r, rec);
+            }
+            if (lane32 == 0) __stcg(&up->t, -1);
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane32 == 0) {
+            const unsigned k = atomicAdd(&q->tail, 1u);
+            atomicExch(slots + (k & mask), u);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- set-up, small windows, finish (complex)
+__global__ void __launch_bounds__(64) css_setup_kernel(Problem<cplx> pr) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= pr.nbatch) return;
+    PolyRec rec;
+    rec.ls.kk = 0; rec.ls.it_max = 0; rec.ls.ord = 0; rec.ls.unconv = 0; rec.ls.sp = 0; rec.ls.pc_sub = 0; rec.ls.pc_small = 0; rec.ls.pn_small = 0;
+    rec.ls.ctr = {0, 1, 0, 15, -1};
+    rec.st = {0, 0, 0, 0, 0};
+    rec.serial_turnovers = 0; rec.chase_turnovers = 0;
+    rec.N = 0; rec.K = 0; rec.mode = 0; rec.nb = 0; rec.iterating = 0; rec.pad = 0;
+    const long long off = pr.offsets[p];
+    const int len = (int)(pr.offsets[p + 1] - off);
+    cplx* out = pr.roots + (off - p);
+    int first, last;
+    trim_zeros(pr.coeffs + off, len, first, last);
+    if (first < 0) {
+        finish_poly(pr, p, out, 0, 0, 0, rec.st);
+    } else {
+        const cplx* ps = pr.coeffs + off + first;
+        const int ncoef = last - first + 1;
+        rec.K = first;
+        if (ncoef <= 3) {
+            const int cnt = solve_simple(ps, ncoef, out);
+            finish_poly(pr, p, out, cnt, rec.K, 0, rec.st);
+        } else {
+            const int N = ncoef - 1;
+            Fact<cplx, false> F = make_fact<cplx, false>(pr, p, N);
+            factor_companion(F, ps);
+            for (int i = 0; i < N; ++i) out[i] = cplx(0.0, 0.0);
+            rec.N = N;
+            rec.ls.ctr = {0, 1, N - 1, 15, -1};
+            rec.ls.it_max = 20ll * (N - 1);
+            rec.iterating = 1;
+        }
+    }
+    pr.rec[p] = rec;
+}
+template <int L>
+__global__ void css_enqueue_kernel(Problem<cplx> pr, RoundQueue* q, int* slots, unsigned mask, UnitPark* park) {
+    constexpr int G = 32 / L;
+    const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nunits = (pr.nbatch + G - 1) / G;
+    if (u >= nunits) return;
+    bool any = false;
+    for (int g = 0; g < G; ++g) {
+        const long long p = u * G + g;
+        if (p < pr.nbatch && pr.rec[p].iterating) any = true;
+    }
+    if (!any) return;
+    UnitPark up;
+    up.t = -1;
+    for (int g = 0; g < 8; ++g) { up.sp[g] = 0; up.nturn[g] = 0; }
+    up.pad[0] = up.pad[1] = up.pad[2] = 0;
+    park[u] = up;
+    __threadfence();
+    atomicAdd(&q->remaining, 1u);
+    const unsigned k = atomicAdd(&q->tail, 1u);
+    atomicExch(slots + (k & mask), (int)u);
+}
+// every deferred window with the reference's one-bulge schedule, in place (windows are disjoint and
+// nothing else runs any more)
+__global__ void __launch_bounds__(64) css_small_kernel(Problem<cplx> pr) {
+    const unsigned w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= pr.counters[CNT_SMALL]) return;
+    const SmallWin sw = reinterpret_cast<const SmallWin*>(pr.swlist)[w];
+    const long long p = sw.poly;
+    PolyRec* rw = pr.rec + p;
+    Fact<cplx, false> F = make_fact<cplx, false>(pr, p, rw->N);
+    cplx* E = pr.roots + (pr.offsets[p] - p) - 1;
+    Counter c2 = {sw.lo - 1, sw.lo, sw.hi, sw.it_count, -1};
+    PolyStats st = {0, 0, 0, 0, 0};
+    int ord = 1000000 + sw.lo;
+    const int left = drive_window(F, sw.lo, sw.hi, c2, E, 20ll * (rw->N - 1), pr.seed, (uint64_t)p, ord, st, ReferenceStep());
+    atomicAdd((unsigned long long*)&rw->serial_turnovers, (unsigned long long)F.turnovers);
+    atomicAdd(&rw->st.sweeps, st.sweeps);
+    if (st.exceptional) atomicAdd(&rw->st.exceptional, st.exceptional);
+    if (left) atomicAdd(&rw->ls.unconv, left);
+}
+__global__ void __launch_bounds__(256) css_finish_kernel(Problem<cplx> pr, int smem_elems) {
+    extern __shared__ __align__(16) unsigned char sort_smem[];
+    cplx* tile = reinterpret_cast<cplx*>(sort_smem);
+    const long long p = blockIdx.x;
+    const PolyRec* recp = pr.rec + p;
+    const int n = recp->N;
+    if (n <= 0) return;
+    cplx* out = pr.roots + (pr.offsets[p] - p);
+    cplx* a = out;
+    const bool in_smem = n <= smem_elems;
+    if (in_smem) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) tile[i] = out[i];
+        a = tile;
+    }
+    __syncthreads();
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    for (int k = 2; k <= np2; k <<= 1) {
+        for (int j = k >> 1; j >= 1; j >>= 1) {
+            const bool first = (j == (k >> 1));
+            for (int t = threadIdx.x; t < (np2 >> 1); t += blockDim.x) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = first ? (i ^ (k - 1)) : (i | j);
+                if (l < n && i < n) {
+                    const cplx x = a[i], y = a[l];
+                    if (eig_less(y, x)) { a[i] = y; a[l] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (in_smem) for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = tile[i];
+    if (threadIdx.x == 0) {
+        PolyRec rec = *recp;
+        rec.st.turnovers = rec.serial_turnovers + rec.chase_turnovers;
+        rec.st.unconverged = rec.ls.unconv + (rec.ls.ctr.stop_index >= 1 ? rec.ls.ctr.stop_index + 1 : 0);
+        finish_poly(pr, p, out, rec.N, rec.K, rec.st.unconverged, rec.st);
+    }
+}
+
+// ---------------------------------------------------------------- host side
+template <int L, int MH>
+static cudaError_t launch_css_units(const Problem<cplx>& pr, const PipeParams& pp, RoundQueue* q, int* slots, unsigned mask, UnitPark* park, CssLane* parked, int seg_steps,
+                                    int sm_count, cudaStream_t st) {
+    constexpr int G = 32 / L;
+    const long long nunits = (pr.nbatch + G - 1) / G;
+    css_enqueue_kernel<L><<<(int)((nunits + 127) / 128), 128, 0, st>>>(pr, q, slots, mask, park);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, css_unit_kernel<L, MH>, 32, 0)) != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    const long long resident = (long long)sm_count * per_sm;
+    const int blocks = (int)(nunits < resident ? nunits : resident);
+    css_unit_kernel<L, MH><<<blocks, 32, 0, st>>>(pr, pp, q, slots, mask, park, parked, seg_steps);
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_css_pipelined(Problem<cplx> pr, const amrvw_options& opt, int max_len, long long total, int sm_count, cudaStream_t st, int* launches,
+                                        RoundQueue* q, int* slots, unsigned mask, UnitPark* park, CssLane* parked) {
+    const int degree = max_len - 1;
+    int L = opt.lanes_per_poly;
+    if (L == 0) L = degree < 64 ? 4 : (degree < 256 ? 8 : 16);
+    PipeParams pp;
+    pp.reuse = 1;
+    pp.small = opt.small_window ? opt.small_window : (L + 8 > 24 ? L + 8 : 24);
+    if (pp.small < L) pp.small = L;
+    if (pp.small > 96) pp.small = 96;
+    pp.ms = pp.small + 4; pp.dense = 0; pp.mh = L;
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(pr.counters, 0, CNT_WORDS * sizeof(unsigned), st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(q, 0, sizeof(RoundQueue), st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(slots, 0xFF, (size_t)(mask + 1) * sizeof(int), st)) != cudaSuccess) return e;
+    css_setup_kernel<<<(int)((pr.nbatch + 63) / 64), 64, 0, st>>>(pr);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    const int seg_steps = 256;
+    switch (L) {
+        case 4: e = launch_css_units<4, 8>(pr, pp, q, slots, mask, park, parked, seg_steps, sm_count, st); break;
+        case 8: e = launch_css_units<8, 8>(pr, pp, q, slots, mask, park, parked, seg_steps, sm_count, st); break;
+        case 16: e = launch_css_units<16, 16>(pr, pp, q, slots, mask, park, parked, seg_steps, sm_count, st); break;
+        default: e = launch_css_units<32, 32>(pr, pp, q, slots, mask, park, parked, seg_steps, sm_count, st); break;
+    }
+    if (e != cudaSuccess) return e;
+    {
+        const long long cap = total / 3 + pr.nbatch + 16;
+        css_small_kernel<<<(int)((cap + 63) / 64), 64, 0, st>>>(pr);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    {
+        const int smem_elems = max_len - 1 <= AMRVW_SORT_SMEM ? (max_len > 1 ? max_len - 1 : 1) : AMRVW_SORT_SMEM;
+        const size_t smem = (size_t)smem_elems * sizeof(cplx);
+        if ((e = cudaFuncSetAttribute(css_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        css_finish_kernel<<<(int)pr.nbatch, 256, smem, st>>>(pr, smem_elems);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    *launches += 5;
+    return cudaSuccess;
+}
+
+}  // namespace amrvw
