@@ -375,6 +375,20 @@ int amrvw_selftest(amrvw_ctx* ctx, int64_t n, double* out4) {
     return AMRVW_OK;
 }
 
+int amrvw_selftest_complex(amrvw_ctx* ctx, int64_t n, double* out4) {
+    if (!ctx || !out4 || n <= 0) return AMRVW_ERR_ARGUMENT;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int rc = reserve(ctx, ctx->state, 4 * sizeof(double));
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->state.ptr, 0, 4 * sizeof(double), st));
+    selftest_complex_kernel<<<ctx->sm_count, 128, 0, st>>>((double*)ctx->state.ptr, (int)n, ctx->opt.seed + 54321);
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaMemcpyAsync(out4, ctx->state.ptr, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return AMRVW_OK;
+}
+
 int amrvw_measure_fp64_peak(amrvw_ctx* ctx, double* tflops) {
     if (!ctx || !tflops) return AMRVW_ERR_ARGUMENT;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));

@@ -237,6 +237,45 @@ __global__ void selftest_kernel(double* out, int n, unsigned long long seed) {
     atomicAdd(&out[3], n_gen);
 }
 
+// complex twin: out[0] max |fast - ieee| over the nine output doubles, out[1] max |Q1 Q2 Q3 - R1 R2 R3|,
+// out[2] max deviation from unit norm, out[3] turnovers sent to the IEEE path
+AMRVW_DI void crot3(cplx M[9], const Rot<cplx> r, int i) {   // M <- M * G(r)@i, G = [c s; -s conj(c)]
+    for (int k = 0; k < 3; ++k) {
+        const cplx a = M[3 * k + i], b = M[3 * k + i + 1];
+        M[3 * k + i] = a * r.c - b * r.s;
+        M[3 * k + i + 1] = a * r.s + b * conj_(r.c);
+    }
+}
+__global__ void selftest_complex_kernel(double* out, int n, unsigned long long seed) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    double e_diff = 0.0, e_prod = 0.0, e_unit = 0.0, n_gen = 0.0;
+    for (int k = tid; k < n; k += gridDim.x * blockDim.x) {
+        Rot<cplx> q[3];
+        for (int j = 0; j < 3; ++j) {
+            double sn, cs, ps, pc;
+            sincos(6.283185307179586 * uniform01(seed, 2 + j, (uint64_t)k), &sn, &cs);
+            sincos(6.283185307179586 * uniform01(seed, 12 + j, (uint64_t)k), &ps, &pc);
+            if (k % 7 == j) { sn *= exp(-40.0 * uniform01(seed, 9, (uint64_t)k)); cs = copysign(sqrt(fmax(0.0, 1.0 - sn * sn)), cs); }
+            q[j] = make_rot<cplx>(cplx(cs * pc, cs * ps), sn);
+        }
+        Rot<cplx> r1, r2, r3, i1, i2, i3;
+        turnover_ieee(q[0], q[1], q[2], i1, i2, i3);
+        if (!turnover_fast_try(q[0], q[1], q[2], r1, r2, r3)) { n_gen += 1.0; r1 = i1; r2 = i2; r3 = i3; }
+        e_diff = fmax(e_diff, fmax(fmax(abs_(r1.c - i1.c), abs_(r2.c - i2.c)), abs_(r3.c - i3.c)));
+        e_diff = fmax(e_diff, fmax(fmax(fabs(r1.s - i1.s), fabs(r2.s - i2.s)), fabs(r3.s - i3.s)));
+        cplx A[9], Bm[9];
+        for (int j = 0; j < 9; ++j) { A[j] = cplx(j % 4 == 0 ? 1.0 : 0.0, 0.0); Bm[j] = A[j]; }
+        crot3(A, q[0], 0); crot3(A, q[1], 1); crot3(A, q[2], 0);
+        crot3(Bm, r1, 1); crot3(Bm, r2, 0); crot3(Bm, r3, 1);
+        for (int j = 0; j < 9; ++j) e_prod = fmax(e_prod, abs_(A[j] - Bm[j]));
+        e_unit = fmax(e_unit, fmax(fabs(abs2_(r1.c) + r1.s * r1.s - 1.0), fmax(fabs(abs2_(r2.c) + r2.s * r2.s - 1.0), fabs(abs2_(r3.c) + r3.s * r3.s - 1.0))));
+    }
+    atomicMax((unsigned long long*)&out[0], (unsigned long long)__double_as_longlong(e_diff));
+    atomicMax((unsigned long long*)&out[1], (unsigned long long)__double_as_longlong(e_prod));
+    atomicMax((unsigned long long*)&out[2], (unsigned long long)__double_as_longlong(e_unit));
+    atomicAdd(&out[3], n_gen);
+}
+
 // ---------------------------------------------------------------- FP64 peak probe
 // 8 independent DFMA chains per thread, no memory traffic: measures the FP64 vector-pipe roofline.
 __global__ void fp64_peak_kernel(double* out, int iters, double seed) {

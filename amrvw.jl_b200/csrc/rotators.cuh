@@ -394,8 +394,50 @@ AMRVW_DI void turnover(const Rot<double> q1, const Rot<double> q2, const Rot<dou
 #endif
     r1 = o.r1; r2 = o.r2; r3 = o.r3;
 }
+// division-free common path (complex), the same rewriting as the real one: 1/r by rsqrt, the first-order
+// renormalisations as FMAs, b = s1 s2 / s5 without the O(u) factor.  The reference's complex givens
+// (transformations.jl:28-31 around zlartg) returns a real s >= 0 and puts the sign of u31 into c:
+// c4' = sign(u31) conj(u21)/r, s4' = |u31|/r, r4 = sign(u31) r.  ~62 FP64-pipe instructions against
+// ~400 (hypot, complex division, three IEEE divisions and two square roots) on the IEEE path.
+AMRVW_DI bool turnover_fast_try(const Rot<cplx> q1, const Rot<cplx> q2, const Rot<cplx> q3, Rot<cplx>& r1, Rot<cplx>& r2, Rot<cplx>& r3) {
+    const cplx c1 = q1.c, c2 = q2.c, c3 = q3.c;
+    const double s1 = q1.s, s2 = q2.s, s3 = q3.s;
+    const double tre = c2.re * s3, tim = c2.im * s3;                                   // t = c2 s3
+    const double u21re = -fma(tre, c1.re, fma(tim, c1.im, c3.re * s1));                // u21 = -t conj(c1) - c3 s1
+    const double u21im = -fma(tim, c1.re, fma(-tre, c1.im, c3.im * s1));
+    const double u31 = s2 * s3;
+    const double u11re = fma(c1.re, c3.re, fma(-c1.im, c3.im, -(tre * s1)));           // u11 = c1 c3 - t s1
+    const double u11im = fma(c1.re, c3.im, fma(c1.im, c3.re, -(tim * s1)));
+    const double x = fma(u21re, u21re, fma(u21im, u21im, u31 * u31));
+    const double y = rsqrt_nr(x);
+    const double sy = u31 >= 0.0 ? y : -y;                                             // sign(u31) / r
+    const cplx c4 = cplx(u21re * sy, u21im * sy);                                      // conj of the givens' c
+    const double s4 = -(u31 * sy);                                                     // -|u31| / r
+    const double r4 = x * sy;
+    const double d5 = fma(u11re, u11re, fma(u11im, u11im, x - 1.0));
+    const double rho5 = fma(-0.5, d5, 1.0);
+    const double w = s2 * s4;
+    const double are = fma(c1.re, w, fma(c2.re, c4.re, c2.im * c4.im));                // a = conj(c1) s2 s4 + conj(c2) c4
+    const double aim = fma(-c1.im, w, fma(c2.re, c4.im, -(c2.im * c4.re)));
+    const double b = -((s1 * s2) * sy);
+    const double d6 = fma(b, b, fma(are, are, fma(aim, aim, -1.0)));
+    const double rho6 = fma(-0.5, d6, 1.0);
+    r1 = make_rot<cplx>(c4, s4);
+    r2 = make_rot<cplx>(cplx(u11re * rho5, u11im * rho5), -(r4 * rho5));
+    r3 = make_rot<cplx>(cplx(are * rho6, -(aim * rho6)), b * rho6);
+    return (unsigned)(__double2hiint(x) - 0x05d00000) < (0x7ff00000u - 0x05d00000u);
+}
+AMRVW_NI Rot3<cplx> turnover_fast_call(const Rot<cplx> q1, const Rot<cplx> q2, const Rot<cplx> q3) {
+    Rot3<cplx> o;
+    if (!turnover_fast_try(q1, q2, q3, o.r1, o.r2, o.r3)) turnover_ieee(q1, q2, q3, o.r1, o.r2, o.r3);
+    return o;
+}
 AMRVW_DI void turnover(const Rot<cplx> q1, const Rot<cplx> q2, const Rot<cplx> q3, Rot<cplx>& r1, Rot<cplx>& r2, Rot<cplx>& r3) {
+#ifdef AMRVW_STRICT
     const Rot3<cplx> o = turnover_ieee_call<cplx>(q1, q2, q3);
+#else
+    const Rot3<cplx> o = turnover_fast_call(q1, q2, q3);
+#endif
     r1 = o.r1; r2 = o.r2; r3 = o.r3;
 }
 

@@ -137,6 +137,9 @@ int amrvw_measure_fp64_peak(amrvw_ctx* ctx, double* tflops);
  * turnover must preserve the product): out4 = {max rel. error of the Newton rsqrt, max |Q1Q2Q3 -
  * R1R2R3| over n random turnovers, max deviation from unit norm, turnovers sent to the IEEE path}. */
 int amrvw_selftest(amrvw_ctx* ctx, int64_t n, double* out4);
+/* The complex twin: out4 = {max |fast - IEEE| over the outputs of n random complex turnovers, max
+ * |Q1Q2Q3 - R1R2R3| of the fast path, max deviation from unit norm, turnovers sent to the IEEE path}. */
+int amrvw_selftest_complex(amrvw_ctx* ctx, int64_t n, double* out4);
 
 /* Accounting of the last pipelined RDS call that asked for stats (development aid, no reference
  * counterpart).  out16 = {[0] sum over phase-B warps of their cycles, [2] of which in the lean

@@ -351,3 +351,15 @@ def test_gpu_fast_primitives_selftest(ctx):
     assert r["rsqrt_rel_err"] <= 2 * eps, r
     assert r["turnover_product_err"] <= 8 * eps, r
     assert r["unit_norm_err"] <= 8 * eps, r
+
+
+def test_gpu_fast_complex_turnover_selftest(ctx):
+    """The division-free complex turnover against the IEEE one (the reference's formulas,
+    transformations.jl:158-229) on random triples, every 7th with a sine down to 1e-18: same rotators to
+    a few ulp, product preserved (test/test-amrvw-basics.jl:79-86), unit norm."""
+    r = ctx.selftest_complex(400000)
+    eps = np.finfo(float).eps
+    assert r["fast_vs_ieee"] <= 16 * eps, r
+    assert r["turnover_product_err"] <= 12 * eps, r
+    assert r["unit_norm_err"] <= 8 * eps, r
+    assert r["general_path"] <= 4, r
