@@ -363,3 +363,76 @@ def test_gpu_fast_complex_turnover_selftest(ctx):
     assert r["turnover_product_err"] <= 12 * eps, r
     assert r["unit_norm_err"] <= 8 * eps, r
     assert r["general_path"] <= 4, r
+
+
+# ------------------------------------------------------------------ complex single shift on the unit queue
+@pytest.mark.parametrize("L", [4, 8, 16, 32])
+def test_gpu_css_pipelined_lanes(A, oracle, L):
+    """The pipelined complex path for every lane-group width: bulges two indices apart, the creation
+    phase of each bulge carried by its lane (diagonal.jl:199-225 without the pass over Q), deferred
+    small windows.  Ragged batch so that groups of one warp see different windows; both schedules of
+    the library must agree with the oracle's reference schedule root by root."""
+    c = A.Context(seed=0, schedule=A.SCHEDULE_PIPELINED, lanes_per_poly=L)
+    try:
+        degs = [40, 41, 64, 97, 130, 200, 257, 33, 5, 3, 2, 1, 350]
+        rows = []
+        for i, d in enumerate(degs):
+            r = oracle.fill_coeffs(77, i, 0, 2 * (d + 1))
+            rows.append(r[0::2] + 1j * r[1::2])
+        want = [oracle.roots(r)[0] for r in rows]
+        got = A.roots(rows, ctx=c)
+        big = [i for i, d in enumerate(degs) if d > 2]
+        check_parity([rows[i] for i in big], [got[i] for i in big], [want[i] for i in big], real_counts=False)
+        for i, d in enumerate(degs):
+            if d <= 2:
+                assert np.allclose(got[i], want[i], rtol=1e-14, atol=0)
+        assert c.last_stats["unconverged"] == 0 and c.last_stats["fat_steps"] > 0
+    finally:
+        c.close()
+
+
+def test_gpu_css_structured_inputs(A, ctx, ctx_ref):
+    """Complex inputs that stagnate or deflate exactly: x^n - i (exceptional shifts, create-bulge.jl:85-93),
+    a polynomial with trimmed zero ends, real coefficients passed as complex (conjugate pairs must still
+    be found, without the real path's exact pairing)."""
+    n = 48
+    p1 = np.zeros(n + 1, dtype=complex); p1[0] = -1j; p1[-1] = 1
+    truth = np.exp(1j * (np.pi / 2 + 2 * np.pi * np.arange(n)) / n)
+    for c in (ctx, ctx_ref):
+        r = A.roots(p1, ctx=c)
+        d, _ = match_roots(r, truth)
+        assert d.max() < 1e-12
+    rng = np.random.default_rng(5)
+    core = rng.standard_normal(61) + 1j * rng.standard_normal(61)
+    p2 = np.concatenate([np.zeros(3), core, np.zeros(2)])
+    r = A.roots(p2, ctx=ctx)
+    assert len(r) == 63 and np.all(r[-3:] == 0)
+    d, _ = match_roots(r[:-3], np.roots(core[::-1]))
+    assert d.max() < 1e-10
+    p3 = rng.standard_normal(201).astype(complex)
+    r = A.roots(p3, ctx=ctx)
+    d, _ = match_roots(r, np.roots(p3[::-1]))
+    assert d.max() < 1e-9
+
+
+def test_gpu_full_size_c3_properties(A, ctx, oracle):
+    """BASELINE config 3 at full size (2000 complex polynomials of degree 1000) through the C ABI:
+    size-independent properties -- every root slot filled, nothing unconverged, Horner backward error at
+    rounding level on every polynomial, and oracle parity on a sample of the batch."""
+    B, n = 2000, 1000
+    rows = [None] * B
+    for p in range(B):
+        r = oracle.fill_coeffs(3, p, 1, 2 * (n + 1))
+        rows[p] = r[0::2] + 1j * r[1::2]
+    got = A.roots(rows, ctx=ctx)
+    assert ctx.last_stats["unconverged"] == 0
+    worst = 0.0
+    for a, g in zip(rows[::8], got[::8]):        # np.polyval is O(n^2) per polynomial: every 8th one
+        assert len(g) == n and np.all(np.isfinite(g.view(np.float64)))
+        worst = max(worst, horner_backward_error(a, g).max())
+    for g in got:
+        assert len(g) == n and np.all(np.isfinite(g.view(np.float64)))
+    assert worst < 1e-10, worst
+    sample = list(range(0, B, 250))
+    want = [oracle.roots(rows[p])[0] for p in sample]
+    check_parity([rows[p] for p in sample], [got[p] for p in sample], want, real_counts=False)
