@@ -95,20 +95,21 @@ __global__ void __launch_bounds__(64) roots_reference_kernel(Problem<S> pr) {
     finish_poly(pr, p, out, N, K, unconv, st);
 }
 
-// ---------------------------------------------------------------- roots(vs, ws), one bulge at a time
+// ---------------------------------------------------------------- roots(vs, ws): trimming, closed forms, factorization
+// deflate_leading_zeros(vs, ws) (utils.jl:29-58), the degree <= 2 shortcut (companion.jl:288-293) and
+// amrvw(vs, ws) (companion.jl:163-204) for polynomial p.  Returns the order n of the pencil to iterate
+// on (chains factored into the workspace, root slots zeroed) or 0 when the polynomial is already
+// finished (finish_poly done); Kz = zero roots to append.
 template <class S>
-__global__ void __launch_bounds__(64) roots_pencil_reference_kernel(Problem<S> pr) {
-    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= pr.nbatch) return;
+AMRVW_DI int pencil_prepare(const Problem<S>& pr, const long long p, cplx* out, const PolyStats& st, Fact<S, true>& F, int& Kz) {
     const long long off = pr.offsets[p];
     const int N0 = (int)(pr.offsets[p + 1] - off);
-    cplx* out = pr.roots + off;
-    PolyStats st = {0, 0, 0, 0, 0};
-    if (N0 <= 0) { finish_poly(pr, p, out, 0, 0, 0, st); return; }
+    Kz = 0;
+    if (N0 <= 0) { finish_poly(pr, p, out, 0, 0, 0, st); return 0; }
     const S* vs = pr.coeffs + off;
     const S* ws = pr.ws + off;
-    // deflate_leading_zeros(vs, ws) (utils.jl:29-58) without touching the inputs: the reference's two
-    // in-place edits become overrides of one entry each.  Indices below are 1-based like the reference.
+    // deflate_leading_zeros(vs, ws) without touching the inputs: the reference's two in-place edits become
+    // overrides of one entry each.  Indices below are 1-based like the reference.
     int N = N0, wsN_idx = 0, vsK_idx = 0;
     S wsN_val = S(0.0), vsK_val = S(0.0);
     if (iszero_(ws[N0 - 1])) {
@@ -132,8 +133,8 @@ __global__ void __launch_bounds__(64) roots_pencil_reference_kernel(Problem<S> p
     auto V = [&](int i) { return i == vsK_idx ? vsK_val : vs[i - 1]; };  // 1-based
     auto W = [&](int i) { return i == wsN_idx ? wsN_val : ws[i - 1]; };
     const int n = N - K + 1;   // length of vs[K:N]
-    const int Kz = K - 1;
-    if (n <= 0) { finish_poly(pr, p, out, 0, 0, 0, st); return; }
+    Kz = K - 1;
+    if (n <= 0) { finish_poly(pr, p, out, 0, 0, 0, st); return 0; }
     if (n <= 2) {  // companion.jl:288-293: rs = vcat(ps,0) + vcat(0,qs); roots(rs)
         S rs[3] = {S(0.0), S(0.0), S(0.0)};
         for (int i = 0; i < n; ++i) { rs[i] = rs[i] + V(K + i); rs[i + 1] = rs[i + 1] + W(K + i); }
@@ -146,10 +147,10 @@ __global__ void __launch_bounds__(64) roots_pencil_reference_kernel(Problem<S> p
             cnt += f2;
         }
         finish_poly(pr, p, out, cnt, Kz, 0, st);
-        return;
+        return 0;
     }
     // amrvw(vs, ws) (companion.jl:163-204): ps = basic_decompose([vs; 1]); ws sign-adjusted; qs = [ws; -1]
-    Fact<S, true> F = make_fact<S, true>(pr, p, n);
+    F = make_fact<S, true>(pr, p, n);
     q_factorization(F);
     {
         const double par = (n % 2 == 0) ? 1.0 : -1.0;
@@ -168,6 +169,20 @@ __global__ void __launch_bounds__(64) roots_pencil_reference_kernel(Problem<S> p
         r_factorization(F.WB, F.WCt, F.WD, n, xs_w);
     }
     for (int i = 0; i < n; ++i) out[i] = cplx(0.0, 0.0);
+    return n;
+}
+
+// ---------------------------------------------------------------- roots(vs, ws), one bulge at a time
+template <class S>
+__global__ void __launch_bounds__(64) roots_pencil_reference_kernel(Problem<S> pr) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= pr.nbatch) return;
+    cplx* out = pr.roots + pr.offsets[p];
+    PolyStats st = {0, 0, 0, 0, 0};
+    Fact<S, true> F;
+    int Kz = 0;
+    const int n = pencil_prepare(pr, p, out, st, F, Kz);
+    if (n == 0) return;
     Counter ctr = {0, 1, n - 1, 15, n - 2};
     int ord = 0;
     const int unconv = drive_window(F, 1, n - 1, ctr, out - 1, 20ll * (n - 1), pr.seed, (unsigned long long)p, ord, st, ReferenceStep());
