@@ -6,6 +6,7 @@
 #include "pipeline.cuh"
 #include "rounds.cuh"
 #include "css_units.cuh"
+#include "pencil_units.cuh"
 
 #include <cstdio>
 #include <cstring>
@@ -171,7 +172,7 @@ static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, cons
         for (int c = 0; c < nd; ++c) { int rc = reserve(ctx, ctx->diags[c], slots * sizeof(S)); if (rc) return rc; }
     }
     { int rc = reserve(ctx, ctx->stats, (size_t)nbatch * sizeof(PolyStats) + sizeof(StatsAccum)); if (rc) return rc; }
-    if (var == V_RDS || var == V_CSS) { int rc = reserve(ctx, ctx->shifts, slots * sizeof(int)); if (rc) return rc; }
+    if (var == V_RDS || var == V_CSS || var == V_PENCIL_R) { int rc = reserve(ctx, ctx->shifts, slots * sizeof(int)); if (rc) return rc; }
 
     Problem<S> pr;
     pr.coeffs = d_a; pr.ws = d_w; pr.offsets = (const long long*)d_offsets; pr.nbatch = nbatch;
@@ -217,6 +218,28 @@ static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, cons
             pr.rec = (PolyRec*)ctx->rec.ptr; pr.shifts = (Shifts*)ctx->fatshifts.ptr; pr.swlist = ctx->swlist.ptr; pr.counters = (unsigned*)ctx->counters.ptr;
             cudaError_t e = launch_rounds_rds(pr, ctx->opt, (int)max_len, (long long)total, ctx->sm_count, st, &launches, ctx->evpool, stats ? &ctx->times : nullptr, qb);
             if (e != cudaSuccess) return fail(ctx, AMRVW_ERR_CUDA, std::string("unit schedule: ") + cudaGetErrorString(e));
+            done = true;
+        }
+        if (var == V_PENCIL_R && ctx->opt.schedule != AMRVW_SCHEDULE_REFERENCE) {
+            // the same unit schedule with five chains per polynomial (pencil_units.cuh)
+            int rc;
+            if ((rc = reserve(ctx, ctx->rec, (size_t)nbatch * sizeof(PolyRec)))) return rc;
+            if ((rc = reserve(ctx, ctx->fatshifts, (size_t)nbatch * 32 * sizeof(Shifts)))) return rc;
+            if ((rc = reserve(ctx, ctx->swlist, ((size_t)total / 3 + (size_t)nbatch + 16) * sizeof(SmallWin)))) return rc;
+            if ((rc = reserve(ctx, ctx->counters, CNT_WORDS * sizeof(unsigned)))) return rc;
+            const size_t max_units = (size_t)nbatch;
+            size_t qcap = 1024;
+            while (qcap < 2 * max_units + 4096) qcap <<= 1;
+            if ((rc = reserve(ctx, ctx->queue, sizeof(RoundQueue)))) return rc;
+            if ((rc = reserve(ctx, ctx->qslots, qcap * sizeof(int)))) return rc;
+            if ((rc = reserve(ctx, ctx->park, max_units * sizeof(UnitPark)))) return rc;
+            if ((rc = reserve(ctx, ctx->parked, max_units * 32 * sizeof(PenLane)))) return rc;
+            QueueBufs qb;
+            qb.q = (RoundQueue*)ctx->queue.ptr; qb.slots = (int*)ctx->qslots.ptr; qb.mask = (unsigned)(qcap - 1);
+            qb.park = (UnitPark*)ctx->park.ptr; qb.parked = nullptr;
+            pr.rec = (PolyRec*)ctx->rec.ptr; pr.shifts = (Shifts*)ctx->fatshifts.ptr; pr.swlist = ctx->swlist.ptr; pr.counters = (unsigned*)ctx->counters.ptr;
+            cudaError_t e = launch_pencil_pipelined(pr, ctx->opt, (int)max_len, (long long)total, ctx->sm_count, st, &launches, qb, (PenLane*)ctx->parked.ptr);
+            if (e != cudaSuccess) return fail(ctx, AMRVW_ERR_CUDA, std::string("pencil unit schedule: ") + cudaGetErrorString(e));
             done = true;
         }
     }

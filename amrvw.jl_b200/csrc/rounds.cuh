@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(256) rounds_finish_kernel(Problem<double> pr, 
     const PolyRec* recp = pr.rec + p;
     const int n = recp->N;
     if (n <= 0) return;   // closed forms were finished by the set-up kernel
-    cplx* out = pr.roots + (pr.offsets[p] - p);
+    cplx* out = pr.roots + (pr.offsets[p] - (pr.extra == 1 ? p : 0));   // pencil batches (extra == 2) have one slot per vs entry
     cplx* a = out;
     const bool in_smem = n <= smem_elems;
     if (in_smem) {

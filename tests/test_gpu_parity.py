@@ -436,3 +436,67 @@ def test_gpu_full_size_c3_properties(A, ctx, oracle):
     sample = list(range(0, B, 250))
     want = [oracle.roots(rows[p])[0] for p in sample]
     check_parity([rows[p] for p in sample], [got[p] for p in sample], want, real_counts=False)
+
+
+# ------------------------------------------------------------------ companion pencil on the unit queue
+@pytest.mark.parametrize("L,solver", [(4, 0), (8, 0), (16, 0), (32, 0), (8, 2), (16, 2)])
+def test_gpu_pencil_pipelined_lanes(A, oracle, L, solver):
+    """roots(vs, ws) on the pipelined path for every lane-group width and both shift solvers (dense
+    V W^{-1} block + Hessenberg QR, and the core-chasing sub-solve): five chains, 11 turnovers per chase
+    step (pencil.jl:63-71).  Ragged batch with trimmed zeros (utils.jl:29-58) and closed-form degrees;
+    roots must agree with the oracle's one-bulge schedule root by root, with equal real-root counts."""
+    c = A.Context(seed=0, schedule=A.SCHEDULE_PIPELINED, lanes_per_poly=L, shift_solver=solver)
+    try:
+        degs = [40, 41, 64, 97, 130, 200, 257, 33, 5, 3, 2, 1, 350]
+        rows = [oracle.fill_coeffs(44, i, 0, d + 1) for i, d in enumerate(degs)]
+        for split in ("basic", "half"):
+            pairs = [A.basic_pencil(r) if split == "basic" or len(r) <= 3 else pencil_split(r, (len(r) - 1) // 2) for r in rows]
+            vs, ws = zip(*pairs)
+            want = [oracle.roots(v, ws=w)[0] for v, w in pairs]
+            got = A.roots(list(vs), list(ws), ctx=c)
+            big = [i for i, d in enumerate(degs) if d > 2]
+            check_parity([rows[i] for i in big], [got[i] for i in big], [want[i] for i in big], C=256.0)
+            for i, d in enumerate(degs):
+                if d <= 2:
+                    assert np.allclose(got[i], want[i], rtol=1e-14, atol=0)
+            assert c.last_stats["unconverged"] == 0 and c.last_stats["fat_steps"] > 0
+    finally:
+        c.close()
+
+
+def test_gpu_pencil_known_answers_pipelined(A, ctx):
+    """test/test-roots.jl:146-188 through the default (pipelined) schedule: basic_pencil and every
+    pencil_split of p4, p5, p6; a pencil with zero leading/trailing entries."""
+    for p, want in ((p4, [1, 2, 3, 4]), (p5, [1, 2, 3, 4, 5]), (p6, [1, 2, 3, 4, 5, 6])):
+        for i in range(0, len(p) - 1):
+            vs, ws = A.basic_pencil(p) if i == 0 else pencil_split(p, i)
+            r = A.roots(vs, ws, ctx=ctx)
+            assert np.all(r.imag == 0) and np.allclose(np.sort(r.real), want, rtol=1e-9, atol=0)
+    rng = np.random.default_rng(9)
+    core = rng.standard_normal(81)
+    vs, ws = A.basic_pencil(np.concatenate([np.zeros(2), core]))
+    r = A.roots(vs, ws, ctx=ctx)
+    assert len(r) == 82 and np.all(r[-2:] == 0)
+    d, _ = match_roots(r[:-2], np.roots(core[::-1]))
+    assert d.max() < 1e-9
+
+
+def test_gpu_full_size_c4_properties(A, ctx, oracle):
+    """BASELINE config 4 at full size (1000 pencils of degree 500, basic split and mid split) through the
+    C ABI: nothing unconverged, Horner backward error at rounding level, exact conjugate pairing, and
+    oracle parity on a sample of the batch."""
+    B, n = 1000, 500
+    rows = batch(oracle, 4, B, n)
+    for split in ("basic", "half"):
+        pairs = [A.basic_pencil(r) if split == "basic" else pencil_split(r, n // 2) for r in rows]
+        vs, ws = zip(*pairs)
+        got = A.roots(list(vs), list(ws), ctx=ctx)
+        assert ctx.last_stats["unconverged"] == 0 and ctx.last_stats["fat_steps"] > 0
+        for a, g in zip(rows[::4], got[::4]):
+            assert len(g) == n
+            assert horner_backward_error(a, g).max() < 1e-10
+            pos = np.sort_complex(g[g.imag > 0]); neg = np.sort_complex(np.conj(g[g.imag < 0]))
+            assert np.array_equal(pos, neg)
+        sample = list(range(0, B, 125))
+        want = [oracle.roots(pairs[p][0], ws=pairs[p][1])[0] for p in sample]
+        check_parity([rows[p] for p in sample], [got[p] for p in sample], want, C=256.0)
