@@ -51,6 +51,7 @@ _SIGS = {
     "amrvw_selftest": (ctypes.c_int, [_P, _I64, ctypes.POINTER(ctypes.c_double)]),
     "amrvw_last_profile": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_int64)]),
     "amrvw_selftest_complex": (ctypes.c_int, [_P, _I64, ctypes.POINTER(ctypes.c_double)]),
+    "amrvw_selftest_robust": (ctypes.c_int, [_P, _I64, ctypes.POINTER(ctypes.c_double)]),
 }
 EXPORTS = tuple(_SIGS)
 

@@ -5,6 +5,7 @@
 #include "kernels.cuh"
 #include "pipeline.cuh"
 #include "rounds.cuh"
+#include "chain.cuh"
 #include "css_units.cuh"
 #include "pencil_units.cuh"
 
@@ -113,9 +114,9 @@ int amrvw_set_options(amrvw_ctx* ctx, const amrvw_options* opt) {
     if (!ctx || !opt) return AMRVW_ERR_ARGUMENT;
     if (opt->schedule < 0 || opt->schedule > 2) return fail(ctx, AMRVW_ERR_ARGUMENT, "schedule must be 0, 1 or 2");
     const int L = opt->lanes_per_poly;
-    if (!(L == 0 || L == 4 || L == 8 || L == 16 || L == 32)) return fail(ctx, AMRVW_ERR_ARGUMENT, "lanes_per_poly must be 0, 4, 8, 16 or 32");
-    if (!(opt->shift_reuse == 0 || opt->shift_reuse == 1 || opt->shift_reuse == 2 || opt->shift_reuse == 4))
-        return fail(ctx, AMRVW_ERR_ARGUMENT, "shift_reuse must be 0, 1, 2 or 4");
+    if (!(L == 0 || L == 4 || L == 8 || L == 16 || L == 32 || L == 64 || L == 128 || L == 256)) return fail(ctx, AMRVW_ERR_ARGUMENT, "lanes_per_poly must be 0, 4, 8, 16, 32, 64, 128 or 256");
+    if (!(opt->shift_reuse == 0 || opt->shift_reuse == 1 || opt->shift_reuse == 2 || opt->shift_reuse == 4 || opt->shift_reuse == 8))
+        return fail(ctx, AMRVW_ERR_ARGUMENT, "shift_reuse must be 0, 1, 2, 4 or 8");
     if (opt->small_window < 0) return fail(ctx, AMRVW_ERR_ARGUMENT, "small_window must be >= 0");
     if (opt->shift_solver < 0 || opt->shift_solver > 2) return fail(ctx, AMRVW_ERR_ARGUMENT, "shift_solver must be 0, 1 or 2");
     ctx->opt = *opt;
@@ -201,7 +202,7 @@ static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, cons
             // unit schedule: per-polynomial records, shifts, small-window queue, unit queue and parking
             int rc;
             if ((rc = reserve(ctx, ctx->rec, (size_t)nbatch * sizeof(PolyRec)))) return rc;
-            if ((rc = reserve(ctx, ctx->fatshifts, (size_t)nbatch * 32 * sizeof(Shifts)))) return rc;
+            if ((rc = reserve(ctx, ctx->fatshifts, (size_t)nbatch * 256 * sizeof(Shifts)))) return rc;   // up to 256 bulges per fat step (chain.cuh)
             if ((rc = reserve(ctx, ctx->swlist, ((size_t)total / 3 + (size_t)nbatch + 16) * sizeof(SmallWin)))) return rc;
             if ((rc = reserve(ctx, ctx->counters, CNT_WORDS * sizeof(unsigned)))) return rc;
             const size_t max_units = (size_t)nbatch;   // one per polynomial is the upper bound (L = 32)
@@ -406,6 +407,20 @@ int amrvw_selftest_complex(amrvw_ctx* ctx, int64_t n, double* out4) {
     cudaStream_t st = ctx->stream;
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->state.ptr, 0, 4 * sizeof(double), st));
     selftest_complex_kernel<<<ctx->sm_count, 128, 0, st>>>((double*)ctx->state.ptr, (int)n, ctx->opt.seed + 54321);
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaMemcpyAsync(out4, ctx->state.ptr, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return AMRVW_OK;
+}
+
+int amrvw_selftest_robust(amrvw_ctx* ctx, int64_t n, double* out4) {
+    if (!ctx || !out4 || n <= 0) return AMRVW_ERR_ARGUMENT;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int rc = reserve(ctx, ctx->state, 4 * sizeof(double));
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->state.ptr, 0, 4 * sizeof(double), st));
+    selftest_robust_kernel<<<ctx->sm_count, 128, 0, st>>>((double*)ctx->state.ptr, (int)n, ctx->opt.seed + 777);
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaMemcpyAsync(out4, ctx->state.ptr, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));

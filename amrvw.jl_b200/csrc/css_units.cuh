@@ -589,6 +589,7 @@ static cudaError_t launch_css_pipelined(Problem<cplx> pr, const amrvw_options& o
     const int degree = max_len - 1;
     int L = opt.lanes_per_poly;
     if (L == 0) L = degree < 64 ? 4 : (degree < 256 ? 8 : 16);
+    if (L > 32) L = 32;      // chained warps exist for the real rank-one path only
     PipeParams pp;
     pp.reuse = 1;
     pp.small = opt.small_window ? opt.small_window : (L + 8 > 24 ? L + 8 : 24);

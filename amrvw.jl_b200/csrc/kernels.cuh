@@ -252,6 +252,38 @@ __global__ void selftest_kernel(double* out, int n, unsigned long long seed) {
     atomicAdd(&out[3], n_gen);
 }
 
+// fall-back turnover on triples with vanishing sines (down to the denormal range): out[0] product error of
+// turnover_robust_call, out[1] its deviation from unit norm, out[2] product error of the reference's
+// formulas (turnover_ieee) on the same inputs, out[3] number of triples
+__global__ void selftest_robust_kernel(double* out, int n, unsigned long long seed) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    double e_rob = 0.0, e_unit = 0.0, e_ref = 0.0, cnt = 0.0;
+    for (int k = tid; k < n; k += gridDim.x * blockDim.x) {
+        Rot<double> q[3];
+        for (int j = 0; j < 3; ++j) {
+            double sn, cs;
+            sincos(6.283185307179586 * uniform01(seed, 2 + j, (uint64_t)k), &sn, &cs);
+            // two of the three rotators (sometimes all three) get a sine between 1e-320 and 1e-100
+            if ((k + j) % 3 != 0 || k % 5 == 0) { sn = copysign(exp(-(230.0 + 507.0 * uniform01(seed, 9 + j, (uint64_t)k))), sn); cs = copysign(1.0, cs); }
+            q[j] = make_rot<double>(cs, sn);
+        }
+        const Rot3<double> o = turnover_robust_call(q[0], q[1], q[2]);
+        Rot<double> i1, i2, i3;
+        turnover_ieee(q[0], q[1], q[2], i1, i2, i3);
+        double A[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, Bm[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, Cm[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        rot3(A, q[0], 0); rot3(A, q[1], 1); rot3(A, q[2], 0);
+        rot3(Bm, o.r1, 1); rot3(Bm, o.r2, 0); rot3(Bm, o.r3, 1);
+        rot3(Cm, i1, 1); rot3(Cm, i2, 0); rot3(Cm, i3, 1);
+        for (int j = 0; j < 9; ++j) { e_rob = fmax(e_rob, fabs(A[j] - Bm[j])); const double d = fabs(A[j] - Cm[j]); e_ref = fmax(e_ref, d == d ? d : 1.0); }
+        e_unit = fmax(e_unit, fmax(fabs(o.r1.c * o.r1.c + o.r1.s * o.r1.s - 1.0), fmax(fabs(o.r2.c * o.r2.c + o.r2.s * o.r2.s - 1.0), fabs(o.r3.c * o.r3.c + o.r3.s * o.r3.s - 1.0))));
+        cnt += 1.0;
+    }
+    atomicMax((unsigned long long*)&out[0], (unsigned long long)__double_as_longlong(e_rob));
+    atomicMax((unsigned long long*)&out[1], (unsigned long long)__double_as_longlong(e_unit));
+    atomicMax((unsigned long long*)&out[2], (unsigned long long)__double_as_longlong(e_ref));
+    atomicAdd(&out[3], cnt);
+}
+
 // complex twin: out[0] max |fast - ieee| over the nine output doubles, out[1] max |Q1 Q2 Q3 - R1 R2 R3|,
 // out[2] max deviation from unit norm, out[3] turnovers sent to the IEEE path
 AMRVW_DI void crot3(cplx M[9], const Rot<cplx> r, int i) {   // M <- M * G(r)@i, G = [c s; -s conj(c)]

@@ -542,6 +542,7 @@ static cudaError_t launch_pencil_pipelined(Problem<double> pr, const amrvw_optio
     const int degree = max_len;          // vs has one entry per degree
     int L = opt.lanes_per_poly;
     if (L == 0) L = degree < 48 ? 4 : (degree < 200 ? 8 : 16);
+    if (L > 32) L = 32;      // chained warps exist for the real rank-one path only
     PipeParams pp;
     pp.reuse = opt.shift_reuse ? opt.shift_reuse : 2;
     if (pp.reuse > L / 2) pp.reuse = L / 2 > 0 ? L / 2 : 1;

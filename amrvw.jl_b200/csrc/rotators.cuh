@@ -369,13 +369,42 @@ AMRVW_DI bool turnover_fast_try(const Rot<double> q1, const Rot<double> q2, cons
     // slot in a loop that is bound by that pipe); false for 0, denormals, inf and NaN
     return (unsigned)(__double2hiint(x) - 0x05d00000) < (0x7ff00000u - 0x05d00000u);
 }
+// Degenerate inputs (u21^2 + u31^2 below 2^-930: the bulge meets rotators whose sines have all but vanished).
+// The reference's last step, b = s1 s2 / s5 (transformations.jl:188-191), is a quotient of two such
+// quantities: once they reach the denormal range it has a few bits left, (a, b) is no longer a unit vector,
+// the first-order renormalisation does not repair it and the chain stops being unitary (backward error 1e-2).
+// The reference never gets there -- it deflates at |s| <= eps before the next bulge -- but a fat step passes
+// up to 128 bulges through rotators that converged under the earlier ones.  Here the third rotator is read
+// off the explicit product instead, M = Q1 Q2 Q3, R3 = (R1 R2)^T M: c6 = s4 M23 + c4 M33 (the reference's a),
+// s6 = -(s4 M22 + c4 M32), no division, absolute accuracy O(u) whatever the sizes; the three rotators are
+// normalised exactly (scaled givens).
+AMRVW_NI Rot3<double> turnover_robust_call(const Rot<double> q1, const Rot<double> q2, const Rot<double> q3) {
+    const double c1 = q1.c, s1 = q1.s, c2 = q2.c, s2 = q2.s, c3 = q3.c, s3 = q3.s;
+    const double u21 = -(c2 * s3) * c1 - c3 * s1;
+    const double u31 = s2 * s3;
+    const double u11 = c1 * c3 - (c2 * s1) * s3;
+    double c, s, r4, tmp;
+    givensrot(u21, u31, c, s, r4);
+    const double c4 = c, s4 = -s;
+    givensrot(u11, r4, c, s, tmp);
+    const double c5 = c, s5 = -s;
+    const double m22 = (c1 * c2) * c3 - s1 * s3, m32 = -(s2 * c3), m23 = c1 * s2, m33 = c2;
+    const double a = s4 * m23 + c4 * m33;
+    const double b = -(s4 * m22 + c4 * m32);
+    const double h = sqrt(a * a + b * b);        // a^2 + b^2 = 1 + O(u): no scaling needed
+    Rot3<double> o;
+    o.r1 = make_rot<double>(c4, s4);
+    o.r2 = make_rot<double>(c5, s5);
+    o.r3 = h > 0.0 ? make_rot<double>(a / h, b / h) : make_rot<double>(1.0, 0.0);
+    return o;
+}
 AMRVW_DI void turnover_fast(const Rot<double> q1, const Rot<double> q2, const Rot<double> q3, Rot<double>& r1, Rot<double>& r2, Rot<double>& r3) {
 #ifdef AMRVW_STRICT
     const Rot3<double> o = turnover_ieee_call<double>(q1, q2, q3);
     r1 = o.r1; r2 = o.r2; r3 = o.r3;
 #else
     if (!turnover_fast_try(q1, q2, q3, r1, r2, r3)) {
-        const Rot3<double> o = turnover_ieee_call<double>(q1, q2, q3);
+        const Rot3<double> o = turnover_robust_call(q1, q2, q3);
         r1 = o.r1; r2 = o.r2; r3 = o.r3;
     }
 #endif

@@ -185,9 +185,11 @@ AMRVW_NI int unit_driver(const Problem<double>& pr, const PipeParams pp, const i
 // Part 2, the shifts of a pending fat step (mode 3), each lane group on its own polynomial: stage the
 // trailing block's rotators, write the block out densely, Hessenberg QR with the lanes sharing rows
 // and columns (shifts.cuh), pair the shifts.
+// L: lanes sharing the work; LB: bulges of a fat step (= L in the unit kernel, 32 NW in the chain kernel)
 template <int MH>
-AMRVW_NI void unit_shifts(const Problem<double>& pr, const PipeParams pp, const int L, const long long p, ShiftScratch<MH>& ws, const int lane, const unsigned gmask) {
+AMRVW_NI void unit_shifts(const Problem<double>& pr, const PipeParams pp, const int L, const long long p, ShiftScratch<MH>& ws, const int lane, const unsigned gmask, const int Lb = 0) {
     constexpr int LDH = MH + 1;
+    const int LB = Lb ? Lb : L;
     PolyRec rec = load_rec(pr.rec + p);
     const int m = rec.nb, stop = rec.ls.ctr.stop_index, k0 = stop - m, M = m + 1;
     Fact<double, false> F = make_fact<double, false>(pr, p, rec.N);
@@ -214,7 +216,7 @@ AMRVW_NI void unit_shifts(const Problem<double>& pr, const PipeParams pp, const 
             W.Q = ws.q - k0; W.B = ws.b - k0; W.Ct = ws.c - k0; W.turnovers = 0;
             rec.serial_turnovers += chase_shifts(W, k0, stop, ws.e, pr.seed, (uint64_t)p, rec.ls.ord, ws.sn, 1);
         }
-        rec.nb = pair_shifts(ws.e, m, pr.shifts + p * L, L, pp.reuse);
+        rec.nb = pair_shifts(ws.e, m, pr.shifts + p * LB, LB, pp.reuse);
         rec.mode = 1;
         store_rec(pr.rec + p, rec);
     }
@@ -553,9 +555,13 @@ static void choose_pipe_params(const amrvw_options& opt, long long nbatch, int m
         else if (degree < 1200 && nbatch * 16 > (long long)sm_count * 512) L = 8;
         else L = 16;
         if (degree >= 1200 && nbatch * 32 <= (long long)sm_count * 256) L = 32;
+        // small batches of large polynomials: chain 2 or 4 warps per polynomial (chain.cuh)
+        if (L == 32 && degree >= 4000 && nbatch * 4 <= (long long)sm_count * 4) L = 128;
+        else if (L == 32 && degree >= 2000 && nbatch * 2 <= (long long)sm_count * 6) L = 64;
     }
     pp.reuse = opt.shift_reuse ? opt.shift_reuse : 2;
     if (pp.reuse > L / 2) pp.reuse = L / 2 > 0 ? L / 2 : 1;
+    while (2 * L / pp.reuse > 64) pp.reuse *= 2;     // the largest dense trailing block is 64 x 64
     const int mshift = 2 * L / pp.reuse;
     pp.small = opt.small_window ? opt.small_window : (mshift + 8 > 24 ? mshift + 8 : 24);
     if (pp.small < mshift) pp.small = mshift;      // a fat step needs delta - 1 >= m
@@ -591,6 +597,9 @@ static cudaError_t launch_units_mh(const Problem<double>& pr, const PipeParams& 
     return cudaErrorInvalidValue;
 }
 
+// chain.cuh: one CTA of NW chained warps per polynomial (small batches of large polynomials)
+template <int NW, int MH> static cudaError_t launch_chain(const Problem<double>& pr, const PipeParams& pp, int sm_count, cudaStream_t st);
+
 // Queues the whole schedule on `st`: set-up, the persistent unit kernel, small windows, finish.
 // Nothing here waits for the device unless `times` is asked for.
 static cudaError_t launch_rounds_rds(Problem<double> pr, const amrvw_options& opt, int max_len, long long total, int sm_count, cudaStream_t st, int* launches, cudaEvent_t* ev,
@@ -612,6 +621,9 @@ static cudaError_t launch_rounds_rds(Problem<double> pr, const amrvw_options& op
         case 4: e = launch_units_mh<4>(pr, pp, qb, seg_steps, sm_count, st); break;
         case 8: e = launch_units_mh<8>(pr, pp, qb, seg_steps, sm_count, st); break;
         case 16: e = launch_units_mh<16>(pr, pp, qb, seg_steps, sm_count, st); break;
+        case 64: e = pp.mh <= 32 ? launch_chain<2, 32>(pr, pp, sm_count, st) : launch_chain<2, 64>(pr, pp, sm_count, st); break;
+        case 128: e = pp.mh <= 32 ? launch_chain<4, 32>(pr, pp, sm_count, st) : launch_chain<4, 64>(pr, pp, sm_count, st); break;
+        case 256: e = launch_chain<8, 64>(pr, pp, sm_count, st); break;
         default: e = launch_units_mh<32>(pr, pp, qb, seg_steps, sm_count, st); break;
     }
     if (e != cudaSuccess) return e;

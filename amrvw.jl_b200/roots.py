@@ -76,6 +76,11 @@ class Context:
         self._check(self._lib.amrvw_selftest_complex(self._h, int(n), out))
         return {"fast_vs_ieee": out[0], "turnover_product_err": out[1], "unit_norm_err": out[2], "general_path": out[3]}
 
+    def selftest_robust(self, n=200000):
+        out = (ctypes.c_double * 4)()
+        self._check(self._lib.amrvw_selftest_robust(self._h, int(n), out))
+        return {"robust_product_err": out[0], "unit_norm_err": out[1], "reference_formula_product_err": out[2], "triples": out[3]}
+
     def last_profile(self):
         """Warp-cycle accounting of the last pipelined RDS call made with stats (amrvw_last_profile)."""
         out = (ctypes.c_int64 * 16)()

@@ -64,8 +64,8 @@ enum amrvw_shift_solver {
  * (create-bulge.jl:9), it_max = 20 n (AMRVW_algorithm.jl:25), tol = eps (AMRVW_algorithm.jl:184). */
 typedef struct amrvw_options {
     int32_t schedule;        /* amrvw_schedule */
-    int32_t lanes_per_poly;  /* pipelined: bulges in flight per polynomial (4, 8, 16 or 32); 0 = auto */
-    int32_t shift_reuse;     /* pipelined: bulges driven by each shift pair (1, 2 or 4); 0 = auto     */
+    int32_t lanes_per_poly;  /* pipelined: bulges in flight per polynomial (4, 8, 16, 32; rds_f64 also 64, 128, 256 = 2, 4 or 8 chained warps); 0 = auto */
+    int32_t shift_reuse;     /* pipelined: bulges driven by each shift pair (1, 2, 4 or 8); 0 = auto  */
     int32_t small_window;    /* pipelined: windows up to this size use the one-bulge step; 0 = auto   */
     int32_t shift_solver;    /* pipelined: amrvw_shift_solver; 0 = auto (dense)                        */
     int32_t reserved;        /* must be 0 */
@@ -140,6 +140,12 @@ int amrvw_selftest(amrvw_ctx* ctx, int64_t n, double* out4);
 /* The complex twin: out4 = {max |fast - IEEE| over the outputs of n random complex turnovers, max
  * |Q1Q2Q3 - R1R2R3| of the fast path, max deviation from unit norm, turnovers sent to the IEEE path}. */
 int amrvw_selftest_complex(amrvw_ctx* ctx, int64_t n, double* out4);
+/* Device self-test of the fall-back turnover of the multishift schedules (no reference counterpart: the
+ * reference deflates before a bulge can meet a vanished sine) on n random real triples whose sines span
+ * 1e-320 .. 1: out4 = {max |Q1 Q2 Q3 - R1 R2 R3| of the division-free fall-back, max deviation of its
+ * rotators from unit norm, the same product error for the reference's formulas (transformations.jl:158-202)
+ * on the same inputs, number of triples}. */
+int amrvw_selftest_robust(amrvw_ctx* ctx, int64_t n, double* out4);
 
 /* Accounting of the last pipelined RDS call that asked for stats (development aid, no reference
  * counterpart).  out16 = {[0] sum over phase-B warps of their cycles, [2] of which in the lean

@@ -500,3 +500,73 @@ def test_gpu_full_size_c4_properties(A, ctx, oracle):
         sample = list(range(0, B, 125))
         want = [oracle.roots(pairs[p][0], ws=pairs[p][1])[0] for p in sample]
         check_parity([rows[p] for p in sample], [got[p] for p in sample], want, C=256.0)
+
+
+# ------------------------------------------------------------------ chained warps (small batches of large polynomials)
+@pytest.mark.parametrize("L,reuse,small,dense", [(64, 2, 72, 1), (64, 4, 40, 1), (128, 4, 72, 1), (128, 4, 72, 0), (256, 8, 72, 1)])
+def test_gpu_chain_bitwise_vs_sequential_multishift(A, oracle, L, reuse, small, dense):
+    """chain.cuh: one CTA per polynomial, 2 or 4 warps chained into one systolic array of 64 / 128 bulges
+    (hand-off through shared memory, one bar.sync per lock-step).  Without FMA contraction it must agree
+    bit for bit with the oracle's sequential multishift schedule at the same L -- windows both shorter
+    (fill/drain loop only, fewer bulges than lanes) and longer (lean loop) than 3 L."""
+    c = A.Context(seed=0, strict=True, schedule=A.SCHEDULE_PIPELINED, lanes_per_poly=L, shift_reuse=reuse, small_window=small,
+                  shift_solver=A.SHIFTS_DENSE if dense else A.SHIFTS_CHASE)
+    try:
+        rows = batch(oracle, 31, 4, 150) + batch(oracle, 32, 3, 700) + batch(oracle, 35, 2, 1300) + [p4, p6]
+        flat = np.concatenate(rows); off = np.zeros(len(rows) + 1, dtype=np.int64); np.cumsum([len(r) for r in rows], out=off[1:])
+        out, roff, nr, tot, pp = oracle.roots_csr(flat, off, sched=1, L=L, small=small, reuse=reuse, dense=dense, per_poly=True)
+        got = A.roots(rows, ctx=c)
+        n_checked = 0
+        for p, g in enumerate(got):
+            if pp[p]["exceptional"]:
+                continue
+            w = out[roff[p]:roff[p] + nr[p]]
+            assert np.array_equal(g.view(np.float64), w.view(np.float64)), f"polynomial {p} (degree {len(rows[p]) - 1}) differs"
+            n_checked += 1
+        assert n_checked >= 8
+        if not any(x["exceptional"] for x in pp):    # an exceptional shift draws sincos(rand): last-bit differences change the path
+            assert c.last_stats["fat_steps"] == tot["fat_steps"] and c.last_stats["turnovers"] == tot["turnovers"]
+    finally:
+        c.close()
+
+
+@pytest.mark.parametrize("L", [64, 128, 256])
+def test_gpu_chain_parity(A, oracle, L):
+    """Product build of the chained kernel against the oracle's reference (one-bulge) schedule: roots by
+    minimum-distance matching within the conditioning-scaled tolerance, equal real-root counts."""
+    c = A.Context(seed=0, schedule=A.SCHEDULE_PIPELINED, lanes_per_poly=L)
+    try:
+        rows = batch(oracle, 5, 3, 1500, kind=2) + batch(oracle, 2, 2, 900)
+        want = [oracle.roots(r)[0] for r in rows]
+        got = A.roots(rows, ctx=c)
+        check_parity(rows, got, want)
+        assert c.last_stats["unconverged"] == 0 and c.last_stats["fat_steps"] > 0
+    finally:
+        c.close()
+
+
+def test_gpu_robust_turnover_selftest(ctx):
+    """The fall-back turnover of the multishift schedules on triples whose sines reach the denormal range
+    (a fat step passes bulges through rotators that converged under earlier bulges of the same step; the
+    reference deflates first, AMRVW_algorithm.jl:181-202): product preserved to rounding, unit norm, while
+    the reference's quotient b = s1 s2 / s5 (transformations.jl:188-191) loses the product on such inputs."""
+    r = ctx.selftest_robust(400000)
+    assert r["triples"] == 400000
+    assert r["robust_product_err"] < 8e-16 and r["unit_norm_err"] < 8e-16
+    assert r["reference_formula_product_err"] > 1e-6      # the failure this path exists for
+
+
+@pytest.mark.parametrize("L,B,n,kind", [(128, 24, 4000, 0), (128, 16, 4000, 2), (32, 16, 2000, 2)])
+def test_gpu_many_bulges_backward_error(A, oracle, L, B, n, kind):
+    """Up to 128 bulges per fat step pass through rotators that have already converged: Horner backward
+    error of every polynomial stays at rounding level (with the reference's turnover formulas as the
+    fall-back 8 of 96 such polynomials came back with backward error 1e-2)."""
+    c = A.Context(seed=0, schedule=A.SCHEDULE_PIPELINED, lanes_per_poly=L)
+    try:
+        rows = batch(oracle, 12 if kind == 0 else 11, B, n, kind=kind)
+        got = A.roots(rows, ctx=c)
+        assert c.last_stats["unconverged"] == 0
+        worst = max(horner_backward_error(r, g).max() for r, g in zip(rows, got))
+        assert worst < 1e-10, worst
+    finally:
+        c.close()
