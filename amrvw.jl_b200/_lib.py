@@ -18,7 +18,7 @@ class Options(ctypes.Structure):
 class Stats(ctypes.Structure):
     _fields_ = [("turnovers", ctypes.c_int64), ("sweeps", ctypes.c_int64), ("exceptional", ctypes.c_int64),
                 ("unconverged", ctypes.c_int64), ("fat_steps", ctypes.c_int64), ("launches", ctypes.c_int64),
-                ("device_ms", ctypes.c_double)]
+                ("device_ms", ctypes.c_double), ("lanes", ctypes.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -32,6 +32,7 @@ struct amrvw_ctx {
     DevBuf chains[5], diags[3], coeffs, coeffs2, offsets, roots, nroots, nunconv, stats, shifts, state, prof, rec, fatshifts, swlist, counters, queue, qslots, park, parked;
     cudaEvent_t evpool[32] = {};
     RoundsTimes times = {};
+    bool prof_valid = false;
     int sm_count = 148;
 };
 
@@ -193,7 +194,10 @@ static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, cons
     pr.seed = ctx->opt.seed;
 
     cudaStream_t st = ctx->stream;
-    int launches = 0;
+    int launches = 0, lanes = 0;
+    ctx->times = RoundsTimes{0.f, 0.f, 0.f, 0.f};
+    ctx->prof_valid = (var == V_RDS && stats != nullptr);
+    if (stats && !ctx->evpool[0]) for (cudaEvent_t& e : ctx->evpool) CUDA_TRY(ctx, cudaEventCreate(&e));
     if (stats) CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, st));
 
     bool done = false;
@@ -215,9 +219,8 @@ static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, cons
             QueueBufs qb;
             qb.q = (RoundQueue*)ctx->queue.ptr; qb.slots = (int*)ctx->qslots.ptr; qb.mask = (unsigned)(qcap - 1);
             qb.park = (UnitPark*)ctx->park.ptr; qb.parked = (StepState*)ctx->parked.ptr;
-            if (stats && !ctx->evpool[0]) for (cudaEvent_t& e : ctx->evpool) CUDA_TRY(ctx, cudaEventCreate(&e));
             pr.rec = (PolyRec*)ctx->rec.ptr; pr.shifts = (Shifts*)ctx->fatshifts.ptr; pr.swlist = ctx->swlist.ptr; pr.counters = (unsigned*)ctx->counters.ptr;
-            cudaError_t e = launch_rounds_rds(pr, ctx->opt, (int)max_len, (long long)total, ctx->sm_count, st, &launches, ctx->evpool, stats ? &ctx->times : nullptr, qb);
+            cudaError_t e = launch_rounds_rds(pr, ctx->opt, (int)max_len, (long long)total, ctx->sm_count, st, &launches, ctx->evpool, stats ? &ctx->times : nullptr, qb, &lanes);
             if (e != cudaSuccess) return fail(ctx, AMRVW_ERR_CUDA, std::string("unit schedule: ") + cudaGetErrorString(e));
             done = true;
         }
@@ -239,7 +242,7 @@ static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, cons
             qb.q = (RoundQueue*)ctx->queue.ptr; qb.slots = (int*)ctx->qslots.ptr; qb.mask = (unsigned)(qcap - 1);
             qb.park = (UnitPark*)ctx->park.ptr; qb.parked = nullptr;
             pr.rec = (PolyRec*)ctx->rec.ptr; pr.shifts = (Shifts*)ctx->fatshifts.ptr; pr.swlist = ctx->swlist.ptr; pr.counters = (unsigned*)ctx->counters.ptr;
-            cudaError_t e = launch_pencil_pipelined(pr, ctx->opt, (int)max_len, (long long)total, ctx->sm_count, st, &launches, qb, (PenLane*)ctx->parked.ptr);
+            cudaError_t e = launch_pencil_pipelined(pr, ctx->opt, (int)max_len, (long long)total, ctx->sm_count, st, &launches, qb, (PenLane*)ctx->parked.ptr, ctx->evpool, stats ? &ctx->times : nullptr, &lanes);
             if (e != cudaSuccess) return fail(ctx, AMRVW_ERR_CUDA, std::string("pencil unit schedule: ") + cudaGetErrorString(e));
             done = true;
         }
@@ -260,7 +263,7 @@ static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, cons
             if ((rc = reserve(ctx, ctx->parked, max_units * 32 * sizeof(CssLane)))) return rc;
             pr.rec = (PolyRec*)ctx->rec.ptr; pr.shifts = (Shifts*)ctx->fatshifts.ptr; pr.swlist = ctx->swlist.ptr; pr.counters = (unsigned*)ctx->counters.ptr;
             cudaError_t e = launch_css_pipelined(pr, ctx->opt, (int)max_len, (long long)total, ctx->sm_count, st, &launches, (RoundQueue*)ctx->queue.ptr, (int*)ctx->qslots.ptr,
-                                                 (unsigned)(qcap - 1), (UnitPark*)ctx->park.ptr, (CssLane*)ctx->parked.ptr);
+                                                 (unsigned)(qcap - 1), (UnitPark*)ctx->park.ptr, (CssLane*)ctx->parked.ptr, ctx->evpool, stats ? &ctx->times : nullptr, &lanes);
             if (e != cudaSuccess) return fail(ctx, AMRVW_ERR_CUDA, std::string("complex unit schedule: ") + cudaGetErrorString(e));
             done = true;
         }
@@ -286,7 +289,7 @@ static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, cons
         CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
         stats->turnovers = h.turnovers; stats->sweeps = h.sweeps; stats->exceptional = h.exceptional;
         stats->unconverged = h.unconverged; stats->fat_steps = h.fat_steps;
-        stats->launches = launches; stats->device_ms = ms;
+        stats->launches = launches; stats->device_ms = ms; stats->lanes = lanes;
     }
     return AMRVW_OK;
 }
@@ -375,10 +378,11 @@ int amrvw_count_real_roots_dev(amrvw_ctx* ctx, const double* d_roots, const int6
 int amrvw_last_profile(amrvw_ctx* ctx, int64_t* out16) {
     if (!ctx || !out16) return AMRVW_ERR_ARGUMENT;
     std::memset(out16, 0, 16 * sizeof(int64_t));
-    if (!ctx->prof.ptr) return AMRVW_OK;
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    CUDA_TRY(ctx, cudaMemcpyAsync(out16, ctx->prof.ptr, 16 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->prof.ptr && ctx->prof_valid) {
+        CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+        CUDA_TRY(ctx, cudaMemcpyAsync(out16, ctx->prof.ptr, 16 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     // kernel times of the unit schedule, microseconds
     out16[8] = (int64_t)(ctx->times.setup_ms * 1e3); out16[9] = (int64_t)(ctx->times.main_ms * 1e3);   // [10] driver cycles, [13] pop cycles stay as counted
     out16[11] = (int64_t)(ctx->times.small_ms * 1e3); out16[12] = (int64_t)(ctx->times.finish_ms * 1e3);

@@ -585,11 +585,13 @@ static cudaError_t launch_css_units(const Problem<cplx>& pr, const PipeParams& p
 }
 
 static cudaError_t launch_css_pipelined(Problem<cplx> pr, const amrvw_options& opt, int max_len, long long total, int sm_count, cudaStream_t st, int* launches,
-                                        RoundQueue* q, int* slots, unsigned mask, UnitPark* park, CssLane* parked) {
+                                        RoundQueue* q, int* slots, unsigned mask, UnitPark* park, CssLane* parked, cudaEvent_t* ev = nullptr, RoundsTimes* times = nullptr,
+                                        int* lanes_out = nullptr) {
     const int degree = max_len - 1;
     int L = opt.lanes_per_poly;
     if (L == 0) L = degree < 64 ? 4 : (degree < 256 ? 8 : 16);
     if (L > 32) L = 32;      // chained warps exist for the real rank-one path only
+    if (lanes_out) *lanes_out = L;
     PipeParams pp;
     pp.reuse = 1;
     pp.small = opt.small_window ? opt.small_window : (L + 8 > 24 ? L + 8 : 24);
@@ -600,8 +602,10 @@ static cudaError_t launch_css_pipelined(Problem<cplx> pr, const amrvw_options& o
     if ((e = cudaMemsetAsync(pr.counters, 0, CNT_WORDS * sizeof(unsigned), st)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(q, 0, sizeof(RoundQueue), st)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(slots, 0xFF, (size_t)(mask + 1) * sizeof(int), st)) != cudaSuccess) return e;
+    if (times) cudaEventRecord(ev[0], st);
     css_setup_kernel<<<(int)((pr.nbatch + 63) / 64), 64, 0, st>>>(pr);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (times) cudaEventRecord(ev[1], st);
     const int seg_steps = 256;
     switch (L) {
         case 4: e = launch_css_units<4, 8>(pr, pp, q, slots, mask, park, parked, seg_steps, sm_count, st); break;
@@ -610,11 +614,13 @@ static cudaError_t launch_css_pipelined(Problem<cplx> pr, const amrvw_options& o
         default: e = launch_css_units<32, 32>(pr, pp, q, slots, mask, park, parked, seg_steps, sm_count, st); break;
     }
     if (e != cudaSuccess) return e;
+    if (times) cudaEventRecord(ev[2], st);
     {
         const long long cap = total / 3 + pr.nbatch + 16;
         css_small_kernel<<<(int)((cap + 63) / 64), 64, 0, st>>>(pr);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
+    if (times) cudaEventRecord(ev[3], st);
     {
         const int smem_elems = max_len - 1 <= AMRVW_SORT_SMEM ? (max_len > 1 ? max_len - 1 : 1) : AMRVW_SORT_SMEM;
         const size_t smem = (size_t)smem_elems * sizeof(cplx);
@@ -623,6 +629,7 @@ static cudaError_t launch_css_pipelined(Problem<cplx> pr, const amrvw_options& o
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     *launches += 5;
+    if (times) return read_round_times(ev, times, st);
     return cudaSuccess;
 }
 

@@ -538,11 +538,12 @@ static cudaError_t launch_pen_units(const Problem<double>& pr, const PipeParams&
 }
 
 static cudaError_t launch_pencil_pipelined(Problem<double> pr, const amrvw_options& opt, int max_len, long long total, int sm_count, cudaStream_t st, int* launches,
-                                           const QueueBufs& qb, PenLane* parked) {
+                                           const QueueBufs& qb, PenLane* parked, cudaEvent_t* ev = nullptr, RoundsTimes* times = nullptr, int* lanes_out = nullptr) {
     const int degree = max_len;          // vs has one entry per degree
     int L = opt.lanes_per_poly;
     if (L == 0) L = degree < 48 ? 4 : (degree < 200 ? 8 : 16);
     if (L > 32) L = 32;      // chained warps exist for the real rank-one path only
+    if (lanes_out) *lanes_out = L;
     PipeParams pp;
     pp.reuse = opt.shift_reuse ? opt.shift_reuse : 2;
     if (pp.reuse > L / 2) pp.reuse = L / 2 > 0 ? L / 2 : 1;
@@ -557,8 +558,10 @@ static cudaError_t launch_pencil_pipelined(Problem<double> pr, const amrvw_optio
     if ((e = cudaMemsetAsync(pr.counters, 0, CNT_WORDS * sizeof(unsigned), st)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(qb.q, 0, sizeof(RoundQueue), st)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(qb.slots, 0xFF, (size_t)(qb.mask + 1) * sizeof(int), st)) != cudaSuccess) return e;
+    if (times) cudaEventRecord(ev[0], st);
     pen_setup_kernel<<<(int)((pr.nbatch + 63) / 64), 64, 0, st>>>(pr);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (times) cudaEventRecord(ev[1], st);
     const int seg_steps = 256;
     e = cudaErrorInvalidValue;
     switch (L) {
@@ -574,6 +577,7 @@ static cudaError_t launch_pencil_pipelined(Problem<double> pr, const amrvw_optio
             break;
     }
     if (e != cudaSuccess) return e;
+    if (times) cudaEventRecord(ev[2], st);
     {
         const long long cap = total / 3 + pr.nbatch + 16;
         const int blocks = (int)((cap + 63) / 64);
@@ -581,6 +585,7 @@ static cudaError_t launch_pencil_pipelined(Problem<double> pr, const amrvw_optio
         else pen_small_kernel<96><<<blocks, 64, 0, st>>>(pr);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
+    if (times) cudaEventRecord(ev[3], st);
     {
         const int smem_elems = max_len <= AMRVW_SORT_SMEM ? (max_len > 1 ? max_len : 1) : AMRVW_SORT_SMEM;
         const size_t smem = (size_t)smem_elems * sizeof(cplx);
@@ -589,6 +594,7 @@ static cudaError_t launch_pencil_pipelined(Problem<double> pr, const amrvw_optio
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     *launches += 5;
+    if (times) return read_round_times(ev, times, st);
     return cudaSuccess;
 }
 

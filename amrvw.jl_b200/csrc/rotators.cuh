@@ -456,9 +456,33 @@ AMRVW_DI bool turnover_fast_try(const Rot<cplx> q1, const Rot<cplx> q2, const Ro
     r3 = make_rot<cplx>(cplx(are * rho6, -(aim * rho6)), b * rho6);
     return (unsigned)(__double2hiint(x) - 0x05d00000) < (0x7ff00000u - 0x05d00000u);
 }
+// complex twin of turnover_robust_call: M = Q1 Q2 Q3 with G(c, s) = [c s; -s conj(c)],
+// conj(c6) = (R1^H M)33 = s4 M23 + c4 M33, s6 = -Re (R1^H M)32 = -Re(s4 M22 + c4 M32) (real up to rounding by
+// the phase the complex givens puts into c4); exact normalisations
+AMRVW_DI void turnover_robust(const Rot<cplx> q1, const Rot<cplx> q2, const Rot<cplx> q3, Rot<cplx>& r1, Rot<cplx>& r2, Rot<cplx>& r3) {
+    const cplx c1 = q1.c, c2 = q2.c, c3 = q3.c;
+    const double s1 = q1.s, s2 = q2.s, s3 = q3.s;
+    const cplx u21 = (-c2) * s3 * conj_(c1) - c3 * s1;
+    const double u31 = s2 * s3;
+    const cplx u11 = c1 * c3 - c2 * s1 * s3;
+    cplx c, r4c; double s;
+    givensrot(u21, u31, c, s, r4c);
+    const cplx c4 = conj_(c);
+    const double s4 = -s, r4 = r4c.re;
+    double h = sqrt(abs2_(u11) + r4 * r4);
+    const cplx c5 = h > 0.0 ? u11 / h : cplx(1.0, 0.0);
+    const double s5 = h > 0.0 ? -r4 / h : 0.0;
+    const cplx m22 = conj_(c1) * c2 * conj_(c3) - s1 * s3, m32 = -(s2 * conj_(c3)), m23 = conj_(c1) * s2, m33 = conj_(c2);
+    const cplx a = s4 * m23 + c4 * m33;
+    const double b = -(s4 * m22 + c4 * m32).re;
+    h = sqrt(abs2_(a) + b * b);
+    r1 = make_rot<cplx>(c4, s4);
+    r2 = make_rot<cplx>(c5, s5);
+    r3 = h > 0.0 ? make_rot<cplx>(conj_(a) / h, b / h) : make_rot<cplx>(cplx(1.0, 0.0), 0.0);
+}
 AMRVW_NI Rot3<cplx> turnover_fast_call(const Rot<cplx> q1, const Rot<cplx> q2, const Rot<cplx> q3) {
     Rot3<cplx> o;
-    if (!turnover_fast_try(q1, q2, q3, o.r1, o.r2, o.r3)) turnover_ieee(q1, q2, q3, o.r1, o.r2, o.r3);
+    if (!turnover_fast_try(q1, q2, q3, o.r1, o.r2, o.r3)) turnover_robust(q1, q2, q3, o.r1, o.r2, o.r3);
     return o;
 }
 AMRVW_DI void turnover(const Rot<cplx> q1, const Rot<cplx> q2, const Rot<cplx> q3, Rot<cplx>& r1, Rot<cplx>& r2, Rot<cplx>& r3) {

@@ -554,10 +554,12 @@ static void choose_pipe_params(const amrvw_options& opt, long long nbatch, int m
         else if (degree < 200) L = 8;
         else if (degree < 1200 && nbatch * 16 > (long long)sm_count * 512) L = 8;
         else L = 16;
-        if (degree >= 1200 && nbatch * 32 <= (long long)sm_count * 256) L = 32;
-        // small batches of large polynomials: chain 2 or 4 warps per polynomial (chain.cuh)
-        if (L == 32 && degree >= 4000 && nbatch * 4 <= (long long)sm_count * 4) L = 128;
-        else if (L == 32 && degree >= 2000 && nbatch * 2 <= (long long)sm_count * 6) L = 64;
+        // measured on B200 (gpurun_out/sweep58.log, sweep59.log; degree 3000): 16 lanes win from ~2000 polynomials
+        // up (400 vs 352 ms at 1500, 435 vs 423 at 2000, 455 vs 495 at 2400), 32 lanes below that, and four chained
+        // warps (chain.cuh, 128 bulges) while every CTA is resident, <= 3 per SM (226 vs 252 ms at 444 polynomials,
+        // 348 vs 255 at 520; config 5: 800 vs 1720 ms); at degree 1500 the chain loses (105 vs 95 ms at 400)
+        if (degree >= 1200 && nbatch * 32 <= (long long)sm_count * 410) L = 32;
+        if (L == 32 && degree >= 2500 && nbatch <= (long long)sm_count * 3) L = 128;
     }
     pp.reuse = opt.shift_reuse ? opt.shift_reuse : 2;
     if (pp.reuse > L / 2) pp.reuse = L / 2 > 0 ? L / 2 : 1;
@@ -602,10 +604,21 @@ template <int NW, int MH> static cudaError_t launch_chain(const Problem<double>&
 
 // Queues the whole schedule on `st`: set-up, the persistent unit kernel, small windows, finish.
 // Nothing here waits for the device unless `times` is asked for.
+static cudaError_t read_round_times(cudaEvent_t* ev, RoundsTimes* times, cudaStream_t st) {
+    cudaError_t e;
+    cudaEventRecord(ev[4], st);
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+    cudaEventElapsedTime(&times->setup_ms, ev[0], ev[1]);
+    cudaEventElapsedTime(&times->main_ms, ev[1], ev[2]);
+    cudaEventElapsedTime(&times->small_ms, ev[2], ev[3]);
+    cudaEventElapsedTime(&times->finish_ms, ev[3], ev[4]);
+    return cudaSuccess;
+}
 static cudaError_t launch_rounds_rds(Problem<double> pr, const amrvw_options& opt, int max_len, long long total, int sm_count, cudaStream_t st, int* launches, cudaEvent_t* ev,
-                                     RoundsTimes* times, const QueueBufs& qb) {
+                                     RoundsTimes* times, const QueueBufs& qb, int* lanes_out = nullptr) {
     int L; PipeParams pp;
     choose_pipe_params(opt, pr.nbatch, max_len, sm_count, L, pp);
+    if (lanes_out) *lanes_out = L;
     cudaError_t e;
     const int nb64 = (int)((pr.nbatch + 63) / 64);
     if ((e = cudaMemsetAsync(pr.counters, 0, CNT_WORDS * sizeof(unsigned), st)) != cudaSuccess) return e;
@@ -643,15 +656,8 @@ static cudaError_t launch_rounds_rds(Problem<double> pr, const amrvw_options& op
         rounds_finish_kernel<<<(int)pr.nbatch, 256, smem, st>>>(pr, smem_elems);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
-    *launches += 5;
-    if (times) {
-        cudaEventRecord(ev[4], st);
-        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
-        cudaEventElapsedTime(&times->setup_ms, ev[0], ev[1]);
-        cudaEventElapsedTime(&times->main_ms, ev[1], ev[2]);
-        cudaEventElapsedTime(&times->small_ms, ev[2], ev[3]);
-        cudaEventElapsedTime(&times->finish_ms, ev[3], ev[4]);
-    }
+    *launches += L > 32 ? 4 : 5;
+    if (times) return read_round_times(ev, times, st);
     return cudaSuccess;
 }
 

@@ -220,7 +220,7 @@ def main():
     for _ in range(max(args.warmup, 1)):
         st = step(stats=True)           # warm-up also yields the per-step counters (launches, turnovers)
     torch.cuda.synchronize()
-    prof = ctx.last_profile() if kind == "rds_f64" and args.schedule != 1 else None   # per-kernel CUDA-event times of the last warm-up step
+    prof = ctx.last_profile() if args.schedule != 1 else None   # per-kernel CUDA-event times (+ warp-cycle counters, RDS) of the last warm-up step
     n_unconv = int(d_u.sum().item())
     nroots_ok = int(d_n.sum().item())
 
@@ -291,8 +291,13 @@ def main():
     useful = useful_per_poly * batch if useful_per_poly else executed
     # dominant kernel: the persistent unit kernel (phase A + systolic chase) for the pipelined RDS path, the
     # one iteration kernel otherwise; its duration is the CUDA-event time of that launch in the last warm-up step
+    lanes = int(st.get("lanes", 0))
     if prof and prof["us_main"] > 0:
-        kernel_ms, kernel_name = prof["us_main"] / 1e3, "unit_kernel<L,MH> (phase A + systolic chase behind the unit queue)"
+        kernel_ms = prof["us_main"] / 1e3
+        kernel_name = {"rds_f64": f"chain_kernel<{lanes // 32},MH> (one CTA of {lanes // 32} chained warps per polynomial: phase A + systolic chase of {lanes} bulges)" if lanes > 32
+                       else f"unit_kernel<{lanes},MH> (phase A + systolic chase behind the unit queue)",
+                       "css_c64": f"css_unit_kernel<{lanes},MH> (complex single shift: phase A + systolic chase behind the unit queue)",
+                       "pencil_f64": f"pen_unit_kernel<{lanes},MH> (companion pencil, five chains: phase A + systolic chase behind the unit queue)"}[kind]
     else:
         kernel_ms, kernel_name = st["device_ms"], "roots_reference_kernel / roots_pencil_reference_kernel (one polynomial per thread)"
     flops = useful * FLOP_PER_TURNOVER[kind]
@@ -308,23 +313,24 @@ def main():
     # (profiles/r01_c2_unit_kernel_ncu_full_keymetrics.csv); only valid for the default c2 launch
     traffic = NCU_TRAFFIC_C2 if (args.config == "c2" and not args.batch and not args.degree and not args.lanes) else None
     roofline = {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak, "traffic": traffic,
-                "traffic_note": "bytes per launch (ncu dram read+write); the reference-schedule algorithmic bytes (96 B per chase step per bulge) are ~12x larger: the systolic chase streams each rotator once per 16 bulges",
+                "traffic_note": "bytes per launch (ncu dram read+write); the reference-schedule algorithmic bytes (96 B per chase step per bulge) are ~12x larger: the systolic chase streams each rotator once per L bulges",
                 "peak_source": "DFMA probe measured live in this run (MEASURED_PEAKS.json has no FP64 entry); nominal 37.2",
                 "kernel": kernel_name, "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / st["device_ms"] if st["device_ms"] else None,
                 "useful_turnovers_per_step": useful, "executed_turnovers_per_step": executed,
                 "useful_definition": "the reference schedule's turnover count on the same inputs (CPU sample mean x batch) x 37 flop (94 complex)",
                 "hbm": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": hbm_src + " copy bandwidth",
-                        "note": "algorithmic bytes = 96 B per 7 turnovers; the path is not HBM-bound"}}
-    if prof:
+                        "note": "algorithmic bytes per chase step: RDS 96 B / 7 turnovers, CSS 208 B / 3, pencil 160 B / 11 (SURVEY 8d); the path is not HBM-bound"}}
+    if prof and prof["us_main"] > 0:
+        roofline["kernel_times_ms"] = {"setup": prof["us_setup"] / 1e3, "main": prof["us_main"] / 1e3, "small_windows": prof["us_small"] / 1e3, "finish": prof["us_finish"] / 1e3}
+    if prof and prof["cycles_units"] > 0:
         busy = max(prof["cycles_units"], 1)
         roofline["warp_cycle_shares"] = {"phase_a": prof["cycles_phase_a"] / busy, "lean_chase": prof["cycles_lean"] / busy, "fill_drain_chase": prof["cycles_general"] / busy,
                                          "queue_wait_vs_busy": prof["cycles_pop"] / busy, "lean_cycles_per_step": prof["cycles_lean"] / max(prof["steps_lean"], 1)}
-        roofline["kernel_times_ms"] = {"setup": prof["us_setup"] / 1e3, "unit_kernel": prof["us_main"] / 1e3, "small_windows": prof["us_small"] / 1e3, "finish": prof["us_finish"] / 1e3}
     line = {"metric": "polynomials/sec", "value": value, "unit": "polynomials/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config, "turnovers_per_sec": world * useful / (ms_step * 1e-3), "roofline": roofline, "cpu_baseline": cb, "e2e": e2e,
             "gpu_launches": int(st["launches"] * args.steps), "clocks": clk.summary(),
-            "stats_per_step": {k: st[k] for k in ("turnovers", "sweeps", "exceptional", "unconverged", "fat_steps", "launches")},
+            "stats_per_step": {k: st[k] for k in ("turnovers", "sweeps", "exceptional", "unconverged", "fat_steps", "launches", "lanes")},
             "unconverged": n_unconv, "roots_found": nroots_ok}
     print(json.dumps(line))
     if world > 1:

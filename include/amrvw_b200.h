@@ -80,6 +80,7 @@ typedef struct amrvw_stats {
     int64_t fat_steps;     /* pipelined multi-bulge steps */
     int64_t launches;      /* kernels launched by this call */
     double device_ms;      /* CUDA-event time of the kernels of this call */
+    int64_t lanes;         /* bulges in flight per polynomial chosen for this call (0: one-bulge schedule) */
 } amrvw_stats;
 
 /* device < 0: current device. */

@@ -570,3 +570,17 @@ def test_gpu_many_bulges_backward_error(A, oracle, L, B, n, kind):
         assert worst < 1e-10, worst
     finally:
         c.close()
+
+
+def test_gpu_css_many_bulges_backward_error(A, oracle):
+    """Complex single shift with 32 bulges per fat step on long windows: backward error at rounding level on
+    every polynomial (complex twin of the fall-back turnover for vanished sines)."""
+    c = A.Context(seed=0, schedule=A.SCHEDULE_PIPELINED, lanes_per_poly=32)
+    try:
+        rows = batch(oracle, 13, 12, 2000, kind=1, cx=True)
+        got = A.roots(rows, ctx=c)
+        assert c.last_stats["unconverged"] == 0
+        worst = max(horner_backward_error(r, g).max() for r, g in zip(rows, got))
+        assert worst < 1e-10, worst
+    finally:
+        c.close()
