@@ -185,7 +185,7 @@ static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, cons
     pr.DQ = (S*)ctx->diags[0].ptr; pr.DR = (S*)ctx->diags[1].ptr; pr.WD = (S*)ctx->diags[2].ptr;
     pr.dstack = (int*)ctx->shifts.ptr;
     pr.prof = nullptr; pr.rec = nullptr; pr.shifts = nullptr; pr.swlist = nullptr; pr.counters = nullptr;
-    if (var == V_RDS && stats) {   // warp-cycle counters ride along with the statistics (real path)
+    if (stats && var != V_PENCIL_C) {   // warp-cycle counters ride along with the statistics
         int rc = reserve(ctx, ctx->prof, 16 * sizeof(unsigned long long)); if (rc) return rc;
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->prof.ptr, 0, 16 * sizeof(unsigned long long), ctx->stream));
         pr.prof = (unsigned long long*)ctx->prof.ptr;
@@ -196,7 +196,7 @@ static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, cons
     cudaStream_t st = ctx->stream;
     int launches = 0, lanes = 0;
     ctx->times = RoundsTimes{0.f, 0.f, 0.f, 0.f};
-    ctx->prof_valid = (var == V_RDS && stats != nullptr);
+    ctx->prof_valid = (var != V_PENCIL_C && stats != nullptr);
     if (stats && !ctx->evpool[0]) for (cudaEvent_t& e : ctx->evpool) CUDA_TRY(ctx, cudaEventCreate(&e));
     if (stats) CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, st));
 

@@ -18,9 +18,10 @@
 //     m-1 is through with that index, before bulge m's turnover on it), and deposits it in D_Q at the
 //     first zero sine / the end of the window.  The push-down costs one complex multiplication per
 //     lock-step instead of a pass over memory;
-//   * shifts: the L eigenvalues of the trailing block come from the core-chasing iteration on a
-//     shared-memory copy (lane 0 of the group); the turnover is the IEEE one.  Both are the obvious
-//     next steps (dense complex Hessenberg QR shared by the lanes, division-free complex turnover).
+//   * shifts: the L / reuse eigenvalues of the trailing block come from the core-chasing iteration on a
+//     shared-memory copy (lane 0 of the group), each driving `reuse` bulges; a dense complex Hessenberg QR
+//     shared by the lanes is the obvious next step.  The chase uses the division-free complex turnover
+//     inline, with the lane's state in registers.
 //
 // Roots agree with the reference schedule to backward-error level (tests: minimum-distance matching
 // against the oracle); there is no bit-level twin of this schedule in the oracle yet.
@@ -91,6 +92,18 @@ AMRVW_DI void css_pass_R(CssIdx& w0, CssIdx& w1, Rot<cplx>& U) {
     U = r1; w0.b = r2; w1.b = r3;
     turnover(w1.c, w0.c, U, r1, r2, r3);      // pass_asc on Ct: U back at i
     U = r1; w1.c = r2; w0.c = r3;
+}
+// the same two passes for the systolic lanes: inline division-free turnovers, state in registers
+AMRVW_DI void css_lane_regular(CssIdx& w0, CssIdx& w1, Rot<cplx>& U) {
+    css_pass_diag(w0.dr, w1.dr, U);
+    Rot<cplx> r1, r2, r3;
+    turnover_fast(w0.b, w1.b, U, r1, r2, r3);
+    U = r1; w0.b = r2; w1.b = r3;
+    turnover_fast(w1.c, w0.c, U, r1, r2, r3);
+    U = r1; w1.c = r2; w0.c = r3;
+    css_pass_diag(w0.dq, w1.dq, U);
+    turnover_fast(w0.q, w1.q, U, r1, r2, r3);
+    U = r1; w0.q = r2; w1.q = r3;
 }
 // regular position (CSS.jl:64-75): through R, then through D_Q and Q; the bulge leaves at i+1
 AMRVW_NI void css_step_regular(CssLane& z) {
@@ -231,7 +244,7 @@ AMRVW_NI int css_unit_driver(const Problem<cplx>& pr, const PipeParams pp, const
             nb = L; mode = 2;
             break;
         } else {
-            nb = min(L - 1, delta - 1);       // rotators of the trailing block: nb + 1 shifts
+            nb = min(L / pp.reuse - 1, delta - 1);       // rotators of the trailing block: nb + 1 shifts, each driving `reuse` bulges
             rec.st.fat_steps++;
             ctr.it_count -= 1;
             mode = 3;
@@ -252,7 +265,7 @@ template <int MH> struct __align__(16) CssShiftScratch {
 // the nb + 1 shifts of a pending fat step: eigenvalues of the trailing block, by the one-bulge iteration
 // on a shared-memory copy whose top rotator is made diagonal (lane 0 of the group; the others stage)
 template <int MH>
-AMRVW_NI void css_unit_shifts(const Problem<cplx>& pr, const int L, const long long p, CssShiftScratch<MH>& ws, const int lane, const unsigned gmask) {
+AMRVW_NI void css_unit_shifts(const Problem<cplx>& pr, const PipeParams pp, const int L, const long long p, CssShiftScratch<MH>& ws, const int lane, const unsigned gmask) {
     PolyRec rec = load_rec(pr.rec + p);
     const int m = rec.nb, stop = rec.ls.ctr.stop_index, k0 = stop - m;
     Fact<cplx, false> F = make_fact<cplx, false>(pr, p, rec.N);
@@ -281,8 +294,9 @@ AMRVW_NI void css_unit_shifts(const Problem<cplx>& pr, const int L, const long l
         drive_window(W, k0 + 1, stop, c2, Es, 20ll * (m + 1), pr.seed, (uint64_t)p, rec.ls.ord, sub, ReferenceStep());
         rec.serial_turnovers += W.turnovers;
         Shifts* shl = pr.shifts + p * L;
-        for (int t = 0; t <= m; ++t) { shl[t].e1 = ws.e[t]; shl[t].e2 = cplx(0.0, 0.0); }
-        rec.nb = m + 1;
+        for (int rep = 0; rep < pp.reuse; ++rep)
+            for (int t = 0; t <= m; ++t) { shl[rep * (m + 1) + t].e1 = ws.e[t]; shl[rep * (m + 1) + t].e2 = cplx(0.0, 0.0); }
+        rec.nb = (m + 1) * pp.reuse;
         rec.mode = 1;
         store_rec(pr.rec + p, rec);
     }
@@ -297,8 +311,12 @@ __global__ void __launch_bounds__(32, 8) css_unit_kernel(Problem<cplx> pr, PipeP
     const int lane32 = threadIdx.x & 31;
     const int grp = lane32 / L, lane = lane32 % L;
 
+    long long pc_all = 0, pc_a = 0, pc_pop = 0;      // warp-cycle accounting (amrvw_last_profile)
+    long long pn_steps = 0;
+    int pn_units = 0;
     for (;;) {
         // ---------------- pop a unit
+        const long long pc_p0 = clock64();
         int u = -1;
         if (lane32 == 0) {
             const unsigned k = atomicAdd(&q->head, 1u);
@@ -314,6 +332,8 @@ __global__ void __launch_bounds__(32, 8) css_unit_kernel(Problem<cplx> pr, PipeP
         u = __shfl_sync(0xffffffffu, u, 0);
         if (u < 0) break;
         __threadfence();
+        const long long pc_u0 = clock64();
+        pc_pop += pc_u0 - pc_p0;
         UnitPark* const up = park + u;
         const long long p = (long long)u * G + grp;
         int t0 = __ldcg(&up->t);
@@ -326,11 +346,13 @@ __global__ void __launch_bounds__(32, 8) css_unit_kernel(Problem<cplx> pr, PipeP
             {
                 const int mg = __shfl_sync(0xffffffffu, m0, grp * L);
                 const unsigned gmask = (L == 32 ? 0xffffffffu : ((1u << L) - 1u)) << (grp * L);
-                if (mg == 3) css_unit_shifts<MH>(pr, L, p, shift_scratch[grp], lane, gmask);
+                if (mg == 3) css_unit_shifts<MH>(pr, pp, L, p, shift_scratch[grp], lane, gmask);
                 __syncwarp();
             }
+            pc_a += clock64() - pc_u0;
             if (!__any_sync(0xffffffffu, m0 != 0)) {
                 if (lane32 == 0) atomicSub(&q->remaining, 1u);
+                pc_all += clock64() - pc_u0;
                 continue;
             }
             if (lane == 0) {
@@ -364,16 +386,21 @@ __global__ void __launch_bounds__(32, 8) css_unit_kernel(Problem<cplx> pr, PipeP
             F = make_fact<cplx, false>(pr, p, N);
             dstack = pr.dstack + (pr.offsets[p] + (long long)pr.extra * p);
         }
+        // the lane's state lives in registers: only copies of it are handed to the out-of-line creation and
+        // last-position steps and to the parking loops (a reference to z itself would pin it in local memory:
+        // 8% of the instructions of the first version were LDL/STL, 21% of its stall samples long-scoreboard)
         CssLane z;
         if (t0 == 0) {
             z.w0 = css_identity_index(); z.w1 = z.w0;
             z.U = make_rot<cplx>(cplx(1.0, 0.0), 0.0); z.U.pad = 0.0;
             z.ca = cplx(1.0, 0.0); z.alive = 0; z.pad[0] = z.pad[1] = z.pad[2] = 0;
         } else {
+            CssLane y;
             const double2* src = reinterpret_cast<const double2*>(parked + ((long long)u * 32 + lane32));
-            double2* dst = reinterpret_cast<double2*>(&z);
+            double2* dst = reinterpret_cast<double2*>(&y);
 #pragma unroll
             for (int i = 0; i < (int)(sizeof(CssLane) / 16); ++i) dst[i] = __ldcg(src + i);
+            z = y;
         }
         const bool has_bulge = act && lane < nb;
         cplx shift = cplx(0.0, 0.0);
@@ -407,9 +434,9 @@ __global__ void __launch_bounds__(32, 8) css_unit_kernel(Problem<cplx> pr, PipeP
             }
             const int i = knew - 1;
             if (has_bulge && tp >= 1 && i <= stop) {
-                if (tp == 1) css_create(z, F, start, stop, shift);
-                if (i < stop) css_step_regular(z);
-                else css_step_final(z);
+                if (tp == 1) { CssLane y = z; css_create(y, F, start, stop, shift); z = y; }
+                if (i < stop) css_lane_regular(z.w0, z.w1, z.U);
+                else { CssLane y = z; css_step_final(y); z = y; }
                 nturn += (i < stop) ? 3 : 2;
             }
             // retire: the last lane writes index i back
@@ -421,8 +448,9 @@ __global__ void __launch_bounds__(32, 8) css_unit_kernel(Problem<cplx> pr, PipeP
         sp = __shfl_sync(0xffffffffu, sp, grp * L + L - 1);
         for (int d = L / 2; d >= 1; d >>= 1) nturn += __shfl_down_sync(0xffffffffu, nturn, d, L);
         if (t1 < Tmax) {
+            const CssLane y = z;
             double2* dst = reinterpret_cast<double2*>(parked + ((long long)u * 32 + lane32));
-            const double2* src = reinterpret_cast<const double2*>(&z);
+            const double2* src = reinterpret_cast<const double2*>(&y);
 #pragma unroll
             for (int i = 0; i < (int)(sizeof(CssLane) / 16); ++i) __stcg(dst + i, src[i]);
             if (lane == 0) { __stcg(&up->sp[grp], sp); __stcg(&up->nturn[grp], __ldcg(&up->nturn[grp]) + nturn); }
@@ -445,6 +473,16 @@ __global__ void __launch_bounds__(32, 8) css_unit_kernel(Problem<cplx> pr, PipeP
             const unsigned k = atomicAdd(&q->tail, 1u);
             atomicExch(slots + (k & mask), u);
         }
+        pn_steps += t1 - t0; pn_units += 1;
+        pc_all += clock64() - pc_u0;
+    }
+    if (pr.prof && lane32 == 0) {
+        atomicAdd(pr.prof + 0, (unsigned long long)pc_all);
+        atomicAdd(pr.prof + 1, (unsigned long long)pc_a);
+        atomicAdd(pr.prof + 3, (unsigned long long)(pc_all - pc_a));
+        atomicAdd(pr.prof + 5, (unsigned long long)pn_steps);
+        atomicAdd(pr.prof + 7, (unsigned long long)pn_units);
+        atomicAdd(pr.prof + 13, (unsigned long long)pc_pop);
     }
 }
 
@@ -593,7 +631,11 @@ static cudaError_t launch_css_pipelined(Problem<cplx> pr, const amrvw_options& o
     if (L > 32) L = 32;      // chained warps exist for the real rank-one path only
     if (lanes_out) *lanes_out = L;
     PipeParams pp;
-    pp.reuse = 1;
+    // bulges per shift: the trailing block has order L / reuse.  Its eigenvalues come from a core-chasing
+    // sub-solve on ONE lane, 40-49% of the busy warp-cycles with reuse = 1 at L = 16; config 3 (gpurun_out/sweep62.log):
+    // reuse 1 530 ms, 2 336 ms (1.04x the turnovers), 4 316 ms (1.30x)
+    pp.reuse = opt.shift_reuse ? opt.shift_reuse : (L >= 16 ? 4 : (L >= 8 ? 2 : 1));
+    while (pp.reuse > 1 && L / pp.reuse < 2) pp.reuse /= 2;
     pp.small = opt.small_window ? opt.small_window : (L + 8 > 24 ? L + 8 : 24);
     if (pp.small < L) pp.small = L;
     if (pp.small > 96) pp.small = 96;

@@ -59,8 +59,10 @@ AMRVW_DI void pen_pass_R(PenIdx& x0, PenIdx& x1, Rot<double>& U) {
     turnover_fast(x0.b, x1.b, U, r1, r2, r3); U = r1; x0.b = r2; x1.b = r3;
     turnover_fast(x1.c, x0.c, U, r1, r2, r3); U = r1; x1.c = r2; x0.c = r3;
 }
-// regular position (RDS.jl:42-70, 97-108): V@i+1 and U@i through R, then through Q, then the limb
-AMRVW_NI void pen_step_regular(PenLane& z) {
+// regular position (RDS.jl:42-70, 97-108): V@i+1 and U@i through R, then through Q, then the limb.
+// Inline: the lane's state stays in registers (only the creation and last-position steps and the parking
+// loops work on copies in local memory)
+AMRVW_DI void pen_step_regular(PenLane& z) {
     pen_pass_R(z.w1, z.w2, z.V);
     pen_pass_R(z.w0, z.w1, z.U);
     Rot<double> r1, r2, r3;
@@ -332,8 +334,12 @@ __global__ void __launch_bounds__(32, 8) pen_unit_kernel(Problem<double> pr, Pip
     const int lane32 = threadIdx.x & 31;
     const int grp = lane32 / L, lane = lane32 % L;
 
+    long long pc_all = 0, pc_a = 0, pc_pop = 0;      // warp-cycle accounting (amrvw_last_profile)
+    long long pn_steps = 0;
+    int pn_units = 0;
     for (;;) {
         // ---------------- pop a unit
+        const long long pc_p0 = clock64();
         int u = -1;
         if (lane32 == 0) {
             const unsigned k = atomicAdd(&q->head, 1u);
@@ -349,6 +355,8 @@ __global__ void __launch_bounds__(32, 8) pen_unit_kernel(Problem<double> pr, Pip
         u = __shfl_sync(0xffffffffu, u, 0);
         if (u < 0) break;
         __threadfence();
+        const long long pc_u0 = clock64();
+        pc_pop += pc_u0 - pc_p0;
         UnitPark* const up = park + u;
         const long long p = (long long)u * G + grp;
         int t0 = __ldcg(&up->t);
@@ -364,8 +372,10 @@ __global__ void __launch_bounds__(32, 8) pen_unit_kernel(Problem<double> pr, Pip
                 if (mg == 3) pen_unit_shifts<MH>(pr, pp, L, p, shift_scratch[grp], lane, gmask);
                 __syncwarp();
             }
+            pc_a += clock64() - pc_u0;
             if (!__any_sync(0xffffffffu, m0 != 0)) {
                 if (lane32 == 0) atomicSub(&q->remaining, 1u);
+                pc_all += clock64() - pc_u0;
                 continue;
             }
             if (lane == 0) {
@@ -404,10 +414,12 @@ __global__ void __launch_bounds__(32, 8) pen_unit_kernel(Problem<double> pr, Pip
             z.w0 = pen_identity_index(); z.w1 = z.w0; z.w2 = z.w0;
             z.U = z.V = z.W = make_rot<double>(1.0, 0.0);
         } else {
+            PenLane y;
             const double2* src = reinterpret_cast<const double2*>(parked + ((long long)u * 32 + lane32));
-            double2* dst = reinterpret_cast<double2*>(&z);
+            double2* dst = reinterpret_cast<double2*>(&y);
 #pragma unroll
             for (int i = 0; i < (int)(sizeof(PenLane) / 16); ++i) dst[i] = __ldcg(src + i);
+            z = y;
         }
         const bool has_bulge = act && lane < nb;
         double pbot = 1.0;
@@ -426,9 +438,9 @@ __global__ void __launch_bounds__(32, 8) pen_unit_kernel(Problem<double> pr, Pip
             z.w0 = z.w1; z.w1 = z.w2; z.w2 = in;
             const int i = start + tp - 2;   // position of this lane's bulge; window = indices i..i+2
             if (has_bulge && tp >= 2 && i <= stop - 1) {
-                if (tp == 2) { pen_create(z, F, start, stop, mode, pr.shifts + p * L, lane, pr.seed, (uint64_t)p, ord0 + lane); nturn += 1; }
+                if (tp == 2) { PenLane y = z; pen_create(y, F, start, stop, mode, pr.shifts + p * L, lane, pr.seed, (uint64_t)p, ord0 + lane); z = y; nturn += 1; }
                 if (i <= stop - 2) pen_step_regular(z);
-                else pen_step_final(z, pbot);
+                else { PenLane y = z; pen_step_final(y, pbot); z = y; }
                 nturn += (i <= stop - 2) ? 11 : 13;
             }
             // retire: the last lane writes index i back
@@ -440,8 +452,9 @@ __global__ void __launch_bounds__(32, 8) pen_unit_kernel(Problem<double> pr, Pip
         sp = __shfl_sync(0xffffffffu, sp, grp * L + L - 1);
         for (int d = L / 2; d >= 1; d >>= 1) nturn += __shfl_down_sync(0xffffffffu, nturn, d, L);
         if (t1 < Tmax) {
+            const PenLane y = z;
             double2* dst = reinterpret_cast<double2*>(parked + ((long long)u * 32 + lane32));
-            const double2* src = reinterpret_cast<const double2*>(&z);
+            const double2* src = reinterpret_cast<const double2*>(&y);
 #pragma unroll
             for (int i = 0; i < (int)(sizeof(PenLane) / 16); ++i) __stcg(dst + i, src[i]);
             if (lane == 0) { __stcg(&up->sp[grp], sp); __stcg(&up->nturn[grp], __ldcg(&up->nturn[grp]) + nturn); }
@@ -464,6 +477,16 @@ __global__ void __launch_bounds__(32, 8) pen_unit_kernel(Problem<double> pr, Pip
             const unsigned k = atomicAdd(&q->tail, 1u);
             atomicExch(slots + (k & mask), u);
         }
+        pn_steps += t1 - t0; pn_units += 1;
+        pc_all += clock64() - pc_u0;
+    }
+    if (pr.prof && lane32 == 0) {
+        atomicAdd(pr.prof + 0, (unsigned long long)pc_all);
+        atomicAdd(pr.prof + 1, (unsigned long long)pc_a);
+        atomicAdd(pr.prof + 3, (unsigned long long)(pc_all - pc_a));
+        atomicAdd(pr.prof + 5, (unsigned long long)pn_steps);
+        atomicAdd(pr.prof + 7, (unsigned long long)pn_units);
+        atomicAdd(pr.prof + 13, (unsigned long long)pc_pop);
     }
 }
 

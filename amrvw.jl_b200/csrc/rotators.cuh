@@ -480,10 +480,27 @@ AMRVW_DI void turnover_robust(const Rot<cplx> q1, const Rot<cplx> q2, const Rot<
     r2 = make_rot<cplx>(c5, s5);
     r3 = h > 0.0 ? make_rot<cplx>(conj_(a) / h, b / h) : make_rot<cplx>(cplx(1.0, 0.0), 0.0);
 }
+AMRVW_NI Rot3<cplx> turnover_robust_call(const Rot<cplx> q1, const Rot<cplx> q2, const Rot<cplx> q3) {
+    Rot3<cplx> o;
+    turnover_robust(q1, q2, q3, o.r1, o.r2, o.r3);
+    return o;
+}
 AMRVW_NI Rot3<cplx> turnover_fast_call(const Rot<cplx> q1, const Rot<cplx> q2, const Rot<cplx> q3) {
     Rot3<cplx> o;
-    if (!turnover_fast_try(q1, q2, q3, o.r1, o.r2, o.r3)) turnover_robust(q1, q2, q3, o.r1, o.r2, o.r3);
+    if (!turnover_fast_try(q1, q2, q3, o.r1, o.r2, o.r3)) o = turnover_robust_call(q1, q2, q3);
     return o;
+}
+// inline fast path, out-of-line fall-back: for the systolic lanes (the serial code calls turnover())
+AMRVW_DI void turnover_fast(const Rot<cplx> q1, const Rot<cplx> q2, const Rot<cplx> q3, Rot<cplx>& r1, Rot<cplx>& r2, Rot<cplx>& r3) {
+#ifdef AMRVW_STRICT
+    const Rot3<cplx> o = turnover_ieee_call<cplx>(q1, q2, q3);
+    r1 = o.r1; r2 = o.r2; r3 = o.r3;
+#else
+    if (!turnover_fast_try(q1, q2, q3, r1, r2, r3)) {
+        const Rot3<cplx> o = turnover_robust_call(q1, q2, q3);
+        r1 = o.r1; r2 = o.r2; r3 = o.r3;
+    }
+#endif
 }
 AMRVW_DI void turnover(const Rot<cplx> q1, const Rot<cplx> q2, const Rot<cplx> q3, Rot<cplx>& r1, Rot<cplx>& r2, Rot<cplx>& r3) {
 #ifdef AMRVW_STRICT

@@ -366,13 +366,13 @@ def test_gpu_fast_complex_turnover_selftest(ctx):
 
 
 # ------------------------------------------------------------------ complex single shift on the unit queue
-@pytest.mark.parametrize("L", [4, 8, 16, 32])
-def test_gpu_css_pipelined_lanes(A, oracle, L):
+@pytest.mark.parametrize("L,reuse", [(4, 0), (8, 0), (16, 0), (32, 0), (16, 1), (32, 2), (8, 4)])
+def test_gpu_css_pipelined_lanes(A, oracle, L, reuse):
     """The pipelined complex path for every lane-group width: bulges two indices apart, the creation
     phase of each bulge carried by its lane (diagonal.jl:199-225 without the pass over Q), deferred
     small windows.  Ragged batch so that groups of one warp see different windows; both schedules of
     the library must agree with the oracle's reference schedule root by root."""
-    c = A.Context(seed=0, schedule=A.SCHEDULE_PIPELINED, lanes_per_poly=L)
+    c = A.Context(seed=0, schedule=A.SCHEDULE_PIPELINED, lanes_per_poly=L, shift_reuse=reuse)
     try:
         degs = [40, 41, 64, 97, 130, 200, 257, 33, 5, 3, 2, 1, 350]
         rows = []
