@@ -71,6 +71,37 @@ AMRVW_DI CssIdx css_shfl_up(const CssIdx& x, const int width) {
     for (int i = 0; i < (int)(sizeof(CssIdx) / 8); ++i) dst[i] = __shfl_up_sync(0xffffffffu, src[i], 1, width);
     return o;
 }
+// look-ahead ring of a group's feeding lane (the same scheme as the real path, pipeline.cuh): the five
+// arrays of index k go global -> shared with eight 16-byte cp.async.cg, AMRVW_RING - 1 steps ahead of their
+// use.  (With a plain load one step ahead ptxas kept the load next to its first use: one DMUL carried 18%
+// of all stall samples, long scoreboard: profiles/.)
+#define AMRVW_CSS_SLOT 128   // bytes per ring slot: Q, B, Ct (32 each), D_Q, D_R (16 each)
+AMRVW_DI void css_prefetch_index(const unsigned slot_sa, const Fact<cplx, false>& F, const int k) {
+    const char* q = reinterpret_cast<const char*>(F.Q + k);
+    const char* b = reinterpret_cast<const char*>(F.B + k);
+    const char* c = reinterpret_cast<const char*>(F.Ct + k);
+    cp_async16_sa(slot_sa, q); cp_async16_sa(slot_sa + 16, q + 16);
+    cp_async16_sa(slot_sa + 32, b); cp_async16_sa(slot_sa + 48, b + 16);
+    cp_async16_sa(slot_sa + 64, c); cp_async16_sa(slot_sa + 80, c + 16);
+    cp_async16_sa(slot_sa + 96, F.DQ + k); cp_async16_sa(slot_sa + 112, F.DR + k);
+}
+AMRVW_DI double2 lds_d2(const unsigned sa) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(sa) : "memory");
+    return v;
+}
+AMRVW_DI CssIdx css_read_slot(const unsigned slot_sa) {
+    CssIdx x;
+    double2 a = lds_d2(slot_sa), b = lds_d2(slot_sa + 16);
+    x.q.c = cplx(a.x, a.y); x.q.s = b.x; x.q.pad = 0.0;
+    a = lds_d2(slot_sa + 32); b = lds_d2(slot_sa + 48);
+    x.b.c = cplx(a.x, a.y); x.b.s = b.x; x.b.pad = 0.0;
+    a = lds_d2(slot_sa + 64); b = lds_d2(slot_sa + 80);
+    x.c.c = cplx(a.x, a.y); x.c.s = b.x; x.c.pad = 0.0;
+    a = lds_d2(slot_sa + 96); b = lds_d2(slot_sa + 112);
+    x.dq = cplx(a.x, a.y); x.dr = cplx(b.x, b.y);
+    return x;
+}
 AMRVW_DI CssIdx css_identity_index() {
     CssIdx x;
     x.q = make_rot<cplx>(cplx(1.0, 0.0), 0.0); x.b = x.q; x.c = x.q; x.q.pad = x.b.pad = x.c.pad = 0.0;
@@ -130,18 +161,66 @@ AMRVW_NI void css_create(CssLane& z, const Fact<cplx, false>& F, const int start
         wm.q = ldcg_crot(F.Q + start - 1); wm.dq = ldcg_cplx(F.DQ + start - 1);       // Q[0], D_Q[0] are sentinels
         if (start > 1) { wm.b = ldcg_crot(F.B + start - 1); wm.c = ldcg_crot(F.Ct + start - 1); wm.dr = ldcg_cplx(F.DR + start - 1); }
     }
+    cplx c; double sn;
+    cplx dph;
+#ifndef AMRVW_STRICT
+    // Only A11 and A21 of the block at `start` enter the bulge (create-bulge.jl:105-108): written out from
+    // the entry formulas (chains.jl:109-158, rfactorization.jl:139-170) with reciprocals instead of the IEEE
+    // complex divisions of diagonal_block.  The bulge only chooses the similarity -- it is applied exactly,
+    // by turnovers -- so its last bits steer convergence, not accuracy (same argument as create_bulge_fast).
+    bool fast = false;
+    {
+        const Rot<cplx> qm = wm.q, q0 = z.w0.q;
+        const cplx qji = (-qm.s) * wm.dq, qjj = conj_(qm.c) * q0.c * z.w0.dq, qkj = (-q0.s) * z.w0.dq;
+        const double ig0 = rcp_(z.w0.c.s);
+        const cplx wjj = (-z.w0.b.s) * z.w0.dr;                   // w(j,j) D_R[j]
+        const cplx rjj = wjj * ig0;
+        cplx rij = cplx(0.0, 0.0);
+        if (start > 1) {
+            const double igm = rcp_(wm.c.s);
+            const cplx wij = conj_(wm.b.c) * z.w0.b.c;            // w(i,j), i = j - 1
+            rij = (wij * z.w0.dr) * igm - (wm.c.c * conj_(z.w0.c.c)) * (igm * ig0) * wjj;
+        }
+        const cplx a = (qji * rij + qjj * rjj) - shift, b = qkj * rjj;
+        // givensrot(a, b) (transformations.jl:28-31): s = |b| / h, c = b conj(a) / (|b| h), h^2 = |a|^2 + |b|^2
+        const double f2 = abs2_(b), g2 = abs2_(a), h2 = f2 + g2;
+        if (f2 >= 1e-280 && h2 <= 1e280 && f2 > fmax(g2, 1.0) * AMRVW_SAFMIN) {
+            const double ih = rsqrt_nr(h2), ib = rsqrt_nr(f2);
+            sn = (f2 * ib) * ih;
+            c = (b * conj_(a)) * (ib * ih);
+            // fuse(R, Q[start]) (transformations.jl:101-118) with 1/|v| by rsqrt
+            const Rot<cplx> qq = z.w0.q;
+            const cplx u = c * qq.c - sn * qq.s;
+            const cplx v = c * qq.s + sn * conj_(qq.c);
+            const double v2 = abs2_(v);
+            if (v2 >= 1e-280 && v2 <= 1e280) {
+                const double iv = rsqrt_nr(v2);
+                const cplx alpha = v * iv;
+                cplx cc = u * alpha;
+                double ss = v2 * iv;
+                polish(cc, ss);
+                dph = conj_(alpha);
+                z.U = make_rot<cplx>(conj_(c), -sn);
+                z.w0.q = make_rot<cplx>(cc, ss);
+                fast = true;
+            }
+        }
+    }
+    if (!fast)
+#endif
+    {
     Rot<cplx> lq[3] = {wm.q, z.w0.q, z.w1.q}, lb[3] = {wm.b, z.w0.b, z.w1.b}, lc[3] = {wm.c, z.w0.c, z.w1.c};
     cplx ldq[3] = {wm.dq, z.w0.dq, z.w1.dq}, ldr[3] = {wm.dr, z.w0.dr, z.w1.dr};
     Fact<cplx, false> Fl = F;
     Fl.Q = lq - (start - 1); Fl.B = lb - (start - 1); Fl.Ct = lc - (start - 1); Fl.DQ = ldq - (start - 1); Fl.DR = ldr - (start - 1);
     cplx A[4];
     diagonal_block(Fl, start, A);
-    cplx c, nrm; double sn;
+    cplx nrm;
     givensrot(A[0] - shift, A[2], c, sn, nrm);
     const Rot<cplx> R = make_rot<cplx>(c, sn);
     z.U = adjoint(R);
-    cplx dph;
     z.w0.q = fuse(R, z.w0.q, dph);
+    }
     // push_phase (diagonal.jl:199-225), first two actions; the rest travels with the bulge
     z.w0.dq = z.w0.dq * dph;
     z.ca = conj_(dph);
@@ -308,8 +387,10 @@ template <int L, int MH>
 __global__ void __launch_bounds__(32, 8) css_unit_kernel(Problem<cplx> pr, PipeParams pp, RoundQueue* q, int* slots, unsigned mask, UnitPark* park, CssLane* parked, int seg_steps) {
     constexpr int G = 32 / L;
     __shared__ CssShiftScratch<MH> shift_scratch[G];
+    __shared__ __align__(16) unsigned char css_ring[G * AMRVW_RING * AMRVW_CSS_SLOT];
     const int lane32 = threadIdx.x & 31;
     const int grp = lane32 / L, lane = lane32 % L;
+    const unsigned stage_sa = (unsigned)__cvta_generic_to_shared(css_ring + grp * (AMRVW_RING * AMRVW_CSS_SLOT));
 
     long long pc_all = 0, pc_a = 0, pc_pop = 0;      // warp-cycle accounting (amrvw_last_profile)
     long long pn_steps = 0;
@@ -414,16 +495,22 @@ __global__ void __launch_bounds__(32, 8) css_unit_kernel(Problem<cplx> pr, PipeP
                 shift = ldcg_cplx(&pr.shifts[p * L + lane].e1);
             }
         }
-        // lane 0 reads one index ahead
-        CssIdx nxt = css_identity_index();
-        if (act && lane == 0) nxt = css_load_index(F, min(start + t0, stop + 1));
+        // lane 0 reads AMRVW_RING - 1 indices ahead, through shared memory
+        if (act && lane == 0) {
+            for (int a = 0; a < AMRVW_RING - 1; ++a) {
+                css_prefetch_index(stage_sa + ((t0 + a) & (AMRVW_RING - 1)) * AMRVW_CSS_SLOT, F, min(start + t0 + a, stop + 1));
+                cp_async_commit();
+            }
+        }
         for (int t = t0; t < t1; ++t) {
             const int tp = t - 2 * lane;
             // ingest: the index the previous lane finished last step (lane 0: from memory)
             CssIdx in = css_shfl_up(z.w0, L);
             if (lane == 0) {
-                in = nxt;
-                if (act) nxt = css_load_index(F, min(start + t + 1, stop + 1));
+                cp_async_wait_ring();
+                in = css_read_slot(stage_sa + (t & (AMRVW_RING - 1)) * AMRVW_CSS_SLOT);
+                if (act) css_prefetch_index(stage_sa + ((t + AMRVW_RING - 1) & (AMRVW_RING - 1)) * AMRVW_CSS_SLOT, F, min(start + t + AMRVW_RING - 1, stop + 1));
+                cp_async_commit();
             }
             z.w0 = z.w1; z.w1 = in;
             const int knew = start + tp;          // index just ingested; the bulge sits at knew - 1
@@ -445,6 +532,7 @@ __global__ void __launch_bounds__(32, 8) css_unit_kernel(Problem<cplx> pr, PipeP
                 if (i <= stop && fabs(z.w0.q.s) <= AMRVW_EPS) dstack[sp++] = i;
             }
         }
+        if (lane == 0) cp_async_wait_all();   // drain look-ahead requests past the end of the segment
         sp = __shfl_sync(0xffffffffu, sp, grp * L + L - 1);
         for (int d = L / 2; d >= 1; d >>= 1) nturn += __shfl_down_sync(0xffffffffu, nturn, d, L);
         if (t1 < Tmax) {

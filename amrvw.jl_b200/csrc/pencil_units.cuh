@@ -38,6 +38,17 @@ AMRVW_DI PenIdx pen_load_index(const Fact<double, true>& F, const int k) {
     x.q = ldcg_rot(F.Q + k); x.b = ldcg_rot(F.B + k); x.c = ldcg_rot(F.Ct + k); x.wb = ldcg_rot(F.WB + k); x.wc = ldcg_rot(F.WCt + k);
     return x;
 }
+// look-ahead ring of the feeding lane: five 16-byte cp.async.cg per index, AMRVW_RING - 1 steps ahead
+#define AMRVW_PEN_SLOT 80
+AMRVW_DI void pen_prefetch_index(const unsigned slot_sa, const Fact<double, true>& F, const int k) {
+    cp_async16_sa(slot_sa, F.Q + k); cp_async16_sa(slot_sa + 16, F.B + k); cp_async16_sa(slot_sa + 32, F.Ct + k);
+    cp_async16_sa(slot_sa + 48, F.WB + k); cp_async16_sa(slot_sa + 64, F.WCt + k);
+}
+AMRVW_DI PenIdx pen_read_slot(const unsigned slot_sa) {
+    PenIdx x;
+    x.q = lds_rot(slot_sa); x.b = lds_rot(slot_sa + 16); x.c = lds_rot(slot_sa + 32); x.wb = lds_rot(slot_sa + 48); x.wc = lds_rot(slot_sa + 64);
+    return x;
+}
 AMRVW_DI void pen_store_index(const Fact<double, true>& F, const int k, const PenIdx& x) {
     stg_rot(F.Q + k, x.q); stg_rot(F.B + k, x.b); stg_rot(F.Ct + k, x.c); stg_rot(F.WB + k, x.wb); stg_rot(F.WCt + k, x.wc);
 }
@@ -331,8 +342,10 @@ template <int L, int MH>
 __global__ void __launch_bounds__(32, 8) pen_unit_kernel(Problem<double> pr, PipeParams pp, RoundQueue* q, int* slots, unsigned mask, UnitPark* park, PenLane* parked, int seg_steps) {
     constexpr int G = 32 / L;
     __shared__ PenShiftScratch<MH> shift_scratch[G];
+    __shared__ __align__(16) unsigned char pen_ring[G * AMRVW_RING * AMRVW_PEN_SLOT];
     const int lane32 = threadIdx.x & 31;
     const int grp = lane32 / L, lane = lane32 % L;
+    const unsigned stage_sa = (unsigned)__cvta_generic_to_shared(pen_ring + grp * (AMRVW_RING * AMRVW_PEN_SLOT));
 
     long long pc_all = 0, pc_a = 0, pc_pop = 0;      // warp-cycle accounting (amrvw_last_profile)
     long long pn_steps = 0;
@@ -424,16 +437,22 @@ __global__ void __launch_bounds__(32, 8) pen_unit_kernel(Problem<double> pr, Pip
         const bool has_bulge = act && lane < nb;
         double pbot = 1.0;
         if (act) pbot = sign_(ldcg_rot(F.Q + stop + 1).c);      // static during the fat step; Q[N] is the (1,0) sentinel
-        // lane 0 reads one index ahead
-        PenIdx nxt = pen_identity_index();
-        if (act && lane == 0) nxt = pen_load_index(F, min(start + t0, stop + 1));
+        // lane 0 reads AMRVW_RING - 1 indices ahead, through shared memory
+        if (act && lane == 0) {
+            for (int a = 0; a < AMRVW_RING - 1; ++a) {
+                pen_prefetch_index(stage_sa + ((t0 + a) & (AMRVW_RING - 1)) * AMRVW_PEN_SLOT, F, min(start + t0 + a, stop + 1));
+                cp_async_commit();
+            }
+        }
         for (int t = t0; t < t1; ++t) {
             const int tp = t - 3 * lane;
             // ingest: the index the previous lane finished last step (lane 0: from memory)
             PenIdx in = pen_shfl_up(z.w0, L);
             if (lane == 0) {
-                in = nxt;
-                if (act) nxt = pen_load_index(F, min(start + t + 1, stop + 1));
+                cp_async_wait_ring();
+                in = pen_read_slot(stage_sa + (t & (AMRVW_RING - 1)) * AMRVW_PEN_SLOT);
+                if (act) pen_prefetch_index(stage_sa + ((t + AMRVW_RING - 1) & (AMRVW_RING - 1)) * AMRVW_PEN_SLOT, F, min(start + t + AMRVW_RING - 1, stop + 1));
+                cp_async_commit();
             }
             z.w0 = z.w1; z.w1 = z.w2; z.w2 = in;
             const int i = start + tp - 2;   // position of this lane's bulge; window = indices i..i+2
@@ -449,6 +468,7 @@ __global__ void __launch_bounds__(32, 8) pen_unit_kernel(Problem<double> pr, Pip
                 if (i <= stop && fabs(z.w0.q.s) <= AMRVW_EPS) dstack[sp++] = i;
             }
         }
+        if (lane == 0) cp_async_wait_all();   // drain look-ahead requests past the end of the segment
         sp = __shfl_sync(0xffffffffu, sp, grp * L + L - 1);
         for (int d = L / 2; d >= 1; d >>= 1) nturn += __shfl_down_sync(0xffffffffu, nturn, d, L);
         if (t1 < Tmax) {

@@ -561,7 +561,7 @@ static void choose_pipe_params(const amrvw_options& opt, long long nbatch, int m
         if (degree >= 1200 && nbatch * 32 <= (long long)sm_count * 410) L = 32;
         if (L == 32 && degree >= 2500 && nbatch <= (long long)sm_count * 3) L = 128;
     }
-    pp.reuse = opt.shift_reuse ? opt.shift_reuse : 2;
+    pp.reuse = opt.shift_reuse ? opt.shift_reuse : (L == 32 ? 4 : 2);   // 32 lanes: 16 shifts x 4 beat 32 x 2 by 4-8% (gpurun_out/sweep63.log)
     if (pp.reuse > L / 2) pp.reuse = L / 2 > 0 ? L / 2 : 1;
     while (2 * L / pp.reuse > 64) pp.reuse *= 2;     // the largest dense trailing block is 64 x 64
     const int mshift = 2 * L / pp.reuse;

@@ -584,3 +584,21 @@ def test_gpu_css_many_bulges_backward_error(A, oracle):
         assert worst < 1e-10, worst
     finally:
         c.close()
+
+
+def test_gpu_full_size_c5_properties(A, ctx, oracle):
+    """BASELINE config 5, one GPU's share at full size (64 polynomials of degree 10 000, U[0,1) - 1/2): the
+    automatic choice is four chained warps per polynomial (128 bulges per fat step).  Nothing unconverged,
+    every root finite, conjugate pairing exact, sorted by real part, and Horner backward error at rounding
+    level on a sample (np.polyval is O(n^2) per polynomial)."""
+    B, n = 64, 10000
+    rows = batch(oracle, 5, B, n, kind=2)
+    got = A.roots(rows, ctx=ctx)
+    assert ctx.last_stats["unconverged"] == 0 and ctx.last_stats["lanes"] == 128
+    for g in got:
+        assert len(g) == n and np.all(np.isfinite(g.view(np.float64)))
+        pos = np.sort_complex(g[g.imag > 0]); neg = np.sort_complex(np.conj(g[g.imag < 0]))
+        assert np.array_equal(pos, neg)
+        assert np.all(np.diff(g.real) >= 0)
+    worst = max(horner_backward_error(rows[p], got[p]).max() for p in range(0, B, 8))
+    assert worst < 1e-9, worst
