@@ -224,8 +224,11 @@ AMRVW_NI void unit_shifts(const Problem<double>& pr, const PipeParams pp, const 
 }
 
 // ---------------------------------------------------------------- the persistent kernel
+// resident CTAs (= warps) per SM the register allocation is held to.  Config 2 has 1500 units: 11 per SM
+// (186 registers, 1628 slots) keeps every unit resident and runs the lean loop at 1538 cycles per step, 12
+// (168 registers) at 1583 -- 506 vs 517 ms; 8-10 leave units queueing, 14 spills (gpurun_out/sweep68/69.log)
 #ifndef AMRVW_PIPE_MINBLOCKS
-#define AMRVW_PIPE_MINBLOCKS 12
+#define AMRVW_PIPE_MINBLOCKS 11
 #endif
 template <int L, int MH>
 __global__ void __launch_bounds__(32, AMRVW_PIPE_MINBLOCKS) unit_kernel(Problem<double> pr, PipeParams pp, RoundQueue* q, int* slots, unsigned mask, UnitPark* park, StepState* parked,

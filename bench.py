@@ -124,7 +124,13 @@ class ClockSampler:
 def cpu_baseline(kind, degree, law, seed, sample, threads=0):
     """The reference's algorithm and schedule (the oracle port) on this box's host cores."""
     from oracle import oracle as orc            # allowed here: cpu_baseline / --impl reference legs only
-    cores = orc.num_threads() if threads <= 0 else threads
+    # all the host cores this process may run on: torchrun exports OMP_NUM_THREADS=1 to its workers, which would
+    # leave the reference arm at N > 1 on a single core (observed: 1.4 instead of 20.7 polynomials/s)
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    cores = max(orc.num_threads(), avail) if threads <= 0 else threads
     if sample <= 0:   # ~12 s of wall time: one polynomial costs about k * degree^2 seconds on one core
         per_poly_s = {"rds_f64": 1.6e-7, "css_c64": 4.7e-7, "pencil_f64": 3.5e-7}[kind] * degree * degree
         sample = max(cores, min(4096, int(cores * max(1.0, 12.0 / max(per_poly_s, 1e-9)))))
