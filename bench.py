@@ -39,7 +39,7 @@ CONFIGS = {
 }
 FLOP_PER_TURNOVER = {"rds_f64": 37.0, "css_c64": 94.0, "pencil_f64": 37.0}
 BYTES_PER_TURNOVER = {"rds_f64": 96.0 / 7, "css_c64": 208.0 / 3, "pencil_f64": 160.0 / 11}
-NCU_TRAFFIC_C2 = 143.5e9   # dram read 62.9 GB + write 80.6 GB: profiles/r01_c2_unit_kernel_ncu_full_keymetrics.csv (ncu --set full, default c2 launch)
+NCU_TRAFFIC_C2 = 143.5e9   # dram read 62.8 GB + write 80.7 GB: profiles/r01_c2_unit_kernel_ncu_keymetrics.csv (ncu --set full, default c2 launch)
 
 
 def parse():

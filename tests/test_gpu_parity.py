@@ -602,3 +602,21 @@ def test_gpu_full_size_c5_properties(A, ctx, oracle):
         assert np.all(np.diff(g.real) >= 0)
     worst = max(horner_backward_error(rows[p], got[p]).max() for p in range(0, B, 8))
     assert worst < 1e-9, worst
+
+
+def test_gpu_chain_more_polynomials_than_resident_ctas(A, ctx, oracle):
+    """chain.cuh takes polynomials blockIdx.x, blockIdx.x + gridDim.x, ...: a batch larger than the number of
+    resident CTAs (148 SMs x <= 3) must give the same roots as the unit kernel, polynomial by polynomial."""
+    c = A.Context(seed=0, schedule=A.SCHEDULE_PIPELINED, lanes_per_poly=64)
+    try:
+        rows = batch(oracle, 17, 700, 120)
+        got = A.roots(rows, ctx=c)
+        ref = A.roots(rows, ctx=ctx)
+        assert c.last_stats["unconverged"] == 0 and c.last_stats["lanes"] == 64
+        for p in range(0, 700, 7):
+            d, _ = match_roots(got[p], ref[p])
+            assert d.max() < 1e-9 and np.sum(got[p].imag == 0) == np.sum(ref[p].imag == 0)
+        want = [oracle.roots(rows[p])[0] for p in (0, 333, 699)]
+        check_parity([rows[p] for p in (0, 333, 699)], [got[p] for p in (0, 333, 699)], want)
+    finally:
+        c.close()
