@@ -10,6 +10,7 @@
 #include "pencil_units.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -29,7 +30,7 @@ struct amrvw_ctx {
     amrvw_options opt;
     std::string err;
     // grow-only device buffers
-    DevBuf chains[5], diags[3], coeffs, coeffs2, offsets, roots, nroots, nunconv, stats, shifts, state, prof, rec, fatshifts, swlist, counters, queue, qslots, park, parked;
+    DevBuf chains[5], diags[3], coeffs, coeffs2, offsets, roots, nroots, nunconv, stats, shifts, state, prof, rec, fatshifts, swlist, counters, queue, qslots, park, parked, order, orderkeys;
     cudaEvent_t evpool[32] = {};
     RoundsTimes times = {};
     bool prof_valid = false;
@@ -99,7 +100,7 @@ int amrvw_destroy(amrvw_ctx* ctx) {
     cudaSetDevice(ctx->device);
     DevBuf* all[] = {&ctx->chains[0], &ctx->chains[1], &ctx->chains[2], &ctx->chains[3], &ctx->chains[4], &ctx->diags[0], &ctx->diags[1], &ctx->diags[2],
                      &ctx->coeffs, &ctx->coeffs2, &ctx->offsets, &ctx->roots, &ctx->nroots, &ctx->nunconv, &ctx->stats, &ctx->shifts, &ctx->state, &ctx->prof,
-                     &ctx->rec, &ctx->fatshifts, &ctx->swlist, &ctx->counters, &ctx->queue, &ctx->qslots, &ctx->park, &ctx->parked};
+                     &ctx->rec, &ctx->fatshifts, &ctx->swlist, &ctx->counters, &ctx->queue, &ctx->qslots, &ctx->park, &ctx->parked, &ctx->order, &ctx->orderkeys};
     for (DevBuf* b : all) if (b->ptr) cudaFree(b->ptr);
     for (cudaEvent_t e : ctx->evpool) if (e) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -184,7 +185,7 @@ static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, cons
     pr.WB = (Rot<S>*)ctx->chains[3].ptr; pr.WCt = (Rot<S>*)ctx->chains[4].ptr;
     pr.DQ = (S*)ctx->diags[0].ptr; pr.DR = (S*)ctx->diags[1].ptr; pr.WD = (S*)ctx->diags[2].ptr;
     pr.dstack = (int*)ctx->shifts.ptr;
-    pr.prof = nullptr; pr.rec = nullptr; pr.shifts = nullptr; pr.swlist = nullptr; pr.counters = nullptr;
+    pr.prof = nullptr; pr.rec = nullptr; pr.shifts = nullptr; pr.swlist = nullptr; pr.counters = nullptr; pr.order = nullptr;
     if (stats && var != V_PENCIL_C) {   // warp-cycle counters ride along with the statistics
         int rc = reserve(ctx, ctx->prof, 16 * sizeof(unsigned long long)); if (rc) return rc;
         CUDA_TRY(ctx, cudaMemsetAsync(ctx->prof.ptr, 0, 16 * sizeof(unsigned long long), ctx->stream));
@@ -193,6 +194,14 @@ static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, cons
     pr.extra = extra;
     pr.seed = ctx->opt.seed;
 
+    // unit schedules form their units from polynomials in order of decreasing degree
+    static const bool no_order = std::getenv("AMRVW_NO_ORDER") != nullptr;   // development knob: units in batch order
+    if (ctx->opt.schedule != AMRVW_SCHEDULE_REFERENCE && var != V_PENCIL_C && nbatch > 1 && !no_order) {
+        int rc;
+        if ((rc = reserve(ctx, ctx->order, (size_t)nbatch * sizeof(int)))) return rc;
+        if ((rc = reserve(ctx, ctx->orderkeys, (size_t)nbatch * sizeof(unsigned long long)))) return rc;
+        pr.order = (const int*)ctx->order.ptr;
+    }
     cudaStream_t st = ctx->stream;
     int launches = 0, lanes = 0;
     ctx->times = RoundsTimes{0.f, 0.f, 0.f, 0.f};
@@ -220,7 +229,7 @@ static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, cons
             qb.q = (RoundQueue*)ctx->queue.ptr; qb.slots = (int*)ctx->qslots.ptr; qb.mask = (unsigned)(qcap - 1);
             qb.park = (UnitPark*)ctx->park.ptr; qb.parked = (StepState*)ctx->parked.ptr;
             pr.rec = (PolyRec*)ctx->rec.ptr; pr.shifts = (Shifts*)ctx->fatshifts.ptr; pr.swlist = ctx->swlist.ptr; pr.counters = (unsigned*)ctx->counters.ptr;
-            cudaError_t e = launch_rounds_rds(pr, ctx->opt, (int)max_len, (long long)total, ctx->sm_count, st, &launches, ctx->evpool, stats ? &ctx->times : nullptr, qb, &lanes);
+            cudaError_t e = launch_rounds_rds(pr, ctx->opt, (int)max_len, (long long)total, ctx->sm_count, st, &launches, ctx->evpool, stats ? &ctx->times : nullptr, qb, &lanes, (unsigned long long*)ctx->orderkeys.ptr);
             if (e != cudaSuccess) return fail(ctx, AMRVW_ERR_CUDA, std::string("unit schedule: ") + cudaGetErrorString(e));
             done = true;
         }
@@ -242,7 +251,7 @@ static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, cons
             qb.q = (RoundQueue*)ctx->queue.ptr; qb.slots = (int*)ctx->qslots.ptr; qb.mask = (unsigned)(qcap - 1);
             qb.park = (UnitPark*)ctx->park.ptr; qb.parked = nullptr;
             pr.rec = (PolyRec*)ctx->rec.ptr; pr.shifts = (Shifts*)ctx->fatshifts.ptr; pr.swlist = ctx->swlist.ptr; pr.counters = (unsigned*)ctx->counters.ptr;
-            cudaError_t e = launch_pencil_pipelined(pr, ctx->opt, (int)max_len, (long long)total, ctx->sm_count, st, &launches, qb, (PenLane*)ctx->parked.ptr, ctx->evpool, stats ? &ctx->times : nullptr, &lanes);
+            cudaError_t e = launch_pencil_pipelined(pr, ctx->opt, (int)max_len, (long long)total, ctx->sm_count, st, &launches, qb, (PenLane*)ctx->parked.ptr, ctx->evpool, stats ? &ctx->times : nullptr, &lanes, (unsigned long long*)ctx->orderkeys.ptr);
             if (e != cudaSuccess) return fail(ctx, AMRVW_ERR_CUDA, std::string("pencil unit schedule: ") + cudaGetErrorString(e));
             done = true;
         }
@@ -263,7 +272,7 @@ static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, cons
             if ((rc = reserve(ctx, ctx->parked, max_units * 32 * sizeof(CssLane)))) return rc;
             pr.rec = (PolyRec*)ctx->rec.ptr; pr.shifts = (Shifts*)ctx->fatshifts.ptr; pr.swlist = ctx->swlist.ptr; pr.counters = (unsigned*)ctx->counters.ptr;
             cudaError_t e = launch_css_pipelined(pr, ctx->opt, (int)max_len, (long long)total, ctx->sm_count, st, &launches, (RoundQueue*)ctx->queue.ptr, (int*)ctx->qslots.ptr,
-                                                 (unsigned)(qcap - 1), (UnitPark*)ctx->park.ptr, (CssLane*)ctx->parked.ptr, ctx->evpool, stats ? &ctx->times : nullptr, &lanes);
+                                                 (unsigned)(qcap - 1), (UnitPark*)ctx->park.ptr, (CssLane*)ctx->parked.ptr, ctx->evpool, stats ? &ctx->times : nullptr, &lanes, (unsigned long long*)ctx->orderkeys.ptr);
             if (e != cudaSuccess) return fail(ctx, AMRVW_ERR_CUDA, std::string("complex unit schedule: ") + cudaGetErrorString(e));
             done = true;
         }

@@ -115,7 +115,8 @@ __global__ void __launch_bounds__(32 * NW) chain_kernel(Problem<double> pr, Pipe
     const unsigned stage_sa = (unsigned)__cvta_generic_to_shared(sm.ring);
     const unsigned hand_sa = (unsigned)__cvta_generic_to_shared(&sm.hand[0][0][0]);
 
-    for (long long p = blockIdx.x; p < pr.nbatch; p += gridDim.x) {
+    for (long long slot = blockIdx.x; slot < pr.nbatch; slot += gridDim.x) {
+        const long long p = unit_poly(pr, slot);      // largest polynomials first
         if (!pr.rec[p].iterating) continue;           // written by the set-up kernel before this launch
         for (;;) {
             // ---------------- phase A: driver on thread 0, shifts on warp 0

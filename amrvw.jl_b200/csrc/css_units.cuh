@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(32, 8) css_unit_kernel(Problem<cplx> pr, PipeP
         const long long pc_u0 = clock64();
         pc_pop += pc_u0 - pc_p0;
         UnitPark* const up = park + u;
-        const long long p = (long long)u * G + grp;
+        const long long p = unit_poly(pr, (long long)u * G + grp);
         int t0 = __ldcg(&up->t);
 
         // ---------------- phase A when due
@@ -619,7 +619,7 @@ __global__ void css_enqueue_kernel(Problem<cplx> pr, RoundQueue* q, int* slots, 
     if (u >= nunits) return;
     bool any = false;
     for (int g = 0; g < G; ++g) {
-        const long long p = u * G + g;
+        const long long p = unit_poly(pr, u * G + g);
         if (p < pr.nbatch && pr.rec[p].iterating) any = true;
     }
     if (!any) return;
@@ -712,7 +712,7 @@ static cudaError_t launch_css_units(const Problem<cplx>& pr, const PipeParams& p
 
 static cudaError_t launch_css_pipelined(Problem<cplx> pr, const amrvw_options& opt, int max_len, long long total, int sm_count, cudaStream_t st, int* launches,
                                         RoundQueue* q, int* slots, unsigned mask, UnitPark* park, CssLane* parked, cudaEvent_t* ev = nullptr, RoundsTimes* times = nullptr,
-                                        int* lanes_out = nullptr) {
+                                        int* lanes_out = nullptr, unsigned long long* order_keys = nullptr) {
     const int degree = max_len - 1;
     int L = opt.lanes_per_poly;
     if (L == 0) L = degree < 64 ? 4 : (degree < 256 ? 8 : 16);
@@ -735,6 +735,11 @@ static cudaError_t launch_css_pipelined(Problem<cplx> pr, const amrvw_options& o
     if (times) cudaEventRecord(ev[0], st);
     css_setup_kernel<<<(int)((pr.nbatch + 63) / 64), 64, 0, st>>>(pr);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (pr.order) {
+        order_by_degree_kernel<<<1, 1024, 0, st>>>(pr.rec, pr.nbatch, max_len, order_keys, const_cast<int*>(pr.order));
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        *launches += 1;
+    }
     if (times) cudaEventRecord(ev[1], st);
     const int seg_steps = 256;
     switch (L) {

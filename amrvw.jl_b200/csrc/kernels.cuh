@@ -26,8 +26,17 @@ template <class S> struct Problem {
     // rounds schedule (rounds.cuh): per-polynomial records, shifts of the pending fat steps, queue of
     // deferred small windows, round counters
     PolyRec* rec; Shifts* shifts; void* swlist; unsigned* counters;
+    // unit schedules: polynomials in order of decreasing trimmed degree (nullable = identity).  The groups of
+    // a warp take their lock-steps together, up to the longer window, so units are formed from neighbours
+    // in this order, not in batch order (ragged batches: SURVEY 8 f2)
+    const int* order;
     unsigned long long seed;
 };
+// polynomial of slot `slot` of the unit schedule (slot = unit * G + group); nbatch = none
+template <class S> AMRVW_DI long long unit_poly(const Problem<S>& pr, const long long slot) {
+    if (slot >= pr.nbatch) return pr.nbatch;
+    return pr.order ? (long long)pr.order[slot] : slot;
+}
 
 template <class S, bool P> AMRVW_DI Fact<S, P> make_fact(const Problem<S>& pr, long long p, int N) {
     const long long base = pr.offsets[p] + (long long)pr.extra * p;

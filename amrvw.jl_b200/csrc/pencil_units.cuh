@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(32, 8) pen_unit_kernel(Problem<double> pr, Pip
         const long long pc_u0 = clock64();
         pc_pop += pc_u0 - pc_p0;
         UnitPark* const up = park + u;
-        const long long p = (long long)u * G + grp;
+        const long long p = unit_poly(pr, (long long)u * G + grp);
         int t0 = __ldcg(&up->t);
 
         // ---------------- phase A when due
@@ -581,7 +581,8 @@ static cudaError_t launch_pen_units(const Problem<double>& pr, const PipeParams&
 }
 
 static cudaError_t launch_pencil_pipelined(Problem<double> pr, const amrvw_options& opt, int max_len, long long total, int sm_count, cudaStream_t st, int* launches,
-                                           const QueueBufs& qb, PenLane* parked, cudaEvent_t* ev = nullptr, RoundsTimes* times = nullptr, int* lanes_out = nullptr) {
+                                           const QueueBufs& qb, PenLane* parked, cudaEvent_t* ev = nullptr, RoundsTimes* times = nullptr, int* lanes_out = nullptr,
+                                           unsigned long long* order_keys = nullptr) {
     const int degree = max_len;          // vs has one entry per degree
     int L = opt.lanes_per_poly;
     if (L == 0) L = degree < 48 ? 4 : (degree < 200 ? 8 : 16);
@@ -604,6 +605,11 @@ static cudaError_t launch_pencil_pipelined(Problem<double> pr, const amrvw_optio
     if (times) cudaEventRecord(ev[0], st);
     pen_setup_kernel<<<(int)((pr.nbatch + 63) / 64), 64, 0, st>>>(pr);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (pr.order) {
+        order_by_degree_kernel<<<1, 1024, 0, st>>>(pr.rec, pr.nbatch, max_len, order_keys, const_cast<int*>(pr.order));
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        *launches += 1;
+    }
     if (times) cudaEventRecord(ev[1], st);
     const int seg_steps = 256;
     e = cudaErrorInvalidValue;

@@ -87,6 +87,32 @@ __global__ void __launch_bounds__(64) rounds_setup_kernel(Problem<double> pr) {
     pr.rec[p] = rec;
 }
 
+// ---------------------------------------------------------------- unit formation by degree
+// keys[p] = (maxN - N_p) << 32 | p, sorted ascending by one CTA with the all-ascending bitonic network of the
+// finish kernel (slots >= n act as +infinity); order[i] = polynomial with the i-th largest trimmed degree,
+// ties in batch order -- the identity for a batch of equal degrees.
+__global__ void __launch_bounds__(1024) order_by_degree_kernel(const PolyRec* rec, const long long n, const int maxN, unsigned long long* keys, int* order) {
+    for (long long p = threadIdx.x; p < n; p += blockDim.x) keys[p] = ((unsigned long long)(unsigned)(maxN - rec[p].N) << 32) | (unsigned long long)p;
+    __syncthreads();
+    long long np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    for (long long k = 2; k <= np2; k <<= 1) {
+        for (long long j = k >> 1; j >= 1; j >>= 1) {
+            const bool first = (j == (k >> 1));
+            for (long long t = threadIdx.x; t < (np2 >> 1); t += blockDim.x) {
+                const long long i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const long long l = first ? (i ^ (k - 1)) : (i | j);
+                if (l < n && i < n) {
+                    const unsigned long long x = keys[i], y = keys[l];
+                    if (y < x) { keys[i] = y; keys[l] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (long long p = threadIdx.x; p < n; p += blockDim.x) order[p] = (int)(keys[p] & 0xffffffffull);
+}
+
 // ---------------------------------------------------------------- records, coherently
 // PolyRec is read and written by whichever warp holds the unit: whole-record ld.cg / st.cg copies.
 static_assert(sizeof(PolyRec) % 8 == 0, "PolyRec is copied in 8-byte words");
@@ -137,7 +163,7 @@ __global__ void unit_enqueue_kernel(Problem<double> pr, RoundQueue* q, int* slot
     if (u >= nunits) return;
     bool any = false;
     for (int g = 0; g < G; ++g) {
-        const long long p = u * G + g;
+        const long long p = unit_poly(pr, u * G + g);
         if (p < pr.nbatch && pr.rec[p].iterating) any = true;
     }
     if (!any) return;
@@ -266,7 +292,7 @@ __global__ void __launch_bounds__(32, AMRVW_PIPE_MINBLOCKS) unit_kernel(Problem<
         const long long pc_u0 = clock64();
         pc_pop += pc_u0 - pc_p0;
         UnitPark* const up = park + u;
-        const long long p = (long long)u * G + grp;
+        const long long p = unit_poly(pr, (long long)u * G + grp);
         int t0 = __ldcg(&up->t);
 
         // ---------------- phase A when due
@@ -618,7 +644,7 @@ static cudaError_t read_round_times(cudaEvent_t* ev, RoundsTimes* times, cudaStr
     return cudaSuccess;
 }
 static cudaError_t launch_rounds_rds(Problem<double> pr, const amrvw_options& opt, int max_len, long long total, int sm_count, cudaStream_t st, int* launches, cudaEvent_t* ev,
-                                     RoundsTimes* times, const QueueBufs& qb, int* lanes_out = nullptr) {
+                                     RoundsTimes* times, const QueueBufs& qb, int* lanes_out = nullptr, unsigned long long* order_keys = nullptr) {
     int L; PipeParams pp;
     choose_pipe_params(opt, pr.nbatch, max_len, sm_count, L, pp);
     if (lanes_out) *lanes_out = L;
@@ -632,6 +658,11 @@ static cudaError_t launch_rounds_rds(Problem<double> pr, const amrvw_options& op
     if (times) cudaEventRecord(ev[0], st);
     rounds_setup_kernel<<<nb64, 64, 0, st>>>(pr);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (pr.order) {
+        order_by_degree_kernel<<<1, 1024, 0, st>>>(pr.rec, pr.nbatch, max_len, order_keys, const_cast<int*>(pr.order));
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        *launches += 1;
+    }
     if (times) cudaEventRecord(ev[1], st);
     switch (L) {
         case 4: e = launch_units_mh<4>(pr, pp, qb, seg_steps, sm_count, st); break;
