@@ -18,10 +18,11 @@
 //     m-1 is through with that index, before bulge m's turnover on it), and deposits it in D_Q at the
 //     first zero sine / the end of the window.  The push-down costs one complex multiplication per
 //     lock-step instead of a pass over memory;
-//   * shifts: the L / reuse eigenvalues of the trailing block come from the core-chasing iteration on a
-//     shared-memory copy (lane 0 of the group), each driving `reuse` bulges; a dense complex Hessenberg QR
-//     shared by the lanes is the obvious next step.  The chase uses the division-free complex turnover
-//     inline, with the lane's state in registers.
+//   * shifts: the L / reuse eigenvalues of the trailing block, each driving `reuse` bulges, from the dense
+//     block (entry recurrences over the reference's formulas) and a single-shift complex Hessenberg QR shared
+//     by the lanes of the group; the core-chasing iteration on a shared-memory copy (lane 0) is the fall-back
+//     and AMRVW_SHIFTS_CHASE.  The chase uses the division-free complex turnover inline, with the lane's
+//     state in registers.
 //
 // Roots agree with the reference schedule to backward-error level (tests: minimum-distance matching
 // against the oracle); there is no bit-level twin of this schedule in the oracle yet.
@@ -336,11 +337,128 @@ AMRVW_NI int css_unit_driver(const Problem<cplx>& pr, const PipeParams pp, const
     return mode;
 }
 
-// shared-memory scratch of one lane group for the shift sub-solve
+// shared-memory scratch of one lane group for the shifts
 template <int MH> struct __align__(16) CssShiftScratch {
     Rot<cplx> q[MH + 3], b[MH + 3], c[MH + 3];
     cplx dq[MH + 3], dr[MH + 3], e[MH + 3];
+    cplx H[MH * (MH + 1)];          // dense trailing block, row major, leading dimension MH + 1
+    cplx gs[2 * MH];                // the Givens rotations of one QR sweep
+    double isg[MH + 2];
 };
+
+// ---------------------------------------------------------------- shifts from the dense trailing block (complex)
+// The complex twin of shifts.cuh.  Entries of the trailing M x M block of (Q D_Q) Ct (B D_R), rotator Q[k0]
+// diagonal, column by column (one column per lane), bottom-up, O(1) per entry:
+//   w(j,k) = -s^B_k (j = k), conj(c^B_j) (prod_{j<l<k} s^B_l) c^B_k          (rfactorization.jl:83-97)
+//   R[j,k] = D_R[k] (w(j,k) + c^Ct_j T_j) / s^Ct_j,  T_k = 0,  T_{j-1} = (-conj(c^Ct_j) w(j,k) - T_j) / s^Ct_j   (:139-170)
+//   rows of D_Q R pushed up through the Q rotators [c s; -s conj(c)]          (chains.jl:109-158, qfactorization.jl:67-70)
+// q/b/c/dq/dr: staged with GLOBAL indices (slot t <-> index k0 + t), q[k0] = (phase, 0).
+AMRVW_DI void css_dense_trailing_block_warp(const Rot<cplx>* q, const Rot<cplx>* b, const Rot<cplx>* c, const cplx* dq, const cplx* dr, const int k0, const int stop,
+                                            cplx* H, const int LD, double* isg, const int M, const int lane, const unsigned gmask, const int GL) {
+    const int j0 = k0 + 1;
+    for (int i = lane; i < M * LD; i += GL) H[i] = cplx(0.0, 0.0);
+    for (int j = j0 + lane; j <= stop + 1; j += GL) isg[j - j0] = rcp_(c[j].s);
+    __syncwarp(gmask);
+    for (int k = j0 + lane; k <= stop + 1; k += GL) {
+        double P = 1.0;
+        cplx T = cplx(0.0, 0.0), Vacc = cplx(0.0, 0.0);
+        const cplx ck = b[k].c, dk = dr[k];
+        const double sk = b[k].s;
+        for (int j = k; j >= j0; --j) {
+            const cplx w = (j == k) ? cplx(-sk, 0.0) : (conj_(b[j].c) * P) * ck;
+            const cplx ctc = c[j].c;
+            const double ig = isg[j - j0];
+            const cplx X = dq[j] * (((w + ctc * T) * ig) * dk);
+            const Rot<cplx> qj = q[j];
+            if (j + 1 <= stop + 1) H[(j + 1 - j0) * LD + (k - j0)] = conj_(qj.c) * Vacc - qj.s * X;
+            Vacc = qj.c * X + qj.s * Vacc;
+            T = (-(conj_(ctc) * w) - T) * ig;
+            if (j < k) P = P * b[j].s;
+        }
+        H[k - j0] = conj_(q[k0].c) * Vacc;
+    }
+    __syncwarp(gmask);
+}
+// Single-shift QR on the complex upper Hessenberg matrix H (destroyed), eigenvalues only, the lanes of the
+// group sharing the row and column updates: Wilkinson shift (exceptional shifts at iterations 10 and 20 as in
+// EISPACK comqr), one sweep = Givens rotations G_k = [conj(c) conj(s); -s c] zeroing H[k+1][k] applied to the
+// rows, then their adjoints to the columns.  false: no convergence in 30 M sweeps or a non-finite value.
+AMRVW_DI bool chqr_eigenvalues_warp(cplx* H, const int LD, const int M, cplx* E, cplx* gs, const int lane, const unsigned gmask, const int GL) {
+    const int gbase = __ffs(gmask) - 1;
+#define AMRVW_HC(i, j) H[(i) * LD + (j)]
+    int en = M - 1, itn = 30 * M, its = 0;
+    cplx t = cplx(0.0, 0.0);
+    while (en >= 0) {
+        __syncwarp(gmask);
+        // highest l in 1..en with a negligible subdiagonal entry, 0 if none
+        int l = 0;
+        for (int base = (en / GL) * GL; base >= 0 && l == 0; base -= GL) {
+            const int lc = base + lane;
+            bool small = false;
+            if (lc >= 1 && lc <= en) {
+                const cplx d0 = AMRVW_HC(lc - 1, lc - 1), d1 = AMRVW_HC(lc, lc), sb = AMRVW_HC(lc, lc - 1);
+                const double sd = fabs(d0.re) + fabs(d0.im) + fabs(d1.re) + fabs(d1.im);
+                small = (sd + (fabs(sb.re) + fabs(sb.im)) == sd);
+            }
+            const unsigned mask = __ballot_sync(gmask, small) & gmask;
+            if (mask) l = base + (31 - __clz(mask)) - gbase;
+        }
+        if (l == en) {
+            if (lane == 0) E[en] = AMRVW_HC(en, en) + t;
+            en -= 1; its = 0;
+            continue;
+        }
+        if (itn == 0) return false;
+        cplx sft;
+        if (its == 10 || its == 20) {
+            sft = cplx(fabs(AMRVW_HC(en, en - 1).re) + (en >= 2 ? fabs(AMRVW_HC(en - 1, en - 2).re) : 0.0), 0.0);
+        } else {
+            sft = AMRVW_HC(en, en);
+            const cplx x = AMRVW_HC(en - 1, en) * AMRVW_HC(en, en - 1);
+            if (!iszero_(x)) {
+                const cplx y = (AMRVW_HC(en - 1, en - 1) - sft) * 0.5;
+                cplx z = csqrt_(y * y + x);
+                if (y.re * z.re + y.im * z.im < 0.0) z = -z;
+                const cplx den = y + z;
+                if (!iszero_(den)) sft = sft - x / den;
+            }
+        }
+        ++its; --itn;
+        __syncwarp(gmask);
+        for (int i = lane; i <= en; i += GL) AMRVW_HC(i, i) = AMRVW_HC(i, i) - sft;
+        t = t + sft;
+        for (int k = l; k < en; ++k) {   // rows
+            __syncwarp(gmask);
+            const cplx a = AMRVW_HC(k, k), bb = AMRVW_HC(k + 1, k);
+            const double r2 = abs2_(a) + abs2_(bb);
+            cplx gc = cplx(1.0, 0.0), gsn = cplx(0.0, 0.0);
+            if (r2 > 0.0) { const double ir = (r2 >= 1e-280 && r2 <= 1e280) ? rsqrt_nr(r2) : 1.0 / sqrt(r2); gc = a * ir; gsn = bb * ir; }
+            __syncwarp(gmask);            // every lane has read column k before it is overwritten
+            if (lane == 0) { gs[2 * k] = gc; gs[2 * k + 1] = gsn; }
+            for (int j = k + lane; j <= en; j += GL) {
+                const cplx u = AMRVW_HC(k, j), v = AMRVW_HC(k + 1, j);
+                AMRVW_HC(k, j) = conj_(gc) * u + conj_(gsn) * v;
+                AMRVW_HC(k + 1, j) = gc * v - gsn * u;
+            }
+        }
+        for (int k = l; k < en; ++k) {   // columns
+            __syncwarp(gmask);
+            const cplx gc = gs[2 * k], gsn = gs[2 * k + 1];
+            const int ihi = min(k + 1, en);
+            for (int i = l + lane; i <= ihi; i += GL) {
+                const cplx u = AMRVW_HC(i, k), v = AMRVW_HC(i, k + 1);
+                AMRVW_HC(i, k) = u * gc + v * gsn;
+                AMRVW_HC(i, k + 1) = v * conj_(gc) - u * conj_(gsn);
+            }
+        }
+    }
+#undef AMRVW_HC
+    __syncwarp(gmask);
+    bool ok = true;
+    for (int i = lane; i < M; i += GL)
+        if (!(isfinite(E[i].re) && isfinite(E[i].im))) ok = false;
+    return __all_sync(gmask, ok);
+}
 // the nb + 1 shifts of a pending fat step: eigenvalues of the trailing block, by the one-bulge iteration
 // on a shared-memory copy whose top rotator is made diagonal (lane 0 of the group; the others stage)
 template <int MH>
@@ -356,22 +474,31 @@ AMRVW_NI void css_unit_shifts(const Problem<cplx>& pr, const PipeParams pp, cons
         else { ws.b[t] = make_rot<cplx>(cplx(1.0, 0.0), 0.0); ws.c[t] = ws.b[t]; ws.dr[t] = cplx(1.0, 0.0); }
     }
     __syncwarp(gmask);
+    if (lane == 0) {   // make Q[k0] diagonal: keep its phase (as deflate does), drop its sine
+        const cplx c0 = ws.q[0].c;
+        const double a = abs_(c0);
+        ws.q[0] = make_rot<cplx>(a == 0.0 ? cplx(1.0, 0.0) : c0 / a, 0.0);
+    }
+    __syncwarp(gmask);
+    bool ok = false;
+    if (pp.dense) {
+        css_dense_trailing_block_warp(ws.q - k0, ws.b - k0, ws.c - k0, ws.dq - k0, ws.dr - k0, k0, stop, ws.H, MH + 1, ws.isg, m + 1, lane, gmask, L);
+        ok = chqr_eigenvalues_warp(ws.H, MH + 1, m + 1, ws.e, ws.gs, lane, gmask, L);
+    }
+    __syncwarp(gmask);
     if (lane == 0) {
-        Fact<cplx, false> W = F;
-        W.Q = ws.q - k0; W.B = ws.b - k0; W.Ct = ws.c - k0; W.DQ = ws.dq - k0; W.DR = ws.dr - k0; W.turnovers = 0;
-        W.N = stop + 1;                       // the copy ends at the window: phase push-downs stop at Q[stop]
-        {   // make Q[k0] diagonal: keep its phase (as deflate does), drop its sine
-            const cplx c0 = W.Q[k0].c;
-            const double a = abs_(c0);
-            W.Q[k0] = make_rot<cplx>(a == 0.0 ? cplx(1.0, 0.0) : c0 / a, 0.0);
-            deflate(W, k0);
+        if (!ok) {   // core-chasing iteration on the staged copy (also AMRVW_SHIFTS_CHASE)
+            Fact<cplx, false> W = F;
+            W.Q = ws.q - k0; W.B = ws.b - k0; W.Ct = ws.c - k0; W.DQ = ws.dq - k0; W.DR = ws.dr - k0; W.turnovers = 0;
+            W.N = stop + 1;                       // the copy ends at the window: phase push-downs stop at Q[stop]
+            deflate(W, k0);                       // the phase of Q[k0] goes down the copy's Q chain
+            cplx* Es = ws.e - (k0 + 1);
+            for (int t = 0; t <= m; ++t) ws.e[t] = cplx(0.0, 0.0);
+            Counter c2 = {k0, k0 + 1, stop, 15, -1};
+            PolyStats sub = {0, 0, 0, 0, 0};
+            drive_window(W, k0 + 1, stop, c2, Es, 20ll * (m + 1), pr.seed, (uint64_t)p, rec.ls.ord, sub, ReferenceStep());
+            rec.serial_turnovers += W.turnovers;
         }
-        cplx* Es = ws.e - (k0 + 1);
-        for (int t = 0; t <= m; ++t) ws.e[t] = cplx(0.0, 0.0);
-        Counter c2 = {k0, k0 + 1, stop, 15, -1};
-        PolyStats sub = {0, 0, 0, 0, 0};
-        drive_window(W, k0 + 1, stop, c2, Es, 20ll * (m + 1), pr.seed, (uint64_t)p, rec.ls.ord, sub, ReferenceStep());
-        rec.serial_turnovers += W.turnovers;
         Shifts* shl = pr.shifts + p * L;
         for (int rep = 0; rep < pp.reuse; ++rep)
             for (int t = 0; t <= m; ++t) { shl[rep * (m + 1) + t].e1 = ws.e[t]; shl[rep * (m + 1) + t].e2 = cplx(0.0, 0.0); }
@@ -719,15 +846,16 @@ static cudaError_t launch_css_pipelined(Problem<cplx> pr, const amrvw_options& o
     if (L > 32) L = 32;      // chained warps exist for the real rank-one path only
     if (lanes_out) *lanes_out = L;
     PipeParams pp;
-    // bulges per shift: the trailing block has order L / reuse.  Its eigenvalues come from a core-chasing
-    // sub-solve on ONE lane, 40-49% of the busy warp-cycles with reuse = 1 at L = 16; config 3 (gpurun_out/sweep62.log):
-    // reuse 1 530 ms, 2 336 ms (1.04x the turnovers), 4 316 ms (1.30x)
-    pp.reuse = opt.shift_reuse ? opt.shift_reuse : (L >= 16 ? 4 : (L >= 8 ? 2 : 1));
+    // bulges per shift: the trailing block has order L / reuse.  With the core-chasing sub-solve on ONE lane the
+    // shifts were 40-49% of the busy warp-cycles at reuse 1, L = 16 (config 3: reuse 1 530 ms, 2 336 ms, 4 316 ms:
+    // gpurun_out/sweep62.log); with the dense block + lane-shared complex Hessenberg QR: reuse 1 201 ms (phase A
+    // 26%), 2 181 ms (11%, 1.06x the turnovers), 4 237 ms (1.34x) (gpurun_out/sweep75.log)
+    pp.reuse = opt.shift_reuse ? opt.shift_reuse : (L >= 8 ? 2 : 1);
     while (pp.reuse > 1 && L / pp.reuse < 2) pp.reuse /= 2;
     pp.small = opt.small_window ? opt.small_window : (L + 8 > 24 ? L + 8 : 24);
     if (pp.small < L) pp.small = L;
     if (pp.small > 96) pp.small = 96;
-    pp.ms = pp.small + 4; pp.dense = 0; pp.mh = L;
+    pp.ms = pp.small + 4; pp.dense = opt.shift_solver != AMRVW_SHIFTS_CHASE; pp.mh = L;
     cudaError_t e;
     if ((e = cudaMemsetAsync(pr.counters, 0, CNT_WORDS * sizeof(unsigned), st)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(q, 0, sizeof(RoundQueue), st)) != cudaSuccess) return e;

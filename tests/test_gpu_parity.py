@@ -366,13 +366,13 @@ def test_gpu_fast_complex_turnover_selftest(ctx):
 
 
 # ------------------------------------------------------------------ complex single shift on the unit queue
-@pytest.mark.parametrize("L,reuse", [(4, 0), (8, 0), (16, 0), (32, 0), (16, 1), (32, 2), (8, 4)])
-def test_gpu_css_pipelined_lanes(A, oracle, L, reuse):
+@pytest.mark.parametrize("L,reuse,solver", [(4, 0, 0), (8, 0, 0), (16, 0, 0), (32, 0, 0), (16, 1, 0), (32, 1, 0), (8, 4, 0), (16, 2, 1), (8, 1, 1)])
+def test_gpu_css_pipelined_lanes(A, oracle, L, reuse, solver):
     """The pipelined complex path for every lane-group width: bulges two indices apart, the creation
     phase of each bulge carried by its lane (diagonal.jl:199-225 without the pass over Q), deferred
     small windows.  Ragged batch so that groups of one warp see different windows; both schedules of
     the library must agree with the oracle's reference schedule root by root."""
-    c = A.Context(seed=0, schedule=A.SCHEDULE_PIPELINED, lanes_per_poly=L, shift_reuse=reuse)
+    c = A.Context(seed=0, schedule=A.SCHEDULE_PIPELINED, lanes_per_poly=L, shift_reuse=reuse, shift_solver=solver)   # 0 dense, 1 chase
     try:
         degs = [40, 41, 64, 97, 130, 200, 257, 33, 5, 3, 2, 1, 350]
         rows = []
