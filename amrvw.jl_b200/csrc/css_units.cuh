@@ -510,8 +510,11 @@ AMRVW_NI void css_unit_shifts(const Problem<cplx>& pr, const PipeParams pp, cons
 }
 
 // ---------------------------------------------------------------- the persistent kernel
+#ifndef AMRVW_CSS_MINBLOCKS
+#define AMRVW_CSS_MINBLOCKS 8
+#endif
 template <int L, int MH>
-__global__ void __launch_bounds__(32, 8) css_unit_kernel(Problem<cplx> pr, PipeParams pp, RoundQueue* q, int* slots, unsigned mask, UnitPark* park, CssLane* parked, int seg_steps) {
+__global__ void __launch_bounds__(32, AMRVW_CSS_MINBLOCKS) css_unit_kernel(Problem<cplx> pr, PipeParams pp, RoundQueue* q, int* slots, unsigned mask, UnitPark* park, CssLane* parked, int seg_steps) {
     constexpr int G = 32 / L;
     __shared__ CssShiftScratch<MH> shift_scratch[G];
     __shared__ __align__(16) unsigned char css_ring[G * AMRVW_RING * AMRVW_CSS_SLOT];
