@@ -844,8 +844,14 @@ static cudaError_t launch_css_pipelined(Problem<cplx> pr, const amrvw_options& o
                                         RoundQueue* q, int* slots, unsigned mask, UnitPark* park, CssLane* parked, cudaEvent_t* ev = nullptr, RoundsTimes* times = nullptr,
                                         int* lanes_out = nullptr, unsigned long long* order_keys = nullptr) {
     const int degree = max_len - 1;
+    const long long nbatch_hint = pr.nbatch;
     int L = opt.lanes_per_poly;
-    if (L == 0) L = degree < 64 ? 4 : (degree < 256 ? 8 : 16);
+    if (L == 0) {
+        L = degree < 64 ? 4 : (degree < 256 ? 8 : 16);
+        // batches that leave warps free get 32 bulges per polynomial (gpurun_out/sweep80.log, sweep75.log: 64 x degree
+        // 3000 944 -> 551 ms, 1000 x 1000 155 -> 121 ms; 2000 x 1000 181 ms with 16 lanes against 199 with 32)
+        if (degree >= 256 && nbatch_hint <= (long long)sm_count * 8) L = 32;
+    }
     if (L > 32) L = 32;      // chained warps exist for the real rank-one path only
     if (lanes_out) *lanes_out = L;
     PipeParams pp;

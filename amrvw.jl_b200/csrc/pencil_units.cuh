@@ -585,7 +585,11 @@ static cudaError_t launch_pencil_pipelined(Problem<double> pr, const amrvw_optio
                                            unsigned long long* order_keys = nullptr) {
     const int degree = max_len;          // vs has one entry per degree
     int L = opt.lanes_per_poly;
-    if (L == 0) L = degree < 48 ? 4 : (degree < 200 ? 8 : 16);
+    if (L == 0) {
+        L = degree < 48 ? 4 : (degree < 200 ? 8 : 16);
+        // small batches of large pencils: 32 bulges (100 x degree 2000: 376 -> 257 ms; 500 x 500 stays at 16: 49 vs 53 ms)
+        if (degree >= 1000 && pr.nbatch <= (long long)sm_count * 8) L = 32;
+    }
     if (L > 32) L = 32;      // chained warps exist for the real rank-one path only
     if (lanes_out) *lanes_out = L;
     PipeParams pp;
