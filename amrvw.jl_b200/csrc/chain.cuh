@@ -115,11 +115,14 @@ __global__ void __launch_bounds__(32 * NW) chain_kernel(Problem<double> pr, Pipe
     const unsigned stage_sa = (unsigned)__cvta_generic_to_shared(sm.ring);
     const unsigned hand_sa = (unsigned)__cvta_generic_to_shared(&sm.hand[0][0][0]);
 
+    long long pc_all = 0, pc_a = 0, pc_lean = 0;      // warp-cycle accounting of warp 0 (amrvw_last_profile)
+    long long pn_lean = 0, pn_all = 0;
     for (long long slot = blockIdx.x; slot < pr.nbatch; slot += gridDim.x) {
         const long long p = unit_poly(pr, slot);      // largest polynomials first
         if (!pr.rec[p].iterating) continue;           // written by the set-up kernel before this launch
         for (;;) {
             // ---------------- phase A: driver on thread 0, shifts on warp 0
+            const long long pc_f0 = clock64();
             if (gl == 0) { sm.mode = unit_driver(pr, pp, LE, p); sm.nturn = 0ull; }
             if (gl < NW * 2 * 3) (&sm.hand[0][0][0])[gl] = make_double2(1.0, 0.0);
             __syncthreads();
@@ -127,6 +130,7 @@ __global__ void __launch_bounds__(32 * NW) chain_kernel(Problem<double> pr, Pipe
             if (m0 == 0) break;
             if (m0 == 3 && warp == 0) unit_shifts<MH>(pr, pp, 32, p, shift_scratch, lane32, 0xffffffffu, LE);
             __syncthreads();
+            pc_a += clock64() - pc_f0;
 
             // ---------------- the fat step: every thread reads the same record
             const PolyRec* r = pr.rec + p;
@@ -154,10 +158,12 @@ __global__ void __launch_bounds__(32 * NW) chain_kernel(Problem<double> pr, Pipe
             for (int t = 0; t < T; ++t) {
                 if (nb == LE && t >= 3 * LE && t <= stop - start) {   // every lane at a regular position: the lean loop
                     const int te = stop - start + 1;
+                    const long long pc_l0 = clock64();
                     StepState z = {q0, q1, q2, b0, b1, b2, c0, c1, c2, U, V, W};
                     sp = chain_lean<NW>(z, FQ, FB, FC, stage_sa, snap_sa, hand_sa, dstack, sp, start, t, te, warp, lane32);
                     q0 = z.q0; q1 = z.q1; q2 = z.q2; b0 = z.b0; b1 = z.b1; b2 = z.b2; c0 = z.c0; c1 = z.c1; c2 = z.c2; U = z.U; V = z.V; W = z.W;
                     nturn += 7 * (te - t);
+                    pc_lean += clock64() - pc_l0; pn_lean += te - t;
                     t = te - 1;
                     continue;
                 }
@@ -212,6 +218,7 @@ __global__ void __launch_bounds__(32 * NW) chain_kernel(Problem<double> pr, Pipe
                 }
                 __syncthreads();
             }
+            pn_all += T;
             if (gl == 0) cp_async_wait_all();   // drain look-ahead requests past the end of the window
             for (int d = 16; d >= 1; d >>= 1) nturn += __shfl_down_sync(0xffffffffu, nturn, d);
             if (lane32 == 0) atomicAdd(&sm.nturn, (unsigned long long)nturn);
@@ -226,8 +233,17 @@ __global__ void __launch_bounds__(32 * NW) chain_kernel(Problem<double> pr, Pipe
                 store_rec(rw, rec);
             }
             __syncthreads();
+            pc_all += clock64() - pc_f0;
         }
         __syncthreads();
+    }
+    if (pr.prof && gl == 0) {
+        atomicAdd(pr.prof + 0, (unsigned long long)pc_all);
+        atomicAdd(pr.prof + 1, (unsigned long long)pc_a);
+        atomicAdd(pr.prof + 2, (unsigned long long)pc_lean);
+        atomicAdd(pr.prof + 3, (unsigned long long)(pc_all - pc_lean - pc_a));
+        atomicAdd(pr.prof + 4, (unsigned long long)pn_lean);
+        atomicAdd(pr.prof + 5, (unsigned long long)(pn_all - pn_lean));
     }
 }
 
