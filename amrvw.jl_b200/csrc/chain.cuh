@@ -31,7 +31,7 @@ template <int NW>
 AMRVW_DI int chain_lean(StepState& z, Rot<double>* gq, Rot<double>* gb, Rot<double>* gc, const unsigned stage_sa, const unsigned snap_sa, const unsigned hand_sa,
                         int* dstack, int sp, const int start, const int t0, const int t1, const int warp, const int lane32) {
     constexpr int LE = 32 * NW;
-    constexpr unsigned SS = LE * 16;     // snapshot slot stride in bytes
+    [[maybe_unused]] constexpr unsigned SS = LE * 16;     // snapshot slot stride in bytes
     Rot<double> q0 = z.q0, q1 = z.q1, q2 = z.q2, b0 = z.b0, b1 = z.b1, b2 = z.b2, c0 = z.c0, c1 = z.c1, c2 = z.c2, U = z.U, V = z.V, W = z.W;
     const bool feeds_g = warp == 0 && lane32 == 0, feeds_h = warp > 0 && lane32 == 0;
     const bool ret_g = warp == NW - 1 && lane32 == 31, ret_h = warp < NW - 1 && lane32 == 31;
@@ -105,7 +105,7 @@ AMRVW_DI int chain_lean(StepState& z, Rot<double>* gq, Rot<double>* gb, Rot<doub
 template <int NW, int MH>
 __global__ void __launch_bounds__(32 * NW) chain_kernel(Problem<double> pr, PipeParams pp) {
     constexpr int LE = 32 * NW;
-    constexpr int NT = LE;
+    [[maybe_unused]] constexpr int NT = LE;
     extern __shared__ __align__(16) unsigned char raw[];   // chain_raw_bytes<NW, MH>(): shift scratch (phase A) and step snapshots (chase) are never live together
     __shared__ __align__(16) ChainSmem<NW> sm;
     ShiftScratch<MH>& shift_scratch = *reinterpret_cast<ShiftScratch<MH>*>(raw);

@@ -55,12 +55,6 @@ AMRVW_DI cplx ldcg_cplx(const cplx* p) {
     const double2 a = __ldcg(reinterpret_cast<const double2*>(p));
     return cplx(a.x, a.y);
 }
-AMRVW_DI CssIdx css_load_index(const Fact<cplx, false>& F, const int k) {
-    CssIdx x;
-    x.q = ldcg_crot(F.Q + k); x.b = ldcg_crot(F.B + k); x.c = ldcg_crot(F.Ct + k);
-    x.dq = ldcg_cplx(F.DQ + k); x.dr = ldcg_cplx(F.DR + k);
-    return x;
-}
 AMRVW_DI void css_store_index(const Fact<cplx, false>& F, const int k, const CssIdx& x) {
     F.Q[k] = x.q; F.B[k] = x.b; F.Ct[k] = x.c; F.DQ[k] = x.dq; F.DR[k] = x.dr;
 }

@@ -33,11 +33,6 @@ AMRVW_DI PenIdx pen_identity_index() {
     x.q = x.b = x.c = x.wb = x.wc = make_rot<double>(1.0, 0.0);
     return x;
 }
-AMRVW_DI PenIdx pen_load_index(const Fact<double, true>& F, const int k) {
-    PenIdx x;
-    x.q = ldcg_rot(F.Q + k); x.b = ldcg_rot(F.B + k); x.c = ldcg_rot(F.Ct + k); x.wb = ldcg_rot(F.WB + k); x.wc = ldcg_rot(F.WCt + k);
-    return x;
-}
 // look-ahead ring of the feeding lane: five 16-byte cp.async.cg per index, AMRVW_RING - 1 steps ahead
 #define AMRVW_PEN_SLOT 80
 AMRVW_DI void pen_prefetch_index(const unsigned slot_sa, const Fact<double, true>& F, const int k) {

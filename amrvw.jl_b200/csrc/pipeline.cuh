@@ -529,7 +529,7 @@ AMRVW_DI int lean_chase(StepState& z, Rot<double>* gq, Rot<double>* gb, Rot<doub
                         const int start, const int t0, const int t1, const int role) {
     Rot<double> q0 = z.q0, q1 = z.q1, q2 = z.q2, b0 = z.b0, b1 = z.b1, b2 = z.b2, c0 = z.c0, c1 = z.c1, c2 = z.c2, U = z.U, V = z.V, W = z.W;
     const bool chasing = role & 1, feeds = (role & 3) == 3, retires = (role & 5) == 5;
-    constexpr unsigned SS = NT * 16;     // snapshot slot stride in bytes
+    [[maybe_unused]] constexpr unsigned SS = NT * 16;     // snapshot slot stride in bytes
     // feeding lane: next index to prefetch; retiring lane: index leaving the pipeline
     gq += start; gb += start; gc += start;
     const int kofs = feeds ? AMRVW_RING - 1 : -(3 * (L - 1) + 2);
