@@ -872,7 +872,8 @@ static cudaError_t launch_css_pipelined(Problem<cplx> pr, const amrvw_options& o
         *launches += 1;
     }
     if (times) cudaEventRecord(ev[1], st);
-    const int seg_steps = 256;
+    static const int seg_env = std::getenv("AMRVW_SEG_STEPS") ? std::atoi(std::getenv("AMRVW_SEG_STEPS")) : 0;   // development knob
+    const int seg_steps = seg_env > 0 ? seg_env : 256;
     switch (L) {
         case 4: e = launch_css_units<4, 8>(pr, pp, q, slots, mask, park, parked, seg_steps, sm_count, st); break;
         case 8: e = launch_css_units<8, 8>(pr, pp, q, slots, mask, park, parked, seg_steps, sm_count, st); break;

@@ -610,7 +610,8 @@ static cudaError_t launch_pencil_pipelined(Problem<double> pr, const amrvw_optio
         *launches += 1;
     }
     if (times) cudaEventRecord(ev[1], st);
-    const int seg_steps = 256;
+    static const int seg_env = std::getenv("AMRVW_SEG_STEPS") ? std::atoi(std::getenv("AMRVW_SEG_STEPS")) : 0;   // development knob
+    const int seg_steps = seg_env > 0 ? seg_env : 256;
     e = cudaErrorInvalidValue;
     switch (L) {
         case 4: if (pp.mh <= 8) e = launch_pen_units<4, 8>(pr, pp, qb, parked, seg_steps, sm_count, st); break;
