@@ -1044,10 +1044,64 @@ static bool hqr_eigenvalues(std::vector<double>& Hm, int M, std::vector<cplx>& E
     return true;
 }
 
+// Pencil twin (csrc/pencil_units.cuh, pen_dense_trailing_block_warp), operation for operation: V and W written
+// out by the rank-one recurrences above without the Q multiplication, X = V W^{-1} row by row (x W = v by forward
+// substitution over the columns of the upper triangular W), H = Q X by the same bottom-up accumulation.
+static void dense_R_block(const RankOne<double>& RF, int k0, int stop, std::vector<double>& R, int M) {
+    const int j0 = k0 + 1;
+    R.assign((size_t)M * M, 0.0);
+    std::vector<double> isg(M);
+    for (int j = j0; j <= stop + 1; ++j) isg[j - j0] = 1.0 / RF.Ct[j].s;
+    for (int k = j0; k <= stop + 1; ++k) {
+        double P = 1.0, T = 0.0;
+        const double ck = RF.B[k].c, sk = RF.B[k].s;
+        for (int j = k; j >= j0; --j) {
+            const double w = (j == k) ? -sk : (RF.B[j].c * P) * ck;
+            const double ctc = RF.Ct[j].c;
+            const double ig = isg[j - j0];
+            R[(size_t)(j - j0) * M + (k - j0)] = (w + ctc * T) * ig;
+            T = (-(ctc * w) - T) * ig;
+            if (j < k) P = P * RF.B[j].s;
+        }
+    }
+}
+static void dense_trailing_block_pencil(const State<double>& s, int k0, int stop, std::vector<double>& H, int M) {
+    const int j0 = k0 + 1;
+    std::vector<double> RV, RW;
+    dense_R_block(s.V, k0, stop, RV, M);
+    dense_R_block(s.W, k0, stop, RW, M);
+    for (int r = 0; r < M; ++r) {
+        for (int k = r; k < M; ++k) {
+            double acc = RV[(size_t)r * M + k];
+            for (int j = r; j < k; ++j) acc -= RV[(size_t)r * M + j] * RW[(size_t)j * M + k];
+            RV[(size_t)r * M + k] = acc * (1.0 / RW[(size_t)k * M + k]);
+        }
+    }
+    std::vector<double> cq(M + 1), sq(M + 1);   // cq[t - k0], t = k0..stop+1
+    const double sg = sign_(s.Q[k0].c);
+    cq[0] = sg == 0 ? 1.0 : sg; sq[0] = 0.0;
+    for (int t = k0 + 1; t <= stop + 1; ++t) {
+        if (t <= s.nq()) { cq[t - k0] = s.Q[t].c; sq[t - k0] = s.Q[t].s; }
+        else { cq[t - k0] = 1.0; sq[t - k0] = 0.0; }
+    }
+    H.assign((size_t)M * M, 0.0);
+    for (int kk = 0; kk < M; ++kk) {
+        double Vacc = 0.0;
+        for (int jj = kk; jj >= 0; --jj) {
+            const double R = RV[(size_t)jj * M + kk];
+            const double qc = cq[j0 + jj - k0], qs = sq[j0 + jj - k0];
+            if (jj + 1 < M) H[(size_t)(jj + 1) * M + kk] = qc * Vacc - qs * R;
+            Vacc = qc * R + qs * Vacc;
+        }
+        H[kk] = cq[0] * Vacc;
+    }
+}
+
 static bool ms_shifts_dense(const State<double>& s, const Counter& ctr, int m, std::vector<cplx>& sh) {
     const int stop = ctr.stop_index, k0 = stop - m, M = m + 1;
     std::vector<double> H;
-    dense_trailing_block(s, k0, stop, H, M);
+    if (s.pencil) dense_trailing_block_pencil(s, k0, stop, H, M);
+    else dense_trailing_block(s, k0, stop, H, M);
     return hqr_eigenvalues(H, M, sh);
 }
 
@@ -1227,7 +1281,8 @@ static void roots_one(const S* ps_in, int len, cplx* out, int* nroots, uint64_t 
 
 // utils.jl:29-58 deflate_leading_zeros(vs, ws) on copies + roots(vs, ws) companion.jl:282-303
 template <class S>
-static void roots_pencil_one(const S* vs_in, const S* ws_in, int N0, cplx* out, int* nroots, uint64_t seed, uint64_t poly, Stats& st) {
+static void roots_pencil_one(const S* vs_in, const S* ws_in, int N0, cplx* out, int* nroots, uint64_t seed, uint64_t poly, Stats& st,
+                             int sched = SCHED_REFERENCE, MsParams P = MsParams()) {
     if (N0 <= 0) { *nroots = 0; return; }
     std::vector<S> vs(vs_in, vs_in + N0), ws(ws_in, ws_in + N0);  // 0-based copies; reference is 1-based
     int N = N0;
@@ -1266,7 +1321,10 @@ static void roots_pencil_one(const S* vs_in, const S* ws_in, int N0, cplx* out, 
         amrvw_pencil(ps, qs, len, s);
         std::vector<cplx> E;
         Rng rng; rng.seed = seed; rng.poly = poly;
-        amrvw_algorithm(s, E, rng, st);
+        if constexpr (is_real<S>::value) {
+            if (sched == SCHED_MULTISHIFT) amrvw_algorithm_ms(s, E, rng, st, P);   // the GPU unit schedule, sequentially
+            else amrvw_algorithm(s, E, rng, st);
+        } else amrvw_algorithm(s, E, rng, st);
         cnt = len;
         for (int i = 0; i < cnt; ++i) out[i] = E[i + 1];
     }
@@ -1393,6 +1451,34 @@ int orc_roots_pencil_batch(const double* vs, const double* ws, const int64_t* of
         if (is_complex) roots_pencil_one<cplx>(reinterpret_cast<const cplx*>(vs) + offsets[p], reinterpret_cast<const cplx*>(ws) + offsets[p], len, out, &nr, seed, (uint64_t)p, st);
         else roots_pencil_one<double>(vs + offsets[p], ws + offsets[p], len, out, &nr, seed, (uint64_t)p, st);
         nroots[p] = nr;
+        if (total) {
+#pragma omp critical
+            add_stats(total, st);
+        }
+    }
+    return 0;
+}
+
+// The same with the multishift schedule of the GPU pencil unit kernel (sched = 1, real only) and per-polynomial stats.
+int orc_roots_pencil_batch_ms(const double* vs, const double* ws, const int64_t* offsets, int64_t B, double* roots_reim, int32_t* nroots,
+                              orc_stats* total, orc_stats* per_poly, uint64_t seed, int threads, int sched, int ms_L, int ms_small) {
+    MsParams P; if (ms_L > 0) P.L = ms_L; if (ms_small > 0) P.small = ms_small % 1000; if (ms_small >= 1000) P.reuse = (ms_small / 1000) % 100; P.dense = (ms_small / 100000) % 10;
+#ifdef _OPENMP
+    int nt = threads > 0 ? threads : omp_get_max_threads();
+#else
+    int nt = 1;
+#endif
+    (void)nt;
+    if (total) std::memset(total, 0, sizeof(*total));
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nt)
+    for (int64_t p = 0; p < B; ++p) {
+        Stats st;
+        int len = (int)(offsets[p + 1] - offsets[p]);
+        cplx* out = reinterpret_cast<cplx*>(roots_reim) + offsets[p];
+        int nr = 0;
+        roots_pencil_one<double>(vs + offsets[p], ws + offsets[p], len, out, &nr, seed, (uint64_t)p, st, sched, P);
+        nroots[p] = nr;
+        if (per_poly) { std::memset(&per_poly[p], 0, sizeof(orc_stats)); add_stats(&per_poly[p], st); }
         if (total) {
 #pragma omp critical
             add_stats(total, st);

@@ -64,8 +64,12 @@ def roots_csr(coeffs, offsets, ws=None, seed=0, threads=0, sched=0, L=8, small=2
         ws = np.ascontiguousarray(ws, dtype=dt)
         roff = offsets.copy()
         out = np.zeros(int(offsets[-1]) + 1, dtype=np.complex128)
-        lib().orc_roots_pencil_batch(_p(coeffs), _p(ws), _p(offsets), ctypes.c_int64(B), int(cx), _p(out), _p(nroots),
-                                     ctypes.byref(st), ctypes.c_uint64(seed), int(threads))
+        if sched and not cx:      # the multishift schedule of the GPU pencil unit kernel, executed sequentially (real only)
+            lib().orc_roots_pencil_batch_ms(_p(coeffs), _p(ws), _p(offsets), ctypes.c_int64(B), _p(out), _p(nroots), ctypes.byref(st),
+                                            pp, ctypes.c_uint64(seed), int(threads), int(sched), int(L), int(small + 1000 * reuse + 100000 * dense))
+        else:
+            lib().orc_roots_pencil_batch(_p(coeffs), _p(ws), _p(offsets), ctypes.c_int64(B), int(cx), _p(out), _p(nroots),
+                                         ctypes.byref(st), ctypes.c_uint64(seed), int(threads))
     res = (out, roff, nroots[:B], st.as_dict())
     if per_poly:
         res = res + ([pp[i].as_dict() for i in range(B)],)

@@ -620,3 +620,31 @@ def test_gpu_chain_more_polynomials_than_resident_ctas(A, ctx, oracle):
         check_parity([rows[p] for p in (0, 333, 699)], [got[p] for p in (0, 333, 699)], want)
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("L,reuse,small,dense", [(4, 1, 16, 1), (8, 2, 16, 1), (16, 2, 24, 1), (16, 2, 24, 0), (32, 2, 40, 1)])
+def test_gpu_pencil_pipelined_bitwise_vs_sequential_multishift(A, oracle, L, reuse, small, dense):
+    """The pencil unit kernel (five chains, 11 turnovers per step, dense V W^{-1} trailing block) against the
+    same multishift schedule executed one bulge after the other on the CPU (oracle amrvw_algorithm_ms on the
+    pencil state, dense_trailing_block_pencil): without FMA contraction the two must agree bit for bit."""
+    c = A.Context(seed=0, strict=True, schedule=A.SCHEDULE_PIPELINED, lanes_per_poly=L, shift_reuse=reuse, small_window=small,
+                  shift_solver=A.SHIFTS_DENSE if dense else A.SHIFTS_CHASE)
+    try:
+        rows = batch(oracle, 41, 8, 150) + batch(oracle, 42, 4, 321) + batch(oracle, 43, 5, 64) + batch(oracle, 44, 3, 30) + [p4, p5, p6]
+        pairs = [A.basic_pencil(r) if i % 2 == 0 or len(r) <= 3 else pencil_split(r, (len(r) - 1) // 2) for i, r in enumerate(rows)]
+        vs = np.concatenate([v for v, _ in pairs]); ws = np.concatenate([w for _, w in pairs])
+        off = np.zeros(len(rows) + 1, dtype=np.int64); np.cumsum([len(v) for v, _ in pairs], out=off[1:])
+        out, roff, nr, tot, pp = oracle.roots_csr(vs, off, ws=ws, sched=1, L=L, small=small, reuse=reuse, dense=dense, per_poly=True)
+        got = A.roots([v for v, _ in pairs], [w for _, w in pairs], ctx=c)
+        n_checked = 0
+        for p, g in enumerate(got):
+            if pp[p]["exceptional"]:
+                continue
+            w = out[roff[p]:roff[p] + nr[p]]
+            assert np.array_equal(g.view(np.float64), w.view(np.float64)), f"pencil {p} (degree {len(rows[p]) - 1}) differs"
+            n_checked += 1
+        assert n_checked >= 18
+        if not any(x["exceptional"] for x in pp):
+            assert c.last_stats["fat_steps"] == tot["fat_steps"] and c.last_stats["turnovers"] == tot["turnovers"]
+    finally:
+        c.close()

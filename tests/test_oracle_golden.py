@@ -438,3 +438,30 @@ def test_readme_statistic_miniature(oracle):
     expect = 2 / np.pi * np.log(n) + 0.625738072 + 2 / (np.pi * n)
     assert abs(counts.mean() - expect) < 4 * counts.std() / np.sqrt(B)
     assert st["unconverged"] == 0
+
+
+def test_oracle_pencil_multishift_schedule_matches_reference_schedule(oracle):
+    """The sequential twin of the GPU pencil unit schedule (amrvw_algorithm_ms on the pencil state, shifts from
+    dense_trailing_block_pencil or the core-chasing sub-solve) finds the roots of the reference's one-bulge
+    schedule: minimum-distance matching within the conditioning-scaled tolerance, equal real-root counts."""
+    from conftest import match_roots, pencil_split, root_condition_tolerance
+    rows = [oracle.fill_coeffs(44, i, 0, d + 1) for i, d in enumerate([120, 97, 64, 33])]
+    for split in ("basic", "half"):
+        pairs = []
+        for r in rows:
+            if split == "basic":
+                vs_ = r[:-1].copy(); ws_ = np.zeros(len(r) - 1); ws_[-1] = r[-1]      # basic_pencil (companion.jl:44-54)
+                pairs.append((vs_, ws_))
+            else:
+                pairs.append(pencil_split(r, (len(r) - 1) // 2))
+        vs = np.concatenate([v for v, _ in pairs]); ws = np.concatenate([w for _, w in pairs])
+        off = np.zeros(len(rows) + 1, dtype=np.int64); np.cumsum([len(v) for v, _ in pairs], out=off[1:])
+        ref = oracle.roots_csr(vs, off, ws=ws)
+        for L, reuse, small, dense in ((8, 2, 16, 1), (16, 2, 24, 0), (4, 1, 16, 1)):
+            out, roff, nr, tot = oracle.roots_csr(vs, off, ws=ws, sched=1, L=L, small=small, reuse=reuse, dense=dense)
+            assert tot["fat_steps"] > 0 and tot["unconverged"] == 0
+            for p, r in enumerate(rows):
+                g = out[roff[p]:roff[p] + nr[p]]; w = ref[0][ref[1][p]:ref[1][p] + ref[2][p]]
+                d, idx = match_roots(g, w)
+                assert np.max(d / root_condition_tolerance(r, w[idx], C=256.0)) <= 1.0
+                assert np.sum(g.imag == 0) == np.sum(w.imag == 0)
