@@ -1246,6 +1246,178 @@ static int solve_simple_cases(const cplx* ps, int N, cplx* out) {
     return 2;
 }
 
+// ------------------------------------------------------------------ complex multishift schedule (GPU: csrc/css_units.cuh)
+// Sequential twin of the complex unit kernel: a fat step sends (m + 1) * reuse bulges, m + 1 = min(L / reuse,
+// delta) shifts = the eigenvalues of the trailing block of the window, through the window one after the other
+// (on the GPU they travel two indices apart, each carrying its creation phase down Q; the reference's
+// push-down, diagonal.jl:199-225, applies the same multiplications to the same rotators in the same order).
+// Shifts: the dense trailing block (entry recurrences) + single-shift complex Hessenberg QR, operation for
+// operation what css_dense_trailing_block_warp / chqr_eigenvalues_warp do.
+static void dense_trailing_block_c(const State<cplx>& s, int k0, int stop, std::vector<cplx>& H, int M) {
+    const int j0 = k0 + 1;
+    H.assign((size_t)M * M, cplx(0.0, 0.0));
+    auto qrot = [&](int t) -> Rot<cplx> { return t <= s.nq() ? s.Q[t] : Rot<cplx>{cplx(1.0, 0.0), 0.0}; };
+    cplx q0c;   // Q[k0] made diagonal: its phase is kept, its sine dropped
+    {
+        const cplx c0 = k0 >= 1 ? s.Q[k0].c : cplx(1.0, 0.0);
+        const double a = abs_(c0);
+        q0c = a == 0.0 ? cplx(1.0, 0.0) : c0 / a;
+    }
+    std::vector<double> isg(M);
+    for (int j = j0; j <= stop + 1; ++j) isg[j - j0] = 1.0 / s.V.Ct[j].s;
+    for (int k = j0; k <= stop + 1; ++k) {
+        double P = 1.0;
+        cplx T = cplx(0.0, 0.0), Vacc = cplx(0.0, 0.0);
+        const cplx ck = s.V.B[k].c, dk = s.V.D[k];
+        const double sk = s.V.B[k].s;
+        for (int j = k; j >= j0; --j) {
+            const cplx w = (j == k) ? cplx(-sk, 0.0) : (conj_(s.V.B[j].c) * P) * ck;
+            const cplx ctc = s.V.Ct[j].c;
+            const double ig = isg[j - j0];
+            const cplx X = s.DQ[j] * (((w + ctc * T) * ig) * dk);
+            const Rot<cplx> qj = qrot(j);
+            if (j + 1 <= stop + 1) H[(size_t)(j + 1 - j0) * M + (k - j0)] = conj_(qj.c) * Vacc - qj.s * X;
+            Vacc = qj.c * X + qj.s * Vacc;
+            T = (-(conj_(ctc) * w) - T) * ig;
+            if (j < k) P = P * s.V.B[j].s;
+        }
+        H[(size_t)(k - j0)] = conj_(q0c) * Vacc;
+    }
+}
+static bool chqr_eigenvalues(std::vector<cplx>& Hm, int M, std::vector<cplx>& E) {
+    auto h = [&](int i, int j) -> cplx& { return Hm[(size_t)i * M + j]; };
+    E.assign(M, cplx(0.0, 0.0));
+    std::vector<cplx> gs(2 * M);
+    int en = M - 1, itn = 30 * M, its = 0;
+    cplx t = cplx(0.0, 0.0);
+    while (en >= 0) {
+        int l = 0;
+        for (int lc = en; lc >= 1; --lc) {
+            const cplx d0 = h(lc - 1, lc - 1), d1 = h(lc, lc), sb = h(lc, lc - 1);
+            const double sd = std::fabs(d0.re) + std::fabs(d0.im) + std::fabs(d1.re) + std::fabs(d1.im);
+            if (sd + (std::fabs(sb.re) + std::fabs(sb.im)) == sd) { l = lc; break; }
+        }
+        if (l == en) { E[en] = h(en, en) + t; en -= 1; its = 0; continue; }
+        if (itn == 0) return false;
+        cplx sft;
+        if (its == 10 || its == 20) {
+            sft = cplx(std::fabs(h(en, en - 1).re) + (en >= 2 ? std::fabs(h(en - 1, en - 2).re) : 0.0), 0.0);
+        } else {
+            sft = h(en, en);
+            const cplx x = h(en - 1, en) * h(en, en - 1);
+            if (!iszero_(x)) {
+                const cplx y = (h(en - 1, en - 1) - sft) * 0.5;
+                cplx z = csqrt_(y * y + x);
+                if (y.re * z.re + y.im * z.im < 0.0) z = -z;
+                const cplx den = y + z;
+                if (!iszero_(den)) sft = sft - x / den;
+            }
+        }
+        ++its; --itn;
+        for (int i = 0; i <= en; ++i) h(i, i) = h(i, i) - sft;
+        t = t + sft;
+        for (int k = l; k < en; ++k) {
+            const cplx a = h(k, k), bb = h(k + 1, k);
+            const double r2 = abs2_(a) + abs2_(bb);
+            cplx gc = cplx(1.0, 0.0), gsn = cplx(0.0, 0.0);
+            if (r2 > 0.0) { const double ir = 1.0 / std::sqrt(r2); gc = a * ir; gsn = bb * ir; }
+            gs[2 * k] = gc; gs[2 * k + 1] = gsn;
+            for (int j = k; j <= en; ++j) {
+                const cplx u = h(k, j), v = h(k + 1, j);
+                h(k, j) = conj_(gc) * u + conj_(gsn) * v;
+                h(k + 1, j) = gc * v - gsn * u;
+            }
+        }
+        for (int k = l; k < en; ++k) {
+            const cplx gc = gs[2 * k], gsn = gs[2 * k + 1];
+            const int ihi = std::min(k + 1, en);
+            for (int i = l; i <= ihi; ++i) {
+                const cplx u = h(i, k), v = h(i, k + 1);
+                h(i, k) = u * gc + v * gsn;
+                h(i, k + 1) = v * conj_(gc) - u * conj_(gsn);
+            }
+        }
+    }
+    for (int i = 0; i < M; ++i)
+        if (!(std::isfinite(E[i].re) && std::isfinite(E[i].im))) return false;
+    return true;
+}
+static void amrvw_algorithm_ms_c(State<cplx>& s, std::vector<cplx>& EIGS, Rng& rng, Stats& st, MsParams P) {
+    int n = s.nq();
+    Counter ctr = {0, 1, n, IT_COUNT, -1};
+    EIGS.assign(n + 2, cplx(0, 0));
+    int64_t it_max = 20 * (int64_t)n, kk = 0;
+    cplx A[4];
+    const int lo = 1;
+    check_deflation(s, ctr);
+    while (kk <= it_max) {
+        if (ctr.stop_index < lo) break;
+        check_deflation(s, ctr);
+        ++kk; ++st.trips;
+        int k = ctr.stop_index;
+        int delta = ctr.stop_index - ctr.zero_index;
+        if (delta == 1) {
+            diagonal_block(s, k, A);
+            cplx e1, e2; eig2(A, e1, e2);
+            EIGS[k] = e1; EIGS[k + 1] = e2;
+            if (ctr.stop_index == lo + 1) { diagonal_block(s, lo, A); EIGS[lo] = A[0]; ctr.stop_index = 0; break; }
+            ctr.stop_index = ctr.zero_index - 1; ctr.zero_index = 0; ctr.start_index = 1;
+            check_deflation(s, ctr);
+            if (ctr.stop_index < lo) break;
+        } else if (delta <= 0) {
+            diagonal_block(s, k, A);
+            if (ctr.stop_index == lo) { EIGS[lo] = A[0]; EIGS[lo + 1] = A[3]; ctr.stop_index = 0; break; }
+            EIGS[k + 1] = A[3];
+            ctr.stop_index = ctr.zero_index - 1;
+            if (ctr.stop_index < lo) break;
+            ctr.zero_index = 0; ctr.start_index = 1;
+            check_deflation(s, ctr);
+        } else if (delta <= P.small) {
+            const int lo2 = ctr.start_index, hi2 = ctr.stop_index;
+            const int64_t t0 = st.turnovers;
+            Counter c2 = {lo2 - 1, lo2, hi2, ctr.it_count, -1};
+            bool ok = driver_window(s, lo2, hi2, c2, EIGS, rng, st, it_max);
+            st.serial_turnovers += st.turnovers - t0;
+            if (!ok) st.unconverged += c2.stop_index - lo2 + 2;
+            if (lo2 == 2) { diagonal_block(s, 1, A); EIGS[1] = A[0]; }
+            ctr.stop_index = lo2 - 2; ctr.zero_index = 0; ctr.start_index = 1; ctr.it_count = IT_COUNT;
+            if (ctr.stop_index >= lo) check_deflation(s, ctr);
+        } else if (ctr.it_count == 0) {
+            ++st.fat_steps;
+            for (int b = 0; b < P.L; ++b) { ctr.it_count = 0; bulge_step(s, ctr, rng, st); }
+            ctr.it_count = IT_COUNT - 1;
+        } else {
+            const int m = std::min(P.L / P.reuse - 1, delta - 1);
+            const int stop = ctr.stop_index, k0 = stop - m;
+            std::vector<cplx> sh;
+            bool ok = false;
+            if (P.dense) {
+                std::vector<cplx> H;
+                dense_trailing_block_c(s, k0, stop, H, m + 1);
+                ok = chqr_eigenvalues(H, m + 1, sh);
+            }
+            if (!ok) {   // core-chasing iteration on a copy whose top rotator is made diagonal (not bit-compared with the GPU)
+                State<cplx> t = s;
+                const cplx c0 = k0 >= 1 ? t.Q[k0].c : cplx(1.0, 0.0);
+                const double a = abs_(c0);
+                if (k0 >= 1) { t.Q[k0] = {a == 0.0 ? cplx(1.0, 0.0) : c0 / a, 0.0}; deflate(t, k0); }
+                Counter c2 = {k0, k0 + 1, stop, IT_COUNT, -1};
+                std::vector<cplx> E(s.N + 2, cplx(0, 0));
+                Stats sub;
+                driver_window(t, k0 + 1, stop, c2, E, rng, sub, 20 * (int64_t)(m + 1));
+                st.turnovers += sub.turnovers; st.serial_turnovers += sub.turnovers;
+                sh.assign(E.begin() + k0 + 1, E.begin() + stop + 2);
+            }
+            ++st.fat_steps;
+            for (int rep = 0; rep < P.reuse; ++rep)
+                for (int b = 0; b <= m; ++b) bulge_step(s, ctr, rng, st, &sh[b]);
+            ctr.it_count -= 1;
+        }
+    }
+    if (ctr.stop_index >= lo) st.unconverged += ctr.stop_index + 1;
+    std::sort(EIGS.begin() + 1, EIGS.begin() + n + 2, eig_less);
+}
+
 enum Schedule { SCHED_REFERENCE = 0, SCHED_MULTISHIFT = 1 };
 
 // roots(ps) companion.jl:252-272.  `out` receives len-1 roots... precisely: (trimmed degree) roots
@@ -1271,7 +1443,10 @@ static void roots_one(const S* ps_in, int len, cplx* out, int* nroots, uint64_t 
         if constexpr (is_real<S>::value) {
             if (sched == SCHED_MULTISHIFT) amrvw_algorithm_ms(s, E, rng, st, P);
             else amrvw_algorithm(s, E, rng, st);
-        } else amrvw_algorithm(s, E, rng, st);
+        } else {
+            if (sched == SCHED_MULTISHIFT) amrvw_algorithm_ms_c(s, E, rng, st, P);
+            else amrvw_algorithm(s, E, rng, st);
+        }
         cnt = n - 1;
         for (int i = 0; i < cnt; ++i) out[i] = E[i + 1];
     }
@@ -1420,7 +1595,7 @@ int orc_roots_batch(const double* coeffs, const int64_t* offsets, int64_t B, int
         int len = (int)(offsets[p + 1] - offsets[p]);
         cplx* out = reinterpret_cast<cplx*>(roots_reim) + (offsets[p] - p);
         int nr = 0;
-        if (is_complex) roots_one<cplx>(reinterpret_cast<const cplx*>(coeffs) + offsets[p], len, out, &nr, seed, (uint64_t)p, st, SCHED_REFERENCE, P);
+        if (is_complex) roots_one<cplx>(reinterpret_cast<const cplx*>(coeffs) + offsets[p], len, out, &nr, seed, (uint64_t)p, st, sched, P);
         else roots_one<double>(coeffs + offsets[p], len, out, &nr, seed, (uint64_t)p, st, sched, P);
         nroots[p] = nr;
         if (per_poly) { std::memset(&per_poly[p], 0, sizeof(orc_stats)); add_stats(&per_poly[p], st); }

@@ -648,3 +648,29 @@ def test_gpu_pencil_pipelined_bitwise_vs_sequential_multishift(A, oracle, L, reu
             assert c.last_stats["fat_steps"] == tot["fat_steps"] and c.last_stats["turnovers"] == tot["turnovers"]
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("L,reuse,small", [(8, 2, 24), (16, 2, 24), (16, 1, 24), (32, 2, 40)])
+def test_gpu_css_pipelined_vs_sequential_multishift(A, oracle, L, reuse, small):
+    """The complex unit kernel (no-FMA build) against its sequential twin in the oracle (amrvw_algorithm_ms_c:
+    same fat steps, shifts from the same dense block + complex Hessenberg QR, bulges one after the other with
+    the reference's phase push-down).  hypot / complex division / complex sqrt come from different math
+    libraries on the two sides, so this is not a bit comparison: same number of fat steps within 2 %, roots
+    within the conditioning-scaled tolerance at a constant 16x tighter than against the reference schedule."""
+    c = A.Context(seed=0, strict=True, schedule=A.SCHEDULE_PIPELINED, lanes_per_poly=L, shift_reuse=reuse, small_window=small,
+                  shift_solver=A.SHIFTS_DENSE)
+    try:
+        rows = []
+        for i, d in enumerate([150, 200, 97, 64, 33, 257, 5, 321]):
+            r = oracle.fill_coeffs(77, i, 0, 2 * (d + 1))
+            rows.append(r[0::2] + 1j * r[1::2])
+        flat = np.concatenate(rows); off = np.zeros(len(rows) + 1, dtype=np.int64); np.cumsum([len(r) for r in rows], out=off[1:])
+        out, roff, nr, tot, pp = oracle.roots_csr(flat, off, sched=1, L=L, small=small, reuse=reuse, dense=1, per_poly=True)
+        got = A.roots(rows, ctx=c)
+        want = [out[roff[p]:roff[p] + nr[p]] for p in range(len(rows))]
+        check_parity(rows, got, want, C=4.0, real_counts=False)
+        assert c.last_stats["unconverged"] == 0
+        assert abs(c.last_stats["fat_steps"] - tot["fat_steps"]) <= 0.02 * tot["fat_steps"] + 1
+        assert abs(c.last_stats["turnovers"] - tot["turnovers"]) <= 0.02 * tot["turnovers"]
+    finally:
+        c.close()

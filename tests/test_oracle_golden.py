@@ -465,3 +465,22 @@ def test_oracle_pencil_multishift_schedule_matches_reference_schedule(oracle):
                 d, idx = match_roots(g, w)
                 assert np.max(d / root_condition_tolerance(r, w[idx], C=256.0)) <= 1.0
                 assert np.sum(g.imag == 0) == np.sum(w.imag == 0)
+
+
+def test_oracle_complex_multishift_schedule_matches_reference_schedule(oracle):
+    """The sequential twin of the GPU complex unit schedule (amrvw_algorithm_ms_c: dense trailing block + complex
+    Hessenberg QR or the core-chasing sub-solve for the shifts) finds the roots of the reference's schedule."""
+    from conftest import match_roots, root_condition_tolerance
+    rows = []
+    for i, d in enumerate([120, 97, 64, 33, 200]):
+        r = oracle.fill_coeffs(77, i, 0, 2 * (d + 1))
+        rows.append(r[0::2] + 1j * r[1::2])
+    flat = np.concatenate(rows); off = np.zeros(len(rows) + 1, dtype=np.int64); np.cumsum([len(r) for r in rows], out=off[1:])
+    ref = oracle.roots_csr(flat, off)
+    for L, reuse, small, dense in ((8, 2, 24, 1), (16, 1, 24, 1), (16, 2, 24, 0), (4, 1, 16, 1)):
+        out, roff, nr, tot = oracle.roots_csr(flat, off, sched=1, L=L, small=small, reuse=reuse, dense=dense)
+        assert tot["fat_steps"] > 0 and tot["unconverged"] == 0
+        for p, r in enumerate(rows):
+            g = out[roff[p]:roff[p] + nr[p]]; w = ref[0][ref[1][p]:ref[1][p] + ref[2][p]]
+            d, idx = match_roots(g, w)
+            assert np.max(d / root_condition_tolerance(r, w[idx])) <= 1.0
