@@ -22,8 +22,11 @@
 // without FMA contraction -- build with -ffp-contract=off).
 //
 // Besides the reference schedule (one bulge at a time) the file also holds the "multishift"
-// schedule used by the pipelined GPU kernel (section MS below): the same rotator operations, a
-// different order of shifts.  It exists so the GPU schedule can be checked step for step.
+// schedules used by the pipelined GPU kernels (section MS below): the same rotator operations, a
+// different order of shifts.  They exist so the GPU schedules can be checked step for step:
+// amrvw_algorithm_ms on the rank-one and on the pencil state (Float64; the no-FMA GPU builds of
+// the unit, chained-warp and pencil kernels are bit-identical to it) and amrvw_algorithm_ms_c
+// (ComplexF64; held to a tight tolerance, the complex math-library calls differ between the sides).
 // =====================================================================================
 #include <algorithm>
 #include <cmath>
