@@ -735,28 +735,6 @@ __global__ void __launch_bounds__(64) css_setup_kernel(Problem<cplx> pr) {
     }
     pr.rec[p] = rec;
 }
-template <int L>
-__global__ void css_enqueue_kernel(Problem<cplx> pr, RoundQueue* q, int* slots, unsigned mask, UnitPark* park) {
-    constexpr int G = 32 / L;
-    const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long nunits = (pr.nbatch + G - 1) / G;
-    if (u >= nunits) return;
-    bool any = false;
-    for (int g = 0; g < G; ++g) {
-        const long long p = unit_poly(pr, u * G + g);
-        if (p < pr.nbatch && pr.rec[p].iterating) any = true;
-    }
-    if (!any) return;
-    UnitPark up;
-    up.t = -1;
-    for (int g = 0; g < 8; ++g) { up.sp[g] = 0; up.nturn[g] = 0; }
-    up.pad[0] = up.pad[1] = up.pad[2] = 0;
-    park[u] = up;
-    __threadfence();
-    atomicAdd(&q->remaining, 1u);
-    const unsigned k = atomicAdd(&q->tail, 1u);
-    atomicExch(slots + (k & mask), (int)u);
-}
 // every deferred window with the reference's one-bulge schedule, in place (windows are disjoint and
 // nothing else runs any more)
 __global__ void __launch_bounds__(64) css_small_kernel(Problem<cplx> pr) {
@@ -776,45 +754,6 @@ __global__ void __launch_bounds__(64) css_small_kernel(Problem<cplx> pr) {
     if (st.exceptional) atomicAdd(&rw->st.exceptional, st.exceptional);
     if (left) atomicAdd(&rw->ls.unconv, left);
 }
-__global__ void __launch_bounds__(256) css_finish_kernel(Problem<cplx> pr, int smem_elems) {
-    extern __shared__ __align__(16) unsigned char sort_smem[];
-    cplx* tile = reinterpret_cast<cplx*>(sort_smem);
-    const long long p = blockIdx.x;
-    const PolyRec* recp = pr.rec + p;
-    const int n = recp->N;
-    if (n <= 0) return;
-    cplx* out = pr.roots + (pr.offsets[p] - p);
-    cplx* a = out;
-    const bool in_smem = n <= smem_elems;
-    if (in_smem) {
-        for (int i = threadIdx.x; i < n; i += blockDim.x) tile[i] = out[i];
-        a = tile;
-    }
-    __syncthreads();
-    int np2 = 1;
-    while (np2 < n) np2 <<= 1;
-    for (int k = 2; k <= np2; k <<= 1) {
-        for (int j = k >> 1; j >= 1; j >>= 1) {
-            const bool first = (j == (k >> 1));
-            for (int t = threadIdx.x; t < (np2 >> 1); t += blockDim.x) {
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const int l = first ? (i ^ (k - 1)) : (i | j);
-                if (l < n && i < n) {
-                    const cplx x = a[i], y = a[l];
-                    if (eig_less(y, x)) { a[i] = y; a[l] = x; }
-                }
-            }
-            __syncthreads();
-        }
-    }
-    if (in_smem) for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = tile[i];
-    if (threadIdx.x == 0) {
-        PolyRec rec = *recp;
-        rec.st.turnovers = rec.serial_turnovers + rec.chase_turnovers;
-        rec.st.unconverged = rec.ls.unconv + (rec.ls.ctr.stop_index >= 1 ? rec.ls.ctr.stop_index + 1 : 0);
-        finish_poly(pr, p, out, rec.N, rec.K, rec.st.unconverged, rec.st);
-    }
-}
 
 // ---------------------------------------------------------------- host side
 template <int L, int MH>
@@ -822,7 +761,7 @@ static cudaError_t launch_css_units(const Problem<cplx>& pr, const PipeParams& p
                                     int sm_count, cudaStream_t st) {
     constexpr int G = 32 / L;
     const long long nunits = (pr.nbatch + G - 1) / G;
-    css_enqueue_kernel<L><<<(int)((nunits + 127) / 128), 128, 0, st>>>(pr, q, slots, mask, park);
+    unit_enqueue_kernel<L, cplx><<<(int)((nunits + 127) / 128), 128, 0, st>>>(pr, q, slots, mask, park);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     int per_sm = 0;
@@ -891,8 +830,8 @@ static cudaError_t launch_css_pipelined(Problem<cplx> pr, const amrvw_options& o
     {
         const int smem_elems = max_len - 1 <= AMRVW_SORT_SMEM ? (max_len > 1 ? max_len - 1 : 1) : AMRVW_SORT_SMEM;
         const size_t smem = (size_t)smem_elems * sizeof(cplx);
-        if ((e = cudaFuncSetAttribute(css_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        css_finish_kernel<<<(int)pr.nbatch, 256, smem, st>>>(pr, smem_elems);
+        if ((e = cudaFuncSetAttribute(rounds_finish_kernel<cplx>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        rounds_finish_kernel<cplx><<<(int)pr.nbatch, 256, smem, st>>>(pr, smem_elems);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     *launches += 5;

@@ -563,7 +563,7 @@ template <int L, int MH>
 static cudaError_t launch_pen_units(const Problem<double>& pr, const PipeParams& pp, const QueueBufs& qb, PenLane* parked, int seg_steps, int sm_count, cudaStream_t st) {
     constexpr int G = 32 / L;
     const long long nunits = (pr.nbatch + G - 1) / G;
-    unit_enqueue_kernel<L><<<(int)((nunits + 127) / 128), 128, 0, st>>>(pr, qb.q, qb.slots, qb.mask, qb.park);
+    unit_enqueue_kernel<L, double><<<(int)((nunits + 127) / 128), 128, 0, st>>>(pr, qb.q, qb.slots, qb.mask, qb.park);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     int per_sm = 0;
@@ -638,8 +638,8 @@ static cudaError_t launch_pencil_pipelined(Problem<double> pr, const amrvw_optio
     {
         const int smem_elems = max_len <= AMRVW_SORT_SMEM ? (max_len > 1 ? max_len : 1) : AMRVW_SORT_SMEM;
         const size_t smem = (size_t)smem_elems * sizeof(cplx);
-        if ((e = cudaFuncSetAttribute(rounds_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        rounds_finish_kernel<<<(int)pr.nbatch, 256, smem, st>>>(pr, smem_elems);
+        if ((e = cudaFuncSetAttribute(rounds_finish_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        rounds_finish_kernel<double><<<(int)pr.nbatch, 256, smem, st>>>(pr, smem_elems);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     *launches += 5;

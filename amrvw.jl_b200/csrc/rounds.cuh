@@ -155,8 +155,8 @@ struct UnitPark {           // mutable per-unit state between visits; accessed w
 AMRVW_DI void st_cg_rot(Rot<double>* p, const Rot<double> r) { __stcg(reinterpret_cast<double2*>(p), make_double2(r.c, r.s)); }
 
 // queue every unit that has a polynomial to iterate; one thread per unit
-template <int L>
-__global__ void unit_enqueue_kernel(Problem<double> pr, RoundQueue* q, int* slots, unsigned mask, UnitPark* park) {
+template <int L, class S>
+__global__ void unit_enqueue_kernel(Problem<S> pr, RoundQueue* q, int* slots, unsigned mask, UnitPark* park) {
     constexpr int G = 32 / L;
     const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long nunits = (pr.nbatch + G - 1) / G;
@@ -528,7 +528,8 @@ __global__ void __launch_bounds__(64) rounds_small_kernel(Problem<double> pr) {
 // being stored; it runs in shared memory when the polynomial fits, otherwise in place in global
 // memory.  eig_less is a total order, so the result is the one the serial heap sort gives.
 #define AMRVW_SORT_SMEM 4096
-__global__ void __launch_bounds__(256) rounds_finish_kernel(Problem<double> pr, int smem_elems) {
+template <class S>
+__global__ void __launch_bounds__(256) rounds_finish_kernel(Problem<S> pr, int smem_elems) {
     extern __shared__ __align__(16) unsigned char sort_smem[];
     cplx* tile = reinterpret_cast<cplx*>(sort_smem);
     const long long p = blockIdx.x;
@@ -606,7 +607,7 @@ template <int L, int MH>
 static cudaError_t launch_units(const Problem<double>& pr, const PipeParams& pp, const QueueBufs& qb, int seg_steps, int sm_count, cudaStream_t st) {
     constexpr int G = 32 / L;
     const long long nunits = (pr.nbatch + G - 1) / G;
-    unit_enqueue_kernel<L><<<(int)((nunits + 127) / 128), 128, 0, st>>>(pr, qb.q, qb.slots, qb.mask, qb.park);
+    unit_enqueue_kernel<L, double><<<(int)((nunits + 127) / 128), 128, 0, st>>>(pr, qb.q, qb.slots, qb.mask, qb.park);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     int per_sm = 0;
@@ -686,8 +687,8 @@ static cudaError_t launch_rounds_rds(Problem<double> pr, const amrvw_options& op
     {
         const int smem_elems = max_len - 1 <= AMRVW_SORT_SMEM ? (max_len > 1 ? max_len - 1 : 1) : AMRVW_SORT_SMEM;
         const size_t smem = (size_t)smem_elems * sizeof(cplx);
-        if ((e = cudaFuncSetAttribute(rounds_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        rounds_finish_kernel<<<(int)pr.nbatch, 256, smem, st>>>(pr, smem_elems);
+        if ((e = cudaFuncSetAttribute(rounds_finish_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        rounds_finish_kernel<double><<<(int)pr.nbatch, 256, smem, st>>>(pr, smem_elems);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     *launches += L > 32 ? 4 : 5;
