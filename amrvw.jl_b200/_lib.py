@@ -12,7 +12,8 @@ class AmrvwError(RuntimeError):
 
 class Options(ctypes.Structure):
     _fields_ = [("schedule", ctypes.c_int32), ("lanes_per_poly", ctypes.c_int32), ("shift_reuse", ctypes.c_int32),
-                ("small_window", ctypes.c_int32), ("shift_solver", ctypes.c_int32), ("reserved", ctypes.c_int32), ("seed", ctypes.c_uint64)]
+                ("small_window", ctypes.c_int32), ("shift_solver", ctypes.c_int32), ("it_count", ctypes.c_int32), ("seed", ctypes.c_uint64),
+                ("it_max_factor", ctypes.c_int32), ("reserved", ctypes.c_int32), ("tol", ctypes.c_double)]
 
 
 class Stats(ctypes.Structure):
@@ -32,6 +33,9 @@ _I64 = ctypes.c_int64
 _SIGS = {
     "amrvw_version": (ctypes.c_int, []),
     "amrvw_create": (ctypes.c_int, [ctypes.POINTER(_P), ctypes.c_int, ctypes.c_uint64]),
+    "amrvw_create_multi": (ctypes.c_int, [ctypes.POINTER(_P), ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_uint64]),
+    "amrvw_device_count": (ctypes.c_int, [_P]),
+    "amrvw_partition_batch": (ctypes.c_int, [_P, _I64, ctypes.c_int, _P]),
     "amrvw_destroy": (ctypes.c_int, [_P]),
     "amrvw_last_error": (ctypes.c_char_p, [_P]),
     "amrvw_default_options": (None, [ctypes.POINTER(Options)]),
@@ -42,6 +46,7 @@ _SIGS = {
     "amrvw_roots_css_c64": (ctypes.c_int, [_P, _P, _P, _I64, _P, _P, _P, ctypes.POINTER(Stats)]),
     "amrvw_roots_pencil_f64": (ctypes.c_int, [_P, _P, _P, _P, _I64, _P, _P, _P, ctypes.POINTER(Stats)]),
     "amrvw_roots_pencil_c64": (ctypes.c_int, [_P, _P, _P, _P, _I64, _P, _P, _P, ctypes.POINTER(Stats)]),
+    "amrvw_count_real_roots_rds_f64": (ctypes.c_int, [_P, _P, _P, _I64, _P, _P, ctypes.POINTER(Stats)]),
     "amrvw_roots_rds_f64_dev": (ctypes.c_int, [_P, _P, _P, _I64, _I64, _I64, _P, _P, _P, ctypes.POINTER(Stats)]),
     "amrvw_roots_css_c64_dev": (ctypes.c_int, [_P, _P, _P, _I64, _I64, _I64, _P, _P, _P, ctypes.POINTER(Stats)]),
     "amrvw_roots_pencil_f64_dev": (ctypes.c_int, [_P, _P, _P, _P, _I64, _I64, _I64, _P, _P, _P, ctypes.POINTER(Stats)]),
@@ -59,16 +64,16 @@ _libs = {}
 
 
 def lib_path(strict=False):
-    if not strict and os.environ.get("AMRVW_B200_LIB"):      # development: try an alternative build of the same ABI
-        return os.environ["AMRVW_B200_LIB"]
     return os.path.join(HERE, "libamrvw_b200_strict.so" if strict else "libamrvw_b200.so")
 
 
-def load(strict=False):
-    """dlopen the in-tree library and type its exports.  Raises AmrvwError if it was not built."""
-    if strict in _libs:
-        return _libs[strict]
-    path = lib_path(strict)
+def load(strict=False, path=None):
+    """dlopen the in-tree library and type its exports.  Raises AmrvwError if it was not built.
+    `path` (tools/ only) loads another build of the same ABI, e.g. a kernel variant under build/."""
+    key = path or strict
+    if key in _libs:
+        return _libs[key]
+    path = path or lib_path(strict)
     if not os.path.exists(path):
         raise AmrvwError(f"{path} is missing: run `python __graft_entry__.py build` (there is no CPU fallback)")
     lib = ctypes.CDLL(path)
@@ -76,5 +81,5 @@ def load(strict=False):
         fn = getattr(lib, name)  # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args
-    _libs[strict] = lib
+    _libs[key] = lib
     return lib

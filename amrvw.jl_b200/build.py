@@ -34,6 +34,7 @@ def build(strict=True, force=False, verbose=False):
     outs = [(os.path.join(HERE, "libamrvw_b200.so"), [])]
     if strict:
         outs.append((os.path.join(HERE, "libamrvw_b200_strict.so"), ["-fmad=false", "-DAMRVW_STRICT"]))
+    procs = []
     for out, extra in outs:
         if not force and not _stale(out):
             continue
@@ -42,7 +43,10 @@ def build(strict=True, force=False, verbose=False):
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), file=sys.stderr)
-        subprocess.run(cmd, check=True)
+        procs.append((cmd, subprocess.Popen(cmd)))     # the two builds are independent: side by side
+    for cmd, p in procs:
+        if p.wait() != 0:
+            raise subprocess.CalledProcessError(p.returncode, cmd)
     return [o for o, _ in outs]
 
 

@@ -12,7 +12,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace amrvw;
@@ -30,11 +32,15 @@ struct amrvw_ctx {
     amrvw_options opt;
     std::string err;
     // grow-only device buffers
-    DevBuf chains[5], diags[3], coeffs, coeffs2, offsets, roots, nroots, nunconv, stats, shifts, state, prof, rec, fatshifts, swlist, counters, queue, qslots, park, parked, order, orderkeys;
+    DevBuf chains[5], diags[3], coeffs, coeffs2, offsets, roots, nroots, nunconv, stats, shifts, state, prof, rec, fatshifts, swlist, counters, queue, qslots, park, parked, order, orderkeys, counts;
+    bool queue_used = false;
     cudaEvent_t evpool[32] = {};
     RoundsTimes times = {};
     bool prof_valid = false;
     int sm_count = 148;
+    // multi-device context (amrvw_create_multi): one single-device context per GPU; this object then owns no
+    // device memory of its own and only partitions host batches over `subs`
+    std::vector<amrvw_ctx*> subs;
 };
 
 static int fail(amrvw_ctx* ctx, int code, const std::string& msg) {
@@ -69,8 +75,11 @@ void amrvw_default_options(amrvw_options* opt) {
     opt->shift_reuse = 0;
     opt->small_window = 0;
     opt->shift_solver = AMRVW_SHIFTS_AUTO;
-    opt->reserved = 0;
+    opt->it_count = 15;                          // create-bulge.jl:9
     opt->seed = 0;
+    opt->it_max_factor = 20;                     // AMRVW_algorithm.jl:25
+    opt->reserved = 0;
+    opt->tol = 2.220446049250313e-16;            // AMRVW_algorithm.jl:184: eps(Float64)
 }
 
 int amrvw_create(amrvw_ctx** out, int device, uint64_t seed) {
@@ -95,12 +104,52 @@ int amrvw_create(amrvw_ctx** out, int device, uint64_t seed) {
     return AMRVW_OK;
 }
 
+int amrvw_create_multi(amrvw_ctx** out, const int* devices, int ndev, uint64_t seed) {
+    if (!out) return AMRVW_ERR_ARGUMENT;
+    *out = nullptr;
+    if (ndev < 0 || (ndev > 0 && !devices)) return AMRVW_ERR_ARGUMENT;
+    int have = 0;
+    if (cudaGetDeviceCount(&have) != cudaSuccess || have == 0) return AMRVW_ERR_NO_DEVICE;  // no CPU fallback
+    std::vector<int> devs;
+    if (ndev == 0) for (int d = 0; d < have; ++d) devs.push_back(d);          // every visible device
+    else devs.assign(devices, devices + ndev);
+    for (size_t i = 0; i < devs.size(); ++i) {
+        if (devs[i] < 0 || devs[i] >= have) return AMRVW_ERR_ARGUMENT;
+        for (size_t j = 0; j < i; ++j) if (devs[j] == devs[i]) return AMRVW_ERR_ARGUMENT;   // each device once
+    }
+    if (devs.size() == 1) return amrvw_create(out, devs[0], seed);
+    amrvw_ctx* ctx = new amrvw_ctx();
+    amrvw_default_options(&ctx->opt);
+    ctx->opt.seed = seed;
+    ctx->device = devs[0];
+    for (int d : devs) {
+        amrvw_ctx* sub = nullptr;
+        const int rc = amrvw_create(&sub, d, seed);
+        if (rc != AMRVW_OK) {
+            for (amrvw_ctx* s2 : ctx->subs) amrvw_destroy(s2);
+            delete ctx;
+            return rc;
+        }
+        ctx->subs.push_back(sub);
+    }
+    ctx->sm_count = ctx->subs[0]->sm_count;
+    *out = ctx;
+    return AMRVW_OK;
+}
+
+int amrvw_device_count(const amrvw_ctx* ctx) { return ctx ? (ctx->subs.empty() ? 1 : (int)ctx->subs.size()) : 0; }
+
 int amrvw_destroy(amrvw_ctx* ctx) {
     if (!ctx) return AMRVW_OK;
+    if (!ctx->subs.empty()) {
+        for (amrvw_ctx* s2 : ctx->subs) amrvw_destroy(s2);
+        delete ctx;
+        return AMRVW_OK;
+    }
     cudaSetDevice(ctx->device);
     DevBuf* all[] = {&ctx->chains[0], &ctx->chains[1], &ctx->chains[2], &ctx->chains[3], &ctx->chains[4], &ctx->diags[0], &ctx->diags[1], &ctx->diags[2],
                      &ctx->coeffs, &ctx->coeffs2, &ctx->offsets, &ctx->roots, &ctx->nroots, &ctx->nunconv, &ctx->stats, &ctx->shifts, &ctx->state, &ctx->prof,
-                     &ctx->rec, &ctx->fatshifts, &ctx->swlist, &ctx->counters, &ctx->queue, &ctx->qslots, &ctx->park, &ctx->parked, &ctx->order, &ctx->orderkeys};
+                     &ctx->rec, &ctx->fatshifts, &ctx->swlist, &ctx->counters, &ctx->queue, &ctx->qslots, &ctx->park, &ctx->parked, &ctx->order, &ctx->orderkeys, &ctx->counts};
     for (DevBuf* b : all) if (b->ptr) cudaFree(b->ptr);
     for (cudaEvent_t e : ctx->evpool) if (e) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -112,6 +161,12 @@ int amrvw_destroy(amrvw_ctx* ctx) {
 
 const char* amrvw_last_error(const amrvw_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
+}  // extern "C"
+// the single-device context behind the calls that need device buffers of their own (self-tests, probes)
+static amrvw_ctx* primary(amrvw_ctx* ctx) { return (ctx && !ctx->subs.empty()) ? ctx->subs[0] : ctx; }
+extern "C" {
+
+
 int amrvw_set_options(amrvw_ctx* ctx, const amrvw_options* opt) {
     if (!ctx || !opt) return AMRVW_ERR_ARGUMENT;
     if (opt->schedule < 0 || opt->schedule > 2) return fail(ctx, AMRVW_ERR_ARGUMENT, "schedule must be 0, 1 or 2");
@@ -121,12 +176,24 @@ int amrvw_set_options(amrvw_ctx* ctx, const amrvw_options* opt) {
         return fail(ctx, AMRVW_ERR_ARGUMENT, "shift_reuse must be 0, 1, 2, 4 or 8");
     if (opt->small_window < 0) return fail(ctx, AMRVW_ERR_ARGUMENT, "small_window must be >= 0");
     if (opt->shift_solver < 0 || opt->shift_solver > 2) return fail(ctx, AMRVW_ERR_ARGUMENT, "shift_solver must be 0, 1 or 2");
+    if (opt->it_count < 0 || opt->it_max_factor < 0) return fail(ctx, AMRVW_ERR_ARGUMENT, "it_count and it_max_factor must be >= 0 (0 = the reference's 15 and 20)");
+    if (!(opt->tol >= 0.0) || opt->tol > 1e-4) return fail(ctx, AMRVW_ERR_ARGUMENT, "tol must be in [0, 1e-4] (0 = the reference's eps)");
+    if (opt->reserved != 0) return fail(ctx, AMRVW_ERR_ARGUMENT, "reserved must be 0");
     ctx->opt = *opt;
+    if (ctx->opt.it_count == 0) ctx->opt.it_count = 15;
+    if (ctx->opt.it_max_factor == 0) ctx->opt.it_max_factor = 20;
+    if (ctx->opt.tol == 0.0) ctx->opt.tol = 2.220446049250313e-16;
+    for (amrvw_ctx* sub : ctx->subs) {
+        amrvw_options o = ctx->opt;
+        const int rc = amrvw_set_options(sub, &o);
+        if (rc != AMRVW_OK) return fail(ctx, rc, sub->err);
+    }
     return AMRVW_OK;
 }
 
 int amrvw_set_stream(amrvw_ctx* ctx, void* s) {
     if (!ctx) return AMRVW_ERR_ARGUMENT;
+    if (!ctx->subs.empty()) return fail(ctx, AMRVW_ERR_ARGUMENT, "a multi-device context runs on its own per-device streams");
     ctx->stream = (cudaStream_t)s;   // NULL = legacy default stream
     return AMRVW_OK;
 }
@@ -155,10 +222,42 @@ __global__ void reduce_stats_kernel(const PolyStats* st, long long n, StatsAccum
     atomicAdd((unsigned long long*)&out->fat_steps, (unsigned long long)f);
 }
 
+// the unit queue's sticky abort flag (rounds.cuh: queue_pop); call with the stream idle
+static int check_queue_abort(amrvw_ctx* ctx) {
+    if (!ctx->queue_used || !ctx->counters.ptr) return AMRVW_OK;
+    unsigned flag = 0;
+    CUDA_TRY(ctx, cudaMemcpy(&flag, (const unsigned*)ctx->counters.ptr + CNT_ABORT, sizeof(flag), cudaMemcpyDeviceToHost));
+    if (flag) return fail(ctx, AMRVW_ERR_QUEUE_TIMEOUT, "unit queue timed out: a warp waited ~10 s for work that never came; results are incomplete");
+    return AMRVW_OK;
+}
+
+// workspace of the unit schedules: records, shifts, small-window list, counters; queue and parking sized by the
+// number of units the chosen lane count really gives (L lanes per polynomial -> 32/L polynomials per unit)
+static int reserve_unit_workspace(amrvw_ctx* ctx, int64_t nbatch, int64_t total, int L, size_t lane_bytes, size_t* qcap_out) {
+    int rc;
+    if ((rc = reserve(ctx, ctx->rec, (size_t)nbatch * sizeof(PolyRec)))) return rc;
+    if ((rc = reserve(ctx, ctx->fatshifts, (size_t)nbatch * (size_t)(L < 4 ? 4 : L) * sizeof(Shifts)))) return rc;
+    if ((rc = reserve(ctx, ctx->swlist, ((size_t)total / 3 + (size_t)nbatch + 16) * sizeof(SmallWin)))) return rc;
+    if ((rc = reserve(ctx, ctx->counters, CNT_WORDS * sizeof(unsigned)))) return rc;
+    *qcap_out = 0;
+    if (L > 32) return 0;     // chained warps: no queue, nothing is parked
+    const size_t G = (size_t)(32 / L);
+    const size_t nunits = ((size_t)nbatch + G - 1) / G;
+    size_t qcap = 1024;
+    while (qcap < 2 * nunits + 4096) qcap <<= 1;
+    if ((rc = reserve(ctx, ctx->queue, sizeof(RoundQueue)))) return rc;
+    if ((rc = reserve(ctx, ctx->qslots, qcap * sizeof(int)))) return rc;
+    if ((rc = reserve(ctx, ctx->park, nunits * sizeof(UnitPark)))) return rc;
+    if ((rc = reserve(ctx, ctx->parked, nunits * 32 * lane_bytes))) return rc;
+    *qcap_out = qcap;
+    return 0;
+}
+
 template <class S>
 static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, const int64_t* d_offsets, int64_t nbatch, int64_t total, int64_t max_len,
                    double* d_roots, int32_t* d_nroots, int32_t* d_nunconv, amrvw_stats* stats) {
     if (!ctx) return AMRVW_ERR_ARGUMENT;
+    if (!ctx->subs.empty()) return fail(ctx, AMRVW_ERR_ARGUMENT, "device-pointer entry points need a single-device context (amrvw_create)");
     if (nbatch < 0 || total < 0) return fail(ctx, AMRVW_ERR_ARGUMENT, "negative batch or total");
     if (stats) std::memset(stats, 0, sizeof(*stats));
     if (nbatch == 0) return AMRVW_OK;
@@ -186,96 +285,68 @@ static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, cons
     pr.DQ = (S*)ctx->diags[0].ptr; pr.DR = (S*)ctx->diags[1].ptr; pr.WD = (S*)ctx->diags[2].ptr;
     pr.dstack = (int*)ctx->shifts.ptr;
     pr.prof = nullptr; pr.rec = nullptr; pr.shifts = nullptr; pr.swlist = nullptr; pr.counters = nullptr; pr.order = nullptr;
+    cudaStream_t st = ctx->stream;
     if (stats && var != V_PENCIL_C) {   // warp-cycle counters ride along with the statistics
         int rc = reserve(ctx, ctx->prof, 16 * sizeof(unsigned long long)); if (rc) return rc;
-        CUDA_TRY(ctx, cudaMemsetAsync(ctx->prof.ptr, 0, 16 * sizeof(unsigned long long), ctx->stream));
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->prof.ptr, 0, 16 * sizeof(unsigned long long), st));
         pr.prof = (unsigned long long*)ctx->prof.ptr;
     }
     pr.extra = extra;
     pr.seed = ctx->opt.seed;
+    {   // the reference's constants as options (solver.cuh: g_algo), written on the call's stream
+        const AlgoConst ac = {ctx->opt.tol, ctx->opt.it_count, ctx->opt.it_max_factor};
+        CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(g_algo, &ac, sizeof(ac), 0, cudaMemcpyHostToDevice, st));
+    }
 
     // unit schedules form their units from polynomials in order of decreasing degree
-    static const bool no_order = std::getenv("AMRVW_NO_ORDER") != nullptr;   // development knob: units in batch order
-    if (ctx->opt.schedule != AMRVW_SCHEDULE_REFERENCE && var != V_PENCIL_C && nbatch > 1 && !no_order) {
+    const bool unit_sched = ctx->opt.schedule != AMRVW_SCHEDULE_REFERENCE && var != V_PENCIL_C;
+    if (unit_sched && nbatch > 1) {
         int rc;
         if ((rc = reserve(ctx, ctx->order, (size_t)nbatch * sizeof(int)))) return rc;
         if ((rc = reserve(ctx, ctx->orderkeys, (size_t)nbatch * sizeof(unsigned long long)))) return rc;
         pr.order = (const int*)ctx->order.ptr;
     }
-    cudaStream_t st = ctx->stream;
     int launches = 0, lanes = 0;
     ctx->times = RoundsTimes{0.f, 0.f, 0.f, 0.f};
     ctx->prof_valid = (var != V_PENCIL_C && stats != nullptr);
+    ctx->queue_used = false;
     if (stats && !ctx->evpool[0]) for (cudaEvent_t& e : ctx->evpool) CUDA_TRY(ctx, cudaEventCreate(&e));
     if (stats) CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, st));
 
     bool done = false;
-    if constexpr (is_real<S>::value) {
-        if (var == V_RDS && ctx->opt.schedule != AMRVW_SCHEDULE_REFERENCE) {
-            // unit schedule: per-polynomial records, shifts, small-window queue, unit queue and parking
-            int rc;
-            if ((rc = reserve(ctx, ctx->rec, (size_t)nbatch * sizeof(PolyRec)))) return rc;
-            if ((rc = reserve(ctx, ctx->fatshifts, (size_t)nbatch * 256 * sizeof(Shifts)))) return rc;   // up to 256 bulges per fat step (chain.cuh)
-            if ((rc = reserve(ctx, ctx->swlist, ((size_t)total / 3 + (size_t)nbatch + 16) * sizeof(SmallWin)))) return rc;
-            if ((rc = reserve(ctx, ctx->counters, CNT_WORDS * sizeof(unsigned)))) return rc;
-            const size_t max_units = (size_t)nbatch;   // one per polynomial is the upper bound (L = 32)
-            size_t qcap = 1024;
-            while (qcap < 2 * max_units + 4096) qcap <<= 1;
-            if ((rc = reserve(ctx, ctx->queue, sizeof(RoundQueue)))) return rc;
-            if ((rc = reserve(ctx, ctx->qslots, qcap * sizeof(int)))) return rc;
-            if ((rc = reserve(ctx, ctx->park, max_units * sizeof(UnitPark)))) return rc;
-            if ((rc = reserve(ctx, ctx->parked, max_units * 32 * sizeof(StepState)))) return rc;
-            QueueBufs qb;
-            qb.q = (RoundQueue*)ctx->queue.ptr; qb.slots = (int*)ctx->qslots.ptr; qb.mask = (unsigned)(qcap - 1);
-            qb.park = (UnitPark*)ctx->park.ptr; qb.parked = (StepState*)ctx->parked.ptr;
-            pr.rec = (PolyRec*)ctx->rec.ptr; pr.shifts = (Shifts*)ctx->fatshifts.ptr; pr.swlist = ctx->swlist.ptr; pr.counters = (unsigned*)ctx->counters.ptr;
-            cudaError_t e = launch_rounds_rds(pr, ctx->opt, (int)max_len, (long long)total, ctx->sm_count, st, &launches, ctx->evpool, stats ? &ctx->times : nullptr, qb, &lanes, (unsigned long long*)ctx->orderkeys.ptr);
-            if (e != cudaSuccess) return fail(ctx, AMRVW_ERR_CUDA, std::string("unit schedule: ") + cudaGetErrorString(e));
-            done = true;
+    if (unit_sched) {
+        int L; PipeParams pp; size_t qcap = 0; int rc;
+        size_t lane_bytes;
+        if constexpr (is_real<S>::value) {
+            if (var == V_RDS) { choose_pipe_params(ctx->opt, nbatch, (int)max_len, ctx->sm_count, L, pp); lane_bytes = sizeof(StepState); }
+            else { choose_pencil_params(ctx->opt, nbatch, (int)max_len, ctx->sm_count, L, pp); lane_bytes = sizeof(PenLane); }
+        } else {
+            choose_css_params(ctx->opt, nbatch, (int)max_len, ctx->sm_count, L, pp); lane_bytes = sizeof(CssLane);
         }
-        if (var == V_PENCIL_R && ctx->opt.schedule != AMRVW_SCHEDULE_REFERENCE) {
-            // the same unit schedule with five chains per polynomial (pencil_units.cuh)
-            int rc;
-            if ((rc = reserve(ctx, ctx->rec, (size_t)nbatch * sizeof(PolyRec)))) return rc;
-            if ((rc = reserve(ctx, ctx->fatshifts, (size_t)nbatch * 32 * sizeof(Shifts)))) return rc;
-            if ((rc = reserve(ctx, ctx->swlist, ((size_t)total / 3 + (size_t)nbatch + 16) * sizeof(SmallWin)))) return rc;
-            if ((rc = reserve(ctx, ctx->counters, CNT_WORDS * sizeof(unsigned)))) return rc;
-            const size_t max_units = (size_t)nbatch;
-            size_t qcap = 1024;
-            while (qcap < 2 * max_units + 4096) qcap <<= 1;
-            if ((rc = reserve(ctx, ctx->queue, sizeof(RoundQueue)))) return rc;
-            if ((rc = reserve(ctx, ctx->qslots, qcap * sizeof(int)))) return rc;
-            if ((rc = reserve(ctx, ctx->park, max_units * sizeof(UnitPark)))) return rc;
-            if ((rc = reserve(ctx, ctx->parked, max_units * 32 * sizeof(PenLane)))) return rc;
-            QueueBufs qb;
-            qb.q = (RoundQueue*)ctx->queue.ptr; qb.slots = (int*)ctx->qslots.ptr; qb.mask = (unsigned)(qcap - 1);
-            qb.park = (UnitPark*)ctx->park.ptr; qb.parked = nullptr;
-            pr.rec = (PolyRec*)ctx->rec.ptr; pr.shifts = (Shifts*)ctx->fatshifts.ptr; pr.swlist = ctx->swlist.ptr; pr.counters = (unsigned*)ctx->counters.ptr;
-            cudaError_t e = launch_pencil_pipelined(pr, ctx->opt, (int)max_len, (long long)total, ctx->sm_count, st, &launches, qb, (PenLane*)ctx->parked.ptr, ctx->evpool, stats ? &ctx->times : nullptr, &lanes, (unsigned long long*)ctx->orderkeys.ptr);
-            if (e != cudaSuccess) return fail(ctx, AMRVW_ERR_CUDA, std::string("pencil unit schedule: ") + cudaGetErrorString(e));
-            done = true;
+        if ((rc = reserve_unit_workspace(ctx, nbatch, total, L, lane_bytes, &qcap))) return rc;
+        QueueBufs qb;
+        qb.q = (RoundQueue*)ctx->queue.ptr; qb.slots = (int*)ctx->qslots.ptr; qb.mask = qcap ? (unsigned)(qcap - 1) : 0u;
+        qb.park = (UnitPark*)ctx->park.ptr; qb.parked = nullptr;
+        pr.rec = (PolyRec*)ctx->rec.ptr; pr.shifts = (Shifts*)ctx->fatshifts.ptr; pr.swlist = ctx->swlist.ptr; pr.counters = (unsigned*)ctx->counters.ptr;
+        ctx->queue_used = qcap != 0;
+        cudaError_t e = cudaSuccess;
+        const char* what = "";
+        if constexpr (is_real<S>::value) {
+            if (var == V_RDS) {
+                what = "unit schedule: ";
+                qb.parked = (StepState*)ctx->parked.ptr;
+                e = launch_rounds_rds(pr, ctx->opt, (int)max_len, (long long)total, ctx->sm_count, st, &launches, ctx->evpool, stats ? &ctx->times : nullptr, qb, &lanes, (unsigned long long*)ctx->orderkeys.ptr);
+            } else {
+                what = "pencil unit schedule: ";
+                e = launch_pencil_pipelined(pr, ctx->opt, (int)max_len, (long long)total, ctx->sm_count, st, &launches, qb, (PenLane*)ctx->parked.ptr, ctx->evpool, stats ? &ctx->times : nullptr, &lanes, (unsigned long long*)ctx->orderkeys.ptr);
+            }
+        } else {
+            what = "complex unit schedule: ";
+            e = launch_css_pipelined(pr, ctx->opt, (int)max_len, (long long)total, ctx->sm_count, st, &launches, qb.q, qb.slots, qb.mask, qb.park, (CssLane*)ctx->parked.ptr,
+                                     ctx->evpool, stats ? &ctx->times : nullptr, &lanes, (unsigned long long*)ctx->orderkeys.ptr);
         }
-    }
-    if constexpr (!is_real<S>::value) {
-        if (var == V_CSS && ctx->opt.schedule != AMRVW_SCHEDULE_REFERENCE) {
-            int rc;
-            if ((rc = reserve(ctx, ctx->rec, (size_t)nbatch * sizeof(PolyRec)))) return rc;
-            if ((rc = reserve(ctx, ctx->fatshifts, (size_t)nbatch * 32 * sizeof(Shifts)))) return rc;
-            if ((rc = reserve(ctx, ctx->swlist, ((size_t)total / 3 + (size_t)nbatch + 16) * sizeof(SmallWin)))) return rc;
-            if ((rc = reserve(ctx, ctx->counters, CNT_WORDS * sizeof(unsigned)))) return rc;
-            const size_t max_units = (size_t)nbatch;
-            size_t qcap = 1024;
-            while (qcap < 2 * max_units + 4096) qcap <<= 1;
-            if ((rc = reserve(ctx, ctx->queue, sizeof(RoundQueue)))) return rc;
-            if ((rc = reserve(ctx, ctx->qslots, qcap * sizeof(int)))) return rc;
-            if ((rc = reserve(ctx, ctx->park, max_units * sizeof(UnitPark)))) return rc;
-            if ((rc = reserve(ctx, ctx->parked, max_units * 32 * sizeof(CssLane)))) return rc;
-            pr.rec = (PolyRec*)ctx->rec.ptr; pr.shifts = (Shifts*)ctx->fatshifts.ptr; pr.swlist = ctx->swlist.ptr; pr.counters = (unsigned*)ctx->counters.ptr;
-            cudaError_t e = launch_css_pipelined(pr, ctx->opt, (int)max_len, (long long)total, ctx->sm_count, st, &launches, (RoundQueue*)ctx->queue.ptr, (int*)ctx->qslots.ptr,
-                                                 (unsigned)(qcap - 1), (UnitPark*)ctx->park.ptr, (CssLane*)ctx->parked.ptr, ctx->evpool, stats ? &ctx->times : nullptr, &lanes, (unsigned long long*)ctx->orderkeys.ptr);
-            if (e != cudaSuccess) return fail(ctx, AMRVW_ERR_CUDA, std::string("complex unit schedule: ") + cudaGetErrorString(e));
-            done = true;
-        }
+        if (e != cudaSuccess) return fail(ctx, AMRVW_ERR_CUDA, std::string(what) + cudaGetErrorString(e));
+        done = true;
     }
     if (!done) {
         const int threads = 64;   // one polynomial per thread; small blocks spread the batch over all SMs
@@ -299,37 +370,43 @@ static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, cons
         stats->turnovers = h.turnovers; stats->sweeps = h.sweeps; stats->exceptional = h.exceptional;
         stats->unconverged = h.unconverged; stats->fat_steps = h.fat_steps;
         stats->launches = launches; stats->device_ms = ms; stats->lanes = lanes;
+        const int rc = check_queue_abort(ctx);     // the stream is idle here: one 4-byte read
+        if (rc) return rc;
     }
     return AMRVW_OK;
 }
 
-template <class S>
-static int run_host(amrvw_ctx* ctx, Variant var, const S* a, const S* w, const int64_t* offsets, int64_t nbatch,
-                    double* roots, int32_t* nroots, int32_t* nunconv, amrvw_stats* stats) {
-    if (!ctx) return AMRVW_ERR_ARGUMENT;
-    if (stats) std::memset(stats, 0, sizeof(*stats));
-    if (nbatch < 0) return fail(ctx, AMRVW_ERR_ARGUMENT, "negative batch");
-    if (nbatch == 0) return AMRVW_OK;
-    if (!offsets || !roots || !nroots || !nunconv) return fail(ctx, AMRVW_ERR_ARGUMENT, "null buffer");
-    const bool pencil = (var == V_PENCIL_R || var == V_PENCIL_C);
-    int64_t max_len = 0;
+// offsets checks shared by the host entry points; max_len out
+static int check_offsets(amrvw_ctx* ctx, const int64_t* offsets, int64_t nbatch, int64_t* max_len) {
+    if (offsets[0] != 0) return fail(ctx, AMRVW_ERR_ARGUMENT, "offsets[0] must be 0");
+    int64_t m = 0;
     for (int64_t p = 0; p < nbatch; ++p) {
         const int64_t len = offsets[p + 1] - offsets[p];
         if (len < 0) return fail(ctx, AMRVW_ERR_ARGUMENT, "offsets must be non-decreasing");
-        if (len > max_len) max_len = len;
+        if (len > 0x7fffff00) return fail(ctx, AMRVW_ERR_ARGUMENT, "polynomial too long");
+        if (len > m) m = len;
     }
-    if (offsets[0] != 0) return fail(ctx, AMRVW_ERR_ARGUMENT, "offsets[0] must be 0");
+    *max_len = m;
+    return AMRVW_OK;
+}
+
+// One device: H2D of the inputs, the kernels, D2H of the results (roots, or with counts3 != NULL only the
+// imag == 0 / > 0 / < 0 counts of real_polynomial_roots), all on the context's stream; returns when the
+// results are in the caller's buffers.
+template <class S>
+static int run_host_single(amrvw_ctx* ctx, Variant var, const S* a, const S* w, const int64_t* offsets, int64_t nbatch, int64_t max_len,
+                           double* roots, int32_t* nroots, int32_t* nunconv, int32_t* counts3, amrvw_stats* stats) {
+    const bool pencil = (var == V_PENCIL_R || var == V_PENCIL_C);
     const int64_t total = offsets[nbatch];
-    if (total > 0 && (!a || (pencil && !w))) return fail(ctx, AMRVW_ERR_ARGUMENT, "null coefficient buffer");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    const size_t root_slots = (size_t)total + 1;  // non-pencil uses total - nbatch of them
     int rc;
     if ((rc = reserve(ctx, ctx->coeffs, (size_t)total * sizeof(S) + 16))) return rc;
     if (pencil && (rc = reserve(ctx, ctx->coeffs2, (size_t)total * sizeof(S) + 16))) return rc;
     if ((rc = reserve(ctx, ctx->offsets, (size_t)(nbatch + 1) * sizeof(int64_t)))) return rc;
-    if ((rc = reserve(ctx, ctx->roots, root_slots * sizeof(cplx)))) return rc;
+    if ((rc = reserve(ctx, ctx->roots, ((size_t)total + 1) * sizeof(cplx)))) return rc;
     if ((rc = reserve(ctx, ctx->nroots, (size_t)nbatch * sizeof(int32_t)))) return rc;
     if ((rc = reserve(ctx, ctx->nunconv, (size_t)nbatch * sizeof(int32_t)))) return rc;
+    if (counts3 && (rc = reserve(ctx, ctx->counts, (size_t)nbatch * 3 * sizeof(int32_t)))) return rc;
     cudaStream_t st = ctx->stream;
     if (total > 0) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->coeffs.ptr, a, (size_t)total * sizeof(S), cudaMemcpyHostToDevice, st));
     if (pencil && total > 0) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->coeffs2.ptr, w, (size_t)total * sizeof(S), cudaMemcpyHostToDevice, st));
@@ -337,27 +414,119 @@ static int run_host(amrvw_ctx* ctx, Variant var, const S* a, const S* w, const i
     rc = run_dev<S>(ctx, var, (const S*)ctx->coeffs.ptr, pencil ? (const S*)ctx->coeffs2.ptr : nullptr, (const int64_t*)ctx->offsets.ptr, nbatch, total, max_len,
                     (double*)ctx->roots.ptr, (int32_t*)ctx->nroots.ptr, (int32_t*)ctx->nunconv.ptr, stats);
     if (rc) return rc;
-    const size_t out_slots = pencil ? (size_t)total : (size_t)(total - nbatch > 0 ? total - nbatch : 0);
-    if (out_slots > 0) CUDA_TRY(ctx, cudaMemcpyAsync(roots, ctx->roots.ptr, out_slots * sizeof(cplx), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(ctx, cudaMemcpyAsync(nroots, ctx->nroots.ptr, (size_t)nbatch * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (counts3) {
+        const int threads = 128;
+        count_real_roots_kernel<<<(int)((nbatch + threads - 1) / threads), threads, 0, st>>>((const cplx*)ctx->roots.ptr, (const long long*)ctx->offsets.ptr, nbatch, 0,
+                                                                                           (const int*)ctx->nroots.ptr, (int*)ctx->counts.ptr);
+        CUDA_TRY(ctx, cudaGetLastError());
+        CUDA_TRY(ctx, cudaMemcpyAsync(counts3, ctx->counts.ptr, (size_t)nbatch * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    } else if (total > 0) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(roots, ctx->roots.ptr, (size_t)total * sizeof(cplx), cudaMemcpyDeviceToHost, st));
+    }
+    if (nroots) CUDA_TRY(ctx, cudaMemcpyAsync(nroots, ctx->nroots.ptr, (size_t)nbatch * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(nunconv, ctx->nunconv.ptr, (size_t)nbatch * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return check_queue_abort(ctx);
+}
+
+// Several devices (amrvw_create_multi): contiguous split of the batch by polynomial, balanced by the sum of
+// squared lengths (the work of a polynomial grows like n^2); one host thread per device drives that device's
+// own context and stream (H2D slice -> kernels -> D2H slice straight into the caller's buffers, so the
+// "gather" is the D2H copies themselves); per-device errors fold into one status.  SURVEY.md 8(e): no
+// collective, polynomials never interact.
+static void partition_batch(const int64_t* offsets, int64_t nbatch, int ndev, std::vector<int64_t>& cut) {
+    cut.assign((size_t)ndev + 1, nbatch);
+    cut[0] = 0;
+    double tot = 0.0;
+    for (int64_t p = 0; p < nbatch; ++p) { const double len = (double)(offsets[p + 1] - offsets[p]); tot += len * len + 64.0; }
+    double acc = 0.0;
+    int d = 1;
+    for (int64_t p = 0; p < nbatch && d < ndev; ++p) {
+        const double len = (double)(offsets[p + 1] - offsets[p]);
+        acc += len * len + 64.0;
+        while (d < ndev && acc >= tot * (double)d / (double)ndev) cut[(size_t)d++] = p + 1;
+    }
+}
+
+template <class S>
+static int run_host(amrvw_ctx* ctx, Variant var, const S* a, const S* w, const int64_t* offsets, int64_t nbatch,
+                    double* roots, int32_t* nroots, int32_t* nunconv, int32_t* counts3, amrvw_stats* stats) {
+    if (!ctx) return AMRVW_ERR_ARGUMENT;
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    if (nbatch < 0) return fail(ctx, AMRVW_ERR_ARGUMENT, "negative batch");
+    if (nbatch == 0) return AMRVW_OK;
+    if (!offsets || (!roots && !counts3) || (!nroots && !counts3) || !nunconv) return fail(ctx, AMRVW_ERR_ARGUMENT, "null buffer");
+    const bool pencil = (var == V_PENCIL_R || var == V_PENCIL_C);
+    int64_t max_len = 0;
+    int rc = check_offsets(ctx, offsets, nbatch, &max_len);
+    if (rc) return rc;
+    const int64_t total = offsets[nbatch];
+    if (total > 0 && (!a || (pencil && !w))) return fail(ctx, AMRVW_ERR_ARGUMENT, "null coefficient buffer");
+    if (ctx->subs.empty()) return run_host_single<S>(ctx, var, a, w, offsets, nbatch, max_len, roots, nroots, nunconv, counts3, stats);
+
+    const int ndev = (int)ctx->subs.size();
+    std::vector<int64_t> cut;
+    partition_batch(offsets, nbatch, ndev, cut);
+    std::vector<int> rcs((size_t)ndev, AMRVW_OK);
+    std::vector<amrvw_stats> sts((size_t)ndev);
+    std::vector<std::thread> workers;
+    for (int d = 0; d < ndev; ++d) {
+        const int64_t p0 = cut[(size_t)d], p1 = cut[(size_t)d + 1];
+        if (p1 <= p0) continue;
+        workers.emplace_back([&, d, p0, p1]() {
+            amrvw_ctx* sub = ctx->subs[(size_t)d];
+            const int64_t base = offsets[p0], nb = p1 - p0;
+            std::vector<int64_t> loc((size_t)nb + 1);
+            int64_t ml = 0;
+            for (int64_t i = 0; i <= nb; ++i) loc[(size_t)i] = offsets[p0 + i] - base;
+            for (int64_t i = 0; i < nb; ++i) ml = std::max(ml, loc[(size_t)i + 1] - loc[(size_t)i]);
+            rcs[(size_t)d] = run_host_single<S>(sub, var, a ? a + base : nullptr, (pencil && w) ? w + base : nullptr, loc.data(), nb, ml,
+                                                roots ? roots + 2 * base : nullptr, nroots ? nroots + p0 : nullptr, nunconv + p0,
+                                                counts3 ? counts3 + 3 * p0 : nullptr, stats ? &sts[(size_t)d] : nullptr);
+        });
+    }
+    for (std::thread& t : workers) t.join();
+    for (int d = 0; d < ndev; ++d)
+        if (rcs[(size_t)d] != AMRVW_OK) return fail(ctx, rcs[(size_t)d], "device " + std::to_string(ctx->subs[(size_t)d]->device) + ": " + ctx->subs[(size_t)d]->err);
+    if (stats) {
+        for (int d = 0; d < ndev; ++d) {
+            const amrvw_stats& x = sts[(size_t)d];
+            stats->turnovers += x.turnovers; stats->sweeps += x.sweeps; stats->exceptional += x.exceptional; stats->unconverged += x.unconverged;
+            stats->fat_steps += x.fat_steps; stats->launches += x.launches;
+            if (x.device_ms > stats->device_ms) stats->device_ms = x.device_ms;    // the devices run side by side
+            if (x.lanes > stats->lanes) stats->lanes = x.lanes;
+        }
+    }
     return AMRVW_OK;
 }
 
 extern "C" {
 
 int amrvw_roots_rds_f64(amrvw_ctx* ctx, const double* coeffs, const int64_t* offsets, int64_t nbatch, double* roots, int32_t* nroots, int32_t* nunconv, amrvw_stats* stats) {
-    return run_host<double>(ctx, V_RDS, coeffs, nullptr, offsets, nbatch, roots, nroots, nunconv, stats);
+    return run_host<double>(ctx, V_RDS, coeffs, nullptr, offsets, nbatch, roots, nroots, nunconv, nullptr, stats);
 }
 int amrvw_roots_css_c64(amrvw_ctx* ctx, const double* coeffs, const int64_t* offsets, int64_t nbatch, double* roots, int32_t* nroots, int32_t* nunconv, amrvw_stats* stats) {
-    return run_host<cplx>(ctx, V_CSS, (const cplx*)coeffs, nullptr, offsets, nbatch, roots, nroots, nunconv, stats);
+    return run_host<cplx>(ctx, V_CSS, (const cplx*)coeffs, nullptr, offsets, nbatch, roots, nroots, nunconv, nullptr, stats);
 }
 int amrvw_roots_pencil_f64(amrvw_ctx* ctx, const double* vs, const double* ws, const int64_t* offsets, int64_t nbatch, double* roots, int32_t* nroots, int32_t* nunconv, amrvw_stats* stats) {
-    return run_host<double>(ctx, V_PENCIL_R, vs, ws, offsets, nbatch, roots, nroots, nunconv, stats);
+    return run_host<double>(ctx, V_PENCIL_R, vs, ws, offsets, nbatch, roots, nroots, nunconv, nullptr, stats);
 }
 int amrvw_roots_pencil_c64(amrvw_ctx* ctx, const double* vs, const double* ws, const int64_t* offsets, int64_t nbatch, double* roots, int32_t* nroots, int32_t* nunconv, amrvw_stats* stats) {
-    return run_host<cplx>(ctx, V_PENCIL_C, (const cplx*)vs, (const cplx*)ws, offsets, nbatch, roots, nroots, nunconv, stats);
+    return run_host<cplx>(ctx, V_PENCIL_C, (const cplx*)vs, (const cplx*)ws, offsets, nbatch, roots, nroots, nunconv, nullptr, stats);
+}
+
+int amrvw_partition_batch(const int64_t* offsets, int64_t nbatch, int ndev, int64_t* cuts) {
+    if (!offsets || !cuts || nbatch < 0 || ndev < 1) return AMRVW_ERR_ARGUMENT;
+    for (int64_t p = 0; p < nbatch; ++p) if (offsets[p + 1] < offsets[p]) return AMRVW_ERR_ARGUMENT;
+    std::vector<int64_t> cut;
+    partition_batch(offsets, nbatch, ndev, cut);
+    for (int d = 0; d <= ndev; ++d) cuts[d] = cut[(size_t)d];
+    return AMRVW_OK;
+}
+
+int amrvw_count_real_roots_rds_f64(amrvw_ctx* ctx, const double* coeffs, const int64_t* offsets, int64_t nbatch, int32_t* counts3, int32_t* nunconv, amrvw_stats* stats) {
+    if (!counts3) return fail(ctx, AMRVW_ERR_ARGUMENT, "null counts buffer");
+    return run_host<double>(ctx, V_RDS, coeffs, nullptr, offsets, nbatch, nullptr, nullptr, nunconv, counts3, stats);
 }
 
 int amrvw_roots_rds_f64_dev(amrvw_ctx* ctx, const double* a, const int64_t* off, int64_t nb, int64_t total, int64_t max_len, double* r, int32_t* nr, int32_t* nu, amrvw_stats* stats) {
@@ -374,6 +543,7 @@ int amrvw_roots_pencil_c64_dev(amrvw_ctx* ctx, const double* v, const double* w,
 }
 
 int amrvw_count_real_roots_dev(amrvw_ctx* ctx, const double* d_roots, const int64_t* d_offsets, int64_t nbatch, int32_t shift, const int32_t* d_nroots, int32_t* d_counts3) {
+    ctx = primary(ctx);
     if (!ctx) return AMRVW_ERR_ARGUMENT;
     if (nbatch <= 0) return AMRVW_OK;
     if (!d_roots || !d_offsets || !d_nroots || !d_counts3) return fail(ctx, AMRVW_ERR_ARGUMENT, "null buffer");
@@ -385,6 +555,7 @@ int amrvw_count_real_roots_dev(amrvw_ctx* ctx, const double* d_roots, const int6
 }
 
 int amrvw_last_profile(amrvw_ctx* ctx, int64_t* out16) {
+    ctx = primary(ctx);
     if (!ctx || !out16) return AMRVW_ERR_ARGUMENT;
     std::memset(out16, 0, 16 * sizeof(int64_t));
     if (ctx->prof.ptr && ctx->prof_valid) {
@@ -399,6 +570,7 @@ int amrvw_last_profile(amrvw_ctx* ctx, int64_t* out16) {
 }
 
 int amrvw_selftest(amrvw_ctx* ctx, int64_t n, double* out4) {
+    ctx = primary(ctx);
     if (!ctx || !out4 || n <= 0) return AMRVW_ERR_ARGUMENT;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     int rc = reserve(ctx, ctx->state, 4 * sizeof(double));
@@ -413,6 +585,7 @@ int amrvw_selftest(amrvw_ctx* ctx, int64_t n, double* out4) {
 }
 
 int amrvw_selftest_complex(amrvw_ctx* ctx, int64_t n, double* out4) {
+    ctx = primary(ctx);
     if (!ctx || !out4 || n <= 0) return AMRVW_ERR_ARGUMENT;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     int rc = reserve(ctx, ctx->state, 4 * sizeof(double));
@@ -427,6 +600,7 @@ int amrvw_selftest_complex(amrvw_ctx* ctx, int64_t n, double* out4) {
 }
 
 int amrvw_selftest_robust(amrvw_ctx* ctx, int64_t n, double* out4) {
+    ctx = primary(ctx);
     if (!ctx || !out4 || n <= 0) return AMRVW_ERR_ARGUMENT;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     int rc = reserve(ctx, ctx->state, 4 * sizeof(double));
@@ -441,6 +615,7 @@ int amrvw_selftest_robust(amrvw_ctx* ctx, int64_t n, double* out4) {
 }
 
 int amrvw_measure_fp64_peak(amrvw_ctx* ctx, double* tflops) {
+    ctx = primary(ctx);
     if (!ctx || !tflops) return AMRVW_ERR_ARGUMENT;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const int blocks = ctx->sm_count * 8, threads = 256, iters = 4096;

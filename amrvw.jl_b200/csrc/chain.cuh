@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(32 * NW) chain_kernel(Problem<double> pr, Pipe
                 rec.ls.sp = sp;
                 rec.st.sweeps += nb;
                 rec.chase_turnovers += (long long)sm.nturn;
-                if (mode == 2) { rec.st.exceptional += nb; rec.ls.ord += nb; rec.ls.ctr.it_count = 14; }
+                if (mode == 2) { rec.st.exceptional += nb; rec.ls.ord += nb; rec.ls.ctr.it_count = AMRVW_IT_COUNT - 1; }
                 store_rec(rw, rec);
             }
             __syncthreads();

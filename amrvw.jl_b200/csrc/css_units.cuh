@@ -25,7 +25,10 @@
 //     state in registers.
 //
 // Roots agree with the reference schedule to backward-error level (tests: minimum-distance matching
-// against the oracle); there is no bit-level twin of this schedule in the oracle yet.
+// against the oracle).  The oracle holds a sequential twin of this schedule (amrvw_algorithm_ms_c: same fat
+// steps, dense block + complex Hessenberg QR, the reference's phase push-down); hypot, complex division and
+// complex sqrt come from different math libraries on the two sides, so the no-FMA build is held to it at a
+// tight tolerance and to the same fat-step and turnover counts within 2 %, not bit for bit.
 #pragma once
 #include "rounds.cuh"
 
@@ -262,7 +265,7 @@ AMRVW_DI void css_check_deflation_stack(Fact<cplx, false>& F, LeaderState& ls, c
             css_deflate_cg(F, k);
             ls.ctr.zero_index = k;
             ls.ctr.start_index = k + 1;
-            ls.ctr.it_count = 15;
+            ls.ctr.it_count = AMRVW_IT_COUNT;
         }
     }
 }
@@ -272,7 +275,7 @@ AMRVW_NI int css_unit_driver(const Problem<cplx>& pr, const PipeParams pp, const
     PolyRec rec = load_rec(pr.rec + p);
     if (!rec.iterating) return 0;
     Fact<cplx, false> F = make_fact<cplx, false>(pr, p, rec.N);
-    cplx* E = pr.roots + (pr.offsets[p] - p) - 1;
+    cplx* E = pr.roots + pr.offsets[p] - 1;
     const int* dstack = pr.dstack + (pr.offsets[p] + (long long)pr.extra * p);
     SmallSink sink;
     sink.list = pr.swlist; sink.count = pr.counters + CNT_SMALL; sink.poly = (int)p;
@@ -310,7 +313,7 @@ AMRVW_NI int css_unit_driver(const Problem<cplx>& pr, const PipeParams pp, const
             sink.push(lo2, hi2, ctr.it_count);
             if (lo2 == 2) { css_diagonal_block_cg(F, 1, A); E[1] = A[0]; }
             pop_window(ls);
-            ctr.stop_index = lo2 - 2; ctr.zero_index = 0; ctr.start_index = 1; ctr.it_count = 15;
+            ctr.stop_index = lo2 - 2; ctr.zero_index = 0; ctr.start_index = 1; ctr.it_count = AMRVW_IT_COUNT;
             if (ctr.stop_index >= 1) css_check_deflation_stack(F, ls, dstack);
             ls.pn_small += 1;
         } else if (ctr.it_count == 0) {
@@ -488,9 +491,9 @@ AMRVW_NI void css_unit_shifts(const Problem<cplx>& pr, const PipeParams pp, cons
             deflate(W, k0);                       // the phase of Q[k0] goes down the copy's Q chain
             cplx* Es = ws.e - (k0 + 1);
             for (int t = 0; t <= m; ++t) ws.e[t] = cplx(0.0, 0.0);
-            Counter c2 = {k0, k0 + 1, stop, 15, -1};
+            Counter c2 = {k0, k0 + 1, stop, AMRVW_IT_COUNT, -1};
             PolyStats sub = {0, 0, 0, 0, 0};
-            drive_window(W, k0 + 1, stop, c2, Es, 20ll * (m + 1), pr.seed, (uint64_t)p, rec.ls.ord, sub, ReferenceStep());
+            drive_window(W, k0 + 1, stop, c2, Es, AMRVW_IT_MAX(m + 1), pr.seed, (uint64_t)p, rec.ls.ord, sub, ReferenceStep());
             rec.serial_turnovers += W.turnovers;
         }
         Shifts* shl = pr.shifts + p * L;
@@ -524,15 +527,7 @@ __global__ void __launch_bounds__(32, AMRVW_CSS_MINBLOCKS) css_unit_kernel(Probl
         const long long pc_p0 = clock64();
         int u = -1;
         if (lane32 == 0) {
-            const unsigned k = atomicAdd(&q->head, 1u);
-            int* slot = slots + (k & mask);
-            for (unsigned spins = 0;; ++spins) {
-                u = atomicExch(slot, -1);
-                if (u >= 0) break;
-                if (*reinterpret_cast<volatile unsigned*>(&q->remaining) == 0u) { u = -2; break; }
-                if (spins > (1u << 24)) { u = -3; break; }
-                __nanosleep(500);
-            }
+            u = queue_pop(q, slots, mask, pr.counters);
         }
         u = __shfl_sync(0xffffffffu, u, 0);
         if (u < 0) break;
@@ -674,7 +669,7 @@ __global__ void __launch_bounds__(32, AMRVW_CSS_MINBLOCKS) css_unit_kernel(Probl
                 rec.ls.sp = sp;
                 rec.st.sweeps += nb;
                 rec.chase_turnovers += nturn + __ldcg(&up->nturn[grp]);
-                if (mode == 2) { rec.st.exceptional += nb; rec.ls.ord += nb; rec.ls.ctr.it_count = 14; }
+                if (mode == 2) { rec.st.exceptional += nb; rec.ls.ord += nb; rec.ls.ctr.it_count = AMRVW_IT_COUNT - 1; }
                 store_rec(r, rec);
             }
             if (lane32 == 0) __stcg(&up->t, -1);
@@ -704,13 +699,13 @@ __global__ void __launch_bounds__(64) css_setup_kernel(Problem<cplx> pr) {
     if (p >= pr.nbatch) return;
     PolyRec rec;
     rec.ls.kk = 0; rec.ls.it_max = 0; rec.ls.ord = 0; rec.ls.unconv = 0; rec.ls.sp = 0; rec.ls.pc_sub = 0; rec.ls.pc_small = 0; rec.ls.pn_small = 0;
-    rec.ls.ctr = {0, 1, 0, 15, -1};
+    rec.ls.ctr = {0, 1, 0, AMRVW_IT_COUNT, -1};
     rec.st = {0, 0, 0, 0, 0};
     rec.serial_turnovers = 0; rec.chase_turnovers = 0;
     rec.N = 0; rec.K = 0; rec.mode = 0; rec.nb = 0; rec.iterating = 0; rec.pad = 0;
     const long long off = pr.offsets[p];
     const int len = (int)(pr.offsets[p + 1] - off);
-    cplx* out = pr.roots + (off - p);
+    cplx* out = pr.roots + off;
     int first, last;
     trim_zeros(pr.coeffs + off, len, first, last);
     if (first < 0) {
@@ -728,8 +723,8 @@ __global__ void __launch_bounds__(64) css_setup_kernel(Problem<cplx> pr) {
             factor_companion(F, ps);
             for (int i = 0; i < N; ++i) out[i] = cplx(0.0, 0.0);
             rec.N = N;
-            rec.ls.ctr = {0, 1, N - 1, 15, -1};
-            rec.ls.it_max = 20ll * (N - 1);
+            rec.ls.ctr = {0, 1, N - 1, AMRVW_IT_COUNT, -1};
+            rec.ls.it_max = AMRVW_IT_MAX(N - 1);
             rec.iterating = 1;
         }
     }
@@ -744,11 +739,11 @@ __global__ void __launch_bounds__(64) css_small_kernel(Problem<cplx> pr) {
     const long long p = sw.poly;
     PolyRec* rw = pr.rec + p;
     Fact<cplx, false> F = make_fact<cplx, false>(pr, p, rw->N);
-    cplx* E = pr.roots + (pr.offsets[p] - p) - 1;
+    cplx* E = pr.roots + pr.offsets[p] - 1;
     Counter c2 = {sw.lo - 1, sw.lo, sw.hi, sw.it_count, -1};
     PolyStats st = {0, 0, 0, 0, 0};
     int ord = 1000000 + sw.lo;
-    const int left = drive_window(F, sw.lo, sw.hi, c2, E, 20ll * (rw->N - 1), pr.seed, (uint64_t)p, ord, st, ReferenceStep());
+    const int left = drive_window(F, sw.lo, sw.hi, c2, E, AMRVW_IT_MAX(rw->N - 1), pr.seed, (uint64_t)p, ord, st, ReferenceStep());
     atomicAdd((unsigned long long*)&rw->serial_turnovers, (unsigned long long)F.turnovers);
     atomicAdd(&rw->st.sweeps, st.sweeps);
     if (st.exceptional) atomicAdd(&rw->st.exceptional, st.exceptional);
@@ -773,21 +768,17 @@ static cudaError_t launch_css_units(const Problem<cplx>& pr, const PipeParams& p
     return cudaGetLastError();
 }
 
-static cudaError_t launch_css_pipelined(Problem<cplx> pr, const amrvw_options& opt, int max_len, long long total, int sm_count, cudaStream_t st, int* launches,
-                                        RoundQueue* q, int* slots, unsigned mask, UnitPark* park, CssLane* parked, cudaEvent_t* ev = nullptr, RoundsTimes* times = nullptr,
-                                        int* lanes_out = nullptr, unsigned long long* order_keys = nullptr) {
+// lanes per polynomial and the rest of the schedule's parameters for a batch (also sizes the workspace: capi.cu)
+static void choose_css_params(const amrvw_options& opt, long long nbatch, int max_len, int sm_count, int& L, PipeParams& pp) {
     const int degree = max_len - 1;
-    const long long nbatch_hint = pr.nbatch;
-    int L = opt.lanes_per_poly;
+    L = opt.lanes_per_poly;
     if (L == 0) {
         L = degree < 64 ? 4 : (degree < 256 ? 8 : 16);
         // batches that leave warps free get 32 bulges per polynomial (gpurun_out/sweep80.log, sweep75.log: 64 x degree
         // 3000 944 -> 551 ms, 1000 x 1000 155 -> 121 ms; 2000 x 1000 181 ms with 16 lanes against 199 with 32)
-        if (degree >= 256 && nbatch_hint <= (long long)sm_count * 8) L = 32;
+        if (degree >= 256 && nbatch <= (long long)sm_count * 8) L = 32;
     }
     if (L > 32) L = 32;      // chained warps exist for the real rank-one path only
-    if (lanes_out) *lanes_out = L;
-    PipeParams pp;
     // bulges per shift: the trailing block has order L / reuse.  With the core-chasing sub-solve on ONE lane the
     // shifts were 40-49% of the busy warp-cycles at reuse 1, L = 16 (config 3: reuse 1 530 ms, 2 336 ms, 4 316 ms:
     // gpurun_out/sweep62.log); with the dense block + lane-shared complex Hessenberg QR: reuse 1 201 ms (phase A
@@ -798,6 +789,14 @@ static cudaError_t launch_css_pipelined(Problem<cplx> pr, const amrvw_options& o
     if (pp.small < L) pp.small = L;
     if (pp.small > 96) pp.small = 96;
     pp.ms = pp.small + 4; pp.dense = opt.shift_solver != AMRVW_SHIFTS_CHASE; pp.mh = L;
+}
+
+static cudaError_t launch_css_pipelined(Problem<cplx> pr, const amrvw_options& opt, int max_len, long long total, int sm_count, cudaStream_t st, int* launches,
+                                        RoundQueue* q, int* slots, unsigned mask, UnitPark* park, CssLane* parked, cudaEvent_t* ev = nullptr, RoundsTimes* times = nullptr,
+                                        int* lanes_out = nullptr, unsigned long long* order_keys = nullptr) {
+    int L; PipeParams pp;
+    choose_css_params(opt, pr.nbatch, max_len, sm_count, L, pp);
+    if (lanes_out) *lanes_out = L;
     cudaError_t e;
     if ((e = cudaMemsetAsync(pr.counters, 0, CNT_WORDS * sizeof(unsigned), st)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(q, 0, sizeof(RoundQueue), st)) != cudaSuccess) return e;
@@ -811,8 +810,7 @@ static cudaError_t launch_css_pipelined(Problem<cplx> pr, const amrvw_options& o
         *launches += 1;
     }
     if (times) cudaEventRecord(ev[1], st);
-    static const int seg_env = std::getenv("AMRVW_SEG_STEPS") ? std::atoi(std::getenv("AMRVW_SEG_STEPS")) : 0;   // development knob
-    const int seg_steps = seg_env > 0 ? seg_env : 256;
+    const int seg_steps = 256;
     switch (L) {
         case 4: e = launch_css_units<4, 8>(pr, pp, q, slots, mask, park, parked, seg_steps, sm_count, st); break;
         case 8: e = launch_css_units<8, 8>(pr, pp, q, slots, mask, park, parked, seg_steps, sm_count, st); break;

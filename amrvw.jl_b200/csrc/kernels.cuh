@@ -13,7 +13,7 @@ template <class S> struct Problem {
     const S* ws;              // pencil only
     const long long* offsets; // nbatch+1, CSR
     long long nbatch;
-    cplx* roots;              // complex slots; polynomial p at offsets[p] - p (non-pencil) / offsets[p] (pencil)
+    cplx* roots;              // complex slots; polynomial p at offsets[p] (one slot per input entry: empty vectors cannot overlap anything)
     int* nroots;
     int* nunconv;
     PolyStats* stats;         // nullable
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(64) roots_reference_kernel(Problem<S> pr) {
     if (p >= pr.nbatch) return;
     const long long off = pr.offsets[p];
     const int len = (int)(pr.offsets[p + 1] - off);
-    cplx* out = pr.roots + (off - p);
+    cplx* out = pr.roots + off;
     PolyStats st = {0, 0, 0, 0, 0};
     int first, last;
     trim_zeros(pr.coeffs + off, len, first, last);
@@ -95,9 +95,9 @@ __global__ void __launch_bounds__(64) roots_reference_kernel(Problem<S> pr) {
     Fact<S, false> F = make_fact<S, false>(pr, p, N);
     factor_companion(F, ps);
     for (int i = 0; i < N; ++i) out[i] = cplx(0.0, 0.0);   // EIGS = zeros (AMRVW_algorithm.jl:23)
-    Counter ctr = {0, 1, N - 1, 15, N - 2};                 // AMRVW_algorithm.jl:18
+    Counter ctr = {0, 1, N - 1, AMRVW_IT_COUNT, N - 2};                 // AMRVW_algorithm.jl:18
     int ord = 0;
-    const int unconv = drive_window(F, 1, N - 1, ctr, out - 1, 20ll * (N - 1), pr.seed, (unsigned long long)p, ord, st, ReferenceStep());
+    const int unconv = drive_window(F, 1, N - 1, ctr, out - 1, AMRVW_IT_MAX(N - 1), pr.seed, (unsigned long long)p, ord, st, ReferenceStep());
     sort_roots(out, N);
     st.turnovers = F.turnovers;
     st.unconverged = unconv;
@@ -192,9 +192,9 @@ __global__ void __launch_bounds__(64) roots_pencil_reference_kernel(Problem<S> p
     int Kz = 0;
     const int n = pencil_prepare(pr, p, out, st, F, Kz);
     if (n == 0) return;
-    Counter ctr = {0, 1, n - 1, 15, n - 2};
+    Counter ctr = {0, 1, n - 1, AMRVW_IT_COUNT, n - 2};
     int ord = 0;
-    const int unconv = drive_window(F, 1, n - 1, ctr, out - 1, 20ll * (n - 1), pr.seed, (unsigned long long)p, ord, st, ReferenceStep());
+    const int unconv = drive_window(F, 1, n - 1, ctr, out - 1, AMRVW_IT_MAX(n - 1), pr.seed, (unsigned long long)p, ord, st, ReferenceStep());
     sort_roots(out, n);
     st.turnovers = F.turnovers;
     st.unconverged = unconv;

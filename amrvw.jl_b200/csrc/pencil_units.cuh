@@ -112,7 +112,7 @@ AMRVW_NI void pen_create(PenLane& z, const Fact<double, true>& F, const int star
         Rot<double> lwb[4] = {wm.wb, z.w0.wb, z.w1.wb, z.w2.wb}, lwc[4] = {wm.wc, z.w0.wc, z.w1.wc, z.w2.wc};
         Fact<double, true> Fl = F;
         Fl.Q = lq - (start - 1); Fl.B = lb - (start - 1); Fl.Ct = lc - (start - 1); Fl.WB = lwb - (start - 1); Fl.WCt = lwc - (start - 1);
-        Counter cl = {start - 1, start, stop, 15, -1};
+        Counter cl = {start - 1, start, stop, AMRVW_IT_COUNT, -1};
         int dummy = 0;
         PolyStats ds = {0, 0, 0, 0, 0};
         create_bulge_rds(Fl, cl, U, V, &sh, seed, poly, dummy, ds);
@@ -150,7 +150,7 @@ AMRVW_DI void pen_check_deflation_stack(Fact<double, true>& F, LeaderState& ls, 
             F.Q[k] = make_rot<double>(sign_(ldcg_rot(F.Q + k).c), 0.0);   // deflate (RDS.jl:134-141)
             ls.ctr.zero_index = k;
             ls.ctr.start_index = k + 1;
-            ls.ctr.it_count = 15;
+            ls.ctr.it_count = AMRVW_IT_COUNT;
         }
     }
 }
@@ -199,7 +199,7 @@ AMRVW_NI int pen_unit_driver(const Problem<double>& pr, const PipeParams pp, con
             sink.push(lo2, hi2, ctr.it_count);
             if (lo2 == 2) { pen_diagonal_block_cg(F, 1, A); E[1] = to_c(A[0]); }
             pop_window(ls);
-            ctr.stop_index = lo2 - 2; ctr.zero_index = 0; ctr.start_index = 1; ctr.it_count = 15;
+            ctr.stop_index = lo2 - 2; ctr.zero_index = 0; ctr.start_index = 1; ctr.it_count = AMRVW_IT_COUNT;
             if (ctr.stop_index >= 1) pen_check_deflation_stack(F, ls, dstack);
             ls.pn_small += 1;
         } else if (ctr.it_count == 0) {
@@ -320,9 +320,9 @@ AMRVW_NI void pen_unit_shifts(const Problem<double>& pr, const PipeParams pp, co
             W.Q = ws.q - k0; W.B = ws.b - k0; W.Ct = ws.c - k0; W.WB = ws.wb - k0; W.WCt = ws.wc - k0; W.turnovers = 0;
             cplx* Es = ws.e - (k0 + 1);
             for (int t = 0; t <= m; ++t) ws.e[t] = cplx(0.0, 0.0);
-            Counter c2 = {k0, k0 + 1, stop, 15, -1};
+            Counter c2 = {k0, k0 + 1, stop, AMRVW_IT_COUNT, -1};
             PolyStats sub = {0, 0, 0, 0, 0};
-            drive_window(W, k0 + 1, stop, c2, Es, 20ll * (m + 1), pr.seed, (uint64_t)p, rec.ls.ord, sub, ReferenceStep());
+            drive_window(W, k0 + 1, stop, c2, Es, AMRVW_IT_MAX(m + 1), pr.seed, (uint64_t)p, rec.ls.ord, sub, ReferenceStep());
             rec.serial_turnovers += W.turnovers;
         }
         rec.nb = pair_shifts(ws.e, m, pr.shifts + p * L, L, pp.reuse);
@@ -350,15 +350,7 @@ __global__ void __launch_bounds__(32, 8) pen_unit_kernel(Problem<double> pr, Pip
         const long long pc_p0 = clock64();
         int u = -1;
         if (lane32 == 0) {
-            const unsigned k = atomicAdd(&q->head, 1u);
-            int* slot = slots + (k & mask);
-            for (unsigned spins = 0;; ++spins) {
-                u = atomicExch(slot, -1);
-                if (u >= 0) break;
-                if (*reinterpret_cast<volatile unsigned*>(&q->remaining) == 0u) { u = -2; break; }
-                if (spins > (1u << 24)) { u = -3; break; }
-                __nanosleep(500);
-            }
+            u = queue_pop(q, slots, mask, pr.counters);
         }
         u = __shfl_sync(0xffffffffu, u, 0);
         if (u < 0) break;
@@ -481,7 +473,7 @@ __global__ void __launch_bounds__(32, 8) pen_unit_kernel(Problem<double> pr, Pip
                 rec.ls.sp = sp;
                 rec.st.sweeps += nb;
                 rec.chase_turnovers += nturn + __ldcg(&up->nturn[grp]);
-                if (mode == 2) { rec.st.exceptional += nb; rec.ls.ord += nb; rec.ls.ctr.it_count = 14; }
+                if (mode == 2) { rec.st.exceptional += nb; rec.ls.ord += nb; rec.ls.ctr.it_count = AMRVW_IT_COUNT - 1; }
                 store_rec(r, rec);
             }
             if (lane32 == 0) __stcg(&up->t, -1);
@@ -511,7 +503,7 @@ __global__ void __launch_bounds__(64) pen_setup_kernel(Problem<double> pr) {
     if (p >= pr.nbatch) return;
     PolyRec rec;
     rec.ls.kk = 0; rec.ls.it_max = 0; rec.ls.ord = 0; rec.ls.unconv = 0; rec.ls.sp = 0; rec.ls.pc_sub = 0; rec.ls.pc_small = 0; rec.ls.pn_small = 0;
-    rec.ls.ctr = {0, 1, 0, 15, -1};
+    rec.ls.ctr = {0, 1, 0, AMRVW_IT_COUNT, -1};
     rec.st = {0, 0, 0, 0, 0};
     rec.serial_turnovers = 0; rec.chase_turnovers = 0;
     rec.N = 0; rec.K = 0; rec.mode = 0; rec.nb = 0; rec.iterating = 0; rec.pad = 0;
@@ -521,8 +513,8 @@ __global__ void __launch_bounds__(64) pen_setup_kernel(Problem<double> pr) {
     const int n = pencil_prepare(pr, p, out, rec.st, F, Kz);   // trimming, closed forms, factorization (kernels.cuh)
     if (n > 0) {
         rec.N = n; rec.K = Kz;
-        rec.ls.ctr = {0, 1, n - 1, 15, -1};
-        rec.ls.it_max = 20ll * (n - 1);
+        rec.ls.ctr = {0, 1, n - 1, AMRVW_IT_COUNT, -1};
+        rec.ls.it_max = AMRVW_IT_MAX(n - 1);
         rec.iterating = 1;
     }
     pr.rec[p] = rec;
@@ -551,7 +543,7 @@ __global__ void __launch_bounds__(64) pen_small_kernel(Problem<double> pr) {
     Counter c2 = {sw.lo - 1, sw.lo, sw.hi, sw.it_count, -1};
     PolyStats st = {0, 0, 0, 0, 0};
     int ord = 1000000 + sw.lo;
-    const int left = drive_window(W, sw.lo, sw.hi, c2, E, 20ll * (rw->N - 1), pr.seed, (uint64_t)p, ord, st, ReferenceStep());
+    const int left = drive_window(W, sw.lo, sw.hi, c2, E, AMRVW_IT_MAX(rw->N - 1), pr.seed, (uint64_t)p, ord, st, ReferenceStep());
     atomicAdd((unsigned long long*)&rw->serial_turnovers, (unsigned long long)W.turnovers);
     atomicAdd(&rw->st.sweeps, st.sweeps);
     if (st.exceptional) atomicAdd(&rw->st.exceptional, st.exceptional);
@@ -575,21 +567,19 @@ static cudaError_t launch_pen_units(const Problem<double>& pr, const PipeParams&
     return cudaGetLastError();
 }
 
-static cudaError_t launch_pencil_pipelined(Problem<double> pr, const amrvw_options& opt, int max_len, long long total, int sm_count, cudaStream_t st, int* launches,
-                                           const QueueBufs& qb, PenLane* parked, cudaEvent_t* ev = nullptr, RoundsTimes* times = nullptr, int* lanes_out = nullptr,
-                                           unsigned long long* order_keys = nullptr) {
+// lanes per polynomial and the rest of the schedule's parameters for a batch (also sizes the workspace: capi.cu)
+static void choose_pencil_params(const amrvw_options& opt, long long nbatch, int max_len, int sm_count, int& L, PipeParams& pp) {
     const int degree = max_len;          // vs has one entry per degree
-    int L = opt.lanes_per_poly;
+    L = opt.lanes_per_poly;
     if (L == 0) {
         L = degree < 48 ? 4 : (degree < 200 ? 8 : 16);
         // small batches of large pencils: 32 bulges (100 x degree 2000: 376 -> 257 ms; 500 x 500 stays at 16: 49 vs 53 ms)
-        if (degree >= 1000 && pr.nbatch <= (long long)sm_count * 8) L = 32;
+        if (degree >= 1000 && nbatch <= (long long)sm_count * 8) L = 32;
     }
     if (L > 32) L = 32;      // chained warps exist for the real rank-one path only
-    if (lanes_out) *lanes_out = L;
-    PipeParams pp;
     pp.reuse = opt.shift_reuse ? opt.shift_reuse : 2;
     if (pp.reuse > L / 2) pp.reuse = L / 2 > 0 ? L / 2 : 1;
+    while (2 * L / pp.reuse > 32) pp.reuse *= 2;     // the largest dense trailing block of the pencil kernels is 32 x 32
     const int mshift = 2 * L / pp.reuse;
     pp.small = opt.small_window ? opt.small_window : (mshift + 8 > 24 ? mshift + 8 : 24);
     if (pp.small < mshift) pp.small = mshift;
@@ -597,6 +587,14 @@ static cudaError_t launch_pencil_pipelined(Problem<double> pr, const amrvw_optio
     pp.ms = pp.small + 4;
     pp.dense = opt.shift_solver != AMRVW_SHIFTS_CHASE;
     pp.mh = mshift;
+}
+
+static cudaError_t launch_pencil_pipelined(Problem<double> pr, const amrvw_options& opt, int max_len, long long total, int sm_count, cudaStream_t st, int* launches,
+                                           const QueueBufs& qb, PenLane* parked, cudaEvent_t* ev = nullptr, RoundsTimes* times = nullptr, int* lanes_out = nullptr,
+                                           unsigned long long* order_keys = nullptr) {
+    int L; PipeParams pp;
+    choose_pencil_params(opt, pr.nbatch, max_len, sm_count, L, pp);
+    if (lanes_out) *lanes_out = L;
     cudaError_t e;
     if ((e = cudaMemsetAsync(pr.counters, 0, CNT_WORDS * sizeof(unsigned), st)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(qb.q, 0, sizeof(RoundQueue), st)) != cudaSuccess) return e;
@@ -610,8 +608,7 @@ static cudaError_t launch_pencil_pipelined(Problem<double> pr, const amrvw_optio
         *launches += 1;
     }
     if (times) cudaEventRecord(ev[1], st);
-    static const int seg_env = std::getenv("AMRVW_SEG_STEPS") ? std::atoi(std::getenv("AMRVW_SEG_STEPS")) : 0;   // development knob
-    const int seg_steps = seg_env > 0 ? seg_env : 256;
+    const int seg_steps = 256;
     e = cudaErrorInvalidValue;
     switch (L) {
         case 4: if (pp.mh <= 8) e = launch_pen_units<4, 8>(pr, pp, qb, parked, seg_steps, sm_count, st); break;

@@ -303,7 +303,7 @@ AMRVW_DI void create_and_absorb(StepState& z, const Rot<double> qm, const Rot<do
 #else
         Fact<double, false> Fl = F;
         Fl.Q = lq - (start - 1); Fl.B = lb - (start - 1); Fl.Ct = lc - (start - 1);
-        Counter cl = {start - 1, start, stop, 15, -1};
+        Counter cl = {start - 1, start, stop, AMRVW_IT_COUNT, -1};
         int dummy = 0;
         PolyStats ds = {0, 0, 0, 0, 0};
         create_bulge_rds(Fl, cl, U, V, &sh, seed, poly, dummy, ds);
@@ -384,7 +384,7 @@ AMRVW_DI void check_deflation_stack(Fact<double, false>& F, LeaderState& ls, con
             F.Q[k] = make_rot<double>(sign_(ldcg_rot(F.Q + k).c), 0.0);   // deflate (RDS.jl:134-141)
             ls.ctr.zero_index = k;
             ls.ctr.start_index = k + 1;
-            ls.ctr.it_count = 15;
+            ls.ctr.it_count = AMRVW_IT_COUNT;
         }
     }
 }
@@ -430,9 +430,9 @@ AMRVW_NI long long chase_shifts(Fact<double, false>& W, const int k0, const int 
     const int m = stop - k0;
     cplx* Es = e - (k0 + 1);
     for (int t = 0; t <= m; ++t) e[t] = cplx(0.0, 0.0);
-    Counter c2 = {k0, k0 + 1, stop, 15, -1};
+    Counter c2 = {k0, k0 + 1, stop, AMRVW_IT_COUNT, -1};
     PolyStats sub = {0, 0, 0, 0, 0};
-    drive_window(W, k0 + 1, stop, c2, Es, 20ll * m, seed, poly, ord, sub, wstep);
+    drive_window(W, k0 + 1, stop, c2, Es, AMRVW_IT_MAX(m), seed, poly, ord, sub, wstep);
     return W.turnovers;
 }
 
@@ -485,7 +485,7 @@ AMRVW_DI int phase_a(Fact<double, false>& F, LeaderState& ls, cplx* E, const Gro
             sink.push(lo2, hi2, ctr.it_count);
             if (lo2 == 2) { diagonal_block_cg(F, 1, A); E[1] = to_c(A[0]); }
             pop_window(ls);
-            ctr.stop_index = lo2 - 2; ctr.zero_index = 0; ctr.start_index = 1; ctr.it_count = 15;
+            ctr.stop_index = lo2 - 2; ctr.zero_index = 0; ctr.start_index = 1; ctr.it_count = AMRVW_IT_COUNT;
             if (ctr.stop_index >= 1) check_deflation_stack(F, ls, dstack);
             ls.pn_small += 1;
         } else if (ctr.it_count == 0) {

@@ -47,7 +47,8 @@ typedef SmallWinRec SmallWin;
 // counters[0]: polynomials that got a fat step from the last phase A launch
 // counters[1]: small windows queued
 // counters[2..]: reserved
-enum { CNT_ACTIVE = 0, CNT_SMALL = 1, CNT_WORDS = 8 };
+// counters[2]: sticky abort flag of the unit queue (a warp waited ~10 s for work: see queue_pop)
+enum { CNT_ACTIVE = 0, CNT_SMALL = 1, CNT_ABORT = 2, CNT_WORDS = 8 };
 
 // ---------------------------------------------------------------- set-up
 __global__ void __launch_bounds__(64) rounds_setup_kernel(Problem<double> pr) {
@@ -55,13 +56,13 @@ __global__ void __launch_bounds__(64) rounds_setup_kernel(Problem<double> pr) {
     if (p >= pr.nbatch) return;
     PolyRec rec;
     rec.ls.kk = 0; rec.ls.it_max = 0; rec.ls.ord = 0; rec.ls.unconv = 0; rec.ls.sp = 0; rec.ls.pc_sub = 0; rec.ls.pc_small = 0; rec.ls.pn_small = 0;
-    rec.ls.ctr = {0, 1, 0, 15, -1};
+    rec.ls.ctr = {0, 1, 0, AMRVW_IT_COUNT, -1};
     rec.st = {0, 0, 0, 0, 0};
     rec.serial_turnovers = 0; rec.chase_turnovers = 0;
     rec.N = 0; rec.K = 0; rec.mode = 0; rec.nb = 0; rec.iterating = 0; rec.pad = 0;
     const long long off = pr.offsets[p];
     const int len = (int)(pr.offsets[p + 1] - off);
-    cplx* out = pr.roots + (off - p);
+    cplx* out = pr.roots + off;
     int first, last;
     trim_zeros(pr.coeffs + off, len, first, last);
     if (first < 0) {
@@ -79,8 +80,8 @@ __global__ void __launch_bounds__(64) rounds_setup_kernel(Problem<double> pr) {
             factor_companion(F, ps);
             for (int i = 0; i < N; ++i) out[i] = cplx(0.0, 0.0);
             rec.N = N;
-            rec.ls.ctr = {0, 1, N - 1, 15, -1};
-            rec.ls.it_max = 20ll * (N - 1);
+            rec.ls.ctr = {0, 1, N - 1, AMRVW_IT_COUNT, -1};
+            rec.ls.it_max = AMRVW_IT_MAX(N - 1);
             rec.iterating = 1;
         }
     }
@@ -152,6 +153,23 @@ struct UnitPark {           // mutable per-unit state between visits; accessed w
     int pad[3];
 };
 
+// Pop a unit: >= 0 its id, -2 no work left, -3 the queue was aborted.  A warp that has waited ~10 s for its
+// ticket's slot (something upstream is broken: a lost unit would otherwise hang the device) raises the sticky
+// abort flag; every other warp sees it in its own wait loop and leaves too, and the host turns the flag into
+// AMRVW_ERR_QUEUE_TIMEOUT instead of returning roots that silently miss the lost units' polynomials.
+AMRVW_DI int queue_pop(RoundQueue* q, int* slots, const unsigned mask, unsigned* counters) {
+    const unsigned k = atomicAdd(&q->head, 1u);
+    int* slot = slots + (k & mask);
+    for (unsigned spins = 0;; ++spins) {
+        const int u = atomicExch(slot, -1);
+        if (u >= 0) return u;
+        if (*reinterpret_cast<volatile unsigned*>(&q->remaining) == 0u) return -2;
+        if (*reinterpret_cast<volatile unsigned*>(counters + CNT_ABORT) != 0u) return -3;
+        if (spins > (1u << 24)) { atomicExch(counters + CNT_ABORT, 1u); return -3; }
+        __nanosleep(500);
+    }
+}
+
 AMRVW_DI void st_cg_rot(Rot<double>* p, const Rot<double> r) { __stcg(reinterpret_cast<double2*>(p), make_double2(r.c, r.s)); }
 
 // queue every unit that has a polynomial to iterate; one thread per unit
@@ -196,7 +214,7 @@ AMRVW_NI int unit_driver(const Problem<double>& pr, const PipeParams pp, const i
     Fact<double, false> F = make_fact<double, false>(pr, p, rec.N);
     GroupScratch sc;
     sc.q = sc.b = sc.c = nullptr; sc.e = nullptr; sc.H = nullptr; sc.isg = nullptr;
-    cplx* out = pr.roots + (pr.offsets[p] - p);
+    cplx* out = pr.roots + pr.offsets[p];
     const int* dstack = pr.dstack + (pr.offsets[p] + (long long)pr.extra * p);
     int nb = 0;
     SmallSink sink;
@@ -276,15 +294,7 @@ __global__ void __launch_bounds__(32, AMRVW_PIPE_MINBLOCKS) unit_kernel(Problem<
         const long long pc_p0 = clock64();
         int u = -1;
         if (lane32 == 0) {
-            const unsigned k = atomicAdd(&q->head, 1u);
-            int* slot = slots + (k & mask);
-            for (unsigned spins = 0;; ++spins) {
-                u = atomicExch(slot, -1);
-                if (u >= 0) break;
-                if (*reinterpret_cast<volatile unsigned*>(&q->remaining) == 0u) { u = -2; break; }
-                if (spins > (1u << 24)) { u = -3; break; }   // ~10 s without work: give up rather than hang the device
-                __nanosleep(500);
-            }
+            u = queue_pop(q, slots, mask, pr.counters);
         }
         u = __shfl_sync(0xffffffffu, u, 0);
         if (u < 0) break;
@@ -458,7 +468,7 @@ __global__ void __launch_bounds__(32, AMRVW_PIPE_MINBLOCKS) unit_kernel(Problem<
                 rec.ls.sp = sp;
                 rec.st.sweeps += nb;
                 rec.chase_turnovers += nturn + __ldcg(&up->nturn[grp]);
-                if (mode == 2) { rec.st.exceptional += nb; rec.ls.ord += nb; rec.ls.ctr.it_count = 14; }
+                if (mode == 2) { rec.st.exceptional += nb; rec.ls.ord += nb; rec.ls.ctr.it_count = AMRVW_IT_COUNT - 1; }
                 store_rec(r, rec);
             }
             if (lane32 == 0) __stcg(&up->t, -1);
@@ -502,7 +512,7 @@ __global__ void __launch_bounds__(64) rounds_small_kernel(Problem<double> pr) {
     const long long p = sw.poly;
     const PolyRec* r = pr.rec + p;
     Fact<double, false> F = make_fact<double, false>(pr, p, r->N);
-    cplx* E = pr.roots + (pr.offsets[p] - p) - 1;
+    cplx* E = pr.roots + pr.offsets[p] - 1;
     Rot<double> sq[SM + 3], sb[SM + 3], scc[SM + 3];
     double2 sn[12];
     GroupScratch sc;
@@ -512,7 +522,7 @@ __global__ void __launch_bounds__(64) rounds_small_kernel(Problem<double> pr) {
     PolyStats st = {0, 0, 0, 0, 0};
     int ord = 1000000 + sw.lo;   // exceptional shifts of a deferred window: ordinal keyed by the window, not by time
     const WindowStep wstep = {sn, 1};
-    const int left = drive_window(W, sw.lo, sw.hi, c2, E, 20ll * (r->N - 1), pr.seed, (uint64_t)p, ord, st, wstep);
+    const int left = drive_window(W, sw.lo, sw.hi, c2, E, AMRVW_IT_MAX(r->N - 1), pr.seed, (uint64_t)p, ord, st, wstep);
     PolyRec* rw = pr.rec + p;
     atomicAdd((unsigned long long*)&rw->serial_turnovers, (unsigned long long)W.turnovers);
     atomicAdd(&rw->st.sweeps, st.sweeps);
@@ -536,7 +546,7 @@ __global__ void __launch_bounds__(256) rounds_finish_kernel(Problem<S> pr, int s
     const PolyRec* recp = pr.rec + p;
     const int n = recp->N;
     if (n <= 0) return;   // closed forms were finished by the set-up kernel
-    cplx* out = pr.roots + (pr.offsets[p] - (pr.extra == 1 ? p : 0));   // pencil batches (extra == 2) have one slot per vs entry
+    cplx* out = pr.roots + pr.offsets[p];
     cplx* a = out;
     const bool in_smem = n <= smem_elems;
     if (in_smem) {
@@ -654,8 +664,7 @@ static cudaError_t launch_rounds_rds(Problem<double> pr, const amrvw_options& op
     if ((e = cudaMemsetAsync(pr.counters, 0, CNT_WORDS * sizeof(unsigned), st)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(qb.q, 0, sizeof(RoundQueue), st)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(qb.slots, 0xFF, (size_t)(qb.mask + 1) * sizeof(int), st)) != cudaSuccess) return e;
-    static const int seg_env = std::getenv("AMRVW_SEG_STEPS") ? std::atoi(std::getenv("AMRVW_SEG_STEPS")) : 0;   // development knob
-    const int seg_steps = seg_env > 0 ? seg_env : 512;
+    const int seg_steps = 512;   // lock-steps a warp chases before it parks the unit and takes the next one (128: 549 ms, 512: 530 ms on config 2)
     if (times) cudaEventRecord(ev[0], st);
     rounds_setup_kernel<<<nb64, 64, 0, st>>>(pr);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;

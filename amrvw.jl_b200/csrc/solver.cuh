@@ -21,6 +21,16 @@
 
 namespace amrvw {
 
+// The reference's compile-time constants, runtime options here (amrvw_options): tol = eps
+// (AMRVW_algorithm.jl:184), IT_COUNT = 15 (create-bulge.jl:9), it_max = 20 n (AMRVW_algorithm.jl:25).
+// They live in constant memory (a c[bank][offset] operand costs what an immediate costs); the host
+// writes them on the call's stream before its first launch.
+struct AlgoConst { double tol; int it_count; int it_max_factor; };
+__constant__ AlgoConst g_algo = {2.220446049250313e-16, 15, 20};
+#define AMRVW_EPS (amrvw::g_algo.tol)
+#define AMRVW_IT_COUNT (amrvw::g_algo.it_count)
+#define AMRVW_IT_MAX(n1) ((long long)amrvw::g_algo.it_max_factor * (long long)(n1))
+
 struct PolyStats {            // per polynomial, optional
     long long turnovers;      // executed turnovers (all schedules)
     int sweeps;               // bulges chased
@@ -187,7 +197,7 @@ AMRVW_NI void create_bulge_rds(Fact<double, P>& F, Counter& ctr, Rot<double>& U,
                                uint64_t seed, uint64_t poly, int& rng_ordinal, PolyStats& st) {
     const int i = ctr.start_index;
     if (ctr.it_count == 0 && !given) {
-        ctr.it_count = 15;
+        ctr.it_count = AMRVW_IT_COUNT;
         st.exceptional++;
         const double t = uniform01(seed ^ 0xA5A5A5A5DEADBEEFull, poly, (uint64_t)rng_ordinal++) * 3.141592653589793;
         double sn, cs;
@@ -280,7 +290,7 @@ AMRVW_NI void bulge_step(Fact<cplx, P>& F, Counter& ctr, const Shifts* given, ui
     cplx A[4];
     cplx shift;
     if (ctr.it_count == 0 && !given) {  // create-bulge.jl:85-93
-        ctr.it_count = 15;
+        ctr.it_count = AMRVW_IT_COUNT;
         st.exceptional++;
         const double t = uniform01(seed ^ 0xA5A5A5A5DEADBEEFull, poly, (uint64_t)rng_ordinal++) * 3.141592653589793;
         double sn, cs;
@@ -337,7 +347,6 @@ template <bool P> AMRVW_DI void deflate(Fact<cplx, P>& F, int k) {  // CSS.jl:98
 }
 
 // ---------------------------------------------------------------- driver
-#define AMRVW_EPS 2.220446049250313e-16
 
 template <class S, bool P> AMRVW_NI void check_deflation(Fact<S, P>& F, Counter& ctr) {  // AMRVW_algorithm.jl:181-202
     for (int k = ctr.stop_index; k >= ctr.start_index; --k) {
@@ -345,7 +354,7 @@ template <class S, bool P> AMRVW_NI void check_deflation(Fact<S, P>& F, Counter&
             deflate(F, k);
             ctr.zero_index = k;
             ctr.start_index = k + 1;
-            ctr.it_count = 15;
+            ctr.it_count = AMRVW_IT_COUNT;
             return;
         }
     }

@@ -25,18 +25,30 @@ def _ptr(a):
 
 
 class Context:
-    """One per host thread and device (amrvw_ctx)."""
+    """One per host thread (amrvw_ctx).  `device`: one GPU (amrvw_create; -1 = current);
+    `devices`: a list of GPUs, or "all" -- one context that splits every host-buffer batch over
+    them (amrvw_create_multi)."""
 
-    def __init__(self, device=-1, seed=0, strict=False, **options):
-        self._lib = _lib.load(strict=strict)
+    def __init__(self, device=-1, seed=0, strict=False, devices=None, lib_path=None, **options):
+        self._lib = _lib.load(strict=strict, path=lib_path)
         self._h = ctypes.c_void_p()
-        rc = self._lib.amrvw_create(ctypes.byref(self._h), int(device), ctypes.c_uint64(seed))
+        if devices is not None:
+            devs = [] if devices == "all" else [int(d) for d in devices]
+            arr = (ctypes.c_int * max(len(devs), 1))(*devs)
+            rc = self._lib.amrvw_create_multi(ctypes.byref(self._h), arr, len(devs), ctypes.c_uint64(seed))
+        else:
+            rc = self._lib.amrvw_create(ctypes.byref(self._h), int(device), ctypes.c_uint64(seed))
         if rc != 0:
             self._h = ctypes.c_void_p()
             raise AmrvwError(f"amrvw_create failed ({rc}): no usable CUDA device; this package has no CPU path")
         self.last_stats = None
+        self._seed = seed
         if options:
             self.set_options(seed=seed, **options)
+
+    @property
+    def device_count(self):
+        return self._lib.amrvw_device_count(self._h)
 
     # -- plumbing
     def close(self):
@@ -50,8 +62,11 @@ class Context:
         if rc != 0:
             raise AmrvwError(f"amrvw error {rc}: {self._lib.amrvw_last_error(self._h).decode()}")
 
-    def set_options(self, schedule=0, lanes_per_poly=0, shift_reuse=0, small_window=0, shift_solver=0, seed=0):
-        o = Options(int(schedule), int(lanes_per_poly), int(shift_reuse), int(small_window), int(shift_solver), 0, int(seed))
+    def set_options(self, schedule=0, lanes_per_poly=0, shift_reuse=0, small_window=0, shift_solver=0, seed=0, it_count=0, it_max_factor=0, tol=0.0):
+        """it_count / it_max_factor / tol: the reference's IT_COUNT = 15 (create-bulge.jl:9), it_max = 20 n
+        (AMRVW_algorithm.jl:25) and deflation tolerance eps (AMRVW_algorithm.jl:184); 0 = those values."""
+        o = Options(int(schedule), int(lanes_per_poly), int(shift_reuse), int(small_window), int(shift_solver), int(it_count), int(seed),
+                    int(it_max_factor), 0, float(tol))
         self._check(self._lib.amrvw_set_options(self._h, ctypes.byref(o)))
 
     def set_stream(self, cuda_stream_handle):
@@ -104,11 +119,8 @@ class Context:
             if ws.shape != coeffs.shape:
                 raise ValueError("vs and ws must have the same layout")
         total = int(offsets[-1]) if B >= 0 and len(offsets) else 0
-        if pencil:
-            root_off = offsets.copy()
-        else:
-            root_off = offsets - np.arange(B + 1, dtype=np.int64)
-        out = np.zeros(max(int(root_off[-1]) if B > 0 else 0, 0) + (B if not pencil else 0) + 1, dtype=np.complex128)
+        root_off = offsets.copy()              # polynomial p's roots start at complex slot offsets[p]
+        out = np.zeros(total + 1, dtype=np.complex128)
         nroots = np.zeros(max(B, 1), dtype=np.int32)
         nunc = np.zeros(max(B, 1), dtype=np.int32)
         st = Stats()
@@ -123,6 +135,19 @@ class Context:
         self._check(rc)
         self.last_stats = st.as_dict() if want_stats else None
         return out, root_off, nroots[:B], nunc[:B]
+
+    def count_real_roots_csr(self, coeffs, offsets, want_stats=False):
+        """real_polynomial_roots counts for a Float64 batch, host buffers: int32[B, 3] =
+        (imag == 0, imag > 0, imag < 0) per polynomial, and n_unconverged int32[B]."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        B = len(offsets) - 1
+        coeffs = np.ascontiguousarray(coeffs, dtype=np.float64)
+        counts = np.zeros((max(B, 1), 3), dtype=np.int32)
+        nunc = np.zeros(max(B, 1), dtype=np.int32)
+        st = Stats()
+        self._check(self._lib.amrvw_count_real_roots_rds_f64(self._h, _ptr(coeffs), _ptr(offsets), B, _ptr(counts), _ptr(nunc), ctypes.byref(st) if want_stats else None))
+        self.last_stats = st.as_dict() if want_stats else None
+        return counts[:B], nunc[:B]
 
     # -- device pointers (ints) in/out: used by bench.py with torch-owned HBM buffers
     def roots_dev(self, kind, d_coeffs, d_offsets, B, total, max_len, d_roots, d_nroots, d_nunconv, d_ws=None, want_stats=False):

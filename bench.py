@@ -6,8 +6,9 @@
 
 A "step" is one pass of the hot path over one batch: rooting `batch` polynomials of degree `degree`
 (default: BASELINE config 2, the README statistics workload -- 3000 N(0,1) polynomials of degree
-3000, Float64 real double shift) per GPU.  Polynomials are independent, so the batch is sharded by
-polynomial with no collective ("scaling": "weak": every rank roots a full batch of its own).
+3000, Float64 real double shift).  Polynomials are independent, so at N GPUs that ONE batch is split
+contiguously by polynomial (`synth.shard_range`: 375 each at N = 8, the north-star configuration) with
+no collective: "scaling": "strong".  `--weak` gives every rank a full batch of its own instead.
 
 Printed JSON (one line, rank 0): metric polynomials/s (`value`: inputs resident in HBM, CUDA-event
 timed; `e2e`: through the C ABI with pinned HOST buffers, H2D + kernels + D2H inside the timed
@@ -39,7 +40,11 @@ CONFIGS = {
 }
 FLOP_PER_TURNOVER = {"rds_f64": 37.0, "css_c64": 94.0, "pencil_f64": 37.0}
 BYTES_PER_TURNOVER = {"rds_f64": 96.0 / 7, "css_c64": 208.0 / 3, "pencil_f64": 160.0 / 11}
-NCU_TRAFFIC_C2 = 143.5e9   # dram read 62.8 GB + write 80.7 GB: profiles/r01_c2_unit_kernel_ncu_keymetrics.csv (ncu --set full, default c2 launch)
+# reference-schedule turnovers per polynomial (the oracle's count: what "useful" means) for runs that do
+# not time the CPU leg themselves (N > 1): profiles/useful_turnovers.json, written by tools/useful_turnovers.py
+USEFUL_FILE = os.path.join(ROOT, "profiles", "useful_turnovers.json")
+# dram bytes of the dominant kernel per launch from the committed `ncu --set full` capture of the same command
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "ncu_traffic.json")
 
 
 def parse():
@@ -58,6 +63,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="polynomials in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--weak", action="store_true", help="every rank roots a full batch of its own (round-1 behaviour) instead of a share of one batch")
     return ap.parse_args()
 
 
@@ -140,7 +146,7 @@ def cpu_baseline(kind, degree, law, seed, sample, threads=0):
     t0 = time.perf_counter()
     out, roff, nr, st = orc.roots_csr(flat, offsets, ws=ws, seed=0, threads=cores)
     dt = time.perf_counter() - t0
-    return {"value": sample / dt, "unit": "polynomials/s", "cores": cores, "kind": "port",
+    return {"value": sample / dt, "unit": "polynomials/s", "cores": cores, "kind": "port", "value_per_core": sample / dt / cores,
             "sample": f"{sample} polynomials of degree {degree} (same generator and seed as the GPU batch), {dt:.2f} s wall, OpenMP dynamic over polynomials",
             "turnovers_per_s": st["turnovers"] / dt, "turnovers_per_poly": st["turnovers"] / sample, "seconds": dt}
 
@@ -155,9 +161,20 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    workload = f"{args.config}: {kind} batch={batch}/GPU degree={degree} law={['N(0,1)', 'U[0,1)', 'U[0,1)-1/2'][law]} seed={seed}"
-    config = {"workload": workload, "kind": kind, "batch_per_gpu": batch, "degree": degree, "parallelism": f"shard-by-polynomial x{world}",
-              "l2": "per-step working set (rotator chains, rewritten by the set-up every step) exceeds the 126 MB L2 for c2/c5; no flush between steps"}
+    from amrvw_jl_b200 import synth as _synth
+    if args.config == "c5" and not args.batch and not args.weak:
+        batch = 512                                    # BASELINE config 5 is 512 polynomials over 8 GPUs
+    if args.weak:
+        lo, hi, total_batch = rank * batch, (rank + 1) * batch, batch * world
+    else:
+        lo, hi = _synth.shard_range(batch, rank, world)
+        total_batch = batch
+    share = hi - lo
+    workload = (f"{args.config}: {kind} batch={total_batch} degree={degree} law={['N(0,1)', 'U[0,1)', 'U[0,1)-1/2'][law]} seed={seed}, "
+                + (f"{batch} per GPU" if args.weak else f"split by polynomial over {world} GPU(s): {batch // world}-{-(-batch // world)} each"))
+    config = {"workload": workload, "kind": kind, "batch": total_batch, "batch_per_gpu": share, "degree": degree, "parallelism": f"shard-by-polynomial x{world}",
+              "l2": "per-step working set (rotator chains, rewritten by the set-up every step) exceeds the 126 MB L2 at every N for c2 (54 MB of chains per 375 polynomials x 3 chains + roots); no flush between steps"}
+    scaling = "weak" if args.weak else "strong"
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
@@ -177,9 +194,10 @@ def main():
         n = sum(int(r["sample"].split()[0]) for r in runs)
         val = n / secs
         line = {"impl": "reference", "metric": "polynomials/sec", "value": val, "unit": "polynomials/s", "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": 1e3 * secs / len(runs), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "warmup": args.warmup, "ms_per_step": 1e3 * secs / len(runs), "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": val, "unit": "polynomials/s", "cores": runs[-1]["cores"], "kind": "port", "sample": runs[-1]["sample"],
+                                 "value_per_core": val / runs[-1]["cores"],
                                  "turnovers_per_s": sum(r["turnovers_per_s"] * r["seconds"] for r in runs) / secs},
                 "e2e": {"value": val, "unit": "polynomials/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "note": "Julia is not available in this image: the reference arm is the C++ oracle (same algorithm, same one-bulge schedule); each step is a bounded sample of the workload"}
@@ -198,7 +216,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    flat, ws, offsets, ncoef = make_inputs(kind, batch, degree, law, seed, rank * batch)
+    batch = share                                      # from here on: this rank's polynomials
+    flat, ws, offsets, ncoef = make_inputs(kind, batch, degree, law, seed, lo)
     total = int(offsets[-1])
     ctx = A.Context(device=local_rank, seed=seed, schedule=args.schedule, lanes_per_poly=args.lanes, shift_reuse=args.reuse, small_window=args.small)
     stream = torch.cuda.current_stream()
@@ -207,7 +226,7 @@ def main():
     d_c = torch.from_numpy(flat).to(dev)
     d_w = torch.from_numpy(ws).to(dev) if ws is not None else None
     d_o = torch.from_numpy(offsets).to(dev)
-    nroot_slots = total if kind.startswith("pencil") else total - batch
+    nroot_slots = total                               # polynomial p's roots start at complex slot offsets[p]
     d_r = torch.zeros(2 * (total + 1), dtype=torch.float64, device=dev)
     d_n = torch.zeros(batch, dtype=torch.int32, device=dev)
     d_u = torch.zeros(batch, dtype=torch.int32, device=dev)
@@ -243,7 +262,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    value = world * batch * args.steps / (ms * 1e-3)
+    value = total_batch * args.steps / (ms * 1e-3)
 
     # ---- end to end through the C ABI with pinned host buffers
     e2e = None
@@ -279,8 +298,36 @@ def main():
         dt = float(tt.item())
         h2d = flat.nbytes + (ws.nbytes if ws is not None else 0) + offsets.nbytes
         d2h = 16 * nroot_slots + 8 * batch
-        e2e = {"value": world * batch * args.steps / dt, "unit": "polynomials/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "roots_checksum": float(h_r[: 2 * nroot_slots].abs().sum().item())}
+        e2e = {"value": total_batch * args.steps / dt, "unit": "polynomials/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "bytes_are": "per rank (every rank copies its own share)", "roots_checksum": float(h_r[: 2 * nroot_slots].abs().sum().item()),
+               "call": "amrvw_roots_*_f64/c64 with pinned host buffers, one single-device context per rank"}
+        # ---- the same batch through ONE call of ONE process: a multi-device context over all N GPUs (amrvw_create_multi)
+        if world > 1 and not args.weak and kind == "rds_f64":
+            barrier()
+            if rank == 0:
+                try:
+                    fa, _, oa, _ = make_inputs(kind, total_batch, degree, law, seed, 0)
+                    g_c = torch.from_numpy(fa).pin_memory(); g_o = torch.from_numpy(oa).pin_memory()
+                    g_r = torch.zeros(2 * (int(oa[-1]) + 1), dtype=torch.float64).pin_memory()
+                    g_n = torch.zeros(total_batch, dtype=torch.int32).pin_memory(); g_u = torch.zeros(total_batch, dtype=torch.int32).pin_memory()
+                    mctx = A.Context(devices=list(range(world)), seed=seed, schedule=args.schedule, lanes_per_poly=args.lanes, shift_reuse=args.reuse, small_window=args.small)
+
+                    def one_call():
+                        rc = lib.amrvw_roots_rds_f64(mctx._h, P(g_c.data_ptr()), P(g_o.data_ptr()), total_batch, P(g_r.data_ptr()), P(g_n.data_ptr()), P(g_u.data_ptr()), None)
+                        assert rc == 0, lib.amrvw_last_error(mctx._h)
+                    one_call()
+                    t0 = time.perf_counter()
+                    for _ in range(args.steps):
+                        one_call()
+                    dt1 = time.perf_counter() - t0
+                    e2e["one_process_one_call"] = {"value": total_batch * args.steps / dt1, "unit": "polynomials/s", "devices": world,
+                                                   "h2d_bytes_per_step": int(fa.nbytes + oa.nbytes), "d2h_bytes_per_step": int(16 * int(oa[-1]) + 8 * total_batch),
+                                                   "unconverged": int(g_u.sum().item()),
+                                                   "call": "one amrvw_roots_rds_f64 call on an amrvw_create_multi context: split, per-device streams, gather inside the library"}
+                    mctx.close()
+                except Exception as ex:      # never lose the main line to the extra measurement
+                    e2e["one_process_one_call"] = {"error": repr(ex)}
+            barrier()
 
     if rank != 0:
         if world > 1:
@@ -292,9 +339,20 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         cb = cpu_baseline(kind, degree, law, seed, args.cpu_sample)
     ms_step = ms / args.steps
-    executed = st["turnovers"]
-    useful_per_poly = cb["turnovers_per_poly"] if cb else None
-    useful = useful_per_poly * batch if useful_per_poly else executed
+    executed = st["turnovers"]                       # this rank's share
+    # "useful" = the reference schedule's turnover count on the same inputs, at every N: from this run's CPU sample
+    # when it has one, else from the committed oracle counts (never from the executed count)
+    useful_per_poly, useful_src = None, None
+    if cb:
+        useful_per_poly, useful_src = cb["turnovers_per_poly"], "CPU sample of this run (oracle, reference schedule)"
+    else:
+        try:
+            tab = json.load(open(USEFUL_FILE))
+            key = f"{kind}:{degree}:{law}:{seed}"
+            useful_per_poly, useful_src = float(tab[key]["turnovers_per_poly"]), f"profiles/useful_turnovers.json[{key}] (oracle, {tab[key]['polynomials']} polynomials)"
+        except Exception:
+            pass
+    useful = useful_per_poly * batch if useful_per_poly else None
     # dominant kernel: the persistent unit kernel (phase A + systolic chase) for the pipelined RDS path, the
     # one iteration kernel otherwise; its duration is the CUDA-event time of that launch in the last warm-up step
     lanes = int(st.get("lanes", 0))
@@ -306,25 +364,32 @@ def main():
                        "pencil_f64": f"pen_unit_kernel<{lanes},MH> (companion pencil, five chains: phase A + systolic chase behind the unit queue)"}[kind]
     else:
         kernel_ms, kernel_name = st["device_ms"], "roots_reference_kernel / roots_pencil_reference_kernel (one polynomial per thread)"
-    flops = useful * FLOP_PER_TURNOVER[kind]
-    tf = flops / (kernel_ms * 1e-3) / 1e12
+    tf = useful * FLOP_PER_TURNOVER[kind] / (kernel_ms * 1e-3) / 1e12 if useful else None
     hbm_peak, hbm_src = 6650.0, "fallback"
     try:
         mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         hbm_peak, hbm_src = float(mp["hbm_gbs"]), "measured"
     except Exception:
         pass
-    gbs = useful * BYTES_PER_TURNOVER[kind] / (kernel_ms * 1e-3) / 1e9
-    # dram__bytes_read.sum + dram__bytes_write.sum of that kernel from the committed ncu --set full capture
-    # (profiles/r01_c2_unit_kernel_ncu_full_keymetrics.csv); only valid for the default c2 launch
-    traffic = NCU_TRAFFIC_C2 if (args.config == "c2" and not args.batch and not args.degree and not args.lanes) else None
-    roofline = {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak, "traffic": traffic,
+    gbs = useful * BYTES_PER_TURNOVER[kind] / (kernel_ms * 1e-3) / 1e9 if useful else None
+    # dram__bytes_read.sum + dram__bytes_write.sum of that kernel per launch: from the committed ncu --set full capture of
+    # the same command (profiles/ncu_traffic.json names the .csv it was read from), only for the launch it was captured on
+    traffic, traffic_src = None, None
+    try:
+        tr = json.load(open(TRAFFIC_FILE)).get(f"{args.config}:{batch}:{degree}:{lanes}")
+        if tr and not args.reuse and not args.small:
+            traffic, traffic_src = float(tr["dram_bytes"]), tr["source"]
+    except Exception:
+        pass
+    roofline = {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak if tf else None, "traffic": traffic, "traffic_source": traffic_src,
+                "per": "GPU (rank 0's share of the batch, its kernel time, one GPU's peak): the same quantity at every N",
                 "traffic_note": "bytes per launch (ncu dram read+write); the reference-schedule algorithmic bytes (96 B per chase step per bulge) are ~12x larger: the systolic chase streams each rotator once per L bulges",
                 "peak_source": "DFMA probe measured live in this run (MEASURED_PEAKS.json has no FP64 entry); nominal 37.2",
                 "kernel": kernel_name, "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / st["device_ms"] if st["device_ms"] else None,
-                "useful_turnovers_per_step": useful, "executed_turnovers_per_step": executed,
-                "useful_definition": "the reference schedule's turnover count on the same inputs (CPU sample mean x batch) x 37 flop (94 complex)",
-                "hbm": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": hbm_src + " copy bandwidth",
+                "useful_turnovers_per_step": useful, "executed_turnovers_per_step": executed, "exec_over_useful": executed / useful if useful else None,
+                "useful_source": useful_src,
+                "useful_definition": "the reference schedule's turnover count on the same inputs (oracle mean per polynomial x this rank's polynomials) x 37 flop (94 complex)",
+                "hbm": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak if gbs else None, "peak_source": hbm_src + " copy bandwidth",
                         "note": "algorithmic bytes per chase step: RDS 96 B / 7 turnovers, CSS 208 B / 3, pencil 160 B / 11 (SURVEY 8d); the path is not HBM-bound"}}
     if prof and prof["us_main"] > 0:
         roofline["kernel_times_ms"] = {"setup": prof["us_setup"] / 1e3, "main": prof["us_main"] / 1e3, "small_windows": prof["us_small"] / 1e3, "finish": prof["us_finish"] / 1e3}
@@ -333,9 +398,9 @@ def main():
         roofline["warp_cycle_shares"] = {"phase_a": prof["cycles_phase_a"] / busy, "lean_chase": prof["cycles_lean"] / busy, "fill_drain_chase": prof["cycles_general"] / busy,
                                          "queue_wait_vs_busy": prof["cycles_pop"] / busy, "lean_cycles_per_step": prof["cycles_lean"] / max(prof["steps_lean"], 1)}
     line = {"metric": "polynomials/sec", "value": value, "unit": "polynomials/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config, "turnovers_per_sec": world * useful / (ms_step * 1e-3), "roofline": roofline, "cpu_baseline": cb, "e2e": e2e,
-            "gpu_launches": int(st["launches"] * args.steps), "clocks": clk.summary(),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config, "turnovers_per_sec": (useful_per_poly * total_batch / (ms_step * 1e-3)) if useful_per_poly else None, "roofline": roofline, "cpu_baseline": cb, "e2e": e2e,
+            "gpu_launches": int(st["launches"] * args.steps), "gpu_launches_are": "this rank's kernels inside the timed region", "clocks": clk.summary(),
             "stats_per_step": {k: st[k] for k in ("turnovers", "sweeps", "exceptional", "unconverged", "fat_steps", "launches", "lanes")},
             "unconverged": n_unconv, "roots_found": nroots_ok}
     print(json.dumps(line))

@@ -12,9 +12,9 @@
  *   - Polynomials are ragged, CSR style: polynomial p owns coeffs[offsets[p] .. offsets[p+1]),
  *     lowest degree first (a0 .. an), exactly the vector AMRVW.roots takes.  Complex data is
  *     interleaved (re, im), bit-compatible with Julia's Vector{ComplexF64}.
- *   - Roots are interleaved (re, im) doubles.  Non-pencil calls write polynomial p's roots at
- *     complex slot offsets[p] - p (a polynomial with len coefficients has at most len-1 roots);
- *     pencil calls (vs, ws of equal length N_p) write at complex slot offsets[p].
+ *   - Roots are interleaved (re, im) doubles: polynomial p's roots start at complex slot offsets[p]
+ *     (the root buffer has offsets[nbatch] complex slots, one per input entry: a polynomial with len
+ *     coefficients has at most len-1 roots, a pencil of order N_p has N_p; empty vectors own nothing).
  *     nroots[p] says how many were written: like the reference, leading/trailing zero coefficients
  *     are trimmed (utils.jl:14-58), degree <= 2 goes through the closed forms (utils.jl:63-140),
  *     roots come back sorted by (real, imag) (AMRVW_algorithm.jl:134) followed by the K zero roots
@@ -42,7 +42,8 @@ enum amrvw_status {
     AMRVW_OK = 0,
     AMRVW_ERR_ARGUMENT = -1,
     AMRVW_ERR_CUDA = -2,
-    AMRVW_ERR_NO_DEVICE = -3
+    AMRVW_ERR_NO_DEVICE = -3,
+    AMRVW_ERR_QUEUE_TIMEOUT = -4   /* the device-side unit queue gave up waiting (~10 s): results incomplete */
 };
 
 enum amrvw_schedule {
@@ -60,16 +61,22 @@ enum amrvw_shift_solver {
     AMRVW_SHIFTS_DENSE = 2    /* trailing block written out densely + double-shift Hessenberg QR     */
 };
 
-/* Mirrors the reference's compile-time constants: IT_COUNT = 15
- * (create-bulge.jl:9), it_max = 20 n (AMRVW_algorithm.jl:25), tol = eps (AMRVW_algorithm.jl:184). */
+/* The schedule knobs of this library plus the reference's compile-time constants as run-time options:
+ * IT_COUNT = 15 (create-bulge.jl:9: bulge steps on one window before an exceptional shift), it_max = 20 n
+ * (AMRVW_algorithm.jl:25: cap on driver trips) and the deflation tolerance eps (AMRVW_algorithm.jl:184).
+ * amrvw_default_options fills in the reference's values; 0 in any of the three also means "reference value".
+ * The three constants live in device constant memory: contexts that share a device must agree on them. */
 typedef struct amrvw_options {
     int32_t schedule;        /* amrvw_schedule */
     int32_t lanes_per_poly;  /* pipelined: bulges in flight per polynomial (4, 8, 16, 32; rds_f64 also 64, 128, 256 = 2, 4 or 8 chained warps); 0 = auto */
     int32_t shift_reuse;     /* pipelined: bulges driven by each shift pair (1, 2, 4 or 8); 0 = auto  */
     int32_t small_window;    /* pipelined: windows up to this size use the one-bulge step; 0 = auto   */
     int32_t shift_solver;    /* pipelined: amrvw_shift_solver; 0 = auto (dense)                        */
-    int32_t reserved;        /* must be 0 */
+    int32_t it_count;        /* IT_COUNT, create-bulge.jl:9; default 15                                */
     uint64_t seed;           /* exceptional (random) shifts: counter-based, reproducible              */
+    int32_t it_max_factor;   /* it_max = it_max_factor * n, AMRVW_algorithm.jl:25; default 20          */
+    int32_t reserved;        /* must be 0 */
+    double tol;              /* |s| <= tol deflates, AMRVW_algorithm.jl:184; default eps(Float64)      */
 } amrvw_options;
 
 typedef struct amrvw_stats {
@@ -85,6 +92,19 @@ typedef struct amrvw_stats {
 
 /* device < 0: current device. */
 int amrvw_create(amrvw_ctx** ctx, int device, uint64_t seed);
+/* One context over several GPUs of the box: the HOST-buffer entry points below split
+ * the batch contiguously by polynomial, balanced by the sum of squared lengths (the work per polynomial
+ * grows like n^2), run every slice on its own device and stream side by side, and copy each slice's
+ * results straight into the caller's buffers -- one call roots the whole batch, as one
+ * `roots.(pss)` comprehension does in the reference (README.md:121, companion.jl:252-272).  No
+ * collective: polynomials never interact.  ndev = 0: every visible device.  Results are identical to
+ * the single-device call (same kernels, same per-polynomial seeds).  The *_dev entry points and
+ * amrvw_set_stream need a single-device context. */
+int amrvw_create_multi(amrvw_ctx** ctx, const int* devices, int ndev, uint64_t seed);
+int amrvw_device_count(const amrvw_ctx* ctx);
+/* The split a multi-device context applies (pure host code, needs no device): device d roots polynomials
+ * cuts[d] .. cuts[d+1]-1; cuts has ndev+1 entries, cuts[0] = 0, cuts[ndev] = nbatch. */
+int amrvw_partition_batch(const int64_t* offsets, int64_t nbatch, int ndev, int64_t* cuts);
 int amrvw_destroy(amrvw_ctx* ctx);
 const char* amrvw_last_error(const amrvw_ctx* ctx);
 void amrvw_default_options(amrvw_options* opt);
@@ -124,11 +144,18 @@ int amrvw_roots_pencil_f64_dev(amrvw_ctx* ctx, const double* d_vs, const double*
 int amrvw_roots_pencil_c64_dev(amrvw_ctx* ctx, const double* d_vs_reim, const double* d_ws_reim, const int64_t* d_offsets, int64_t nbatch, int64_t total, int64_t max_len,
                                double* d_roots_reim, int32_t* d_nroots, int32_t* d_n_unconverged, amrvw_stats* stats);
 
-/* real_polynomial_roots (src/complex_conjugate_root_theorem.jl:32-54) reduced on device: for each
+/* real_polynomial_roots (src/complex_conjugate_root_theorem.jl:32-54) for a batch, HOST buffers: roots the
+ * polynomials like amrvw_roots_rds_f64 and returns only, per polynomial, the number of roots with imag == 0
+ * exactly, imag > 0 and imag < 0 (counts3[3p..3p+2]) -- 12 bytes per polynomial come back instead of 16 n
+ * (README.md:121-127 needs exactly count(isreal)).  Works on single- and multi-device contexts. */
+int amrvw_count_real_roots_rds_f64(amrvw_ctx* ctx, const double* coeffs, const int64_t* offsets, int64_t nbatch,
+                                   int32_t* counts3, int32_t* n_unconverged, amrvw_stats* stats);
+
+/* The same reduction on roots already on the device (src/complex_conjugate_root_theorem.jl:32-54): for each
  * polynomial the number of roots with imag == 0 exactly, imag > 0 and imag < 0 (counts[3*p..]).
  * Device pointers; the README statistics workload (README.md:121) needs only this. */
 int amrvw_count_real_roots_dev(amrvw_ctx* ctx, const double* d_roots_reim, const int64_t* d_offsets, int64_t nbatch,
-                               int32_t slot_shift_per_poly, const int32_t* d_nroots, int32_t* d_counts3);
+                               int32_t slot_shift_per_poly /* 0: roots at slot offsets[p] */, const int32_t* d_nroots, int32_t* d_counts3);
 
 /* FP64 DFMA micro-benchmark: dependent-chain-free FMA throughput of the device, in TFLOP/s
  * (the FP64 roofline denominator; MEASURED_PEAKS.json only has HBM and bf16). */

@@ -48,6 +48,9 @@ def test_default_options_and_argument_errors_need_no_gpu(A):
     o = A.Options(9, 9, 9, 9, 9)
     lib.amrvw_default_options(ctypes.byref(o))
     assert (o.schedule, o.lanes_per_poly, o.shift_reuse, o.small_window) == (0, 0, 0, 0)
+    # the reference's constants (create-bulge.jl:9, AMRVW_algorithm.jl:25,184) are the defaults of the options
+    assert (o.it_count, o.it_max_factor, o.reserved) == (15, 20, 0) and o.tol == np.finfo(np.float64).eps
+    assert ctypes.sizeof(A.Options) == 48
     assert lib.amrvw_set_options(None, ctypes.byref(o)) == -1
     assert lib.amrvw_destroy(None) == 0
     assert lib.amrvw_last_error(None) == b"null context"
@@ -87,3 +90,35 @@ def test_host_packing_logic(A):
     assert R._is_batch([[1.0, 2.0], [3.0]]) and not R._is_batch([1.0, 2.0]) and R._is_batch(np.zeros((3, 4)))
     vs, ws = A.basic_pencil([1.0, 2.0, 3.0])
     assert vs.tolist() == [1.0, 2.0] and ws.tolist() == [0.0, 3.0]
+
+
+def test_partition_batch_is_contiguous_and_balanced_by_squared_length(A):
+    """Host logic of the multi-device context (amrvw_create_multi): contiguous cuts, every polynomial on
+    exactly one device, work (sum of len^2) balanced; pure host code, runs without a GPU."""
+    lib = A.load()
+    rng = np.random.default_rng(5)
+
+    def cuts_of(lens, ndev):
+        off = np.zeros(len(lens) + 1, dtype=np.int64)
+        np.cumsum(lens, out=off[1:])
+        cuts = np.zeros(ndev + 1, dtype=np.int64)
+        assert lib.amrvw_partition_batch(off.ctypes.data, len(lens), ndev, cuts.ctypes.data) == 0
+        return cuts
+
+    for B, ndev in ((3000, 8), (512, 8), (7, 8), (1, 2), (0, 4), (11, 3)):
+        lens = np.full(B, 3001, dtype=np.int64)
+        cuts = cuts_of(lens, ndev)
+        assert cuts[0] == 0 and cuts[-1] == B and np.all(np.diff(cuts) >= 0)
+        if B >= ndev:
+            sizes = np.diff(cuts)
+            assert sizes.max() - sizes.min() <= 1, sizes          # equal degrees: an even split (3000 over 8 = 375 each)
+    lens = rng.integers(0, 4000, size=2000).astype(np.int64)     # ragged, with empty vectors
+    for ndev in (2, 4, 8):
+        cuts = cuts_of(lens, ndev)
+        assert cuts[0] == 0 and cuts[-1] == len(lens) and np.all(np.diff(cuts) >= 0)
+        w = (lens.astype(float) ** 2 + 64.0)
+        per = np.array([w[cuts[d]:cuts[d + 1]].sum() for d in range(ndev)])
+        assert per.max() <= w.sum() / ndev + w.max() + 1.0, per   # no device exceeds its share by more than one polynomial
+    off = np.array([0, 5, 3], dtype=np.int64)
+    cuts = np.zeros(3, dtype=np.int64)
+    assert lib.amrvw_partition_batch(off.ctypes.data, 2, 2, cuts.ctypes.data) == -1     # decreasing offsets

@@ -1,7 +1,8 @@
-"""CPU test of the multi-GPU path's host logic: the batch is sharded by polynomial,
-every rank handles a contiguous slice, results are gathered on rank 0 -- no data-path collective.
-Runs with the gloo backend, world_size 2; the per-rank compute is stood in for by the oracle (this
-is host-logic coverage, the CUDA path needs a GPU)."""
+"""CPU tests of the plumbing bench.py uses at N > 1: `synth.shard_range` splits one batch
+contiguously by polynomial and a world_size-2 gloo group gathers per-rank results on rank 0 -- no data-path
+collective.  No product code runs here (there is no GPU): the per-rank "compute" is the oracle, so these
+tests can only catch a broken partition or gather.  The product's own multi-GPU path (amrvw_create_multi)
+is covered by tests/test_capi_symbols.py (the split, on CPU) and tests/test_gpu_multi.py (two GPUs)."""
 import os
 import socket
 
@@ -49,7 +50,7 @@ def test_shard_range_partitions():
             assert max(sizes) - min(sizes) <= 1
 
 
-def test_world2_gloo_shard_and_gather(oracle):
+def test_world2_gloo_shard_range_and_gather_plumbing(oracle):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

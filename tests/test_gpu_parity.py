@@ -6,6 +6,9 @@ Parity rule (north star / SURVEY.md 8c): roots matched by minimum-distance assig
 exactly-real roots (imag == 0) must agree exactly.  For the one-bulge (reference-schedule) kernels
 built without FMA contraction the real double shift path is additionally bit-identical to the
 oracle, which itself reproduces the reference's printed digits."""
+import json
+import os
+
 import numpy as np
 import pytest
 
@@ -20,6 +23,8 @@ pc = np.array([40.0 + 10.0j, -76.0 + 60.0j, 10.0 - 95.0j, 25.0 + 40.0j, -10.0 - 
 pc_rts = np.array([1j, 1 + 1j, 2 + 1j, 3 + 1j, 4 + 1j])
 pc2 = np.array([1j, -1, 0, 0, -1j, 1])
 SQEPS = np.sqrt(np.finfo(float).eps)
+# tolerance constants of the parity rule; see check_parity and profiles/r02_parity_margins.txt for what is observed
+C_RDS = 64.0
 
 
 def _g(rows):
@@ -55,17 +60,33 @@ def batch(oracle, seed, B, n, kind=0, cx=False):
     return rows
 
 
+MARGIN_LOG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_margins.jsonl")
+
+
 def check_parity(coeff_rows, got, want, C=64.0, real_counts=True):
+    """Every root within C n u ||a||/|a_n| kappa(z) max(1,|z|) of its minimum-distance partner, equal counts of
+    exactly-real roots.  The worst observed |dz|/tol (in units of the tolerance with C = 1, so the number is
+    the constant the data needs) is printed and appended to gpurun_out/parity_margins.jsonl: the constants
+    passed by the callers are held to at most 8x what profiles/r02_parity_margins.txt records."""
     worst = 0.0
     for a, g, w in zip(coeff_rows, got, want):
         assert len(g) == len(w)
         d, idx = match_roots(g, w)
-        tol = root_condition_tolerance(a, w[idx], C=C)
-        ratio = np.max(d / np.maximum(tol, 1e-300))
-        worst = max(worst, ratio)
-        assert ratio <= 1.0, f"root parity violated: max |dz|/tol = {ratio:.3g}"
+        tol1 = root_condition_tolerance(a, w[idx], C=1.0)
+        need = np.max(d / np.maximum(tol1, 1e-300))       # the C this polynomial needs
+        worst = max(worst, need)
+        assert need <= C, f"root parity violated: max |dz|/tol = {need / C:.3g} (needs C = {need:.3g}, allowed {C})"
         if real_counts:
             assert np.sum(g.imag == 0) == np.sum(w.imag == 0)
+    name = os.environ.get("PYTEST_CURRENT_TEST", "?").split(" ")[0]
+    line = {"test": name, "polynomials": len(coeff_rows), "degree": int(max(len(a) for a in coeff_rows)) - 1, "needed_C": worst, "allowed_C": C}
+    print("parity margin:", json.dumps(line))
+    try:
+        os.makedirs(os.path.dirname(MARGIN_LOG), exist_ok=True)
+        with open(MARGIN_LOG, "a") as f:
+            f.write(json.dumps(line) + "\n")
+    except OSError:
+        pass
     return worst
 
 
@@ -296,7 +317,8 @@ def horner_backward_error(a, z):
 def test_gpu_full_size_c2_properties(A, ctx, oracle):
     """BASELINE config 2 at full degree (n = 3000), a slice of the batch: every polynomial converges,
     residuals are at backward-error level, conjugate pairing is exact, real-root statistics follow
-    README.md:121-127; and one polynomial is checked root-by-root against the oracle."""
+    README.md:121-127; and 64 polynomials are checked root by root against the oracle (minimum-distance matching,
+    condition-scaled tolerance, exact counts of real roots)."""
     n, B = 3000, 96
     rows = batch(oracle, 2, B, n)
     got = A.roots(rows, ctx=ctx)
@@ -314,8 +336,11 @@ def test_gpu_full_size_c2_properties(A, ctx, oracle):
     expect = 2 / np.pi * np.log(n) + 0.625738072 + 2 / (np.pi * n)
     counts = np.array(counts)
     assert abs(counts.mean() - expect) < 4 * counts.std() / np.sqrt(B) + 0.2
-    want, _ = oracle.roots(rows[0])
-    check_parity(rows[:1], got[:1], [want])
+    K = 64
+    flat = np.concatenate(rows[:K]); off = np.arange(K + 1, dtype=np.int64) * (n + 1)
+    out, roff, nr, _ = oracle.roots_csr(flat, off)       # the reference's schedule, all host cores
+    want = [out[roff[p]:roff[p] + nr[p]] for p in range(K)]
+    check_parity(rows[:K], got[:K], want, C=C_RDS)
 
 
 def test_gpu_count_real_roots_dev(A, ctx, oracle):
@@ -329,7 +354,7 @@ def test_gpu_count_real_roots_dev(A, ctx, oracle):
     d_cnt = torch.zeros(120, dtype=torch.int32, device=dev)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     ctx.roots_dev("rds_f64", d_c.data_ptr(), d_o.data_ptr(), 40, int(off[-1]), 121, d_r.data_ptr(), d_n.data_ptr(), d_u.data_ptr())
-    ctx.count_real_roots_dev(d_r.data_ptr(), d_o.data_ptr(), 40, 1, d_n.data_ptr(), d_cnt.data_ptr())
+    ctx.count_real_roots_dev(d_r.data_ptr(), d_o.data_ptr(), 40, 0, d_n.data_ptr(), d_cnt.data_ptr())
     torch.cuda.synchronize()
     ctx.set_stream(None)
     cnt = d_cnt.cpu().numpy().reshape(40, 3)
@@ -602,6 +627,12 @@ def test_gpu_full_size_c5_properties(A, ctx, oracle):
         assert np.all(np.diff(g.real) >= 0)
     worst = max(horner_backward_error(rows[p], got[p]).max() for p in range(0, B, 8))
     assert worst < 1e-9, worst
+    # two of them root by root against the oracle, at the only size where 128 bulges per fat step run on degree 10 000
+    K = 2
+    flat = np.concatenate(rows[:K]); off = np.arange(K + 1, dtype=np.int64) * (n + 1)
+    out, roff, nr, _ = oracle.roots_csr(flat, off)
+    want = [out[roff[p]:roff[p] + nr[p]] for p in range(K)]
+    check_parity(rows[:K], got[:K], want, C=C_RDS)
 
 
 def test_gpu_chain_more_polynomials_than_resident_ctas(A, ctx, oracle):
@@ -674,3 +705,122 @@ def test_gpu_css_pipelined_vs_sequential_multishift(A, oracle, L, reuse, small):
         assert abs(c.last_stats["turnovers"] - tot["turnovers"]) <= 0.02 * tot["turnovers"]
     finally:
         c.close()
+
+
+# ------------------------------------------------------------------ round 2: the gaps VERDICT r01 named
+def test_gpu_empty_vector_in_the_middle_of_a_batch(A, ctx, ctx_ref, oracle):
+    """roots(S[]) = S[] (test/test-roots.jl:18-27) inside a batch: an empty coefficient vector owns no root
+    slot, so it must not shift its neighbours' results (slot offsets[p] - p overlapped)."""
+    for c in (ctx, ctx_ref):
+        for cx in (False, True):
+            q5 = (p5 + 0j) if cx else p5
+            q4 = (p4 + 0j) if cx else p4
+            empty = np.zeros(0, dtype=q5.dtype)
+            for seq in ([q5, empty, q5], [empty, q5], [q5, empty], [empty, empty, q4, empty, q5, empty]):
+                got = A.roots(seq, ctx=c)
+                for a, g in zip(seq, got):
+                    if len(a) == 0:
+                        assert len(g) == 0
+                    else:
+                        assert np.allclose(g.real, np.arange(1, len(a)), rtol=1e-9, atol=0) and np.all(np.abs(g.imag) <= 1e-9), (seq, g)
+    rows = batch(oracle, 21, 6, 60)
+    seq = [rows[0], np.zeros(0), rows[1], np.zeros(0), np.zeros(0), rows[2], np.zeros(1), rows[3], rows[4], np.zeros(0), rows[5]]
+    got = A.roots(seq, ctx=ctx)
+    alone = A.roots(rows, ctx=ctx)
+    k = 0
+    for a, g in zip(seq, got):
+        if len(a) > 1:
+            assert np.array_equal(g, alone[k])       # same kernels, same per-polynomial work: the neighbours change nothing
+            k += 1
+        else:
+            assert len(g) == 0
+    vs, ws = A.basic_pencil(p5)
+    gp = A.roots([vs, np.zeros(0), vs], [ws, np.zeros(0), ws], ctx=ctx)
+    assert len(gp[1]) == 0 and np.allclose(gp[0].real, [1, 2, 3, 4, 5]) and np.allclose(gp[2].real, [1, 2, 3, 4, 5])
+
+
+def test_gpu_chain_regime_c2_split_over_8_gpus(A, ctx, oracle):
+    """The north-star split: 3000 polynomials of degree 3000 over 8 GPUs = 375 per GPU, the regime where the
+    automatic choice is chained warps (128 bulges per fat step).  One GPU's share through the default path:
+    nothing unconverged, exact conjugate pairs, and 16 polynomials root by root against the oracle."""
+    n, B = 3000, 375
+    rows = batch(oracle, 2, B, n)
+    got = A.roots(rows, ctx=ctx)
+    assert ctx.last_stats["unconverged"] == 0 and ctx.last_stats["lanes"] >= 64
+    for g in got[::25]:
+        pos = np.sort_complex(g[g.imag > 0]); neg = np.sort_complex(np.conj(g[g.imag < 0]))
+        assert len(g) == n and np.array_equal(pos, neg)
+    sel = list(range(0, B, 24))[:16]
+    flat = np.concatenate([rows[p] for p in sel]); off = np.arange(len(sel) + 1, dtype=np.int64) * (n + 1)
+    out, roff, nr, _ = oracle.roots_csr(flat, off)
+    want = [out[roff[i]:roff[i] + nr[i]] for i in range(len(sel))]
+    check_parity([rows[p] for p in sel], [got[p] for p in sel], want, C=C_RDS)
+
+
+@pytest.mark.parametrize("n,B", [(60, 24), (300, 6)])
+def test_gpu_complex_pencil_random_parity(A, ctx, oracle, n, B):
+    """roots(vs, ws) for ComplexF64 (pencil.jl:63-80 with the complex single shift) on random inputs against the
+    oracle: basic_pencil and a mid split of random complex polynomials (the reference tests only known answers)."""
+    rows = batch(oracle, 23, B, n, kind=1, cx=True)
+    for split in ("basic", "mid"):
+        pairs = [A.basic_pencil(r) if split == "basic" else pencil_split(r, n // 2) for r in rows]
+        got = A.roots([v for v, _ in pairs], [w for _, w in pairs], ctx=ctx)
+        want = [oracle.roots(v, ws=w)[0] for v, w in pairs]
+        check_parity(rows, got, want, C=256.0, real_counts=False)
+
+
+def test_gpu_reference_constants_as_options(A, oracle):
+    """IT_COUNT, it_max = 20 n and tol = eps are options of the context (create-bulge.jl:9, AMRVW_algorithm.jl:25,184)
+    with the reference's values as defaults; non-convergence is not an error: missing roots stay 0 and are counted."""
+    rows = batch(oracle, 31, 8, 80)
+    base = A.Context(seed=0, schedule=A.SCHEDULE_REFERENCE)
+    try:
+        ref = A.roots(rows, ctx=base)
+        explicit = A.Context(seed=0, schedule=A.SCHEDULE_REFERENCE, it_count=15, it_max_factor=20, tol=np.finfo(float).eps)
+        same = A.roots(rows, ctx=explicit)
+        assert all(np.array_equal(a, b) for a, b in zip(ref, same))      # the defaults ARE the reference's constants
+        explicit.close()
+        capped = A.Context(seed=0, schedule=A.SCHEDULE_REFERENCE, it_max_factor=1)
+        out, roff, nr, nunc = capped.roots_csr(np.concatenate(rows), np.arange(9, dtype=np.int64) * 81)
+        assert np.all(nunc > 0) and capped.last_stats["unconverged"] == int(nunc.sum())       # AMRVW_algorithm.jl:23-30
+        for p in range(8):
+            g = out[roff[p]:roff[p] + nr[p]]
+            assert np.sum(g == 0) >= nunc[p]
+        capped.close()
+        loose = A.Context(seed=0, schedule=A.SCHEDULE_REFERENCE, tol=1e-9)
+        got = A.roots(rows, ctx=loose)
+        for g, w in zip(got, ref):
+            d, _ = match_roots(g, w)
+            assert d.max() < 1e-5
+        st_loose = dict(loose.last_stats)
+        loose.close()
+        A.roots(rows, ctx=base)
+        assert st_loose["turnovers"] <= base.last_stats["turnovers"]       # earlier deflation: no more work than with eps
+        eager = A.Context(seed=0, schedule=A.SCHEDULE_REFERENCE, it_count=2)
+        got = A.roots(rows, ctx=eager)
+        assert eager.last_stats["exceptional"] > 0 and eager.last_stats["unconverged"] == 0      # create-bulge.jl:25-37 taken often
+        for r, g in zip(rows, got):
+            assert horner_backward_error(r, g).max() < 1e-11
+        eager.close()
+        piped = A.Context(seed=0, it_max_factor=1)                      # the unit schedule honours the cap too
+        out, roff, nr, nunc = piped.roots_csr(np.concatenate(rows), np.arange(9, dtype=np.int64) * 81)
+        assert piped.last_stats["unconverged"] == int(nunc.sum())
+        piped.close()
+        with pytest.raises(A.AmrvwError):
+            A.Context(seed=0, tol=0.5)
+    finally:
+        base.close()
+
+
+def test_gpu_count_real_roots_host_entry(A, ctx, oracle):
+    """real_polynomial_roots for a batch with host buffers (complex_conjugate_root_theorem.jl:32-54, README.md:121-127):
+    only 12 bytes per polynomial come back; the counts equal those of the roots call and of the oracle."""
+    rows = batch(oracle, 8, 60, 150)
+    flat = np.concatenate(rows); off = np.arange(61, dtype=np.int64) * 151
+    counts, nunc = ctx.count_real_roots_csr(flat, off)
+    got = A.roots(rows, ctx=ctx)
+    assert np.all(nunc == 0)
+    for p, r in enumerate(rows):
+        w, _ = oracle.roots(r)
+        assert counts[p, 0] == np.sum(got[p].imag == 0) == np.sum(w.imag == 0)
+        assert counts[p, 1] == counts[p, 2] == np.sum(w.imag > 0) and counts[p].sum() == 150

@@ -1,5 +1,5 @@
 """Development probe: a ragged batch (degrees uniform in [lo, hi]) through the C ABI, device time of the call.
-usage: ragged_bench.py kind B lo hi   (kind: rds | css | pencil);  AMRVW_NO_ORDER=1 forms units in batch order"""
+usage: ragged_bench.py kind B lo hi   (kind: rds | css | pencil)"""
 import sys, os, time
 import numpy as np
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
@@ -25,5 +25,5 @@ for rep in range(3):
     else:
         got = A.roots(rows, ctx=ctx)
     best = min(best, ctx.last_stats["device_ms"])
-print(kind, "B", B, "degrees", lo, hi, "order", "batch" if os.environ.get("AMRVW_NO_ORDER") else "by degree", "device ms %.1f" % best, "lanes", ctx.last_stats["lanes"],
+print(kind, "B", B, "degrees", lo, hi, "device ms %.1f" % best, "lanes", ctx.last_stats["lanes"],
       "unconverged", ctx.last_stats["unconverged"], "sum|roots| %.6f" % sum(float(np.abs(g).sum()) for g in got))
