@@ -19,13 +19,13 @@ class Options(ctypes.Structure):
 class Stats(ctypes.Structure):
     _fields_ = [("turnovers", ctypes.c_int64), ("sweeps", ctypes.c_int64), ("exceptional", ctypes.c_int64),
                 ("unconverged", ctypes.c_int64), ("fat_steps", ctypes.c_int64), ("launches", ctypes.c_int64),
-                ("device_ms", ctypes.c_double), ("lanes", ctypes.c_int64)]
+                ("device_ms", ctypes.c_double), ("lanes", ctypes.c_int64), ("schedule_used", ctypes.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
-SCHEDULE_AUTO, SCHEDULE_REFERENCE, SCHEDULE_PIPELINED = 0, 1, 2
+SCHEDULE_AUTO, SCHEDULE_REFERENCE, SCHEDULE_PIPELINED, SCHEDULE_STREAMED = 0, 1, 2, 3
 SHIFTS_AUTO, SHIFTS_CHASE, SHIFTS_DENSE = 0, 1, 2
 
 _P = ctypes.c_void_p

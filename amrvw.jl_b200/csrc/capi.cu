@@ -6,6 +6,7 @@
 #include "pipeline.cuh"
 #include "rounds.cuh"
 #include "chain.cuh"
+#include "stream.cuh"
 #include "css_units.cuh"
 #include "pencil_units.cuh"
 
@@ -32,7 +33,7 @@ struct amrvw_ctx {
     amrvw_options opt;
     std::string err;
     // grow-only device buffers
-    DevBuf chains[5], diags[3], coeffs, coeffs2, offsets, roots, nroots, nunconv, stats, shifts, state, prof, rec, fatshifts, swlist, counters, queue, qslots, park, parked, order, orderkeys, counts;
+    DevBuf chains[5], diags[3], coeffs, coeffs2, offsets, roots, nroots, nunconv, stats, shifts, state, prof, rec, fatshifts, swlist, counters, queue, qslots, park, parked, order, orderkeys, counts, squeues, sslots;
     bool queue_used = false;
     cudaEvent_t evpool[32] = {};
     RoundsTimes times = {};
@@ -149,7 +150,7 @@ int amrvw_destroy(amrvw_ctx* ctx) {
     cudaSetDevice(ctx->device);
     DevBuf* all[] = {&ctx->chains[0], &ctx->chains[1], &ctx->chains[2], &ctx->chains[3], &ctx->chains[4], &ctx->diags[0], &ctx->diags[1], &ctx->diags[2],
                      &ctx->coeffs, &ctx->coeffs2, &ctx->offsets, &ctx->roots, &ctx->nroots, &ctx->nunconv, &ctx->stats, &ctx->shifts, &ctx->state, &ctx->prof,
-                     &ctx->rec, &ctx->fatshifts, &ctx->swlist, &ctx->counters, &ctx->queue, &ctx->qslots, &ctx->park, &ctx->parked, &ctx->order, &ctx->orderkeys, &ctx->counts};
+                     &ctx->rec, &ctx->fatshifts, &ctx->swlist, &ctx->counters, &ctx->queue, &ctx->qslots, &ctx->park, &ctx->parked, &ctx->order, &ctx->orderkeys, &ctx->counts, &ctx->squeues, &ctx->sslots};
     for (DevBuf* b : all) if (b->ptr) cudaFree(b->ptr);
     for (cudaEvent_t e : ctx->evpool) if (e) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -169,11 +170,10 @@ extern "C" {
 
 int amrvw_set_options(amrvw_ctx* ctx, const amrvw_options* opt) {
     if (!ctx || !opt) return AMRVW_ERR_ARGUMENT;
-    if (opt->schedule < 0 || opt->schedule > 2) return fail(ctx, AMRVW_ERR_ARGUMENT, "schedule must be 0, 1 or 2");
+    if (opt->schedule < 0 || opt->schedule > 3) return fail(ctx, AMRVW_ERR_ARGUMENT, "schedule must be 0, 1, 2 or 3");
     const int L = opt->lanes_per_poly;
     if (!(L == 0 || L == 4 || L == 8 || L == 16 || L == 32 || L == 64 || L == 128 || L == 256)) return fail(ctx, AMRVW_ERR_ARGUMENT, "lanes_per_poly must be 0, 4, 8, 16, 32, 64, 128 or 256");
-    if (!(opt->shift_reuse == 0 || opt->shift_reuse == 1 || opt->shift_reuse == 2 || opt->shift_reuse == 4 || opt->shift_reuse == 8))
-        return fail(ctx, AMRVW_ERR_ARGUMENT, "shift_reuse must be 0, 1, 2, 4 or 8");
+    if (opt->shift_reuse < 0 || opt->shift_reuse > 16) return fail(ctx, AMRVW_ERR_ARGUMENT, "shift_reuse must be 0 (auto) or 1..16");
     if (opt->small_window < 0) return fail(ctx, AMRVW_ERR_ARGUMENT, "small_window must be >= 0");
     if (opt->shift_solver < 0 || opt->shift_solver > 2) return fail(ctx, AMRVW_ERR_ARGUMENT, "shift_solver must be 0, 1 or 2");
     if (opt->it_count < 0 || opt->it_max_factor < 0) return fail(ctx, AMRVW_ERR_ARGUMENT, "it_count and it_max_factor must be >= 0 (0 = the reference's 15 and 20)");
@@ -306,7 +306,7 @@ static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, cons
         if ((rc = reserve(ctx, ctx->orderkeys, (size_t)nbatch * sizeof(unsigned long long)))) return rc;
         pr.order = (const int*)ctx->order.ptr;
     }
-    int launches = 0, lanes = 0;
+    int launches = 0, lanes = 0, sched_used = AMRVW_SCHEDULE_REFERENCE;
     ctx->times = RoundsTimes{0.f, 0.f, 0.f, 0.f};
     ctx->prof_valid = (var != V_PENCIL_C && stats != nullptr);
     ctx->queue_used = false;
@@ -324,18 +324,28 @@ static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, cons
             choose_css_params(ctx->opt, nbatch, (int)max_len, ctx->sm_count, L, pp); lane_bytes = sizeof(CssLane);
         }
         if ((rc = reserve_unit_workspace(ctx, nbatch, total, L, lane_bytes, &qcap))) return rc;
+        StreamBufs sbuf = {nullptr, nullptr, nullptr, nullptr, 0u, nullptr};
+        if (var == V_RDS && pp.stream) {     // two device-wide queues of polynomial ids + the count of iterating polynomials
+            size_t cap = 1024;
+            while (cap < (size_t)nbatch + 64) cap <<= 1;
+            if ((rc = reserve(ctx, ctx->squeues, 2 * sizeof(MpmcQueue) + 64))) return rc;
+            if ((rc = reserve(ctx, ctx->sslots, 2 * cap * sizeof(MpmcSlot)))) return rc;
+            sbuf.ready = (MpmcQueue*)ctx->squeues.ptr; sbuf.work = sbuf.ready + 1; sbuf.remaining = (unsigned*)(sbuf.work + 1);
+            sbuf.ready_slots = (MpmcSlot*)ctx->sslots.ptr; sbuf.work_slots = sbuf.ready_slots + cap; sbuf.mask = (unsigned)(cap - 1);
+        }
         QueueBufs qb;
         qb.q = (RoundQueue*)ctx->queue.ptr; qb.slots = (int*)ctx->qslots.ptr; qb.mask = qcap ? (unsigned)(qcap - 1) : 0u;
         qb.park = (UnitPark*)ctx->park.ptr; qb.parked = nullptr;
         pr.rec = (PolyRec*)ctx->rec.ptr; pr.shifts = (Shifts*)ctx->fatshifts.ptr; pr.swlist = ctx->swlist.ptr; pr.counters = (unsigned*)ctx->counters.ptr;
-        ctx->queue_used = qcap != 0;
+        ctx->queue_used = qcap != 0 || sbuf.ready != nullptr;
+        sched_used = sbuf.ready ? AMRVW_SCHEDULE_STREAMED : AMRVW_SCHEDULE_PIPELINED;
         cudaError_t e = cudaSuccess;
         const char* what = "";
         if constexpr (is_real<S>::value) {
             if (var == V_RDS) {
                 what = "unit schedule: ";
                 qb.parked = (StepState*)ctx->parked.ptr;
-                e = launch_rounds_rds(pr, ctx->opt, (int)max_len, (long long)total, ctx->sm_count, st, &launches, ctx->evpool, stats ? &ctx->times : nullptr, qb, &lanes, (unsigned long long*)ctx->orderkeys.ptr);
+                e = launch_rounds_rds(pr, ctx->opt, (int)max_len, (long long)total, ctx->sm_count, st, &launches, ctx->evpool, stats ? &ctx->times : nullptr, qb, &lanes, (unsigned long long*)ctx->orderkeys.ptr, sbuf.ready ? &sbuf : nullptr);
             } else {
                 what = "pencil unit schedule: ";
                 e = launch_pencil_pipelined(pr, ctx->opt, (int)max_len, (long long)total, ctx->sm_count, st, &launches, qb, (PenLane*)ctx->parked.ptr, ctx->evpool, stats ? &ctx->times : nullptr, &lanes, (unsigned long long*)ctx->orderkeys.ptr);
@@ -369,7 +379,7 @@ static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, cons
         CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
         stats->turnovers = h.turnovers; stats->sweeps = h.sweeps; stats->exceptional = h.exceptional;
         stats->unconverged = h.unconverged; stats->fat_steps = h.fat_steps;
-        stats->launches = launches; stats->device_ms = ms; stats->lanes = lanes;
+        stats->launches = launches; stats->device_ms = ms; stats->lanes = lanes; stats->schedule_used = sched_used;
         const int rc = check_queue_abort(ctx);     // the stream is idle here: one 4-byte read
         if (rc) return rc;
     }
@@ -495,6 +505,7 @@ static int run_host(amrvw_ctx* ctx, Variant var, const S* a, const S* w, const i
             stats->fat_steps += x.fat_steps; stats->launches += x.launches;
             if (x.device_ms > stats->device_ms) stats->device_ms = x.device_ms;    // the devices run side by side
             if (x.lanes > stats->lanes) stats->lanes = x.lanes;
+            if (x.schedule_used > stats->schedule_used) stats->schedule_used = x.schedule_used;
         }
     }
     return AMRVW_OK;

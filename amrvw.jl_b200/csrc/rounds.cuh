@@ -601,7 +601,15 @@ static void choose_pipe_params(const amrvw_options& opt, long long nbatch, int m
         if (degree >= 1200 && nbatch * 32 <= (long long)sm_count * 410) L = 32;
         if (L == 32 && degree >= 2500 && nbatch <= (long long)sm_count * 3) L = 128;
     }
-    pp.reuse = opt.shift_reuse ? opt.shift_reuse : (L == 32 ? 4 : 2);   // 32 lanes: 16 shifts x 4 beat 32 x 2 by 4-8% (gpurun_out/sweep63.log)
+    // chained warps: one CTA per polynomial (chain.cuh) while there are fewer polynomials than SMs can hold two of;
+    // above that the CTAs take the fat steps of all polynomials as one stream (stream.cuh): no fill/drain, phase A hidden
+    pp.stream = 0;
+    if (opt.schedule == AMRVW_SCHEDULE_STREAMED && L != 64) L = 128;
+    if (L == 128 || L == 64) {
+        if (opt.schedule == AMRVW_SCHEDULE_STREAMED) pp.stream = 1;
+        else if (opt.schedule == AMRVW_SCHEDULE_AUTO && opt.lanes_per_poly == 0 && nbatch >= (long long)sm_count * 2 + sm_count / 4) pp.stream = 1;
+    }
+    pp.reuse = opt.shift_reuse ? opt.shift_reuse : (L == 32 ? 4 : (pp.stream ? 8 : 2));   // 32 lanes: 16 shifts x 4 beat 32 x 2 by 4-8% (gpurun_out/sweep63.log)
     if (pp.reuse > L / 2) pp.reuse = L / 2 > 0 ? L / 2 : 1;
     while (2 * L / pp.reuse > 64) pp.reuse *= 2;     // the largest dense trailing block is 64 x 64
     const int mshift = 2 * L / pp.reuse;
@@ -641,6 +649,9 @@ static cudaError_t launch_units_mh(const Problem<double>& pr, const PipeParams& 
 
 // chain.cuh: one CTA of NW chained warps per polynomial (small batches of large polynomials)
 template <int NW, int MH> static cudaError_t launch_chain(const Problem<double>& pr, const PipeParams& pp, int sm_count, cudaStream_t st);
+// stream.cuh: chained warps fed by a stream of fat steps of different polynomials
+struct StreamBufs;
+template <int NW, int MH> static cudaError_t launch_stream(const Problem<double>& pr, const PipeParams& pp, const StreamBufs& sb, int sm_count, cudaStream_t st);
 
 // Queues the whole schedule on `st`: set-up, the persistent unit kernel, small windows, finish.
 // Nothing here waits for the device unless `times` is asked for.
@@ -655,7 +666,7 @@ static cudaError_t read_round_times(cudaEvent_t* ev, RoundsTimes* times, cudaStr
     return cudaSuccess;
 }
 static cudaError_t launch_rounds_rds(Problem<double> pr, const amrvw_options& opt, int max_len, long long total, int sm_count, cudaStream_t st, int* launches, cudaEvent_t* ev,
-                                     RoundsTimes* times, const QueueBufs& qb, int* lanes_out = nullptr, unsigned long long* order_keys = nullptr) {
+                                     RoundsTimes* times, const QueueBufs& qb, int* lanes_out = nullptr, unsigned long long* order_keys = nullptr, const StreamBufs* sb = nullptr) {
     int L; PipeParams pp;
     choose_pipe_params(opt, pr.nbatch, max_len, sm_count, L, pp);
     if (lanes_out) *lanes_out = L;
@@ -678,8 +689,14 @@ static cudaError_t launch_rounds_rds(Problem<double> pr, const amrvw_options& op
         case 4: e = launch_units_mh<4>(pr, pp, qb, seg_steps, sm_count, st); break;
         case 8: e = launch_units_mh<8>(pr, pp, qb, seg_steps, sm_count, st); break;
         case 16: e = launch_units_mh<16>(pr, pp, qb, seg_steps, sm_count, st); break;
-        case 64: e = pp.mh <= 32 ? launch_chain<2, 32>(pr, pp, sm_count, st) : launch_chain<2, 64>(pr, pp, sm_count, st); break;
-        case 128: e = pp.mh <= 32 ? launch_chain<4, 32>(pr, pp, sm_count, st) : launch_chain<4, 64>(pr, pp, sm_count, st); break;
+        case 64:
+            if (pp.stream && sb) e = pp.mh <= 32 ? launch_stream<2, 32>(pr, pp, *sb, sm_count, st) : launch_stream<2, 64>(pr, pp, *sb, sm_count, st);
+            else e = pp.mh <= 32 ? launch_chain<2, 32>(pr, pp, sm_count, st) : launch_chain<2, 64>(pr, pp, sm_count, st);
+            break;
+        case 128:
+            if (pp.stream && sb) e = pp.mh <= 32 ? launch_stream<4, 32>(pr, pp, *sb, sm_count, st) : launch_stream<4, 64>(pr, pp, *sb, sm_count, st);
+            else e = pp.mh <= 32 ? launch_chain<4, 32>(pr, pp, sm_count, st) : launch_chain<4, 64>(pr, pp, sm_count, st);
+            break;
         case 256: e = launch_chain<8, 64>(pr, pp, sm_count, st); break;
         default: e = launch_units_mh<32>(pr, pp, qb, seg_steps, sm_count, st); break;
     }
@@ -700,7 +717,7 @@ static cudaError_t launch_rounds_rds(Problem<double> pr, const amrvw_options& op
         rounds_finish_kernel<double><<<(int)pr.nbatch, 256, smem, st>>>(pr, smem_elems);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
-    *launches += L > 32 ? 4 : 5;
+    *launches += L > 32 ? (pp.stream && sb ? 6 : 4) : 5;
     if (times) return read_round_times(ev, times, st);
     return cudaSuccess;
 }

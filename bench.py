@@ -358,7 +358,8 @@ def main():
     lanes = int(st.get("lanes", 0))
     if prof and prof["us_main"] > 0:
         kernel_ms = prof["us_main"] / 1e3
-        kernel_name = {"rds_f64": f"chain_kernel<{lanes // 32},MH> (one CTA of {lanes // 32} chained warps per polynomial: phase A + systolic chase of {lanes} bulges)" if lanes > 32
+        kernel_name = {"rds_f64": (f"stream_kernel<{lanes // 32},MH> ({lanes // 32} chained warps per CTA fed by a stream of fat steps of different polynomials, {lanes} bulges each; phase A on service warps)" if st.get("schedule_used") == 3
+                                   else f"chain_kernel<{lanes // 32},MH> (one CTA of {lanes // 32} chained warps per polynomial: phase A + systolic chase of {lanes} bulges)") if lanes > 32
                        else f"unit_kernel<{lanes},MH> (phase A + systolic chase behind the unit queue)",
                        "css_c64": f"css_unit_kernel<{lanes},MH> (complex single shift: phase A + systolic chase behind the unit queue)",
                        "pencil_f64": f"pen_unit_kernel<{lanes},MH> (companion pencil, five chains: phase A + systolic chase behind the unit queue)"}[kind]
@@ -401,7 +402,7 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config, "turnovers_per_sec": (useful_per_poly * total_batch / (ms_step * 1e-3)) if useful_per_poly else None, "roofline": roofline, "cpu_baseline": cb, "e2e": e2e,
             "gpu_launches": int(st["launches"] * args.steps), "gpu_launches_are": "this rank's kernels inside the timed region", "clocks": clk.summary(),
-            "stats_per_step": {k: st[k] for k in ("turnovers", "sweeps", "exceptional", "unconverged", "fat_steps", "launches", "lanes")},
+            "stats_per_step": {k: st[k] for k in ("turnovers", "sweeps", "exceptional", "unconverged", "fat_steps", "launches", "lanes", "schedule_used")},
             "unconverged": n_unconv, "roots_found": nroots_ok}
     print(json.dumps(line))
     if world > 1:

@@ -50,7 +50,10 @@ enum amrvw_schedule {
     AMRVW_SCHEDULE_AUTO = 0,       /* pipelined multishift for Float64 RDS, one-bulge otherwise */
     AMRVW_SCHEDULE_REFERENCE = 1,  /* one bulge at a time, shifts from the trailing 2x2 block: the
                                       reference's own order of operations (bulge-step.jl:11-19)    */
-    AMRVW_SCHEDULE_PIPELINED = 2   /* several bulges in flight per polynomial, three indices apart */
+    AMRVW_SCHEDULE_PIPELINED = 2,  /* several bulges in flight per polynomial, three indices apart */
+    AMRVW_SCHEDULE_STREAMED = 3    /* rds_f64 with 64 or 128 lanes_per_poly (0 = 128): chained warps that take the fat steps of
+                                      all polynomials as one stream -- no fill/drain between fat steps, shifts computed by
+                                      service warps meanwhile; AUTO picks it for batches of a few hundred large polynomials */
 };
 
 /* Where the 2L/reuse shifts of a pipelined fat step come from (no reference counterpart: the
@@ -88,6 +91,7 @@ typedef struct amrvw_stats {
     int64_t launches;      /* kernels launched by this call */
     double device_ms;      /* CUDA-event time of the kernels of this call */
     int64_t lanes;         /* bulges in flight per polynomial chosen for this call (0: one-bulge schedule) */
+    int64_t schedule_used; /* amrvw_schedule that ran: 1 one-bulge, 2 pipelined (unit queue or chained warps), 3 streamed */
 } amrvw_stats;
 
 /* device < 0: current device. */

@@ -824,3 +824,49 @@ def test_gpu_count_real_roots_host_entry(A, ctx, oracle):
         w, _ = oracle.roots(r)
         assert counts[p, 0] == np.sum(got[p].imag == 0) == np.sum(w.imag == 0)
         assert counts[p, 1] == counts[p, 2] == np.sum(w.imag > 0) and counts[p].sum() == 150
+
+
+@pytest.mark.parametrize("L,reuse,small,dense", [(128, 8, 40, 1), (128, 4, 72, 1), (64, 4, 40, 1), (128, 8, 40, 0)])
+def test_gpu_stream_bitwise_vs_sequential_multishift(A, oracle, L, reuse, small, dense):
+    """stream.cuh: chained warps fed by a stream of fat steps of different polynomials -- bulges created one lock-step
+    early, the last chase step split over two lock-steps, jobs of several polynomials in the array at once, polynomials
+    migrating between CTAs, phase A on service warps.  Per polynomial the operations and their order are unchanged, so
+    without FMA contraction the roots must agree bit for bit with the oracle's sequential multishift schedule at the
+    same L, whatever the interleaving (more polynomials than CTAs, windows shorter and longer than 3 L)."""
+    c = A.Context(seed=0, strict=True, schedule=A.SCHEDULE_STREAMED, lanes_per_poly=L, shift_reuse=reuse, small_window=small,
+                  shift_solver=A.SHIFTS_DENSE if dense else A.SHIFTS_CHASE)
+    try:
+        rows = batch(oracle, 31, 40, 150) + batch(oracle, 32, 30, 700) + batch(oracle, 35, 6, 1300) + [p4, p6, np.zeros(0), np.array([1.0, 2.0, 1.0])]
+        flat = np.concatenate(rows); off = np.zeros(len(rows) + 1, dtype=np.int64); np.cumsum([len(r) for r in rows], out=off[1:])
+        out, roff, nr, tot, pp = oracle.roots_csr(flat, off, sched=1, L=L, small=small, reuse=reuse, dense=dense, per_poly=True)
+        for rep in range(2):       # twice: the interleaving differs from run to run, the roots must not
+            got = A.roots(rows, ctx=c)
+            assert c.last_stats["lanes"] == L
+            n_checked = 0
+            for p, g in enumerate(got):
+                if pp[p]["exceptional"]:
+                    continue
+                w = out[roff[p]:roff[p] + nr[p]]
+                assert np.array_equal(g.view(np.float64), w.view(np.float64)), f"polynomial {p} (degree {len(rows[p]) - 1}) differs"
+                n_checked += 1
+            assert n_checked >= 70
+            if not any(x["exceptional"] for x in pp):
+                assert c.last_stats["fat_steps"] == tot["fat_steps"] and c.last_stats["turnovers"] == tot["turnovers"]
+    finally:
+        c.close()
+
+
+def test_gpu_stream_parity_and_auto_choice(A, ctx, oracle):
+    """Product build of the streamed kernel (the automatic choice for a few hundred large polynomials, e.g. one GPU's
+    share of config 2 split over 8) against the oracle's reference schedule on a mixed batch."""
+    c = A.Context(seed=0, schedule=A.SCHEDULE_STREAMED)
+    try:
+        rows = batch(oracle, 5, 6, 1500, kind=2) + batch(oracle, 2, 10, 900) + batch(oracle, 7, 30, 200)
+        flat = np.concatenate(rows); off = np.zeros(len(rows) + 1, dtype=np.int64); np.cumsum([len(r) for r in rows], out=off[1:])
+        out, roff, nr, _ = oracle.roots_csr(flat, off)
+        want = [out[roff[p]:roff[p] + nr[p]] for p in range(len(rows))]
+        got = A.roots(rows, ctx=c)
+        check_parity(rows, got, want, C=C_RDS)
+        assert c.last_stats["unconverged"] == 0 and c.last_stats["fat_steps"] > 0 and c.last_stats["lanes"] == 128
+    finally:
+        c.close()
