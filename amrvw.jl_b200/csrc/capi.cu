@@ -46,6 +46,7 @@ struct amrvw_ctx {
 
 static int fail(amrvw_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg;
+    if (code == AMRVW_ERR_CUDA) (void)cudaGetLastError();   // reported: do not leave it behind for the next call's launch check
     return code;
 }
 #define CUDA_TRY(ctx, call)                                                                     \
@@ -233,14 +234,14 @@ static int check_queue_abort(amrvw_ctx* ctx) {
 
 // workspace of the unit schedules: records, shifts, small-window list, counters; queue and parking sized by the
 // number of units the chosen lane count really gives (L lanes per polynomial -> 32/L polynomials per unit)
-static int reserve_unit_workspace(amrvw_ctx* ctx, int64_t nbatch, int64_t total, int L, size_t lane_bytes, size_t* qcap_out) {
+static int reserve_unit_workspace(amrvw_ctx* ctx, int64_t nbatch, int64_t total, int L, size_t lane_bytes, bool streamed, size_t* qcap_out) {
     int rc;
     if ((rc = reserve(ctx, ctx->rec, (size_t)nbatch * sizeof(PolyRec)))) return rc;
     if ((rc = reserve(ctx, ctx->fatshifts, (size_t)nbatch * (size_t)(L < 4 ? 4 : L) * sizeof(Shifts)))) return rc;
     if ((rc = reserve(ctx, ctx->swlist, ((size_t)total / 3 + (size_t)nbatch + 16) * sizeof(SmallWin)))) return rc;
     if ((rc = reserve(ctx, ctx->counters, CNT_WORDS * sizeof(unsigned)))) return rc;
     *qcap_out = 0;
-    if (L > 32) return 0;     // chained warps: no queue, nothing is parked
+    if (L > 32 || streamed) return 0;     // chained warps and streams: no unit queue, nothing is parked
     const size_t G = (size_t)(32 / L);
     const size_t nunits = ((size_t)nbatch + G - 1) / G;
     size_t qcap = 1024;
@@ -263,6 +264,7 @@ static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, cons
     if (nbatch == 0) return AMRVW_OK;
     if (!d_a || !d_offsets || !d_roots || !d_nroots || !d_nunconv) return fail(ctx, AMRVW_ERR_ARGUMENT, "null buffer");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    (void)cudaGetLastError();      // a stale error of someone else's earlier call must not fail this call's launch checks
     const bool pencil = (var == V_PENCIL_R || var == V_PENCIL_C);
     if (pencil && !d_w) return fail(ctx, AMRVW_ERR_ARGUMENT, "null ws buffer");
     const int extra = pencil ? 2 : 1;
@@ -323,7 +325,7 @@ static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, cons
         } else {
             choose_css_params(ctx->opt, nbatch, (int)max_len, ctx->sm_count, L, pp); lane_bytes = sizeof(CssLane);
         }
-        if ((rc = reserve_unit_workspace(ctx, nbatch, total, L, lane_bytes, &qcap))) return rc;
+        if ((rc = reserve_unit_workspace(ctx, nbatch, total, L, lane_bytes, var == V_RDS && pp.stream, &qcap))) return rc;
         StreamBufs sbuf = {nullptr, nullptr, nullptr, nullptr, 0u, nullptr};
         if (var == V_RDS && pp.stream) {     // two device-wide queues of polynomial ids + the count of iterating polynomials
             size_t cap = 1024;

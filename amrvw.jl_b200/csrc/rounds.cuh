@@ -604,12 +604,13 @@ static void choose_pipe_params(const amrvw_options& opt, long long nbatch, int m
     // chained warps: one CTA per polynomial (chain.cuh) while there are fewer polynomials than SMs can hold two of;
     // above that the CTAs take the fat steps of all polynomials as one stream (stream.cuh): no fill/drain, phase A hidden
     pp.stream = 0;
-    if (opt.schedule == AMRVW_SCHEDULE_STREAMED && L != 64) L = 128;
+    if (opt.schedule == AMRVW_SCHEDULE_STREAMED && opt.lanes_per_poly == 0) L = 128;
+    if (opt.schedule == AMRVW_SCHEDULE_STREAMED && (L == 16 || L == 32)) pp.stream = 1;     // sub-warp pipelines (stream.cuh, second half)
     if (L == 128 || L == 64) {
         if (opt.schedule == AMRVW_SCHEDULE_STREAMED) pp.stream = 1;
         else if (opt.schedule == AMRVW_SCHEDULE_AUTO && opt.lanes_per_poly == 0 && nbatch >= (long long)sm_count * 2 + sm_count / 4) pp.stream = 1;
     }
-    pp.reuse = opt.shift_reuse ? opt.shift_reuse : (L == 32 ? 4 : (pp.stream ? 8 : 2));   // 32 lanes: 16 shifts x 4 beat 32 x 2 by 4-8% (gpurun_out/sweep63.log)
+    pp.reuse = opt.shift_reuse ? opt.shift_reuse : (L == 32 ? 4 : (pp.stream && L >= 64 ? 8 : 2));   // 32 lanes: 16 shifts x 4 beat 32 x 2 by 4-8% (gpurun_out/sweep63.log)
     if (pp.reuse > L / 2) pp.reuse = L / 2 > 0 ? L / 2 : 1;
     while (2 * L / pp.reuse > 64) pp.reuse *= 2;     // the largest dense trailing block is 64 x 64
     const int mshift = 2 * L / pp.reuse;
@@ -652,6 +653,7 @@ template <int NW, int MH> static cudaError_t launch_chain(const Problem<double>&
 // stream.cuh: chained warps fed by a stream of fat steps of different polynomials
 struct StreamBufs;
 template <int NW, int MH> static cudaError_t launch_stream(const Problem<double>& pr, const PipeParams& pp, const StreamBufs& sb, int sm_count, cudaStream_t st);
+template <int L, int MH, int NW, int NS> static cudaError_t launch_ustream(const Problem<double>& pr, const PipeParams& pp, const StreamBufs& sb, int sm_count, cudaStream_t st);
 
 // Queues the whole schedule on `st`: set-up, the persistent unit kernel, small windows, finish.
 // Nothing here waits for the device unless `times` is asked for.
@@ -673,8 +675,10 @@ static cudaError_t launch_rounds_rds(Problem<double> pr, const amrvw_options& op
     cudaError_t e;
     const int nb64 = (int)((pr.nbatch + 63) / 64);
     if ((e = cudaMemsetAsync(pr.counters, 0, CNT_WORDS * sizeof(unsigned), st)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(qb.q, 0, sizeof(RoundQueue), st)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(qb.slots, 0xFF, (size_t)(qb.mask + 1) * sizeof(int), st)) != cudaSuccess) return e;
+    if (L <= 32) {    // the unit queue (chained warps have none)
+        if ((e = cudaMemsetAsync(qb.q, 0, sizeof(RoundQueue), st)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(qb.slots, 0xFF, (size_t)(qb.mask + 1) * sizeof(int), st)) != cudaSuccess) return e;
+    }
     const int seg_steps = 512;   // lock-steps a warp chases before it parks the unit and takes the next one (128: 549 ms, 512: 530 ms on config 2)
     if (times) cudaEventRecord(ev[0], st);
     rounds_setup_kernel<<<nb64, 64, 0, st>>>(pr);
@@ -688,7 +692,14 @@ static cudaError_t launch_rounds_rds(Problem<double> pr, const amrvw_options& op
     switch (L) {
         case 4: e = launch_units_mh<4>(pr, pp, qb, seg_steps, sm_count, st); break;
         case 8: e = launch_units_mh<8>(pr, pp, qb, seg_steps, sm_count, st); break;
-        case 16: e = launch_units_mh<16>(pr, pp, qb, seg_steps, sm_count, st); break;
+        case 16:
+            if (pp.stream && sb) e = pp.mh <= 16 ? launch_ustream<16, 16, 4, 1>(pr, pp, *sb, sm_count, st) : launch_ustream<16, 32, 4, 1>(pr, pp, *sb, sm_count, st);
+            else e = launch_units_mh<16>(pr, pp, qb, seg_steps, sm_count, st);
+            break;
+        case 32:
+            if (pp.stream && sb) e = pp.mh <= 16 ? launch_ustream<32, 16, 4, 1>(pr, pp, *sb, sm_count, st) : (pp.mh <= 32 ? launch_ustream<32, 32, 4, 1>(pr, pp, *sb, sm_count, st) : cudaErrorInvalidValue);
+            else e = launch_units_mh<32>(pr, pp, qb, seg_steps, sm_count, st);
+            break;
         case 64:
             if (pp.stream && sb) e = pp.mh <= 32 ? launch_stream<2, 32>(pr, pp, *sb, sm_count, st) : launch_stream<2, 64>(pr, pp, *sb, sm_count, st);
             else e = pp.mh <= 32 ? launch_chain<2, 32>(pr, pp, sm_count, st) : launch_chain<2, 64>(pr, pp, sm_count, st);
@@ -717,7 +728,7 @@ static cudaError_t launch_rounds_rds(Problem<double> pr, const amrvw_options& op
         rounds_finish_kernel<double><<<(int)pr.nbatch, 256, smem, st>>>(pr, smem_elems);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
-    *launches += L > 32 ? (pp.stream && sb ? 6 : 4) : 5;
+    *launches += (pp.stream && sb) ? 6 : (L > 32 ? 4 : 5);
     if (times) return read_round_times(ev, times, st);
     return cudaSuccess;
 }

@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(32 * (NW + 2), 2) stream_kernel(Problem<double
     }
 
     // ---------------- chase warps
-    double2* const snap_t = reinterpret_cast<double2*>(raw) + gl;
+    [[maybe_unused]] double2* const snap_t = reinterpret_cast<double2*>(raw) + gl;
     [[maybe_unused]] const unsigned snap_sa = (unsigned)__cvta_generic_to_shared(snap_t);
     const unsigned stage_sa = (unsigned)__cvta_generic_to_shared(sm.ring);
     const unsigned hand_sa = (unsigned)__cvta_generic_to_shared(&sm.hand[0][0][0]);
@@ -425,6 +425,281 @@ static cudaError_t launch_stream(const Problem<double>& pr, const PipeParams& pp
     const long long cap = (long long)sm_count * per_sm;
     const int blocks = (int)(pr.nbatch < cap ? pr.nbatch : cap);
     stream_kernel<NW, MH><<<blocks, 32 * (NW + 2), smem, st>>>(pr, pp, sq);
+    return cudaGetLastError();
+}
+
+
+// ================================================================ sub-warp pipelines (L <= 32 lanes per polynomial)
+// The same stream for large batches (config 2 on one GPU: 3000 polynomials, 16 bulges each): every group of L lanes
+// of a chase warp is an independent systolic array with its own stream of jobs -- no hand-off between warps, no CTA
+// barrier, each group steps with its warp.  What it removes from the unit schedule of rounds.cuh: the 3 L fill/drain
+// lock-steps of every fat step (lanes idle 9% of the lock-steps at 1.9x the cost of a lean one), the waiting of a
+// unit's shorter window for its longer one, parking (the bulges in flight never leave their registers), and phase A
+// inside the chase warps (service warps compute it while other jobs stream).  One manager warp per CTA, one lane
+// per pipeline.
+#define AMRVW_USTREAM_JOBS 8
+struct UPipe {
+    StreamJob jobs[AMRVW_USTREAM_JOBS];
+    double2 ring[3 * AMRVW_RING];
+    unsigned ringtag[AMRVW_RING];
+    volatile int jobs_tail, jobs_head, jobs_done, feed_left, no_more, quit;
+    int pad[2];
+};
+
+// manager warp: lane i serves pipeline i of the CTA
+template <int NP>
+AMRVW_DI void ustream_manager(const Problem<double>& pr, const StreamQueues& sq, UPipe* pipes, const int L) {
+    const int lane32 = threadIdx.x & 31;
+    if (lane32 >= NP) return;
+    UPipe& sm = pipes[lane32];
+    int mgr_done = 0;
+    unsigned long long wd_time = global_ns();
+    unsigned wd_progress = ld_volatile_u32(sq.progress), wd_polls = 0;
+    for (;;) {
+        bool worked = false;
+        if ((++wd_polls & 1023u) == 0u) {
+            const unsigned pg = ld_volatile_u32(sq.progress);
+            const unsigned long long now = global_ns();
+            if (pg != wd_progress) { wd_progress = pg; wd_time = now; }
+            else if (now - wd_time > 20000000000ull && ld_volatile_u32(sq.remaining) != 0u) atomicExch(sq.abort_flag, 1u);
+            if (ld_volatile_u32(sq.abort_flag) != 0u) sm.no_more = 2;
+        }
+        while (mgr_done < sm.jobs_done) {
+            __threadfence_block();
+            const StreamJob j = sm.jobs[mgr_done % AMRVW_USTREAM_JOBS];
+            PolyRec* r = pr.rec + j.p;
+            PolyRec rec = load_rec(r);
+            rec.ls.sp = j.sp;
+            rec.st.sweeps += j.nb;
+            rec.chase_turnovers += (long long)j.nb * (7ll * (j.stop - j.start) + 1ll);
+            if (j.mode == 2) { rec.st.exceptional += j.nb; rec.ls.ord += j.nb; rec.ls.ctr.it_count = AMRVW_IT_COUNT - 1; }
+            store_rec(r, rec);
+            __threadfence();
+            mpmc_push(sq.work, sq.work_slots, sq.mask, j.p);
+            atomicAdd(sq.progress, 1u);
+            mgr_done += 1;
+            worked = true;
+        }
+        const int tail = sm.jobs_tail;
+        if (!sm.no_more && tail - sm.jobs_head == 0 && sm.feed_left < 6 * L + 64 && tail - mgr_done < AMRVW_USTREAM_JOBS - 1) {
+            const int p = mpmc_try_pop(sq.ready, sq.ready_slots, sq.mask);
+            if (p >= 0) {
+                const PolyRec* r = pr.rec + p;
+                StreamJob j;
+                j.p = p; j.base = pr.offsets[p] + (long long)pr.extra * p;
+                j.mode = __ldcg(&r->mode); j.nb = __ldcg(&r->nb); j.start = __ldcg(&r->ls.ctr.start_index); j.stop = __ldcg(&r->ls.ctr.stop_index);
+                j.ord0 = __ldcg(&r->ls.ord); j.sp = __ldcg(&r->ls.sp); j.pad = 0;
+                sm.jobs[tail % AMRVW_USTREAM_JOBS] = j;
+                __threadfence_block();
+                sm.jobs_tail = tail + 1;
+                worked = true;
+            } else if (ld_volatile_u32(sq.remaining) == 0u) {
+                sm.no_more = 1;
+            }
+        }
+        if (sm.quit) return;
+        if (!worked) __nanosleep(300);
+    }
+}
+
+// service warp of the sub-warp stream: the lane groups of the warp each take a polynomial (the unit kernel's
+// side-by-side phase A, rounds.cuh)
+template <int L, int MH>
+AMRVW_DI void ustream_service(const Problem<double>& pr, const PipeParams& pp, const StreamQueues& sq, ShiftScratch<MH>* scratch) {
+    constexpr int G = 32 / L;
+    const int lane32 = threadIdx.x & 31, grp = lane32 / L, lane = lane32 % L;
+    const unsigned gmask = (L == 32 ? 0xffffffffu : ((1u << L) - 1u)) << (grp * L);
+    for (;;) {
+        // up to G polynomials, one per group; a group without one idles through this round
+        int p = -1;
+        if (lane == 0) p = mpmc_try_pop(sq.work, sq.work_slots, sq.mask);
+        if (!__any_sync(0xffffffffu, p >= 0)) {
+            if (ld_volatile_u32(sq.remaining) == 0u || ld_volatile_u32(sq.abort_flag) != 0u) return;
+            __nanosleep(500);
+            continue;
+        }
+        __threadfence();
+        int m0 = 0;
+        if (lane == 0 && p >= 0) m0 = unit_driver(pr, pp, L, p);
+        __syncwarp();
+        const int mg = __shfl_sync(0xffffffffu, m0, grp * L);
+        const int pg = __shfl_sync(0xffffffffu, p, grp * L);
+        if (mg == 3) unit_shifts<MH>(pr, pp, L, pg, scratch[grp], lane, gmask);
+        __syncwarp();
+        if (lane == 0 && p >= 0) {
+            __threadfence();
+            if (m0 == 0) atomicSub(sq.remaining, 1u);
+            else mpmc_push(sq.ready, sq.ready_slots, sq.mask, p);
+        }
+        (void)G;
+    }
+}
+
+// NW chase warps (G = 32/L pipelines each), 1 manager warp, NS service warps per CTA
+template <int L, int MH, int NW, int NS>
+__global__ void __launch_bounds__(32 * (NW + 1 + NS), 2) ustream_kernel(Problem<double> pr, PipeParams pp, StreamQueues sq) {
+    constexpr int G = 32 / L, NP = NW * G, NT = 32 * NW;
+    static_assert(NP <= 32, "one manager lane per pipeline");
+    extern __shared__ __align__(16) unsigned char raw[];       // [12][NT] step snapshots, then the service warps' shift scratch
+    __shared__ __align__(16) UPipe pipes[NP];
+    const int gl = threadIdx.x, warp = gl >> 5, lane32 = gl & 31;
+    if (gl < NP) {
+        UPipe& z = pipes[gl];
+        z.jobs_tail = 0; z.jobs_head = 0; z.jobs_done = 0; z.feed_left = 0; z.no_more = 0; z.quit = 0;
+        for (int a = 0; a < AMRVW_RING; ++a) z.ringtag[a] = 0u;
+    }
+    __syncthreads();
+    if (warp == NW) { ustream_manager<NP>(pr, sq, pipes, L); return; }
+    if (warp > NW) {
+        ShiftScratch<MH>* scratch = reinterpret_cast<ShiftScratch<MH>*>(raw + 12 * NT * sizeof(double2)) + (warp - NW - 1) * G;
+        ustream_service<L, MH>(pr, pp, sq, scratch);
+        return;
+    }
+
+    // ---------------- chase warps
+    const int grp = lane32 / L, lane = lane32 % L;
+    UPipe& sm = pipes[warp * G + grp];
+    [[maybe_unused]] double2* const snap_t = reinterpret_cast<double2*>(raw) + gl;
+    const unsigned stage_sa = (unsigned)__cvta_generic_to_shared(sm.ring);
+    const bool feeds = lane == 0, retires = lane == L - 1;
+
+    Rot<double> q0, q1, q2, b0, b1, b2, c0, c1, c2, U, V, W;
+    q0 = q1 = q2 = b0 = b1 = b2 = c0 = c1 = c2 = U = V = W = make_rot<double>(1.0, 0.0);
+    unsigned tag0 = 0u, tag1 = 0u, tag2 = 0u;
+    bool active = false, pend_b = false;
+
+    int f_slot = -1, f_k = 0, f_stop1 = -1, f_start = 0;
+    const Rot<double>* f_q = nullptr; const Rot<double>* f_b = nullptr; const Rot<double>* f_c = nullptr;
+    int f_started = 0;
+    auto request = [&](const int tslot) {
+        unsigned tag = 0u;
+        if (f_slot >= 0 && f_k > f_stop1) f_slot = -1;
+        if (f_slot < 0 && f_started < sm.jobs_tail) {
+            __threadfence_block();
+            const StreamJob& j = sm.jobs[f_started % AMRVW_USTREAM_JOBS];
+            f_slot = f_started % AMRVW_USTREAM_JOBS; f_start = j.start; f_k = j.start; f_stop1 = j.stop + 1;
+            f_q = pr.Q + j.base; f_b = pr.B + j.base; f_c = pr.Ct + j.base;
+            f_started += 1;
+            sm.jobs_head = f_started;
+        }
+        if (f_slot >= 0) {
+            const unsigned sg = stage_sa + (unsigned)tslot * 48u;
+            cp_async16_sa(sg, f_q + f_k); cp_async16_sa(sg + 16, f_b + f_k); cp_async16_sa(sg + 32, f_c + f_k);
+            tag = AMRVW_TAG_VALID | ((unsigned)f_slot << AMRVW_TAG_SLOT_SHIFT) | (unsigned)f_k | (f_k == f_start ? AMRVW_TAG_FIRST : 0u) | (f_k == f_stop1 ? AMRVW_TAG_LAST : 0u);
+            f_k += 1;
+            sm.feed_left = f_stop1 - f_k + 1;
+        } else {
+            sm.feed_left = 0;
+        }
+        cp_async_commit();
+        sm.ringtag[tslot] = tag;
+    };
+    if (feeds) for (int a = 0; a < AMRVW_RING - 1; ++a) request(a);
+
+    int r_done = 0;
+    bool my_quit = false;      // this lane's pipeline is through (feeding lane decides, the group follows)
+    for (unsigned t = 0;; ++t) {
+        Rot<double> iq = shfl_up_rot(q0, L), ib = shfl_up_rot(b0, L), ic = shfl_up_rot(c0, L);
+        unsigned itag = __shfl_up_sync(0xffffffffu, tag0, 1, L);
+        if (feeds) {
+            cp_async_wait_ring();
+            const int rs = (int)(t & (AMRVW_RING - 1));
+            const unsigned sg = stage_sa + (unsigned)rs * 48u;
+            iq = lds_rot(sg); ib = lds_rot(sg + 16); ic = lds_rot(sg + 32);
+            itag = sm.ringtag[rs];
+            request((int)((t + AMRVW_RING - 1) & (AMRVW_RING - 1)));
+        }
+        q0 = q1; q1 = q2; q2 = iq;
+        b0 = b1; b1 = b2; b2 = ib;
+        c0 = c1; c1 = c2; c2 = ic;
+        tag0 = tag1; tag1 = tag2; tag2 = itag;
+
+        const bool cr = (tag1 & AMRVW_TAG_FIRST) != 0u;
+        const bool fa = active && (tag2 & AMRVW_TAG_LAST) != 0u;
+        const bool reg = active && !fa;
+        if (cr) {
+            const StreamJob& j = sm.jobs[(tag1 >> AMRVW_TAG_SLOT_SHIFT) & (AMRVW_USTREAM_JOBS - 1)];
+            if (lane < j.nb) {
+                const Created o = stream_create(q1, q2, b1, b2, c1, c2, pr.Q + j.base, pr.B + j.base, pr.Ct + j.base, 0, j.start, j.stop, j.mode,
+                                                pr.shifts + (long long)j.p * L, lane, pr.seed, (uint64_t)j.p, j.ord0 + lane);
+                q1 = o.qa; q2 = o.qb; U = o.U; V = o.V; W = o.W;
+                active = true;
+            }
+        } else if (fa) {
+            turnover_fast(b1, b2, V, V, b1, b2);
+            turnover_fast(c2, c1, V, V, c2, c1);
+            turnover_fast(b0, b1, U, U, b0, b1);
+            turnover_fast(c1, c0, U, U, c1, c0);
+            V.s = sign_(sign_(q2.c)) * V.s;
+            q1 = fuse(q1, V);
+            turnover_fast(q0, q1, U, U, q0, q1);
+            U = fuse(W, U);
+            active = false; pend_b = true;
+        } else if (pend_b) {
+            turnover_fast(b0, b1, U, U, b0, b1);
+            turnover_fast(c1, c0, U, U, c1, c0);
+            U.s = sign_(sign_(q1.c)) * U.s;
+            q0 = fuse(q0, U);
+            pend_b = false;
+        }
+        if (reg) {
+#ifndef AMRVW_STRICT
+            AMRVW_CHASE_REGULAR(snap_t, NT);
+#else
+            AMRVW_CHASE_GENERAL();
+#endif
+        }
+
+        if (retires && (tag0 & AMRVW_TAG_VALID)) {
+            StreamJob& j = sm.jobs[(tag0 >> AMRVW_TAG_SLOT_SHIFT) & (AMRVW_USTREAM_JOBS - 1)];
+            const int k = (int)(tag0 & AMRVW_TAG_INDEX_MASK);
+            const long long at = j.base + k;
+            stg_rot(pr.Q + at, q0); stg_rot(pr.B + at, b0); stg_rot(pr.Ct + at, c0);
+            if (!(tag0 & AMRVW_TAG_LAST)) {
+                if (fabs(q0.s) <= AMRVW_EPS) { pr.dstack[j.base + j.sp] = k; j.sp += 1; }
+            } else {
+                __threadfence();
+                r_done += 1;
+                sm.jobs_done = r_done;
+            }
+        }
+        bool empty = false;
+        if (feeds) {
+            empty = f_slot < 0 && sm.jobs_done == f_started;
+            if (!my_quit && ((empty && sm.no_more && f_started == sm.jobs_tail) || sm.no_more == 2)) { my_quit = true; sm.quit = 1; }
+        }
+        __syncwarp();          // the retiring lane's writes to the job ring before the next step's reads
+        // leave when every pipeline of the warp is through; sleep when none has anything in flight
+        const unsigned feeders = __ballot_sync(0xffffffffu, feeds);
+        if ((__ballot_sync(0xffffffffu, feeds && my_quit) & feeders) == feeders) break;
+        if ((__ballot_sync(0xffffffffu, feeds && empty) & feeders) == feeders) __nanosleep(400);
+    }
+    if (feeds) cp_async_wait_all();
+}
+
+template <int L, int MH, int NW, int NS> constexpr size_t ustream_raw_bytes() { return 12 * 32 * NW * sizeof(double2) + (size_t)NS * (32 / L) * sizeof(ShiftScratch<MH>); }
+
+template <int L, int MH, int NW, int NS>
+static cudaError_t launch_ustream(const Problem<double>& pr, const PipeParams& pp, const StreamBufs& sb, int sm_count, cudaStream_t st) {
+    StreamQueues sq;
+    sq.ready = sb.ready; sq.ready_slots = sb.ready_slots; sq.work = sb.work; sq.work_slots = sb.work_slots; sq.mask = sb.mask; sq.remaining = sb.remaining;
+    sq.progress = sb.remaining + 1; sq.abort_flag = pr.counters + CNT_ABORT;
+    stream_init_queues_kernel<<<(int)((sb.mask + 1 + 255) / 256), 256, 0, st>>>(sq);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    stream_enqueue_kernel<<<(int)((pr.nbatch + 127) / 128), 128, 0, st>>>(pr, sq);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    constexpr size_t smem = ustream_raw_bytes<L, MH, NW, NS>();
+    int per_sm = 0;
+    if ((e = cudaFuncSetAttribute(ustream_kernel<L, MH, NW, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ustream_kernel<L, MH, NW, NS>, 32 * (NW + 1 + NS), smem)) != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 2) per_sm = 2;
+    constexpr int NP = NW * (32 / L);
+    const long long cap = (long long)sm_count * per_sm;
+    const long long want = (pr.nbatch + NP - 1) / NP;       // more pipelines than polynomials would only poll
+    const int blocks = (int)(want < cap ? want : cap);
+    ustream_kernel<L, MH, NW, NS><<<blocks, 32 * (NW + 1 + NS), smem, st>>>(pr, pp, sq);
     return cudaGetLastError();
 }
 

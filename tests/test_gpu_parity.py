@@ -2,8 +2,10 @@
 (ctypes over amrvw.jl_b200/libamrvw_b200.so); the oracle is only the checker.
 
 Parity rule (north star / SURVEY.md 8c): roots matched by minimum-distance assignment,
-|dz| <= tau * kappa(z) * max(1,|z|) with tau = C n u ||a||/|a_n| (C = 64), and the number of
-exactly-real roots (imag == 0) must agree exactly.  For the one-bulge (reference-schedule) kernels
+|dz| <= tau * kappa(z) * max(1,|z|) with tau = C n u ||a||/|a_n|, and the number of exactly-real roots
+(imag == 0) must agree exactly.  C is held to what is observed (profiles/r02_parity_margins.txt: the worst
+needed constant over every parity test of a GPU run): C_RDS = 6 (observed 0.92), C_CSS = 24 (3.4), C_PENCIL =
+16 (2.8) -- no more than 8x the observation, so the constants are measurements, not guesses.  For the one-bulge (reference-schedule) kernels
 built without FMA contraction the real double shift path is additionally bit-identical to the
 oracle, which itself reproduces the reference's printed digits."""
 import json
@@ -24,7 +26,9 @@ pc_rts = np.array([1j, 1 + 1j, 2 + 1j, 3 + 1j, 4 + 1j])
 pc2 = np.array([1j, -1, 0, 0, -1j, 1])
 SQEPS = np.sqrt(np.finfo(float).eps)
 # tolerance constants of the parity rule; see check_parity and profiles/r02_parity_margins.txt for what is observed
-C_RDS = 64.0
+C_RDS = 6.0          # observed <= 0.92 over 60 cases, 0.67 at config 2's full size, 0.83 on the streamed 375-share
+C_CSS = 24.0         # observed <= 3.4
+C_PENCIL = 16.0      # observed <= 2.8 (real and complex pencils)
 
 
 def _g(rows):
@@ -63,12 +67,13 @@ def batch(oracle, seed, B, n, kind=0, cx=False):
 MARGIN_LOG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_margins.jsonl")
 
 
-def check_parity(coeff_rows, got, want, C=64.0, real_counts=True):
+def check_parity(coeff_rows, got, want, C=None, real_counts=True):
     """Every root within C n u ||a||/|a_n| kappa(z) max(1,|z|) of its minimum-distance partner, equal counts of
     exactly-real roots.  The worst observed |dz|/tol (in units of the tolerance with C = 1, so the number is
     the constant the data needs) is printed and appended to gpurun_out/parity_margins.jsonl: the constants
     passed by the callers are held to at most 8x what profiles/r02_parity_margins.txt records."""
     worst = 0.0
+    C = C_RDS if C is None else C
     for a, g, w in zip(coeff_rows, got, want):
         assert len(g) == len(w)
         d, idx = match_roots(g, w)
@@ -224,7 +229,7 @@ def test_gpu_rds_parity(A, ctx, ctx_ref, oracle, n, B, which):
     rows = batch(oracle, 1, B, n)                       # C1-style: N(0,1) coefficients
     want = [oracle.roots(r)[0] for r in rows]
     got = A.roots(rows, ctx=c)
-    check_parity(rows, got, want)
+    check_parity(rows, got, want, C=C_RDS)
     assert c.last_stats["unconverged"] == 0
 
 
@@ -233,7 +238,7 @@ def test_gpu_css_parity(A, ctx, oracle, n, B, kind):   # C3-style: U[0,1) + i U[
     rows = batch(oracle, 3, B, n, kind=kind, cx=True)
     want = [oracle.roots(r)[0] for r in rows]
     got = A.roots(rows, ctx=ctx)
-    check_parity(rows, got, want, real_counts=False)
+    check_parity(rows, got, want, C=C_CSS, real_counts=False)
 
 
 @pytest.mark.parametrize("n,B", [(100, 32), (500, 8)])
@@ -244,14 +249,14 @@ def test_gpu_pencil_parity(A, ctx, oracle, n, B):      # C4-style: basic_pencil 
         vs, ws = zip(*pairs)
         want = [oracle.roots(v, ws=w)[0] for v, w in pairs]
         got = A.roots(list(vs), list(ws), ctx=ctx)
-        check_parity(rows, got, want, C=256.0)
+        check_parity(rows, got, want, C=C_PENCIL)
 
 
 def test_gpu_c5_style_uniform_shifted(A, ctx, oracle):  # C5 input law U[0,1) - 1/2 at reduced degree
     rows = batch(oracle, 5, 8, 600, kind=2)
     want = [oracle.roots(r)[0] for r in rows]
     got = A.roots(rows, ctx=ctx)
-    check_parity(rows, got, want)
+    check_parity(rows, got, want, C=C_RDS)
 
 
 def test_gpu_ragged_batch(A, ctx, oracle):
@@ -262,7 +267,7 @@ def test_gpu_ragged_batch(A, ctx, oracle):
         w, _ = oracle.roots(r)
         assert len(g) == len(w)
         if len(r) > 3:
-            check_parity([r], [g], [w])
+            check_parity([r], [g], [w], C=C_RDS)
         else:
             assert np.array_equal(g, w)
 
@@ -407,7 +412,7 @@ def test_gpu_css_pipelined_lanes(A, oracle, L, reuse, solver):
         want = [oracle.roots(r)[0] for r in rows]
         got = A.roots(rows, ctx=c)
         big = [i for i, d in enumerate(degs) if d > 2]
-        check_parity([rows[i] for i in big], [got[i] for i in big], [want[i] for i in big], real_counts=False)
+        check_parity([rows[i] for i in big], [got[i] for i in big], [want[i] for i in big], C=C_CSS, real_counts=False)
         for i, d in enumerate(degs):
             if d <= 2:
                 assert np.allclose(got[i], want[i], rtol=1e-14, atol=0)
@@ -460,7 +465,7 @@ def test_gpu_full_size_c3_properties(A, ctx, oracle):
     assert worst < 1e-10, worst
     sample = list(range(0, B, 250))
     want = [oracle.roots(rows[p])[0] for p in sample]
-    check_parity([rows[p] for p in sample], [got[p] for p in sample], want, real_counts=False)
+    check_parity([rows[p] for p in sample], [got[p] for p in sample], want, C=C_CSS, real_counts=False)
 
 
 # ------------------------------------------------------------------ companion pencil on the unit queue
@@ -480,7 +485,7 @@ def test_gpu_pencil_pipelined_lanes(A, oracle, L, solver):
             want = [oracle.roots(v, ws=w)[0] for v, w in pairs]
             got = A.roots(list(vs), list(ws), ctx=c)
             big = [i for i, d in enumerate(degs) if d > 2]
-            check_parity([rows[i] for i in big], [got[i] for i in big], [want[i] for i in big], C=256.0)
+            check_parity([rows[i] for i in big], [got[i] for i in big], [want[i] for i in big], C=C_PENCIL)
             for i, d in enumerate(degs):
                 if d <= 2:
                     assert np.allclose(got[i], want[i], rtol=1e-14, atol=0)
@@ -524,7 +529,7 @@ def test_gpu_full_size_c4_properties(A, ctx, oracle):
             assert np.array_equal(pos, neg)
         sample = list(range(0, B, 125))
         want = [oracle.roots(pairs[p][0], ws=pairs[p][1])[0] for p in sample]
-        check_parity([rows[p] for p in sample], [got[p] for p in sample], want, C=256.0)
+        check_parity([rows[p] for p in sample], [got[p] for p in sample], want, C=C_PENCIL)
 
 
 # ------------------------------------------------------------------ chained warps (small batches of large polynomials)
@@ -564,7 +569,7 @@ def test_gpu_chain_parity(A, oracle, L):
         rows = batch(oracle, 5, 3, 1500, kind=2) + batch(oracle, 2, 2, 900)
         want = [oracle.roots(r)[0] for r in rows]
         got = A.roots(rows, ctx=c)
-        check_parity(rows, got, want)
+        check_parity(rows, got, want, C=C_RDS)
         assert c.last_stats["unconverged"] == 0 and c.last_stats["fat_steps"] > 0
     finally:
         c.close()
@@ -648,7 +653,7 @@ def test_gpu_chain_more_polynomials_than_resident_ctas(A, ctx, oracle):
             d, _ = match_roots(got[p], ref[p])
             assert d.max() < 1e-9 and np.sum(got[p].imag == 0) == np.sum(ref[p].imag == 0)
         want = [oracle.roots(rows[p])[0] for p in (0, 333, 699)]
-        check_parity([rows[p] for p in (0, 333, 699)], [got[p] for p in (0, 333, 699)], want)
+        check_parity([rows[p] for p in (0, 333, 699)], [got[p] for p in (0, 333, 699)], want, C=C_RDS)
     finally:
         c.close()
 
@@ -766,7 +771,7 @@ def test_gpu_complex_pencil_random_parity(A, ctx, oracle, n, B):
         pairs = [A.basic_pencil(r) if split == "basic" else pencil_split(r, n // 2) for r in rows]
         got = A.roots([v for v, _ in pairs], [w for _, w in pairs], ctx=ctx)
         want = [oracle.roots(v, ws=w)[0] for v, w in pairs]
-        check_parity(rows, got, want, C=256.0, real_counts=False)
+        check_parity(rows, got, want, C=C_PENCIL, real_counts=False)
 
 
 def test_gpu_reference_constants_as_options(A, oracle):
@@ -826,7 +831,7 @@ def test_gpu_count_real_roots_host_entry(A, ctx, oracle):
         assert counts[p, 1] == counts[p, 2] == np.sum(w.imag > 0) and counts[p].sum() == 150
 
 
-@pytest.mark.parametrize("L,reuse,small,dense", [(128, 8, 40, 1), (128, 4, 72, 1), (64, 4, 40, 1), (128, 8, 40, 0)])
+@pytest.mark.parametrize("L,reuse,small,dense", [(128, 8, 40, 1), (128, 4, 72, 1), (64, 4, 40, 1), (128, 8, 40, 0), (16, 2, 24, 1), (16, 1, 40, 1), (32, 2, 40, 1), (32, 4, 24, 0)])
 def test_gpu_stream_bitwise_vs_sequential_multishift(A, oracle, L, reuse, small, dense):
     """stream.cuh: chained warps fed by a stream of fat steps of different polynomials -- bulges created one lock-step
     early, the last chase step split over two lock-steps, jobs of several polynomials in the array at once, polynomials
