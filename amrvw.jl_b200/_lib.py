@@ -13,7 +13,7 @@ class AmrvwError(RuntimeError):
 class Options(ctypes.Structure):
     _fields_ = [("schedule", ctypes.c_int32), ("lanes_per_poly", ctypes.c_int32), ("shift_reuse", ctypes.c_int32),
                 ("small_window", ctypes.c_int32), ("shift_solver", ctypes.c_int32), ("it_count", ctypes.c_int32), ("seed", ctypes.c_uint64),
-                ("it_max_factor", ctypes.c_int32), ("reserved", ctypes.c_int32), ("tol", ctypes.c_double)]
+                ("it_max_factor", ctypes.c_int32), ("stream_ctas_per_sm", ctypes.c_int32), ("tol", ctypes.c_double)]
 
 
 class Stats(ctypes.Structure):
@@ -55,6 +55,7 @@ _SIGS = {
     "amrvw_measure_fp64_peak": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double)]),
     "amrvw_selftest": (ctypes.c_int, [_P, _I64, ctypes.POINTER(ctypes.c_double)]),
     "amrvw_last_profile": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_int64)]),
+    "amrvw_debug_counters": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_int64)]),
     "amrvw_selftest_complex": (ctypes.c_int, [_P, _I64, ctypes.POINTER(ctypes.c_double)]),
     "amrvw_selftest_robust": (ctypes.c_int, [_P, _I64, ctypes.POINTER(ctypes.c_double)]),
 }

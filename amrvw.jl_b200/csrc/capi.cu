@@ -80,7 +80,7 @@ void amrvw_default_options(amrvw_options* opt) {
     opt->it_count = 15;                          // create-bulge.jl:9
     opt->seed = 0;
     opt->it_max_factor = 20;                     // AMRVW_algorithm.jl:25
-    opt->reserved = 0;
+    opt->stream_ctas_per_sm = 0;
     opt->tol = 2.220446049250313e-16;            // AMRVW_algorithm.jl:184: eps(Float64)
 }
 
@@ -179,7 +179,7 @@ int amrvw_set_options(amrvw_ctx* ctx, const amrvw_options* opt) {
     if (opt->shift_solver < 0 || opt->shift_solver > 2) return fail(ctx, AMRVW_ERR_ARGUMENT, "shift_solver must be 0, 1 or 2");
     if (opt->it_count < 0 || opt->it_max_factor < 0) return fail(ctx, AMRVW_ERR_ARGUMENT, "it_count and it_max_factor must be >= 0 (0 = the reference's 15 and 20)");
     if (!(opt->tol >= 0.0) || opt->tol > 1e-4) return fail(ctx, AMRVW_ERR_ARGUMENT, "tol must be in [0, 1e-4] (0 = the reference's eps)");
-    if (opt->reserved != 0) return fail(ctx, AMRVW_ERR_ARGUMENT, "reserved must be 0");
+    if (opt->stream_ctas_per_sm < 0 || opt->stream_ctas_per_sm > 2) return fail(ctx, AMRVW_ERR_ARGUMENT, "stream_ctas_per_sm must be 0, 1 or 2");
     ctx->opt = *opt;
     if (ctx->opt.it_count == 0) ctx->opt.it_count = 15;
     if (ctx->opt.it_max_factor == 0) ctx->opt.it_max_factor = 20;
@@ -289,8 +289,8 @@ static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, cons
     pr.prof = nullptr; pr.rec = nullptr; pr.shifts = nullptr; pr.swlist = nullptr; pr.counters = nullptr; pr.order = nullptr;
     cudaStream_t st = ctx->stream;
     if (stats && var != V_PENCIL_C) {   // warp-cycle counters ride along with the statistics
-        int rc = reserve(ctx, ctx->prof, 16 * sizeof(unsigned long long)); if (rc) return rc;
-        CUDA_TRY(ctx, cudaMemsetAsync(ctx->prof.ptr, 0, 16 * sizeof(unsigned long long), st));
+        int rc = reserve(ctx, ctx->prof, 64 * sizeof(unsigned long long)); if (rc) return rc;      // 16 documented counters + 48 development slots
+        CUDA_TRY(ctx, cudaMemsetAsync(ctx->prof.ptr, 0, 64 * sizeof(unsigned long long), st));
         pr.prof = (unsigned long long*)ctx->prof.ptr;
     }
     pr.extra = extra;
@@ -330,7 +330,7 @@ static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, cons
         if (var == V_RDS && pp.stream) {     // two device-wide queues of polynomial ids + the count of iterating polynomials
             size_t cap = 1024;
             while (cap < (size_t)nbatch + 64) cap <<= 1;
-            if ((rc = reserve(ctx, ctx->squeues, 2 * sizeof(MpmcQueue) + 64))) return rc;
+            if ((rc = reserve(ctx, ctx->squeues, 2 * sizeof(MpmcQueue) + 64))) return rc;     // + remaining, progress, t0
             if ((rc = reserve(ctx, ctx->sslots, 2 * cap * sizeof(MpmcSlot)))) return rc;
             sbuf.ready = (MpmcQueue*)ctx->squeues.ptr; sbuf.work = sbuf.ready + 1; sbuf.remaining = (unsigned*)(sbuf.work + 1);
             sbuf.ready_slots = (MpmcSlot*)ctx->sslots.ptr; sbuf.work_slots = sbuf.ready_slots + cap; sbuf.mask = (unsigned)(cap - 1);
@@ -579,6 +579,18 @@ int amrvw_last_profile(amrvw_ctx* ctx, int64_t* out16) {
     // kernel times of the unit schedule, microseconds
     out16[8] = (int64_t)(ctx->times.setup_ms * 1e3); out16[9] = (int64_t)(ctx->times.main_ms * 1e3);   // [10] driver cycles, [13] pop cycles stay as counted
     out16[11] = (int64_t)(ctx->times.small_ms * 1e3); out16[12] = (int64_t)(ctx->times.finish_ms * 1e3);
+    return AMRVW_OK;
+}
+
+int amrvw_debug_counters(amrvw_ctx* ctx, int64_t* out48) {
+    if (!ctx || !out48) return AMRVW_ERR_ARGUMENT;
+    ctx = primary(ctx);
+    std::memset(out48, 0, 48 * sizeof(int64_t));
+    if (ctx->prof.ptr && ctx->prof_valid) {
+        CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+        CUDA_TRY(ctx, cudaMemcpyAsync(out48, (const int64_t*)ctx->prof.ptr + 16, 48 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     return AMRVW_OK;
 }
 

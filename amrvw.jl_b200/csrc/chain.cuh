@@ -27,7 +27,8 @@ template <int NW> struct ChainSmem {
 
 // Steps [t0, t1) during which every lane of the CTA is at a regular chase position: ingest -> 7 turnovers
 // -> retire -> bar.sync (the chain twin of lean_chase, pipeline.cuh)
-template <int NW>
+// BAR: named barrier of the NW chase warps (0 = the whole CTA, __syncthreads; stream.cuh has service warps beside them)
+template <int NW, int BAR = 0>
 AMRVW_DI int chain_lean(StepState& z, Rot<double>* gq, Rot<double>* gb, Rot<double>* gc, const unsigned stage_sa, const unsigned snap_sa, const unsigned hand_sa,
                         int* dstack, int sp, const int start, const int t0, const int t1, const int warp, const int lane32) {
     constexpr int LE = 32 * NW;
@@ -96,7 +97,8 @@ AMRVW_DI int chain_lean(StepState& z, Rot<double>* gq, Rot<double>* gb, Rot<doub
             sts_rot(so, q0); sts_rot(so + 16, b0); sts_rot(so + 32, c0);
         }
         gq += 1; gb += 1; gc += 1; kidx += 1;
-        __syncthreads();
+        if constexpr (BAR == 0) __syncthreads();
+        else asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(32 * NW) : "memory");
     }
     z.q0 = q0; z.q1 = q1; z.q2 = q2; z.b0 = b0; z.b1 = b1; z.b2 = b2; z.c0 = c0; z.c1 = c1; z.c2 = c2; z.U = U; z.V = V; z.W = W;
     return sp;

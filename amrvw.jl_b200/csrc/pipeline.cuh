@@ -41,7 +41,8 @@ struct PipeParams {
     int ms;      // scratch slots per group and chain (>= max(2L/reuse, small) + 3)
     int dense;   // shifts from the dense trailing block (shifts.cuh) instead of the core-chasing sub-solve
     int mh;      // dense: order of the largest trailing block (2L/reuse)
-    int stream;  // chained warps only: the CTAs take the fat steps of all polynomials as one stream (stream.cuh)
+    int stream;  // the CTAs take the fat steps of all polynomials as one stream (stream.cuh)
+    int stream_ctas;   // stream: resident CTAs per SM (0 = as many as fit, at most 2)
 };
 
 AMRVW_DI Rot<double> shfl_up_rot(const Rot<double> r, int width) {

@@ -604,6 +604,7 @@ static void choose_pipe_params(const amrvw_options& opt, long long nbatch, int m
     // chained warps: one CTA per polynomial (chain.cuh) while there are fewer polynomials than SMs can hold two of;
     // above that the CTAs take the fat steps of all polynomials as one stream (stream.cuh): no fill/drain, phase A hidden
     pp.stream = 0;
+    pp.stream_ctas = opt.stream_ctas_per_sm;
     if (opt.schedule == AMRVW_SCHEDULE_STREAMED && opt.lanes_per_poly == 0) L = 128;
     if (opt.schedule == AMRVW_SCHEDULE_STREAMED && (L == 16 || L == 32)) pp.stream = 1;     // sub-warp pipelines (stream.cuh, second half)
     if (L == 128 || L == 64) {
@@ -675,7 +676,7 @@ static cudaError_t launch_rounds_rds(Problem<double> pr, const amrvw_options& op
     cudaError_t e;
     const int nb64 = (int)((pr.nbatch + 63) / 64);
     if ((e = cudaMemsetAsync(pr.counters, 0, CNT_WORDS * sizeof(unsigned), st)) != cudaSuccess) return e;
-    if (L <= 32) {    // the unit queue (chained warps have none)
+    if (L <= 32 && !(pp.stream && sb)) {    // the unit queue (chained warps and streams have none)
         if ((e = cudaMemsetAsync(qb.q, 0, sizeof(RoundQueue), st)) != cudaSuccess) return e;
         if ((e = cudaMemsetAsync(qb.slots, 0xFF, (size_t)(qb.mask + 1) * sizeof(int), st)) != cudaSuccess) return e;
     }

@@ -42,6 +42,7 @@ struct StreamQueues {
     unsigned* remaining;                          // polynomials still iterating
     unsigned* progress;                           // fat steps completed, device-wide (watchdog)
     unsigned* abort_flag;                         // counters[CNT_ABORT]: sticky, turned into AMRVW_ERR_QUEUE_TIMEOUT by the host
+    unsigned long long* t0;                       // globaltimer at queue initialisation (accounting only)
 };
 AMRVW_DI unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 AMRVW_DI unsigned ld_volatile_u32(const unsigned* p) { return *reinterpret_cast<const volatile unsigned*>(p); }
@@ -81,7 +82,7 @@ __global__ void stream_init_queues_kernel(StreamQueues sq) {
     }
     if (i == 0) {
         sq.ready->head = sq.ready->tail = 0u; sq.work->head = sq.work->tail = 0u;
-        *sq.remaining = 0u; *sq.progress = 0u;
+        *sq.remaining = 0u; *sq.progress = 0u; *sq.t0 = global_ns();
     }
 }
 // every iterating polynomial starts in the phase A queue, largest first (pr.order)
@@ -91,6 +92,7 @@ __global__ void stream_enqueue_kernel(Problem<double> pr, StreamQueues sq) {
     const long long p = unit_poly(pr, slot);
     if (!pr.rec[p].iterating) return;
     atomicAdd(sq.remaining, 1u);
+    pr.rec[p].ls.pc_sub = (long long)global_ns();      // time stamps of the queue hand-overs (accounting only)
     mpmc_push(sq.work, sq.work_slots, sq.mask, (int)p);
 }
 
@@ -107,7 +109,23 @@ struct StreamJob {
     long long base;       // chain slot of the polynomial: offsets[p] + extra * p
     int p, start, stop, nb;
     int mode, ord0, sp, pad;
+    double2 qm, bm, cm;   // rotators of index start - 1: constant during the job, needed by every bulge creation
 };
+// descriptor of the next fat step of polynomial p from its record (manager lanes)
+AMRVW_DI StreamJob stream_job_from_record(const Problem<double>& pr, const int p) {
+    const PolyRec* r = pr.rec + p;
+    StreamJob j;
+    j.p = p; j.base = pr.offsets[p] + (long long)pr.extra * p;
+    j.mode = __ldcg(&r->mode); j.nb = __ldcg(&r->nb); j.start = __ldcg(&r->ls.ctr.start_index); j.stop = __ldcg(&r->ls.ctr.stop_index);
+    j.ord0 = __ldcg(&r->ls.ord); j.sp = __ldcg(&r->ls.sp); j.pad = 0;
+    j.qm = __ldcg(reinterpret_cast<const double2*>(pr.Q + j.base + j.start - 1));       // Q[0] is the (1,0) sentinel
+    j.bm = make_double2(1.0, 0.0); j.cm = make_double2(1.0, 0.0);
+    if (j.start > 1) {
+        j.bm = __ldcg(reinterpret_cast<const double2*>(pr.B + j.base + j.start - 1));
+        j.cm = __ldcg(reinterpret_cast<const double2*>(pr.Ct + j.base + j.start - 1));
+    }
+    return j;
+}
 template <int NW> struct StreamSmem {
     StreamJob jobs[AMRVW_STREAM_JOBS];
     double2 ring[3 * AMRVW_RING];          // look-ahead ring of the feeding thread
@@ -119,39 +137,115 @@ template <int NW> struct StreamSmem {
     volatile int jobs_done;                // retiring thread: jobs whose last triple has been written back
     volatile int feed_left;                // feeding thread: triples of the current job not yet requested
     volatile int no_more;                  // manager: nothing iterates any more
-    volatile int quit;                     // feeding thread: the array is empty and nothing will come
-    volatile int idle;                     // feeding thread: nothing in the array right now
+    volatile int ctl;                      // feeding thread, every lock-step: > 0 lock-steps the array may run lean, 0 go on, -1 nap, -2 leave
+    volatile int quit;                     // chase warps have left (manager's exit)
+    volatile int sptype;                   // development: special operation of this lock-step (1 create, 2 last step part one, 3 part two)
 };
 
 struct Created { Rot<double> qa, qb, U, V, W; };
-// create_bulge + absorb_Ut (create-bulge.jl:20-77, RDS.jl:14-36) for the bulge of chain lane `bl` of a job: the
-// lane's window holds final values of indices start (qa, ba, ca) and start+1 (qb, bb, cb); index start-1 never
-// changes during the job and is read here, like the lane's shifts.
+// create_bulge + absorb_Ut (create-bulge.jl:20-77, RDS.jl:14-36) for one bulge of a job: the lane's window holds final
+// values of indices start (qa, ba, ca) and start+1 (qb, bb, cb); index start-1 (qm, bm, cm: constant during the job)
+// comes from the job descriptor, the lane's shift pair (e1, e2) was loaded one lock-step earlier.  Everything by
+// value: no memory access on the path.
 AMRVW_NI Created stream_create(const Rot<double> qa, const Rot<double> qb, const Rot<double> ba, const Rot<double> bb, const Rot<double> ca, const Rot<double> cb,
-                               const Rot<double>* FQ, const Rot<double>* FB, const Rot<double>* FC, const int N, const int start, const int stop, const int mode,
-                               const Shifts* shl, const int bl, const uint64_t seed, const uint64_t poly, const int ordinal) {
+                               const double2 qm2, const double2 bm2, const double2 cm2, const double2 e1, const double2 e2,
+                               const int start, const int stop, const int mode, const uint64_t seed, const uint64_t poly, const int ordinal) {
     const Rot<double> one = make_rot<double>(1.0, 0.0);
-    const Rot<double> qm = ldcg_rot(FQ + start - 1);                // Q[0] is the (1,0) sentinel
-    Rot<double> bm = one, cm = one;
-    if (start > 1) { bm = ldcg_rot(FB + start - 1); cm = ldcg_rot(FC + start - 1); }
+    const Rot<double> qm = make_rot<double>(qm2.x, qm2.y), bm = make_rot<double>(bm2.x, bm2.y), cm = make_rot<double>(cm2.x, cm2.y);
     Shifts sh;
-    sh.e1 = cplx(0.0, 0.0); sh.e2 = cplx(0.0, 0.0);
-    if (mode == 1) {
-        const double2 v1 = __ldcg(reinterpret_cast<const double2*>(shl + bl)), v2 = __ldcg(reinterpret_cast<const double2*>(shl + bl) + 1);
-        sh.e1 = cplx(v1.x, v1.y); sh.e2 = cplx(v2.x, v2.y);
-    }
+    sh.e1 = cplx(e1.x, e1.y); sh.e2 = cplx(e2.x, e2.y);
     StepState z;
     z.q0 = qa; z.q1 = qb; z.q2 = one; z.b0 = ba; z.b1 = bb; z.b2 = one; z.c0 = ca; z.c1 = cb; z.c2 = one;   // index start+2 is not read
     z.U = one; z.V = one; z.W = one;
     Fact<double, false> F;
-    F.Q = F.B = F.Ct = F.WB = F.WCt = nullptr; F.DQ = F.DR = F.WD = nullptr; F.N = N; F.turnovers = 0;
+    F.Q = F.B = F.Ct = F.WB = F.WCt = nullptr; F.DQ = F.DR = F.WD = nullptr; F.N = 0; F.turnovers = 0;
     create_and_absorb(z, qm, bm, cm, F, start, stop, mode, sh, seed, poly, ordinal);
     Created o;
     o.qa = z.q0; o.qb = z.q1; o.U = z.U; o.V = z.V; o.W = z.W;
     return o;
 }
 
+// ---------------------------------------------------------------- one lock-step of a lane that holds a bulge
+// A lane is at a regular position (reg: 7 turnovers, RDS.jl:42-70, 97-108), at the first half of its bulge's last position
+// (fa: window [stop-1, stop, stop+1] -- the four passthrough_triu turnovers, V fused into Q, U through Q, U <- W U;
+// RDS.jl:110-128) or at the second half (fb: window [stop, stop+1, *] -- U through R, then fused into Q).  The three
+// share their operand patterns turnover by turnover, so in the product build they are ONE straight-line instruction
+// stream with the results committed under per-lane predicates: the lanes of a warp that sit at the end of a window cost
+// nothing extra (taken as divergent branches the same warp paid regular + last-a + last-b in turn, 1.5x - 1.9x a regular
+// step while a window boundary crosses it).  A degenerate turnover (flagged, essentially never) redoes the lane's step on
+// the general path from the shared-memory snapshot.  The strict build keeps the branches (it exists to be bit-identical
+// to the oracle, which needs the IEEE turnover).
+AMRVW_DI Rot<double> rsel(const bool p, const Rot<double> a, const Rot<double> b) { return make_rot<double>(p ? a.c : b.c, p ? a.s : b.s); }
+AMRVW_NI void stream_last_a_general(StepState& z) {
+    turnover_fast(z.b1, z.b2, z.V, z.V, z.b1, z.b2);
+    turnover_fast(z.c2, z.c1, z.V, z.V, z.c2, z.c1);
+    turnover_fast(z.b0, z.b1, z.U, z.U, z.b0, z.b1);
+    turnover_fast(z.c1, z.c0, z.U, z.U, z.c1, z.c0);
+    z.V.s = sign_(sign_(z.q2.c)) * z.V.s;          // Q[stop+1]: the diagonal rotator below the window (or the (1,0) sentinel)
+    z.q1 = fuse(z.q1, z.V);
+    turnover_fast(z.q0, z.q1, z.U, z.U, z.q0, z.q1);
+    z.U = fuse(z.W, z.U);
+}
+AMRVW_NI void stream_last_b_general(StepState& z) {
+    turnover_fast(z.b0, z.b1, z.U, z.U, z.b0, z.b1);
+    turnover_fast(z.c1, z.c0, z.U, z.U, z.c1, z.c0);
+    z.U.s = sign_(sign_(z.q1.c)) * z.U.s;
+    z.q0 = fuse(z.q0, z.U);
+}
+#define AMRVW_STREAM_COMPUTE(sn, NT)                                                                                                  \
+    do {                                                                                                                              \
+        if (reg | fa | fb) {                                                                                                          \
+            (sn)[0 * (NT)] = make_double2(q0.c, q0.s); (sn)[1 * (NT)] = make_double2(q1.c, q1.s); (sn)[2 * (NT)] = make_double2(q2.c, q2.s); \
+            (sn)[3 * (NT)] = make_double2(b0.c, b0.s); (sn)[4 * (NT)] = make_double2(b1.c, b1.s); (sn)[5 * (NT)] = make_double2(b2.c, b2.s); \
+            (sn)[6 * (NT)] = make_double2(c0.c, c0.s); (sn)[7 * (NT)] = make_double2(c1.c, c1.s); (sn)[8 * (NT)] = make_double2(c2.c, c2.s); \
+            (sn)[9 * (NT)] = make_double2(U.c, U.s); (sn)[10 * (NT)] = make_double2(V.c, V.s); (sn)[11 * (NT)] = make_double2(W.c, W.s);    \
+            const bool m12_ = reg | fa, m34_ = reg | fa | fb;                                                                         \
+            bool ok_ = true, k_;                                                                                                      \
+            Rot<double> t1_, t2_, t3_;                                                                                                \
+            k_ = turnover_fast_try(b1, b2, V, t1_, t2_, t3_); ok_ &= k_ | !m12_; V = rsel(m12_, t1_, V); b1 = rsel(m12_, t2_, b1); b2 = rsel(m12_, t3_, b2); \
+            k_ = turnover_fast_try(c2, c1, V, t1_, t2_, t3_); ok_ &= k_ | !m12_; V = rsel(m12_, t1_, V); c2 = rsel(m12_, t2_, c2); c1 = rsel(m12_, t3_, c1); \
+            k_ = turnover_fast_try(b0, b1, U, t1_, t2_, t3_); ok_ &= k_ | !m34_; U = rsel(m34_, t1_, U); b0 = rsel(m34_, t2_, b0); b1 = rsel(m34_, t3_, b1); \
+            k_ = turnover_fast_try(c1, c0, U, t1_, t2_, t3_); ok_ &= k_ | !m34_; U = rsel(m34_, t1_, U); c1 = rsel(m34_, t2_, c1); c0 = rsel(m34_, t3_, c0); \
+            {   /* regular: V through Q; last-a: V (with the sign of the rotator below the window) fused into Q[stop] */              \
+                Rot<double> vf_ = V; vf_.s = sign_(sign_(q2.c)) * V.s;                                                                \
+                const Rot<double> qf_ = fuse(q1, vf_);                                                                                \
+                k_ = turnover_fast_try(q1, q2, V, t1_, t2_, t3_); ok_ &= k_ | !reg;                                                   \
+                V = rsel(reg, t1_, V); q1 = rsel(reg, t2_, rsel(fa, qf_, q1)); q2 = rsel(reg, t3_, q2);                               \
+            }                                                                                                                         \
+            {   /* regular, last-a: U through Q; last-b: U fused into Q[stop] */                                                      \
+                Rot<double> uf_ = U; uf_.s = sign_(sign_(q1.c)) * U.s;                                                                \
+                const Rot<double> qg_ = fuse(q0, uf_);                                                                                \
+                k_ = turnover_fast_try(q0, q1, U, t1_, t2_, t3_); ok_ &= k_ | !m12_;                                                  \
+                U = rsel(m12_, t1_, U); q0 = rsel(m12_, t2_, rsel(fb, qg_, q0)); q1 = rsel(m12_, t3_, q1);                            \
+            }                                                                                                                         \
+            {   /* regular: the limb turnover; last-a: U <- W U */                                                                    \
+                const Rot<double> uw_ = fuse(W, U);                                                                                   \
+                k_ = turnover_fast_try(W, V, U, t1_, t2_, t3_); ok_ &= k_ | !reg;                                                     \
+                V = rsel(reg, t1_, V); U = rsel(reg, t2_, rsel(fa, uw_, U)); W = rsel(reg, t3_, W);                                   \
+            }                                                                                                                         \
+            if (!ok_) {                                                                                                               \
+                StepState z_;                                                                                                         \
+                double2 v_;                                                                                                           \
+                v_ = (sn)[0 * (NT)]; z_.q0 = make_rot<double>(v_.x, v_.y); v_ = (sn)[1 * (NT)]; z_.q1 = make_rot<double>(v_.x, v_.y); \
+                v_ = (sn)[2 * (NT)]; z_.q2 = make_rot<double>(v_.x, v_.y); v_ = (sn)[3 * (NT)]; z_.b0 = make_rot<double>(v_.x, v_.y); \
+                v_ = (sn)[4 * (NT)]; z_.b1 = make_rot<double>(v_.x, v_.y); v_ = (sn)[5 * (NT)]; z_.b2 = make_rot<double>(v_.x, v_.y); \
+                v_ = (sn)[6 * (NT)]; z_.c0 = make_rot<double>(v_.x, v_.y); v_ = (sn)[7 * (NT)]; z_.c1 = make_rot<double>(v_.x, v_.y); \
+                v_ = (sn)[8 * (NT)]; z_.c2 = make_rot<double>(v_.x, v_.y); v_ = (sn)[9 * (NT)]; z_.U = make_rot<double>(v_.x, v_.y);  \
+                v_ = (sn)[10 * (NT)]; z_.V = make_rot<double>(v_.x, v_.y); v_ = (sn)[11 * (NT)]; z_.W = make_rot<double>(v_.x, v_.y); \
+                if (reg) chase_step_general(z_); else if (fa) stream_last_a_general(z_); else stream_last_b_general(z_);              \
+                q0 = z_.q0; q1 = z_.q1; q2 = z_.q2; b0 = z_.b0; b1 = z_.b1; b2 = z_.b2; c0 = z_.c0; c1 = z_.c1; c2 = z_.c2;           \
+                U = z_.U; V = z_.V; W = z_.W;                                                                                         \
+            }                                                                                                                         \
+        }                                                                                                                             \
+    } while (0)
+
 #define AMRVW_BAR_CHASE(n) asm volatile("bar.sync 1, %0;" ::"n"(n) : "memory")
+// the same barrier with an AND reduction of a predicate over the N chase threads
+template <int N> AMRVW_DI bool bar_chase_and(const bool pred) {
+    int r;
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 q, %1, 0;\n\tbar.red.and.pred p, 1, %2, q;\n\tselp.s32 %0, 1, 0, p;\n\t}" : "=r"(r) : "r"((int)pred), "n"(N) : "memory");
+    return r != 0;
+}
 
 // ---------------------------------------------------------------- the three roles of a CTA
 // manager warp (one lane works): completed jobs go back to their records and into the phase A queue; the next
@@ -182,6 +276,7 @@ AMRVW_DI void stream_manager(const Problem<double>& pr, const StreamQueues& sq, 
             rec.st.sweeps += j.nb;
             rec.chase_turnovers += (long long)j.nb * (7ll * (j.stop - j.start) + 1ll);
             if (j.mode == 2) { rec.st.exceptional += j.nb; rec.ls.ord += j.nb; rec.ls.ctr.it_count = AMRVW_IT_COUNT - 1; }
+            rec.ls.pc_sub = (long long)global_ns();
             store_rec(r, rec);
             __threadfence();                  // the chase warps' write-backs of this job are visible before the polynomial is
             mpmc_push(sq.work, sq.work_slots, sq.mask, j.p);
@@ -193,11 +288,7 @@ AMRVW_DI void stream_manager(const Problem<double>& pr, const StreamQueues& sq, 
         if (!sm.no_more && tail - sm.jobs_head == 0 && sm.feed_left < 3 * LE && tail - mgr_done < AMRVW_STREAM_JOBS - 1) {
             const int p = mpmc_try_pop(sq.ready, sq.ready_slots, sq.mask);
             if (p >= 0) {
-                const PolyRec* r = pr.rec + p;
-                StreamJob j;
-                j.p = p; j.base = pr.offsets[p] + (long long)pr.extra * p;
-                j.mode = __ldcg(&r->mode); j.nb = __ldcg(&r->nb); j.start = __ldcg(&r->ls.ctr.start_index); j.stop = __ldcg(&r->ls.ctr.stop_index);
-                j.ord0 = __ldcg(&r->ls.ord); j.sp = __ldcg(&r->ls.sp); j.pad = 0;
+                const StreamJob j = stream_job_from_record(pr, p);
                 sm.jobs[tail % AMRVW_STREAM_JOBS] = j;
                 __threadfence_block();
                 sm.jobs_tail = tail + 1;
@@ -227,6 +318,7 @@ AMRVW_DI void stream_service(const Problem<double>& pr, const PipeParams& pp, co
         }
         p = __shfl_sync(0xffffffffu, p, 0);
         if (p < 0) return;
+        const long long pc_s0 = clock64();
         __threadfence();
         int m0 = 0;
         if (lane32 == 0) m0 = unit_driver(pr, pp, LE, p);
@@ -234,9 +326,12 @@ AMRVW_DI void stream_service(const Problem<double>& pr, const PipeParams& pp, co
         if (m0 == 3) unit_shifts<MH>(pr, pp, 32, p, scratch, lane32, 0xffffffffu, LE);
         __syncwarp();
         if (lane32 == 0) {
+            __stcg(&pr.rec[p].ls.pc_small, (long long)global_ns());
             __threadfence();
             if (m0 == 0) atomicSub(sq.remaining, 1u);
             else mpmc_push(sq.ready, sq.ready_slots, sq.mask, p);
+            if (pr.prof) { atomicAdd(pr.prof + 1, (unsigned long long)(clock64() - pc_s0)); atomicAdd(pr.prof + 10, 1ull); }   // phase A: cycles, count
+
         }
     }
 }
@@ -249,7 +344,7 @@ __global__ void __launch_bounds__(32 * (NW + 2), 2) stream_kernel(Problem<double
     __shared__ __align__(16) StreamSmem<NW> sm;
     const int gl = threadIdx.x, warp = gl >> 5, lane32 = gl & 31;
     if (gl == 0) {
-        sm.jobs_tail = 0; sm.jobs_head = 0; sm.jobs_done = 0; sm.feed_left = 0; sm.no_more = 0; sm.quit = 0; sm.idle = 1;
+        sm.jobs_tail = 0; sm.jobs_head = 0; sm.jobs_done = 0; sm.feed_left = 0; sm.no_more = 0; sm.quit = 0; sm.ctl = -1; sm.sptype = 0;
     }
     if (gl < NW * 2 * 3) (&sm.hand[0][0][0])[gl] = make_double2(1.0, 0.0);
     if (gl < NW * 2) (&sm.handtag[0][0])[gl] = 0u;
@@ -275,32 +370,33 @@ __global__ void __launch_bounds__(32 * (NW + 2), 2) stream_kernel(Problem<double
     q0 = q1 = q2 = b0 = b1 = b2 = c0 = c1 = c2 = U = V = W = make_rot<double>(1.0, 0.0);
     unsigned tag0 = 0u, tag1 = 0u, tag2 = 0u;
     bool active = false, pend_b = false;
+    double2 she1 = make_double2(0.0, 0.0), she2 = make_double2(0.0, 0.0);      // shift pair of the bulge this lane creates next
 
     // feeding thread: the job being streamed in
     int f_slot = -1, f_k = 0, f_stop1 = -1, f_start = 0;       // next index to request, last index (stop + 1) of the job
-    const Rot<double>* f_q = nullptr; const Rot<double>* f_b = nullptr; const Rot<double>* f_c = nullptr;
+    long long f_base = 0;                                      // chain slot of the job being fed
     int f_started = 0;                                         // jobs started
     auto request = [&](const int tslot) {
         // the triple that enters the array AMRVW_RING - 1 steps from now: next index of the current job, else the first
         // index of the next prepared job, else nothing
         unsigned tag = 0u;
-        if (f_slot >= 0 && f_k > f_stop1) f_slot = -1;
+        if (f_slot >= 0 && f_k > f_stop1) { f_slot = -1; sm.feed_left = 0; }
         if (f_slot < 0 && f_started < sm.jobs_tail) {
             __threadfence_block();
             const StreamJob& j = sm.jobs[f_started % AMRVW_STREAM_JOBS];
             f_slot = f_started % AMRVW_STREAM_JOBS; f_start = j.start; f_k = j.start; f_stop1 = j.stop + 1;
-            f_q = pr.Q + j.base; f_b = pr.B + j.base; f_c = pr.Ct + j.base;
+            f_base = j.base;
             f_started += 1;
             sm.jobs_head = f_started;
+            sm.feed_left = f_stop1 - f_k + 1;
         }
         if (f_slot >= 0) {
             const unsigned sg = stage_sa + (unsigned)tslot * 48u;
-            cp_async16_sa(sg, f_q + f_k); cp_async16_sa(sg + 16, f_b + f_k); cp_async16_sa(sg + 32, f_c + f_k);
+            const long long at = f_base + f_k;
+            cp_async16_sa(sg, pr.Q + at); cp_async16_sa(sg + 16, pr.B + at); cp_async16_sa(sg + 32, pr.Ct + at);
             tag = AMRVW_TAG_VALID | ((unsigned)f_slot << AMRVW_TAG_SLOT_SHIFT) | (unsigned)f_k | (f_k == f_start ? AMRVW_TAG_FIRST : 0u) | (f_k == f_stop1 ? AMRVW_TAG_LAST : 0u);
             f_k += 1;
-            sm.feed_left = f_stop1 - f_k + 1;
-        } else {
-            sm.feed_left = 0;
+            if (f_stop1 - f_k < 3 * LE) sm.feed_left = f_stop1 - f_k + 1;      // the manager only needs it near the end of the job
         }
         cp_async_commit();
         sm.ringtag[tslot] = tag;
@@ -308,6 +404,14 @@ __global__ void __launch_bounds__(32 * (NW + 2), 2) stream_kernel(Problem<double
     if (feeds_g) for (int a = 0; a < AMRVW_RING - 1; ++a) request(a);
 
     int r_done = 0;      // retiring thread: jobs completed
+    // accounting of the feeding thread (amrvw_last_profile): lock-steps, of which in the lean loop / with an empty array / with
+    // bulges in flight but nothing to feed
+    long long pn_steps = 0, pn_fast = 0, pn_empty = 0, pn_starved = 0, pc_fast = 0, pc_nap = 0;
+#ifdef AMRVW_STREAM_DEV
+    long long dv_c[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dv_n[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dv_last = clock64();      // development: lock-step time by special operation
+#endif
+    unsigned long long ns_first = 0ull, ns_last = 0ull;      // first / last lock-step with something in the array
+    const long long pc_t0 = clock64();
     for (unsigned t = 0;; ++t) {
         // ---------------- ingest: what the previous lane finished last step
         Rot<double> iq = shfl_up_rot(q0, 32), ib = shfl_up_rot(b0, 32), ic = shfl_up_rot(c0, 32);
@@ -329,43 +433,47 @@ __global__ void __launch_bounds__(32 * (NW + 2), 2) stream_kernel(Problem<double
         b0 = b1; b1 = b2; b2 = ib;
         c0 = c1; c1 = c2; c2 = ic;
         tag0 = tag1; tag1 = tag2; tag2 = itag;
+        if (tag2 & AMRVW_TAG_FIRST) {      // a window enters: this lane creates its bulge NEXT step -- its shift pair is on its way meanwhile
+            const StreamJob& j = sm.jobs[(tag2 >> AMRVW_TAG_SLOT_SHIFT) & (AMRVW_STREAM_JOBS - 1)];
+            if (gl < j.nb && j.mode == 1) {
+                const double2* sp2 = reinterpret_cast<const double2*>(pr.shifts + (long long)j.p * LE + gl);
+                she1 = __ldcg(sp2); she2 = __ldcg(sp2 + 1);
+            }
+        }
 
         // ---------------- what this lane does in this lock-step (the lanes of a warp that differ take their branches in turn)
         const bool cr = (tag1 & AMRVW_TAG_FIRST) != 0u;
         const bool fa = active && (tag2 & AMRVW_TAG_LAST) != 0u;
+        const bool fb = pend_b;
         const bool reg = active && !fa;
+#ifdef AMRVW_STREAM_DEV
+        if (pr.prof && (fa || fb || (cr && active == false))) atomicOr((int*)&sm.sptype, (cr ? 1 : 0) | (fa ? 2 : 0) | (fb ? 4 : 0));
+#endif
         if (cr) {              // window [*, start, start+1]: create the bulge one step before its first chase position
             const StreamJob& j = sm.jobs[(tag1 >> AMRVW_TAG_SLOT_SHIFT) & (AMRVW_STREAM_JOBS - 1)];
             if (gl < j.nb) {
-                const Created o = stream_create(q1, q2, b1, b2, c1, c2, pr.Q + j.base, pr.B + j.base, pr.Ct + j.base, 0, j.start, j.stop, j.mode,
-                                                pr.shifts + (long long)j.p * LE, gl, pr.seed, (uint64_t)j.p, j.ord0 + gl);
+                const Created o = stream_create(q1, q2, b1, b2, c1, c2, j.qm, j.bm, j.cm, she1, she2, j.start, j.stop, j.mode, pr.seed, (uint64_t)j.p, j.ord0 + gl);
                 q1 = o.qa; q2 = o.qb; U = o.U; V = o.V; W = o.W;
                 active = true;
             }
-        } else if (fa) {       // window [stop-1, stop, stop+1]: passthrough_triu, V into Q, U through Q, U <- W U  (RDS.jl:110-128, first part)
-            turnover_fast(b1, b2, V, V, b1, b2);
-            turnover_fast(c2, c1, V, V, c2, c1);
-            turnover_fast(b0, b1, U, U, b0, b1);
-            turnover_fast(c1, c0, U, U, c1, c0);
-            V.s = sign_(sign_(q2.c)) * V.s;          // Q[stop+1]: the diagonal rotator below the window (or the (1,0) sentinel)
-            q1 = fuse(q1, V);
-            turnover_fast(q0, q1, U, U, q0, q1);
-            U = fuse(W, U);
-            active = false; pend_b = true;
-        } else if (pend_b) {   // window [stop, stop+1, *]: U through R, then into Q (second part)
-            turnover_fast(b0, b1, U, U, b0, b1);
-            turnover_fast(c1, c0, U, U, c1, c0);
-            U.s = sign_(sign_(q1.c)) * U.s;
-            q0 = fuse(q0, U);
-            pend_b = false;
         }
-        if (reg) {             // regular position: the 7 turnovers of one chase step as one straight-line block
 #ifndef AMRVW_STRICT
-            AMRVW_CHASE_REGULAR(snap_t, NT);
+        AMRVW_STREAM_COMPUTE(snap_t, NT);       // regular / last-a / last-b lanes in one predicated instruction stream
 #else
+        if (reg) {
             AMRVW_CHASE_GENERAL();
-#endif
+        } else if (fa) {
+            StepState z_ = {q0, q1, q2, b0, b1, b2, c0, c1, c2, U, V, W};
+            stream_last_a_general(z_);
+            q0 = z_.q0; q1 = z_.q1; q2 = z_.q2; b0 = z_.b0; b1 = z_.b1; b2 = z_.b2; c0 = z_.c0; c1 = z_.c1; c2 = z_.c2; U = z_.U; V = z_.V; W = z_.W;
+        } else if (fb) {
+            StepState z_ = {q0, q1, q2, b0, b1, b2, c0, c1, c2, U, V, W};
+            stream_last_b_general(z_);
+            q0 = z_.q0; q1 = z_.q1; q2 = z_.q2; b0 = z_.b0; b1 = z_.b1; b2 = z_.b2; c0 = z_.c0; c1 = z_.c1; c2 = z_.c2; U = z_.U; V = z_.V; W = z_.W;
         }
+#endif
+        if (fa) { active = false; pend_b = true; }
+        else if (fb) pend_b = false;
 
         // ---------------- retire: the last lane of the chain writes back, the last lane of a warp hands on
         if (ret_g) {
@@ -388,17 +496,86 @@ __global__ void __launch_bounds__(32 * (NW + 2), 2) stream_kernel(Problem<double
             sts_rot(so, q0); sts_rot(so + 16, b0); sts_rot(so + 32, c0);
             sm.handtag[warp][par] = tag0;
         }
+
+        // ---------------- can the whole array run lean next?  Every lane chasing inside ONE window (no first / last triple of
+        // a window anywhere in flight) and the rest of that window still to be requested: nothing but regular steps until then
+        const bool clean = active && (tag0 & tag1 & tag2 & AMRVW_TAG_VALID) != 0u && ((tag0 | tag1 | tag2) & (AMRVW_TAG_FIRST | AMRVW_TAG_LAST)) == 0u;
         if (feeds_g) {
-            // nothing in the array and nothing to come: leave; nothing in the array right now: do not spin at full speed
-            const bool empty = f_slot < 0 && sm.jobs_done == f_started;
-            if ((empty && sm.no_more && f_started == sm.jobs_tail) || sm.no_more == 2) sm.quit = 1;     // 2: aborted by the watchdog
-            sm.idle = empty ? 1 : 0;
+            int code = 0;      // > 0: lock-steps the array may run lean if every lane is clean; -1: nothing in the array (nap); -2: leave
+            if (f_slot >= 0) {
+                const int left = f_stop1 - f_k + 1;               // triples of the window not yet requested
+                if (left >= 16 && f_k - f_start >= 4) code = left;
+            } else {
+                // nothing to feed.  Nothing in the array either: do not spin at full speed; and nothing to come: leave
+                const bool empty = sm.jobs_done == f_started;
+                if (empty) code = -1;
+                if ((empty && sm.no_more && f_started == sm.jobs_tail) || sm.no_more == 2) code = -2;     // no_more == 2: aborted by the watchdog
+                pn_empty += empty ? 1 : 0; pn_starved += empty ? 0 : 1;
+            }
+            sm.ctl = code;
+            pn_steps += 1;
+            if (pr.prof && code >= 0 && (t & 63u) == 0u) { ns_last = global_ns(); if (ns_first == 0ull) ns_first = ns_last; }
         }
-        AMRVW_BAR_CHASE(32 * NW);
-        if (sm.quit) break;
-        if (sm.idle) __nanosleep(400);
+        const bool all_clean = bar_chase_and<32 * NW>(clean);      // the lock-step's barrier, with the AND of `clean` over the array
+#ifdef AMRVW_STREAM_DEV
+        if (pr.prof && feeds_g) {
+            const long long now = clock64();
+            const int ty = sm.sptype & 7;
+            if (sm.ctl >= 0) { dv_c[ty] += now - dv_last; dv_n[ty] += 1; }
+            dv_last = now; sm.sptype = 0;
+        }
+#endif
+        const int code = sm.ctl;
+        if (code == -2) break;
+        if (code == -1) { const long long c0_ = clock64(); __nanosleep(400); pc_nap += clock64() - c0_; }
+        const int fk = all_clean ? code : 0;
+        if (fk > 0) {
+            // ---------------- the lean loop of chain.cuh for fk lock-steps: same operations, no tags, no case analysis
+            StreamJob& j = sm.jobs[(tag0 >> AMRVW_TAG_SLOT_SHIFT) & (AMRVW_STREAM_JOBS - 1)];
+            const int idx_next = (int)(tag2 & AMRVW_TAG_INDEX_MASK) + 3 * gl + 1;     // index the feeding thread ingests next
+            const int t0 = (int)t + 1, t1 = t0 + fk;
+            int sp = ret_g ? j.sp : 0;
+            const long long pc_f0 = clock64();
+            StepState z = {q0, q1, q2, b0, b1, b2, c0, c1, c2, U, V, W};
+            sp = chain_lean<NW, 1>(z, pr.Q + j.base, pr.B + j.base, pr.Ct + j.base, stage_sa, snap_sa, hand_sa, pr.dstack + j.base, sp, idx_next - t0, t0, t1, warp, lane32);
+            q0 = z.q0; q1 = z.q1; q2 = z.q2; b0 = z.b0; b1 = z.b1; b2 = z.b2; c0 = z.c0; c1 = z.c1; c2 = z.c2; U = z.U; V = z.V; W = z.W;
+            pc_fast += clock64() - pc_f0;
+            tag0 += (unsigned)fk; tag1 += (unsigned)fk; tag2 += (unsigned)fk;
+            if (ret_g) j.sp = sp;
+            if (ret_h) sm.handtag[warp][(unsigned)(t1 - 1) & 1u] = tag0;
+            if (feeds_g) {
+                f_k += fk;                                     // the window's remaining triples have all been requested
+                sm.feed_left = f_stop1 - f_k + 1;
+                const unsigned base_tag = AMRVW_TAG_VALID | ((unsigned)f_slot << AMRVW_TAG_SLOT_SHIFT);
+                for (int a = 0; a < AMRVW_RING - 1; ++a) {
+                    const int idx = f_k - (AMRVW_RING - 1) + a;
+                    sm.ringtag[(unsigned)(t1 + a) & (AMRVW_RING - 1)] = base_tag | (unsigned)idx | (idx == f_stop1 ? AMRVW_TAG_LAST : 0u);
+                }
+                pn_steps += fk; pn_fast += fk;
+            }
+            t = (unsigned)(t1 - 1);
+            AMRVW_BAR_CHASE(32 * NW);      // the tags written above, before the next step reads them
+#ifdef AMRVW_STREAM_DEV
+            if (pr.prof && feeds_g) dv_last = clock64();
+#endif
+        }
     }
-    if (feeds_g) cp_async_wait_all();
+    if (feeds_g) { cp_async_wait_all(); sm.quit = 1; }
+    if (pr.prof && feeds_g) {
+        atomicAdd(pr.prof + 0, (unsigned long long)(clock64() - pc_t0));   // chase loop, feeding thread
+        atomicAdd(pr.prof + 2, (unsigned long long)pn_fast);               // lock-steps in the lean loop
+        atomicAdd(pr.prof + 3, (unsigned long long)pc_fast);               // cycles in the lean loop
+        atomicAdd(pr.prof + 13, (unsigned long long)pc_nap);               // cycles napping with an empty array
+        atomicAdd(pr.prof + 4, (unsigned long long)pn_steps);
+        atomicAdd(pr.prof + 5, (unsigned long long)pn_empty);              // lock-steps with nothing in the array
+        atomicAdd(pr.prof + 6, (unsigned long long)f_started);             // jobs
+        atomicAdd(pr.prof + 7, (unsigned long long)pn_starved);            // lock-steps with bulges in flight but no job to feed
+        atomicAdd(pr.prof + 14, ns_last ? (ns_last - *sq.t0) / 1000ull : 0ull);     // sum over CTAs of the time of their last busy step (us)
+        atomicAdd(pr.prof + 15, ns_first ? (ns_first - *sq.t0) / 1000ull : 0ull);   // and of their first
+#ifdef AMRVW_STREAM_DEV
+        for (int a = 0; a < 8; ++a) { atomicAdd(pr.prof + 16 + a, (unsigned long long)dv_c[a]); atomicAdd(pr.prof + 24 + a, (unsigned long long)dv_n[a]); }
+#endif
+    }
 }
 
 template <int NW, int MH> constexpr size_t stream_raw_bytes() { return 12 * 32 * NW * sizeof(double2) + sizeof(ShiftScratch<MH>); }
@@ -409,7 +586,7 @@ template <int NW, int MH>
 static cudaError_t launch_stream(const Problem<double>& pr, const PipeParams& pp, const StreamBufs& sb, int sm_count, cudaStream_t st) {
     StreamQueues sq;
     sq.ready = sb.ready; sq.ready_slots = sb.ready_slots; sq.work = sb.work; sq.work_slots = sb.work_slots; sq.mask = sb.mask; sq.remaining = sb.remaining;
-    sq.progress = sb.remaining + 1; sq.abort_flag = pr.counters + CNT_ABORT;
+    sq.progress = sb.remaining + 1; sq.abort_flag = pr.counters + CNT_ABORT; sq.t0 = reinterpret_cast<unsigned long long*>(sb.remaining + 2);
     stream_init_queues_kernel<<<(int)((sb.mask + 1 + 255) / 256), 256, 0, st>>>(sq);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -421,6 +598,7 @@ static cudaError_t launch_stream(const Problem<double>& pr, const PipeParams& pp
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stream_kernel<NW, MH>, 32 * (NW + 2), smem)) != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 2) per_sm = 2;
+    if (pp.stream_ctas > 0 && pp.stream_ctas < per_sm) per_sm = pp.stream_ctas;
     // every CTA must be resident (they exchange polynomials through the queues); more CTAs than polynomials would only poll
     const long long cap = (long long)sm_count * per_sm;
     const int blocks = (int)(pr.nbatch < cap ? pr.nbatch : cap);
@@ -484,11 +662,7 @@ AMRVW_DI void ustream_manager(const Problem<double>& pr, const StreamQueues& sq,
         if (!sm.no_more && tail - sm.jobs_head == 0 && sm.feed_left < 6 * L + 64 && tail - mgr_done < AMRVW_USTREAM_JOBS - 1) {
             const int p = mpmc_try_pop(sq.ready, sq.ready_slots, sq.mask);
             if (p >= 0) {
-                const PolyRec* r = pr.rec + p;
-                StreamJob j;
-                j.p = p; j.base = pr.offsets[p] + (long long)pr.extra * p;
-                j.mode = __ldcg(&r->mode); j.nb = __ldcg(&r->nb); j.start = __ldcg(&r->ls.ctr.start_index); j.stop = __ldcg(&r->ls.ctr.stop_index);
-                j.ord0 = __ldcg(&r->ls.ord); j.sp = __ldcg(&r->ls.sp); j.pad = 0;
+                const StreamJob j = stream_job_from_record(pr, p);
                 sm.jobs[tail % AMRVW_USTREAM_JOBS] = j;
                 __threadfence_block();
                 sm.jobs_tail = tail + 1;
@@ -518,6 +692,7 @@ AMRVW_DI void ustream_service(const Problem<double>& pr, const PipeParams& pp, c
             __nanosleep(500);
             continue;
         }
+        const long long pc_s0 = clock64();
         __threadfence();
         int m0 = 0;
         if (lane == 0 && p >= 0) m0 = unit_driver(pr, pp, L, p);
@@ -530,6 +705,7 @@ AMRVW_DI void ustream_service(const Problem<double>& pr, const PipeParams& pp, c
             __threadfence();
             if (m0 == 0) atomicSub(sq.remaining, 1u);
             else mpmc_push(sq.ready, sq.ready_slots, sq.mask, p);
+            if (pr.prof) { atomicAdd(pr.prof + 1, (unsigned long long)(clock64() - pc_s0)); atomicAdd(pr.prof + 10, 1ull); }
         }
         (void)G;
     }
@@ -567,9 +743,10 @@ __global__ void __launch_bounds__(32 * (NW + 1 + NS), 2) ustream_kernel(Problem<
     q0 = q1 = q2 = b0 = b1 = b2 = c0 = c1 = c2 = U = V = W = make_rot<double>(1.0, 0.0);
     unsigned tag0 = 0u, tag1 = 0u, tag2 = 0u;
     bool active = false, pend_b = false;
+    double2 she1 = make_double2(0.0, 0.0), she2 = make_double2(0.0, 0.0);      // shift pair of the bulge this lane creates next
 
     int f_slot = -1, f_k = 0, f_stop1 = -1, f_start = 0;
-    const Rot<double>* f_q = nullptr; const Rot<double>* f_b = nullptr; const Rot<double>* f_c = nullptr;
+    long long f_base = 0;                                      // chain slot of the job being fed
     int f_started = 0;
     auto request = [&](const int tslot) {
         unsigned tag = 0u;
@@ -578,13 +755,14 @@ __global__ void __launch_bounds__(32 * (NW + 1 + NS), 2) ustream_kernel(Problem<
             __threadfence_block();
             const StreamJob& j = sm.jobs[f_started % AMRVW_USTREAM_JOBS];
             f_slot = f_started % AMRVW_USTREAM_JOBS; f_start = j.start; f_k = j.start; f_stop1 = j.stop + 1;
-            f_q = pr.Q + j.base; f_b = pr.B + j.base; f_c = pr.Ct + j.base;
+            f_base = j.base;
             f_started += 1;
             sm.jobs_head = f_started;
         }
         if (f_slot >= 0) {
             const unsigned sg = stage_sa + (unsigned)tslot * 48u;
-            cp_async16_sa(sg, f_q + f_k); cp_async16_sa(sg + 16, f_b + f_k); cp_async16_sa(sg + 32, f_c + f_k);
+            const long long at = f_base + f_k;
+            cp_async16_sa(sg, pr.Q + at); cp_async16_sa(sg + 16, pr.B + at); cp_async16_sa(sg + 32, pr.Ct + at);
             tag = AMRVW_TAG_VALID | ((unsigned)f_slot << AMRVW_TAG_SLOT_SHIFT) | (unsigned)f_k | (f_k == f_start ? AMRVW_TAG_FIRST : 0u) | (f_k == f_stop1 ? AMRVW_TAG_LAST : 0u);
             f_k += 1;
             sm.feed_left = f_stop1 - f_k + 1;
@@ -598,6 +776,8 @@ __global__ void __launch_bounds__(32 * (NW + 1 + NS), 2) ustream_kernel(Problem<
 
     int r_done = 0;
     bool my_quit = false;      // this lane's pipeline is through (feeding lane decides, the group follows)
+    long long pn_steps = 0, pn_empty = 0, pn_starved = 0;
+    const long long pc_t0 = clock64();
     for (unsigned t = 0;; ++t) {
         Rot<double> iq = shfl_up_rot(q0, L), ib = shfl_up_rot(b0, L), ic = shfl_up_rot(c0, L);
         unsigned itag = __shfl_up_sync(0xffffffffu, tag0, 1, L);
@@ -613,42 +793,43 @@ __global__ void __launch_bounds__(32 * (NW + 1 + NS), 2) ustream_kernel(Problem<
         b0 = b1; b1 = b2; b2 = ib;
         c0 = c1; c1 = c2; c2 = ic;
         tag0 = tag1; tag1 = tag2; tag2 = itag;
+        if (tag2 & AMRVW_TAG_FIRST) {      // a window enters: this lane creates its bulge NEXT step -- its shift pair is on its way meanwhile
+            const StreamJob& j = sm.jobs[(tag2 >> AMRVW_TAG_SLOT_SHIFT) & (AMRVW_USTREAM_JOBS - 1)];
+            if (lane < j.nb && j.mode == 1) {
+                const double2* sp2 = reinterpret_cast<const double2*>(pr.shifts + (long long)j.p * L + lane);
+                she1 = __ldcg(sp2); she2 = __ldcg(sp2 + 1);
+            }
+        }
 
         const bool cr = (tag1 & AMRVW_TAG_FIRST) != 0u;
         const bool fa = active && (tag2 & AMRVW_TAG_LAST) != 0u;
+        const bool fb = pend_b;
         const bool reg = active && !fa;
-        if (cr) {
+        if (cr) {              // window [*, start, start+1]: create the bulge one step before its first chase position
             const StreamJob& j = sm.jobs[(tag1 >> AMRVW_TAG_SLOT_SHIFT) & (AMRVW_USTREAM_JOBS - 1)];
             if (lane < j.nb) {
-                const Created o = stream_create(q1, q2, b1, b2, c1, c2, pr.Q + j.base, pr.B + j.base, pr.Ct + j.base, 0, j.start, j.stop, j.mode,
-                                                pr.shifts + (long long)j.p * L, lane, pr.seed, (uint64_t)j.p, j.ord0 + lane);
+                const Created o = stream_create(q1, q2, b1, b2, c1, c2, j.qm, j.bm, j.cm, she1, she2, j.start, j.stop, j.mode, pr.seed, (uint64_t)j.p, j.ord0 + lane);
                 q1 = o.qa; q2 = o.qb; U = o.U; V = o.V; W = o.W;
                 active = true;
             }
-        } else if (fa) {
-            turnover_fast(b1, b2, V, V, b1, b2);
-            turnover_fast(c2, c1, V, V, c2, c1);
-            turnover_fast(b0, b1, U, U, b0, b1);
-            turnover_fast(c1, c0, U, U, c1, c0);
-            V.s = sign_(sign_(q2.c)) * V.s;
-            q1 = fuse(q1, V);
-            turnover_fast(q0, q1, U, U, q0, q1);
-            U = fuse(W, U);
-            active = false; pend_b = true;
-        } else if (pend_b) {
-            turnover_fast(b0, b1, U, U, b0, b1);
-            turnover_fast(c1, c0, U, U, c1, c0);
-            U.s = sign_(sign_(q1.c)) * U.s;
-            q0 = fuse(q0, U);
-            pend_b = false;
         }
-        if (reg) {
 #ifndef AMRVW_STRICT
-            AMRVW_CHASE_REGULAR(snap_t, NT);
+        AMRVW_STREAM_COMPUTE(snap_t, NT);       // regular / last-a / last-b lanes in one predicated instruction stream
 #else
+        if (reg) {
             AMRVW_CHASE_GENERAL();
-#endif
+        } else if (fa) {
+            StepState z_ = {q0, q1, q2, b0, b1, b2, c0, c1, c2, U, V, W};
+            stream_last_a_general(z_);
+            q0 = z_.q0; q1 = z_.q1; q2 = z_.q2; b0 = z_.b0; b1 = z_.b1; b2 = z_.b2; c0 = z_.c0; c1 = z_.c1; c2 = z_.c2; U = z_.U; V = z_.V; W = z_.W;
+        } else if (fb) {
+            StepState z_ = {q0, q1, q2, b0, b1, b2, c0, c1, c2, U, V, W};
+            stream_last_b_general(z_);
+            q0 = z_.q0; q1 = z_.q1; q2 = z_.q2; b0 = z_.b0; b1 = z_.b1; b2 = z_.b2; c0 = z_.c0; c1 = z_.c1; c2 = z_.c2; U = z_.U; V = z_.V; W = z_.W;
         }
+#endif
+        if (fa) { active = false; pend_b = true; }
+        else if (fb) pend_b = false;
 
         if (retires && (tag0 & AMRVW_TAG_VALID)) {
             StreamJob& j = sm.jobs[(tag0 >> AMRVW_TAG_SLOT_SHIFT) & (AMRVW_USTREAM_JOBS - 1)];
@@ -667,6 +848,7 @@ __global__ void __launch_bounds__(32 * (NW + 1 + NS), 2) ustream_kernel(Problem<
         if (feeds) {
             empty = f_slot < 0 && sm.jobs_done == f_started;
             if (!my_quit && ((empty && sm.no_more && f_started == sm.jobs_tail) || sm.no_more == 2)) { my_quit = true; sm.quit = 1; }
+            if (!my_quit) { pn_steps += 1; pn_empty += empty ? 1 : 0; pn_starved += (!empty && f_slot < 0) ? 1 : 0; }
         }
         __syncwarp();          // the retiring lane's writes to the job ring before the next step's reads
         // leave when every pipeline of the warp is through; sleep when none has anything in flight
@@ -675,6 +857,13 @@ __global__ void __launch_bounds__(32 * (NW + 1 + NS), 2) ustream_kernel(Problem<
         if ((__ballot_sync(0xffffffffu, feeds && empty) & feeders) == feeders) __nanosleep(400);
     }
     if (feeds) cp_async_wait_all();
+    if (pr.prof && feeds) {
+        if (lane32 == 0) atomicAdd(pr.prof + 0, (unsigned long long)(clock64() - pc_t0));   // chase loop, per warp
+        atomicAdd(pr.prof + 4, (unsigned long long)pn_steps);                                // per pipeline
+        atomicAdd(pr.prof + 5, (unsigned long long)pn_empty);
+        atomicAdd(pr.prof + 6, (unsigned long long)f_started);
+        atomicAdd(pr.prof + 7, (unsigned long long)pn_starved);
+    }
 }
 
 template <int L, int MH, int NW, int NS> constexpr size_t ustream_raw_bytes() { return 12 * 32 * NW * sizeof(double2) + (size_t)NS * (32 / L) * sizeof(ShiftScratch<MH>); }
@@ -683,7 +872,7 @@ template <int L, int MH, int NW, int NS>
 static cudaError_t launch_ustream(const Problem<double>& pr, const PipeParams& pp, const StreamBufs& sb, int sm_count, cudaStream_t st) {
     StreamQueues sq;
     sq.ready = sb.ready; sq.ready_slots = sb.ready_slots; sq.work = sb.work; sq.work_slots = sb.work_slots; sq.mask = sb.mask; sq.remaining = sb.remaining;
-    sq.progress = sb.remaining + 1; sq.abort_flag = pr.counters + CNT_ABORT;
+    sq.progress = sb.remaining + 1; sq.abort_flag = pr.counters + CNT_ABORT; sq.t0 = reinterpret_cast<unsigned long long*>(sb.remaining + 2);
     stream_init_queues_kernel<<<(int)((sb.mask + 1 + 255) / 256), 256, 0, st>>>(sq);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -695,6 +884,7 @@ static cudaError_t launch_ustream(const Problem<double>& pr, const PipeParams& p
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ustream_kernel<L, MH, NW, NS>, 32 * (NW + 1 + NS), smem)) != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 2) per_sm = 2;
+    if (pp.stream_ctas > 0 && pp.stream_ctas < per_sm) per_sm = pp.stream_ctas;
     constexpr int NP = NW * (32 / L);
     const long long cap = (long long)sm_count * per_sm;
     const long long want = (pr.nbatch + NP - 1) / NP;       // more pipelines than polynomials would only poll

@@ -62,11 +62,11 @@ class Context:
         if rc != 0:
             raise AmrvwError(f"amrvw error {rc}: {self._lib.amrvw_last_error(self._h).decode()}")
 
-    def set_options(self, schedule=0, lanes_per_poly=0, shift_reuse=0, small_window=0, shift_solver=0, seed=0, it_count=0, it_max_factor=0, tol=0.0):
+    def set_options(self, schedule=0, lanes_per_poly=0, shift_reuse=0, small_window=0, shift_solver=0, seed=0, it_count=0, it_max_factor=0, tol=0.0, stream_ctas_per_sm=0):
         """it_count / it_max_factor / tol: the reference's IT_COUNT = 15 (create-bulge.jl:9), it_max = 20 n
         (AMRVW_algorithm.jl:25) and deflation tolerance eps (AMRVW_algorithm.jl:184); 0 = those values."""
         o = Options(int(schedule), int(lanes_per_poly), int(shift_reuse), int(small_window), int(shift_solver), int(it_count), int(seed),
-                    int(it_max_factor), 0, float(tol))
+                    int(it_max_factor), int(stream_ctas_per_sm), float(tol))
         self._check(self._lib.amrvw_set_options(self._h, ctypes.byref(o)))
 
     def set_stream(self, cuda_stream_handle):
@@ -103,6 +103,11 @@ class Context:
         keys = ("cycles_units", "cycles_phase_a", "cycles_lean", "cycles_general", "steps_lean", "steps_general", "lean_calls", "unit_visits",
                 "us_setup", "us_main", "cycles_driver", "us_small", "us_finish", "cycles_pop", "cycles_loop", "lane_cycles_special")
         return {k: int(out[i]) for i, k in enumerate(keys)}
+
+    def debug_counters(self):
+        out = (ctypes.c_int64 * 48)()
+        self._check(self._lib.amrvw_debug_counters(self._h, out))
+        return [int(v) for v in out]
 
     # -- host buffers (CSR) in, host buffers out
     def roots_csr(self, coeffs, offsets, ws=None, want_stats=True):

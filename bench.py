@@ -60,6 +60,8 @@ def parse():
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--reuse", type=int, default=0)
     ap.add_argument("--small", type=int, default=0)
+    ap.add_argument("--stream-ctas", type=int, default=0, help="streamed schedule: resident CTAs per SM (development)")
+    ap.add_argument("--lib", default=None, help="another build of the library (development: kernel variants under build/)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="polynomials in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -219,7 +221,7 @@ def main():
     batch = share                                      # from here on: this rank's polynomials
     flat, ws, offsets, ncoef = make_inputs(kind, batch, degree, law, seed, lo)
     total = int(offsets[-1])
-    ctx = A.Context(device=local_rank, seed=seed, schedule=args.schedule, lanes_per_poly=args.lanes, shift_reuse=args.reuse, small_window=args.small)
+    ctx = A.Context(device=local_rank, seed=seed, schedule=args.schedule, lanes_per_poly=args.lanes, shift_reuse=args.reuse, small_window=args.small, stream_ctas_per_sm=args.stream_ctas, lib_path=args.lib)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
 
@@ -246,6 +248,7 @@ def main():
         st = step(stats=True)           # warm-up also yields the per-step counters (launches, turnovers)
     torch.cuda.synchronize()
     prof = ctx.last_profile() if args.schedule != 1 else None   # per-kernel CUDA-event times (+ warp-cycle counters, RDS) of the last warm-up step
+    dv = ctx.debug_counters() if args.schedule != 1 else None
     n_unconv = int(d_u.sum().item())
     nroots_ok = int(d_n.sum().item())
 
@@ -273,7 +276,7 @@ def main():
         h_r = torch.zeros(2 * (total + 1), dtype=torch.float64).pin_memory()
         h_n = torch.zeros(batch, dtype=torch.int32).pin_memory()
         h_u = torch.zeros(batch, dtype=torch.int32).pin_memory()
-        lib = A.load()
+        lib = A.load(path=args.lib)
         import ctypes
         P = ctypes.c_void_p
 
@@ -394,7 +397,18 @@ def main():
                         "note": "algorithmic bytes per chase step: RDS 96 B / 7 turnovers, CSS 208 B / 3, pencil 160 B / 11 (SURVEY 8d); the path is not HBM-bound"}}
     if prof and prof["us_main"] > 0:
         roofline["kernel_times_ms"] = {"setup": prof["us_setup"] / 1e3, "main": prof["us_main"] / 1e3, "small_windows": prof["us_small"] / 1e3, "finish": prof["us_finish"] / 1e3}
-    if prof and prof["cycles_units"] > 0:
+    if prof and st.get("schedule_used") == 3:
+        # stream.cuh accounting (feeding threads): lock-steps, with an empty array, with bulges in flight but nothing to feed
+        steps = max(prof["steps_lean"], 1)
+        roofline["stream_profile"] = {"chase_cycles_per_lock_step": prof["cycles_units"] / steps, "lean_share_of_lock_steps": prof["cycles_lean"] / steps,
+                                      "lock_steps": prof["steps_lean"], "empty_share": prof["steps_general"] / steps, "starved_share": prof["unit_visits"] / steps,
+                                      "jobs": prof["lean_calls"], "phase_a_count": prof["cycles_driver"], "phase_a_cycles_each": prof["cycles_phase_a"] / max(prof["cycles_driver"], 1),
+                                      "lean_cycles_per_step": prof["cycles_general"] / max(prof["cycles_lean"], 1), "nap_share_of_cycles": prof["cycles_pop"] / max(prof["cycles_units"], 1),
+                                      "other_cycles_per_step": (prof["cycles_units"] - prof["cycles_general"] - prof["cycles_pop"]) / max(steps - prof["cycles_lean"] - prof["steps_general"], 1),
+                                      "cta_last_busy_ms_sum": prof["cycles_loop"] / 1e3, "cta_first_busy_ms_sum": prof["lane_cycles_special"] / 1e3}
+        if dv and any(dv[8:16]):
+            roofline["stream_profile"]["generic_step_cycles_by_special"] = {k: (dv[i] / dv[8 + i] if dv[8 + i] else None, dv[8 + i]) for i, k in enumerate(["none", "create", "last_a", "create+?", "last_b", "create+last_b", "last_a+last_b", "all"])}
+    elif prof and prof["cycles_units"] > 0:
         busy = max(prof["cycles_units"], 1)
         roofline["warp_cycle_shares"] = {"phase_a": prof["cycles_phase_a"] / busy, "lean_chase": prof["cycles_lean"] / busy, "fill_drain_chase": prof["cycles_general"] / busy,
                                          "queue_wait_vs_busy": prof["cycles_pop"] / busy, "lean_cycles_per_step": prof["cycles_lean"] / max(prof["steps_lean"], 1)}

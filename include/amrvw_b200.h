@@ -78,7 +78,7 @@ typedef struct amrvw_options {
     int32_t it_count;        /* IT_COUNT, create-bulge.jl:9; default 15                                */
     uint64_t seed;           /* exceptional (random) shifts: counter-based, reproducible              */
     int32_t it_max_factor;   /* it_max = it_max_factor * n, AMRVW_algorithm.jl:25; default 20          */
-    int32_t reserved;        /* must be 0 */
+    int32_t stream_ctas_per_sm; /* streamed schedule: resident CTAs per SM (1 or 2); 0 = auto                  */
     double tol;              /* |s| <= tol deflates, AMRVW_algorithm.jl:184; default eps(Float64)      */
 } amrvw_options;
 
@@ -185,6 +185,10 @@ int amrvw_selftest_robust(amrvw_ctx* ctx, int64_t n, double* out4);
  * [7] phase-B warp launches; kernel times in microseconds: [8] set-up, [9] phase A (all rounds),
  * [10] phase B (all rounds), [11] small windows, [12] finish; [13] rounds, [14] small windows}. */
 int amrvw_last_profile(amrvw_ctx* ctx, int64_t* out16);
+
+/* Development counters of the last call made with stats (48 slots whose meaning belongs to the kernel under study;
+ * see the kernel source).  No reference counterpart. */
+int amrvw_debug_counters(amrvw_ctx* ctx, int64_t* out48);
 
 int amrvw_version(void);
 

@@ -1596,7 +1596,7 @@ int orc_roots_batch(const double* coeffs, const int64_t* offsets, int64_t B, int
     for (int64_t p = 0; p < B; ++p) {
         Stats st;
         int len = (int)(offsets[p + 1] - offsets[p]);
-        cplx* out = reinterpret_cast<cplx*>(roots_reim) + (offsets[p] - p);
+        cplx* out = reinterpret_cast<cplx*>(roots_reim) + offsets[p];   // one slot per coefficient: an empty vector owns none and cannot shift its neighbours
         int nr = 0;
         if (is_complex) roots_one<cplx>(reinterpret_cast<const cplx*>(coeffs) + offsets[p], len, out, &nr, seed, (uint64_t)p, st, sched, P);
         else roots_one<double>(coeffs + offsets[p], len, out, &nr, seed, (uint64_t)p, st, sched, P);

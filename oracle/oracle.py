@@ -56,7 +56,7 @@ def roots_csr(coeffs, offsets, ws=None, seed=0, threads=0, sched=0, L=8, small=2
     st = OStats()
     pp = (OStats * max(B, 1))() if per_poly else None
     if ws is None:
-        roff = offsets - np.arange(B + 1, dtype=np.int64)
+        roff = offsets.copy()          # polynomial p's roots start at complex slot offsets[p]
         out = np.zeros(int(offsets[-1]) + 1, dtype=np.complex128)
         lib().orc_roots_batch(_p(coeffs), _p(offsets), ctypes.c_int64(B), int(cx), _p(out), _p(nroots), ctypes.byref(st),
                               pp, ctypes.c_uint64(seed), int(threads), int(sched), int(L), int(small + 1000 * reuse + 100000 * dense))

@@ -49,7 +49,7 @@ def test_default_options_and_argument_errors_need_no_gpu(A):
     lib.amrvw_default_options(ctypes.byref(o))
     assert (o.schedule, o.lanes_per_poly, o.shift_reuse, o.small_window) == (0, 0, 0, 0)
     # the reference's constants (create-bulge.jl:9, AMRVW_algorithm.jl:25,184) are the defaults of the options
-    assert (o.it_count, o.it_max_factor, o.reserved) == (15, 20, 0) and o.tol == np.finfo(np.float64).eps
+    assert (o.it_count, o.it_max_factor, o.stream_ctas_per_sm) == (15, 20, 0) and o.tol == np.finfo(np.float64).eps
     assert ctypes.sizeof(A.Options) == 48
     assert lib.amrvw_set_options(None, ctypes.byref(o)) == -1
     assert lib.amrvw_destroy(None) == 0
