@@ -179,7 +179,7 @@ int amrvw_set_options(amrvw_ctx* ctx, const amrvw_options* opt) {
     if (opt->shift_solver < 0 || opt->shift_solver > 2) return fail(ctx, AMRVW_ERR_ARGUMENT, "shift_solver must be 0, 1 or 2");
     if (opt->it_count < 0 || opt->it_max_factor < 0) return fail(ctx, AMRVW_ERR_ARGUMENT, "it_count and it_max_factor must be >= 0 (0 = the reference's 15 and 20)");
     if (!(opt->tol >= 0.0) || opt->tol > 1e-4) return fail(ctx, AMRVW_ERR_ARGUMENT, "tol must be in [0, 1e-4] (0 = the reference's eps)");
-    if (opt->stream_ctas_per_sm < 0 || opt->stream_ctas_per_sm > 2) return fail(ctx, AMRVW_ERR_ARGUMENT, "stream_ctas_per_sm must be 0, 1 or 2");
+    if (opt->stream_ctas_per_sm < 0 || opt->stream_ctas_per_sm > 3) return fail(ctx, AMRVW_ERR_ARGUMENT, "stream_ctas_per_sm must be 0..3");
     ctx->opt = *opt;
     if (ctx->opt.it_count == 0) ctx->opt.it_count = 15;
     if (ctx->opt.it_max_factor == 0) ctx->opt.it_max_factor = 20;

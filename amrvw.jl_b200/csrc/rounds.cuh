@@ -599,7 +599,10 @@ static void choose_pipe_params(const amrvw_options& opt, long long nbatch, int m
         // warps (chain.cuh, 128 bulges) while every CTA is resident, <= 3 per SM (226 vs 252 ms at 444 polynomials,
         // 348 vs 255 at 520; config 5: 800 vs 1720 ms); at degree 1500 the chain loses (105 vs 95 ms at 400)
         if (degree >= 1200 && nbatch * 32 <= (long long)sm_count * 410) L = 32;
-        if (L == 32 && degree >= 2500 && nbatch <= (long long)sm_count * 3) L = 128;
+        // round 2 (gpurun_out/r2b_sweep.txt, r2k_sweep.txt; degree 3000): 375 polynomials 205-211 ms streamed (stream.cuh) against
+        // 345 ms with one CTA per polynomial (two CTAs fit an SM, the 79 polynomials beyond 296 wait for a second wave);
+        // 750: 303 ms streamed, 247 ms with 32 lanes on the unit queue; 1500: 562 vs 333 ms
+        if (L == 32 && degree >= 2500 && nbatch * 2 <= (long long)sm_count * 7) L = 128;
     }
     // chained warps: one CTA per polynomial (chain.cuh) while there are fewer polynomials than SMs can hold two of;
     // above that the CTAs take the fat steps of all polynomials as one stream (stream.cuh): no fill/drain, phase A hidden
@@ -609,9 +612,9 @@ static void choose_pipe_params(const amrvw_options& opt, long long nbatch, int m
     if (opt.schedule == AMRVW_SCHEDULE_STREAMED && (L == 16 || L == 32)) pp.stream = 1;     // sub-warp pipelines (stream.cuh, second half)
     if (L == 128 || L == 64) {
         if (opt.schedule == AMRVW_SCHEDULE_STREAMED) pp.stream = 1;
-        else if (opt.schedule == AMRVW_SCHEDULE_AUTO && opt.lanes_per_poly == 0 && nbatch >= (long long)sm_count * 2 + sm_count / 4) pp.stream = 1;
+        else if (opt.schedule == AMRVW_SCHEDULE_AUTO && opt.lanes_per_poly == 0 && nbatch > (long long)sm_count * 2) pp.stream = 1;     // more polynomials than resident chain CTAs
     }
-    pp.reuse = opt.shift_reuse ? opt.shift_reuse : (L == 32 ? 4 : (pp.stream && L >= 64 ? 8 : 2));   // 32 lanes: 16 shifts x 4 beat 32 x 2 by 4-8% (gpurun_out/sweep63.log)
+    pp.reuse = opt.shift_reuse ? opt.shift_reuse : (L == 32 ? 4 : (pp.stream && L >= 64 ? L / 16 : 2));   // 32 lanes: 16 shifts x 4 beat 32 x 2 by 4-8% (gpurun_out/sweep63.log)
     if (pp.reuse > L / 2) pp.reuse = L / 2 > 0 ? L / 2 : 1;
     while (2 * L / pp.reuse > 64) pp.reuse *= 2;     // the largest dense trailing block is 64 x 64
     const int mshift = 2 * L / pp.reuse;

@@ -337,7 +337,7 @@ AMRVW_DI void stream_service(const Problem<double>& pr, const PipeParams& pp, co
 }
 
 template <int NW, int MH>
-__global__ void __launch_bounds__(32 * (NW + 2), 2) stream_kernel(Problem<double> pr, PipeParams pp, StreamQueues sq) {
+__global__ void __launch_bounds__(32 * (NW + 2), NW <= 2 ? 3 : 2) stream_kernel(Problem<double> pr, PipeParams pp, StreamQueues sq) {
     constexpr int LE = 32 * NW;
     [[maybe_unused]] constexpr int NT = LE;
     extern __shared__ __align__(16) unsigned char raw[];       // [12][NT] step snapshots, then the service warp's shift scratch
@@ -597,7 +597,7 @@ static cudaError_t launch_stream(const Problem<double>& pr, const PipeParams& pp
     if ((e = cudaFuncSetAttribute(stream_kernel<NW, MH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stream_kernel<NW, MH>, 32 * (NW + 2), smem)) != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 2) per_sm = 2;
+    if (per_sm > (NW <= 2 ? 3 : 2)) per_sm = NW <= 2 ? 3 : 2;
     if (pp.stream_ctas > 0 && pp.stream_ctas < per_sm) per_sm = pp.stream_ctas;
     // every CTA must be resident (they exchange polynomials through the queues); more CTAs than polynomials would only poll
     const long long cap = (long long)sm_count * per_sm;

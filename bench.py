@@ -162,6 +162,8 @@ def main():
         degree = args.degree
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference" and world == 1 and args.gpus > 1:
+        world = args.gpus          # launched without torchrun: describe the same N-GPU workload our arm runs
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     from amrvw_jl_b200 import synth as _synth
     if args.config == "c5" and not args.batch and not args.weak:
@@ -215,8 +217,10 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: this framework has no CPU path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    host_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        host_group = dist.new_group(backend="gloo")      # host-side barriers: a rank waiting in an NCCL barrier keeps a kernel spinning on its GPU
 
     batch = share                                      # from here on: this rank's polynomials
     flat, ws, offsets, ncoef = make_inputs(kind, batch, degree, law, seed, lo)
@@ -307,6 +311,8 @@ def main():
         # ---- the same batch through ONE call of ONE process: a multi-device context over all N GPUs (amrvw_create_multi)
         if world > 1 and not args.weak and kind == "rds_f64":
             barrier()
+            torch.cuda.synchronize()
+            dist.barrier(group=host_group)            # every GPU idle from here on: rank 0 drives all of them from one process
             if rank == 0:
                 try:
                     fa, _, oa, _ = make_inputs(kind, total_batch, degree, law, seed, 0)
@@ -330,7 +336,7 @@ def main():
                     mctx.close()
                 except Exception as ex:      # never lose the main line to the extra measurement
                     e2e["one_process_one_call"] = {"error": repr(ex)}
-            barrier()
+            dist.barrier(group=host_group)
 
     if rank != 0:
         if world > 1:

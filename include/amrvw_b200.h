@@ -78,7 +78,7 @@ typedef struct amrvw_options {
     int32_t it_count;        /* IT_COUNT, create-bulge.jl:9; default 15                                */
     uint64_t seed;           /* exceptional (random) shifts: counter-based, reproducible              */
     int32_t it_max_factor;   /* it_max = it_max_factor * n, AMRVW_algorithm.jl:25; default 20          */
-    int32_t stream_ctas_per_sm; /* streamed schedule: resident CTAs per SM (1 or 2); 0 = auto                  */
+    int32_t stream_ctas_per_sm; /* streamed schedule: resident CTAs per SM (1..3); 0 = auto                    */
     double tol;              /* |s| <= tol deflates, AMRVW_algorithm.jl:184; default eps(Float64)      */
 } amrvw_options;
 
