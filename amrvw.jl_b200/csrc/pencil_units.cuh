@@ -603,9 +603,7 @@ static cudaError_t launch_pencil_pipelined(Problem<double> pr, const amrvw_optio
     pen_setup_kernel<<<(int)((pr.nbatch + 63) / 64), 64, 0, st>>>(pr);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (pr.order) {
-        order_by_degree_kernel<<<1, 1024, 0, st>>>(pr.rec, pr.nbatch, max_len, order_keys, const_cast<int*>(pr.order));
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        *launches += 1;
+        if ((e = launch_order_by_degree(pr.rec, pr.nbatch, max_len, order_keys, const_cast<int*>(pr.order), st, launches)) != cudaSuccess) return e;
     }
     if (times) cudaEventRecord(ev[1], st);
     const int seg_steps = 256;

@@ -113,6 +113,42 @@ __global__ void __launch_bounds__(1024) order_by_degree_kernel(const PolyRec* re
     }
     for (long long p = threadIdx.x; p < n; p += blockDim.x) order[p] = (int)(keys[p] & 0xffffffffull);
 }
+// The same network for batches too large for one CTA: one launch per comparator stage over the whole grid
+// (log2(n) (log2(n) + 1) / 2 launches: 210 for a million polynomials, a few microseconds each).
+__global__ void order_keys_kernel(const PolyRec* rec, const long long n, const int maxN, unsigned long long* keys) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) keys[p] = ((unsigned long long)(unsigned)(maxN - rec[p].N) << 32) | (unsigned long long)p;
+}
+__global__ void order_stage_kernel(unsigned long long* keys, const long long n, const long long k, const long long j) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+    const long long l = (j == (k >> 1)) ? (i ^ (k - 1)) : (i | j);
+    if (l < n && i < n) {
+        const unsigned long long x = keys[i], y = keys[l];
+        if (y < x) { keys[i] = y; keys[l] = x; }
+    }
+}
+__global__ void order_extract_kernel(const unsigned long long* keys, const long long n, int* order) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) order[p] = (int)(keys[p] & 0xffffffffull);
+}
+static cudaError_t launch_order_by_degree(const PolyRec* rec, const long long n, const int maxN, unsigned long long* keys, int* order, cudaStream_t st, int* launches) {
+    if (n <= 8192) {
+        order_by_degree_kernel<<<1, 1024, 0, st>>>(rec, n, maxN, keys, order);
+        *launches += 1;
+        return cudaGetLastError();
+    }
+    const int threads = 256;
+    order_keys_kernel<<<(int)((n + threads - 1) / threads), threads, 0, st>>>(rec, n, maxN, keys);
+    long long np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    const int blocks = (int)(((np2 >> 1) + threads - 1) / threads);
+    for (long long k = 2; k <= np2; k <<= 1)
+        for (long long j = k >> 1; j >= 1; j >>= 1) { order_stage_kernel<<<blocks, threads, 0, st>>>(keys, n, k, j); *launches += 1; }
+    order_extract_kernel<<<(int)((n + threads - 1) / threads), threads, 0, st>>>(keys, n, order);
+    *launches += 2;
+    return cudaGetLastError();
+}
 
 // ---------------------------------------------------------------- records, coherently
 // PolyRec is read and written by whichever warp holds the unit: whole-record ld.cg / st.cg copies.
@@ -688,9 +724,7 @@ static cudaError_t launch_rounds_rds(Problem<double> pr, const amrvw_options& op
     rounds_setup_kernel<<<nb64, 64, 0, st>>>(pr);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (pr.order) {
-        order_by_degree_kernel<<<1, 1024, 0, st>>>(pr.rec, pr.nbatch, max_len, order_keys, const_cast<int*>(pr.order));
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        *launches += 1;
+        if ((e = launch_order_by_degree(pr.rec, pr.nbatch, max_len, order_keys, const_cast<int*>(pr.order), st, launches)) != cudaSuccess) return e;
     }
     if (times) cudaEventRecord(ev[1], st);
     switch (L) {

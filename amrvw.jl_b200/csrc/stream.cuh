@@ -260,7 +260,7 @@ AMRVW_DI void stream_manager(const Problem<double>& pr, const StreamQueues& sq, 
     unsigned wd_progress = ld_volatile_u32(sq.progress), wd_polls = 0;
     for (;;) {
         bool worked = false;
-        if ((++wd_polls & 1023u) == 0u) {
+        if ((++wd_polls & 127u) == 0u) {
             const unsigned pg = ld_volatile_u32(sq.progress);
             const unsigned long long now = global_ns();
             if (pg != wd_progress) { wd_progress = pg; wd_time = now; }
@@ -298,7 +298,10 @@ AMRVW_DI void stream_manager(const Problem<double>& pr, const StreamQueues& sq, 
             }
         }
         if (sm.quit) return;
-        if (!worked) __nanosleep(200);
+        // nap between polls: a manager that spins takes issue slots from the chase warp that shares its scheduler (ncu, round 2:
+        // the 296 managers of config 2's 375-share executed a third of the kernel's warp-instructions at 200 ns).  Its events are
+        // a job completed and a job about to end, both hundreds of lock-steps (~microseconds each) apart
+        if (!worked) __nanosleep(2000);
     }
 }
 
@@ -313,7 +316,7 @@ AMRVW_DI void stream_service(const Problem<double>& pr, const PipeParams& pp, co
                 p = mpmc_try_pop(sq.work, sq.work_slots, sq.mask);
                 if (p >= 0) break;
                 if (ld_volatile_u32(sq.remaining) == 0u || ld_volatile_u32(sq.abort_flag) != 0u) { p = -2; break; }
-                __nanosleep(spins < 64 ? 200 : 1000);
+                __nanosleep(spins < 8 ? 500 : 2000);
             }
         }
         p = __shfl_sync(0xffffffffu, p, 0);
@@ -412,7 +415,14 @@ __global__ void __launch_bounds__(32 * (NW + 2), NW <= 2 ? 3 : 2) stream_kernel(
 #endif
     unsigned long long ns_first = 0ull, ns_last = 0ull;      // first / last lock-step with something in the array
     const long long pc_t0 = clock64();
+#ifdef AMRVW_STREAM_DEV
+    long long dp[4] = {0, 0, 0, 0}, dpn = 0;      // development: ingest / compute / retire+control / barrier wait of threads 0, 40, LE-1 in steps without a special
+    const int dslot = gl == 0 ? 0 : (gl == 40 ? 1 : (gl == LE - 1 ? 2 : -1));
+#endif
     for (unsigned t = 0;; ++t) {
+#ifdef AMRVW_STREAM_DEV
+        const long long dta = clock64();
+#endif
         // ---------------- ingest: what the previous lane finished last step
         Rot<double> iq = shfl_up_rot(q0, 32), ib = shfl_up_rot(b0, 32), ic = shfl_up_rot(c0, 32);
         unsigned itag = __shfl_up_sync(0xffffffffu, tag0, 1);
@@ -442,6 +452,9 @@ __global__ void __launch_bounds__(32 * (NW + 2), NW <= 2 ? 3 : 2) stream_kernel(
         }
 
         // ---------------- what this lane does in this lock-step (the lanes of a warp that differ take their branches in turn)
+#ifdef AMRVW_STREAM_DEV
+        const long long dtb = clock64();
+#endif
         const bool cr = (tag1 & AMRVW_TAG_FIRST) != 0u;
         const bool fa = active && (tag2 & AMRVW_TAG_LAST) != 0u;
         const bool fb = pend_b;
@@ -475,6 +488,9 @@ __global__ void __launch_bounds__(32 * (NW + 2), NW <= 2 ? 3 : 2) stream_kernel(
         if (fa) { active = false; pend_b = true; }
         else if (fb) pend_b = false;
 
+#ifdef AMRVW_STREAM_DEV
+        const long long dtc = clock64();
+#endif
         // ---------------- retire: the last lane of the chain writes back, the last lane of a warp hands on
         if (ret_g) {
             if (tag0 & AMRVW_TAG_VALID) {
@@ -516,8 +532,16 @@ __global__ void __launch_bounds__(32 * (NW + 2), NW <= 2 ? 3 : 2) stream_kernel(
             pn_steps += 1;
             if (pr.prof && code >= 0 && (t & 63u) == 0u) { ns_last = global_ns(); if (ns_first == 0ull) ns_first = ns_last; }
         }
+#ifdef AMRVW_STREAM_DEV
+        const long long dtd = clock64();
+#endif
         const bool all_clean = bar_chase_and<32 * NW>(clean);      // the lock-step's barrier, with the AND of `clean` over the array
 #ifdef AMRVW_STREAM_DEV
+        if (pr.prof && dslot >= 0 && (sm.sptype & 7) == 0 && sm.ctl >= 0) {
+            const long long dte = clock64();
+            dp[0] += dtb - dta; dp[1] += dtc - dtb; dp[2] += dtd - dtc; dp[3] += dte - dtd; dpn += 1;
+        }
+        AMRVW_BAR_CHASE(32 * NW);      // (development build only: every thread has read sptype before the feeding thread clears it)
         if (pr.prof && feeds_g) {
             const long long now = clock64();
             const int ty = sm.sptype & 7;
@@ -561,6 +585,12 @@ __global__ void __launch_bounds__(32 * (NW + 2), NW <= 2 ? 3 : 2) stream_kernel(
         }
     }
     if (feeds_g) { cp_async_wait_all(); sm.quit = 1; }
+#ifdef AMRVW_STREAM_DEV
+    if (pr.prof && dslot >= 0) {
+        for (int a = 0; a < 4; ++a) atomicAdd(pr.prof + 32 + 5 * dslot + a, (unsigned long long)dp[a]);
+        atomicAdd(pr.prof + 32 + 5 * dslot + 4, (unsigned long long)dpn);
+    }
+#endif
     if (pr.prof && feeds_g) {
         atomicAdd(pr.prof + 0, (unsigned long long)(clock64() - pc_t0));   // chase loop, feeding thread
         atomicAdd(pr.prof + 2, (unsigned long long)pn_fast);               // lock-steps in the lean loop
@@ -635,7 +665,7 @@ AMRVW_DI void ustream_manager(const Problem<double>& pr, const StreamQueues& sq,
     unsigned wd_progress = ld_volatile_u32(sq.progress), wd_polls = 0;
     for (;;) {
         bool worked = false;
-        if ((++wd_polls & 1023u) == 0u) {
+        if ((++wd_polls & 127u) == 0u) {
             const unsigned pg = ld_volatile_u32(sq.progress);
             const unsigned long long now = global_ns();
             if (pg != wd_progress) { wd_progress = pg; wd_time = now; }
@@ -672,7 +702,7 @@ AMRVW_DI void ustream_manager(const Problem<double>& pr, const StreamQueues& sq,
             }
         }
         if (sm.quit) return;
-        if (!worked) __nanosleep(300);
+        if (!worked) __nanosleep(2000);      // see stream_manager
     }
 }
 
@@ -689,7 +719,7 @@ AMRVW_DI void ustream_service(const Problem<double>& pr, const PipeParams& pp, c
         if (lane == 0) p = mpmc_try_pop(sq.work, sq.work_slots, sq.mask);
         if (!__any_sync(0xffffffffu, p >= 0)) {
             if (ld_volatile_u32(sq.remaining) == 0u || ld_volatile_u32(sq.abort_flag) != 0u) return;
-            __nanosleep(500);
+            __nanosleep(2000);
             continue;
         }
         const long long pc_s0 = clock64();

@@ -412,6 +412,8 @@ def main():
                                       "lean_cycles_per_step": prof["cycles_general"] / max(prof["cycles_lean"], 1), "nap_share_of_cycles": prof["cycles_pop"] / max(prof["cycles_units"], 1),
                                       "other_cycles_per_step": (prof["cycles_units"] - prof["cycles_general"] - prof["cycles_pop"]) / max(steps - prof["cycles_lean"] - prof["steps_general"], 1),
                                       "cta_last_busy_ms_sum": prof["cycles_loop"] / 1e3, "cta_first_busy_ms_sum": prof["lane_cycles_special"] / 1e3}
+        if dv and any(dv[16:31]):
+            roofline["stream_profile"]["plain_generic_step_phases"] = {nm: {ph: dv[16 + 5 * i + k] / max(dv[16 + 5 * i + 4], 1) for k, ph in enumerate(["ingest", "compute", "retire_control", "barrier_wait"])} for i, nm in enumerate(["thread0", "thread40", "last_thread"])}
         if dv and any(dv[8:16]):
             roofline["stream_profile"]["generic_step_cycles_by_special"] = {k: (dv[i] / dv[8 + i] if dv[8 + i] else None, dv[8 + i]) for i, k in enumerate(["none", "create", "last_a", "create+?", "last_b", "create+last_b", "last_a+last_b", "all"])}
     elif prof and prof["cycles_units"] > 0:
