@@ -638,7 +638,9 @@ static void choose_pipe_params(const amrvw_options& opt, long long nbatch, int m
         // round 2 (gpurun_out/r2b_sweep.txt, r2k_sweep.txt; degree 3000): 375 polynomials 205-211 ms streamed (stream.cuh) against
         // 345 ms with one CTA per polynomial (two CTAs fit an SM, the 79 polynomials beyond 296 wait for a second wave);
         // 750: 303 ms streamed, 247 ms with 32 lanes on the unit queue; 1500: 562 vs 333 ms
-        if (L == 32 && degree >= 2500 && nbatch * 2 <= (long long)sm_count * 7) L = 128;
+        // streamed: 64 and 128 bulges tie at 375 polynomials (206 / 205 ms), 64 wins above (750: 267 / 303 ms) and executes
+        // 1.75x instead of 2.39x the reference's turnovers
+        if (L == 32 && degree >= 2500 && nbatch * 2 <= (long long)sm_count * 7) L = nbatch > (long long)sm_count * 2 ? 64 : 128;
     }
     // chained warps: one CTA per polynomial (chain.cuh) while there are fewer polynomials than SMs can hold two of;
     // above that the CTAs take the fat steps of all polynomials as one stream (stream.cuh): no fill/drain, phase A hidden
