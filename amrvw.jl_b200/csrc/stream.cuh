@@ -806,7 +806,7 @@ __global__ void __launch_bounds__(32 * (NW + 1 + NS), 2) ustream_kernel(Problem<
 
     int r_done = 0;
     bool my_quit = false;      // this lane's pipeline is through (feeding lane decides, the group follows)
-    long long pn_steps = 0, pn_empty = 0, pn_starved = 0;
+    long long pn_steps = 0, pn_empty = 0, pn_starved = 0, pn_fast = 0;
     const long long pc_t0 = clock64();
     for (unsigned t = 0;; ++t) {
         Rot<double> iq = shfl_up_rot(q0, L), ib = shfl_up_rot(b0, L), ic = shfl_up_rot(c0, L);
@@ -885,10 +885,44 @@ __global__ void __launch_bounds__(32 * (NW + 1 + NS), 2) ustream_kernel(Problem<
         const unsigned feeders = __ballot_sync(0xffffffffu, feeds);
         if ((__ballot_sync(0xffffffffu, feeds && my_quit) & feeders) == feeders) break;
         if ((__ballot_sync(0xffffffffu, feeds && empty) & feeders) == feeders) __nanosleep(400);
+
+        // ---------------- every lane of the warp chasing inside its group's current window, and every group's window with
+        // triples still to be requested: the lean loop of pipeline.cuh (no tags, no case analysis) until the first group
+        // has requested its last triple
+        const bool clean = active && (tag0 & tag1 & tag2 & AMRVW_TAG_VALID) != 0u && ((tag0 | tag1 | tag2) & (AMRVW_TAG_FIRST | AMRVW_TAG_LAST)) == 0u;
+        int left = 0x7fffffff;
+        if (feeds) left = (f_slot >= 0 && f_k - f_start >= 4) ? f_stop1 - f_k + 1 : 0;
+        const int fk = __reduce_min_sync(0xffffffffu, left);
+        if (fk >= 16 && __all_sync(0xffffffffu, clean)) {
+            StreamJob& j = sm.jobs[(tag0 >> AMRVW_TAG_SLOT_SHIFT) & (AMRVW_USTREAM_JOBS - 1)];
+            const int idx_next = (int)(tag2 & AMRVW_TAG_INDEX_MASK) + 3 * lane + 1;     // index the group's feeding lane ingests next
+            const int t0 = (int)t + 1, t1 = t0 + fk;
+            int sp = retires ? j.sp : 0;
+            const int role = 1 | (feeds ? 2 : 0) | (retires ? 4 : 0);
+            StepState z = {q0, q1, q2, b0, b1, b2, c0, c1, c2, U, V, W};
+            sp = lean_chase<L, NT>(z, pr.Q + j.base, pr.B + j.base, pr.Ct + j.base, stage_sa, (unsigned)__cvta_generic_to_shared(snap_t), pr.dstack + j.base, sp,
+                                   idx_next - t0, t0, t1, role);
+            q0 = z.q0; q1 = z.q1; q2 = z.q2; b0 = z.b0; b1 = z.b1; b2 = z.b2; c0 = z.c0; c1 = z.c1; c2 = z.c2; U = z.U; V = z.V; W = z.W;
+            tag0 += (unsigned)fk; tag1 += (unsigned)fk; tag2 += (unsigned)fk;
+            if (retires) j.sp = sp;
+            if (feeds) {
+                f_k += fk;
+                sm.feed_left = f_stop1 - f_k + 1;
+                const unsigned base_tag = AMRVW_TAG_VALID | ((unsigned)f_slot << AMRVW_TAG_SLOT_SHIFT);
+                for (int a = 0; a < AMRVW_RING - 1; ++a) {
+                    const int idx = f_k - (AMRVW_RING - 1) + a;
+                    sm.ringtag[(unsigned)(t1 + a) & (AMRVW_RING - 1)] = base_tag | (unsigned)idx | (idx == f_stop1 ? AMRVW_TAG_LAST : 0u);
+                }
+                pn_steps += fk; pn_fast += fk;
+            }
+            t = (unsigned)(t1 - 1);
+            __syncwarp();
+        }
     }
     if (feeds) cp_async_wait_all();
     if (pr.prof && feeds) {
         if (lane32 == 0) atomicAdd(pr.prof + 0, (unsigned long long)(clock64() - pc_t0));   // chase loop, per warp
+        atomicAdd(pr.prof + 2, (unsigned long long)pn_fast);                                 // lock-steps in the lean loop, per pipeline
         atomicAdd(pr.prof + 4, (unsigned long long)pn_steps);                                // per pipeline
         atomicAdd(pr.prof + 5, (unsigned long long)pn_empty);
         atomicAdd(pr.prof + 6, (unsigned long long)f_started);
