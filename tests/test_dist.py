@@ -68,3 +68,22 @@ def test_world2_gloo_shard_range_and_gather_plumbing(oracle):
     for i, r in res:
         want, _ = oracle.roots(synth.fill_coeffs(9, [i], 0, 25)[0])
         assert np.array_equal(np.array(r), want)
+
+
+def test_bench_shards_one_batch_over_the_ranks():
+    """bench.py --gpus N roots ONE config-2 batch split by polynomial (strong scaling): the ranks' inputs, concatenated
+    in rank order, are the single-GPU batch, whatever N."""
+    import importlib, sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    bench = importlib.import_module("bench")
+    synth = importlib.import_module("amrvw_jl_b200.synth")
+    kind, batch, degree, law, seed = "rds_f64", 37, 12, 0, 2
+    whole, _, off, ncoef = bench.make_inputs(kind, batch, degree, law, seed, 0)
+    for world in (2, 4, 8):
+        parts = []
+        for r in range(world):
+            lo, hi = synth.shard_range(batch, r, world)
+            flat, _, o, _ = bench.make_inputs(kind, hi - lo, degree, law, seed, lo)
+            assert o[-1] == (hi - lo) * ncoef
+            parts.append(flat)
+        assert np.array_equal(np.concatenate(parts), whole)
