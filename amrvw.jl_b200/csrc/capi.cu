@@ -42,6 +42,11 @@ struct amrvw_ctx {
     // multi-device context (amrvw_create_multi): one single-device context per GPU; this object then owns no
     // device memory of its own and only partitions host batches over `subs`
     std::vector<amrvw_ctx*> subs;
+    // degree classes of a ragged host batch: one sub-context per class on THIS device, created on first use,
+    // each with its own stream and workspace so that the classes' kernels run side by side with their own lane counts
+    std::vector<amrvw_ctx*> klass;
+    DevBuf members;                 // class sub-context: batch indices of its polynomials
+    cudaEvent_t ev_in = nullptr, ev_done = nullptr;
 };
 
 static int fail(amrvw_ctx* ctx, int code, const std::string& msg) {
@@ -148,7 +153,12 @@ int amrvw_destroy(amrvw_ctx* ctx) {
         delete ctx;
         return AMRVW_OK;
     }
+    for (amrvw_ctx* k : ctx->klass) amrvw_destroy(k);
+    ctx->klass.clear();
     cudaSetDevice(ctx->device);
+    if (ctx->members.ptr) cudaFree(ctx->members.ptr);
+    if (ctx->ev_in) cudaEventDestroy(ctx->ev_in);
+    if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
     DevBuf* all[] = {&ctx->chains[0], &ctx->chains[1], &ctx->chains[2], &ctx->chains[3], &ctx->chains[4], &ctx->diags[0], &ctx->diags[1], &ctx->diags[2],
                      &ctx->coeffs, &ctx->coeffs2, &ctx->offsets, &ctx->roots, &ctx->nroots, &ctx->nunconv, &ctx->stats, &ctx->shifts, &ctx->state, &ctx->prof,
                      &ctx->rec, &ctx->fatshifts, &ctx->swlist, &ctx->counters, &ctx->queue, &ctx->qslots, &ctx->park, &ctx->parked, &ctx->order, &ctx->orderkeys, &ctx->counts, &ctx->squeues, &ctx->sslots};
@@ -256,7 +266,7 @@ static int reserve_unit_workspace(amrvw_ctx* ctx, int64_t nbatch, int64_t total,
 
 template <class S>
 static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, const int64_t* d_offsets, int64_t nbatch, int64_t total, int64_t max_len,
-                   double* d_roots, int32_t* d_nroots, int32_t* d_nunconv, amrvw_stats* stats) {
+                   double* d_roots, int32_t* d_nroots, int32_t* d_nunconv, amrvw_stats* stats, int64_t load_hint = 0) {
     if (!ctx) return AMRVW_ERR_ARGUMENT;
     if (!ctx->subs.empty()) return fail(ctx, AMRVW_ERR_ARGUMENT, "device-pointer entry points need a single-device context (amrvw_create)");
     if (nbatch < 0 || total < 0) return fail(ctx, AMRVW_ERR_ARGUMENT, "negative batch or total");
@@ -295,6 +305,8 @@ static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, cons
     }
     pr.extra = extra;
     pr.seed = ctx->opt.seed;
+    pr.load_hint = load_hint;
+    const int64_t nload = load_hint > nbatch ? load_hint : nbatch;
     {   // the reference's constants as options (solver.cuh: g_algo), written on the call's stream
         const AlgoConst ac = {ctx->opt.tol, ctx->opt.it_count, ctx->opt.it_max_factor};
         CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(g_algo, &ac, sizeof(ac), 0, cudaMemcpyHostToDevice, st));
@@ -320,10 +332,10 @@ static int run_dev(amrvw_ctx* ctx, Variant var, const S* d_a, const S* d_w, cons
         int L; PipeParams pp; size_t qcap = 0; int rc;
         size_t lane_bytes;
         if constexpr (is_real<S>::value) {
-            if (var == V_RDS) { choose_pipe_params(ctx->opt, nbatch, (int)max_len, ctx->sm_count, L, pp); lane_bytes = sizeof(StepState); }
-            else { choose_pencil_params(ctx->opt, nbatch, (int)max_len, ctx->sm_count, L, pp); lane_bytes = sizeof(PenLane); }
+            if (var == V_RDS) { choose_pipe_params(ctx->opt, nload, (int)max_len, ctx->sm_count, L, pp, nbatch); lane_bytes = sizeof(StepState); }
+            else { choose_pencil_params(ctx->opt, nload, (int)max_len, ctx->sm_count, L, pp); lane_bytes = sizeof(PenLane); }
         } else {
-            choose_css_params(ctx->opt, nbatch, (int)max_len, ctx->sm_count, L, pp); lane_bytes = sizeof(CssLane);
+            choose_css_params(ctx->opt, nload, (int)max_len, ctx->sm_count, L, pp); lane_bytes = sizeof(CssLane);
         }
         if ((rc = reserve_unit_workspace(ctx, nbatch, total, L, lane_bytes, var == V_RDS && pp.stream, &qcap))) return rc;
         StreamBufs sbuf = {nullptr, nullptr, nullptr, nullptr, 0u, nullptr};
@@ -402,6 +414,117 @@ static int check_offsets(amrvw_ctx* ctx, const int64_t* offsets, int64_t nbatch,
     return AMRVW_OK;
 }
 
+// ---------------------------------------------------------------- degree classes of a ragged batch
+// One lane count serves one degree range: 16 lanes on a degree-60 polynomial are mostly fill and drain (2.1x the
+// reference's turnovers at degree 100 against 1.56x with 8), and the few large polynomials of a heavy-tailed batch want
+// chained warps while thousands of small ones want the unit queue.  A host batch whose lengths span several classes is
+// therefore split: each class is gathered on the device into its own contiguous CSR batch, rooted by its own sub-context
+// (own stream, own workspace, lane count chosen from ITS degree and ITS size), and scattered back into the caller's root
+// slots; the classes' kernels run side by side.  Per polynomial nothing changes (same kernels, seeds keyed by the
+// polynomial's index in ITS class batch only for the exceptional shift).  Not used when the caller pins lanes_per_poly
+// or asks for the reference schedule.
+static const int64_t CLASS_BOUNDS[] = {64, 256, 1280};        // coefficient counts: class k = number of bounds <= len
+enum { NCLASS = 4 };
+template <class S>
+__global__ void class_gather_kernel(const S* src, const long long* src_off, const int* members, const long long* cls_off, S* dst) {
+    const long long i = blockIdx.x;
+    const long long from = src_off[members[i]], to = cls_off[i];
+    const int len = (int)(cls_off[i + 1] - to);
+    for (int k = threadIdx.x; k < len; k += blockDim.x) dst[to + k] = src[from + k];
+}
+__global__ void class_scatter_kernel(const cplx* cls_roots, const long long* cls_off, const int* cls_nroots, const int* cls_nunconv, const int* members,
+                                     const long long* dst_off, cplx* roots, int* nroots, int* nunconv) {
+    const long long i = blockIdx.x;
+    const int p = members[i];
+    const int n = cls_nroots[i];
+    const long long from = cls_off[i], to = dst_off[p];
+    for (int k = threadIdx.x; k < n; k += blockDim.x) roots[to + k] = cls_roots[from + k];
+    if (threadIdx.x == 0) { nroots[p] = n; nunconv[p] = cls_nunconv[i]; }
+}
+
+// roots every class of the batch already resident in the parent's coeffs / coeffs2 / offsets buffers; results land in
+// the parent's roots / nroots / nunconv buffers.  The parent's stream has the H2D copies queued; on return it waits for
+// every class.
+template <class S>
+static int run_classes(amrvw_ctx* ctx, Variant var, const int64_t* offsets, int64_t nbatch, const std::vector<std::vector<int>>& members, amrvw_stats* stats) {
+    const bool pencil = (var == V_PENCIL_R || var == V_PENCIL_C);
+    if (!ctx->ev_in) { CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_in, cudaEventDisableTiming)); }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_in, ctx->stream));
+    while ((int)ctx->klass.size() < NCLASS) {
+        amrvw_ctx* k = nullptr;
+        const int rc = amrvw_create(&k, ctx->device, ctx->opt.seed);
+        if (rc != AMRVW_OK) return fail(ctx, rc, "cannot create the sub-context of a degree class");
+        ctx->klass.push_back(k);
+    }
+    std::vector<std::vector<int64_t>> cls_off((size_t)NCLASS);
+    // the classes share the device: a lower class's lane count is chosen for the whole batch's work expressed in polynomials
+    // of ITS size (work grows like n^2), not for its own head count
+    double work_all = 0.0;
+    for (int64_t p = 0; p < nbatch; ++p) { const double len = (double)(offsets[p + 1] - offsets[p]); work_all += len * len; }
+    bool top = true;
+    for (int c = NCLASS - 1; c >= 0; --c) {      // the largest polynomials first: theirs is the longest chain of dependent fat steps
+        const std::vector<int>& mem = members[(size_t)c];
+        if (mem.empty()) continue;
+        amrvw_ctx* k = ctx->klass[(size_t)c];
+        k->opt = ctx->opt;
+        const int64_t nb = (int64_t)mem.size();
+        std::vector<int64_t>& off = cls_off[(size_t)c];
+        off.assign((size_t)nb + 1, 0);
+        int64_t ml = 0;
+        for (int64_t i = 0; i < nb; ++i) {
+            const int64_t len = offsets[mem[(size_t)i] + 1] - offsets[mem[(size_t)i]];
+            off[(size_t)i + 1] = off[(size_t)i] + len;
+            ml = std::max(ml, len);
+        }
+        const int64_t tot = off[(size_t)nb];
+        double work_cls = 0.0;
+        for (int64_t i = 0; i < nb; ++i) { const double len = (double)(off[(size_t)i + 1] - off[(size_t)i]); work_cls += len * len; }
+        // the top class sets the time of the whole call: it gets the lanes its own head count allows; the others fill the
+        // machine around it and are sized for the whole batch's work
+        const int64_t hint = (top || work_cls <= 0.0) ? nb : (int64_t)(work_all / (work_cls / (double)nb));
+        top = false;
+        int rc;
+        if ((rc = reserve(k, k->coeffs, (size_t)tot * sizeof(S) + 16))) return fail(ctx, rc, k->err);
+        if (pencil && (rc = reserve(k, k->coeffs2, (size_t)tot * sizeof(S) + 16))) return fail(ctx, rc, k->err);
+        if ((rc = reserve(k, k->offsets, (size_t)(nb + 1) * sizeof(int64_t)))) return fail(ctx, rc, k->err);
+        if ((rc = reserve(k, k->roots, ((size_t)tot + 1) * sizeof(cplx)))) return fail(ctx, rc, k->err);
+        if ((rc = reserve(k, k->nroots, (size_t)nb * sizeof(int32_t)))) return fail(ctx, rc, k->err);
+        if ((rc = reserve(k, k->nunconv, (size_t)nb * sizeof(int32_t)))) return fail(ctx, rc, k->err);
+        if ((rc = reserve(k, k->members, (size_t)nb * sizeof(int)))) return fail(ctx, rc, k->err);
+        cudaStream_t ks = k->stream;
+        CUDA_TRY(ctx, cudaMemcpyAsync(k->members.ptr, mem.data(), (size_t)nb * sizeof(int), cudaMemcpyHostToDevice, ks));
+        CUDA_TRY(ctx, cudaMemcpyAsync(k->offsets.ptr, off.data(), (size_t)(nb + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ks));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ks, ctx->ev_in, 0));
+        if (tot > 0) {
+            class_gather_kernel<S><<<(int)nb, 128, 0, ks>>>((const S*)ctx->coeffs.ptr, (const long long*)ctx->offsets.ptr, (const int*)k->members.ptr,
+                                                             (const long long*)k->offsets.ptr, (S*)k->coeffs.ptr);
+            if (pencil) class_gather_kernel<S><<<(int)nb, 128, 0, ks>>>((const S*)ctx->coeffs2.ptr, (const long long*)ctx->offsets.ptr, (const int*)k->members.ptr,
+                                                                         (const long long*)k->offsets.ptr, (S*)k->coeffs2.ptr);
+            CUDA_TRY(ctx, cudaGetLastError());
+        }
+        amrvw_stats kst;
+        rc = run_dev<S>(k, var, (const S*)k->coeffs.ptr, pencil ? (const S*)k->coeffs2.ptr : nullptr, (const int64_t*)k->offsets.ptr, nb, tot, ml,
+                        (double*)k->roots.ptr, (int32_t*)k->nroots.ptr, (int32_t*)k->nunconv.ptr, stats ? &kst : nullptr, hint);
+        if (rc) return fail(ctx, rc, "degree class " + std::to_string(c) + ": " + k->err);
+        class_scatter_kernel<<<(int)nb, 128, 0, ks>>>((const cplx*)k->roots.ptr, (const long long*)k->offsets.ptr, (const int*)k->nroots.ptr, (const int*)k->nunconv.ptr,
+                                                      (const int*)k->members.ptr, (const long long*)ctx->offsets.ptr, (cplx*)ctx->roots.ptr, (int*)ctx->nroots.ptr,
+                                                      (int*)ctx->nunconv.ptr);
+        CUDA_TRY(ctx, cudaGetLastError());
+        if (!k->ev_done) { CUDA_TRY(ctx, cudaEventCreateWithFlags(&k->ev_done, cudaEventDisableTiming)); }
+        CUDA_TRY(ctx, cudaEventRecord(k->ev_done, ks));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, k->ev_done, 0));
+        if (stats) {
+            stats->turnovers += kst.turnovers; stats->sweeps += kst.sweeps; stats->exceptional += kst.exceptional; stats->unconverged += kst.unconverged;
+            stats->fat_steps += kst.fat_steps; stats->launches += kst.launches + 2 + (pencil ? 1 : 0); stats->device_ms += kst.device_ms;
+            if (kst.lanes > stats->lanes) stats->lanes = kst.lanes;
+            if (kst.schedule_used > stats->schedule_used) stats->schedule_used = kst.schedule_used;
+        }
+    }
+    // the host vectors above were pageable sources of asynchronous copies: those are staged before the call returns
+    (void)nbatch;
+    return AMRVW_OK;
+}
+
 // One device: H2D of the inputs, the kernels, D2H of the results (roots, or with counts3 != NULL only the
 // imag == 0 / > 0 / < 0 counts of real_polynomial_roots), all on the context's stream; returns when the
 // results are in the caller's buffers.
@@ -423,8 +546,37 @@ static int run_host_single(amrvw_ctx* ctx, Variant var, const S* a, const S* w, 
     if (total > 0) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->coeffs.ptr, a, (size_t)total * sizeof(S), cudaMemcpyHostToDevice, st));
     if (pencil && total > 0) CUDA_TRY(ctx, cudaMemcpyAsync(ctx->coeffs2.ptr, w, (size_t)total * sizeof(S), cudaMemcpyHostToDevice, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->offsets.ptr, offsets, (size_t)(nbatch + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-    rc = run_dev<S>(ctx, var, (const S*)ctx->coeffs.ptr, pencil ? (const S*)ctx->coeffs2.ptr : nullptr, (const int64_t*)ctx->offsets.ptr, nbatch, total, max_len,
-                    (double*)ctx->roots.ptr, (int32_t*)ctx->nroots.ptr, (int32_t*)ctx->nunconv.ptr, stats);
+    // a ragged batch: one sub-batch per degree class, each with its own lane count (run_classes)
+    bool by_class = false;
+    std::vector<std::vector<int>> members;
+    if (ctx->opt.schedule != AMRVW_SCHEDULE_REFERENCE && ctx->opt.lanes_per_poly == 0 && var != V_PENCIL_C && nbatch >= 2 && nbatch < 0x7fffffff) {
+        members.assign((size_t)NCLASS, std::vector<int>());
+        for (int64_t p = 0; p < nbatch; ++p) {
+            const int64_t len = offsets[p + 1] - offsets[p];
+            int c = 0;
+            while (c < NCLASS - 1 && len >= CLASS_BOUNDS[c]) ++c;
+            members[(size_t)c].push_back((int)p);
+        }
+        int used = 0;
+        for (const std::vector<int>& m : members) used += m.empty() ? 0 : 1;
+        // ... when the batch is bound by the latency of its largest polynomials, not by throughput: only then do more lanes
+        // for the top class pay for running several persistent kernels side by side (measured, tools/ragged_bench.py: 2000
+        // polynomials of degree 200-3000 384 -> 297 ms, 5000 of degree 40-120 + 8 of degree 2500-3000 325 -> 162 ms; but 8000
+        // of degree 100-1500 233 -> 283 ms and 6000 of degree 500-2000 325 -> 374 ms, which this test leaves on one launch).
+        // Model (config 2 on one B200): the unit queue retires 2.9e11 turnovers/s, a polynomial of degree n costs 5.4 n^2 of
+        // them and, on 16 lanes alone, 3.8e-8 n^2 seconds
+        double sum_sq = 0.0;
+        for (int64_t p = 0; p < nbatch; ++p) { const double len = (double)(offsets[p + 1] - offsets[p]); sum_sq += len * len; }
+        const double t_throughput = 5.4 * sum_sq / 2.9e11, t_latency = 3.8e-8 * (double)max_len * (double)max_len;
+        by_class = used >= 2 && t_latency > 1.5 * t_throughput;
+    }
+    if (by_class) {
+        if (stats) std::memset(stats, 0, sizeof(*stats));
+        rc = run_classes<S>(ctx, var, offsets, nbatch, members, stats);
+    } else {
+        rc = run_dev<S>(ctx, var, (const S*)ctx->coeffs.ptr, pencil ? (const S*)ctx->coeffs2.ptr : nullptr, (const int64_t*)ctx->offsets.ptr, nbatch, total, max_len,
+                        (double*)ctx->roots.ptr, (int32_t*)ctx->nroots.ptr, (int32_t*)ctx->nunconv.ptr, stats);
+    }
     if (rc) return rc;
     if (counts3) {
         const int threads = 128;
@@ -438,6 +590,10 @@ static int run_host_single(amrvw_ctx* ctx, Variant var, const S* a, const S* w, 
     if (nroots) CUDA_TRY(ctx, cudaMemcpyAsync(nroots, ctx->nroots.ptr, (size_t)nbatch * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(nunconv, ctx->nunconv.ptr, (size_t)nbatch * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    if (by_class) {
+        for (amrvw_ctx* k : ctx->klass) { const int r2 = check_queue_abort(k); if (r2) return fail(ctx, r2, k->err); }
+        return AMRVW_OK;
+    }
     return check_queue_abort(ctx);
 }
 

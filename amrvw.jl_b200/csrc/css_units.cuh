@@ -795,7 +795,7 @@ static cudaError_t launch_css_pipelined(Problem<cplx> pr, const amrvw_options& o
                                         RoundQueue* q, int* slots, unsigned mask, UnitPark* park, CssLane* parked, cudaEvent_t* ev = nullptr, RoundsTimes* times = nullptr,
                                         int* lanes_out = nullptr, unsigned long long* order_keys = nullptr) {
     int L; PipeParams pp;
-    choose_css_params(opt, pr.nbatch, max_len, sm_count, L, pp);
+    choose_css_params(opt, pr.load_hint > pr.nbatch ? pr.load_hint : pr.nbatch, max_len, sm_count, L, pp);
     if (lanes_out) *lanes_out = L;
     cudaError_t e;
     if ((e = cudaMemsetAsync(pr.counters, 0, CNT_WORDS * sizeof(unsigned), st)) != cudaSuccess) return e;

@@ -31,6 +31,9 @@ template <class S> struct Problem {
     // in this order, not in batch order (ragged batches: SURVEY 8 f2)
     const int* order;
     unsigned long long seed;
+    // host only: the batch this one competes with on the device, in polynomials of ITS size (degree classes of a ragged
+    // batch run side by side: capi.cu); 0 = it is alone.  Only the choice of the lane count looks at it
+    long long load_hint;
 };
 // polynomial of slot `slot` of the unit schedule (slot = unit * G + group); nbatch = none
 template <class S> AMRVW_DI long long unit_poly(const Problem<S>& pr, const long long slot) {

@@ -593,7 +593,7 @@ static cudaError_t launch_pencil_pipelined(Problem<double> pr, const amrvw_optio
                                            const QueueBufs& qb, PenLane* parked, cudaEvent_t* ev = nullptr, RoundsTimes* times = nullptr, int* lanes_out = nullptr,
                                            unsigned long long* order_keys = nullptr) {
     int L; PipeParams pp;
-    choose_pencil_params(opt, pr.nbatch, max_len, sm_count, L, pp);
+    choose_pencil_params(opt, pr.load_hint > pr.nbatch ? pr.load_hint : pr.nbatch, max_len, sm_count, L, pp);
     if (lanes_out) *lanes_out = L;
     cudaError_t e;
     if ((e = cudaMemsetAsync(pr.counters, 0, CNT_WORDS * sizeof(unsigned), st)) != cudaSuccess) return e;

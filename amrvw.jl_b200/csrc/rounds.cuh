@@ -622,7 +622,10 @@ struct QueueBufs { RoundQueue* q; int* slots; unsigned mask; UnitPark* park; Ste
 
 // Chooses L (bulges in flight per polynomial) from the degree and the batch: enough lanes to fill the
 // GPU, not more than the windows can feed (a fat step needs a window > small >= 2L/reuse).
-static void choose_pipe_params(const amrvw_options& opt, long long nbatch, int max_len, int sm_count, int& L, PipeParams& pp) {
+// nbatch: the load the lane count is chosen for (the batch, or more when other degree classes share the device);
+// nresident: the polynomials that will really hold CTAs (chain or stream)
+static void choose_pipe_params(const amrvw_options& opt, long long nbatch, int max_len, int sm_count, int& L, PipeParams& pp, long long nresident = -1) {
+    if (nresident < 0) nresident = nbatch;
     const int degree = max_len - 1;
     L = opt.lanes_per_poly;
     if (L == 0) {
@@ -640,7 +643,7 @@ static void choose_pipe_params(const amrvw_options& opt, long long nbatch, int m
         // 750: 303 ms streamed, 247 ms with 32 lanes on the unit queue; 1500: 562 vs 333 ms
         // streamed: 64 and 128 bulges tie at 375 polynomials (206 / 205 ms), 64 wins above (750: 267 / 303 ms) and executes
         // 1.75x instead of 2.39x the reference's turnovers
-        if (L == 32 && degree >= 2500 && nbatch * 2 <= (long long)sm_count * 7) L = nbatch > (long long)sm_count * 2 ? 64 : 128;
+        if (L == 32 && degree >= 2500 && nbatch * 2 <= (long long)sm_count * 7) L = nresident > (long long)sm_count * 2 ? 64 : 128;
     }
     // chained warps: one CTA per polynomial (chain.cuh) while there are fewer polynomials than SMs can hold two of;
     // above that the CTAs take the fat steps of all polynomials as one stream (stream.cuh): no fill/drain, phase A hidden
@@ -650,7 +653,7 @@ static void choose_pipe_params(const amrvw_options& opt, long long nbatch, int m
     if (opt.schedule == AMRVW_SCHEDULE_STREAMED && (L == 16 || L == 32)) pp.stream = 1;     // sub-warp pipelines (stream.cuh, second half)
     if (L == 128 || L == 64) {
         if (opt.schedule == AMRVW_SCHEDULE_STREAMED) pp.stream = 1;
-        else if (opt.schedule == AMRVW_SCHEDULE_AUTO && opt.lanes_per_poly == 0 && nbatch > (long long)sm_count * 2) pp.stream = 1;     // more polynomials than resident chain CTAs
+        else if (opt.schedule == AMRVW_SCHEDULE_AUTO && opt.lanes_per_poly == 0 && nresident > (long long)sm_count * 2) pp.stream = 1;     // more polynomials than resident chain CTAs
     }
     pp.reuse = opt.shift_reuse ? opt.shift_reuse : (L == 32 ? 4 : (pp.stream && L >= 64 ? L / 16 : 2));   // 32 lanes: 16 shifts x 4 beat 32 x 2 by 4-8% (gpurun_out/sweep63.log)
     if (pp.reuse > L / 2) pp.reuse = L / 2 > 0 ? L / 2 : 1;
@@ -712,7 +715,7 @@ static cudaError_t read_round_times(cudaEvent_t* ev, RoundsTimes* times, cudaStr
 static cudaError_t launch_rounds_rds(Problem<double> pr, const amrvw_options& opt, int max_len, long long total, int sm_count, cudaStream_t st, int* launches, cudaEvent_t* ev,
                                      RoundsTimes* times, const QueueBufs& qb, int* lanes_out = nullptr, unsigned long long* order_keys = nullptr, const StreamBufs* sb = nullptr) {
     int L; PipeParams pp;
-    choose_pipe_params(opt, pr.nbatch, max_len, sm_count, L, pp);
+    choose_pipe_params(opt, pr.load_hint > pr.nbatch ? pr.load_hint : pr.nbatch, max_len, sm_count, L, pp, pr.nbatch);
     if (lanes_out) *lanes_out = L;
     cudaError_t e;
     const int nb64 = (int)((pr.nbatch + 63) / 64);

@@ -897,3 +897,42 @@ def test_gpu_large_ragged_batch_multi_cta_ordering(A, ctx, oracle):
     sel = list(range(0, B, 997))
     want = [oracle.roots(rows[p])[0] for p in sel]
     check_parity([rows[p] for p in sel], [got[p] for p in sel], want, C=C_RDS)
+
+
+def test_gpu_ragged_degree_classes(A, ctx, oracle):
+    """a ragged host batch is split into degree classes, each rooted by its own sub-context with the lane count
+    its degree and size call for, side by side -- here hundreds of small polynomials (unit queue, few lanes) next to a few
+    large ones (chained warps).  Every polynomial against the oracle; pinning the lane count switches the split off and
+    must give the same roots up to the parity tolerance."""
+    rng = np.random.default_rng(5)
+    degs = np.concatenate([rng.integers(30, 61, size=300), rng.integers(300, 501, size=40), rng.integers(2600, 3001, size=6), [0, 1, 2]])
+    rng.shuffle(degs)
+    rows = [oracle.fill_coeffs(61, p, 0, int(d) + 1) if d >= 1 else np.zeros(int(d)) for p, d in enumerate(degs)]
+    got = A.roots(rows, ctx=ctx)
+    st = dict(ctx.last_stats)
+    assert st["unconverged"] == 0 and st["lanes"] >= 64          # the large class runs on chained warps ...
+    pinned = A.Context(seed=0, schedule=A.SCHEDULE_PIPELINED, lanes_per_poly=16)
+    try:
+        ref = A.roots(rows, ctx=pinned)
+        assert pinned.last_stats["lanes"] == 16                    # ... which one lane count for the whole batch cannot give
+    finally:
+        pinned.close()
+    flat = np.concatenate(rows); off = np.zeros(len(rows) + 1, dtype=np.int64); np.cumsum([len(r) for r in rows], out=off[1:])
+    out, roff, nr, _ = oracle.roots_csr(flat, off)
+    big = [p for p, r in enumerate(rows) if len(r) > 3]
+    want = [out[roff[p]:roff[p] + nr[p]] for p in big]
+    check_parity([rows[p] for p in big], [got[p] for p in big], want, C=C_RDS)
+    check_parity([rows[p] for p in big], [ref[p] for p in big], want, C=C_RDS)
+    for p, r in enumerate(rows):
+        assert len(got[p]) == max(len(r) - 1, 0)
+    # complex and pencil batches go through the same split
+    crow = [oracle.fill_coeffs(62, p, 1, 2 * (int(d) + 1)) for p, d in enumerate([40] * 30 + [300] * 6 + [1400] * 2)]
+    crow = [r[0::2] + 1j * r[1::2] for r in crow]
+    cg = A.roots(crow, ctx=ctx)
+    cw = [oracle.roots(r)[0] for r in crow]
+    check_parity(crow, cg, cw, C=C_CSS, real_counts=False)
+    prow = [oracle.fill_coeffs(63, p, 0, int(d) + 1) for p, d in enumerate([40] * 30 + [300] * 6 + [1400] * 2)]
+    pairs = [A.basic_pencil(r) for r in prow]
+    pg = A.roots([v for v, _ in pairs], [w for _, w in pairs], ctx=ctx)
+    pw = [oracle.roots(v, ws=w)[0] for v, w in pairs]
+    check_parity(prow, pg, pw, C=C_PENCIL)
