@@ -10,7 +10,7 @@ imported through the shim `amrvw_jl_b200.py` at the repository root:
 from ._lib import (AmrvwError, Options, Stats, EXPORTS, SCHEDULE_AUTO, SCHEDULE_PIPELINED, SCHEDULE_REFERENCE, SCHEDULE_STREAMED,
                    SHIFTS_AUTO, SHIFTS_CHASE, SHIFTS_DENSE, lib_path, load)
 from .roots import (ComplexConjugateException, ComplexConjugateRootTheoremRoots, Context, basic_pencil, default_context,
-                    real_polynomial_roots, roots)
+                    real_polynomial_roots, roots, QRFactorization, qr_factorization, eigvals)
 from . import build as _build
 
 
@@ -18,6 +18,6 @@ def build(**kw):
     return _build.build(**kw)
 
 
-__all__ = ["roots", "basic_pencil", "real_polynomial_roots", "ComplexConjugateRootTheoremRoots", "ComplexConjugateException",
+__all__ = ["roots", "qr_factorization", "eigvals", "QRFactorization", "basic_pencil", "real_polynomial_roots", "ComplexConjugateRootTheoremRoots", "ComplexConjugateException",
            "Context", "default_context", "AmrvwError", "Options", "Stats", "EXPORTS", "load", "lib_path", "build",
            "SCHEDULE_AUTO", "SCHEDULE_REFERENCE", "SCHEDULE_PIPELINED", "SCHEDULE_STREAMED", "SHIFTS_AUTO", "SHIFTS_CHASE", "SHIFTS_DENSE"]

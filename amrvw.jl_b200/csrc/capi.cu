@@ -9,6 +9,7 @@
 #include "stream.cuh"
 #include "css_units.cuh"
 #include "pencil_units.cuh"
+#include "hessenberg.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -45,6 +46,7 @@ struct amrvw_ctx {
     // degree classes of a ragged host batch: one sub-context per class on THIS device, created on first use,
     // each with its own stream and workspace so that the classes' kernels run side by side with their own lane counts
     std::vector<amrvw_ctx*> klass;
+    DevBuf hwork, hmeta;            // Hessenberg eigenproblems: global R workspace, offsets
     DevBuf members;                 // class sub-context: batch indices of its polynomials
     cudaEvent_t ev_in = nullptr, ev_done = nullptr;
 };
@@ -161,7 +163,7 @@ int amrvw_destroy(amrvw_ctx* ctx) {
     if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
     DevBuf* all[] = {&ctx->chains[0], &ctx->chains[1], &ctx->chains[2], &ctx->chains[3], &ctx->chains[4], &ctx->diags[0], &ctx->diags[1], &ctx->diags[2],
                      &ctx->coeffs, &ctx->coeffs2, &ctx->offsets, &ctx->roots, &ctx->nroots, &ctx->nunconv, &ctx->stats, &ctx->shifts, &ctx->state, &ctx->prof,
-                     &ctx->rec, &ctx->fatshifts, &ctx->swlist, &ctx->counters, &ctx->queue, &ctx->qslots, &ctx->park, &ctx->parked, &ctx->order, &ctx->orderkeys, &ctx->counts, &ctx->squeues, &ctx->sslots};
+                     &ctx->rec, &ctx->fatshifts, &ctx->swlist, &ctx->counters, &ctx->queue, &ctx->qslots, &ctx->park, &ctx->parked, &ctx->order, &ctx->orderkeys, &ctx->counts, &ctx->squeues, &ctx->sslots, &ctx->hwork, &ctx->hmeta};
     for (DevBuf* b : all) if (b->ptr) cudaFree(b->ptr);
     for (cudaEvent_t e : ctx->evpool) if (e) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -819,3 +821,107 @@ int amrvw_measure_fp64_peak(amrvw_ctx* ctx, double* tflops) {
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------- Hessenberg eigenproblems
+// eigvals(qr_factorization(H; unitary)) for a batch of upper Hessenberg matrices from host buffers: one warp per matrix
+// (hessenberg.cuh), R in shared memory when the largest matrix of the batch fits, else in a global workspace.
+template <class S>
+static int run_hessenberg(amrvw_ctx* ctx, const S* H, const int32_t* dims, int64_t nbatch, int unitary, double* eig, int32_t* nunconv, amrvw_stats* stats) {
+    ctx = primary(ctx);
+    if (!ctx) return AMRVW_ERR_ARGUMENT;
+    if (nbatch < 0) return fail(ctx, AMRVW_ERR_ARGUMENT, "negative batch size");
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    if (nbatch == 0) return AMRVW_OK;
+    if (!H || !dims || !eig || !nunconv) return fail(ctx, AMRVW_ERR_ARGUMENT, "null buffer");
+    if (nbatch > 0x7fffffffLL) return fail(ctx, AMRVW_ERR_ARGUMENT, "batch too large");
+    std::vector<long long> meta(2 * (size_t)(nbatch + 1));
+    long long* moff = meta.data(); long long* eoff = moff + nbatch + 1;
+    int nmax = 1;
+    moff[0] = 0; eoff[0] = 0;
+    for (int64_t p = 0; p < nbatch; ++p) {
+        const long long n = dims[p];
+        if (n < 0 || n > 32768) return fail(ctx, AMRVW_ERR_ARGUMENT, "matrix dimension out of range (0..32768)");
+        moff[p + 1] = moff[p] + n * n; eoff[p + 1] = eoff[p] + n;
+        if (n > nmax) nmax = (int)n;
+    }
+    const long long nelem = moff[nbatch], neig = eoff[nbatch];
+    if (neig == 0) { std::fill(nunconv, nunconv + nbatch, 0); return AMRVW_OK; }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    (void)cudaGetLastError();
+    cudaStream_t st = ctx->stream;
+    const int ld = nmax | 1;                                    // odd: rows and columns of R both map to distinct banks
+    const size_t smem_cap = 220 * 1024;
+    const size_t full = hess_warp_bytes<S>(nmax, ld, true), lean = hess_warp_bytes<S>(nmax, ld, false);
+    // the chase is latency bound: 16 resident warps per SM matter more than where R lives.  R stays in shared memory only while
+    // 16 warps' worth fits (real n <= 39, complex n <= 27; measured: n = 32 +12 %), else in the global workspace, which the L2 holds
+    // (n = 64: 1.4x, n = 96: 3.2x, n = 128: 4.9x over one-warp-per-SM shared memory; profiles/r02_hessenberg.json)
+    const bool in_smem = full * 16 <= smem_cap;
+    const size_t per_warp = in_smem ? full : lean;
+    if (per_warp > smem_cap) return fail(ctx, AMRVW_ERR_ARGUMENT, "matrix too large for the per-warp rotator storage");
+    int wpc = (int)std::min<size_t>(8, smem_cap / per_warp);
+    if ((int64_t)wpc > nbatch) wpc = (int)nbatch;
+    // several CTAs per SM when they fit: the chase is latency bound, more warps hide it
+    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, smem_cap / (per_warp * wpc)));
+    while (per_sm * wpc > 16) { if (per_sm > 1) --per_sm; else break; }
+    int64_t ctas = (nbatch + wpc - 1) / wpc;
+    if (ctas > (int64_t)ctx->sm_count * per_sm) ctas = (int64_t)ctx->sm_count * per_sm;
+    const size_t work_stride = ((size_t)nmax * ld * sizeof(S) + 255) & ~(size_t)255;
+    int rc;
+    if ((rc = reserve(ctx, ctx->coeffs, (size_t)nelem * sizeof(S)))) return rc;
+    if ((rc = reserve(ctx, ctx->hmeta, meta.size() * sizeof(long long) + (size_t)nbatch * sizeof(int)))) return rc;
+    if ((rc = reserve(ctx, ctx->roots, (size_t)neig * sizeof(cplx)))) return rc;
+    if ((rc = reserve(ctx, ctx->nunconv, (size_t)nbatch * sizeof(int)))) return rc;
+    if ((rc = reserve(ctx, ctx->stats, (size_t)nbatch * sizeof(PolyStats) + sizeof(StatsAccum)))) return rc;
+    if ((rc = reserve(ctx, ctx->counters, 64 * sizeof(unsigned int)))) return rc;
+    if (!in_smem && (rc = reserve(ctx, ctx->hwork, work_stride * (size_t)ctas * wpc))) return rc;
+    long long* d_meta = (long long*)ctx->hmeta.ptr;
+    int* d_dims = (int*)(d_meta + meta.size());
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->coeffs.ptr, H, (size_t)nelem * sizeof(S), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_meta, meta.data(), meta.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_dims, dims, (size_t)nbatch * sizeof(int), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.ptr, 0, sizeof(unsigned int), st));
+    {
+        const AlgoConst ac = {ctx->opt.tol, ctx->opt.it_count, ctx->opt.it_max_factor};
+        CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(g_algo, &ac, sizeof(ac), 0, cudaMemcpyHostToDevice, st));
+    }
+    HessArgs a;
+    a.H = ctx->coeffs.ptr; a.dims = d_dims; a.moff = d_meta; a.eoff = d_meta + nbatch + 1;
+    a.eig = (cplx*)ctx->roots.ptr; a.nunconv = (int*)ctx->nunconv.ptr; a.stats = (PolyStats*)ctx->stats.ptr;
+    a.next = (unsigned int*)ctx->counters.ptr; a.work = in_smem ? nullptr : ctx->hwork.ptr; a.work_stride = work_stride;
+    a.nbatch = nbatch; a.unitary = unitary ? 1 : 0; a.ld_max = ld; a.seed = ctx->opt.seed;
+    const size_t smem = per_warp * wpc;
+    auto kern = in_smem ? hess_kernel<S, true> : hess_kernel<S, false>;
+    CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (stats) CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, st));
+    kern<<<(int)ctas, 32 * wpc, smem, st>>>(a, nmax);
+    CUDA_TRY(ctx, cudaGetLastError());
+    if (stats) CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(eig, ctx->roots.ptr, (size_t)neig * sizeof(cplx), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(nunconv, ctx->nunconv.ptr, (size_t)nbatch * sizeof(int), cudaMemcpyDeviceToHost, st));
+    std::vector<PolyStats> ps;
+    if (stats) {
+        ps.resize((size_t)nbatch);
+        CUDA_TRY(ctx, cudaMemcpyAsync(ps.data(), ctx->stats.ptr, (size_t)nbatch * sizeof(PolyStats), cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    ctx->prof_valid = false;
+    if (stats) {
+        for (const PolyStats& q : ps) {
+            stats->turnovers += q.turnovers; stats->sweeps += q.sweeps; stats->exceptional += q.exceptional; stats->unconverged += q.unconverged;
+        }
+        float ms = 0.f;
+        CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        stats->device_ms = ms; stats->launches = 1; stats->lanes = in_smem ? 1 : 0;   // lanes: 1 = R in shared memory, 0 = R in the global workspace
+        stats->schedule_used = AMRVW_SCHEDULE_REFERENCE;
+    }
+    return AMRVW_OK;
+}
+
+extern "C" {
+int amrvw_eigvals_hessenberg_f64(amrvw_ctx* ctx, const double* H, const int32_t* dims, int64_t nbatch, int unitary, double* eig, int32_t* nunconv, amrvw_stats* stats) {
+    return run_hessenberg<double>(ctx, H, dims, nbatch, unitary, eig, nunconv, stats);
+}
+int amrvw_eigvals_hessenberg_c64(amrvw_ctx* ctx, const double* H, const int32_t* dims, int64_t nbatch, int unitary, double* eig, int32_t* nunconv, amrvw_stats* stats) {
+    return run_hessenberg<cplx>(ctx, (const cplx*)H, dims, nbatch, unitary, eig, nunconv, stats);
+}
+}

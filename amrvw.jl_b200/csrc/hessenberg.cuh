@@ -1,0 +1,432 @@
+// hessenberg.cuh -- eigenvalues of upper Hessenberg matrices through qr_factorization:
+// the same core chase as the companion path, with R held as a dense upper triangular matrix
+// (RFactorizationUpperTriangular, rfactorization.jl:259-357) or, for a unitary H, as a unitary diagonal
+// (RFactorizationUnitaryDiagonal, rfactorization.jl:230-248).
+//
+// One warp per matrix.  The scalar part of the algorithm (shifts, turnovers in Q, deflation) is executed by all
+// 32 lanes on the same values; the O(n) part -- passing a rotator through the dense R is a column rotation of
+// columns i, i+1 and a row rotation of rows i, i+1 -- is split over the lanes.  Only the diagonal block of the
+// active window is kept up to date: rows above it and columns right of it never feed an eigenvalue (a row
+// rotation mixes rows i, i+1 only, a column rotation columns i, i+1 only), so each entry that is read sees exactly
+// the arithmetic of the reference and the eigenvalues do not change.  R lives in shared memory when the matrix
+// fits (leading dimension odd: rows and columns are both conflict free), else in a global workspace (L2).
+// Q, D_Q and the unitary diagonal are shared by the warp: every update is "all lanes read, __syncwarp, lane 0 writes,
+// __syncwarp" (hput / HWRITE below), so no lane can read a value another lane has already replaced.
+#pragma once
+#include "solver.cuh"
+
+namespace amrvw {
+
+template <class S> struct HFact {
+    Rot<S>* Q;     // descending chain, slots 0..N (1..N-1 live, 0 and N identity sentinels)
+    S* DQ;         // complex only: slots 0..N+1
+    S* R;          // dense mode: column major, entry (l,k) 1-based at R[(l-1) + (k-1)*ld]
+    S* D;          // unitary mode: diagonal of R, slots 1..N
+    int ld, N;
+    bool unitary;
+    int lane;
+    long long turnovers;
+};
+
+// lane 0 stores, between two warp barriers: the reads every lane did before the call are complete, the new values are visible after it
+#define HWRITE(F, ...) do { __syncwarp(); if ((F).lane == 0) { __VA_ARGS__; } __syncwarp(); } while (0)
+
+template <class S> AMRVW_DI S& hr(const HFact<S>& F, int l, int k) { return F.R[(size_t)(k - 1) * F.ld + (l - 1)]; }
+template <class S> AMRVW_DI S hr_entry(const HFact<S>& F, int l, int k) {   // rfactorization.jl:268-274 / diagonal.jl:30-36
+    if (F.unitary) return l == k ? F.D[l] : S(0.0);
+    return hr(F, l, k);
+}
+// A = (Q R)[j:j+1, j:j+1]   (diagonal-block.jl:12-36); same closed form for the Q side as solver.cuh: q_block
+template <class S> AMRVW_NI void diagonal_block(const HFact<S>& F, int j, S A[4]) {
+    const Rot<S> qm = F.Q[j - 1], q0 = F.Q[j], qp = F.Q[j + 1];
+    const S dm = dget(F.DQ, j - 1), d0 = dget(F.DQ, j), dp = dget(F.DQ, j + 1);
+    const S qji = S(-qm.s) * dm;
+    const S qjj = conj_(qm.c) * q0.c * d0;
+    const S qjk = qp.c * q0.s * conj_(qm.c) * dp;
+    const S qkj = S(-q0.s) * d0;
+    const S qkk = conj_(q0.c) * qp.c * dp;
+    const int i = j - 1, k = j + 1;
+    const S rjj = hr_entry(F, j, j), rjk = hr_entry(F, j, k), rkk = hr_entry(F, k, k);
+    S rij = S(0.0), rik = S(0.0);
+    if (i >= 1) { rij = hr_entry(F, i, j); rik = hr_entry(F, i, k); }
+    A[0] = qji * rij + qjj * rjj;
+    A[1] = qji * rik + qjj * rjk + qjk * rkk;
+    A[2] = qkj * rjj;
+    A[3] = qkj * rjk + qkk * rkk;
+}
+
+// passthrough!(RF::RFactorizationUpperTriangular, V) (rfactorization.jl:317-352): R V = U' R'.  Rows lo..i of the column
+// rotation and columns i+1..hi of the row rotation (the active window) are split over the lanes; the three entries of the
+// 2x2 diagonal block are carried in registers by every lane, so the Givens rotation in the middle needs no exchange.
+template <class S> AMRVW_DI void pass_dense(HFact<S>& F, Rot<S>& V, int i, int lo, int hi) {
+    const int j = i + 1, lane = F.lane;
+    S* Ri = F.R + (size_t)(i - 1) * F.ld;
+    S* Rj = Ri + F.ld;
+    const S c = V.c; const double sn = V.s;
+    __syncwarp();
+    const S rii = Ri[i - 1], rij = Rj[i - 1], rjj = Rj[j - 1];
+    __syncwarp();
+    for (int k = lo - 1 + lane; k < i - 1; k += 32) {
+        const S rki = Ri[k], rkj = Rj[k];
+        Ri[k] = c * rki - sn * rkj;
+        Rj[k] = sn * rki + conj_(c) * rkj;
+    }
+    const S nii = c * rii - sn * rij;
+    const S nij = sn * rii + conj_(c) * rij;
+    const S rji = c * S(0.0) - sn * rjj;              // R[j,i] is a structural zero
+    const S njj = sn * S(0.0) + conj_(c) * rjj;
+    S c2, r; double s2;
+    givensrot(nii, rji, c2, s2, r);
+    for (int k = j + 1 + lane; k <= hi; k += 32) {
+        S* Rk = F.R + (size_t)(k - 1) * F.ld;
+        const S rik = Rk[i - 1], rjk = Rk[j - 1];
+        Rk[i - 1] = c2 * rik + s2 * rjk;
+        Rk[j - 1] = -(s2 * rik) + conj_(c2) * rjk;
+    }
+    if (lane == 0) {
+        Ri[i - 1] = c2 * nii + s2 * rji;
+        Rj[i - 1] = c2 * nij + s2 * njj;
+        Rj[j - 1] = -(s2 * nij) + conj_(c2) * njj;
+    }
+    __syncwarp();
+    V = adjoint(make_rot<S>(c2, s2));
+}
+// diagonal.jl:84-96 on a diagonal shared by the warp; real: no-op
+template <class S> AMRVW_DI void hpass_diag(HFact<S>& F, S* D, Rot<S>& U, int i) {
+    if constexpr (!is_real<S>::value) {
+        const S alpha = D[i], beta = D[i + 1];
+        HWRITE(F, D[i] = beta; D[i + 1] = alpha);
+        U.c = (alpha * conj_(beta)) * U.c;
+    }
+}
+// passthrough!(RF, U) for the two R factorizations of qr_factorization
+template <class S> AMRVW_DI void pass_R(HFact<S>& F, Rot<S>& U, int i, int lo, int hi) {
+    if (F.unitary) {   // diagonal.jl:84-96 (complex: the entries swap, the cosine takes the phase), :113-118 (real: the sine takes d_i d_{i+1})
+        if constexpr (is_real<S>::value) U.s = U.s * F.D[i] * F.D[i + 1];
+        else hpass_diag(F, F.D, U, i);
+        return;
+    }
+    pass_dense(F, U, i, lo, hi);
+}
+template <class S> AMRVW_DI void pass_Qh(HFact<S>& F, Rot<S>& U, int& i) {   // qfactorization.jl:86-91
+    hpass_diag(F, F.DQ, U, i);
+    Rot<S> r1, r2, r3;
+    turnover(F.Q[i], F.Q[i + 1], U, r1, r2, r3);   // chains.jl:360
+    F.turnovers++;
+    U = r1;
+    HWRITE(F, F.Q[i] = r2; F.Q[i + 1] = r3);
+    i += 1;
+}
+
+AMRVW_NI void push_phase(HFact<cplx>& F, cplx alpha, int i) {   // diagonal.jl:199-225; nothing comes back, lane 0 does it
+    __syncwarp();
+    if (F.lane == 0) {
+        const int M = F.N - 1;
+        F.DQ[i] = F.DQ[i] * alpha;
+        const cplx ca = conj_(alpha);
+        while (i < M) {
+            Rot<cplx> q = F.Q[i + 1];
+            if (q.s == 0.0) break;
+            q.c = ca * q.c;
+            F.Q[i + 1] = q;
+            ++i;
+        }
+        F.DQ[i + 1] = F.DQ[i + 1] * ca;
+    }
+    __syncwarp();
+}
+
+// real double shift (create-bulge.jl:20-77, RDS.jl, bulge-step.jl:36-49) -- solver.cuh: bulge_step without the rank-one shortcut
+AMRVW_NI void bulge_step(HFact<double>& F, Counter& ctr, uint64_t seed, uint64_t mat, int& ord, PolyStats& st) {
+    st.sweeps++;
+    Rot<double> U, V, W;
+    int i = ctr.start_index;
+    const int lo = ctr.start_index, hi = ctr.stop_index + 1;
+    if (ctr.it_count == 0) {
+        ctr.it_count = AMRVW_IT_COUNT;
+        st.exceptional++;
+        const double t = uniform01(seed ^ 0xA5A5A5A5DEADBEEFull, mat, (uint64_t)ord++) * 3.141592653589793;
+        double sn, cs;
+        sincos(t, &sn, &cs);
+        U = make_rot<double>(sn, cs);
+        V = make_rot<double>(sn, -cs);
+    } else {
+        double A[4];
+        cplx e1, e2;
+        diagonal_block(F, ctr.stop_index, A);
+        eig2x2(A, e1, e2);
+        diagonal_block(F, i, A);
+        const double bk11 = A[0], bk12 = A[1], bk21 = A[2], bk22 = A[3];
+        const double bk32 = (-F.Q[i + 1].s) * hr_entry(F, i + 1, i + 1);
+        const double c1 = -e1.im * e2.im + e1.re * e2.re - e1.re * bk11 - e2.re * bk11 + bk11 * bk11 + bk12 * bk21;
+        const double c2 = -e1.re * bk21 - e2.re * bk21 + bk11 * bk21 + bk21 * bk22;
+        const double c3 = bk21 * bk32;
+        double c, s, nrm, tmp;
+        givensrot(c2, c3, c, s, nrm);
+        V = make_rot<double>(c, -s);
+        givensrot(c1, nrm, c, s, tmp);
+        U = make_rot<double>(c, -s);
+    }
+    const int nq = F.N - 1;
+    {   // absorb_Ut (RDS.jl:14-36)
+        const double p = i == 1 ? 1.0 : sign_(F.Q[i - 1].c);
+        Rot<double> w = F.Q[i];
+        w.s = sign_(p) * w.s;
+        Rot<double> r1, r2, r3;
+        turnover(adjoint(U), adjoint(V), w, r1, r2, r3);
+        F.turnovers++;
+        W = r1;
+        const Rot<double> f = fuse(r3, F.Q[i + 1]);
+        r2.s = sign_(p) * r2.s;
+        HWRITE(F, F.Q[i + 1] = f; F.Q[i] = r2);
+    }
+    for (;;) {
+        const int j = i + 1;
+        pass_R(F, V, j, lo, hi);      // passthrough_triu (RDS.jl:42-70)
+        pass_R(F, U, i, lo, hi);
+        if (j < ctr.stop_index) {     // passthrough_Q (RDS.jl:97-131)
+            int jv = j, iu = i;
+            pass_Qh(F, V, jv);
+            pass_Qh(F, U, iu);
+            Rot<double> r1, r2, r3;
+            turnover(W, V, U, r1, r2, r3);
+            F.turnovers++;
+            V = r1; U = r2; W = r3;
+            i += 1;
+        } else {
+            const double p = (j + 1 > nq) ? 1.0 : sign_(F.Q[j + 1].c);
+            V.s = sign_(p) * V.s;
+            const Rot<double> fj = fuse(F.Q[j], V);
+            HWRITE(F, F.Q[j] = fj);
+            int iu = i;
+            pass_Qh(F, U, iu);        // real: no diagonal; U now at j
+            U = fuse(W, U);
+            pass_R(F, U, iu, lo, hi);
+            U.s = sign_(p) * U.s;
+            const Rot<double> fu = fuse(F.Q[iu], U);
+            HWRITE(F, F.Q[iu] = fu);
+            break;
+        }
+    }
+}
+AMRVW_DI void deflate(HFact<double>& F, int k) {  // RDS.jl:134-141
+    const Rot<double> q = make_rot<double>(sign_(F.Q[k].c), 0.0);
+    HWRITE(F, F.Q[k] = q);
+}
+
+// complex single shift (create-bulge.jl:85-110, CSS.jl)
+AMRVW_NI void bulge_step(HFact<cplx>& F, Counter& ctr, uint64_t seed, uint64_t mat, int& ord, PolyStats& st) {
+    st.sweeps++;
+    cplx A[4];
+    cplx shift;
+    const int lo = ctr.start_index, hi = ctr.stop_index + 1;
+    if (ctr.it_count == 0) {
+        ctr.it_count = AMRVW_IT_COUNT;
+        st.exceptional++;
+        const double t = uniform01(seed ^ 0xA5A5A5A5DEADBEEFull, mat, (uint64_t)ord++) * 3.141592653589793;
+        double sn, cs;
+        sincos(t, &sn, &cs);
+        shift = cplx(cs, sn);
+    } else {
+        diagonal_block(F, ctr.stop_index, A);
+        cplx e1, e2;
+        eig2x2(A, e1, e2);
+        shift = abs_(A[3] - e1) < abs_(A[3] - e2) ? e1 : e2;
+    }
+    int i = ctr.start_index;
+    diagonal_block(F, i, A);
+    cplx c, nrm; double sn;
+    givensrot(A[0] - shift, A[2], c, sn, nrm);
+    const Rot<cplx> R = make_rot<cplx>(c, sn);
+    Rot<cplx> U = adjoint(R);
+    {
+        cplx dph;
+        const Rot<cplx> f = fuse(R, F.Q[i], dph);
+        HWRITE(F, F.Q[i] = f);
+        push_phase(F, dph, i);
+    }
+    for (;;) {
+        pass_R(F, U, i, lo, hi);
+        if (i < ctr.stop_index) {
+            pass_Qh(F, U, i);
+        } else {
+            hpass_diag(F, F.DQ, U, i);
+            cplx dph;
+            const Rot<cplx> f = fuse(F.Q[i], U, dph);
+            const cplx d0 = F.DQ[i] * dph, d1 = F.DQ[i + 1] * conj_(dph);
+            HWRITE(F, F.Q[i] = f; F.DQ[i] = d0; F.DQ[i + 1] = d1);
+            break;
+        }
+    }
+}
+AMRVW_DI void deflate(HFact<cplx>& F, int k) {  // CSS.jl:98-122
+    const cplx alpha = F.Q[k].c;
+    HWRITE(F, F.Q[k] = make_rot<cplx>(cplx(1.0, 0.0), 0.0));
+    push_phase(F, alpha, k);
+}
+
+template <class S> AMRVW_NI void check_deflation(HFact<S>& F, Counter& ctr) {  // AMRVW_algorithm.jl:181-202
+    for (int k = ctr.stop_index; k >= ctr.start_index; --k) {
+        if (fabs(F.Q[k].s) <= AMRVW_EPS) {
+            deflate(F, k);
+            ctr.zero_index = k;
+            ctr.start_index = k + 1;
+            ctr.it_count = AMRVW_IT_COUNT;
+            return;
+        }
+    }
+}
+
+// AMRVW_algorithm.jl:10-138 -- the driver of solver.cuh: drive_window for lo = 1
+template <class S> AMRVW_DI int drive_hessenberg(HFact<S>& F, cplx* E, uint64_t seed, uint64_t mat, PolyStats& st) {
+    const int n = F.N;
+    Counter ctr = {0, 1, n - 1, AMRVW_IT_COUNT, -1};
+    const long long it_max = AMRVW_IT_MAX(n);
+    const bool w = F.lane == 0;
+    long long kk = 0;
+    int ord = 0;
+    S A[4];
+    check_deflation(F, ctr);
+    while (kk <= it_max) {
+        if (ctr.stop_index <= 0) return 0;
+        check_deflation(F, ctr);
+        ++kk;
+        const int k = ctr.stop_index;
+        const int delta = ctr.stop_index - ctr.zero_index;
+        if (delta == 1) {
+            diagonal_block(F, k, A);
+            cplx e1, e2;
+            eig2x2(A, e1, e2);
+            if (w) { E[k] = e1; E[k + 1] = e2; }
+            if (ctr.stop_index == 2) {
+                diagonal_block(F, 1, A);
+                if (w) E[1] = to_c(A[0]);
+                return 0;
+            }
+            ctr.stop_index = ctr.zero_index - 1;
+            ctr.zero_index = 0;
+            ctr.start_index = 1;
+            check_deflation(F, ctr);
+            if (ctr.stop_index <= 0) return 0;
+        } else if (delta <= 0) {
+            diagonal_block(F, k, A);
+            if (ctr.stop_index == 1) {
+                if (w) { E[1] = to_c(A[0]); E[2] = to_c(A[3]); }
+                return 0;
+            }
+            if (w) E[k + 1] = to_c(A[3]);
+            ctr.stop_index = ctr.zero_index - 1;
+            if (ctr.stop_index <= 0) return 0;
+            ctr.zero_index = 0;
+            ctr.start_index = 1;
+            check_deflation(F, ctr);
+        } else {
+            bulge_step(F, ctr, seed, mat, ord, st);
+            ctr.it_count -= 1;
+        }
+    }
+    return ctr.stop_index <= 0 ? 0 : ctr.stop_index + 1;
+}
+
+struct HessArgs {
+    const void* H;              // matrices back to back, column major, matrix p is dims[p] x dims[p]
+    const int* dims;
+    const long long* moff;      // element offset of matrix p in H (nbatch + 1)
+    const long long* eoff;      // eigenvalue slot offset of matrix p (nbatch + 1)
+    cplx* eig;
+    int* nunconv;
+    PolyStats* stats;           // one per matrix
+    unsigned int* next;         // work counter
+    void* work;                 // global workspace when R does not fit in shared memory: per warp slot `work_stride` bytes
+    size_t work_stride;
+    long long nbatch;
+    int unitary;
+    int ld_max;                 // leading dimension used for every matrix of the call (odd)
+    uint64_t seed;
+};
+
+template <class S> __host__ __device__ inline size_t hess_warp_bytes(int nmax, int ld, bool with_r) {
+    size_t b = (size_t)(nmax + 2) * sizeof(Rot<S>) + 2 * (size_t)(nmax + 2) * sizeof(S);   // Q, DQ, D
+    if (with_r) b += (size_t)nmax * ld * sizeof(S);
+    return (b + 15) & ~(size_t)15;
+}
+
+// One warp per matrix, matrices handed out by an atomic counter.  SMEM: R in shared memory, else in a.work.
+template <class S, bool SMEM>
+__global__ void hess_kernel(HessArgs a, int nmax) {
+    extern __shared__ __align__(16) unsigned char hsm[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t small = hess_warp_bytes<S>(nmax, a.ld_max, SMEM);
+    unsigned char* mine = hsm + (size_t)warp * small;
+    HFact<S> F;
+    F.Q = reinterpret_cast<Rot<S>*>(mine);
+    F.DQ = reinterpret_cast<S*>(mine + (size_t)(nmax + 2) * sizeof(Rot<S>));
+    F.D = F.DQ + (nmax + 2);
+    F.R = SMEM ? F.D + (nmax + 2)
+               : reinterpret_cast<S*>(static_cast<unsigned char*>(a.work) + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * a.work_stride);
+    F.ld = a.ld_max;
+    F.lane = lane;
+    const S* Hall = static_cast<const S*>(a.H);
+    for (;;) {
+        unsigned int p = 0;
+        if (lane == 0) p = atomicAdd(a.next, 1u);
+        p = __shfl_sync(0xffffffffu, p, 0);
+        if ((long long)p >= a.nbatch) break;
+        const int n = a.dims[p];
+        cplx* E = a.eig + a.eoff[p] - 1;     // 1-based slots
+        PolyStats st = {0, 0, 0, 0, 0};
+        F.N = n; F.unitary = false; F.turnovers = 0;
+        int unconv = 0;
+        if (n == 1) {
+            if (lane == 0) E[1] = to_c(Hall[a.moff[p]]);
+        } else if (n >= 2) {
+            const S* H = Hall + a.moff[p];
+            // load the upper Hessenberg part (column major, coalesced over rows)
+            for (int k = 1; k <= n; ++k) {
+                const int top = min(n, k + 1);
+                for (int l = 1 + lane; l <= top; l += 32) hr(F, l, k) = H[(size_t)(k - 1) * n + (l - 1)];
+            }
+            __syncwarp();
+            // qr_factorization! (qrfactorization.jl:69-85): Givens on (R[i,i], R[i+1,i]), row rotation of columns i+1..n
+            if (lane == 0) {
+                F.Q[0] = make_rot<S>(S(1.0), 0.0);
+                F.Q[n] = make_rot<S>(S(1.0), 0.0);
+            }
+            if constexpr (!is_real<S>::value) for (int k = lane; k <= n + 1; k += 32) F.DQ[k] = cplx(1.0, 0.0);
+            for (int i = 1; i <= n - 1; ++i) {
+                const int j = i + 1;
+                S c, r; double sn;
+                givensrot(hr(F, i, i), hr(F, j, i), c, sn, r);
+                if (lane == 0) F.Q[i] = adjoint(make_rot<S>(c, sn));
+                __syncwarp();
+                for (int k = j + lane; k <= n; k += 32) {
+                    const S rik = hr(F, i, k), rjk = hr(F, j, k);
+                    hr(F, i, k) = c * rik + sn * rjk;
+                    hr(F, j, k) = -(sn * rik) + conj_(c) * rjk;
+                }
+                if (lane == 0) { hr(F, i, i) = r; hr(F, j, i) = S(0.0); }
+                __syncwarp();
+            }
+            if (a.unitary) {   // R = sign.(diag(R))  (qrfactorization.jl:87-93)
+                for (int k = 1 + lane; k <= n; k += 32) {
+                    const S z = hr(F, k, k);
+                    if constexpr (is_real<S>::value) F.D[k] = sign_(z);
+                    else F.D[k] = iszero_(z) ? z : z / abs_(z);
+                }
+                F.unitary = true;
+            }
+            __syncwarp();
+            if (lane == 0) for (int k = 1; k <= n; ++k) E[k] = cplx(0.0, 0.0);
+            unconv = drive_hessenberg(F, E, a.seed, (uint64_t)p, st);
+            __syncwarp();
+            if (lane == 0) sort_roots(E + 1, n);
+        }
+        if (lane == 0) {
+            a.nunconv[p] = unconv;
+            if (a.stats) { st.turnovers = F.turnovers; st.unconverged = unconv; a.stats[p] = st; }
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace amrvw

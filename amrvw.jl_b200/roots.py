@@ -154,6 +154,35 @@ class Context:
         self.last_stats = st.as_dict() if want_stats else None
         return counts[:B], nunc[:B]
 
+    def eigvals_hessenberg(self, mats, unitary=False, want_stats=True):
+        """Eigenvalues of a sequence of upper Hessenberg matrices (qr_factorization + eigvals, qrfactorization.jl:63-103) in one
+        GPU call.  Returns (list of complex128 arrays sorted by (real, imag), n_unconverged int32[B])."""
+        flat, dims = pack_matrices(mats)
+        out, eoff, nunc = self.eigvals_hessenberg_packed(flat, dims, unitary=unitary, want_stats=want_stats)
+        return [out[eoff[p]:eoff[p + 1]].copy() for p in range(len(dims))], nunc
+
+    def eigvals_hessenberg_packed(self, flat, dims, unitary=False, want_stats=True):
+        """The C call itself: `flat` holds the matrices back to back in column major order (float64 or complex128), matrix p is
+        dims[p] x dims[p].  Returns (eigenvalues flat complex128, slot offsets int64[B+1], n_unconverged int32[B])."""
+        dims = np.ascontiguousarray(dims, dtype=np.int32)
+        B = len(dims)
+        cx = np.iscomplexobj(flat)
+        flat = np.ascontiguousarray(flat, dtype=np.complex128 if cx else np.float64)
+        if flat.size < int((dims.astype(np.int64) ** 2).sum()):
+            raise ValueError("matrix buffer shorter than sum(dims^2)")
+        if flat.size == 0:
+            flat = np.zeros(1, dtype=flat.dtype)
+        eoff = np.zeros(B + 1, dtype=np.int64)
+        np.cumsum(dims, out=eoff[1:])
+        out = np.zeros(int(eoff[-1]) + 1, dtype=np.complex128)
+        nunc = np.zeros(max(B, 1), dtype=np.int32)
+        st = Stats()
+        fn = self._lib.amrvw_eigvals_hessenberg_c64 if cx else self._lib.amrvw_eigvals_hessenberg_f64
+        self._check(fn(self._h, _ptr(flat), _ptr(dims if B else np.zeros(1, dtype=np.int32)), B, int(bool(unitary)), _ptr(out), _ptr(nunc),
+                       ctypes.byref(st) if want_stats else None))
+        self.last_stats = st.as_dict() if want_stats else None
+        return out, eoff, nunc[:B]
+
     # -- device pointers (ints) in/out: used by bench.py with torch-owned HBM buffers
     def roots_dev(self, kind, d_coeffs, d_offsets, B, total, max_len, d_roots, d_nroots, d_nunconv, d_ws=None, want_stats=False):
         st = Stats()
@@ -228,6 +257,53 @@ def roots(ps, ws=None, ctx=None):
             wflat = wflat.astype(np.complex128)
     out, roff, nroots, _ = ctx.roots_csr(flat, offsets, wflat)
     res = [out[roff[p]: roff[p] + nroots[p]].copy() for p in range(len(seq))]
+    return res if batch else res[0]
+
+
+def pack_matrices(mats):
+    """Square matrices -> (flat column-major buffer, dims int32[B]) as amrvw_eigvals_hessenberg_* take them."""
+    mats = [np.asarray(m) for m in mats]
+    for m in mats:
+        if m.ndim != 2 or m.shape[0] != m.shape[1]:
+            raise ValueError("qr_factorization needs square matrices")
+    cx = any(np.iscomplexobj(m) for m in mats)
+    dt = np.complex128 if cx else np.float64
+    dims = np.array([m.shape[0] for m in mats], dtype=np.int32)
+    if len(mats) and int((dims.astype(np.int64) ** 2).sum()):
+        flat = np.concatenate([np.asfortranarray(m, dtype=dt).reshape(-1, order="F") for m in mats])
+    else:
+        flat = np.zeros(0, dtype=dt)
+    return flat, dims
+
+
+class QRFactorization:
+    """What `AMRVW.qr_factorization(H; unitary)` returns (qrfactorization.jl:63-103), as far as this package needs it: the
+    Hessenberg matrix and the kind of R.  The factorization itself is formed on the GPU inside `eigvals`."""
+
+    def __init__(self, H, unitary=False):
+        H = np.asarray(H)
+        if H.ndim != 2 or H.shape[0] != H.shape[1]:
+            raise ValueError("qr_factorization needs a square matrix")
+        self.H = H
+        self.unitary = bool(unitary)
+
+
+def qr_factorization(H, unitary=False):
+    """AMRVW.qr_factorization (qrfactorization.jl:63-66): H upper Hessenberg; `unitary=True` keeps R as a unitary diagonal."""
+    return QRFactorization(H, unitary)
+
+
+def eigvals(state, ctx=None):
+    """eigvals(state) (AMRVW_algorithm.jl:207-216) of one QRFactorization or of a sequence of them (one GPU call; the
+    sequence must share `unitary`).  Complex128 eigenvalues sorted by (real, imag)."""
+    ctx = ctx or default_context()
+    batch = isinstance(state, (list, tuple))
+    seq = list(state) if batch else [state]
+    if not all(isinstance(s, QRFactorization) for s in seq):
+        raise TypeError("eigvals needs the result of qr_factorization")
+    if len({s.unitary for s in seq}) > 1:
+        raise ValueError("one call roots factorizations of one kind (unitary or not)")
+    res, _ = ctx.eigvals_hessenberg([s.H for s in seq], unitary=seq[0].unitary if seq else False)
     return res if batch else res[0]
 
 

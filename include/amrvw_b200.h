@@ -148,6 +148,20 @@ int amrvw_roots_pencil_f64_dev(amrvw_ctx* ctx, const double* d_vs, const double*
 int amrvw_roots_pencil_c64_dev(amrvw_ctx* ctx, const double* d_vs_reim, const double* d_ws_reim, const int64_t* d_offsets, int64_t nbatch, int64_t total, int64_t max_len,
                                double* d_roots_reim, int32_t* d_nroots, int32_t* d_n_unconverged, amrvw_stats* stats);
 
+/* eigvals(qr_factorization(H; unitary)) for a batch of upper Hessenberg matrices, HOST buffers:
+ * replaces `eigvals(AMRVW.qr_factorization(M, unitary=...))` per matrix (src/qrfactorization.jl:63-103 with
+ * src/AMRVW_algorithm.jl:207-216; R as RFactorizationUpperTriangular, src/rfactorization.jl:259-357, or -- unitary != 0, for a
+ * unitary H -- as RFactorizationUnitaryDiagonal, :230-248).  H holds the matrices back to back, each dims[p] x dims[p] in
+ * column major order (Julia's layout; _c64: interleaved re, im); entries below the first subdiagonal are not read.  The
+ * eigenvalues of matrix p are written, sorted like LinearAlgebra.sorteig!, to complex slots sum(dims[0..p-1]) onwards of
+ * eig_reim; n_unconverged[p] counts the slots the iteration cap left at zero.  Real matrices run the real double shift
+ * chase, complex ones the single shift chase, one bulge at a time as the reference does.  A multi-device context runs the
+ * call on its first device. */
+int amrvw_eigvals_hessenberg_f64(amrvw_ctx* ctx, const double* H, const int32_t* dims, int64_t nbatch, int unitary,
+                                 double* eig_reim, int32_t* n_unconverged, amrvw_stats* stats);
+int amrvw_eigvals_hessenberg_c64(amrvw_ctx* ctx, const double* H_reim, const int32_t* dims, int64_t nbatch, int unitary,
+                                 double* eig_reim, int32_t* n_unconverged, amrvw_stats* stats);
+
 /* real_polynomial_roots (src/complex_conjugate_root_theorem.jl:32-54) for a batch, HOST buffers: roots the
  * polynomials like amrvw_roots_rds_f64 and returns only, per polynomial, the number of roots with imag == 0
  * exactly, imag > 0 and imag < 0 (counts3[3p..3p+2]) -- 12 bytes per polynomial come back instead of 16 n

@@ -343,6 +343,15 @@ template <class S> struct State {  // QRFactorization (qrfactorization.jl:15-18)
     RankOne<S> V;                  // R = V (rank one) or V * W^{-1} (pencil.jl:13-16)
     RankOne<S> W;
     bool pencil = false;
+    // R as a full upper triangular matrix (RFactorizationUpperTriangular, rfactorization.jl:259-357): the QR factorization of
+    // a general Hessenberg matrix (qr_factorization, qrfactorization.jl:63-103).  1-based, leading dimension N + 2.
+    bool dense = false;
+    // R as a unitary diagonal (RFactorizationUnitaryDiagonal, rfactorization.jl:230-248): qr_factorization(H; unitary=true)
+    bool udiag = false;
+    std::vector<S> Dd;       // 1-based
+    std::vector<S> Rd;
+    S& R(int i, int j) { return Rd[(size_t)i * (N + 2) + j]; }
+    const S& R(int i, int j) const { return Rd[(size_t)i * (N + 2) + j]; }
     S dq(int k) const { if constexpr (is_real<S>::value) return 1.0; else return DQ[k]; }
     int nq() const { return N - 1; }
 };
@@ -381,6 +390,8 @@ template <class S> static inline S r_entry(const RankOne<S>& RF, int j, int k) {
 }
 // pencil.jl:29-45 -- entries of V * W^{-1}
 template <class S> static inline S r_entry(const State<S>& st, int l, int k) {
+    if (st.udiag) return (l == k && l >= 1 && l <= st.N) ? st.Dd[l] : S(0.0);                   // diagonal.jl:30-36
+    if (st.dense) return (l >= 1 && k >= 1 && l <= st.N && k <= st.N) ? st.R(l, k) : S(0.0);   // rfactorization.jl:268-274
     if (!st.pencil) return r_entry(st.V, l, k);
     const RankOne<S>& V = st.V; const RankOne<S>& W = st.W;
     int delta = k - l;
@@ -513,8 +524,40 @@ template <class S> static inline void pass_rankone_lr(Rot<S>& U, RankOne<S>& RF,
     pass_desc_lr(U, RF.B, i, st);
     pass_diag(RF.D, U, i);  // diagonal.jl:100-101: passthrough!(U, D) returns passthrough!(D, U)
 }
-// passthrough!(RF, U) for rank one (rfactorization.jl:198) or pencil (pencil.jl:63-71)
+// passthrough!(RF::RFactorizationUpperTriangular, V) (rfactorization.jl:317-352): R V = U' R' with R' upper triangular again;
+// the rotator comes out on the left at the same index.  O(n) row/column rotations, no turnover.
+template <class S> static inline void pass_dense(State<S>& s, Rot<S>& V, int i) {
+    const int n = s.N, j = i + 1;
+    const S c = V.c; const double sn = V.s;
+    for (int k = 1; k <= i; ++k) {
+        const S rki = s.R(k, i), rkj = s.R(k, j);
+        s.R(k, i) = c * rki - sn * rkj;
+        s.R(k, j) = sn * rki + conj_(c) * rkj;
+    }
+    const S rji = c * s.R(j, i) - sn * s.R(j, j);
+    s.R(j, j) = sn * s.R(j, i) + conj_(c) * s.R(j, j);
+    S c2, r; double s2;
+    givensrot(s.R(i, i), rji, c2, s2, r);
+    {
+        const S rik = s.R(i, i), rjk = rji;
+        s.R(i, i) = c2 * rik + s2 * rjk;
+        s.R(j, i) = S(0.0);
+    }
+    for (int k = j; k <= n; ++k) {
+        const S rik = s.R(i, k), rjk = s.R(j, k);
+        s.R(i, k) = c2 * rik + s2 * rjk;
+        s.R(j, k) = -(s2 * rik) + conj_(c2) * rjk;
+    }
+    V = adjoint(Rot<S>{c2, s2});
+}
+// passthrough!(RF, U) for rank one (rfactorization.jl:198), pencil (pencil.jl:63-71) or dense R
 template <class S> static inline void pass_R(State<S>& s, Rot<S>& U, int& i, Stats& st) {
+    if (s.udiag) {   // passthrough!(D::SparseDiagonal, U): diagonal.jl:84-96 (complex), :113-118 (real: D stays, the sine takes d_i d_{i+1})
+        if constexpr (is_real<S>::value) U.s = U.s * s.Dd[i] * s.Dd[i + 1];
+        else pass_diag(s.Dd, U, i);
+        return;
+    }
+    if (s.dense) { pass_dense(s, U, i); return; }
     if (s.pencil) {
         Rot<S> Ut = adjoint(U);
         pass_rankone_lr(Ut, s.W, i, st);
@@ -622,6 +665,39 @@ template <class S> static void amrvw_pencil(const S* vs, const S* ws_in, int N, 
     r_factorization(ps, st.V);
     r_factorization(qs, st.W);
     st.pencil = true;
+}
+
+// qrfactorization.jl:63-103 -- qr_factorization(H): Givens QR of an upper Hessenberg matrix, Q as a descending chain of
+// n-1 rotators, R dense upper triangular.  H is column major n x n (Julia's layout).
+template <class S> static void qr_factorization(const S* H, int n, State<S>& st, bool unitary = false) {
+    q_factorization(st, n);
+    st.dense = true; st.pencil = false;
+    st.Rd.assign((size_t)(n + 2) * (n + 2), S(0.0));
+    for (int j = 1; j <= n; ++j)
+        for (int i = 1; i <= n; ++i) st.R(i, j) = H[(size_t)(j - 1) * n + (i - 1)];
+    for (int i = 1; i <= n - 1; ++i) {
+        S c, r; double sn;
+        givensrot(st.R(i, i), st.R(i + 1, i), c, sn, r);
+        st.Q[i] = adjoint(Rot<S>{c, sn});
+        const int j = i + 1;
+        st.R(i, i) = r;
+        st.R(j, i) = S(0.0);
+        for (int k = j; k <= n; ++k) {
+            const S rik = st.R(i, k), rjk = st.R(j, k);
+            st.R(i, k) = c * rik + sn * rjk;
+            st.R(j, k) = -(sn * rik) + conj_(c) * rjk;
+        }
+    }
+    if (unitary) {   // _qr_factorization(..., Val(true)): R = sign.(diag(R))  (qrfactorization.jl:87-93)
+        st.Dd.assign(n + 2, S(1.0));
+        for (int k = 1; k <= n; ++k) {
+            const S z = st.R(k, k);
+            if constexpr (is_real<S>::value) st.Dd[k] = sign_(z);
+            else st.Dd[k] = (z.re == 0.0 && z.im == 0.0) ? z : z / std::hypot(z.re, z.im);
+        }
+        st.dense = false; st.udiag = true;
+        st.Rd.clear();
+    }
 }
 
 // ------------------------------------------------------------------ bulge step, RDS (create-bulge.jl:20-77, RDS.jl)
@@ -882,7 +958,7 @@ static bool driver_window(State<S>& s, int lo, int /*hi*/, Counter& ctr, std::ve
 template <class S>
 static void amrvw_algorithm(State<S>& s, std::vector<cplx>& EIGS, Rng& rng, Stats& st) {
     int n = s.nq();
-    Counter ctr = {0, 1, n, IT_COUNT, n - 1};  // AMRVW_algorithm.jl:18
+    Counter ctr = {0, 1, n, IT_COUNT, (s.dense || s.udiag) ? -1 : n - 1};  // AMRVW_algorithm.jl:18; simple_passthrough! is false for a dense R (rfactorization.jl:355)
     EIGS.assign(n + 2, cplx(0, 0));
     int64_t it_max = 20 * (int64_t)n;          // :25
     bool ok = driver_window(s, 1, n, ctr, EIGS, rng, st, it_max);
@@ -1745,6 +1821,32 @@ int orc_ms_shift_check(const double* state, int N, const int32_t* ctr5, int m, d
     ms_shifts(s, c, m, sh, rng, sub);
     for (int i = 0; i < M; ++i) { chase_reim[2 * i] = sh[i].re; chase_reim[2 * i + 1] = sh[i].im; }
     return ok ? 0 : 1;
+}
+
+// eigvals(qr_factorization(H)) (qrfactorization.jl:63-103, AMRVW_algorithm.jl:207): H column major n x n upper Hessenberg
+// (entries below the first subdiagonal are ignored), real or interleaved complex; eigenvalues sorted like sorteig!.
+int orc_eigvals_hessenberg(const double* H, int n, int is_complex, int unitary, double* eig_reim, uint64_t seed, uint64_t index, orc_stats* stats) {
+    std::vector<cplx> E;
+    Stats st;
+    Rng rng; rng.seed = seed; rng.poly = index;     // index: position of the matrix in its batch (the exceptional shifts' stream)
+    if (n <= 0) return 0;
+    if (n == 1) {   // no rotator at all: the entry itself (the reference has no 1x1 case)
+        eig_reim[0] = H[0]; eig_reim[1] = is_complex ? H[1] : 0.0;
+        if (stats) std::memset(stats, 0, sizeof(*stats));
+        return 0;
+    }
+    if (is_complex) {
+        State<cplx> s;
+        qr_factorization(reinterpret_cast<const cplx*>(H), n, s, unitary != 0);
+        amrvw_algorithm(s, E, rng, st);
+    } else {
+        State<double> s;
+        qr_factorization(H, n, s, unitary != 0);
+        amrvw_algorithm(s, E, rng, st);
+    }
+    for (int i = 0; i < n; ++i) { eig_reim[2 * i] = E[i + 1].re; eig_reim[2 * i + 1] = E[i + 1].im; }
+    if (stats) { std::memset(stats, 0, sizeof(*stats)); add_stats(stats, st); }
+    return (int)st.unconverged;
 }
 
 // Synthetic inputs shared by every leg: kind 0 = N(0,1) (Box-Muller), 1 = U[0,1),

@@ -84,6 +84,18 @@ def roots(ps, ws=None, **kw):
     return out[:nr[0]].copy(), st
 
 
+def eigvals_hessenberg(H, unitary=False, seed=0, index=0):
+    """Oracle eigvals(qr_factorization(H)) (qrfactorization.jl:63-103): H upper Hessenberg, real or complex -> (eigenvalues, stats)."""
+    H = np.asarray(H)
+    n = H.shape[0]
+    cx = np.iscomplexobj(H)
+    Hf = np.asfortranarray(H, dtype=np.complex128 if cx else np.float64)
+    out = np.zeros(max(n, 1), dtype=np.complex128)
+    st = OStats()
+    lib().orc_eigvals_hessenberg(_p(Hf), int(n), int(cx), int(bool(unitary)), _p(out), ctypes.c_uint64(seed), ctypes.c_uint64(index), ctypes.byref(st))
+    return out[:n].copy(), st.as_dict()
+
+
 def fill_coeffs(seed, poly, kind, count):
     """Synthetic inputs shared by every leg: kind 0 = N(0,1), 1 = U[0,1), 2 = U[0,1) - 1/2."""
     out = np.zeros(count, dtype=np.float64)
