@@ -519,8 +519,8 @@ __global__ void __launch_bounds__(32, AMRVW_CSS_MINBLOCKS) css_unit_kernel(Probl
     const int grp = lane32 / L, lane = lane32 % L;
     const unsigned stage_sa = (unsigned)__cvta_generic_to_shared(css_ring + grp * (AMRVW_RING * AMRVW_CSS_SLOT));
 
-    long long pc_all = 0, pc_a = 0, pc_pop = 0;      // warp-cycle accounting (amrvw_last_profile)
-    long long pn_steps = 0;
+    long long pc_all = 0, pc_a = 0, pc_pop = 0, pc_lean = 0;      // warp-cycle accounting (amrvw_last_profile)
+    long long pn_steps = 0, pn_lean = 0;
     int pn_units = 0;
     for (;;) {
         // ---------------- pop a unit
@@ -621,7 +621,46 @@ __global__ void __launch_bounds__(32, AMRVW_CSS_MINBLOCKS) css_unit_kernel(Probl
                 cp_async_commit();
             }
         }
+        // lock-steps during which every lane of the warp (both groups) sits at a regular chase position: no creation, no last
+        // position, no window end -- the lean loop below (the complex twin of pipeline.cuh: lean_chase)
+        const bool lean_ok = __all_sync(0xffffffffu, act && nb == L);
+        const int lean_hi = lean_ok ? __reduce_min_sync(0xffffffffu, stop - start + 1) : 0;
         for (int t = t0; t < t1; ++t) {
+            if (lean_ok && t >= 2 * L && t < lean_hi) {
+                const int te = min(t1, lean_hi);
+                const long long pc_l0 = clock64();
+                CssIdx w0 = z.w0, w1 = z.w1;
+                Rot<cplx> U = z.U;
+                const cplx ca = z.ca;
+                int alive = z.alive;
+                int i = start + t - 2 * lane - 1;          // position of this lane's bulge
+                const int tb = t;
+#pragma unroll 1
+                for (; t < te; ++t, ++i) {
+                    CssIdx in = css_shfl_up(w0, L);
+                    if (lane == 0) {
+                        cp_async_wait_ring();
+                        in = css_read_slot(stage_sa + (t & (AMRVW_RING - 1)) * AMRVW_CSS_SLOT);
+                        css_prefetch_index(stage_sa + ((t + AMRVW_RING - 1) & (AMRVW_RING - 1)) * AMRVW_CSS_SLOT, F, min(start + t + AMRVW_RING - 1, stop + 1));
+                        cp_async_commit();
+                    }
+                    w0 = w1; w1 = in;
+                    if (alive) {   // the creation phase of this lane's bulge reaches index i + 1 (diagonal.jl:199-225)
+                        if (w1.q.s == 0.0) { w1.dq = w1.dq * ca; alive = 0; }
+                        else w1.q.c = ca * w1.q.c;
+                    }
+                    css_lane_regular(w0, w1, U);
+                    if (lane == L - 1) {
+                        css_store_index(F, i, w0);
+                        if (fabs(w0.q.s) <= AMRVW_EPS) dstack[sp++] = i;
+                    }
+                }
+                nturn += 3 * (te - tb);
+                z.w0 = w0; z.w1 = w1; z.U = U; z.alive = alive;
+                pc_lean += clock64() - pc_l0; pn_lean += te - tb;
+                t = te - 1;
+                continue;
+            }
             const int tp = t - 2 * lane;
             // ingest: the index the previous lane finished last step (lane 0: from memory)
             CssIdx in = css_shfl_up(z.w0, L);
@@ -686,8 +725,10 @@ __global__ void __launch_bounds__(32, AMRVW_CSS_MINBLOCKS) css_unit_kernel(Probl
     if (pr.prof && lane32 == 0) {
         atomicAdd(pr.prof + 0, (unsigned long long)pc_all);
         atomicAdd(pr.prof + 1, (unsigned long long)pc_a);
-        atomicAdd(pr.prof + 3, (unsigned long long)(pc_all - pc_a));
-        atomicAdd(pr.prof + 5, (unsigned long long)pn_steps);
+        atomicAdd(pr.prof + 2, (unsigned long long)pc_lean);
+        atomicAdd(pr.prof + 3, (unsigned long long)(pc_all - pc_a - pc_lean));
+        atomicAdd(pr.prof + 4, (unsigned long long)pn_lean);
+        atomicAdd(pr.prof + 5, (unsigned long long)(pn_steps - pn_lean));
         atomicAdd(pr.prof + 7, (unsigned long long)pn_units);
         atomicAdd(pr.prof + 13, (unsigned long long)pc_pop);
     }
