@@ -826,14 +826,63 @@ int amrvw_measure_fp64_peak(amrvw_ctx* ctx, double* tflops) {
 // eigvals(qr_factorization(H; unitary)) for a batch of upper Hessenberg matrices from host buffers: one warp per matrix
 // (hessenberg.cuh), R in shared memory when the largest matrix of the batch fits, else in a global workspace.
 template <class S>
+static int run_hessenberg_single(amrvw_ctx* ctx, const S* H, const int32_t* dims, int64_t nbatch, int unitary, double* eig, int32_t* nunconv, amrvw_stats* stats);
+
+// Several devices: contiguous split by matrix, balanced by the sum of n^3 (the work of the dense-R chase), one host thread per
+// device, results copied straight into the caller's buffers -- the same scheme as run_host.
+template <class S>
 static int run_hessenberg(amrvw_ctx* ctx, const S* H, const int32_t* dims, int64_t nbatch, int unitary, double* eig, int32_t* nunconv, amrvw_stats* stats) {
-    ctx = primary(ctx);
     if (!ctx) return AMRVW_ERR_ARGUMENT;
     if (nbatch < 0) return fail(ctx, AMRVW_ERR_ARGUMENT, "negative batch size");
     if (stats) std::memset(stats, 0, sizeof(*stats));
     if (nbatch == 0) return AMRVW_OK;
     if (!H || !dims || !eig || !nunconv) return fail(ctx, AMRVW_ERR_ARGUMENT, "null buffer");
     if (nbatch > 0x7fffffffLL) return fail(ctx, AMRVW_ERR_ARGUMENT, "batch too large");
+    for (int64_t p = 0; p < nbatch; ++p)
+        if (dims[p] < 0 || dims[p] > 32768) return fail(ctx, AMRVW_ERR_ARGUMENT, "matrix dimension out of range (0..32768)");
+    if (ctx->subs.empty()) return run_hessenberg_single<S>(ctx, H, dims, nbatch, unitary, eig, nunconv, stats);
+    const int ndev = (int)ctx->subs.size();
+    double work = 0.0;
+    for (int64_t p = 0; p < nbatch; ++p) { const double n = dims[p]; work += n * n * n; }
+    std::vector<int64_t> cut((size_t)ndev + 1, nbatch), moff((size_t)ndev + 1, 0), eoff((size_t)ndev + 1, 0);
+    cut[0] = 0;
+    {
+        double acc = 0.0; long long mo = 0, eo = 0; int d = 1;
+        for (int64_t p = 0; p < nbatch; ++p) {
+            while (d < ndev && acc >= work * d / ndev) { cut[(size_t)d] = p; moff[(size_t)d] = mo; eoff[(size_t)d] = eo; ++d; }
+            const long long n = dims[p];
+            acc += (double)n * n * n; mo += n * n; eo += n;
+        }
+        while (d <= ndev) { cut[(size_t)d] = nbatch; moff[(size_t)d] = mo; eoff[(size_t)d] = eo; ++d; }
+    }
+    std::vector<int> rcs((size_t)ndev, AMRVW_OK);
+    std::vector<amrvw_stats> sts((size_t)ndev);
+    std::vector<std::thread> workers;
+    for (int d = 0; d < ndev; ++d) {
+        const int64_t p0 = cut[(size_t)d], p1 = cut[(size_t)d + 1];
+        if (p1 <= p0) continue;
+        workers.emplace_back([&, d, p0, p1]() {
+            rcs[(size_t)d] = run_hessenberg_single<S>(ctx->subs[(size_t)d], H + moff[(size_t)d], dims + p0, p1 - p0, unitary, eig + 2 * eoff[(size_t)d], nunconv + p0,
+                                                      stats ? &sts[(size_t)d] : nullptr);
+        });
+    }
+    for (std::thread& t : workers) t.join();
+    for (int d = 0; d < ndev; ++d)
+        if (rcs[(size_t)d] != AMRVW_OK) return fail(ctx, rcs[(size_t)d], "device " + std::to_string(ctx->subs[(size_t)d]->device) + ": " + ctx->subs[(size_t)d]->err);
+    if (stats) {
+        for (int d = 0; d < ndev; ++d) {
+            const amrvw_stats& x = sts[(size_t)d];
+            stats->turnovers += x.turnovers; stats->sweeps += x.sweeps; stats->exceptional += x.exceptional; stats->unconverged += x.unconverged;
+            stats->launches += x.launches; stats->device_ms = std::max(stats->device_ms, x.device_ms); stats->lanes = std::max(stats->lanes, x.lanes);
+        }
+        stats->schedule_used = AMRVW_SCHEDULE_REFERENCE;
+    }
+    return AMRVW_OK;
+}
+
+template <class S>
+static int run_hessenberg_single(amrvw_ctx* ctx, const S* H, const int32_t* dims, int64_t nbatch, int unitary, double* eig, int32_t* nunconv, amrvw_stats* stats) {
+    if (stats) std::memset(stats, 0, sizeof(*stats));
     std::vector<long long> meta(2 * (size_t)(nbatch + 1));
     long long* moff = meta.data(); long long* eoff = moff + nbatch + 1;
     int nmax = 1;

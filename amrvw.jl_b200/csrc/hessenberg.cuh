@@ -64,9 +64,19 @@ template <class S> AMRVW_DI void pass_dense(HFact<S>& F, Rot<S>& V, int i, int l
     S* Rj = Ri + F.ld;
     const S c = V.c; const double sn = V.s;
     __syncwarp();
+    // the block and the first slice of both rotations are requested together (their addresses are disjoint from this position's stores)
     const S rii = Ri[i - 1], rij = Rj[i - 1], rjj = Rj[j - 1];
-    __syncwarp();
-    for (int k = lo - 1 + lane; k < i - 1; k += 32) {
+    const int r0 = lo - 1 + lane, m0 = j + 1 + lane;
+    const bool has_r = r0 < i - 1, has_m = m0 <= hi;
+    const int r0s = has_r ? r0 : i - 1;
+    S* Rm0 = F.R + (size_t)((has_m ? m0 : j) - 1) * F.ld;
+    const S a0 = Ri[r0s], b0 = Rj[r0s];
+    const S x0 = Rm0[i - 1], y0 = Rm0[j - 1];
+    if (has_r) {
+        Ri[r0] = c * a0 - sn * b0;
+        Rj[r0] = sn * a0 + conj_(c) * b0;
+    }
+    for (int k = r0 + 32; k < i - 1; k += 32) {
         const S rki = Ri[k], rkj = Rj[k];
         Ri[k] = c * rki - sn * rkj;
         Rj[k] = sn * rki + conj_(c) * rkj;
@@ -77,12 +87,17 @@ template <class S> AMRVW_DI void pass_dense(HFact<S>& F, Rot<S>& V, int i, int l
     const S njj = sn * S(0.0) + conj_(c) * rjj;
     S c2, r; double s2;
     givensrot(nii, rji, c2, s2, r);
-    for (int k = j + 1 + lane; k <= hi; k += 32) {
+    if (has_m) {
+        Rm0[i - 1] = c2 * x0 + s2 * y0;
+        Rm0[j - 1] = -(s2 * x0) + conj_(c2) * y0;
+    }
+    for (int k = m0 + 32; k <= hi; k += 32) {
         S* Rk = F.R + (size_t)(k - 1) * F.ld;
         const S rik = Rk[i - 1], rjk = Rk[j - 1];
         Rk[i - 1] = c2 * rik + s2 * rjk;
         Rk[j - 1] = -(s2 * rik) + conj_(c2) * rjk;
     }
+    __syncwarp();                                     // every lane has read the block before lane 0 replaces it
     if (lane == 0) {
         Ri[i - 1] = c2 * nii + s2 * rji;
         Rj[i - 1] = c2 * nij + s2 * njj;
@@ -90,6 +105,79 @@ template <class S> AMRVW_DI void pass_dense(HFact<S>& F, Rot<S>& V, int i, int l
     }
     __syncwarp();
     V = adjoint(make_rot<S>(c2, s2));
+}
+// The two passes of a real double-shift chase position -- V at j = i + 1, then U at i (RDS.jl:42-70) -- in one sweep over R:
+// the column rotations of columns (j, j+1) and (i, j) act on the same rows, the row rotations of rows (j, j+1) and (i, j) on the
+// same columns, so every entry above / right of the 3 x 3 diagonal block is read and written once instead of twice, with half the
+// barriers.  Per entry the operations and their order are those of two pass_dense calls (the strict build stays bit-identical).
+AMRVW_DI void pass_dense2(HFact<double>& F, Rot<double>& V, Rot<double>& U, int i, int lo, int hi) {
+    const int j = i + 1, k = i + 2, lane = F.lane;
+    double* Ci = F.R + (size_t)(i - 1) * F.ld;
+    double* Cj = Ci + F.ld;
+    double* Ck = Cj + F.ld;
+    const double cV = V.c, sV = V.s, cU = U.c, sU = U.s;
+    __syncwarp();
+    // every load of this position is independent of its stores (rows < i, the 3 x 3 block, columns > k are disjoint): the block and
+    // the first slice of both rotations are requested together, so the position pays one round trip to R instead of three
+    const double rii = Ci[i - 1], rij = Cj[i - 1], rik = Ck[i - 1], rjj = Cj[j - 1], rjk = Ck[j - 1], rkk = Ck[k - 1];
+    const int r0 = lo - 1 + lane, m0 = k + 1 + lane;
+    const bool has_r = r0 < i - 1, has_m = m0 <= hi;
+    const int r0s = has_r ? r0 : i - 1;                              // a valid address when this lane has no row
+    double* Cm0 = F.R + (size_t)((has_m ? m0 : k) - 1) * F.ld;
+    const double a0 = Ci[r0s], b0 = Cj[r0s], c0 = Ck[r0s];
+    const double x0 = Cm0[i - 1], y0 = Cm0[j - 1], z0 = Cm0[k - 1];
+    if (has_r) {
+        const double b1 = cV * b0 - sV * c0, c1 = sV * b0 + cV * c0;  // V on columns (j, k)
+        Ci[r0] = cU * a0 - sU * b1;                                    // U on columns (i, j)
+        Cj[r0] = sU * a0 + cU * b1;
+        Ck[r0] = c1;
+    }
+    for (int r = r0 + 32; r < i - 1; r += 32) {
+        const double a = Ci[r], b = Cj[r], c = Ck[r];
+        const double b1 = cV * b - sV * c, c1 = sV * b + cV * c;
+        Ci[r] = cU * a - sU * b1;
+        Cj[r] = sU * a + cU * b1;
+        Ck[r] = c1;
+    }
+    // V at j: row i is an ordinary row of its column rotation, rows j, k its diagonal block
+    const double bi1 = cV * rij - sV * rik, ci1 = sV * rij + cV * rik;
+    const double njj = cV * rjj - sV * rjk, njk = sV * rjj + cV * rjk;
+    const double rkj = cV * 0.0 - sV * rkk, nkk = sV * 0.0 + cV * rkk;
+    double c2V, s2V, tV;
+    givensrot(njj, rkj, c2V, s2V, tV);
+    const double rjj1 = c2V * njj + s2V * rkj;
+    const double rjk1 = c2V * njk + s2V * nkk, rkk1 = -(s2V * njk) + c2V * nkk;
+    // U at i: rows i, j are its diagonal block
+    const double nii = cU * rii - sU * bi1, nij = sU * rii + cU * bi1;
+    const double rji = cU * 0.0 - sU * rjj1, njj2 = sU * 0.0 + cU * rjj1;
+    double c2U, s2U, tU;
+    givensrot(nii, rji, c2U, s2U, tU);
+    if (has_m) {
+        const double y1 = c2V * y0 + s2V * z0;                         // V' on rows (j, k)
+        Cm0[k - 1] = -(s2V * y0) + c2V * z0;
+        Cm0[i - 1] = c2U * x0 + s2U * y1;                              // U' on rows (i, j)
+        Cm0[j - 1] = -(s2U * x0) + c2U * y1;
+    }
+    for (int m = m0 + 32; m <= hi; m += 32) {
+        double* Cm = F.R + (size_t)(m - 1) * F.ld;
+        const double x = Cm[i - 1], y = Cm[j - 1], z = Cm[k - 1];
+        const double y1 = c2V * y + s2V * z;
+        Cm[k - 1] = -(s2V * y) + c2V * z;
+        Cm[i - 1] = c2U * x + s2U * y1;
+        Cm[j - 1] = -(s2U * x) + c2U * y1;
+    }
+    __syncwarp();                                                      // every lane has read the block before lane 0 replaces it
+    if (lane == 0) {
+        Ci[i - 1] = c2U * nii + s2U * rji;
+        Cj[i - 1] = c2U * nij + s2U * njj2;
+        Cj[j - 1] = -(s2U * nij) + c2U * njj2;
+        Ck[i - 1] = c2U * ci1 + s2U * rjk1;
+        Ck[j - 1] = -(s2U * ci1) + c2U * rjk1;
+        Ck[k - 1] = rkk1;
+    }
+    __syncwarp();
+    V = adjoint(make_rot<double>(c2V, s2V));
+    U = adjoint(make_rot<double>(c2U, s2U));
 }
 // diagonal.jl:84-96 on a diagonal shared by the warp; real: no-op
 template <class S> AMRVW_DI void hpass_diag(HFact<S>& F, S* D, Rot<S>& U, int i) {
@@ -182,8 +270,12 @@ AMRVW_NI void bulge_step(HFact<double>& F, Counter& ctr, uint64_t seed, uint64_t
     }
     for (;;) {
         const int j = i + 1;
-        pass_R(F, V, j, lo, hi);      // passthrough_triu (RDS.jl:42-70)
-        pass_R(F, U, i, lo, hi);
+        if (F.unitary) {              // passthrough_triu (RDS.jl:42-70)
+            pass_R(F, V, j, lo, hi);
+            pass_R(F, U, i, lo, hi);
+        } else {
+            pass_dense2(F, V, U, i, lo, hi);
+        }
         if (j < ctr.stop_index) {     // passthrough_Q (RDS.jl:97-131)
             int jv = j, iu = i;
             pass_Qh(F, V, jv);

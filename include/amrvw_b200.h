@@ -102,7 +102,8 @@ int amrvw_create(amrvw_ctx** ctx, int device, uint64_t seed);
  * results straight into the caller's buffers -- one call roots the whole batch, as one
  * `roots.(pss)` comprehension does in the reference (README.md:121, companion.jl:252-272).  No
  * collective: polynomials never interact.  ndev = 0: every visible device.  Results are identical to
- * the single-device call (same kernels, same per-polynomial seeds).  The *_dev entry points and
+ * the single-device call (same kernels) except where an exceptional shift is drawn: its random stream is keyed by the
+ * polynomial's position in the device's slice (create-bulge.jl:28,88 draw from the global RNG).  The *_dev entry points and
  * amrvw_set_stream need a single-device context. */
 int amrvw_create_multi(amrvw_ctx** ctx, const int* devices, int ndev, uint64_t seed);
 int amrvw_device_count(const amrvw_ctx* ctx);
@@ -155,8 +156,8 @@ int amrvw_roots_pencil_c64_dev(amrvw_ctx* ctx, const double* d_vs_reim, const do
  * column major order (Julia's layout; _c64: interleaved re, im); entries below the first subdiagonal are not read.  The
  * eigenvalues of matrix p are written, sorted like LinearAlgebra.sorteig!, to complex slots sum(dims[0..p-1]) onwards of
  * eig_reim; n_unconverged[p] counts the slots the iteration cap left at zero.  Real matrices run the real double shift
- * chase, complex ones the single shift chase, one bulge at a time as the reference does.  A multi-device context runs the
- * call on its first device. */
+ * chase, complex ones the single shift chase, one bulge at a time as the reference does.  A multi-device context splits
+ * the batch contiguously by matrix, balanced by the sum of n^3, and gathers into the caller's buffers like the roots calls. */
 int amrvw_eigvals_hessenberg_f64(amrvw_ctx* ctx, const double* H, const int32_t* dims, int64_t nbatch, int unitary,
                                  double* eig_reim, int32_t* n_unconverged, amrvw_stats* stats);
 int amrvw_eigvals_hessenberg_c64(amrvw_ctx* ctx, const double* H_reim, const int32_t* dims, int64_t nbatch, int unitary,

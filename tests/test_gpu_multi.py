@@ -95,3 +95,28 @@ def test_multi_device_c2_share_e2e(A, oracle):
             assert len(g) == 3000 and np.array_equal(pos, neg)
     finally:
         many.close()
+
+
+@pytest.mark.parametrize("ndev", [2, 4])
+def test_multi_device_hessenberg_split(A, ndev):
+    """amrvw_eigvals_hessenberg_* on a multi-device context: contiguous split by matrix balanced by n^3, eigenvalues land in the
+    caller's buffer at the single-device slots; identical values (no exceptional shift is drawn on these matrices)."""
+    if _ndev() < ndev:
+        pytest.skip(f"needs {ndev} GPUs")
+    rng = np.random.default_rng(11)
+    mats = [np.triu(rng.standard_normal((int(n), int(n))), -1) for n in rng.integers(0, 70, 90)]
+    one = A.Context(device=0, seed=7)
+    many = A.Context(devices=list(range(ndev)), seed=7)
+    try:
+        a, ua = one.eigvals_hessenberg(mats)
+        b, ub = many.eigvals_hessenberg(mats)
+        assert many.last_stats["launches"] == ndev and np.all(ua == 0) and np.all(ub == 0)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+        cm = [m + 1j * np.triu(rng.standard_normal(m.shape), -1) for m in mats[:30]]
+        ca, _ = one.eigvals_hessenberg(cm, unitary=False)
+        cb, _ = many.eigvals_hessenberg(cm, unitary=False)
+        for x, y in zip(ca, cb):
+            assert np.array_equal(x, y)
+    finally:
+        one.close(); many.close()
