@@ -907,6 +907,10 @@ static int run_hessenberg_single(amrvw_ctx* ctx, const S* H, const int32_t* dims
     const bool in_smem = full * 16 <= smem_cap;
     const size_t per_warp = in_smem ? full : lean;
     if (per_warp > smem_cap) return fail(ctx, AMRVW_ERR_ARGUMENT, "matrix too large for the per-warp rotator storage");
+    // small matrices, many of them: one thread per matrix (hess_thread_kernel) when a warp's worth of matrices fits in an SM's
+    // shared memory and the batch fills the device (lanes_per_poly = 32 keeps one warp per matrix: development / comparison)
+    size_t tstride = (full + 15) / 16; if (tstride % 2 == 0) ++tstride; tstride *= 16;      // odd multiple of 16 bytes
+    const bool by_thread = tstride <= 5000 && nbatch >= 64ll * ctx->sm_count && ctx->opt.lanes_per_poly != 32;   // real n <= 22, complex n <= 15 (measured: n = 8 3.5x, 15 2.0x / 1.6x, 24 1.0x)
     int wpc = (int)std::min<size_t>(8, smem_cap / per_warp);
     if ((int64_t)wpc > nbatch) wpc = (int)nbatch;
     // several CTAs per SM when they fit: the chase is latency bound, more warps hide it
@@ -914,6 +918,10 @@ static int run_hessenberg_single(amrvw_ctx* ctx, const S* H, const int32_t* dims
     while (per_sm * wpc > 16) { if (per_sm > 1) --per_sm; else break; }
     int64_t ctas = (nbatch + wpc - 1) / wpc;
     if (ctas > (int64_t)ctx->sm_count * per_sm) ctas = (int64_t)ctx->sm_count * per_sm;
+    if (by_thread) {      // CTAs of one warp, as many per SM as the shared memory holds (at most 8)
+        per_sm = (int)std::min<size_t>(8, smem_cap / (tstride * 32));
+        ctas = std::min<int64_t>((nbatch + 31) / 32, (int64_t)ctx->sm_count * per_sm);
+    }
     const size_t work_stride = ((size_t)nmax * ld * sizeof(S) + 255) & ~(size_t)255;
     int rc;
     if ((rc = reserve(ctx, ctx->coeffs, (size_t)nelem * sizeof(S)))) return rc;
@@ -938,11 +946,18 @@ static int run_hessenberg_single(amrvw_ctx* ctx, const S* H, const int32_t* dims
     a.eig = (cplx*)ctx->roots.ptr; a.nunconv = (int*)ctx->nunconv.ptr; a.stats = (PolyStats*)ctx->stats.ptr;
     a.next = (unsigned int*)ctx->counters.ptr; a.work = in_smem ? nullptr : ctx->hwork.ptr; a.work_stride = work_stride;
     a.nbatch = nbatch; a.unitary = unitary ? 1 : 0; a.ld_max = ld; a.seed = ctx->opt.seed;
-    const size_t smem = per_warp * wpc;
-    auto kern = in_smem ? hess_kernel<S, true> : hess_kernel<S, false>;
-    CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (stats) CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, st));
-    kern<<<(int)ctas, 32 * wpc, smem, st>>>(a, nmax);
+    if (by_thread) {
+        const size_t smem = tstride * 32;
+        CUDA_TRY(ctx, cudaFuncSetAttribute(hess_thread_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (stats) CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, st));
+        hess_thread_kernel<S><<<(int)ctas, 32, smem, st>>>(a, nmax, (unsigned)tstride);
+    } else {
+        const size_t smem = per_warp * wpc;
+        auto kern = in_smem ? hess_kernel<S, true> : hess_kernel<S, false>;
+        CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (stats) CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, st));
+        kern<<<(int)ctas, 32 * wpc, smem, st>>>(a, nmax);
+    }
     CUDA_TRY(ctx, cudaGetLastError());
     if (stats) CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, st));
     CUDA_TRY(ctx, cudaMemcpyAsync(eig, ctx->roots.ptr, (size_t)neig * sizeof(cplx), cudaMemcpyDeviceToHost, st));
@@ -960,7 +975,8 @@ static int run_hessenberg_single(amrvw_ctx* ctx, const S* H, const int32_t* dims
         }
         float ms = 0.f;
         CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-        stats->device_ms = ms; stats->launches = 1; stats->lanes = in_smem ? 1 : 0;   // lanes: 1 = R in shared memory, 0 = R in the global workspace
+        stats->device_ms = ms; stats->launches = 1;
+        stats->lanes = by_thread ? 2 : (in_smem ? 1 : 0);   // 2 = one thread per matrix (shared memory), 1 = one warp per matrix with R in shared memory, 0 = R in the global workspace
         stats->schedule_used = AMRVW_SCHEDULE_REFERENCE;
     }
     return AMRVW_OK;

@@ -17,27 +17,29 @@
 
 namespace amrvw {
 
-template <class S> struct HFact {
+template <class S, int CW> struct HFact {
     Rot<S>* Q;     // descending chain, slots 0..N (1..N-1 live, 0 and N identity sentinels)
     S* DQ;         // complex only: slots 0..N+1
     S* R;          // dense mode: column major, entry (l,k) 1-based at R[(l-1) + (k-1)*ld]
     S* D;          // unitary mode: diagonal of R, slots 1..N
     int ld, N;
     bool unitary;
-    int lane;
+    int lane;      // position in the cooperating group
+    // CW: lanes cooperating on this matrix: 32 (one warp per matrix) or 1 (one thread per matrix, small n)
     long long turnovers;
 };
 
 // lane 0 stores, between two warp barriers: the reads every lane did before the call are complete, the new values are visible after it
-#define HWRITE(F, ...) do { __syncwarp(); if ((F).lane == 0) { __VA_ARGS__; } __syncwarp(); } while (0)
+#define HSYNC(F) do { if constexpr (CW == 32) __syncwarp(); } while (0)
+#define HWRITE(F, ...) do { HSYNC(F); if ((F).lane == 0) { __VA_ARGS__; } HSYNC(F); } while (0)
 
-template <class S> AMRVW_DI S& hr(const HFact<S>& F, int l, int k) { return F.R[(size_t)(k - 1) * F.ld + (l - 1)]; }
-template <class S> AMRVW_DI S hr_entry(const HFact<S>& F, int l, int k) {   // rfactorization.jl:268-274 / diagonal.jl:30-36
+template <class S, int CW> AMRVW_DI S& hr(const HFact<S, CW>& F, int l, int k) { return F.R[(size_t)(k - 1) * F.ld + (l - 1)]; }
+template <class S, int CW> AMRVW_DI S hr_entry(const HFact<S, CW>& F, int l, int k) {   // rfactorization.jl:268-274 / diagonal.jl:30-36
     if (F.unitary) return l == k ? F.D[l] : S(0.0);
     return hr(F, l, k);
 }
 // A = (Q R)[j:j+1, j:j+1]   (diagonal-block.jl:12-36); same closed form for the Q side as solver.cuh: q_block
-template <class S> AMRVW_NI void diagonal_block(const HFact<S>& F, int j, S A[4]) {
+template <class S, int CW> AMRVW_NI void diagonal_block(const HFact<S, CW>& F, int j, S A[4]) {
     const Rot<S> qm = F.Q[j - 1], q0 = F.Q[j], qp = F.Q[j + 1];
     const S dm = dget(F.DQ, j - 1), d0 = dget(F.DQ, j), dp = dget(F.DQ, j + 1);
     const S qji = S(-qm.s) * dm;
@@ -58,12 +60,12 @@ template <class S> AMRVW_NI void diagonal_block(const HFact<S>& F, int j, S A[4]
 // passthrough!(RF::RFactorizationUpperTriangular, V) (rfactorization.jl:317-352): R V = U' R'.  Rows lo..i of the column
 // rotation and columns i+1..hi of the row rotation (the active window) are split over the lanes; the three entries of the
 // 2x2 diagonal block are carried in registers by every lane, so the Givens rotation in the middle needs no exchange.
-template <class S> AMRVW_DI void pass_dense(HFact<S>& F, Rot<S>& V, int i, int lo, int hi) {
+template <class S, int CW> AMRVW_DI void pass_dense(HFact<S, CW>& F, Rot<S>& V, int i, int lo, int hi) {
     const int j = i + 1, lane = F.lane;
     S* Ri = F.R + (size_t)(i - 1) * F.ld;
     S* Rj = Ri + F.ld;
     const S c = V.c; const double sn = V.s;
-    __syncwarp();
+    HSYNC(F);
     // the block and the first slice of both rotations are requested together (their addresses are disjoint from this position's stores)
     const S rii = Ri[i - 1], rij = Rj[i - 1], rjj = Rj[j - 1];
     const int r0 = lo - 1 + lane, m0 = j + 1 + lane;
@@ -76,7 +78,7 @@ template <class S> AMRVW_DI void pass_dense(HFact<S>& F, Rot<S>& V, int i, int l
         Ri[r0] = c * a0 - sn * b0;
         Rj[r0] = sn * a0 + conj_(c) * b0;
     }
-    for (int k = r0 + 32; k < i - 1; k += 32) {
+    for (int k = r0 + CW; k < i - 1; k += CW) {
         const S rki = Ri[k], rkj = Rj[k];
         Ri[k] = c * rki - sn * rkj;
         Rj[k] = sn * rki + conj_(c) * rkj;
@@ -91,32 +93,32 @@ template <class S> AMRVW_DI void pass_dense(HFact<S>& F, Rot<S>& V, int i, int l
         Rm0[i - 1] = c2 * x0 + s2 * y0;
         Rm0[j - 1] = -(s2 * x0) + conj_(c2) * y0;
     }
-    for (int k = m0 + 32; k <= hi; k += 32) {
+    for (int k = m0 + CW; k <= hi; k += CW) {
         S* Rk = F.R + (size_t)(k - 1) * F.ld;
         const S rik = Rk[i - 1], rjk = Rk[j - 1];
         Rk[i - 1] = c2 * rik + s2 * rjk;
         Rk[j - 1] = -(s2 * rik) + conj_(c2) * rjk;
     }
-    __syncwarp();                                     // every lane has read the block before lane 0 replaces it
+    HSYNC(F);                                     // every lane has read the block before lane 0 replaces it
     if (lane == 0) {
         Ri[i - 1] = c2 * nii + s2 * rji;
         Rj[i - 1] = c2 * nij + s2 * njj;
         Rj[j - 1] = -(s2 * nij) + conj_(c2) * njj;
     }
-    __syncwarp();
+    HSYNC(F);
     V = adjoint(make_rot<S>(c2, s2));
 }
 // The two passes of a real double-shift chase position -- V at j = i + 1, then U at i (RDS.jl:42-70) -- in one sweep over R:
 // the column rotations of columns (j, j+1) and (i, j) act on the same rows, the row rotations of rows (j, j+1) and (i, j) on the
 // same columns, so every entry above / right of the 3 x 3 diagonal block is read and written once instead of twice, with half the
 // barriers.  Per entry the operations and their order are those of two pass_dense calls (the strict build stays bit-identical).
-AMRVW_DI void pass_dense2(HFact<double>& F, Rot<double>& V, Rot<double>& U, int i, int lo, int hi) {
+template <int CW> AMRVW_DI void pass_dense2(HFact<double, CW>& F, Rot<double>& V, Rot<double>& U, int i, int lo, int hi) {
     const int j = i + 1, k = i + 2, lane = F.lane;
     double* Ci = F.R + (size_t)(i - 1) * F.ld;
     double* Cj = Ci + F.ld;
     double* Ck = Cj + F.ld;
     const double cV = V.c, sV = V.s, cU = U.c, sU = U.s;
-    __syncwarp();
+    HSYNC(F);
     // every load of this position is independent of its stores (rows < i, the 3 x 3 block, columns > k are disjoint): the block and
     // the first slice of both rotations are requested together, so the position pays one round trip to R instead of three
     const double rii = Ci[i - 1], rij = Cj[i - 1], rik = Ck[i - 1], rjj = Cj[j - 1], rjk = Ck[j - 1], rkk = Ck[k - 1];
@@ -132,7 +134,7 @@ AMRVW_DI void pass_dense2(HFact<double>& F, Rot<double>& V, Rot<double>& U, int 
         Cj[r0] = sU * a0 + cU * b1;
         Ck[r0] = c1;
     }
-    for (int r = r0 + 32; r < i - 1; r += 32) {
+    for (int r = r0 + CW; r < i - 1; r += CW) {
         const double a = Ci[r], b = Cj[r], c = Ck[r];
         const double b1 = cV * b - sV * c, c1 = sV * b + cV * c;
         Ci[r] = cU * a - sU * b1;
@@ -158,7 +160,7 @@ AMRVW_DI void pass_dense2(HFact<double>& F, Rot<double>& V, Rot<double>& U, int 
         Cm0[i - 1] = c2U * x0 + s2U * y1;                              // U' on rows (i, j)
         Cm0[j - 1] = -(s2U * x0) + c2U * y1;
     }
-    for (int m = m0 + 32; m <= hi; m += 32) {
+    for (int m = m0 + CW; m <= hi; m += CW) {
         double* Cm = F.R + (size_t)(m - 1) * F.ld;
         const double x = Cm[i - 1], y = Cm[j - 1], z = Cm[k - 1];
         const double y1 = c2V * y + s2V * z;
@@ -166,7 +168,7 @@ AMRVW_DI void pass_dense2(HFact<double>& F, Rot<double>& V, Rot<double>& U, int 
         Cm[i - 1] = c2U * x + s2U * y1;
         Cm[j - 1] = -(s2U * x) + c2U * y1;
     }
-    __syncwarp();                                                      // every lane has read the block before lane 0 replaces it
+    HSYNC(F);                                                      // every lane has read the block before lane 0 replaces it
     if (lane == 0) {
         Ci[i - 1] = c2U * nii + s2U * rji;
         Cj[i - 1] = c2U * nij + s2U * njj2;
@@ -175,12 +177,12 @@ AMRVW_DI void pass_dense2(HFact<double>& F, Rot<double>& V, Rot<double>& U, int 
         Ck[j - 1] = -(s2U * ci1) + c2U * rjk1;
         Ck[k - 1] = rkk1;
     }
-    __syncwarp();
+    HSYNC(F);
     V = adjoint(make_rot<double>(c2V, s2V));
     U = adjoint(make_rot<double>(c2U, s2U));
 }
 // diagonal.jl:84-96 on a diagonal shared by the warp; real: no-op
-template <class S> AMRVW_DI void hpass_diag(HFact<S>& F, S* D, Rot<S>& U, int i) {
+template <class S, int CW> AMRVW_DI void hpass_diag(HFact<S, CW>& F, S* D, Rot<S>& U, int i) {
     if constexpr (!is_real<S>::value) {
         const S alpha = D[i], beta = D[i + 1];
         HWRITE(F, D[i] = beta; D[i + 1] = alpha);
@@ -188,7 +190,7 @@ template <class S> AMRVW_DI void hpass_diag(HFact<S>& F, S* D, Rot<S>& U, int i)
     }
 }
 // passthrough!(RF, U) for the two R factorizations of qr_factorization
-template <class S> AMRVW_DI void pass_R(HFact<S>& F, Rot<S>& U, int i, int lo, int hi) {
+template <class S, int CW> AMRVW_DI void pass_R(HFact<S, CW>& F, Rot<S>& U, int i, int lo, int hi) {
     if (F.unitary) {   // diagonal.jl:84-96 (complex: the entries swap, the cosine takes the phase), :113-118 (real: the sine takes d_i d_{i+1})
         if constexpr (is_real<S>::value) U.s = U.s * F.D[i] * F.D[i + 1];
         else hpass_diag(F, F.D, U, i);
@@ -196,7 +198,7 @@ template <class S> AMRVW_DI void pass_R(HFact<S>& F, Rot<S>& U, int i, int lo, i
     }
     pass_dense(F, U, i, lo, hi);
 }
-template <class S> AMRVW_DI void pass_Qh(HFact<S>& F, Rot<S>& U, int& i) {   // qfactorization.jl:86-91
+template <class S, int CW> AMRVW_DI void pass_Qh(HFact<S, CW>& F, Rot<S>& U, int& i) {   // qfactorization.jl:86-91
     hpass_diag(F, F.DQ, U, i);
     Rot<S> r1, r2, r3;
     turnover(F.Q[i], F.Q[i + 1], U, r1, r2, r3);   // chains.jl:360
@@ -206,8 +208,8 @@ template <class S> AMRVW_DI void pass_Qh(HFact<S>& F, Rot<S>& U, int& i) {   // 
     i += 1;
 }
 
-AMRVW_NI void push_phase(HFact<cplx>& F, cplx alpha, int i) {   // diagonal.jl:199-225; nothing comes back, lane 0 does it
-    __syncwarp();
+template <int CW> AMRVW_NI void push_phase(HFact<cplx, CW>& F, cplx alpha, int i) {   // diagonal.jl:199-225; nothing comes back, lane 0 does it
+    HSYNC(F);
     if (F.lane == 0) {
         const int M = F.N - 1;
         F.DQ[i] = F.DQ[i] * alpha;
@@ -221,11 +223,11 @@ AMRVW_NI void push_phase(HFact<cplx>& F, cplx alpha, int i) {   // diagonal.jl:1
         }
         F.DQ[i + 1] = F.DQ[i + 1] * ca;
     }
-    __syncwarp();
+    HSYNC(F);
 }
 
 // real double shift (create-bulge.jl:20-77, RDS.jl, bulge-step.jl:36-49) -- solver.cuh: bulge_step without the rank-one shortcut
-AMRVW_NI void bulge_step(HFact<double>& F, Counter& ctr, uint64_t seed, uint64_t mat, int& ord, PolyStats& st) {
+template <int CW> AMRVW_NI void bulge_step(HFact<double, CW>& F, Counter& ctr, uint64_t seed, uint64_t mat, int& ord, PolyStats& st) {
     st.sweeps++;
     Rot<double> U, V, W;
     int i = ctr.start_index;
@@ -301,13 +303,13 @@ AMRVW_NI void bulge_step(HFact<double>& F, Counter& ctr, uint64_t seed, uint64_t
         }
     }
 }
-AMRVW_DI void deflate(HFact<double>& F, int k) {  // RDS.jl:134-141
+template <int CW> AMRVW_DI void deflate(HFact<double, CW>& F, int k) {  // RDS.jl:134-141
     const Rot<double> q = make_rot<double>(sign_(F.Q[k].c), 0.0);
     HWRITE(F, F.Q[k] = q);
 }
 
 // complex single shift (create-bulge.jl:85-110, CSS.jl)
-AMRVW_NI void bulge_step(HFact<cplx>& F, Counter& ctr, uint64_t seed, uint64_t mat, int& ord, PolyStats& st) {
+template <int CW> AMRVW_NI void bulge_step(HFact<cplx, CW>& F, Counter& ctr, uint64_t seed, uint64_t mat, int& ord, PolyStats& st) {
     st.sweeps++;
     cplx A[4];
     cplx shift;
@@ -351,13 +353,13 @@ AMRVW_NI void bulge_step(HFact<cplx>& F, Counter& ctr, uint64_t seed, uint64_t m
         }
     }
 }
-AMRVW_DI void deflate(HFact<cplx>& F, int k) {  // CSS.jl:98-122
+template <int CW> AMRVW_DI void deflate(HFact<cplx, CW>& F, int k) {  // CSS.jl:98-122
     const cplx alpha = F.Q[k].c;
     HWRITE(F, F.Q[k] = make_rot<cplx>(cplx(1.0, 0.0), 0.0));
     push_phase(F, alpha, k);
 }
 
-template <class S> AMRVW_NI void check_deflation(HFact<S>& F, Counter& ctr) {  // AMRVW_algorithm.jl:181-202
+template <class S, int CW> AMRVW_NI void check_deflation(HFact<S, CW>& F, Counter& ctr) {  // AMRVW_algorithm.jl:181-202
     for (int k = ctr.stop_index; k >= ctr.start_index; --k) {
         if (fabs(F.Q[k].s) <= AMRVW_EPS) {
             deflate(F, k);
@@ -370,7 +372,7 @@ template <class S> AMRVW_NI void check_deflation(HFact<S>& F, Counter& ctr) {  /
 }
 
 // AMRVW_algorithm.jl:10-138 -- the driver of solver.cuh: drive_window for lo = 1
-template <class S> AMRVW_DI int drive_hessenberg(HFact<S>& F, cplx* E, uint64_t seed, uint64_t mat, PolyStats& st) {
+template <class S, int CW> AMRVW_DI int drive_hessenberg(HFact<S, CW>& F, cplx* E, uint64_t seed, uint64_t mat, PolyStats& st) {
     const int n = F.N;
     Counter ctr = {0, 1, n - 1, AMRVW_IT_COUNT, -1};
     const long long it_max = AMRVW_IT_MAX(n);
@@ -443,81 +445,106 @@ template <class S> __host__ __device__ inline size_t hess_warp_bytes(int nmax, i
     return (b + 15) & ~(size_t)15;
 }
 
+// qr_factorization + eigvals of matrix p by the group F describes (a warp, or one thread); E, nunconv, stats written by its lane 0
+template <class S, int CW> AMRVW_DI void hess_solve_one(HFact<S, CW>& F, const HessArgs& a, const unsigned int p) {
+    const int lane = F.lane; constexpr int w = CW;
+    const S* Hall = static_cast<const S*>(a.H);
+    const int n = a.dims[p];
+    cplx* E = a.eig + a.eoff[p] - 1;     // 1-based slots
+    PolyStats st = {0, 0, 0, 0, 0};
+    F.N = n; F.unitary = false; F.turnovers = 0;
+    int unconv = 0;
+    if (n == 1) {
+        if (lane == 0) E[1] = to_c(Hall[a.moff[p]]);
+    } else if (n >= 2) {
+        const S* H = Hall + a.moff[p];
+        // load the upper Hessenberg part (column major, coalesced over rows when a warp shares the matrix)
+        for (int k = 1; k <= n; ++k) {
+            const int top = min(n, k + 1);
+            for (int l = 1 + lane; l <= top; l += w) hr(F, l, k) = H[(size_t)(k - 1) * n + (l - 1)];
+        }
+        HSYNC(F);
+        // qr_factorization! (qrfactorization.jl:69-85): Givens on (R[i,i], R[i+1,i]), row rotation of columns i+1..n
+        if (lane == 0) {
+            F.Q[0] = make_rot<S>(S(1.0), 0.0);
+            F.Q[n] = make_rot<S>(S(1.0), 0.0);
+        }
+        if constexpr (!is_real<S>::value) for (int k = lane; k <= n + 1; k += w) F.DQ[k] = cplx(1.0, 0.0);
+        for (int i = 1; i <= n - 1; ++i) {
+            const int j = i + 1;
+            S c, r; double sn;
+            givensrot(hr(F, i, i), hr(F, j, i), c, sn, r);
+            if (lane == 0) F.Q[i] = adjoint(make_rot<S>(c, sn));
+            HSYNC(F);
+            for (int k = j + lane; k <= n; k += w) {
+                const S rik = hr(F, i, k), rjk = hr(F, j, k);
+                hr(F, i, k) = c * rik + sn * rjk;
+                hr(F, j, k) = -(sn * rik) + conj_(c) * rjk;
+            }
+            if (lane == 0) { hr(F, i, i) = r; hr(F, j, i) = S(0.0); }
+            HSYNC(F);
+        }
+        if (a.unitary) {   // R = sign.(diag(R))  (qrfactorization.jl:87-93)
+            for (int k = 1 + lane; k <= n; k += w) {
+                const S z = hr(F, k, k);
+                if constexpr (is_real<S>::value) F.D[k] = sign_(z);
+                else F.D[k] = iszero_(z) ? z : z / abs_(z);
+            }
+            F.unitary = true;
+        }
+        HSYNC(F);
+        if (lane == 0) for (int k = 1; k <= n; ++k) E[k] = cplx(0.0, 0.0);
+        unconv = drive_hessenberg(F, E, a.seed, (uint64_t)p, st);
+        HSYNC(F);
+        if (lane == 0) sort_roots(E + 1, n);
+    }
+    if (lane == 0) {
+        a.nunconv[p] = unconv;
+        if (a.stats) { st.turnovers = F.turnovers; st.unconverged = unconv; a.stats[p] = st; }
+    }
+    HSYNC(F);
+}
+
+template <class S, int CW> AMRVW_DI void hess_place(HFact<S, CW>& F, unsigned char* mine, const int nmax, const int ld) {
+    F.Q = reinterpret_cast<Rot<S>*>(mine);
+    F.DQ = reinterpret_cast<S*>(mine + (size_t)(nmax + 2) * sizeof(Rot<S>));
+    F.D = F.DQ + (nmax + 2);
+    F.R = F.D + (nmax + 2);
+    F.ld = ld;
+}
+
 // One warp per matrix, matrices handed out by an atomic counter.  SMEM: R in shared memory, else in a.work.
 template <class S, bool SMEM>
 __global__ void hess_kernel(HessArgs a, int nmax) {
     extern __shared__ __align__(16) unsigned char hsm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const size_t small = hess_warp_bytes<S>(nmax, a.ld_max, SMEM);
-    unsigned char* mine = hsm + (size_t)warp * small;
-    HFact<S> F;
-    F.Q = reinterpret_cast<Rot<S>*>(mine);
-    F.DQ = reinterpret_cast<S*>(mine + (size_t)(nmax + 2) * sizeof(Rot<S>));
-    F.D = F.DQ + (nmax + 2);
-    F.R = SMEM ? F.D + (nmax + 2)
-               : reinterpret_cast<S*>(static_cast<unsigned char*>(a.work) + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * a.work_stride);
-    F.ld = a.ld_max;
+    HFact<S, 32> F;
+    hess_place(F, hsm + (size_t)warp * hess_warp_bytes<S>(nmax, a.ld_max, SMEM), nmax, a.ld_max);
+    if (!SMEM) F.R = reinterpret_cast<S*>(static_cast<unsigned char*>(a.work) + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * a.work_stride);
     F.lane = lane;
-    const S* Hall = static_cast<const S*>(a.H);
     for (;;) {
         unsigned int p = 0;
         if (lane == 0) p = atomicAdd(a.next, 1u);
         p = __shfl_sync(0xffffffffu, p, 0);
         if ((long long)p >= a.nbatch) break;
-        const int n = a.dims[p];
-        cplx* E = a.eig + a.eoff[p] - 1;     // 1-based slots
-        PolyStats st = {0, 0, 0, 0, 0};
-        F.N = n; F.unitary = false; F.turnovers = 0;
-        int unconv = 0;
-        if (n == 1) {
-            if (lane == 0) E[1] = to_c(Hall[a.moff[p]]);
-        } else if (n >= 2) {
-            const S* H = Hall + a.moff[p];
-            // load the upper Hessenberg part (column major, coalesced over rows)
-            for (int k = 1; k <= n; ++k) {
-                const int top = min(n, k + 1);
-                for (int l = 1 + lane; l <= top; l += 32) hr(F, l, k) = H[(size_t)(k - 1) * n + (l - 1)];
-            }
-            __syncwarp();
-            // qr_factorization! (qrfactorization.jl:69-85): Givens on (R[i,i], R[i+1,i]), row rotation of columns i+1..n
-            if (lane == 0) {
-                F.Q[0] = make_rot<S>(S(1.0), 0.0);
-                F.Q[n] = make_rot<S>(S(1.0), 0.0);
-            }
-            if constexpr (!is_real<S>::value) for (int k = lane; k <= n + 1; k += 32) F.DQ[k] = cplx(1.0, 0.0);
-            for (int i = 1; i <= n - 1; ++i) {
-                const int j = i + 1;
-                S c, r; double sn;
-                givensrot(hr(F, i, i), hr(F, j, i), c, sn, r);
-                if (lane == 0) F.Q[i] = adjoint(make_rot<S>(c, sn));
-                __syncwarp();
-                for (int k = j + lane; k <= n; k += 32) {
-                    const S rik = hr(F, i, k), rjk = hr(F, j, k);
-                    hr(F, i, k) = c * rik + sn * rjk;
-                    hr(F, j, k) = -(sn * rik) + conj_(c) * rjk;
-                }
-                if (lane == 0) { hr(F, i, i) = r; hr(F, j, i) = S(0.0); }
-                __syncwarp();
-            }
-            if (a.unitary) {   // R = sign.(diag(R))  (qrfactorization.jl:87-93)
-                for (int k = 1 + lane; k <= n; k += 32) {
-                    const S z = hr(F, k, k);
-                    if constexpr (is_real<S>::value) F.D[k] = sign_(z);
-                    else F.D[k] = iszero_(z) ? z : z / abs_(z);
-                }
-                F.unitary = true;
-            }
-            __syncwarp();
-            if (lane == 0) for (int k = 1; k <= n; ++k) E[k] = cplx(0.0, 0.0);
-            unconv = drive_hessenberg(F, E, a.seed, (uint64_t)p, st);
-            __syncwarp();
-            if (lane == 0) sort_roots(E + 1, n);
-        }
-        if (lane == 0) {
-            a.nunconv[p] = unconv;
-            if (a.stats) { st.turnovers = F.turnovers; st.unconverged = unconv; a.stats[p] = st; }
-        }
-        __syncwarp();
+        hess_solve_one(F, a, p);
+    }
+}
+
+// One THREAD per matrix for batches of small matrices (n <= 16 or so: the reference's own test size is 15): the warp-per-matrix
+// kernel is bound by the instructions of the scalar part, which one warp issues for one matrix; here a warp issues them for up
+// to 32 matrices (as far as their control flow agrees).  Every thread owns `stride` bytes of shared memory (an odd multiple of
+// 16 bytes: the 32 threads' 16-byte accesses fall into different banks); same code, cooperation width 1.
+template <class S>
+__global__ void hess_thread_kernel(HessArgs a, int nmax, unsigned stride) {
+    extern __shared__ __align__(16) unsigned char hsm[];
+    HFact<S, 1> F;
+    hess_place(F, hsm + (size_t)threadIdx.x * stride, nmax, a.ld_max);
+    F.lane = 0;
+    for (;;) {
+        const unsigned int p = atomicAdd(a.next, 1u);
+        if ((long long)p >= a.nbatch) break;
+        hess_solve_one(F, a, p);
     }
 }
 

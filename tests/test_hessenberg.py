@@ -181,3 +181,40 @@ def test_gpu_hessenberg_large_batch_and_options(A, oracle):
         assert dist(got[k], np.linalg.eigvals(mats[k])) <= SQEPS
     with pytest.raises(ValueError):
         A.qr_factorization(np.zeros((3, 4)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cx", [False, True])
+def test_gpu_hessenberg_thread_per_matrix_kernel(A, ctx_strict, oracle, cx):
+    """Batches of at least 64 x #SM small matrices run one THREAD per matrix (hess_thread_kernel, amrvw_stats.lanes == 2): same
+    code at cooperation width 1, so the strict build is again bit-identical to the oracle for real matrices; ragged sizes 0..15."""
+    rng = np.random.default_rng(900 + cx)
+    dims = rng.integers(0, 16, 12000)
+    dims[:4] = [15, 15, 2, 1]
+    mats = [hess(rng, int(n), cx, "randn") for n in dims]
+    got, nunc = ctx_strict.eigvals_hessenberg(mats)
+    assert ctx_strict.last_stats["lanes"] == 2 and np.all(nunc == 0)
+    for p in list(range(0, 12000, 61)) + [0, 1, 2, 3]:
+        n = int(dims[p])
+        assert len(got[p]) == n
+        if n == 0:
+            continue
+        want, ost = oracle.eigvals_hessenberg(mats[p], index=p)
+        if cx or ost["exceptional"]:      # an exceptional shift goes through sincos, whose last bits differ between CUDA and glibc
+            assert dist(got[p], want) <= 1e-12 * n * max(1.0, np.abs(want).max())
+        else:
+            assert np.array_equal(got[p].real, want.real) and np.array_equal(got[p].imag, want.imag), f"matrix {p}, n = {n}"
+    # unitary mode on the same kernel
+    um = [unitary_hess(rng, 8 + (p % 8), cx) for p in range(10000)]
+    ug, nunc = ctx_strict.eigvals_hessenberg(um, unitary=True)
+    assert ctx_strict.last_stats["lanes"] == 2
+    # the reference algorithm itself stagnates on a few random orthogonal matrices in 10000 (all eigenvalues on the unit circle; the
+    # oracle leaves the same matrices unconverged after 20 n trips, in either R mode): the kernel must agree on which
+    bad = np.nonzero(nunc)[0]
+    assert len(bad) <= 10
+    for p in bad:
+        _, ost = oracle.eigvals_hessenberg(um[p], unitary=True, index=int(p))
+        assert ost["unconverged"] > 0
+    for p in range(0, 10000, 173):
+        if nunc[p] == 0:
+            assert dist(ug[p], np.linalg.eigvals(um[p])) <= SQEPS

@@ -20,7 +20,8 @@ def main():
     rows = []
     from importlib import import_module
     pack = import_module("amrvw_jl_b200.roots").pack_matrices
-    cases = ((15, 20000, False), (15, 20000, True), (32, 8000, False), (64, 4000, False), (64, 2000, True), (96, 2368, False), (128, 2368, False), (100, 1184, True), (256, 1184, False))
+    warp_ctx = A.Context(seed=0, lanes_per_poly=32)        # keeps one warp per matrix for small matrices too (comparison)
+    cases = ((8, 40000, False), (15, 20000, False), (15, 20000, True), (24, 12000, False), (32, 8000, False), (64, 4000, False), (64, 2000, True), (96, 2368, False), (128, 2368, False), (100, 1184, True), (256, 1184, False))
     for n, B, cx in cases:
         mats = [np.triu(rng.standard_normal((n, n)) + (1j * rng.standard_normal((n, n)) if cx else 0.0), -1) for _ in range(B)]
         flat, dims = pack(mats)
@@ -34,6 +35,11 @@ def main():
                 best = dt; dev = ctx.last_stats["device_ms"]
         got = [out[eoff[p]:eoff[p + 1]] for p in range(4)]
         st = ctx.last_stats
+        warp_ms = None
+        if st["lanes"] == 2:
+            warp_ctx.eigvals_hessenberg_packed(flat, dims)
+            warp_ctx.eigvals_hessenberg_packed(flat, dims)
+            warp_ms = warp_ctx.last_stats["device_ms"]
         ns = max(2, min(B, int(2e6 / n ** 3) + 2))
         t0 = time.perf_counter()
         for M in mats[:ns]:
@@ -45,7 +51,7 @@ def main():
         t_lap = (time.perf_counter() - t0) / ns
         err = max(float(np.abs(np.sort_complex(g) - np.sort_complex(np.linalg.eigvals(M))).max()) for g, M in zip(got[:4], mats[:4]))
         row = {"n": n, "batch": B, "complex": cx, "gpu_call_ms": best * 1e3, "gpu_kernel_ms": dev, "matrices_per_s_e2e": B / best,
-               "matrices_per_s_kernel": B / (dev * 1e-3), "r_in_shared_memory": bool(st["lanes"]), "sweeps": st["sweeps"], "unconverged": int(nunc.sum()),
+               "matrices_per_s_kernel": B / (dev * 1e-3), "r_in_shared_memory": bool(st["lanes"]), "thread_per_matrix": st["lanes"] == 2, "warp_per_matrix_kernel_ms": warp_ms, "sweeps": st["sweeps"], "unconverged": int(nunc.sum()),
                "oracle_one_core_matrices_per_s": 1.0 / t_orc, "lapack_one_core_matrices_per_s": 1.0 / t_lap, "max_abs_diff_vs_lapack_first4": err}
         print(json.dumps(row), flush=True)
         rows.append(row)
