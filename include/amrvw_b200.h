@@ -157,7 +157,10 @@ int amrvw_roots_pencil_c64_dev(amrvw_ctx* ctx, const double* d_vs_reim, const do
  * eigenvalues of matrix p are written, sorted like LinearAlgebra.sorteig!, to complex slots sum(dims[0..p-1]) onwards of
  * eig_reim; n_unconverged[p] counts the slots the iteration cap left at zero.  Real matrices run the real double shift
  * chase, complex ones the single shift chase, one bulge at a time as the reference does.  A multi-device context splits
- * the batch contiguously by matrix, balanced by the sum of n^3, and gathers into the caller's buffers like the roots calls. */
+ * the batch contiguously by matrix, balanced by the sum of n^3, and gathers into the caller's buffers like the roots calls.
+ * Limits: the rotators of a matrix live in shared memory, so n <= 7030 (Float64) / 3510 (ComplexF64) -- larger matrices
+ * return AMRVW_ERR_ARGUMENT; amrvw_stats.lanes reports the kernel that ran (2: one thread per matrix, 1: one warp per matrix
+ * with R in shared memory, 0: one warp per matrix with R in a global workspace); it_count, it_max_factor and tol apply. */
 int amrvw_eigvals_hessenberg_f64(amrvw_ctx* ctx, const double* H, const int32_t* dims, int64_t nbatch, int unitary,
                                  double* eig_reim, int32_t* n_unconverged, amrvw_stats* stats);
 int amrvw_eigvals_hessenberg_c64(amrvw_ctx* ctx, const double* H_reim, const int32_t* dims, int64_t nbatch, int unitary,
