@@ -911,11 +911,12 @@ static int run_hessenberg_single(amrvw_ctx* ctx, const S* H, const int32_t* dims
     // shared memory and the batch fills the device (lanes_per_poly = 32 keeps one warp per matrix: development / comparison)
     size_t tstride = (full + 15) / 16; if (tstride % 2 == 0) ++tstride; tstride *= 16;      // odd multiple of 16 bytes
     const bool by_thread = tstride <= 5000 && nbatch >= 64ll * ctx->sm_count && ctx->opt.lanes_per_poly != 32;   // real n <= 22, complex n <= 15 (measured: n = 8 3.5x, 15 2.0x / 1.6x, 24 1.0x)
-    int wpc = (int)std::min<size_t>(8, smem_cap / per_warp);
+    // resident warps per SM: as many as the shared memory holds, at most 16 (20 were tried: nothing at n = 64..128, -12 % at n = 256
+    // where the workspace outgrows the L2 faster), in CTAs of four (n = 24, 32: +8-10 % over CTAs of eight)
+    const int fit = (int)std::min<size_t>(16, smem_cap / per_warp);
+    int wpc = std::min(4, fit);
     if ((int64_t)wpc > nbatch) wpc = (int)nbatch;
-    // several CTAs per SM when they fit: the chase is latency bound, more warps hide it
-    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, smem_cap / (per_warp * wpc)));
-    while (per_sm * wpc > 16) { if (per_sm > 1) --per_sm; else break; }
+    int per_sm = std::max(1, fit / wpc);
     int64_t ctas = (nbatch + wpc - 1) / wpc;
     if (ctas > (int64_t)ctx->sm_count * per_sm) ctas = (int64_t)ctx->sm_count * per_sm;
     if (by_thread) {      // CTAs of one warp, as many per SM as the shared memory holds (at most 8)

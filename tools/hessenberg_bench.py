@@ -1,6 +1,6 @@
 """Timing of the Hessenberg eigenvalue entry on the GPU box: matrices per second through the C ABI with HOST
 buffers (H2D/D2H inside), the kernel's device time, and beside it the oracle (one core) and LAPACK (numpy) on a sample.
-Usage: python tools/hessenberg_bench.py [out.json]"""
+Usage: python tools/hessenberg_bench.py [out.json] [--cases n:batch:complex,...]   (e.g. --cases 128:2368:0 for a profiler run)"""
 import json
 import os
 import sys
@@ -14,7 +14,13 @@ from oracle import oracle as orc   # noqa: E402  (CPU baseline only)
 
 
 def main():
-    out_path = sys.argv[1] if len(sys.argv) > 1 else None
+    argv = sys.argv[1:]
+    only = None
+    if "--cases" in argv:
+        k = argv.index("--cases")
+        only = tuple((int(a), int(b), bool(int(c))) for a, b, c in (x.split(":") for x in argv[k + 1].split(",")))
+        del argv[k:k + 2]
+    out_path = argv[0] if argv else None
     ctx = A.Context(seed=0)
     rng = np.random.default_rng(3)
     rows = []
@@ -22,7 +28,7 @@ def main():
     pack = import_module("amrvw_jl_b200.roots").pack_matrices
     warp_ctx = A.Context(seed=0, lanes_per_poly=32)        # keeps one warp per matrix for small matrices too (comparison)
     cases = ((8, 40000, False), (15, 20000, False), (15, 20000, True), (24, 12000, False), (32, 8000, False), (64, 4000, False), (64, 2000, True), (96, 2368, False), (128, 2368, False), (100, 1184, True), (256, 1184, False))
-    for n, B, cx in cases:
+    for n, B, cx in (only or cases):
         mats = [np.triu(rng.standard_normal((n, n)) + (1j * rng.standard_normal((n, n)) if cx else 0.0), -1) for _ in range(B)]
         flat, dims = pack(mats)
         ctx.eigvals_hessenberg(mats[:64])
