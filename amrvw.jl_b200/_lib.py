@@ -49,6 +49,8 @@ _SIGS = {
     "amrvw_count_real_roots_rds_f64": (ctypes.c_int, [_P, _P, _P, _I64, _P, _P, ctypes.POINTER(Stats)]),
     "amrvw_eigvals_hessenberg_f64": (ctypes.c_int, [_P, _P, _P, _I64, ctypes.c_int, _P, _P, ctypes.POINTER(Stats)]),
     "amrvw_eigvals_hessenberg_c64": (ctypes.c_int, [_P, _P, _P, _I64, ctypes.c_int, _P, _P, ctypes.POINTER(Stats)]),
+    "amrvw_eigvals_hessenberg_f64_dev": (ctypes.c_int, [_P, _P, _P, _P, _P, _I64, ctypes.c_int32, ctypes.c_int, _P, _P, ctypes.POINTER(Stats)]),
+    "amrvw_eigvals_hessenberg_c64_dev": (ctypes.c_int, [_P, _P, _P, _P, _P, _I64, ctypes.c_int32, ctypes.c_int, _P, _P, ctypes.POINTER(Stats)]),
     "amrvw_roots_rds_f64_dev": (ctypes.c_int, [_P, _P, _P, _I64, _I64, _I64, _P, _P, _P, ctypes.POINTER(Stats)]),
     "amrvw_roots_css_c64_dev": (ctypes.c_int, [_P, _P, _P, _I64, _I64, _I64, _P, _P, _P, ctypes.POINTER(Stats)]),
     "amrvw_roots_pencil_f64_dev": (ctypes.c_int, [_P, _P, _P, _P, _I64, _I64, _I64, _P, _P, _P, ctypes.POINTER(Stats)]),

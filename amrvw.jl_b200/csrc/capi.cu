@@ -880,21 +880,13 @@ static int run_hessenberg(amrvw_ctx* ctx, const S* H, const int32_t* dims, int64
     return AMRVW_OK;
 }
 
+// The launch itself, device pointers in and out, asynchronous on the context's stream unless stats are asked for.
+// d_moff / d_eoff: element offset of matrix p in d_H and eigenvalue slot offset (nbatch + 1 each); nmax: largest dimension.
 template <class S>
-static int run_hessenberg_single(amrvw_ctx* ctx, const S* H, const int32_t* dims, int64_t nbatch, int unitary, double* eig, int32_t* nunconv, amrvw_stats* stats) {
+static int run_hessenberg_dev(amrvw_ctx* ctx, const S* d_H, const int32_t* d_dims, const int64_t* d_moff, const int64_t* d_eoff, int64_t nbatch, int nmax, int unitary,
+                              double* d_eig, int32_t* d_nunconv, amrvw_stats* stats) {
     if (stats) std::memset(stats, 0, sizeof(*stats));
-    std::vector<long long> meta(2 * (size_t)(nbatch + 1));
-    long long* moff = meta.data(); long long* eoff = moff + nbatch + 1;
-    int nmax = 1;
-    moff[0] = 0; eoff[0] = 0;
-    for (int64_t p = 0; p < nbatch; ++p) {
-        const long long n = dims[p];
-        if (n < 0 || n > 32768) return fail(ctx, AMRVW_ERR_ARGUMENT, "matrix dimension out of range (0..32768)");
-        moff[p + 1] = moff[p] + n * n; eoff[p + 1] = eoff[p] + n;
-        if (n > nmax) nmax = (int)n;
-    }
-    const long long nelem = moff[nbatch], neig = eoff[nbatch];
-    if (neig == 0) { std::fill(nunconv, nunconv + nbatch, 0); return AMRVW_OK; }
+    if (nmax < 1) nmax = 1;
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     (void)cudaGetLastError();
     cudaStream_t st = ctx->stream;
@@ -911,10 +903,11 @@ static int run_hessenberg_single(amrvw_ctx* ctx, const S* H, const int32_t* dims
     // shared memory and the batch fills the device (lanes_per_poly = 32 keeps one warp per matrix: development / comparison)
     size_t tstride = (full + 15) / 16; if (tstride % 2 == 0) ++tstride; tstride *= 16;      // odd multiple of 16 bytes
     const bool by_thread = tstride <= 5000 && nbatch >= 64ll * ctx->sm_count && ctx->opt.lanes_per_poly != 32;   // real n <= 22, complex n <= 15 (measured: n = 8 3.5x, 15 2.0x / 1.6x, 24 1.0x)
-    // resident warps per SM: as many as the shared memory holds, at most 16 (20 were tried: nothing at n = 64..128, -12 % at n = 256
-    // where the workspace outgrows the L2 faster), in CTAs of four (n = 24, 32: +8-10 % over CTAs of eight)
-    const int fit = (int)std::min<size_t>(16, smem_cap / per_warp);
-    int wpc = std::min(4, fit);
+    // resident warps per SM (measured, tools/hessenberg_bench.py): R in shared memory: up to 20 (96 registers per thread) in CTAs of
+    // four (n = 24, 32: +8-10 % over 16 in CTAs of eight); R in the global workspace: 16 in CTAs of eight (20 gain nothing at n = 64..128;
+    // CTAs of four lose 12 % at n = 256)
+    const int fit = (int)std::min<size_t>(in_smem ? 20 : 16, smem_cap / per_warp);
+    int wpc = std::min(in_smem ? 4 : 8, fit);
     if ((int64_t)wpc > nbatch) wpc = (int)nbatch;
     int per_sm = std::max(1, fit / wpc);
     int64_t ctas = (nbatch + wpc - 1) / wpc;
@@ -925,61 +918,84 @@ static int run_hessenberg_single(amrvw_ctx* ctx, const S* H, const int32_t* dims
     }
     const size_t work_stride = ((size_t)nmax * ld * sizeof(S) + 255) & ~(size_t)255;
     int rc;
-    if ((rc = reserve(ctx, ctx->coeffs, (size_t)nelem * sizeof(S)))) return rc;
-    if ((rc = reserve(ctx, ctx->hmeta, meta.size() * sizeof(long long) + (size_t)nbatch * sizeof(int)))) return rc;
-    if ((rc = reserve(ctx, ctx->roots, (size_t)neig * sizeof(cplx)))) return rc;
-    if ((rc = reserve(ctx, ctx->nunconv, (size_t)nbatch * sizeof(int)))) return rc;
     if ((rc = reserve(ctx, ctx->stats, (size_t)nbatch * sizeof(PolyStats) + sizeof(StatsAccum)))) return rc;
     if ((rc = reserve(ctx, ctx->counters, 64 * sizeof(unsigned int)))) return rc;
-    if (!in_smem && (rc = reserve(ctx, ctx->hwork, work_stride * (size_t)ctas * wpc))) return rc;
-    long long* d_meta = (long long*)ctx->hmeta.ptr;
-    int* d_dims = (int*)(d_meta + meta.size());
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->coeffs.ptr, H, (size_t)nelem * sizeof(S), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_meta, meta.data(), meta.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
-    CUDA_TRY(ctx, cudaMemcpyAsync(d_dims, dims, (size_t)nbatch * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (!in_smem && !by_thread && (rc = reserve(ctx, ctx->hwork, work_stride * (size_t)ctas * wpc))) return rc;
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->counters.ptr, 0, sizeof(unsigned int), st));
     {
         const AlgoConst ac = {ctx->opt.tol, ctx->opt.it_count, ctx->opt.it_max_factor};
         CUDA_TRY(ctx, cudaMemcpyToSymbolAsync(g_algo, &ac, sizeof(ac), 0, cudaMemcpyHostToDevice, st));
     }
     HessArgs a;
-    a.H = ctx->coeffs.ptr; a.dims = d_dims; a.moff = d_meta; a.eoff = d_meta + nbatch + 1;
-    a.eig = (cplx*)ctx->roots.ptr; a.nunconv = (int*)ctx->nunconv.ptr; a.stats = (PolyStats*)ctx->stats.ptr;
-    a.next = (unsigned int*)ctx->counters.ptr; a.work = in_smem ? nullptr : ctx->hwork.ptr; a.work_stride = work_stride;
+    a.H = d_H; a.dims = d_dims; a.moff = (const long long*)d_moff; a.eoff = (const long long*)d_eoff;
+    a.eig = (cplx*)d_eig; a.nunconv = d_nunconv; a.stats = (PolyStats*)ctx->stats.ptr;
+    a.next = (unsigned int*)ctx->counters.ptr; a.work = (in_smem || by_thread) ? nullptr : ctx->hwork.ptr; a.work_stride = work_stride;
     a.nbatch = nbatch; a.unitary = unitary ? 1 : 0; a.ld_max = ld; a.seed = ctx->opt.seed;
+    if (stats) CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, st));
     if (by_thread) {
         const size_t smem = tstride * 32;
         CUDA_TRY(ctx, cudaFuncSetAttribute(hess_thread_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        if (stats) CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, st));
         hess_thread_kernel<S><<<(int)ctas, 32, smem, st>>>(a, nmax, (unsigned)tstride);
     } else {
         const size_t smem = per_warp * wpc;
         auto kern = in_smem ? hess_kernel<S, true> : hess_kernel<S, false>;
         CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        if (stats) CUDA_TRY(ctx, cudaEventRecord(ctx->ev0, st));
         kern<<<(int)ctas, 32 * wpc, smem, st>>>(a, nmax);
     }
     CUDA_TRY(ctx, cudaGetLastError());
-    if (stats) CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, st));
-    CUDA_TRY(ctx, cudaMemcpyAsync(eig, ctx->roots.ptr, (size_t)neig * sizeof(cplx), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(ctx, cudaMemcpyAsync(nunconv, ctx->nunconv.ptr, (size_t)nbatch * sizeof(int), cudaMemcpyDeviceToHost, st));
-    std::vector<PolyStats> ps;
-    if (stats) {
-        ps.resize((size_t)nbatch);
-        CUDA_TRY(ctx, cudaMemcpyAsync(ps.data(), ctx->stats.ptr, (size_t)nbatch * sizeof(PolyStats), cudaMemcpyDeviceToHost, st));
-    }
-    CUDA_TRY(ctx, cudaStreamSynchronize(st));
     ctx->prof_valid = false;
     if (stats) {
-        for (const PolyStats& q : ps) {
-            stats->turnovers += q.turnovers; stats->sweeps += q.sweeps; stats->exceptional += q.exceptional; stats->unconverged += q.unconverged;
-        }
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev1, st));
+        StatsAccum* acc = (StatsAccum*)((char*)ctx->stats.ptr + (size_t)nbatch * sizeof(PolyStats));
+        CUDA_TRY(ctx, cudaMemsetAsync(acc, 0, sizeof(StatsAccum), st));
+        reduce_stats_kernel<<<64, 256, 0, st>>>((const PolyStats*)ctx->stats.ptr, nbatch, acc);
+        CUDA_TRY(ctx, cudaGetLastError());
+        StatsAccum h;
+        CUDA_TRY(ctx, cudaMemcpyAsync(&h, acc, sizeof(h), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
         float ms = 0.f;
         CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        stats->turnovers = h.turnovers; stats->sweeps = h.sweeps; stats->exceptional = h.exceptional; stats->unconverged = h.unconverged;
         stats->device_ms = ms; stats->launches = 1;
         stats->lanes = by_thread ? 2 : (in_smem ? 1 : 0);   // 2 = one thread per matrix (shared memory), 1 = one warp per matrix with R in shared memory, 0 = R in the global workspace
         stats->schedule_used = AMRVW_SCHEDULE_REFERENCE;
     }
+    return AMRVW_OK;
+}
+
+// One device, host buffers: H2D, the launch, D2H; returns when the results are in the caller's buffers.
+template <class S>
+static int run_hessenberg_single(amrvw_ctx* ctx, const S* H, const int32_t* dims, int64_t nbatch, int unitary, double* eig, int32_t* nunconv, amrvw_stats* stats) {
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    std::vector<long long> meta(2 * (size_t)(nbatch + 1));
+    long long* moff = meta.data(); long long* eoff = moff + nbatch + 1;
+    int nmax = 1;
+    moff[0] = 0; eoff[0] = 0;
+    for (int64_t p = 0; p < nbatch; ++p) {
+        const long long n = dims[p];
+        if (n < 0 || n > 32768) return fail(ctx, AMRVW_ERR_ARGUMENT, "matrix dimension out of range (0..32768)");
+        moff[p + 1] = moff[p] + n * n; eoff[p + 1] = eoff[p] + n;
+        if (n > nmax) nmax = (int)n;
+    }
+    const long long nelem = moff[nbatch], neig = eoff[nbatch];
+    if (neig == 0) { std::fill(nunconv, nunconv + nbatch, 0); return AMRVW_OK; }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int rc;
+    if ((rc = reserve(ctx, ctx->coeffs, (size_t)nelem * sizeof(S)))) return rc;
+    if ((rc = reserve(ctx, ctx->hmeta, meta.size() * sizeof(long long) + (size_t)nbatch * sizeof(int)))) return rc;
+    if ((rc = reserve(ctx, ctx->roots, (size_t)neig * sizeof(cplx)))) return rc;
+    if ((rc = reserve(ctx, ctx->nunconv, (size_t)nbatch * sizeof(int)))) return rc;
+    long long* d_meta = (long long*)ctx->hmeta.ptr;
+    int* d_dims = (int*)(d_meta + meta.size());
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->coeffs.ptr, H, (size_t)nelem * sizeof(S), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_meta, meta.data(), meta.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(d_dims, dims, (size_t)nbatch * sizeof(int), cudaMemcpyHostToDevice, st));
+    if ((rc = run_hessenberg_dev<S>(ctx, (const S*)ctx->coeffs.ptr, d_dims, (const int64_t*)d_meta, (const int64_t*)(d_meta + nbatch + 1), nbatch, nmax, unitary,
+                                    (double*)ctx->roots.ptr, (int32_t*)ctx->nunconv.ptr, stats))) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(eig, ctx->roots.ptr, (size_t)neig * sizeof(cplx), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(nunconv, ctx->nunconv.ptr, (size_t)nbatch * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
     return AMRVW_OK;
 }
 
@@ -989,5 +1005,24 @@ int amrvw_eigvals_hessenberg_f64(amrvw_ctx* ctx, const double* H, const int32_t*
 }
 int amrvw_eigvals_hessenberg_c64(amrvw_ctx* ctx, const double* H, const int32_t* dims, int64_t nbatch, int unitary, double* eig, int32_t* nunconv, amrvw_stats* stats) {
     return run_hessenberg<cplx>(ctx, (const cplx*)H, dims, nbatch, unitary, eig, nunconv, stats);
+}
+static int hess_dev_args(amrvw_ctx*& ctx, const void* H, const void* dims, const void* moff, const void* eoff, int64_t nbatch, int32_t max_dim, const void* eig, const void* nunconv) {
+    if (!ctx) return AMRVW_ERR_ARGUMENT;
+    if (!ctx->subs.empty()) return fail(ctx, AMRVW_ERR_ARGUMENT, "device-pointer entry points need a single-device context");
+    if (nbatch < 0 || max_dim < 0 || max_dim > 32768) return fail(ctx, AMRVW_ERR_ARGUMENT, "batch size or largest dimension out of range");
+    if (nbatch > 0 && (!H || !dims || !moff || !eoff || !eig || !nunconv)) return fail(ctx, AMRVW_ERR_ARGUMENT, "null buffer");
+    return AMRVW_OK;
+}
+int amrvw_eigvals_hessenberg_f64_dev(amrvw_ctx* ctx, const double* d_H, const int32_t* d_dims, const int64_t* d_moff, const int64_t* d_eoff, int64_t nbatch, int32_t max_dim,
+                                     int unitary, double* d_eig, int32_t* d_nunconv, amrvw_stats* stats) {
+    const int rc = hess_dev_args(ctx, d_H, d_dims, d_moff, d_eoff, nbatch, max_dim, d_eig, d_nunconv);
+    if (rc || nbatch == 0) { if (!rc && stats) std::memset(stats, 0, sizeof(*stats)); return rc; }
+    return run_hessenberg_dev<double>(ctx, d_H, d_dims, d_moff, d_eoff, nbatch, max_dim, unitary, d_eig, d_nunconv, stats);
+}
+int amrvw_eigvals_hessenberg_c64_dev(amrvw_ctx* ctx, const double* d_H, const int32_t* d_dims, const int64_t* d_moff, const int64_t* d_eoff, int64_t nbatch, int32_t max_dim,
+                                     int unitary, double* d_eig, int32_t* d_nunconv, amrvw_stats* stats) {
+    const int rc = hess_dev_args(ctx, d_H, d_dims, d_moff, d_eoff, nbatch, max_dim, d_eig, d_nunconv);
+    if (rc || nbatch == 0) { if (!rc && stats) std::memset(stats, 0, sizeof(*stats)); return rc; }
+    return run_hessenberg_dev<cplx>(ctx, (const cplx*)d_H, d_dims, d_moff, d_eoff, nbatch, max_dim, unitary, d_eig, d_nunconv, stats);
 }
 }

@@ -183,6 +183,13 @@ class Context:
         self.last_stats = st.as_dict() if want_stats else None
         return out, eoff, nunc[:B]
 
+    def eigvals_hessenberg_dev(self, complex_, d_H, d_dims, d_moff, d_eoff, B, max_dim, d_eig, d_nunconv, unitary=False, want_stats=False):
+        """Device pointers (ints) in and out, asynchronous on the context's stream unless want_stats."""
+        st = Stats()
+        fn = self._lib.amrvw_eigvals_hessenberg_c64_dev if complex_ else self._lib.amrvw_eigvals_hessenberg_f64_dev
+        self._check(fn(self._h, d_H, d_dims, d_moff, d_eoff, B, int(max_dim), int(bool(unitary)), d_eig, d_nunconv, ctypes.byref(st) if want_stats else None))
+        self.last_stats = st.as_dict() if want_stats else None
+
     # -- device pointers (ints) in/out: used by bench.py with torch-owned HBM buffers
     def roots_dev(self, kind, d_coeffs, d_offsets, B, total, max_len, d_roots, d_nroots, d_nunconv, d_ws=None, want_stats=False):
         st = Stats()

@@ -165,6 +165,14 @@ int amrvw_eigvals_hessenberg_f64(amrvw_ctx* ctx, const double* H, const int32_t*
                                  double* eig_reim, int32_t* n_unconverged, amrvw_stats* stats);
 int amrvw_eigvals_hessenberg_c64(amrvw_ctx* ctx, const double* H_reim, const int32_t* dims, int64_t nbatch, int unitary,
                                  double* eig_reim, int32_t* n_unconverged, amrvw_stats* stats);
+/* The same with DEVICE pointers, asynchronous on the context's stream (stats != NULL synchronizes); single-device contexts.
+ * d_moff[p] / d_eoff[p]: element offset of matrix p in d_H and complex slot offset of its eigenvalues (nbatch + 1 entries
+ * each, the running sums of dims^2 and dims); max_dim: the largest dims[p].  A slot of an eigenvalue the iteration cap
+ * left unconverged holds zero. */
+int amrvw_eigvals_hessenberg_f64_dev(amrvw_ctx* ctx, const double* d_H, const int32_t* d_dims, const int64_t* d_moff, const int64_t* d_eoff,
+                                     int64_t nbatch, int32_t max_dim, int unitary, double* d_eig_reim, int32_t* d_n_unconverged, amrvw_stats* stats);
+int amrvw_eigvals_hessenberg_c64_dev(amrvw_ctx* ctx, const double* d_H_reim, const int32_t* d_dims, const int64_t* d_moff, const int64_t* d_eoff,
+                                     int64_t nbatch, int32_t max_dim, int unitary, double* d_eig_reim, int32_t* d_n_unconverged, amrvw_stats* stats);
 
 /* real_polynomial_roots (src/complex_conjugate_root_theorem.jl:32-54) for a batch, HOST buffers: roots the
  * polynomials like amrvw_roots_rds_f64 and returns only, per polynomial, the number of roots with imag == 0

@@ -184,6 +184,33 @@ def test_gpu_hessenberg_large_batch_and_options(A, oracle):
 
 
 @pytest.mark.gpu
+def test_gpu_hessenberg_edge_cases(A, ctx):
+    """Empty batch, a matrix beyond the documented size limit (argument error, nothing launched), and non-finite entries (the trip
+    cap ends the iteration: slots reported unconverged, no hang)."""
+    got, nunc = ctx.eigvals_hessenberg([])
+    assert got == [] and len(nunc) == 0
+    with pytest.raises(A.AmrvwError):
+        ctx.eigvals_hessenberg_packed(np.zeros(8000 * 8000), np.array([8000], dtype=np.int32))
+    rng = np.random.default_rng(4)
+    G = hess(rng, 6, False, "randn")
+    M = G.copy()
+    M[2, 3] = np.nan
+    got, nunc = ctx.eigvals_hessenberg([M, G])
+    assert nunc[0] > 0 and nunc[1] == 0
+    assert dist(got[1], np.linalg.eigvals(G)) <= SQEPS
+    # the iteration cap as an option: it_max_factor = 1 leaves most of a 40 x 40 matrix unconverged, the default does not
+    rng = np.random.default_rng(5)
+    H = hess(rng, 40, False, "randn")
+    c = A.Context(seed=0, it_max_factor=1)
+    try:
+        _, few = c.eigvals_hessenberg([H])
+    finally:
+        c.close()
+    _, full = ctx.eigvals_hessenberg([H])
+    assert few[0] > 0 and full[0] == 0
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("cx", [False, True])
 def test_gpu_hessenberg_thread_per_matrix_kernel(A, ctx_strict, oracle, cx):
     """Batches of at least 64 x #SM small matrices run one THREAD per matrix (hess_thread_kernel, amrvw_stats.lanes == 2): same
@@ -218,3 +245,35 @@ def test_gpu_hessenberg_thread_per_matrix_kernel(A, ctx_strict, oracle, cx):
     for p in range(0, 10000, 173):
         if nunc[p] == 0:
             assert dist(ug[p], np.linalg.eigvals(um[p])) <= SQEPS
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cx", [False, True])
+def test_gpu_hessenberg_device_pointers(A, ctx, cx):
+    """amrvw_eigvals_hessenberg_*_dev: matrices, offsets and results stay in HBM (torch owns the buffers), the launch runs on
+    torch's current stream; same eigenvalues as the host-buffer call."""
+    import torch
+    from importlib import import_module
+    pack = import_module("amrvw_jl_b200.roots").pack_matrices
+    rng = np.random.default_rng(21 + cx)
+    mats = [hess(rng, int(n), cx, "randn") for n in rng.integers(1, 50, 64)]
+    want, _ = ctx.eigvals_hessenberg(mats)
+    flat, dims = pack(mats)
+    d64 = dims.astype(np.int64)
+    moff = np.concatenate([[0], np.cumsum(d64 * d64)]); eoff = np.concatenate([[0], np.cumsum(d64)])
+    host = torch.from_numpy(np.ascontiguousarray(flat).view(np.float64)) if cx else torch.from_numpy(flat)
+    d_H = host.cuda(); d_dims = torch.from_numpy(dims).cuda()
+    d_moff = torch.from_numpy(moff).cuda(); d_eoff = torch.from_numpy(eoff).cuda()
+    d_eig = torch.zeros(2 * int(eoff[-1]) + 2, dtype=torch.float64, device="cuda"); d_nu = torch.ones(len(mats), dtype=torch.int32, device="cuda")
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    try:
+        ctx.eigvals_hessenberg_dev(cx, d_H.data_ptr(), d_dims.data_ptr(), d_moff.data_ptr(), d_eoff.data_ptr(), len(mats), int(dims.max()),
+                                   d_eig.data_ptr(), d_nu.data_ptr(), want_stats=True)
+        assert ctx.last_stats["launches"] == 1 and ctx.last_stats["sweeps"] > 0
+        torch.cuda.synchronize()
+    finally:
+        ctx.set_stream(None)
+    got = d_eig.cpu().numpy()[: 2 * int(eoff[-1])].view(np.complex128)
+    assert int(d_nu.sum().item()) == 0
+    for p, w in enumerate(want):
+        assert np.array_equal(got[eoff[p]:eoff[p + 1]], w)
