@@ -749,6 +749,13 @@ int amrvw_debug_counters(amrvw_ctx* ctx, int64_t* out48) {
         CUDA_TRY(ctx, cudaMemcpyAsync(out48, (const int64_t*)ctx->prof.ptr + 16, 48 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     }
+    if (ctx->counters.ptr) {      // [47]: polynomials that changed units in the last unit-queue call (compaction of half-empty units, rounds.cuh)
+        unsigned adopted = 0;
+        CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+        CUDA_TRY(ctx, cudaMemcpyAsync(&adopted, (const unsigned*)ctx->counters.ptr + CNT_ADOPTED, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        out48[47] = (int64_t)adopted;
+    }
     return AMRVW_OK;
 }
 

@@ -48,7 +48,9 @@ typedef SmallWinRec SmallWin;
 // counters[1]: small windows queued
 // counters[2..]: reserved
 // counters[2]: sticky abort flag of the unit queue (a warp waited ~10 s for work: see queue_pop)
-enum { CNT_ACTIVE = 0, CNT_SMALL = 1, CNT_ABORT = 2, CNT_WORDS = 8 };
+// counters[3]: compaction of the real unit kernel: polynomial (+1) waiting for a unit with a free lane group, 0 = none
+// counters[4]: polynomials adopted so far (diagnostic)
+enum { CNT_ACTIVE = 0, CNT_SMALL = 1, CNT_ABORT = 2, CNT_ORPHAN = 3, CNT_ADOPTED = 4, CNT_WORDS = 8 };
 
 // ---------------------------------------------------------------- set-up
 __global__ void __launch_bounds__(64) rounds_setup_kernel(Problem<double> pr) {
@@ -186,6 +188,8 @@ struct UnitPark {           // mutable per-unit state between visits; accessed w
     int t;                  // next lock-step of the pending fat step; < 0: phase A is due
     int sp[8];              // deflation-stack sizes of the unit's polynomials
     int nturn[8];           // turnovers so far in this fat step
+    int poly[8];            // the polynomials of the unit's lane groups, -1 = none (unit_kernel: a group whose polynomial has finished
+                            // adopts another unit's leftover polynomial, see the compaction at the top of phase A)
     int pad[3];
 };
 
@@ -223,7 +227,11 @@ __global__ void unit_enqueue_kernel(Problem<S> pr, RoundQueue* q, int* slots, un
     if (!any) return;
     UnitPark up;
     up.t = -1;
-    for (int g = 0; g < 8; ++g) { up.sp[g] = 0; up.nturn[g] = 0; }
+    for (int g = 0; g < 8; ++g) { up.sp[g] = 0; up.nturn[g] = 0; up.poly[g] = -1; }
+    for (int g = 0; g < G; ++g) {
+        const long long p = unit_poly(pr, u * G + g);
+        if (p < pr.nbatch && pr.rec[p].iterating) up.poly[g] = (int)p;
+    }
     up.pad[0] = up.pad[1] = up.pad[2] = 0;
     park[u] = up;
     __threadfence();
@@ -312,7 +320,7 @@ AMRVW_NI void unit_shifts(const Problem<double>& pr, const PipeParams pp, const 
 #endif
 template <int L, int MH>
 __global__ void __launch_bounds__(32, AMRVW_PIPE_MINBLOCKS) unit_kernel(Problem<double> pr, PipeParams pp, RoundQueue* q, int* slots, unsigned mask, UnitPark* park, StepState* parked,
-                                                                        int seg_steps) {
+                                                                        int seg_steps, int compact) {
     constexpr int G = 32 / L;
     constexpr int NT = 32;
     __shared__ __align__(16) double2 smem_snap[12 * NT + G * 3 * AMRVW_RING];
@@ -338,13 +346,66 @@ __global__ void __launch_bounds__(32, AMRVW_PIPE_MINBLOCKS) unit_kernel(Problem<
         const long long pc_u0 = clock64();
         pc_pop += pc_u0 - pc_p0;
         UnitPark* const up = park + u;
-        const long long p = unit_poly(pr, (long long)u * G + grp);
+        long long p = pr.nbatch;      // the polynomial of this lane group (nbatch = none)
+        {
+            const int mapped = __ldcg(&up->poly[grp]);
+            if (mapped >= 0) p = mapped;
+        }
         int t0 = __ldcg(&up->t);
 
         // ---------------- phase A when due
         if (t0 < 0) {
+            if (G == 2 && compact) {
+                // Compaction (two polynomials per warp): a lane group whose polynomial has finished would idle until its
+                // partner is done too.  One polynomial may wait in a device-wide slot: a unit with a free group takes it;
+                // a half-empty unit that finds the slot empty leaves its own polynomial there and retires, so two half-empty
+                // units become one full one.  `remaining` counts live units, never 0 while the slot is taken: a donor that turns
+                // out to be the last unit takes its polynomial back, a retiring unit looks into the slot once more.
+                // A polynomial's own sequence of phase A / fat steps does not depend on the unit that hosts it.
+                unsigned* const orphan = pr.counters + CNT_ORPHAN;
+                const unsigned heldm = __ballot_sync(0xffffffffu, lane == 0 && p < pr.nbatch);
+                const int nheld = __popc(heldm);
+                if (nheld < 2) {
+                    const int mine = nheld == 1 ? (int)__shfl_sync(0xffffffffu, (int)p, (heldm & 1u) ? 0 : L) : -1;
+                    int act = 0, x = 0;      // act 1: adopt polynomial x - 1, 2: this unit is gone
+                    if (lane32 == 0) {
+                        x = (int)atomicExch(orphan, 0u);
+                        if (x > 0) act = 1;
+                        else if (nheld == 1) {
+                            // nothing waits: offer ours -- while enough units are alive that a free group turns up soon
+                            if (*reinterpret_cast<volatile unsigned*>(&q->remaining) >= 32u && atomicCAS(orphan, 0u, (unsigned)mine + 1u) == 0u) {
+                                __threadfence();
+                                const unsigned old = atomicSub(&q->remaining, 1u);
+                                act = 2;
+                                if (old <= 1u && atomicCAS(orphan, (unsigned)mine + 1u, 0u) == (unsigned)mine + 1u) { atomicAdd(&q->remaining, 1u); act = 0; }
+                            }
+                        } else {
+                            // nothing here, nothing waiting: retire, then look once more (a donor may have counted on this unit)
+                            atomicSub(&q->remaining, 1u);
+                            __threadfence();
+                            x = (int)atomicExch(orphan, 0u);
+                            if (x > 0) { atomicAdd(&q->remaining, 1u); act = 1; } else act = 2;
+                        }
+                        if (act == 1) {
+                            __stcg(&up->poly[(heldm & 1u) ? 1 : 0], x - 1);
+                            atomicAdd(pr.counters + CNT_ADOPTED, 1u);
+                        } else if (act == 2) {
+                            __stcg(&up->poly[0], -1); __stcg(&up->poly[1], -1);
+                        }
+                    }
+                    act = __shfl_sync(0xffffffffu, act, 0); x = __shfl_sync(0xffffffffu, x, 0);
+                    if (act == 2) continue;
+                    if (act == 1) {
+                        __threadfence();
+                        if (grp == ((heldm & 1u) ? 1 : 0)) p = x - 1;
+                    }
+                }
+            }
             int m0 = 0;
-            if (lane == 0 && p < pr.nbatch) m0 = unit_driver(pr, pp, L, p);
+            if (lane == 0 && p < pr.nbatch) {
+                m0 = unit_driver(pr, pp, L, p);
+                if (m0 == 0) __stcg(&up->poly[grp], -1);      // finished: the group is free from the next phase A on
+            }
             __syncwarp();
             pc_drv += clock64() - pc_u0;
             {   // the groups compute their shifts side by side
@@ -355,7 +416,17 @@ __global__ void __launch_bounds__(32, AMRVW_PIPE_MINBLOCKS) unit_kernel(Problem<
             }
             pc_a += clock64() - pc_u0;
             if (!__any_sync(0xffffffffu, m0 != 0)) {   // every polynomial of the unit is finished
-                if (lane32 == 0) atomicSub(&q->remaining, 1u);
+                if (G == 2 && compact) {
+                    // come back once more as an empty unit: the compaction above retires it or gives it a waiting polynomial
+                    if (lane32 == 0) {
+                        __stcg(&up->t, -1);
+                        __threadfence();
+                        const unsigned k = atomicAdd(&q->tail, 1u);
+                        atomicExch(slots + (k & mask), u);
+                    }
+                } else {
+                    if (lane32 == 0) atomicSub(&q->remaining, 1u);
+                }
                 continue;
             }
             if (lane == 0) {
@@ -679,7 +750,11 @@ static cudaError_t launch_units(const Problem<double>& pr, const PipeParams& pp,
     if (per_sm < 1) per_sm = 1;
     const long long resident = (long long)sm_count * per_sm;     // every warp of the grid must be resident: they wait on each other
     const int blocks = (int)(nunits < resident ? nunits : resident);
-    unit_kernel<L, MH><<<blocks, 32, 0, st>>>(pr, pp, qb.q, qb.slots, qb.mask, qb.park, qb.parked, seg_steps);
+    // compaction of half-empty units frees warps for units that wait in the queue; when every unit is resident anyway it only
+    // costs (config 2, 1500 units on 1628 resident warps: 509.8 -> 513.1 ms), so it is on when units outnumber the resident warps
+    int compact = (G == 2 && nunits > resident) ? 1 : 0;
+    if (const char* ev = std::getenv("AMRVW_COMPACT")) compact = (G == 2 && std::atoi(ev) != 0) ? 1 : 0;      // development: force on / off
+    unit_kernel<L, MH><<<blocks, 32, 0, st>>>(pr, pp, qb.q, qb.slots, qb.mask, qb.park, qb.parked, seg_steps, compact);
     return cudaGetLastError();
 }
 template <int L>

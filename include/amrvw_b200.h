@@ -213,7 +213,8 @@ int amrvw_selftest_robust(amrvw_ctx* ctx, int64_t n, double* out4);
 int amrvw_last_profile(amrvw_ctx* ctx, int64_t* out16);
 
 /* Development counters of the last call made with stats (48 slots whose meaning belongs to the kernel under study;
- * see the kernel source).  No reference counterpart. */
+ * see the kernel source; [47] = polynomials that moved to another unit in the last unit-queue call: the compaction of
+ * half-empty units, on when units outnumber the resident warps).  No reference counterpart. */
 int amrvw_debug_counters(amrvw_ctx* ctx, int64_t* out48);
 
 int amrvw_version(void);

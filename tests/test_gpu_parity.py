@@ -936,3 +936,33 @@ def test_gpu_ragged_degree_classes(A, ctx, oracle):
     pg = A.roots([v for v, _ in pairs], [w for _, w in pairs], ctx=ctx)
     pw = [oracle.roots(v, ws=w)[0] for v, w in pairs]
     check_parity(prow, pg, pw, C=C_PENCIL)
+
+
+def test_gpu_unit_compaction_moves_polynomials_and_keeps_roots(A, oracle):
+    """North star: "lanes are compacted as polynomials converge".  With two polynomials per warp and more units than resident
+    warps, a unit whose first polynomial has finished takes over another half-empty unit's polynomial (rounds.cuh: phase A).  A
+    polynomial's own sequence of fat steps does not depend on the unit that hosts it: the roots are bit-identical with the
+    compaction forced off, and amrvw_debug_counters[47] counts the polynomials that moved."""
+    rows = batch(oracle, 77, 4000, 96)
+    flat = np.concatenate(rows); off = np.arange(len(rows) + 1, dtype=np.int64) * 97
+    res = {}
+    for flag in ("1", "0"):
+        os.environ["AMRVW_COMPACT"] = flag
+        try:
+            c = A.Context(seed=0, lanes_per_poly=16, schedule=A.SCHEDULE_PIPELINED)
+            try:
+                out, roff, nroots, nunc = c.roots_csr(flat, off, want_stats=True)
+                moved = c.debug_counters()[47]
+                res[flag] = (out.copy(), nroots.copy(), int(nunc.sum()), int(moved), dict(c.last_stats))
+            finally:
+                c.close()
+        finally:
+            del os.environ["AMRVW_COMPACT"]
+    on, offr = res["1"], res["0"]
+    assert on[2] == 0 and offr[2] == 0
+    assert on[3] > 100 and offr[3] == 0, (on[3], offr[3])
+    assert np.array_equal(on[1], offr[1]) and np.array_equal(on[0].view(np.float64), offr[0].view(np.float64))
+    assert on[4]["turnovers"] == offr[4]["turnovers"] and on[4]["fat_steps"] == offr[4]["fat_steps"]
+    got = [on[0][roff[p]: roff[p] + on[1][p]] for p in range(0, 4000, 400)]
+    want = [oracle.roots(rows[p])[0] for p in range(0, 4000, 400)]
+    check_parity([rows[p] for p in range(0, 4000, 400)], got, want)
