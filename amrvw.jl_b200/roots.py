@@ -303,13 +303,13 @@ def qr_factorization(H, unitary=False):
 def eigvals(state, ctx=None):
     """eigvals(state) (AMRVW_algorithm.jl:207-216) of one QRFactorization or of a sequence of them (one GPU call; the
     sequence must share `unitary`).  Complex128 eigenvalues sorted by (real, imag)."""
-    ctx = ctx or default_context()
     batch = isinstance(state, (list, tuple))
     seq = list(state) if batch else [state]
     if not all(isinstance(s, QRFactorization) for s in seq):
         raise TypeError("eigvals needs the result of qr_factorization")
     if len({s.unitary for s in seq}) > 1:
         raise ValueError("one call roots factorizations of one kind (unitary or not)")
+    ctx = ctx or default_context()
     res, _ = ctx.eigvals_hessenberg([s.H for s in seq], unitary=seq[0].unitary if seq else False)
     return res if batch else res[0]
 

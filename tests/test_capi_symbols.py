@@ -122,3 +122,25 @@ def test_partition_batch_is_contiguous_and_balanced_by_squared_length(A):
     off = np.array([0, 5, 3], dtype=np.int64)
     cuts = np.zeros(3, dtype=np.int64)
     assert lib.amrvw_partition_batch(off.ctypes.data, 2, 2, cuts.ctypes.data) == -1     # decreasing offsets
+
+
+def test_hessenberg_host_packing_and_argument_errors(A):
+    """Host side of the Hessenberg entries (no GPU): column-major packing as Julia stores matrices, dims, and the argument
+    checks that need no device."""
+    from importlib import import_module
+    roots_mod = import_module("amrvw_jl_b200.roots")
+    M1 = np.arange(9.0).reshape(3, 3)
+    M2 = np.array([[1.0, 2.0], [3.0, 4.0]])
+    flat, dims = roots_mod.pack_matrices([M1, np.zeros((0, 0)), M2])
+    assert dims.tolist() == [3, 0, 2] and flat.dtype == np.float64
+    assert np.array_equal(flat[:9], M1.reshape(-1, order="F")) and np.array_equal(flat[9:], [1.0, 3.0, 2.0, 4.0])
+    cflat, cdims = roots_mod.pack_matrices([M2, 1j * M2])
+    assert cflat.dtype == np.complex128 and cdims.tolist() == [2, 2]
+    with pytest.raises(ValueError):
+        roots_mod.pack_matrices([np.zeros((2, 3))])
+    with pytest.raises(ValueError):
+        A.qr_factorization(np.zeros(4))
+    f = A.qr_factorization(M2, unitary=True)
+    assert f.unitary and f.H.shape == (2, 2)
+    with pytest.raises(TypeError):
+        A.eigvals([M2])                 # eigvals takes factorizations, as in the reference
