@@ -3,15 +3,18 @@
 // (RFactorizationUpperTriangular, rfactorization.jl:259-357) or, for a unitary H, as a unitary diagonal
 // (RFactorizationUnitaryDiagonal, rfactorization.jl:230-248).
 //
-// One warp per matrix.  The scalar part of the algorithm (shifts, turnovers in Q, deflation) is executed by all
-// 32 lanes on the same values; the O(n) part -- passing a rotator through the dense R is a column rotation of
-// columns i, i+1 and a row rotation of rows i, i+1 -- is split over the lanes.  Only the diagonal block of the
+// One warp per matrix (hess_kernel), or one thread per matrix for large batches of small matrices (hess_thread_kernel):
+// the same code, the number of cooperating lanes CW = 32 or 1 is a template parameter.  The scalar part of the
+// algorithm (shifts, turnovers in Q, deflation) is executed by all cooperating lanes on the same values; the O(n)
+// part -- passing a rotator through the dense R is a column rotation of columns i, i+1 and a row rotation of rows
+// i, i+1 -- is split over the lanes.  Only the diagonal block of the
 // active window is kept up to date: rows above it and columns right of it never feed an eigenvalue (a row
 // rotation mixes rows i, i+1 only, a column rotation columns i, i+1 only), so each entry that is read sees exactly
 // the arithmetic of the reference and the eigenvalues do not change.  R lives in shared memory when the matrix
 // fits (leading dimension odd: rows and columns are both conflict free), else in a global workspace (L2).
 // Q, D_Q and the unitary diagonal are shared by the warp: every update is "all lanes read, __syncwarp, lane 0 writes,
-// __syncwarp" (hput / HWRITE below), so no lane can read a value another lane has already replaced.
+// __syncwarp" (HWRITE below; both barriers compile away for CW = 1), so no lane can read a value another lane has
+// already replaced.
 #pragma once
 #include "solver.cuh"
 
