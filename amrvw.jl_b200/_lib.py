@@ -36,6 +36,7 @@ _SIGS = {
     "amrvw_create_multi": (ctypes.c_int, [ctypes.POINTER(_P), ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_uint64]),
     "amrvw_device_count": (ctypes.c_int, [_P]),
     "amrvw_partition_batch": (ctypes.c_int, [_P, _I64, ctypes.c_int, _P]),
+    "amrvw_partition_hessenberg": (ctypes.c_int, [_P, _I64, ctypes.c_int, _P]),
     "amrvw_destroy": (ctypes.c_int, [_P]),
     "amrvw_last_error": (ctypes.c_char_p, [_P]),
     "amrvw_default_options": (None, [ctypes.POINTER(Options)]),

@@ -835,6 +835,22 @@ int amrvw_measure_fp64_peak(amrvw_ctx* ctx, double* tflops) {
 template <class S>
 static int run_hessenberg_single(amrvw_ctx* ctx, const S* H, const int32_t* dims, int64_t nbatch, int unitary, double* eig, int32_t* nunconv, amrvw_stats* stats);
 
+// contiguous split of a batch of matrices over ndev devices, balanced by the sum of n^3; cut[d] .. cut[d+1]-1 are device d's
+// matrices, moff / eoff the element and eigenvalue offsets of its first one
+static void partition_hessenberg(const int32_t* dims, int64_t nbatch, int ndev, std::vector<int64_t>& cut, std::vector<int64_t>& moff, std::vector<int64_t>& eoff) {
+    double work = 0.0;
+    for (int64_t p = 0; p < nbatch; ++p) { const double n = dims[p]; work += n * n * n; }
+    cut.assign((size_t)ndev + 1, nbatch); moff.assign((size_t)ndev + 1, 0); eoff.assign((size_t)ndev + 1, 0);
+    cut[0] = 0;
+    double acc = 0.0; long long mo = 0, eo = 0; int d = 1;
+    for (int64_t p = 0; p < nbatch; ++p) {
+        while (d < ndev && acc >= work * d / ndev) { cut[(size_t)d] = p; moff[(size_t)d] = mo; eoff[(size_t)d] = eo; ++d; }
+        const long long n = dims[p];
+        acc += (double)n * n * n; mo += n * n; eo += n;
+    }
+    while (d <= ndev) { cut[(size_t)d] = nbatch; moff[(size_t)d] = mo; eoff[(size_t)d] = eo; ++d; }
+}
+
 // Several devices: contiguous split by matrix, balanced by the sum of n^3 (the work of the dense-R chase), one host thread per
 // device, results copied straight into the caller's buffers -- the same scheme as run_host.
 template <class S>
@@ -849,19 +865,8 @@ static int run_hessenberg(amrvw_ctx* ctx, const S* H, const int32_t* dims, int64
         if (dims[p] < 0 || dims[p] > 32768) return fail(ctx, AMRVW_ERR_ARGUMENT, "matrix dimension out of range (0..32768)");
     if (ctx->subs.empty()) return run_hessenberg_single<S>(ctx, H, dims, nbatch, unitary, eig, nunconv, stats);
     const int ndev = (int)ctx->subs.size();
-    double work = 0.0;
-    for (int64_t p = 0; p < nbatch; ++p) { const double n = dims[p]; work += n * n * n; }
-    std::vector<int64_t> cut((size_t)ndev + 1, nbatch), moff((size_t)ndev + 1, 0), eoff((size_t)ndev + 1, 0);
-    cut[0] = 0;
-    {
-        double acc = 0.0; long long mo = 0, eo = 0; int d = 1;
-        for (int64_t p = 0; p < nbatch; ++p) {
-            while (d < ndev && acc >= work * d / ndev) { cut[(size_t)d] = p; moff[(size_t)d] = mo; eoff[(size_t)d] = eo; ++d; }
-            const long long n = dims[p];
-            acc += (double)n * n * n; mo += n * n; eo += n;
-        }
-        while (d <= ndev) { cut[(size_t)d] = nbatch; moff[(size_t)d] = mo; eoff[(size_t)d] = eo; ++d; }
-    }
+    std::vector<int64_t> cut, moff, eoff;
+    partition_hessenberg(dims, nbatch, ndev, cut, moff, eoff);
     std::vector<int> rcs((size_t)ndev, AMRVW_OK);
     std::vector<amrvw_stats> sts((size_t)ndev);
     std::vector<std::thread> workers;
@@ -1012,6 +1017,14 @@ int amrvw_eigvals_hessenberg_f64(amrvw_ctx* ctx, const double* H, const int32_t*
 }
 int amrvw_eigvals_hessenberg_c64(amrvw_ctx* ctx, const double* H, const int32_t* dims, int64_t nbatch, int unitary, double* eig, int32_t* nunconv, amrvw_stats* stats) {
     return run_hessenberg<cplx>(ctx, (const cplx*)H, dims, nbatch, unitary, eig, nunconv, stats);
+}
+int amrvw_partition_hessenberg(const int32_t* dims, int64_t nbatch, int ndev, int64_t* cuts) {
+    if (!dims || !cuts || nbatch < 0 || ndev < 1) return AMRVW_ERR_ARGUMENT;
+    for (int64_t p = 0; p < nbatch; ++p) if (dims[p] < 0 || dims[p] > 32768) return AMRVW_ERR_ARGUMENT;
+    std::vector<int64_t> cut, moff, eoff;
+    partition_hessenberg(dims, nbatch, ndev, cut, moff, eoff);
+    for (int d = 0; d <= ndev; ++d) cuts[d] = cut[(size_t)d];
+    return AMRVW_OK;
 }
 static int hess_dev_args(amrvw_ctx*& ctx, const void* H, const void* dims, const void* moff, const void* eoff, int64_t nbatch, int32_t max_dim, const void* eig, const void* nunconv) {
     if (!ctx) return AMRVW_ERR_ARGUMENT;

@@ -165,6 +165,9 @@ int amrvw_eigvals_hessenberg_f64(amrvw_ctx* ctx, const double* H, const int32_t*
                                  double* eig_reim, int32_t* n_unconverged, amrvw_stats* stats);
 int amrvw_eigvals_hessenberg_c64(amrvw_ctx* ctx, const double* H_reim, const int32_t* dims, int64_t nbatch, int unitary,
                                  double* eig_reim, int32_t* n_unconverged, amrvw_stats* stats);
+/* The split a multi-device context applies to a batch of matrices (pure host code, needs no device): device d takes matrices
+ * cuts[d] .. cuts[d+1]-1; cuts has ndev+1 entries. */
+int amrvw_partition_hessenberg(const int32_t* dims, int64_t nbatch, int ndev, int64_t* cuts);
 /* The same with DEVICE pointers, asynchronous on the context's stream (stats != NULL synchronizes); single-device contexts.
  * d_moff[p] / d_eoff[p]: element offset of matrix p in d_H and complex slot offset of its eigenvalues (nbatch + 1 entries
  * each, the running sums of dims^2 and dims); max_dim: the largest dims[p].  A slot of an eigenvalue the iteration cap

@@ -144,3 +144,22 @@ def test_hessenberg_host_packing_and_argument_errors(A):
     assert f.unitary and f.H.shape == (2, 2)
     with pytest.raises(TypeError):
         A.eigvals([M2])                 # eigvals takes factorizations, as in the reference
+
+
+def test_partition_hessenberg_is_contiguous_and_balanced_by_cubed_dimension(A):
+    """The split amrvw_eigvals_hessenberg_* apply on a multi-device context (host code): contiguous, every matrix once, shares of
+    sum(n^3) within one matrix of equal."""
+    lib = A.load()
+    rng = np.random.default_rng(8)
+    dims = rng.integers(0, 200, 500).astype(np.int32)
+    w = dims.astype(np.float64) ** 3
+    for ndev in (1, 2, 3, 8):
+        cuts = np.zeros(ndev + 1, dtype=np.int64)
+        assert lib.amrvw_partition_hessenberg(dims.ctypes.data, len(dims), ndev, cuts.ctypes.data) == 0
+        assert cuts[0] == 0 and cuts[-1] == len(dims) and np.all(np.diff(cuts) >= 0)
+        shares = np.array([w[cuts[d]:cuts[d + 1]].sum() for d in range(ndev)])
+        assert np.all(np.abs(shares - w.sum() / ndev) <= w.max() + 1e-9)
+    cuts = np.zeros(3, dtype=np.int64)
+    bad = np.array([3, -1], dtype=np.int32)
+    assert lib.amrvw_partition_hessenberg(bad.ctypes.data, 2, 2, cuts.ctypes.data) == -1
+    assert lib.amrvw_partition_hessenberg(dims.ctypes.data, 0, 2, cuts.ctypes.data) == 0 and cuts.tolist() == [0, 0, 0]
